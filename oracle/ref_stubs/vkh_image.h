@@ -1,0 +1,2 @@
+/* TEST INFRASTRUCTURE ONLY — forwards to the stub vkh.h */
+#include "vkh.h"
