@@ -1,0 +1,113 @@
+/*
+ * vkvg_b200.h — extension entry points of libvkvg_b200.so beyond the vkvg.h drop-in surface.
+ *
+ * Plain C ABI (pointers and sizes only).  Three groups:
+ *   1. stage introspection for parity tests: run the CUDA flatten / stroke / raster stages on the context's
+ *      current path or on raw edges and copy the intermediate results to host buffers,
+ *   2. measurement: launch counters, device-timed stage durations, a resident-batch replay so that the bench
+ *      can time the pipeline with its inputs already in HBM,
+ *   3. a packed command stream (`vkvg_b200_replay`) that drives the ordinary vkvg_* calls from arrays, so a
+ *      host program in any language can submit a whole scene with one FFI call instead of one per point
+ *      (the reference's equivalent is its optional recording facility, src/recording/vkvg_record_internal.h:31-95).
+ */
+#ifndef VKVG_B200_H
+#define VKVG_B200_H
+#include "vkvg.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- 1. stage introspection ------------------------------------------------------------------------- */
+
+/* Flatten the context's current path on the GPU (replaces _recursive_bezier + arc loops,
+ * src/vkvg_context_internal.c:1313-1461, src/vkvg_context.c:394-503).  Writes up to cap_points (x,y) pairs,
+ * the per-point "curved segment" flag, and per sub-path first/count.  Returns the number of points (which may
+ * exceed cap_points; nothing past the capacity is written).  The path is preserved. */
+vkvg_public uint32_t vkvg_b200_flatten_path(VkvgContext ctx, float *xy, uint8_t *curved, uint32_t cap_points, uint32_t *sp_first,
+                                            uint32_t *sp_count, uint32_t cap_subpaths, uint32_t *n_subpaths);
+
+/* Stroke the current path with the current line state on the GPU and return the triangle list in the
+ * reference's vertex order (replaces _stroke_preserve / _build_vb_step / _draw_stoke_cap / _draw_dashed_segment,
+ * src/vkvg_context.c:822-948, src/vkvg_context_internal.c:924-1264).  Indices are relative to the first
+ * vertex of the call.  Nothing is drawn; the path is preserved. */
+vkvg_public void vkvg_b200_stroke_geometry(VkvgContext ctx, float *xy, uint32_t cap_verts, uint32_t *n_verts, uint32_t *indices,
+                                           uint32_t cap_indices, uint32_t *n_indices);
+
+/* Device-space edges (24.8 fixed point x0,y0,x1,y1) that filling or stroking the current path would hand to
+ * the rasteriser.  kind: 0 = fill, 1 = stroke.  Returns the edge count. */
+vkvg_public uint64_t vkvg_b200_path_edges(VkvgContext ctx, int kind, int32_t *edges_xyxy, uint64_t cap_edges);
+
+/* Flush the context; additionally copy the per-sample integer winding computed by the tile rasteriser for the
+ * LAST draw of the flushed batch into winding (height*width*samples int32, 0 where that draw has no tile). */
+vkvg_public void vkvg_b200_flush_capture_winding(VkvgContext ctx, int32_t *winding);
+
+/* Run binning + fine pass on raw directed edges as one draw and return the per-sample winding
+ * (height*width*samples).  This is the integer core that must match oracle ovk_winding_brute bit for bit. */
+vkvg_public vkvg_status_t vkvg_b200_winding(VkvgDevice dev, const int32_t *edges_xyxy, uint64_t n_edges, uint32_t width, uint32_t height,
+                                            int32_t *winding);
+
+/* premultiplied RGBA8 pixels exactly as stored (vkvg_surface_write_to_memory un-premultiplies) */
+vkvg_public vkvg_status_t vkvg_b200_surface_read_premultiplied(VkvgSurface surf, unsigned char *rgba);
+
+/* ---- 2. measurement ------------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t n_elems, n_points, n_fill_edges, n_stroke_items, n_verts, n_inds, n_edges, n_path_tiles, n_nonempty, n_tile_edges;
+    float    ms_total, ms_fine;
+    uint64_t h2d_bytes;
+} vkvg_b200_stats_t;
+
+vkvg_public uint64_t vkvg_b200_launch_count(void);                          /* kernels launched by this library so far */
+vkvg_public void     vkvg_b200_set_profiling(VkvgDevice dev, int on);       /* on: every flush synchronises and records stats */
+vkvg_public void     vkvg_b200_last_stats(VkvgDevice dev, vkvg_b200_stats_t *out);
+vkvg_public void     vkvg_b200_device_synchronize(VkvgDevice dev);
+vkvg_public int      vkvg_b200_device_ordinal(VkvgDevice dev);
+vkvg_public const void *vkvg_b200_surface_device_pointer(VkvgSurface surf); /* CUDA device pointer of the RGBA8 image */
+
+/* Resident replay: `vkvg_b200_flush_keep` flushes like vkvg_flush but keeps the uploaded batch on the device;
+ * `vkvg_b200_replay_resident` re-runs the whole pipeline on it (no host->device traffic) onto surf. */
+vkvg_public void vkvg_b200_flush_keep(VkvgContext ctx);
+vkvg_public void vkvg_b200_replay_resident(VkvgDevice dev, VkvgSurface surf, int clear_first);
+
+/* ---- 3. packed command stream -------------------------------------------------------------------------- */
+enum {
+    VKVG_B200_OP_MOVE_TO = 1,   /* x y */
+    VKVG_B200_OP_LINE_TO,       /* x y */
+    VKVG_B200_OP_CURVE_TO,      /* x1 y1 x2 y2 x3 y3 */
+    VKVG_B200_OP_CLOSE_PATH,
+    VKVG_B200_OP_NEW_PATH,
+    VKVG_B200_OP_ARC,           /* xc yc r a1 a2 */
+    VKVG_B200_OP_ARC_NEGATIVE,  /* xc yc r a1 a2 */
+    VKVG_B200_OP_RECTANGLE,     /* x y w h */
+    VKVG_B200_OP_FILL,
+    VKVG_B200_OP_FILL_PRESERVE,
+    VKVG_B200_OP_STROKE,
+    VKVG_B200_OP_STROKE_PRESERVE,
+    VKVG_B200_OP_PAINT,
+    VKVG_B200_OP_SET_SOURCE_RGBA,   /* r g b a */
+    VKVG_B200_OP_SET_LINE_WIDTH,    /* w */
+    VKVG_B200_OP_SET_LINE_CAP,      /* cap */
+    VKVG_B200_OP_SET_LINE_JOIN,     /* join */
+    VKVG_B200_OP_SET_MITER_LIMIT,   /* limit */
+    VKVG_B200_OP_SET_FILL_RULE,     /* rule */
+    VKVG_B200_OP_SET_DASH,          /* n offset d0 .. dn-1 */
+    VKVG_B200_OP_SET_SOURCE_LINEAR, /* x0 y0 x1 y1 nstops (offset r g b a)* */
+    VKVG_B200_OP_SET_SOURCE_RADIAL, /* cx0 cy0 r0 cx1 cy1 r1 nstops (offset r g b a)* */
+    VKVG_B200_OP_TRANSLATE,         /* dx dy */
+    VKVG_B200_OP_SCALE,             /* sx sy */
+    VKVG_B200_OP_ROTATE,            /* radians */
+    VKVG_B200_OP_IDENTITY_MATRIX,
+    VKVG_B200_OP_SAVE,
+    VKVG_B200_OP_RESTORE,
+    VKVG_B200_OP_CLEAR,
+    VKVG_B200_OP_SET_OPACITY,       /* opacity */
+    VKVG_B200_OP_POLYLINE,          /* n x0 y0 .. : move_to the first point, line_to the others; n is a uint32 stored in the float slot bit for bit */
+    VKVG_B200_OP_FLUSH,
+};
+/* ops[i] selects the call; its float arguments are consumed from args in order.  Equivalent to issuing the
+ * corresponding vkvg_* calls one by one (it does exactly that).  Returns the context status. */
+vkvg_public vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *args, uint64_t n_args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,386 @@
+"""vkvg_b200 — B200-native implementation of vkvg's path-rendering hot path behind the vkvg.h C API.
+
+The product is the shared library ``vkvg_b200/libvkvg_b200.so`` (hand-written sm_100a CUDA + a C host that
+exports the reference's ``vkvg_*`` entry points, see ``include/vkvg.h``).  This module is only a thin ctypes
+binding of that C ABI for tests and benchmarks written in Python; it contains no rendering logic and has no
+CPU fallback: if the library or a CUDA device is missing, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvkvg_b200.so")
+_f, _u, _i, _p = C.c_float, C.c_uint32, C.c_int, C.c_void_p
+
+# vkvg.h enum values
+CAP_BUTT, CAP_ROUND, CAP_SQUARE = 0, 1, 2
+JOIN_MITER, JOIN_ROUND, JOIN_BEVEL = 0, 1, 2
+FILL_EVEN_ODD, FILL_NON_ZERO = 0, 1
+STATUS_SUCCESS = 0
+
+# vkvg_b200.h op codes for the packed command stream
+OPS = {name: i + 1 for i, name in enumerate([
+    "MOVE_TO", "LINE_TO", "CURVE_TO", "CLOSE_PATH", "NEW_PATH", "ARC", "ARC_NEGATIVE", "RECTANGLE", "FILL", "FILL_PRESERVE",
+    "STROKE", "STROKE_PRESERVE", "PAINT", "SET_SOURCE_RGBA", "SET_LINE_WIDTH", "SET_LINE_CAP", "SET_LINE_JOIN",
+    "SET_MITER_LIMIT", "SET_FILL_RULE", "SET_DASH", "SET_SOURCE_LINEAR", "SET_SOURCE_RADIAL", "TRANSLATE", "SCALE", "ROTATE",
+    "IDENTITY_MATRIX", "SAVE", "RESTORE", "CLEAR", "SET_OPACITY", "POLYLINE", "FLUSH"])}
+
+
+class DeviceCreateInfo(C.Structure):
+    """vkvg_device_create_info_t (include/vkvg.h)."""
+    _fields_ = [("samples", _u), ("deferredResolve", C.c_bool), ("inst", _p), ("phy", _p), ("vkdev", _p), ("qFamIdx", _u),
+                ("qIndex", _u), ("threadAware", C.c_bool)]
+
+
+class Stats(C.Structure):
+    """vkvg_b200_stats_t (include/vkvg_b200.h)."""
+    _fields_ = [(n, C.c_uint64) for n in ("n_elems", "n_points", "n_fill_edges", "n_stroke_items", "n_verts", "n_inds", "n_edges",
+                                          "n_path_tiles", "n_nonempty", "n_tile_edges")] + [("ms_total", _f), ("ms_fine", _f),
+                                                                                           ("h2d_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "vkvg_device_create": (_p, [_p]), "vkvg_device_destroy": (None, [_p]), "vkvg_device_status": (_i, [_p]),
+    "vkvg_device_reference": (_p, [_p]), "vkvg_device_get_reference_count": (_u, [_p]),
+    "vkvg_surface_create": (_p, [_p, _u, _u]), "vkvg_surface_destroy": (None, [_p]), "vkvg_surface_status": (_i, [_p]),
+    "vkvg_surface_reference": (_p, [_p]), "vkvg_surface_get_reference_count": (_u, [_p]), "vkvg_surface_clear": (None, [_p]),
+    "vkvg_surface_get_width": (_u, [_p]), "vkvg_surface_get_height": (_u, [_p]), "vkvg_surface_get_vk_format": (_i, [_p]),
+    "vkvg_surface_write_to_png": (_i, [_p, C.c_char_p]), "vkvg_surface_write_to_memory": (_i, [_p, _p]),
+    "vkvg_create": (_p, [_p]), "vkvg_destroy": (None, [_p]), "vkvg_status": (_i, [_p]), "vkvg_reference": (_p, [_p]),
+    "vkvg_get_reference_count": (_u, [_p]), "vkvg_flush": (None, [_p]), "vkvg_status_to_string": (C.c_char_p, [_i]),
+    "vkvg_new_path": (None, [_p]), "vkvg_close_path": (None, [_p]), "vkvg_new_sub_path": (None, [_p]),
+    "vkvg_get_current_point": (None, [_p, C.POINTER(_f), C.POINTER(_f)]), "vkvg_has_current_point": (C.c_bool, [_p]),
+    "vkvg_line_to": (None, [_p, _f, _f]), "vkvg_rel_line_to": (None, [_p, _f, _f]), "vkvg_move_to": (None, [_p, _f, _f]),
+    "vkvg_rel_move_to": (None, [_p, _f, _f]), "vkvg_arc": (None, [_p] + [_f] * 5), "vkvg_arc_negative": (None, [_p] + [_f] * 5),
+    "vkvg_curve_to": (None, [_p] + [_f] * 6), "vkvg_rel_curve_to": (None, [_p] + [_f] * 6),
+    "vkvg_quadratic_to": (None, [_p] + [_f] * 4), "vkvg_rel_quadratic_to": (None, [_p] + [_f] * 4),
+    "vkvg_rectangle": (_i, [_p] + [_f] * 4), "vkvg_rounded_rectangle": (_i, [_p] + [_f] * 5), "vkvg_ellipse": (None, [_p] + [_f] * 5),
+    "vkvg_stroke": (None, [_p]), "vkvg_stroke_preserve": (None, [_p]), "vkvg_fill": (None, [_p]), "vkvg_fill_preserve": (None, [_p]),
+    "vkvg_paint": (None, [_p]), "vkvg_clear": (None, [_p]),
+    "vkvg_set_opacity": (None, [_p, _f]), "vkvg_get_opacity": (_f, [_p]), "vkvg_set_source_color": (None, [_p, _u]),
+    "vkvg_set_source_rgba": (None, [_p] + [_f] * 4), "vkvg_set_source_rgb": (None, [_p] + [_f] * 3), "vkvg_set_source": (None, [_p, _p]),
+    "vkvg_set_line_width": (None, [_p, _f]), "vkvg_set_miter_limit": (None, [_p, _f]), "vkvg_get_miter_limit": (_f, [_p]),
+    "vkvg_set_line_cap": (None, [_p, _i]), "vkvg_set_line_join": (None, [_p, _i]), "vkvg_set_operator": (None, [_p, _i]),
+    "vkvg_set_fill_rule": (None, [_p, _i]), "vkvg_set_dash": (None, [_p, C.POINTER(_f), _u, _f]),
+    "vkvg_get_dash": (None, [_p, C.POINTER(_f), C.POINTER(_u), C.POINTER(_f)]),
+    "vkvg_get_line_width": (_f, [_p]), "vkvg_get_line_cap": (_i, [_p]), "vkvg_get_line_join": (_i, [_p]),
+    "vkvg_get_operator": (_i, [_p]), "vkvg_get_fill_rule": (_i, [_p]), "vkvg_get_source": (_p, [_p]), "vkvg_get_target": (_p, [_p]),
+    "vkvg_save": (None, [_p]), "vkvg_restore": (None, [_p]), "vkvg_translate": (None, [_p, _f, _f]), "vkvg_scale": (None, [_p, _f, _f]),
+    "vkvg_rotate": (None, [_p, _f]), "vkvg_transform": (None, [_p, _p]), "vkvg_set_matrix": (None, [_p, _p]),
+    "vkvg_get_matrix": (None, [_p, _p]), "vkvg_identity_matrix": (None, [_p]),
+    "vkvg_matrix_init_identity": (None, [_p]), "vkvg_matrix_init": (None, [_p] + [_f] * 6),
+    "vkvg_matrix_init_translate": (None, [_p, _f, _f]), "vkvg_matrix_init_scale": (None, [_p, _f, _f]),
+    "vkvg_matrix_init_rotate": (None, [_p, _f]), "vkvg_matrix_translate": (None, [_p, _f, _f]), "vkvg_matrix_scale": (None, [_p, _f, _f]),
+    "vkvg_matrix_rotate": (None, [_p, _f]), "vkvg_matrix_multiply": (None, [_p, _p, _p]),
+    "vkvg_matrix_transform_distance": (None, [_p, C.POINTER(_f), C.POINTER(_f)]),
+    "vkvg_matrix_transform_point": (None, [_p, C.POINTER(_f), C.POINTER(_f)]), "vkvg_matrix_invert": (_i, [_p]),
+    "vkvg_matrix_get_scale": (None, [_p, C.POINTER(_f), C.POINTER(_f)]),
+    "vkvg_pattern_status": (_i, [_p]), "vkvg_pattern_reference": (_p, [_p]), "vkvg_pattern_get_reference_count": (_u, [_p]),
+    "vkvg_pattern_create_linear": (_p, [_f] * 4), "vkvg_pattern_create_radial": (_p, [_f] * 6), "vkvg_pattern_destroy": (None, [_p]),
+    "vkvg_pattern_add_color_stop": (_i, [_p] + [_f] * 5), "vkvg_pattern_get_color_stop_count": (_i, [_p, C.POINTER(_u)]),
+    "vkvg_pattern_get_type": (_i, [_p]), "vkvg_pattern_set_matrix": (None, [_p, _p]), "vkvg_pattern_get_matrix": (None, [_p, _p]),
+    "vkvg_pattern_set_extend": (None, [_p, _i]), "vkvg_pattern_get_extend": (_i, [_p]),
+    # vkvg_b200.h
+    "vkvg_b200_flatten_path": (_u, [_p, _p, _p, _u, _p, _p, _u, C.POINTER(_u)]),
+    "vkvg_b200_stroke_geometry": (None, [_p, _p, _u, C.POINTER(_u), _p, _u, C.POINTER(_u)]),
+    "vkvg_b200_path_edges": (C.c_uint64, [_p, _i, _p, C.c_uint64]),
+    "vkvg_b200_flush_capture_winding": (None, [_p, _p]),
+    "vkvg_b200_winding": (_i, [_p, _p, C.c_uint64, _u, _u, _p]),
+    "vkvg_b200_surface_read_premultiplied": (_i, [_p, _p]),
+    "vkvg_b200_launch_count": (C.c_uint64, []), "vkvg_b200_set_profiling": (None, [_p, _i]),
+    "vkvg_b200_last_stats": (None, [_p, C.POINTER(Stats)]), "vkvg_b200_device_synchronize": (None, [_p]),
+    "vkvg_b200_device_ordinal": (_i, [_p]), "vkvg_b200_surface_device_pointer": (_p, [_p]),
+    "vkvg_b200_flush_keep": (None, [_p]), "vkvg_b200_replay_resident": (None, [_p, _p, _i]),
+    "vkvg_b200_replay": (_i, [_p, _p, C.c_uint64, _p, C.c_uint64]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libvkvg_b200.so (building it first if it is missing) and attach prototypes."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError here means include/*.h and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+class VkvgError(RuntimeError):
+    pass
+
+
+class Device:
+    def __init__(self, samples=4):
+        L = lib()
+        info = DeviceCreateInfo(samples=samples)
+        self.h = L.vkvg_device_create(C.byref(info))
+        st = L.vkvg_device_status(self.h)
+        if st != STATUS_SUCCESS:
+            self.h = None
+            raise VkvgError("vkvg_device_create failed: %s (no CUDA device? this library has no CPU path)" %
+                            L.vkvg_status_to_string(st).decode())
+        self.samples = samples
+
+    def close(self):
+        if self.h:
+            lib().vkvg_device_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_profiling(self, on=True):
+        lib().vkvg_b200_set_profiling(self.h, int(on))
+
+    def last_stats(self):
+        s = Stats()
+        lib().vkvg_b200_last_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    def synchronize(self):
+        lib().vkvg_b200_device_synchronize(self.h)
+
+    def winding(self, edges, width, height):
+        """per-sample integer winding of raw 24.8 edges through the tile rasteriser: (H, W, samples) int32."""
+        e = np.ascontiguousarray(edges, np.int32).reshape(-1, 4)
+        out = np.zeros((height, width, self.samples), np.int32)
+        st = lib().vkvg_b200_winding(self.h, e.ctypes.data, len(e), width, height, out.ctypes.data)
+        if st:
+            raise VkvgError("vkvg_b200_winding: status %d" % st)
+        return out
+
+
+class Surface:
+    def __init__(self, dev, width, height):
+        self.dev = dev
+        self.width, self.height = width, height
+        self.h = lib().vkvg_surface_create(dev.h, width, height)
+        st = lib().vkvg_surface_status(self.h)
+        if st:
+            raise VkvgError("vkvg_surface_create: status %d" % st)
+
+    def close(self):
+        if self.h:
+            lib().vkvg_surface_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        lib().vkvg_surface_clear(self.h)
+
+    def pixels(self):
+        """premultiplied RGBA8 exactly as stored, (H, W, 4)."""
+        out = np.zeros((self.height, self.width, 4), np.uint8)
+        st = lib().vkvg_b200_surface_read_premultiplied(self.h, out.ctypes.data)
+        if st:
+            raise VkvgError("surface read: status %d" % st)
+        return out
+
+    def write_to_memory(self, out=None):
+        """vkvg_surface_write_to_memory: un-premultiplied RGBA8."""
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), np.uint8)
+        st = lib().vkvg_surface_write_to_memory(self.h, out.ctypes.data)
+        if st:
+            raise VkvgError("vkvg_surface_write_to_memory: status %d" % st)
+        return out
+
+    def write_to_png(self, path):
+        return lib().vkvg_surface_write_to_png(self.h, path.encode())
+
+
+_CTX_CALLS = ["new_path", "close_path", "new_sub_path", "line_to", "rel_line_to", "move_to", "rel_move_to", "arc", "arc_negative",
+              "curve_to", "rel_curve_to", "quadratic_to", "rel_quadratic_to", "rectangle", "rounded_rectangle", "ellipse", "stroke",
+              "stroke_preserve", "fill", "fill_preserve", "paint", "clear", "set_opacity", "set_source_color", "set_source_rgba",
+              "set_source_rgb", "set_line_width", "set_miter_limit", "set_line_cap", "set_line_join", "set_operator", "set_fill_rule",
+              "save", "restore", "translate", "scale", "rotate", "identity_matrix", "flush"]
+
+
+class Context:
+    """vkvg context; drawing methods have the vkvg_* names without the prefix."""
+
+    def __init__(self, surf):
+        self.surf = surf
+        self.h = lib().vkvg_create(surf.h)
+        st = lib().vkvg_status(self.h)
+        if st:
+            raise VkvgError("vkvg_create: status %d" % st)
+
+    def __getattr__(self, name):
+        if name in _CTX_CALLS:
+            fn = getattr(lib(), "vkvg_" + name)
+            h = self.h
+            return lambda *a: fn(h, *a)
+        raise AttributeError(name)
+
+    def close(self):
+        if self.h:
+            lib().vkvg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def status(self):
+        return lib().vkvg_status(self.h)
+
+    def set_dash(self, dashes, offset=0.0):
+        arr = (_f * max(len(dashes), 1))(*dashes)
+        lib().vkvg_set_dash(self.h, arr, len(dashes), offset)
+
+    def set_matrix(self, m):
+        a = np.asarray(m, np.float32)
+        lib().vkvg_set_matrix(self.h, a.ctypes.data)
+
+    def get_matrix(self):
+        a = np.zeros(6, np.float32)
+        lib().vkvg_get_matrix(self.h, a.ctypes.data)
+        return a
+
+    def get_current_point(self):
+        x, y = _f(), _f()
+        lib().vkvg_get_current_point(self.h, C.byref(x), C.byref(y))
+        return x.value, y.value
+
+    def _grad(self, pat, stops):
+        L = lib()
+        for s in np.asarray(stops, np.float32).reshape(-1, 5):
+            L.vkvg_pattern_add_color_stop(pat, *[float(v) for v in s])
+        L.vkvg_set_source(self.h, pat)
+        L.vkvg_pattern_destroy(pat)
+
+    def set_source_linear(self, x0, y0, x1, y1, stops):
+        self._grad(lib().vkvg_pattern_create_linear(x0, y0, x1, y1), stops)
+
+    def set_source_radial(self, cx0, cy0, r0, cx1, cy1, r1, stops):
+        self._grad(lib().vkvg_pattern_create_radial(cx0, cy0, r0, cx1, cy1, r1), stops)
+
+    # ---- stage introspection (vkvg_b200.h) ----
+    def path_points(self):
+        """flattened points of the current path, computed by the CUDA flatten kernels: (n,2) float32."""
+        L = lib()
+        ns = _u()
+        n = L.vkvg_b200_flatten_path(self.h, None, None, 0, None, None, 0, C.byref(ns))
+        xy = np.zeros((n, 2), np.float32)
+        cur = np.zeros(n, np.uint8)
+        first = np.zeros(ns.value, np.uint32)
+        cnt = np.zeros(ns.value, np.uint32)
+        L.vkvg_b200_flatten_path(self.h, xy.ctypes.data, cur.ctypes.data, n, first.ctypes.data, cnt.ctypes.data, ns.value, C.byref(ns))
+        self._last_subpaths = (first, cnt, cur)
+        return xy
+
+    def path_subpaths(self):
+        self.path_points()
+        return self._last_subpaths
+
+    def stroke_geometry(self):
+        L = lib()
+        nv, ni = _u(), _u()
+        L.vkvg_b200_stroke_geometry(self.h, None, 0, C.byref(nv), None, 0, C.byref(ni))
+        v = np.zeros((nv.value, 2), np.float32)
+        ix = np.zeros(ni.value, np.uint32)
+        L.vkvg_b200_stroke_geometry(self.h, v.ctypes.data, nv.value, C.byref(nv), ix.ctypes.data, ni.value, C.byref(ni))
+        return v, ix
+
+    def path_edges(self, stroke=False):
+        L = lib()
+        n = L.vkvg_b200_path_edges(self.h, int(stroke), None, 0)
+        e = np.zeros((n, 4), np.int32)
+        L.vkvg_b200_path_edges(self.h, int(stroke), e.ctypes.data, n)
+        return e
+
+    def flush_capture_winding(self):
+        d = self.surf.dev
+        out = np.zeros((self.surf.height, self.surf.width, d.samples), np.int32)
+        lib().vkvg_b200_flush_capture_winding(self.h, out.ctypes.data)
+        return out
+
+    def replay(self, ops, args):
+        ops = np.ascontiguousarray(ops, np.uint8)
+        args = np.ascontiguousarray(args, np.float32)
+        return lib().vkvg_b200_replay(self.h, ops.ctypes.data, len(ops), args.ctypes.data, len(args))
+
+
+class CommandStream:
+    """Builds the packed (ops, args) arrays consumed by vkvg_b200_replay; method names as on Context."""
+
+    def __init__(self):
+        self.ops = []
+        self.args = []
+
+    def _op(self, name, *a):
+        self.ops.append(OPS[name])
+        self.args.extend(float(v) for v in a)
+
+    def __getattr__(self, name):
+        key = name.upper()
+        if key in OPS and key not in ("SET_DASH", "SET_SOURCE_LINEAR", "SET_SOURCE_RADIAL", "POLYLINE"):
+            return lambda *a: self._op(key, *a)
+        raise AttributeError(name)
+
+    def set_dash(self, dashes, offset=0.0):
+        self._op("SET_DASH", len(dashes), offset, *dashes)
+
+    def set_source_linear(self, x0, y0, x1, y1, stops):
+        s = np.asarray(stops, np.float32).reshape(-1, 5)
+        self._op("SET_SOURCE_LINEAR", x0, y0, x1, y1, len(s), *s.ravel())
+
+    def set_source_radial(self, cx0, cy0, r0, cx1, cy1, r1, stops):
+        s = np.asarray(stops, np.float32).reshape(-1, 5)
+        self._op("SET_SOURCE_RADIAL", cx0, cy0, r0, cx1, cy1, r1, len(s), *s.ravel())
+
+    def polyline(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        self.ops.append(OPS["POLYLINE"])
+        self.args.append(np.array([len(xy)], np.uint32).view(np.float32)[0])
+        self.args.append(xy.ravel())
+
+    def arrays(self):
+        parts = []
+        run = []
+        for a in self.args:
+            if isinstance(a, np.ndarray):
+                if run:
+                    parts.append(np.asarray(run, np.float32))
+                    run = []
+                parts.append(a.astype(np.float32, copy=False))
+            elif isinstance(a, np.floating):
+                if run:
+                    parts.append(np.asarray(run, np.float32))
+                    run = []
+                parts.append(np.array([a], np.float32))
+            else:
+                run.append(a)
+        if run:
+            parts.append(np.asarray(run, np.float32))
+        args = np.concatenate(parts) if parts else np.zeros(0, np.float32)
+        return np.asarray(self.ops, np.uint8), args

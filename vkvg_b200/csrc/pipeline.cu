@@ -1,0 +1,502 @@
+// Orchestration of one flush: upload -> flatten -> stroke / fill edges -> binning -> fine pass.
+// Everything runs on one CUDA stream per device; device buffers are grow-only and reused between flushes.
+#include "pipeline.h"
+#include "renderer.h"
+#include <string.h>
+#include <vector>
+
+unsigned long long g_vkb_launches = 0;
+static int         g_cuda_failed  = 0;
+void               vkb_note_cuda_error(cudaError_t) { g_cuda_failed = 1; }
+
+struct vkb_device_impl {
+    int          ordinal = 0;
+    cudaStream_t stream  = nullptr;
+    cudaEvent_t  ev_begin = nullptr, ev_end = nullptr, ev_fine0 = nullptr, ev_fine1 = nullptr;
+    // pinned staging
+    uint8_t *stage     = nullptr;
+    size_t   stage_cap = 0;
+    uint64_t *readback = nullptr;  // pinned, 16 slots
+    // batch (device)
+    DevBuf   elem_hdr, elem_data, subpaths, draws, grads, dashes, paints;
+    DevBuf   fjob_draw, fjob_sp, sjob_draw, sjob_sp, sdraw_id, sdraw_first_item, extra_edges, extra_edge_draw;
+    uint32_t n_elems = 0, n_sp = 0, n_draws = 0, n_fjobs = 0, n_sjobs = 0, n_sdraws = 0, n_extra = 0;
+    bool     any_dash = false;
+    uint64_t h2d_bytes = 0;
+    std::vector<uint32_t> h_sdraw_first_job;
+    // intermediates
+    DevBuf elem_cnt, totals, pts, ptflags, sp_first, sp_count;
+    DevBuf fjob_base, sjob_base, seglen, cum, item_counts, verts, inds, job_inverse;
+    DevBuf edges, edge_draw;
+    DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
+    DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
+    DevBuf winding, tmp_image;
+    ScanScratch scan;
+    SortScratch sort;
+};
+struct vkb_surface_impl {
+    vkb_device_impl *dev;
+    uint32_t         w, h;
+    DevBuf           image;
+    bool             known_clear;
+};
+
+vkb_device_impl *vkb_device_open(int ordinal) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return nullptr;
+    if (ordinal < 0 || ordinal >= n) ordinal = 0;
+    if (cudaSetDevice(ordinal) != cudaSuccess) return nullptr;
+    vkb_device_impl *d = new vkb_device_impl();
+    d->ordinal         = ordinal;
+    VKB_CUDA_OK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    VKB_CUDA_OK(cudaEventCreate(&d->ev_begin));
+    VKB_CUDA_OK(cudaEventCreate(&d->ev_end));
+    VKB_CUDA_OK(cudaEventCreate(&d->ev_fine0));
+    VKB_CUDA_OK(cudaEventCreate(&d->ev_fine1));
+    VKB_CUDA_OK(cudaHostAlloc((void **)&d->readback, 16 * sizeof(uint64_t), cudaHostAllocDefault));
+    if (g_cuda_failed) { delete d; return nullptr; }
+    return d;
+}
+void vkb_device_close(vkb_device_impl *d) {
+    if (!d) return;
+    cudaSetDevice(d->ordinal);
+    cudaStreamSynchronize(d->stream);
+    DevBuf *bufs[] = {&d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
+                      &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
+                      &d->sp_first, &d->sp_count, &d->fjob_base, &d->sjob_base, &d->seglen, &d->cum, &d->item_counts, &d->verts, &d->inds, &d->job_inverse,
+                      &d->edges, &d->edge_draw, &d->draw_bbox, &d->draw_rect, &d->draw_counts, &d->draw_ptbase, &d->draw_rowbase, &d->pt_count,
+                      &d->pt_backdrop, &d->pt_flags, &d->pt_draw, &d->keys, &d->vals, &d->sorted_cnt, &d->pt_slot, &d->cursor, &d->hdr, &d->tile_first,
+                      &d->tile_end, &d->tile_edges, &d->winding, &d->tmp_image, &d->scan.sums, &d->sort.hist, &d->sort.k2, &d->sort.v2, &d->sort.scan.sums};
+    for (DevBuf *b : bufs) b->release();
+    if (d->stage) cudaFreeHost(d->stage);
+    cudaFreeHost(d->readback);
+    cudaEventDestroy(d->ev_begin); cudaEventDestroy(d->ev_end); cudaEventDestroy(d->ev_fine0); cudaEventDestroy(d->ev_fine1);
+    cudaStreamDestroy(d->stream);
+    delete d;
+}
+int  vkb_device_failed(vkb_device_impl *) { return g_cuda_failed; }
+void vkb_device_sync(vkb_device_impl *d) {
+    cudaSetDevice(d->ordinal);
+    VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
+}
+
+vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h) {
+    cudaSetDevice(d->ordinal);
+    vkb_surface_impl *s = new vkb_surface_impl();
+    s->dev = d; s->w = w; s->h = h;
+    s->image.ensure((size_t)w * h * 4 + 16, d->stream);
+    VKB_CUDA_OK(cudaMemsetAsync(s->image.p, 0, (size_t)w * h * 4, d->stream));
+    s->known_clear = true;
+    return s;
+}
+void vkb_surface_free(vkb_surface_impl *s) {
+    if (!s) return;
+    cudaSetDevice(s->dev->ordinal);
+    cudaStreamSynchronize(s->dev->stream);
+    s->image.release();
+    delete s;
+}
+void vkb_surface_clear(vkb_surface_impl *s) {
+    cudaSetDevice(s->dev->ordinal);
+    if (!s->known_clear) VKB_CUDA_OK(cudaMemsetAsync(s->image.p, 0, (size_t)s->w * s->h * 4, s->dev->stream));
+    s->known_clear = true;
+}
+const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s) { return s->image.as<uint32_t>(); }
+int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) {
+    vkb_device_impl *d = s->dev;
+    cudaSetDevice(d->ordinal);
+    size_t          bytes = (size_t)s->w * s->h * 4;
+    const uint32_t *src   = s->image.as<uint32_t>();
+    if (unpremultiply) {
+        d->tmp_image.ensure(bytes, d->stream);
+        vkb_launch_unpremultiply(src, (uint64_t)s->w * s->h, d->tmp_image.as<uint32_t>(), d->stream);
+        src = d->tmp_image.as<uint32_t>();
+    }
+    VKB_CUDA_OK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, d->stream));
+    VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
+    return g_cuda_failed;
+}
+
+// ---- upload ----
+static uint8_t *stage_reserve(vkb_device_impl *d, size_t bytes) {
+    if (bytes > d->stage_cap) {
+        if (d->stage) {
+            cudaStreamSynchronize(d->stream);
+            cudaFreeHost(d->stage);
+        }
+        size_t cap = d->stage_cap ? d->stage_cap : (1u << 20);
+        while (cap < bytes) cap *= 2;
+        VKB_CUDA_OK(cudaHostAlloc((void **)&d->stage, cap, cudaHostAllocDefault));
+        d->stage_cap = cap;
+    }
+    return d->stage;
+}
+struct Uploader {
+    vkb_device_impl *d;
+    size_t           off = 0;
+    struct Item { DevBuf *dst; size_t off, bytes; };
+    std::vector<Item> items;
+    size_t total = 0;
+    void   plan(DevBuf *dst, size_t bytes) {
+        items.push_back({dst, total, bytes});
+        total += (bytes + 255) & ~(size_t)255;
+    }
+};
+
+int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
+    cudaSetDevice(d->ordinal);
+    cudaStream_t st = d->stream;
+    // the previous flush may still be reading the staging area
+    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    // job tables (host): one job per (draw, sub-path)
+    std::vector<uint32_t> fjd, fjs, sjd, sjs, sdid, extra_draw;
+    std::vector<vkb_paint> paints(b.draws.size());
+    std::vector<int32_t>   extra;
+    d->h_sdraw_first_job.clear();
+    d->any_dash = false;
+    for (uint32_t i = 0; i < b.draws.size(); i++) {
+        const vkb_draw &dr = b.draws[i];
+        paints[i]          = vkb_paint{dr.rule | (dr.pattern << 8), dr.color, dr.opacity, dr.gradient};
+        if (dr.kind == VKB_DRAW_FILL) {
+            for (uint32_t s = 0; s < dr.n_subpaths; s++) { fjd.push_back(i); fjs.push_back(dr.first_subpath + s); }
+        } else if (dr.kind == VKB_DRAW_STROKE) {
+            if (dr.n_subpaths) {
+                sdid.push_back(i);
+                d->h_sdraw_first_job.push_back((uint32_t)sjd.size());
+            }
+            for (uint32_t s = 0; s < dr.n_subpaths; s++) { sjd.push_back(i); sjs.push_back(dr.first_subpath + s); }
+            if (dr.dash_count) d->any_dash = true;
+        } else {  // whole-surface paint: a rectangle well outside the surface, filled non-zero; the exact size is
+                  // irrelevant as long as it encloses every sample (internal.c:1919-1952 draws an oversized triangle)
+            extra_draw.insert(extra_draw.end(), 4, i);
+            extra.insert(extra.end(), 16, 0);  // patched with the surface size at render time
+        }
+    }
+    d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
+    d->n_fjobs = (uint32_t)fjd.size(); d->n_sjobs = (uint32_t)sjd.size(); d->n_sdraws = (uint32_t)sdid.size(); d->n_extra = (uint32_t)extra_draw.size();
+
+    struct Src { DevBuf *dst; const void *p; size_t bytes; };
+    Src srcs[] = {
+        {&d->elem_hdr, b.elem_hdr.data(), b.elem_hdr.size() * 4},       {&d->elem_data, b.elem_data.data(), b.elem_data.size() * 4},
+        {&d->subpaths, b.subpaths.data(), b.subpaths.size() * sizeof(vkb_subpath)}, {&d->draws, b.draws.data(), b.draws.size() * sizeof(vkb_draw)},
+        {&d->grads, b.grads.data(), b.grads.size() * sizeof(vkb_gradient)}, {&d->dashes, b.dashes.data(), b.dashes.size() * 4},
+        {&d->paints, paints.data(), paints.size() * sizeof(vkb_paint)}, {&d->fjob_draw, fjd.data(), fjd.size() * 4},
+        {&d->fjob_sp, fjs.data(), fjs.size() * 4},                       {&d->sjob_draw, sjd.data(), sjd.size() * 4},
+        {&d->sjob_sp, sjs.data(), sjs.size() * 4},                       {&d->sdraw_id, sdid.data(), sdid.size() * 4},
+        {&d->extra_edge_draw, extra_draw.data(), extra_draw.size() * 4},
+    };
+    size_t total = 0;
+    for (Src &s : srcs) total += (s.bytes + 255) & ~(size_t)255;
+    uint8_t *stg = stage_reserve(d, total + 256);
+    size_t   off = 0;
+    for (Src &s : srcs) {
+        s.dst->ensure(s.bytes + 16, st);
+        if (s.bytes) {
+            memcpy(stg + off, s.p, s.bytes);
+            VKB_CUDA_OK(cudaMemcpyAsync(s.dst->p, stg + off, s.bytes, cudaMemcpyHostToDevice, st));
+        }
+        off += (s.bytes + 255) & ~(size_t)255;
+    }
+    d->extra_edges.ensure((size_t)d->n_extra * 16 + 16, st);
+    d->h2d_bytes = 0;
+    for (Src &s : srcs) d->h2d_bytes += s.bytes;
+    return g_cuda_failed;
+}
+
+static uint64_t read_total(vkb_device_impl *d, const void *dev_ptr, size_t bytes) {
+    d->readback[0] = 0;
+    VKB_CUDA_OK(cudaMemcpyAsync(d->readback, dev_ptr, bytes, cudaMemcpyDeviceToHost, d->stream));
+    VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
+    return d->readback[0];
+}
+template <class T> static void download(vkb_device_impl *d, std::vector<T> *out, const void *src, size_t n) {
+    if (!out) return;
+    out->resize(n);
+    if (n) VKB_CUDA_OK(cudaMemcpyAsync(out->data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, d->stream));
+    VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
+}
+
+__global__ void gather_first_items_k(const uint32_t *first_job, const uint32_t *job_base, uint32_t n, uint32_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = job_base[first_job[i]];
+}
+__global__ void paint_rect_edges_k(vkb_edge *e, uint32_t n_rects, int32_t W, int32_t H) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rects) return;
+    const int32_t x0 = -VKB_TILE_FX, y0 = -VKB_TILE_FX, x1 = W * 256 + VKB_TILE_FX, y1 = H * 256 + VKB_TILE_FX;
+    e[4 * i]     = vkb_edge{x0, y0, x1, y0};
+    e[4 * i + 1] = vkb_edge{x1, y0, x1, y1};
+    e[4 * i + 2] = vkb_edge{x1, y1, x0, y1};
+    e[4 * i + 3] = vkb_edge{x0, y1, x0, y0};
+}
+
+// binning + fine pass over d->edges / d->edge_draw (n_edges entries, nd draws, paints/grads already on the device)
+static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc sd, uint32_t nd, uint64_t n_edges, vkb_capture *cap, vkb_stats &S,
+                        vkb_stats *stats) {
+    cudaStream_t st     = d->stream;
+    uint64_t    *totals = d->totals.as<uint64_t>();
+    const uint32_t samples = sd.samples;
+    vkb_edge *edges = d->edges.as<vkb_edge>();
+    uint32_t *edraw = d->edge_draw.as<uint32_t>();
+    // ---- 5. binning ----
+    const uint32_t n_tiles = sd.tiles_x * sd.tiles_y;
+    d->draw_bbox.ensure((size_t)nd * 16, st);
+    d->draw_rect.ensure((size_t)nd * 16, st);
+    d->draw_counts.ensure((size_t)(nd + 1) * 8, st);
+    d->draw_ptbase.ensure((size_t)(nd + 1) * 4, st);
+    d->draw_rowbase.ensure((size_t)(nd + 1) * 4, st);
+    vkb_launch_draw_bbox(edges, edraw, n_edges, nd, d->draw_bbox.as<int32_t>(), st);
+    unsigned long long *dc = d->draw_counts.as<unsigned long long>();
+    vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), nd, sd, d->draw_rect.as<int32_t>(), dc, st);
+    vkb_exclusive_scan<unsigned long long, unsigned long long>(dc, dc, nd, (unsigned long long *)(totals + 4), d->scan, st);
+    vkb_launch_split_bases(dc, nd, d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), st);
+    unsigned long long tr = read_total(d, totals + 4, 8);
+    const uint32_t     n_pt = (uint32_t)(tr & 0xffffffffull);
+    S.n_path_tiles = n_pt;
+
+    d->pt_count.ensure((size_t)(n_pt + 1) * 4, st);
+    d->pt_backdrop.ensure((size_t)(n_pt + 1) * 4, st);
+    d->pt_flags.ensure((size_t)(n_pt + 1) * 4, st);
+    d->pt_slot.ensure((size_t)(n_pt + 1) * 4, st);
+    VKB_CUDA_OK(cudaMemsetAsync(d->pt_count.p, 0, (size_t)n_pt * 4, st));
+    VKB_CUDA_OK(cudaMemsetAsync(d->pt_backdrop.p, 0, (size_t)n_pt * 4, st));
+    vkb_launch_bin_count(edges, edraw, n_edges, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_count.as<uint32_t>(),
+                         d->pt_backdrop.as<int32_t>(), st);
+    vkb_launch_backdrop_prefix(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd,
+                               (unsigned long long *)(totals + 4), d->pt_backdrop.as<int32_t>(), st);
+    vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), n_pt, d->pt_flags.as<uint32_t>(), st);
+    // pt_slot doubles as the exclusive scan of the flags until the sorted slots overwrite it
+    d->sorted_cnt.ensure((size_t)(n_pt + 1) * 4, st);
+    uint32_t *flag_scan = d->sorted_cnt.as<uint32_t>();
+    vkb_exclusive_scan<uint32_t, uint32_t>(d->pt_flags.as<uint32_t>(), flag_scan, n_pt, (uint32_t *)(totals + 5), d->scan, st);
+    const uint32_t n_ne = n_pt ? (uint32_t)read_total(d, totals + 5, 4) : 0;
+    S.n_nonempty = n_ne;
+
+    d->keys.ensure((size_t)(n_ne + 1) * 4, st);
+    d->vals.ensure((size_t)(n_ne + 1) * 4, st);
+    d->pt_draw.ensure((size_t)(n_ne + 1) * 4, st);
+    d->cursor.ensure((size_t)(n_ne + 1) * 4, st);
+    d->hdr.ensure((size_t)(n_ne + 1) * 16, st);
+    d->tile_first.ensure((size_t)n_tiles * 4 + 16, st);
+    d->tile_end.ensure((size_t)n_tiles * 4 + 16, st);
+    vkb_launch_pt_compact(d->pt_flags.as<uint32_t>(), flag_scan, n_pt, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), nd, sd,
+                          d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), d->pt_draw.as<uint32_t>(), st);
+    int bits = 1;
+    while ((1u << bits) < n_tiles && bits < 32) bits++;
+    vkb_radix_sort(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), n_ne, bits, d->sort, st);
+    // edge offsets in sorted (tile-major, draw-ordered) order
+    uint32_t *eoff = d->cursor.as<uint32_t>();  // scan output; cursor proper is a separate zeroed array below
+    DevBuf   &cur2 = d->winding;                // reuse: winding capture buffer is only needed after scatter
+    cur2.ensure((size_t)(n_ne + 1) * 4, st);
+    {
+        // sorted_cnt currently holds flag_scan which headers_k still needs: put the sorted counts in pt_flags instead
+        uint32_t *scnt = d->pt_flags.as<uint32_t>();
+        vkb_launch_sorted_counts(d->vals.as<uint32_t>(), n_ne, d->pt_count.as<uint32_t>(), scnt, d->pt_slot.as<uint32_t>(), st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(scnt, eoff, n_ne, (uint32_t *)(totals + 6), d->scan, st);
+    }
+    const uint32_t n_te = n_ne ? (uint32_t)read_total(d, totals + 6, 4) : 0;
+    S.n_tile_edges = n_te;
+    d->tile_edges.ensure((size_t)(n_te + 1) * 16, st);
+    VKB_CUDA_OK(cudaMemsetAsync(d->tile_first.p, 0, (size_t)n_tiles * 4, st));
+    VKB_CUDA_OK(cudaMemsetAsync(d->tile_end.p, 0, (size_t)n_tiles * 4, st));
+    vkb_launch_headers(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), n_ne, d->pt_draw.as<uint32_t>(), flag_scan, d->pt_backdrop.as<int32_t>(),
+                       d->pt_count.as<uint32_t>(), eoff, d->hdr.as<int4>(), d->tile_first.as<uint32_t>(), d->tile_end.as<uint32_t>(), st);
+    VKB_CUDA_OK(cudaMemsetAsync(cur2.p, 0, (size_t)n_ne * 4, st));
+    vkb_launch_bin_scatter(edges, edraw, n_edges, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_slot.as<uint32_t>(), eoff,
+                           cur2.as<uint32_t>(), d->tile_edges.as<vkb_edge>(), st);
+
+    // ---- 6. fine pass ----
+    FineArgs fa;
+    fa.sd = sd;
+    fa.tile_first = d->tile_first.as<uint32_t>(); fa.tile_end = d->tile_end.as<uint32_t>();
+    fa.hdr = d->hdr.as<int4>(); fa.tile_edges = d->tile_edges.as<vkb_edge>();
+    fa.paints = d->paints.as<vkb_paint>(); fa.grads = d->grads.as<vkb_gradient>();
+    fa.image = surf->image.as<uint32_t>();
+    fa.dst_is_clear = surf->known_clear ? 1 : 0;
+    fa.winding_out = nullptr; fa.winding_draw = 0;
+    DevBuf wbuf;
+    if (cap && cap->winding) {
+        size_t wb = (size_t)sd.width * sd.height * samples * 4;
+        wbuf.ensure(wb, st);
+        VKB_CUDA_OK(cudaMemsetAsync(wbuf.p, 0, wb, st));
+        fa.winding_out = wbuf.as<int32_t>(); fa.winding_draw = cap->winding_draw;
+    }
+    VKB_CUDA_OK(cudaEventRecord(d->ev_fine0, st));
+    vkb_launch_fine(fa, st);
+    VKB_CUDA_OK(cudaEventRecord(d->ev_fine1, st));
+    surf->known_clear = false;
+    VKB_CUDA_OK(cudaEventRecord(d->ev_end, st));
+    if (cap && cap->winding) {
+        VKB_CUDA_OK(cudaMemcpyAsync(cap->winding, wbuf.p, (size_t)sd.width * sd.height * samples * 4, cudaMemcpyDeviceToHost, st));
+        VKB_CUDA_OK(cudaStreamSynchronize(st));
+        wbuf.release();
+    }
+    if (stats) {
+        VKB_CUDA_OK(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&S.ms_total, d->ev_begin, d->ev_end);
+        cudaEventElapsedTime(&S.ms_fine, d->ev_fine0, d->ev_fine1);
+        *stats = S;
+    }
+    return g_cuda_failed;
+}
+
+int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats) {
+    cudaSetDevice(d->ordinal);
+    cudaStream_t st = d->stream;
+    vkb_stats    S;
+    memset(&S, 0, sizeof S);
+    S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes;
+    SurfaceDesc sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE};
+    VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
+    d->totals.ensure(16 * 8, st);
+    uint64_t *totals = d->totals.as<uint64_t>();
+
+    // ---- 1. flatten: count -> scan -> emit ----
+    uint32_t n_points = 0;
+    d->elem_cnt.ensure((size_t)(d->n_elems + 1) * 4, st);
+    d->sp_first.ensure((size_t)(d->n_sp + 1) * 4, st);
+    d->sp_count.ensure((size_t)(d->n_sp + 1) * 4, st);
+    if (d->n_elems) {
+        vkb_launch_flatten_count(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->elem_cnt.as<uint32_t>(), d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals, d->scan, st);
+        n_points = (uint32_t)read_total(d, totals, 4);
+        d->pts.ensure((size_t)(n_points + 1) * 8, st);
+        d->ptflags.ensure((size_t)n_points + 16, st);
+        vkb_launch_flatten_emit(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), d->pts.as<float2>(),
+                                d->ptflags.as<uint8_t>(), st);
+        vkb_launch_subpath_ranges(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals,
+                                  d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), st);
+    }
+    S.n_points = n_points;
+    if (cap) {
+        download(d, cap->points, d->pts.p, (size_t)n_points * 2);
+        download(d, cap->ptflags, d->ptflags.p, (size_t)n_points);
+        download(d, cap->sp_first, d->sp_first.p, d->n_sp);
+        download(d, cap->sp_count, d->sp_count.p, d->n_sp);
+    }
+
+    // ---- 2. job sizes: fill jobs need > 2 points, stroke jobs >= 2 ----
+    uint32_t n_fill = 0, n_sitems = 0;
+    d->fjob_base.ensure((size_t)(d->n_fjobs + 1) * 4, st);
+    d->sjob_base.ensure((size_t)(d->n_sjobs + 1) * 4, st);
+    if (d->n_fjobs) {
+        vkb_launch_job_counts(d->fjob_sp.as<uint32_t>(), d->n_fjobs, d->sp_count.as<uint32_t>(), 3, d->fjob_base.as<uint32_t>(), st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->fjob_base.as<uint32_t>(), d->fjob_base.as<uint32_t>(), d->n_fjobs, (uint32_t *)(totals + 1), d->scan, st);
+    }
+    if (d->n_sjobs) {
+        vkb_launch_job_counts(d->sjob_sp.as<uint32_t>(), d->n_sjobs, d->sp_count.as<uint32_t>(), 2, d->sjob_base.as<uint32_t>(), st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->sjob_base.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, (uint32_t *)(totals + 2), d->scan, st);
+    }
+    if (d->n_fjobs || d->n_sjobs) {
+        VKB_CUDA_OK(cudaMemcpyAsync(d->readback, totals, 24, cudaMemcpyDeviceToHost, st));
+        VKB_CUDA_OK(cudaStreamSynchronize(st));
+        n_fill   = d->n_fjobs ? (uint32_t)d->readback[1] : 0;
+        n_sitems = d->n_sjobs ? (uint32_t)d->readback[2] : 0;
+    }
+    S.n_fill_edges = n_fill; S.n_stroke_items = n_sitems;
+
+    // ---- 3. strokes: (dash phase scan) -> count -> scan -> emit ----
+    uint32_t n_verts = 0, n_inds = 0;
+    if (n_sitems) {
+        StrokeArgs sa = {d->pts.as<float2>(), d->ptflags.as<uint8_t>(), d->draws.as<vkb_draw>(), d->dashes.as<float>(), d->sjob_draw.as<uint32_t>(),
+                         d->sjob_sp.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(),
+                         d->subpaths.as<vkb_subpath>(), nullptr, n_sitems};
+        if (d->any_dash) {
+            d->seglen.ensure((size_t)(n_sitems + 1) * 4, st);
+            d->cum.ensure((size_t)(n_sitems + 1) * 8, st);
+            vkb_launch_stroke_seglen(sa, d->seglen.as<float>(), st);
+            vkb_exclusive_scan<float, double>(d->seglen.as<float>(), d->cum.as<double>(), (uint64_t)n_sitems + 1, nullptr, d->scan, st);
+            sa.cum = d->cum.as<double>();
+        }
+        d->item_counts.ensure((size_t)(n_sitems + 1) * 8, st);
+        d->job_inverse.ensure((size_t)(d->n_sjobs + 1) * 4, st);
+        VKB_CUDA_OK(cudaMemsetAsync(d->job_inverse.p, 0, (size_t)d->n_sjobs * 4, st));
+        unsigned long long *ic = d->item_counts.as<unsigned long long>();
+        vkb_launch_stroke_count(sa, ic, st);
+        vkb_exclusive_scan<unsigned long long, unsigned long long>(ic, ic, n_sitems, (unsigned long long *)(totals + 3), d->scan, st);
+        unsigned long long tot = read_total(d, totals + 3, 8);
+        n_verts = (uint32_t)(tot & 0xffffffffull); n_inds = (uint32_t)(tot >> 32);
+        d->verts.ensure((size_t)(n_verts + 1) * 8, st);
+        d->inds.ensure((size_t)(n_inds + 3) * 4, st);
+        vkb_launch_stroke_emit(sa, ic, tot, d->verts.as<float2>(), d->inds.as<uint32_t>(), d->job_inverse.as<uint32_t>(), st);
+        if (cap) {
+            download(d, cap->verts, d->verts.p, (size_t)n_verts * 2);
+            download(d, cap->inds, d->inds.p, (size_t)n_inds);
+        }
+    }
+    S.n_verts = n_verts; S.n_inds = n_inds;
+
+    // ---- 4. edges ----
+    const uint32_t n_tris  = n_inds / 3;
+    const uint64_t n_edges = (uint64_t)n_fill + 3ull * n_tris + d->n_extra;
+    S.n_edges = n_edges;
+    d->edges.ensure((n_edges + 1) * 16, st);
+    d->edge_draw.ensure((n_edges + 1) * 4, st);
+    vkb_edge *edges = d->edges.as<vkb_edge>();
+    uint32_t *edraw = d->edge_draw.as<uint32_t>();
+    vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
+                          d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), n_fill, sd, edges, edraw, st);
+    if (n_tris) {
+        // first work item of every stroke draw (to map a triangle back to its draw)
+        d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
+        d->keys.ensure((size_t)d->n_sdraws * 4 + 16, st);
+        VKB_CUDA_OK(cudaMemcpyAsync(d->keys.p, d->h_sdraw_first_job.data(), (size_t)d->n_sdraws * 4, cudaMemcpyHostToDevice, st));
+        gather_first_items_k<<<vkb_div_up(d->n_sdraws, 256), 256, 0, st>>>(d->keys.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
+                                                                          d->sdraw_first_item.as<uint32_t>());
+        VKB_LAUNCHED();
+        vkb_launch_tri_edges(d->verts.as<float2>(), n_verts, d->inds.as<uint32_t>(), n_tris, d->draws.as<vkb_draw>(), d->sdraw_id.as<uint32_t>(),
+                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges + n_fill, edraw + n_fill, st);
+    }
+    if (d->n_extra) {
+        paint_rect_edges_k<<<vkb_div_up(d->n_extra / 4, 64), 64, 0, st>>>(edges + n_fill + 3ull * n_tris, d->n_extra / 4, (int32_t)sd.width, (int32_t)sd.height);
+        VKB_LAUNCHED();
+        VKB_CUDA_OK(cudaMemcpyAsync(edraw + n_fill + 3ull * n_tris, d->extra_edge_draw.p, (size_t)d->n_extra * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (cap) {
+        download(d, cap->edges, edges, (size_t)n_edges * 4);
+        download(d, cap->edge_draw, edraw, (size_t)n_edges);
+    }
+    if ((cap && cap->geometry_only) || d->n_draws == 0) {
+        VKB_CUDA_OK(cudaEventRecord(d->ev_end, st));
+        VKB_CUDA_OK(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&S.ms_total, d->ev_begin, d->ev_end);
+        if (stats) *stats = S;
+        return g_cuda_failed;
+    }
+    return bin_and_fine(d, surf, sd, d->n_draws, n_edges, cap, S, stats);
+}
+
+int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const vkb_batch &b, vkb_capture *cap, vkb_stats *stats) {
+    if (vkb_upload(d, b)) return 1;
+    return vkb_render_resident(d, s, samples, cap, stats);
+}
+
+int vkb_device_ordinal(vkb_device_impl *d) { return d->ordinal; }
+
+// raw directed edges as a single non-zero draw; returns the per-sample winding the fine pass computed
+int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h, uint64_t n, uint32_t w, uint32_t h, int32_t *out) {
+    cudaSetDevice(d->ordinal);
+    cudaStream_t st = d->stream;
+    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    vkb_surface_impl *surf = vkb_surface_new(d, w, h);
+    SurfaceDesc sd = {w, h, samples, (w + VKB_TILE - 1) / VKB_TILE, (h + VKB_TILE - 1) / VKB_TILE};
+    d->totals.ensure(16 * 8, st);
+    d->edges.ensure((n + 1) * 16, st);
+    d->edge_draw.ensure((n + 1) * 4, st);
+    d->paints.ensure(sizeof(vkb_paint), st);
+    d->grads.ensure(sizeof(vkb_gradient), st);
+    vkb_paint p = {VKB_RULE_NON_ZERO | (VKB_PAT_SOLID << 8), 0xffffffffu, 1.0f, 0};
+    VKB_CUDA_OK(cudaMemcpyAsync(d->paints.p, &p, sizeof p, cudaMemcpyHostToDevice, st));
+    if (n) VKB_CUDA_OK(cudaMemcpyAsync(d->edges.p, edges_h, n * 16, cudaMemcpyHostToDevice, st));
+    VKB_CUDA_OK(cudaMemsetAsync(d->edge_draw.p, 0, (n + 1) * 4, st));
+    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    vkb_capture cap;
+    cap.winding = out; cap.winding_draw = 0;
+    vkb_stats S;
+    memset(&S, 0, sizeof S);
+    VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
+    int r = bin_and_fine(d, surf, sd, 1, n, &cap, S, nullptr);
+    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    vkb_surface_free(surf);
+    return r;
+}

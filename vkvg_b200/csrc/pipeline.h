@@ -1,0 +1,85 @@
+// Internal interface between the CUDA stages (flatten.cu, stroke.cu, raster.cu) and the orchestrator
+// (pipeline.cu).  Nothing here is exported from the shared library.
+#pragma once
+#include "dev_util.cuh"
+#include "vkb_types.h"
+
+// ---- flatten.cu ----
+void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, cudaStream_t s);
+void vkb_launch_flatten_emit(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, const uint32_t *offsets, float2 *pts, uint8_t *flags,
+                             cudaStream_t s);
+void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_off, uint32_t n_elems, const uint32_t *total,
+                               uint32_t *sp_first, uint32_t *sp_count, cudaStream_t s);
+
+// ---- job tables: one job = one sub-path of one draw; items = its points ----
+void vkb_launch_job_counts(const uint32_t *job_sp, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, uint32_t *job_n, cudaStream_t s);
+
+// ---- stroke.cu ----
+struct StrokeArgs {
+    const float2      *pts;
+    const uint8_t     *ptflags;
+    const vkb_draw    *draws;
+    const float       *dash_table;
+    const uint32_t    *job_draw, *job_sp, *job_base;
+    uint32_t           n_jobs;
+    const uint32_t    *sp_first, *sp_count;
+    const vkb_subpath *sps;
+    const double      *cum;  // exclusive scan of segment lengths over all stroke items (+1), or null if nothing is dashed
+    uint32_t           n_items;
+};
+void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s);
+void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s);
+void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, unsigned long long total, float2 *verts, uint32_t *inds,
+                            uint32_t *job_inverse, cudaStream_t s);
+
+// ---- raster.cu ----
+struct SurfaceDesc {
+    uint32_t width, height, samples;
+    uint32_t tiles_x, tiles_y;
+};
+void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
+                           uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges,
+                           uint32_t *edge_draw, cudaStream_t s);
+void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws,
+                          const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
+                          SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
+
+struct BinBuffers {  // all device pointers
+    int32_t  *draw_bbox;    // n_draws x 4 (minx, miny, maxx, maxy), fixed point
+    int32_t  *draw_rect;    // n_draws x 4 (tx0, ty0, tw, th) in tiles
+    uint32_t *draw_ptbase;  // n_draws (+1): first path-tile of the draw
+    uint32_t *draw_rowbase; // n_draws (+1): first path-tile row of the draw
+};
+void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s);
+void vkb_launch_draw_rects(const int32_t *draw_bbox, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect, unsigned long long *tile_row_counts,
+                           cudaStream_t s);
+void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s);
+void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+                          uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s);
+void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
+                                const unsigned long long *totals, int32_t *pt_backdrop, cudaStream_t s);
+void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, uint32_t *flags, cudaStream_t s);
+void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+                           uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
+void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot, cudaStream_t s);
+void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
+                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, int4 *hdr, uint32_t *tile_first,
+                        uint32_t *tile_end, cudaStream_t s);
+void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+                            const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s);
+
+struct FineArgs {
+    SurfaceDesc         sd;
+    const uint32_t     *tile_first, *tile_end;
+    const int4         *hdr;         // per sorted path-tile: draw, backdrop, edge offset, edge count
+    const vkb_edge     *tile_edges;
+    const vkb_paint    *paints;      // per draw
+    const vkb_gradient *grads;
+    uint32_t           *image;       // width*height premultiplied RGBA8
+    int                 dst_is_clear;  // destination known to be transparent black: do not read it
+    int32_t            *winding_out; // optional: per-sample winding of the LAST draw touching each sample (parity tests), or null
+    uint32_t            winding_draw; // draw index captured into winding_out
+};
+void vkb_launch_fine(const FineArgs &a, cudaStream_t s);
+
+void vkb_launch_unpremultiply(const uint32_t *image, uint64_t n_pixels, uint32_t *out, cudaStream_t s);

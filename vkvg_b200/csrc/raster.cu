@@ -1,0 +1,634 @@
+// Tile-binned winding rasteriser + paint/composite pass.
+//
+// Replaces the reference's stencil-then-cover GPU passes (pipelinePolyFill fan + scissored cover,
+// src/vkvg_context_internal.c:1583-1655,1919-1952; direct blending of stroke / libtess triangles through
+// pipe_OVER, src/vkvg_device_internal.c:200-246) and the ICD's rasterisation they rely on.
+//
+// Geometry reaches this file as directed edges in 24.8 fixed-point window coordinates:
+//   even-odd / non-zero fills: the polygon edges of each sub-path (implicitly closed),
+//   strokes: three edges per stroke triangle, every triangle oriented so that it winds +1,
+//   paint: a rectangle larger than the surface.
+// For a sample s the integer winding is  W(s) = sum_e sign(dy_e) [e spans s.y] [x_e(s.y) <= s.x]  with the
+// sample displaced by (+eps', +eps), eps << eps' — exactly the top-left rule of the triangle rasteriser the
+// reference runs on (oracle/vkvg_oracle.c: edge_winding / tri_edge_in).  Per 16x16 tile it is evaluated as
+//   W(s) = B + V(s.y) + H(s)
+//   B    = W at the virtual sample C = (X0+1/2, Y0+1/2) units of the tile origin   ("backdrop")
+//   V    = signed crossings of the vertical segment from C down to (X0+1/2, s.y)
+//   H    = signed crossings of the horizontal segment from (X0+1/2, s.y) to s
+// B needs every edge of the draw and is accumulated by the binning kernel (atomic add at the first tile to
+// the right of the crossing, then a prefix sum along each tile row); V and H only need edges that touch the
+// tile, which the binning kernel scatters into per-tile lists.  All tests are exact (int64 products of
+// 32-bit differences; half-unit coordinates are handled by doubling).
+//
+// The fine pass keeps the S per-sample colours of its pixel in registers across every draw that touches the
+// tile, applies Porter-Duff OVER with the reference's UNORM8 rounding per sample, resolves (box filter) and
+// writes each pixel once.
+#include "pipeline.h"
+
+// ---- vertex stage: shaders/vkvg_main.vert:74-79 + viewport + 8-bit sub-pixel snap (round half up) ----
+__device__ __forceinline__ void vs_snap(const float *m, float W, float H, float x, float y, int32_t &fx, int32_t &fy) {
+    float px = m[0] * x + m[2] * y + m[4];
+    float py = m[1] * x + m[3] * y + m[5];
+    float nx = px * 2.0f / W - 1.0f;
+    float ny = py * 2.0f / H - 1.0f;
+    float wx = nx * (W * 0.5f) + (W * 0.5f);
+    float wy = ny * (H * 0.5f) + (H * 0.5f);
+    // clamp far outside the guard band so the int32 conversion is defined; such coordinates are off-surface
+    wx = fminf(fmaxf(wx, -1.0e6f), 1.0e6f);
+    wy = fminf(fmaxf(wy, -1.0e6f), 1.0e6f);
+    fx = (int32_t)floorf(wx * 256.0f + 0.5f);
+    fy = (int32_t)floorf(wy * 256.0f + 0.5f);
+}
+
+__device__ __forceinline__ uint32_t find_job(const uint32_t *job_base, uint32_t n_jobs, uint32_t item) {
+    uint32_t lo = 0, hi = n_jobs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (job_base[mid] <= item) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void job_counts_k(const uint32_t *job_sp, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, uint32_t *job_n) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    uint32_t n = sp_count[job_sp[j]];
+    job_n[j]   = n >= min_points ? n : 0;
+}
+void vkb_launch_job_counts(const uint32_t *job_sp, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, uint32_t *job_n, cudaStream_t s) {
+    if (!n_jobs) return;
+    job_counts_k<<<vkb_div_up(n_jobs, 256), 256, 0, s>>>(job_sp, n_jobs, sp_count, min_points, job_n);
+    VKB_LAUNCHED();
+}
+
+// ---- fill: one edge per point of every sub-path with > 2 points (the fan of _poly_fill covers exactly the
+//      implicitly closed polygon, internal.c:1617-1642) ----
+__global__ void __launch_bounds__(256)
+fill_edges_k(const float2 *pts, const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs,
+             const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw) {
+    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    uint32_t j = find_job(job_base, n_jobs, item), k = item - job_base[j];
+    uint32_t s = job_sp[j], first = sp_first[s], n = sp_count[s], d = job_draw[j];
+    float2   a = pts[first + k], b = pts[first + (k + 1 == n ? 0 : k + 1)];
+    const float *m = draws[d].mat;
+    vkb_edge e;
+    vs_snap(m, (float)sd.width, (float)sd.height, a.x, a.y, e.x0, e.y0);
+    vs_snap(m, (float)sd.width, (float)sd.height, b.x, b.y, e.x1, e.y1);
+    edges[item]     = e;
+    edge_draw[item] = d;
+}
+void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
+                           uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges,
+                           uint32_t *edge_draw, cudaStream_t s) {
+    if (!n_items) return;
+    fill_edges_k<<<vkb_div_up(n_items, 256), 256, 0, s>>>(pts, draws, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, n_items, sd, edges, edge_draw);
+    VKB_LAUNCHED();
+}
+
+// ---- stroke: three edges per triangle, oriented to wind +1 (so the sum over triangles is the number of
+//      triangles covering the sample, which is how many times the reference blends it) ----
+__global__ void __launch_bounds__(256)
+tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const uint32_t *sdraw_id,
+            const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges,
+            uint32_t *edge_draw) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    // stroke draw owning index 3t: last q whose first item's index offset <= 3t
+    uint32_t lo = 0, hi = n_sdraws;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)(item_offsets[sdraw_first_item[mid]] >> 32) <= 3 * t) lo = mid; else hi = mid;
+    }
+    uint32_t d  = sdraw_id[lo];
+    uint32_t ia = inds[3 * t], ib = inds[3 * t + 1], ic = inds[3 * t + 2];
+    vkb_edge e0 = {0, 0, 0, 0}, e1 = e0, e2 = e0;
+    if (ia < n_verts && ib < n_verts && ic < n_verts) {
+        const float *m = draws[d].mat;
+        float2       a = verts[ia], b = verts[ib], c = verts[ic];
+        int32_t      ax, ay, bx, by, cx, cy;
+        vs_snap(m, (float)sd.width, (float)sd.height, a.x, a.y, ax, ay);
+        vs_snap(m, (float)sd.width, (float)sd.height, b.x, b.y, bx, by);
+        vs_snap(m, (float)sd.width, (float)sd.height, c.x, c.y, cx, cy);
+        long long area = (long long)(bx - ax) * (cy - ay) - (long long)(cx - ax) * (by - ay);
+        if (area > 0) {  // cross > 0 winds -1 under our convention: flip
+            int32_t tx = bx, ty = by;
+            bx = cx; by = cy; cx = tx; cy = ty;
+        }
+        if (area != 0) {
+            e0 = vkb_edge{ax, ay, bx, by};
+            e1 = vkb_edge{bx, by, cx, cy};
+            e2 = vkb_edge{cx, cy, ax, ay};
+        }
+    }
+    edges[3 * t] = e0; edges[3 * t + 1] = e1; edges[3 * t + 2] = e2;
+    edge_draw[3 * t] = d; edge_draw[3 * t + 1] = d; edge_draw[3 * t + 2] = d;
+}
+void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws,
+                          const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
+                          SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
+    if (!n_tris) return;
+    tri_edges_k<<<vkb_div_up(n_tris, 256), 256, 0, s>>>(verts, n_verts, inds, n_tris, draws, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, edges, edge_draw);
+    VKB_LAUNCHED();
+}
+
+// ---- per-draw bounding boxes ----
+__device__ __forceinline__ bool edge_degenerate(const vkb_edge &e) { return e.x0 == e.x1 && e.y0 == e.y1; }
+
+__global__ void draw_bbox_init_k(int32_t *bbox, uint32_t n_draws) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_draws) return;
+    bbox[4 * i] = INT32_MAX; bbox[4 * i + 1] = INT32_MAX; bbox[4 * i + 2] = INT32_MIN; bbox[4 * i + 3] = INT32_MIN;
+}
+__global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, int32_t *bbox) {
+    uint64_t i  = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool     ok = i < n_edges;
+    vkb_edge e  = ok ? edges[i] : vkb_edge{0, 0, 0, 0};
+    uint32_t d  = ok ? edge_draw[i] : 0xffffffffu;
+    ok          = ok && !edge_degenerate(e);
+    int32_t mnx = ok ? min(e.x0, e.x1) : INT32_MAX, mny = ok ? min(e.y0, e.y1) : INT32_MAX;
+    int32_t mxx = ok ? max(e.x0, e.x1) : INT32_MIN, mxy = ok ? max(e.y0, e.y1) : INT32_MIN;
+    // one long stroke puts millions of edges on one draw: reduce inside the block when it is uniform
+    __shared__ uint32_t d0;
+    __shared__ int32_t  red[4][8];
+    if (threadIdx.x == 0) d0 = edge_draw[min((uint64_t)blockIdx.x * blockDim.x, n_edges - 1)];
+    __syncthreads();
+    bool uniform = __syncthreads_and(d == d0 || i >= n_edges);
+    if (uniform) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = mnx; red[1][threadIdx.x >> 5] = mny; red[2][threadIdx.x >> 5] = mxx; red[3][threadIdx.x >> 5] = mxy;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; w++) {
+                mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
+            }
+            if (mnx <= mxx) {
+                atomicMin(&bbox[4 * d0], mnx); atomicMin(&bbox[4 * d0 + 1], mny); atomicMax(&bbox[4 * d0 + 2], mxx); atomicMax(&bbox[4 * d0 + 3], mxy);
+            }
+        }
+    } else if (ok) {
+        atomicMin(&bbox[4 * d], mnx); atomicMin(&bbox[4 * d + 1], mny); atomicMax(&bbox[4 * d + 2], mxx); atomicMax(&bbox[4 * d + 3], mxy);
+    }
+}
+void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s) {
+    draw_bbox_init_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, n_draws);
+    VKB_LAUNCHED();
+    if (!n_edges) return;
+    draw_bbox_k<<<vkb_div_up(n_edges, 256), 256, 0, s>>>(edges, edge_draw, n_edges, draw_bbox);
+    VKB_LAUNCHED();
+}
+
+__device__ __forceinline__ int32_t floor_div(int32_t a, int32_t b) {  // b > 0
+    int32_t q = a / b;
+    return (a % b < 0) ? q - 1 : q;
+}
+// tile rectangle of each draw (clipped to the surface) and its path-tile / row counts packed as lo | hi<<32
+__global__ void draw_rects_k(const int32_t *bbox, uint32_t n_draws, SurfaceDesc sd, int32_t *rect, unsigned long long *counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_draws) return;
+    int32_t mnx = bbox[4 * i], mny = bbox[4 * i + 1], mxx = bbox[4 * i + 2], mxy = bbox[4 * i + 3];
+    int32_t tx0 = 0, ty0 = 0, tw = 0, th = 0;
+    if (mnx <= mxx && mxx >= 0 && mxy >= 0 && mnx < (int32_t)sd.width * 256 && mny < (int32_t)sd.height * 256) {
+        tx0         = max(floor_div(mnx, VKB_TILE_FX), 0);
+        ty0         = max(floor_div(mny, VKB_TILE_FX), 0);
+        int32_t tx1 = min(floor_div(mxx, VKB_TILE_FX), (int32_t)sd.tiles_x - 1);
+        int32_t ty1 = min(floor_div(mxy, VKB_TILE_FX), (int32_t)sd.tiles_y - 1);
+        tw = tx1 - tx0 + 1; th = ty1 - ty0 + 1;
+        if (tw <= 0 || th <= 0) tw = th = 0;
+    }
+    rect[4 * i] = tx0; rect[4 * i + 1] = ty0; rect[4 * i + 2] = tw; rect[4 * i + 3] = th;
+    counts[i] = (unsigned long long)((uint32_t)(tw * th)) | ((unsigned long long)(uint32_t)th << 32);
+}
+void vkb_launch_draw_rects(const int32_t *draw_bbox, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect, unsigned long long *tile_row_counts, cudaStream_t s) {
+    draw_rects_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, n_draws, sd, draw_rect, tile_row_counts);
+    VKB_LAUNCHED();
+}
+__global__ void split_bases_k(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lo[i] = (uint32_t)(packed[i] & 0xffffffffull);
+    hi[i] = (uint32_t)(packed[i] >> 32);
+}
+void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s) {
+    if (!n) return;
+    split_bases_k<<<vkb_div_up(n, 256), 256, 0, s>>>(packed, n, lo, hi);
+    VKB_LAUNCHED();
+}
+
+// ---- binning: walk the tile rows an edge touches ----
+struct EdgeWalk {
+    int32_t r0, r1;  // tile rows (clamped to the draw rectangle), r0 > r1 when nothing
+};
+// first absolute tile column whose virtual sample column X0+1/2 is at or right of the edge at height Y0+1/2
+__device__ __forceinline__ long long backdrop_first_col(const vkb_edge &e, int32_t Y0) {
+    long long dx = (long long)e.x1 - e.x0, dy = (long long)e.y1 - e.y0;
+    long long num = dx * (2ll * Y0 + 1 - 2ll * e.y0);  // doubled coordinates: Q = 2*x0 + num/dy
+    // ceil(num / dy) exactly
+    long long q = num / dy, r = num % dy;
+    if (r != 0 && ((r < 0) == (dy < 0))) q++;
+    long long Qc = 2ll * e.x0 + q;            // smallest integer L2 with L2 >= Q
+    // L2 = 2*4096*tc + 1 >= Qc  <=>  tc >= ceil((Qc - 1) / 8192)
+    long long n2 = Qc - 1, t = n2 / 8192;
+    if (n2 % 8192 > 0) t++;                   // (for negative n2 truncation already rounds toward +inf)
+    return t;
+}
+template <class F> __device__ __forceinline__ void for_each_tile_of_edge(const vkb_edge &e, const int32_t *rect, F &&f_tile, bool want_backdrop,
+                                                                        int32_t *pt_backdrop, uint32_t ptbase) {
+    const int32_t tx0 = rect[0], ty0 = rect[1], tw = rect[2], th = rect[3];
+    if (tw <= 0) return;
+    const int32_t ymin = min(e.y0, e.y1), ymax = max(e.y0, e.y1);
+    int32_t r0 = max(floor_div(ymin, VKB_TILE_FX), ty0), r1 = min(floor_div(ymax, VKB_TILE_FX), ty0 + th - 1);
+    const double dxdy = (e.y1 != e.y0) ? ((double)e.x1 - (double)e.x0) / ((double)e.y1 - (double)e.y0) : 0.0;
+    const int    sgn  = e.y1 > e.y0 ? 1 : -1;
+    for (int32_t r = r0; r <= r1; r++) {
+        const int32_t Y0 = r * VKB_TILE_FX;
+        if (want_backdrop && e.y0 != e.y1 && ((e.y0 <= Y0) != (e.y1 <= Y0))) {
+            long long tc = backdrop_first_col(e, Y0);
+            if (tc < tx0) tc = tx0;
+            if (tc < tx0 + tw) atomicAdd(&pt_backdrop[ptbase + (uint32_t)(r - ty0) * tw + (uint32_t)(tc - tx0)], sgn);
+        }
+        // conservative column range of the edge inside this row band
+        double xa, xb;
+        if (e.y0 == e.y1) { xa = e.x0; xb = e.x1; }
+        else {
+            double ya = max(ymin, Y0), yb = min(ymax, Y0 + VKB_TILE_FX);
+            xa = (double)e.x0 + (ya - (double)e.y0) * dxdy;
+            xb = (double)e.x0 + (yb - (double)e.y0) * dxdy;
+        }
+        double  xl = floor(fmin(xa, xb)) - 1.0, xh = ceil(fmax(xa, xb)) + 1.0;
+        int32_t c0 = (int32_t)fmax(floor(xl / VKB_TILE_FX), (double)tx0), c1 = (int32_t)fmin(floor(xh / VKB_TILE_FX), (double)(tx0 + tw - 1));
+        for (int32_t c = c0; c <= c1; c++) f_tile(ptbase + (uint32_t)(r - ty0) * tw + (uint32_t)(c - tx0));
+    }
+}
+__global__ void __launch_bounds__(256) bin_count_k(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect,
+                                                  const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges) return;
+    vkb_edge e = edges[i];
+    if (edge_degenerate(e)) return;
+    uint32_t d = edge_draw[i];
+    for_each_tile_of_edge(e, draw_rect + 4 * d, [&](uint32_t pt) { atomicAdd(&pt_count[pt], 1u); }, true, pt_backdrop, draw_ptbase[d]);
+}
+void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+                          uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s) {
+    if (!n_edges) return;
+    bin_count_k<<<vkb_div_up(n_edges, 256), 256, 0, s>>>(edges, edge_draw, n_edges, draw_rect, draw_ptbase, pt_count, pt_backdrop);
+    VKB_LAUNCHED();
+}
+__global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect,
+                                                    const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor,
+                                                    vkb_edge *tile_edges) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges) return;
+    vkb_edge e = edges[i];
+    if (edge_degenerate(e)) return;
+    uint32_t d = edge_draw[i];
+    for_each_tile_of_edge(
+        e, draw_rect + 4 * d,
+        [&](uint32_t pt) {
+            uint32_t p   = pt_slot[pt];
+            uint32_t pos = eoff[p] + atomicAdd(&cursor[p], 1u);
+            tile_edges[pos] = e;
+        },
+        false, nullptr, draw_ptbase[d]);
+}
+void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+                            const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s) {
+    if (!n_edges) return;
+    bin_scatter_k<<<vkb_div_up(n_edges, 256), 256, 0, s>>>(edges, edge_draw, n_edges, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges);
+    VKB_LAUNCHED();
+}
+
+// ---- backdrop: inclusive prefix sum along every path-tile row; one warp per row, grid-stride over rows ----
+__global__ void __launch_bounds__(256) backdrop_prefix_k(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase,
+                                                        uint32_t n_draws, const unsigned long long *totals, int32_t *pt_backdrop) {
+    const uint32_t n_rows = (uint32_t)(*totals >> 32);
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+        uint32_t d = find_job(draw_rowbase, n_draws, row);
+        // skip draws with zero rows that share the same base
+        while (d + 1 < n_draws && draw_rowbase[d + 1] <= row) d++;
+        uint32_t tw   = (uint32_t)draw_rect[4 * d + 2];
+        int32_t *p    = pt_backdrop + draw_ptbase[d] + (row - draw_rowbase[d]) * tw;
+        int32_t  carry = 0;
+        for (uint32_t c = 0; c < tw; c += 32) {
+            int32_t v = c + lane < tw ? p[c + lane] : 0;
+            int32_t s = warp_incl_scan(v) + carry;
+            if (c + lane < tw) p[c + lane] = s;
+            carry = __shfl_sync(0xffffffffu, s, 31);
+        }
+    }
+}
+void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
+                                const unsigned long long *totals, int32_t *pt_backdrop, cudaStream_t s) {
+    backdrop_prefix_k<<<148 * 4, 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, n_draws, totals, pt_backdrop);
+    VKB_LAUNCHED();
+}
+
+// ---- compaction of non-empty path-tiles and the per-tile ordered lists ----
+__global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, uint32_t *flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pt) return;
+    flags[i] = (pt_count[i] != 0 || pt_backdrop[i] != 0) ? 1u : 0u;
+}
+void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, uint32_t *flags, cudaStream_t s) {
+    if (!n_pt) return;
+    pt_flags_k<<<vkb_div_up(n_pt, 256), 256, 0, s>>>(pt_count, pt_backdrop, n_pt, flags);
+    VKB_LAUNCHED();
+}
+__global__ void pt_compact_k(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+                             uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pt || !flags[i]) return;
+    uint32_t d = find_job(draw_ptbase, n_draws, i);
+    while (d + 1 < n_draws && draw_ptbase[d + 1] <= i) d++;
+    uint32_t tw = (uint32_t)draw_rect[4 * d + 2], local = i - draw_ptbase[d];
+    uint32_t tx = (uint32_t)draw_rect[4 * d] + local % tw, ty = (uint32_t)draw_rect[4 * d + 1] + local / tw;
+    uint32_t p = flag_scan[i];
+    keys[p]    = ty * sd.tiles_x + tx;
+    vals[p]    = i;
+    pt_draw[p] = d;  // in compaction order == path-tile order; re-read through vals after the sort
+}
+void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+                           uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s) {
+    if (!n_pt) return;
+    pt_compact_k<<<vkb_div_up(n_pt, 256), 256, 0, s>>>(flags, flag_scan, n_pt, draw_rect, draw_ptbase, n_draws, sd, keys, vals, pt_draw);
+    VKB_LAUNCHED();
+}
+__global__ void sorted_counts_k(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_ne) return;
+    uint32_t pt   = vals[p];
+    sorted_cnt[p] = pt_count[pt];
+    pt_slot[pt]   = p;
+}
+void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot, cudaStream_t s) {
+    if (!n_ne) return;
+    sorted_counts_k<<<vkb_div_up(n_ne, 256), 256, 0, s>>>(vals, n_ne, pt_count, sorted_cnt, pt_slot);
+    VKB_LAUNCHED();
+}
+// pt_draw_by_flagpos: draw of the path-tile at compaction position flag_scan[pt] (pt_compact_k output)
+__global__ void headers_k(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
+                          const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, int4 *hdr, uint32_t *tile_first,
+                          uint32_t *tile_end) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_ne) return;
+    uint32_t pt = vals[p], key = keys[p];
+    hdr[p]      = make_int4((int)pt_draw_by_flagpos[flag_scan[pt]], pt_backdrop[pt], (int)eoff[p], (int)pt_count[pt]);
+    if (p == 0 || keys[p - 1] != key) tile_first[key] = p;
+    if (p == n_ne - 1 || keys[p + 1] != key) tile_end[key] = p + 1;
+}
+void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
+                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, int4 *hdr, uint32_t *tile_first,
+                        uint32_t *tile_end, cudaStream_t s) {
+    if (!n_ne) return;
+    headers_k<<<vkb_div_up(n_ne, 256), 256, 0, s>>>(keys, vals, n_ne, pt_draw_by_flagpos, flag_scan, pt_backdrop, pt_count, eoff, hdr, tile_first, tile_end);
+    VKB_LAUNCHED();
+}
+
+// ----------------------------------------------------------------------------------------------------
+// fine pass
+// ----------------------------------------------------------------------------------------------------
+template <int S> struct SamplePos;
+template <> struct SamplePos<1> { static __device__ __forceinline__ int x(int) { return 8; } static __device__ __forceinline__ int y(int) { return 8; } };
+template <> struct SamplePos<2> {
+    static __device__ __forceinline__ int x(int s) { return s == 0 ? 12 : 4; }
+    static __device__ __forceinline__ int y(int s) { return s == 0 ? 12 : 4; }
+};
+template <> struct SamplePos<4> {
+    static __device__ __forceinline__ int x(int s) { const int t[4] = {6, 14, 2, 10}; return t[s]; }
+    static __device__ __forceinline__ int y(int s) { const int t[4] = {2, 6, 10, 14}; return t[s]; }
+};
+template <> struct SamplePos<8> {
+    static __device__ __forceinline__ int x(int s) { const int t[8] = {9, 7, 13, 5, 3, 1, 11, 15}; return t[s]; }
+    static __device__ __forceinline__ int y(int s) { const int t[8] = {5, 11, 9, 3, 13, 7, 15, 1}; return t[s]; }
+};
+template <> struct SamplePos<16> {
+    static __device__ __forceinline__ int x(int s) { const int t[16] = {9, 7, 5, 12, 3, 10, 13, 11, 6, 8, 4, 2, 0, 15, 14, 1}; return t[s]; }
+    static __device__ __forceinline__ int y(int s) { const int t[16] = {9, 5, 10, 7, 6, 13, 11, 3, 14, 1, 2, 12, 8, 4, 15, 0}; return t[s]; }
+};
+
+__device__ __forceinline__ float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+__device__ __forceinline__ float smoothstepf(float e0, float e1, float x) {
+    float t = clamp01((x - e0) / (e1 - e0));
+    return t * t * (3.0f - 2.0f * t);
+}
+__device__ __forceinline__ void mix4(float *c, const float *b, float t) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = c[k] * (1.0f - t) + b[k] * t;
+}
+// shaders/vkvg_main.frag:68-157 (SOLID / LINEAR / RADIAL) at the pixel centre; identical arithmetic to
+// oracle/vkvg_oracle.c: eval_paint
+__device__ void eval_paint(uint32_t pattern, const vkb_gradient *g, float W, float H, uint32_t solid, float opacity, float fx, float fy, float out[4]) {
+    float c[4];
+    if (pattern == VKB_PAT_LINEAR) {
+        float p0x = g->cp[0][0] / W, p0y = g->cp[0][1] / H;
+        float p1x = g->cp[0][2] / W, p1y = g->cp[0][3] / H;
+        float px = fx / W, py = fy / H;
+        float dx = p1x - p0x, dy = p1y - p0y;
+        float l  = sqrtf(dx * dx + dy * dy);
+        float ux = dx / l, uy = dy / l;
+        float dist;
+        if (uy == 0.0f) {
+            if (ux < 0.0f) dist = -(px - p0x) / l;
+            else dist = (px - p0x) / l;
+        } else {
+            float m  = -ux / uy;
+            float bb = p0y - m * p0x;
+            dist     = ((py - m * px - bb) / sqrtf(1.0f + m * m)) / l;
+            if (uy < 0.0f) dist = -dist;
+        }
+        for (int k = 0; k < 4; k++) c[k] = g->colors[0][k];
+        mix4(c, g->colors[1], smoothstepf(g->stops[0], g->stops[1], dist));
+        for (uint32_t i = 1; i + 1 < g->count; ++i) mix4(c, g->colors[i + 1], smoothstepf(g->stops[i], g->stops[i + 1], dist));
+    } else if (pattern == VKB_PAT_RADIAL) {
+        float px = fx / W, py = fy / H;
+        float c0x = g->cp[0][0] / W, c0y = g->cp[0][1] / H;
+        float c1x = g->cp[1][0] / W, c1y = g->cp[1][1] / H;
+        float r0 = g->cp[0][2] / W, r1 = g->cp[1][2] / W;
+        float gradLength = 1.0f;
+        float dfx = c0x - c1x, dfy = c0y - c1y;
+        float rx = px - c0x, ry = py - c0y;
+        float rl = sqrtf(rx * rx + ry * ry);
+        float rdx = rx / rl, rdy = ry / rl;
+        float a    = rdx * rdx + rdy * rdy;
+        float b    = 2.0f * (rdx * dfx + rdy * dfy);
+        float cc   = (dfx * dfx + dfy * dfy) - r1 * r1;
+        float disc = b * b - 4.0f * a * cc;
+        if (disc >= 0.0f) {
+            float t   = (-b + sqrtf(fabsf(disc))) / (2.0f * a);
+            float prx = c0x + rdx * t, pry = c0y + rdy * t;
+            float ex = prx - c0x, ey = pry - c0y;
+            gradLength = sqrtf(ex * ex + ey * ey) - r0;
+        }
+        float grad = (rl - r0) / gradLength;
+        for (int k = 0; k < 4; k++) c[k] = g->colors[0][k];
+        mix4(c, g->colors[1], smoothstepf(g->stops[0], g->stops[1], grad));
+        for (uint32_t i = 2; i < g->count; i++) mix4(c, g->colors[i], smoothstepf(g->stops[i - 1], g->stops[i], grad));
+    } else {
+        c[0] = (float)(solid & 0xFF) / 255.0f;
+        c[1] = (float)((solid >> 8) & 0xFF) / 255.0f;
+        c[2] = (float)((solid >> 16) & 0xFF) / 255.0f;
+        c[3] = (float)((solid >> 24) & 0xFF) / 255.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = c[k] * opacity;
+}
+__device__ __forceinline__ uint32_t unorm8(float v) {
+    float q = v * 255.0f + 0.5f;
+    if (!(q > 0.0f)) return 0;
+    if (q >= 255.5f) return 255;
+    return (uint32_t)q;
+}
+// premultiplied OVER per channel with UNORM8 store, src/vkvg_device_internal.c:203-209
+__device__ __forceinline__ uint32_t blend_over(uint32_t dst, const float s[4]) {
+    uint32_t out = 0;
+    float    ia  = 1.0f - s[3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float d = (float)((dst >> (8 * k)) & 0xFF) / 255.0f;
+        float r = s[k] + d * ia;
+        out |= unorm8(r) << (8 * k);
+    }
+    return out;
+}
+
+template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
+    const uint32_t tile  = blockIdx.x;
+    const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
+    if (first == end) return;  // no draw of this batch touches the tile: the stored pixels stay as they are
+    const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
+    const uint32_t px = tx * VKB_TILE + (threadIdx.x & 15), py = ty * VKB_TILE + (threadIdx.x >> 4);
+    const bool     inside = px < a.sd.width && py < a.sd.height;
+    const size_t   pix    = (size_t)py * a.sd.width + px;
+
+    uint32_t col[S];
+    {
+        uint32_t c = (!a.dst_is_clear && inside) ? a.image[pix] : 0u;
+#pragma unroll
+        for (int s = 0; s < S; s++) col[s] = c;
+    }
+    const int32_t   X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
+    const long long L2 = 2ll * X0 + 1, C2 = 2ll * Y0 + 1;
+    int32_t         sx[S], sy[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        sx[s] = (int32_t)px * 256 + SamplePos<S>::x(s) * 16;
+        sy[s] = (int32_t)py * 256 + SamplePos<S>::y(s) * 16;
+    }
+
+    for (uint32_t p = first; p < end; p++) {
+        const int4 h = a.hdr[p];
+        int32_t    w[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) w[s] = h.y;
+        const vkb_edge *ep = a.tile_edges + (uint32_t)h.z;
+        for (uint32_t k = 0; k < (uint32_t)h.w; k++) {
+            // coordinates are clamped to +-2^28 by vs_snap, so every difference fits int32 and every product
+            // below is one 32x32->64 multiply (IMAD.WIDE)
+            const int4      ev = __ldg((const int4 *)(ep + k));
+            const int32_t   ax = ev.x, ay = ev.y, bx = ev.z, by = ev.w;
+            const int32_t   dx = bx - ax, dy = by - ay;
+            const int       sdy = dy > 0 ? 1 : (dy < 0 ? -1 : 0), sdx = dx > 0 ? 1 : (dx < 0 ? -1 : 0);
+            const bool      crossL = (ax <= X0) != (bx <= X0);
+            const long long kL     = (long long)dy * (int32_t)(L2 - 2ll * ax);  // E2(L, y) = 2*dx*(y - ay) - kL
+            int             belowC = 0;
+            if (crossL) {
+                long long EC = (long long)dx * (int32_t)(C2 - 2ll * ay) - kL;
+                belowC       = (sdx > 0 ? EC > 0 : EC < 0) || (EC == 0 && (dy == 0 || sdx != sdy));
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int32_t   ys = sy[s];
+                const long long t  = (long long)dx * (ys - ay);
+                const long long EL = 2 * t - kL;
+                if ((ay <= ys) != (by <= ys)) {  // H term: crossing strictly right of L and at or left of the sample
+                    const long long Es = t - (long long)dy * (sx[s] - ax);
+                    const int       ls = dy > 0 ? (Es <= 0) : (Es >= 0);
+                    const int       lL = dy > 0 ? (EL <= 0) : (EL >= 0);
+                    w[s] += sdy * (ls - lL);
+                }
+                if (crossL) {  // V term
+                    const int below = (sdx > 0 ? EL > 0 : EL < 0) || (EL == 0 && (dy == 0 || sdx != sdy));
+                    w[s] -= sdx * (below - belowC);
+                }
+            }
+        }
+        if (a.winding_out && (uint32_t)h.x == a.winding_draw && inside) {
+#pragma unroll
+            for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
+        }
+        const vkb_paint pt      = a.paints[h.x];
+        const uint32_t  rule    = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
+        uint32_t        any     = 0;
+        int32_t         n[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            int32_t v = w[s];
+            n[s]      = rule == VKB_RULE_EVEN_ODD ? (v & 1) : (rule == VKB_RULE_NON_ZERO ? (v != 0) : (v < 0 ? -v : v));
+            any |= (uint32_t)n[s];
+        }
+        if (any) {
+            float src[4];
+            eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src);
+            const bool opaque = src[3] >= 1.0f;  // repeated OVER of an opaque source is idempotent
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                int32_t reps = opaque ? (n[s] ? 1 : 0) : n[s];
+                for (int32_t r = 0; r < reps; r++) col[s] = blend_over(col[s], src);
+            }
+        }
+    }
+    if (inside) {
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int s = 0; s < S; s++) sum += (col[s] >> (8 * k)) & 0xFF;
+            out |= ((sum + S / 2) / S) << (8 * k);
+        }
+        a.image[pix] = out;
+    }
+}
+void vkb_launch_fine(const FineArgs &a, cudaStream_t s) {
+    uint32_t tiles = a.sd.tiles_x * a.sd.tiles_y;
+    if (!tiles) return;
+    switch (a.sd.samples) {
+    case 1: fine_k<1><<<tiles, 256, 0, s>>>(a); break;
+    case 2: fine_k<2><<<tiles, 256, 0, s>>>(a); break;
+    case 4: fine_k<4><<<tiles, 256, 0, s>>>(a); break;
+    case 8: fine_k<8><<<tiles, 256, 0, s>>>(a); break;
+    case 16: fine_k<16><<<tiles, 256, 0, s>>>(a); break;
+    default: return;
+    }
+    VKB_LAUNCHED();
+}
+
+// vkvg_surface_write_to_png / _to_memory un-premultiply in double with truncation (src/vkvg_surface.c:371-382)
+__global__ void unpremultiply_k(const uint32_t *image, uint64_t n, uint32_t *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = image[i], a = p >> 24, r = 0;
+    double   alpha = (double)a / 255.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double v = (double)((p >> (8 * k)) & 0xFF) / alpha;
+        uint32_t q = (v == v && v < 2147483648.0) ? ((uint32_t)(int32_t)v & 0xFF) : 0u;
+        r |= q << (8 * k);
+    }
+    out[i] = r | (a << 24);
+}
+void vkb_launch_unpremultiply(const uint32_t *image, uint64_t n_pixels, uint32_t *out, cudaStream_t s) {
+    if (!n_pixels) return;
+    unpremultiply_k<<<vkb_div_up(n_pixels, 256), 256, 0, s>>>(image, n_pixels, out);
+    VKB_LAUNCHED();
+}

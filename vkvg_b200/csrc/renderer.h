@@ -1,0 +1,63 @@
+// Host-side C++ interface of the CUDA pipeline, used by the C API layer (vkvg_api.cpp).
+#pragma once
+#include <stdint.h>
+#include <vector>
+#include "vkb_types.h"
+
+// One flush worth of recorded work (host memory).  See vkb_types.h for the record formats.
+struct vkb_batch {
+    std::vector<uint32_t>     elem_hdr;
+    std::vector<float>        elem_data;
+    std::vector<vkb_subpath>  subpaths;
+    std::vector<vkb_draw>     draws;
+    std::vector<vkb_gradient> grads;
+    std::vector<float>        dashes;
+    void clear() {
+        elem_hdr.clear(); elem_data.clear(); subpaths.clear(); draws.clear(); grads.clear(); dashes.clear();
+    }
+    size_t upload_bytes() const {
+        return elem_hdr.size() * 4 + elem_data.size() * 4 + subpaths.size() * sizeof(vkb_subpath) + draws.size() * sizeof(vkb_draw) +
+               grads.size() * sizeof(vkb_gradient) + dashes.size() * 4;
+    }
+};
+
+// Optional host-side copies of intermediate results (parity tests only; null members are skipped)
+struct vkb_capture {
+    std::vector<float>    *points    = nullptr;  // x,y per flattened point
+    std::vector<uint8_t>  *ptflags   = nullptr;
+    std::vector<uint32_t> *sp_first  = nullptr, *sp_count = nullptr;
+    std::vector<float>    *verts     = nullptr;  // stroke vertices x,y
+    std::vector<uint32_t> *inds      = nullptr;  // stroke indices (absolute into verts)
+    std::vector<int32_t>  *edges     = nullptr;  // x0,y0,x1,y1 fixed point
+    std::vector<uint32_t> *edge_draw = nullptr;
+    int32_t               *winding   = nullptr;  // width*height*samples, winding of draw `winding_draw`
+    uint32_t               winding_draw = 0;
+    bool                   geometry_only = false;  // stop before binning / fine
+};
+
+struct vkb_stats {            // filled by every render
+    uint64_t n_elems, n_points, n_fill_edges, n_stroke_items, n_verts, n_inds, n_edges, n_path_tiles, n_nonempty, n_tile_edges;
+    float    ms_total, ms_fine;  // CUDA-event durations on the device stream
+    uint64_t h2d_bytes;
+};
+
+struct vkb_device_impl;
+struct vkb_surface_impl;
+
+vkb_device_impl *vkb_device_open(int ordinal);  // nullptr when no usable CUDA device
+void             vkb_device_close(vkb_device_impl *d);
+int              vkb_device_failed(vkb_device_impl *d);
+void             vkb_device_sync(vkb_device_impl *d);
+
+vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h);
+void              vkb_surface_free(vkb_surface_impl *s);
+void              vkb_surface_clear(vkb_surface_impl *s);
+// premultiplied RGBA8 rows, or un-premultiplied as vkvg_surface_write_to_memory does; synchronous
+int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply);
+const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s);
+
+// upload `b` and render it onto `s`.  Returns 0 on success.
+int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const vkb_batch &b, vkb_capture *cap, vkb_stats *stats);
+// upload only (bench: inputs resident in HBM); then vkb_render_resident re-runs the pipeline on that batch
+int vkb_upload(vkb_device_impl *d, const vkb_batch &b);
+int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, vkb_capture *cap, vkb_stats *stats);

@@ -1,0 +1,395 @@
+// Stroke expansion kernels: flattened points -> stroke triangles (vertices + indices).
+//
+// Replaces the serial loop of the reference (_stroke_preserve src/vkvg_context.c:822-948, _build_vb_step
+// src/vkvg_context_internal.c:924-1163, _draw_stoke_cap :1165-1239, _draw_dashed_segment :1240-1264).
+// The reference's output order depends on a running vertex counter and, for dashes, on a carried dash
+// phase.  Here every point of every stroked sub-path is one work item: a count pass reproduces every
+// branch (including the float `while` loops that size round joins / caps), a prefix scan turns counts into
+// vertex / index offsets, and an emit pass writes the same vertices in the same order.  Because vertex
+// numbering is contiguous, the reference's forward references ("closing quad of a join uses the next
+// join's first two vertices") are simply base + own_count (+1).  The dash phase comes from a
+// double-precision prefix scan of the float segment lengths instead of a carried float.
+#include "pipeline.h"
+#include <float.h>
+
+#define PIF 3.14159265358979323846f
+#define PIF_2 1.57079632679489661923f
+#define EQUF(a, b) (fabsf((a) - (b)) <= FLT_EPSILON)
+
+struct v2 {
+    float x, y;
+};
+__device__ __forceinline__ v2    mk(float x, float y) { v2 r = {x, y}; return r; }
+__device__ __forceinline__ v2    v2add(v2 a, v2 b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ v2    v2sub(v2 a, v2 b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ v2    v2mul(v2 a, float m) { return mk(a.x * m, a.y * m); }
+__device__ __forceinline__ v2    v2div(v2 a, float m) { return mk(a.x / m, a.y / m); }
+__device__ __forceinline__ v2    v2perp(v2 a) { return mk(a.y, -a.x); }
+__device__ __forceinline__ float v2len(v2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ v2    v2norm(v2 a) { float m = sqrtf(a.x * a.x + a.y * a.y); return mk(a.x / m, a.y / m); }
+__device__ __forceinline__ v2    ld(const float2 *p, uint32_t i) { float2 f = p[i]; return mk(f.x, f.y); }
+
+template <bool EMIT> struct Out {
+    float2  *v;
+    uint32_t *idx;
+    uint32_t vbase, ibase;  // absolute offsets of this item
+    uint32_t nv, ni;
+    __device__ __forceinline__ uint32_t cur() const { return vbase + nv; }  // == reference's (vertCount - curVertOffset)
+    __device__ __forceinline__ void     vert(v2 p) {
+        if (EMIT) v[vbase + nv] = make_float2(p.x, p.y);
+        nv++;
+    }
+    __device__ __forceinline__ void tri(uint32_t a, uint32_t b, uint32_t c) {
+        if (EMIT) {
+            idx[ibase + ni]     = a;
+            idx[ibase + ni + 1] = b;
+            idx[ibase + ni + 2] = c;
+        }
+        ni += 3;
+    }
+    __device__ __forceinline__ void rect(uint32_t i) {  // _add_tri_indices_for_rect, internal.c:341-354
+        tri(i, i + 2, i + 1);
+        tri(i + 1, i + 2, i + 3);
+    }
+};
+
+struct StrokeParams {
+    float    hw, lhMax, arcStep;
+    uint32_t join, cap;
+};
+
+// one join, internal.c:924-1163.  Returns the reference's `inverse` flag.
+template <bool EMIT> __device__ bool build_join(Out<EMIT> &o, const StrokeParams &sp, v2 pL, v2 p0, v2 pR, bool isCurve) {
+    v2    v0 = v2sub(p0, pL), v1 = v2sub(pR, p0);
+    float length_v0 = v2len(v0), length_v1 = v2len(v1);
+    if (length_v0 < FLT_EPSILON || length_v1 < FLT_EPSILON) return false;
+    v2    v0n = v2div(v0, length_v0), v1n = v2div(v1, length_v1);
+    float dot = (v0n.x * v1n.x) + (v0n.y * v1n.y);
+    float det = v0n.x * v1n.y - v0n.y * v1n.x;
+    if (EQUF(dot, 1.0f)) return false;
+    uint32_t idx = o.cur();
+    if (EQUF(dot, -1.0f)) {  // cusp
+        v2 vPerp = v2mul(v2perp(v0n), sp.hw);
+        o.vert(v2add(p0, vPerp));
+        o.vert(v2sub(p0, vPerp));
+        o.tri(idx, idx + 1, idx + 2);
+        o.tri(idx, idx + 2, idx + 3);
+        return true;
+    }
+    v2    bisec_n = v2norm(v2add(v0n, v1n));
+    float alpha   = acosf(dot);
+    if (det < 0) alpha = -alpha;
+    float halfAlpha    = alpha / 2.f;
+    float cosHalfAlpha = cosf(halfAlpha);
+    float lh           = sp.hw / cosHalfAlpha;
+    v2    bisec_n_perp = v2perp(bisec_n);
+    float rlh          = lh;
+    if (dot < 0.f) rlh = fminf(rlh, fminf(length_v0, length_v1));
+    v2 bisec = v2mul(bisec_n_perp, rlh);
+    v2 in_pos, out_pos;
+    if (rlh < lh) {
+        v2    vnPerp  = length_v0 < length_v1 ? v2perp(v1n) : v2perp(v0n);
+        v2    vHwPerp = v2mul(vnPerp, sp.hw);
+        float lbc     = cosHalfAlpha * rlh;  // a double temporary in the reference, but computed and consumed as float
+        if (det < 0.f) {
+            in_pos  = v2add(v2add(v2mul(vnPerp, -lbc), v2add(p0, bisec)), vHwPerp);
+            out_pos = v2sub(p0, v2mul(bisec_n_perp, lh));
+        } else {
+            in_pos  = v2sub(v2add(v2mul(vnPerp, lbc), v2sub(p0, bisec)), vHwPerp);
+            out_pos = v2add(p0, v2mul(bisec_n_perp, lh));
+        }
+    } else {
+        if (det < 0.0f) { in_pos = v2add(p0, bisec); out_pos = v2sub(p0, bisec); }
+        else { in_pos = v2sub(p0, bisec); out_pos = v2add(p0, bisec); }
+    }
+    uint32_t join = sp.join;
+    if (isCurve) join = dot < 0.8f ? 1u /*ROUND*/ : 0u /*MITER*/;
+    if (join == 0) {  // VKVG_LINE_JOIN_MITER
+        if (lh > sp.lhMax) {
+            float x         = (lh - sp.lhMax) * cosHalfAlpha;
+            v2    bisecPerp = v2mul(bisec_n, x);
+            bisec           = v2mul(bisec_n_perp, sp.lhMax);
+            if (det < 0) {
+                o.vert(in_pos);
+                v2 p = v2sub(p0, bisec);
+                o.vert(v2sub(p, bisecPerp));
+                o.vert(v2add(p, bisecPerp));
+                o.tri(idx, idx + 2, idx + 1);
+                o.tri(idx + 2, idx + 4, idx);
+                o.tri(idx, idx + 3, idx + 4);
+                return true;
+            } else {
+                v2 p = v2add(p0, bisec);
+                o.vert(v2sub(p, bisecPerp));
+                o.vert(in_pos);
+                o.vert(v2add(p, bisecPerp));
+                o.tri(idx, idx + 2, idx + 1);
+                o.tri(idx + 2, idx + 3, idx + 1);
+                o.tri(idx + 1, idx + 3, idx + 4);
+                return false;
+            }
+        } else {
+            if (det < 0) { o.vert(in_pos); o.vert(out_pos); }
+            else { o.vert(out_pos); o.vert(in_pos); }
+            o.rect(idx);
+            return false;
+        }
+    } else {
+        v2 vp = v2perp(v0n);
+        if (det < 0) {
+            o.vert((dot < 0 && rlh < lh) ? in_pos : v2add(p0, bisec));
+            o.vert(v2sub(p0, v2mul(vp, sp.hw)));
+        } else {
+            o.vert(v2add(p0, v2mul(vp, sp.hw)));
+            o.vert((dot < 0 && rlh < lh) ? in_pos : v2sub(p0, bisec));
+        }
+        if (join == 2) {  // BEVEL
+            if (det < 0) { o.tri(idx, idx + 2, idx + 1); o.tri(idx + 2, idx + 4, idx + 0); o.tri(idx, idx + 3, idx + 4); }
+            else { o.tri(idx, idx + 2, idx + 1); o.tri(idx + 2, idx + 3, idx + 1); o.tri(idx + 1, idx + 3, idx + 4); }
+        } else if (join == 1) {  // ROUND
+            float a = acosf(vp.x);
+            if (vp.y < 0) a = -a;
+            if (det < 0) {
+                a += PIF;
+                float a1 = a + alpha;
+                a -= sp.arcStep;
+                while (a > a1) { o.vert(mk(cosf(a) * sp.hw + p0.x, sinf(a) * sp.hw + p0.y)); a -= sp.arcStep; }
+            } else {
+                float a1 = a + alpha;
+                a += sp.arcStep;
+                while (a < a1) { o.vert(mk(cosf(a) * sp.hw + p0.x, sinf(a) * sp.hw + p0.y)); a += sp.arcStep; }
+            }
+            uint32_t p0Idx = o.cur();
+            o.tri(idx, idx + 2, idx + 1);
+            if (det < 0) {
+                for (uint32_t p = idx + 2; p < p0Idx; p++) o.tri(p, p + 1, idx);
+                o.tri(p0Idx, p0Idx + 2, idx);
+                o.tri(idx, p0Idx + 1, p0Idx + 2);
+            } else {
+                for (uint32_t p = idx + 2; p < p0Idx; p++) o.tri(p, p + 1, idx + 1);
+                o.tri(p0Idx, p0Idx + 1, idx + 1);
+                o.tri(idx + 1, p0Idx + 1, p0Idx + 2);
+            }
+        }
+        vp = v2mul(v2perp(v1n), sp.hw);
+        o.vert(det < 0 ? v2sub(p0, vp) : v2add(p0, vp));
+    }
+    return (det < 0);
+}
+
+// caps, internal.c:1165-1239
+template <bool EMIT> __device__ void draw_cap(Out<EMIT> &o, const StrokeParams &sp, v2 p0, v2 n, bool isStart) {
+    uint32_t firstIdx = o.cur();
+    if (isStart) {
+        v2 vhw = v2mul(n, sp.hw);
+        if (sp.cap == 2) p0 = v2sub(p0, vhw);  // SQUARE
+        vhw = v2perp(vhw);
+        if (sp.cap == 1) {  // ROUND
+            float a = acosf(n.x) + PIF_2;
+            if (n.y < 0) a = PIF - a;
+            float a1 = a + PIF;
+            a += sp.arcStep;
+            while (a < a1) { o.vert(mk(cosf(a) * sp.hw + p0.x, sinf(a) * sp.hw + p0.y)); a += sp.arcStep; }
+            uint32_t p0Idx = o.cur();
+            for (uint32_t p = firstIdx; p < p0Idx; p++) o.tri(p0Idx + 1, p, p + 1);
+            firstIdx = p0Idx;
+        }
+        o.vert(v2add(p0, vhw));
+        o.vert(v2sub(p0, vhw));
+        o.rect(firstIdx);
+    } else {
+        v2 vhw = v2mul(n, sp.hw);
+        if (sp.cap == 2) p0 = v2add(p0, vhw);
+        vhw = v2perp(vhw);
+        o.vert(v2add(p0, vhw));
+        o.vert(v2sub(p0, vhw));
+        firstIdx = o.cur();
+        if (sp.cap == 1) {
+            float a = acosf(n.x) + PIF_2;
+            if (n.y < 0) a = PIF - a;
+            float a1 = a - PIF;
+            a -= sp.arcStep;
+            while (a > a1) { o.vert(mk(cosf(a) * sp.hw + p0.x, sinf(a) * sp.hw + p0.y)); a -= sp.arcStep; }
+            uint32_t p0Idx = o.cur() - 1;
+            for (uint32_t p = firstIdx - 1; p < p0Idx; p++) o.tri(p + 1, p, firstIdx - 2);
+        }
+    }
+}
+
+// ---- dash bookkeeping in exact (double) arc length --------------------------------------------------
+struct DashPat {
+    float  d[VKB_MAX_DASHES];
+    double pre[VKB_MAX_DASHES + 1];  // pre[j] = d[0]+..+d[j-1]; pre[n] = total
+    int    n;
+    double off0;  // fmodf(dashOffset, total), vkvg_context.c:864-866
+};
+// number of dash boundaries strictly before arc length c (boundary m sits at off0 + (m/n)*tot + pre[m%n])
+__device__ __forceinline__ long long dash_count_before(const DashPat &dp, double c) {
+    double t = c - dp.off0;
+    if (!(t > 0.0)) return 0;
+    double    tot = dp.pre[dp.n];
+    long long P   = (long long)floor(t / tot);
+    double    r   = t - (double)P * tot;
+    if (r < 0.0) { P--; r += tot; }
+    if (r >= tot) { P++; r -= tot; }
+    int j = 0;
+    while (j < dp.n && dp.pre[j] < r) j++;
+    return P * dp.n + j;
+}
+__device__ __forceinline__ double dash_boundary_pos(const DashPat &dp, long long m) {
+    long long P = m / dp.n;
+    int       j = (int)(m - P * dp.n);
+    return dp.off0 + (double)P * dp.pre[dp.n] + dp.pre[j];
+}
+
+// job table entry for strokes
+struct StrokeJob {
+    uint32_t draw, first_point, n_points, flags;  // flags: VKB_SP_CLOSED
+    uint32_t item_base;                           // first work item (== point) of this job in the global item space
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128)
+stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws, const float *dash_table, const uint32_t *job_draw,
+               const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count,
+               const vkb_subpath *sps, const double *cum, uint32_t n_items, unsigned long long *counts, const unsigned long long *offsets,
+               float2 *verts, uint32_t *inds, uint32_t *job_inverse) {
+    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    // locate the job (sub-path of a stroke draw) this point belongs to: last j with job_base[j] <= item
+    uint32_t lo = 0, hi = n_jobs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (job_base[mid] <= item) lo = mid; else hi = mid;
+    }
+    const uint32_t j = lo, k = item - job_base[j];
+    const uint32_t s = job_sp[j];
+    const uint32_t first = sp_first[s], n = sp_count[s];
+    const bool     closed = sps[s].flags & VKB_SP_CLOSED;
+    const vkb_draw &d = draws[job_draw[j]];
+    StrokeParams   sp = {d.hw, d.lhMax, d.arcStep, d.join, d.cap};
+
+    Out<EMIT> o;
+    o.v = verts; o.idx = inds; o.nv = 0; o.ni = 0;
+    if (EMIT) {
+        unsigned long long off = offsets[item];
+        o.vbase = (uint32_t)(off & 0xffffffffull);
+        o.ibase = (uint32_t)(off >> 32);
+    } else
+        o.vbase = o.ibase = 0;
+
+    const float2 *P = pts + first;
+    if (n >= 2) {
+        if (d.dash_count == 0) {
+            if (closed) {
+                // join at every point; the one at the last point closes the loop (vkvg_context.c:917-932)
+                uint32_t iL = k == 0 ? n - 1 : k - 1, iR = k == n - 1 ? 0 : k + 1;
+                bool     inv = build_join(o, sp, ld(P, iL), ld(P, k), ld(P, iR), k == n - 1 ? false : (ptflags[first + k] != 0));
+                if (EMIT && k == n - 1) job_inverse[j] = inv;
+            } else if (k == 0) {
+                draw_cap(o, sp, ld(P, 0), v2norm(v2sub(ld(P, 1), ld(P, 0))), true);  // vkvg_context.c:871-873
+            } else if (k == n - 1) {
+                draw_cap(o, sp, ld(P, k), v2norm(v2sub(ld(P, k), ld(P, k - 1))), false);  // :934-935
+            } else {
+                build_join(o, sp, ld(P, k - 1), ld(P, k), ld(P, k + 1), ptflags[first + k] != 0);
+            }
+        } else {
+            // dashed: item k owns segment k -> k+1 (the closing segment for k == n-1 of a closed path) and,
+            // if it is the last segment, the tail cap (vkvg_context.c:898-916)
+            DashPat dp;
+            dp.n      = (int)d.dash_count;
+            dp.pre[0] = 0.0;
+            for (int i = 0; i < dp.n; i++) {
+                dp.d[i]       = dash_table[d.dash_first + i];
+                dp.pre[i + 1] = dp.pre[i] + (double)dp.d[i];
+            }
+            float totf = 0.f;
+            for (int i = 0; i < dp.n; i++) totf += dp.d[i];  // float accumulation as the reference, :858-859
+            dp.off0 = (double)fmodf(d.dash_offset, totf);
+            const double   c0       = cum[job_base[j]];
+            const bool     has_seg  = (k + 1 < n) || closed;
+            const uint32_t last_seg = closed ? n - 1 : n - 2;
+            if (has_seg) {
+                const double ck = cum[item] - c0, ck1 = cum[item + 1] - c0;
+                long long    m0 = k == 0 ? 0 : dash_count_before(dp, ck);
+                long long    m1 = dash_count_before(dp, ck1);
+                uint32_t     iL = k == 0 ? n - 1 : k - 1, iR = k == n - 1 ? 0 : k + 1;  // str.iL = lastPathPointIdx, :867
+                v2           p = ld(P, k), pR = ld(P, iR);
+                if (m0 & 1)  // inside a dash at the segment start: !dashOn, internal.c:1245
+                    build_join(o, sp, ld(P, iL), p, pR, k == n - 1 ? false : (ptflags[first + k] != 0));
+                v2 dvec = v2sub(pR, p);
+                v2 nrm  = v2norm(dvec);
+                for (long long m = m0; m < m1; m++) {
+                    float off = (float)(dash_boundary_pos(dp, m) - ck);
+                    draw_cap(o, sp, v2add(p, v2mul(nrm, off)), nrm, (m & 1) == 0);
+                }
+                if (k == last_seg && (m1 & 1)) {
+                    int   cur  = (int)(m1 % dp.n);
+                    int   prev = cur - 1 < 0 ? dp.n - 1 : cur - 1;  // the reference reads dashes[-1] here for odd counts (UB)
+                    float curOff = (float)(dash_boundary_pos(dp, m1) - ck1);
+                    float mlen   = fminf(dp.d[prev] - curOff, dp.d[cur]);
+                    draw_cap(o, sp, v2sub(pR, v2mul(nrm, mlen)), nrm, false);
+                }
+            }
+        }
+    }
+    if (!EMIT) counts[item] = (unsigned long long)o.nv | ((unsigned long long)o.ni << 32);
+}
+
+// float segment lengths for the dash phase scan (one per stroke item; 0 where there is no segment)
+__global__ void stroke_seglen_k(const float2 *pts, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first,
+                                const uint32_t *sp_count, const vkb_subpath *sps, uint32_t n_items, float *seglen) {
+    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item > n_items) return;
+    if (item == n_items) { seglen[item] = 0.f; return; }
+    uint32_t lo = 0, hi = n_jobs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (job_base[mid] <= item) lo = mid; else hi = mid;
+    }
+    uint32_t k = item - job_base[lo], s = job_sp[lo], first = sp_first[s], n = sp_count[s];
+    float    L = 0.f;
+    if (n >= 2) {
+        uint32_t iR = k + 1 < n ? k + 1 : ((sps[s].flags & VKB_SP_CLOSED) ? 0 : n);
+        if (iR < n) L = v2len(v2sub(ld(pts + first, iR), ld(pts + first, k)));
+    }
+    seglen[item] = L;
+}
+
+// closed, undashed sub-paths: redirect the forward references of the closing quad to the first two
+// vertices of the sub-path (vkvg_context.c:921-931)
+__global__ void stroke_patch_closed_k(const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
+                                      uint32_t n_jobs, const vkb_subpath *sps, const uint32_t *sp_count, const unsigned long long *offsets,
+                                      uint32_t n_items, unsigned long long total, const uint32_t *job_inverse, uint32_t *inds) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    uint32_t s = job_sp[j];
+    if (!(sps[s].flags & VKB_SP_CLOSED) || draws[job_draw[j]].dash_count != 0 || sp_count[s] < 2) return;
+    unsigned long long a = offsets[job_base[j]];
+    uint32_t           e = job_base[j] + sp_count[s];
+    unsigned long long b = e < n_items ? offsets[e] : total;
+    uint32_t           ia = (uint32_t)(a >> 32), ib = (uint32_t)(b >> 32), ii = (uint32_t)(a & 0xffffffffull);
+    if (ib - ia < 6) return;
+    uint32_t *t = inds + ib - 6;
+    if (job_inverse[j]) { t[1] = ii + 1; t[4] = ii + 1; t[5] = ii; }
+    else { t[1] = ii; t[4] = ii; t[5] = ii + 1; }
+}
+
+void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s) {
+    stroke_seglen_k<<<vkb_div_up(a.n_items + 1, 256), 256, 0, s>>>(a.pts, a.job_sp, a.job_base, a.n_jobs, a.sp_first, a.sp_count, a.sps, a.n_items, seglen);
+    VKB_LAUNCHED();
+}
+void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s) {
+    stroke_items_k<false><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
+                                                                   a.sp_first, a.sp_count, a.sps, a.cum, a.n_items, counts, nullptr, nullptr, nullptr, nullptr);
+    VKB_LAUNCHED();
+}
+void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, unsigned long long total, float2 *verts, uint32_t *inds,
+                            uint32_t *job_inverse, cudaStream_t s) {
+    stroke_items_k<true><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
+                                                                  a.sp_first, a.sp_count, a.sps, a.cum, a.n_items, nullptr, offsets, verts, inds, job_inverse);
+    VKB_LAUNCHED();
+    stroke_patch_closed_k<<<vkb_div_up(a.n_jobs, 128), 128, 0, s>>>(a.draws, a.job_draw, a.job_sp, a.job_base, a.n_jobs, a.sps, a.sp_count, offsets,
+                                                                   a.n_items, total, job_inverse, inds);
+    VKB_LAUNCHED();
+}

@@ -1,0 +1,87 @@
+// Plain-data records shared by the host recorder (vkvg_api.cpp) and the CUDA pipeline (pipeline.cu).
+// These are the host->device wire format of one flushed batch.
+#pragma once
+#include <stdint.h>
+
+// ---- path elements: what the host records instead of flattening on the CPU -------------------------
+// (the reference flattens in vkvg_curve_to / vkvg_arc on the calling thread, src/vkvg_context.c:394-566)
+// An element is a 32-bit header plus a payload of floats in a separate array:
+//   header = type | VKB_EL_CURVED | payload_offset << 3        (payload_offset counts floats)
+//   VKB_EL_POINT  payload {x, y}                      -> that point (move_to / line_to target, arc start/end, rectangle corner)
+//   VKB_EL_CUBIC  payload {x0,y0, x1,y1, x2,y2, x3,y3, tol} -> the recursion points followed by the end point
+//   VKB_EL_ARC    payload {xc, yc, radius, a_first, a_limit, step} -> interior points a_first, a_first+step, ... before a_limit
+// A 1M-point polyline is therefore 12 MB on the wire, not 48.
+enum : uint32_t {
+    VKB_EL_POINT  = 0,
+    VKB_EL_CUBIC  = 1,
+    VKB_EL_ARC    = 2,
+    VKB_EL_TYPE_MASK = 0x3,
+    VKB_EL_CURVED = 0x4,  // points of this element belong to a curved segment (PATH_HAS_CURVES_BIT on the segment)
+    VKB_EL_PAYLOAD_SHIFT = 3,
+};
+
+enum : uint32_t {
+    VKB_SP_CLOSED    = 1,  // PATH_CLOSED_BIT
+    VKB_SP_CONVEX    = 2,  // PATH_IS_CONVEX_BIT
+    VKB_SP_DROP_LAST = 4,  // close_path removed a last point equal to the first (src/vkvg_context.c:363-368)
+};
+struct vkb_subpath {
+    uint32_t first_elem, n_elems;
+    uint32_t flags;
+    uint32_t pad;
+};
+
+// ---- draws ------------------------------------------------------------------------------------------
+enum : uint32_t {
+    VKB_DRAW_FILL   = 0,  // polygon edges of every sub-path with > 2 points
+    VKB_DRAW_STROKE = 1,  // stroke triangles
+    VKB_DRAW_PAINT  = 2,  // whole-surface paint
+};
+enum : uint32_t {
+    VKB_RULE_EVEN_ODD = 0,  // blend once where winding is odd      (stencil INVERT fan + cover)
+    VKB_RULE_NON_ZERO = 1,  // blend once where winding != 0        (libtess triangles, non-overlapping)
+    VKB_RULE_COUNT    = 2,  // blend |winding| times                (stroke triangles blended one by one)
+};
+enum : uint32_t { VKB_PAT_SOLID = 0, VKB_PAT_LINEAR = 2, VKB_PAT_RADIAL = 3 };  // vkvg_pattern_type_t values
+
+struct vkb_draw {
+    uint32_t kind;       // VKB_DRAW_*
+    uint32_t rule;       // VKB_RULE_*
+    uint32_t first_subpath, n_subpaths;
+    float    mat[6];     // CTM at draw time: xx yx xy yy x0 y0
+    uint32_t color;      // premultiplied RGBA8, R in byte 0 (CreateRgbaf, src/vkvg_context_internal.h:60-62)
+    uint32_t pattern;    // VKB_PAT_*
+    uint32_t gradient;   // index into the batch's gradient table
+    float    opacity;
+    // stroke parameters (src/vkvg_context.c:830-832, internal.c:245-252)
+    float    hw, lhMax, arcStep;
+    uint32_t join, cap;
+    uint32_t dash_first, dash_count;  // into the batch's dash table
+    float    dash_offset;
+};
+
+struct vkb_gradient {  // vkvg_gradient_t in scalar block layout, src/vkvg_pattern.h:38-47
+    float    colors[16][4];
+    float    stops[16];
+    float    cp[2][4];
+    uint32_t count;
+    uint32_t pad[3];
+};
+static_assert(sizeof(vkb_gradient) == 368, "vkb_gradient layout");
+
+// what the fine pass reads per draw (16 B)
+struct vkb_paint {
+    uint32_t rule_pattern;  // rule | pattern << 8
+    uint32_t color;
+    float    opacity;
+    uint32_t gradient;
+};
+
+// device-space edge, 24.8 fixed point window coordinates (16 B per edge)
+struct vkb_edge {
+    int32_t x0, y0, x1, y1;
+};
+
+#define VKB_TILE 16            // pixels
+#define VKB_TILE_FX 4096       // VKB_TILE << 8
+#define VKB_MAX_DASHES 32

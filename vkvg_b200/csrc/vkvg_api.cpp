@@ -1,0 +1,1109 @@
+// Host side of the drop-in: the vkvg.h entry points.  Path commands are recorded (not flattened) into a
+// vkb_batch; fill / stroke / paint append draws; vkvg_flush hands the batch to the CUDA pipeline.
+// Every entry point cites the reference function whose behaviour (argument meaning, status handling,
+// bookkeeping quirks) it mirrors.  There is deliberately no CPU rendering path: without a CUDA device
+// vkvg_device_create returns an object whose status is VKVG_STATUS_DEVICE_ERROR.
+#include "../../include/vkvg.h"
+#include "../../include/vkvg_b200.h"
+#include "renderer.h"
+#include <float.h>
+#include <math.h>
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#define M_PIF 3.14159265358979323846f
+#define M_PIF_2 1.57079632679489661923f
+#define EQUF(a, b) (fabsf((a) - (b)) <= FLT_EPSILON)
+
+// objects returned instead of NULL on failed construction: the first field of every handle is its status
+// (reference src/vkvg_internal.h:104-109)
+static vkvg_status_t s_no_memory       = VKVG_STATUS_NO_MEMORY;
+static vkvg_status_t s_null_pointer    = VKVG_STATUS_NULL_POINTER; // (kept for parity with the reference table)
+static vkvg_status_t s_invalid_dev_ci  = VKVG_STATUS_INVALID_DEVICE_CREATE_INFO;
+static vkvg_status_t s_device_error    = VKVG_STATUS_DEVICE_ERROR;
+static vkvg_status_t s_invalid_surface = VKVG_STATUS_INVALID_SURFACE;
+
+struct _vkvg_device_t {
+    vkvg_status_t    status;
+    uint32_t         references;
+    uint32_t         samples;
+    int              hdpi, vdpi;
+    bool             threadAware;
+    vkb_device_impl *impl;
+    std::mutex       mtx;  // one stream + shared scratch buffers per device: flushes are serialised
+    bool             profiling;
+    vkb_stats        last;
+};
+struct _vkvg_surface_t {
+    vkvg_status_t     status;
+    uint32_t          references;
+    VkvgDevice        dev;
+    uint32_t          width, height;
+    vkb_surface_impl *impl;
+};
+struct _vkvg_pattern_t {
+    vkvg_status_t       status;
+    uint32_t            references;
+    vkvg_pattern_type_t type;
+    vkvg_extend_t       extend;
+    vkvg_filter_t       filter;
+    vkvg_matrix_t       matrix;
+    bool                hasMatrix;
+    vkb_gradient        grad;
+};
+
+struct saved_state {  // vkvg_context_save_t, src/vkvg_context_internal.h:101-125
+    float              lineWidth, miterLimit, dashOffset, opacity;
+    std::vector<float> dashes;
+    vkvg_operator_t    op;
+    vkvg_line_cap_t    cap;
+    vkvg_fill_rule_t   fillRule;
+    vkvg_matrix_t      mat;
+    uint32_t           curColor;
+    VkvgPattern        pattern;
+    uint32_t           patType;
+    vkb_gradient       grad;
+};
+
+struct _vkvg_context_t {
+    vkvg_status_t status;
+    uint32_t      references;
+    VkvgDevice    dev;
+    VkvgSurface   pSurf;
+
+    vkb_batch batch;
+    uint32_t  path_first_sp;  // first sub-path of the current path inside batch.subpaths
+    // the open sub-path (the reference's pathes[pathPtr] + segmentPtr bookkeeping, internal.c:136-238)
+    uint32_t sp_first_elem;
+    uint32_t sp_points;   // point count; exact for lines/arcs, a lower bound (>= true count impossible to miss 3/4 tests) once a curve is in
+    float    first_x, first_y, cur_x, cur_y;
+    bool     simpleConvex;
+
+    float              lineWidth, miterLimit, dashOffset;
+    std::vector<float> dashes;
+    vkvg_operator_t    op;
+    vkvg_line_cap_t    cap;
+    vkvg_line_join_t   join;
+    vkvg_fill_rule_t   fillRule;
+    float              opacity;
+    vkvg_matrix_t      mat;
+    uint32_t           curColor;
+    VkvgPattern        pattern;
+    uint32_t           patType;
+    vkb_gradient       grad;      // gradient as uploaded by _update_cur_pattern (control points already through the CTM)
+    int32_t            grad_slot; // index of `grad` in batch.grads, or -1
+    bool               clear_pending;
+    std::vector<saved_state> saved;
+};
+
+// ====================================================================================================
+// matrices — cairo-derived 2x3 affine, reference src/vkvg_matrix.c
+// ====================================================================================================
+void vkvg_matrix_init(vkvg_matrix_t *m, float xx, float yx, float xy, float yy, float x0, float y0) {
+    m->xx = xx; m->yx = yx; m->xy = xy; m->yy = yy; m->x0 = x0; m->y0 = y0;
+}
+void vkvg_matrix_init_identity(vkvg_matrix_t *m) { vkvg_matrix_init(m, 1, 0, 0, 1, 0, 0); }
+void vkvg_matrix_init_translate(vkvg_matrix_t *m, float tx, float ty) { vkvg_matrix_init(m, 1, 0, 0, 1, tx, ty); }
+void vkvg_matrix_init_scale(vkvg_matrix_t *m, float sx, float sy) { vkvg_matrix_init(m, sx, 0, 0, sy, 0, 0); }
+void vkvg_matrix_init_rotate(vkvg_matrix_t *m, float radians) {
+    float s = sinf(radians), c = cosf(radians);
+    vkvg_matrix_init(m, c, s, -s, c, 0, 0);
+}
+void vkvg_matrix_multiply(vkvg_matrix_t *result, const vkvg_matrix_t *a, const vkvg_matrix_t *b) {  // :193-206
+    vkvg_matrix_t r;
+    r.xx = a->xx * b->xx + a->yx * b->xy;
+    r.yx = a->xx * b->yx + a->yx * b->yy;
+    r.xy = a->xy * b->xx + a->yy * b->xy;
+    r.yy = a->xy * b->yx + a->yy * b->yy;
+    r.x0 = a->x0 * b->xx + a->y0 * b->xy + b->x0;
+    r.y0 = a->x0 * b->yx + a->y0 * b->yy + b->y0;
+    *result = r;
+}
+void vkvg_matrix_translate(vkvg_matrix_t *m, float tx, float ty) {
+    vkvg_matrix_t t;
+    vkvg_matrix_init_translate(&t, tx, ty);
+    vkvg_matrix_multiply(m, &t, m);
+}
+void vkvg_matrix_scale(vkvg_matrix_t *m, float sx, float sy) {
+    vkvg_matrix_t t;
+    vkvg_matrix_init_scale(&t, sx, sy);
+    vkvg_matrix_multiply(m, &t, m);
+}
+void vkvg_matrix_rotate(vkvg_matrix_t *m, float radians) {
+    vkvg_matrix_t t;
+    vkvg_matrix_init_rotate(&t, radians);
+    vkvg_matrix_multiply(m, &t, m);
+}
+void vkvg_matrix_transform_distance(const vkvg_matrix_t *m, float *dx, float *dy) {
+    float nx = (m->xx * *dx + m->xy * *dy), ny = (m->yx * *dx + m->yy * *dy);
+    *dx = nx; *dy = ny;
+}
+void vkvg_matrix_transform_point(const vkvg_matrix_t *m, float *x, float *y) {
+    vkvg_matrix_transform_distance(m, x, y);
+    *x += m->x0; *y += m->y0;
+}
+vkvg_status_t vkvg_matrix_invert(vkvg_matrix_t *m) {  // :107-147
+    if (m->xy == 0. && m->yx == 0.) {
+        m->x0 = -m->x0; m->y0 = -m->y0;
+        if (m->xx != 1.f) {
+            if (m->xx == 0.) return VKVG_STATUS_INVALID_MATRIX;
+            m->xx = 1.f / m->xx;
+            m->x0 *= m->xx;
+        }
+        if (m->yy != 1.f) {
+            if (m->yy == 0.) return VKVG_STATUS_INVALID_MATRIX;
+            m->yy = 1.f / m->yy;
+            m->y0 *= m->yy;
+        }
+        return VKVG_STATUS_SUCCESS;
+    }
+    float det = m->xx * m->yy - m->yx * m->xy;
+    if (!((det) * (det) >= 0.) || det == 0) return VKVG_STATUS_INVALID_MATRIX;
+    float a = m->xx, b = m->yx, c = m->xy, d = m->yy, tx = m->x0, ty = m->y0;
+    vkvg_matrix_init(m, d, -b, -c, a, c * ty - d * tx, b * tx - a * ty);
+    float s = 1 / det;
+    m->xx *= s; m->yx *= s; m->xy *= s; m->yy *= s; m->x0 *= s; m->y0 *= s;
+    return VKVG_STATUS_SUCCESS;
+}
+void vkvg_matrix_get_scale(const vkvg_matrix_t *m, float *sx, float *sy) {  // :222-229 (double sqrt, float store)
+    *sx = sqrt(m->xx * m->xx + m->xy * m->xy);
+    *sy = sqrt(m->yx * m->yx + m->yy * m->yy);
+}
+
+// ====================================================================================================
+// device — reference src/vkvg_device.c
+// ====================================================================================================
+VkvgDevice vkvg_device_create(vkvg_device_create_info_t *info) {
+    uint32_t samples = info ? info->samples : 1;
+    if (samples == 0) samples = 1;
+    if (samples != 1 && samples != 2 && samples != 4 && samples != 8 && samples != 16) return (VkvgDevice)&s_invalid_dev_ci;
+    int         ordinal = 0;
+    const char *e       = getenv("VKVG_B200_DEVICE");
+    if (!e) e = getenv("LOCAL_RANK");
+    if (e) ordinal = atoi(e);
+    vkb_device_impl *impl = vkb_device_open(ordinal);
+    if (!impl) {
+        fprintf(stderr, "vkvg_b200: no usable CUDA device — this library has no CPU path (vkvg_device_create fails)\n");
+        return (VkvgDevice)&s_device_error;
+    }
+    VkvgDevice dev   = new _vkvg_device_t();
+    dev->status      = VKVG_STATUS_SUCCESS;
+    dev->references  = 1;
+    dev->samples     = samples;
+    dev->hdpi = dev->vdpi = 96;
+    dev->threadAware = info ? info->threadAware : false;
+    dev->impl        = impl;
+    dev->profiling   = getenv("VKVG_B200_PROFILE") != nullptr;
+    memset(&dev->last, 0, sizeof dev->last);
+    return dev;
+}
+vkvg_status_t vkvg_device_status(VkvgDevice dev) { return !dev ? VKVG_STATUS_NULL_POINTER : dev->status; }
+void vkvg_device_destroy(VkvgDevice dev) {
+    if (vkvg_device_status(dev)) return;
+    if (--dev->references > 0) return;
+    vkb_device_close(dev->impl);
+    delete dev;
+}
+VkvgDevice vkvg_device_reference(VkvgDevice dev) {
+    if (!vkvg_device_status(dev)) dev->references++;
+    return dev;
+}
+uint32_t vkvg_device_get_reference_count(VkvgDevice dev) { return vkvg_device_status(dev) ? 0 : dev->references; }
+void vkvg_device_set_dpy(VkvgDevice dev, int hdpy, int vdpy) {
+    if (vkvg_device_status(dev)) return;
+    dev->hdpi = hdpy; dev->vdpi = vdpy;
+}
+void vkvg_device_get_dpy(VkvgDevice dev, int *hdpy, int *vdpy) {
+    if (vkvg_device_status(dev)) return;
+    *hdpy = dev->hdpi; *vdpy = dev->vdpi;
+}
+void vkvg_device_set_context_cache_size(VkvgDevice, uint32_t) {}  // contexts hold no device objects here: nothing to cache
+
+// ====================================================================================================
+// surface — reference src/vkvg_surface.c
+// ====================================================================================================
+VkvgSurface vkvg_surface_create(VkvgDevice dev, uint32_t width, uint32_t height) {
+    if (vkvg_device_status(dev)) return (VkvgSurface)&s_device_error;  // _create_surface, surface_internal.c:213-224
+    VkvgSurface surf = new _vkvg_surface_t();
+    surf->status     = VKVG_STATUS_SUCCESS;
+    surf->references = 1;
+    surf->dev        = dev;
+    surf->width      = width > 1 ? width : 1;
+    surf->height     = height > 1 ? height : 1;
+    {
+        std::lock_guard<std::mutex> lk(dev->mtx);
+        surf->impl = vkb_surface_new(dev->impl, surf->width, surf->height);
+    }
+    if (!surf->impl || vkb_device_failed(dev->impl)) surf->status = VKVG_STATUS_DEVICE_ERROR;
+    vkvg_device_reference(dev);
+    return surf;
+}
+vkvg_status_t vkvg_surface_status(VkvgSurface surf) { return !surf ? VKVG_STATUS_NULL_POINTER : surf->status; }
+VkvgSurface   vkvg_surface_reference(VkvgSurface surf) {
+    if (!vkvg_surface_status(surf)) surf->references++;
+    return surf;
+}
+uint32_t vkvg_surface_get_reference_count(VkvgSurface surf) { return vkvg_surface_status(surf) ? 0 : surf->references; }
+void     vkvg_surface_destroy(VkvgSurface surf) {
+    if (vkvg_surface_status(surf)) return;
+    if (--surf->references > 0) return;
+    {
+        std::lock_guard<std::mutex> lk(surf->dev->mtx);
+        vkb_surface_free(surf->impl);
+    }
+    vkvg_device_destroy(surf->dev);
+    delete surf;
+}
+void vkvg_surface_clear(VkvgSurface surf) {
+    if (vkvg_surface_status(surf)) return;
+    std::lock_guard<std::mutex> lk(surf->dev->mtx);
+    vkb_surface_clear(surf->impl);
+}
+VkImage  vkvg_surface_get_vk_image(VkvgSurface) { return NULL; }
+VkFormat vkvg_surface_get_vk_format(VkvgSurface surf) { return vkvg_surface_status(surf) ? 0 : VK_FORMAT_B8G8R8A8_UNORM; }
+uint32_t vkvg_surface_get_width(VkvgSurface surf) { return vkvg_surface_status(surf) ? 0 : surf->width; }
+uint32_t vkvg_surface_get_height(VkvgSurface surf) { return vkvg_surface_status(surf) ? 0 : surf->height; }
+void     vkvg_surface_resolve(VkvgSurface) {}  // every flush resolves
+vkvg_status_t vkvg_surface_write_to_memory(VkvgSurface surf, unsigned char *const bitmap) {  // :393-467
+    if (vkvg_surface_status(surf)) return VKVG_STATUS_INVALID_STATUS;
+    if (!bitmap) return VKVG_STATUS_WRITE_ERROR;
+    std::lock_guard<std::mutex> lk(surf->dev->mtx);
+    return vkb_surface_download(surf->impl, bitmap, true) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
+}
+vkvg_status_t vkvg_b200_surface_read_premultiplied(VkvgSurface surf, unsigned char *rgba) {
+    if (vkvg_surface_status(surf)) return VKVG_STATUS_INVALID_STATUS;
+    if (!rgba) return VKVG_STATUS_WRITE_ERROR;
+    std::lock_guard<std::mutex> lk(surf->dev->mtx);
+    return vkb_surface_download(surf->impl, rgba, false) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
+}
+int vkb_write_png(const char *path, const unsigned char *rgba, uint32_t w, uint32_t h);  // png.cpp
+vkvg_status_t vkvg_surface_write_to_png(VkvgSurface surf, const char *path) {  // :283-391
+    if (vkvg_surface_status(surf) || vkvg_device_status(surf->dev)) return VKVG_STATUS_INVALID_STATUS;
+    if (!path) return VKVG_STATUS_WRITE_ERROR;
+    std::vector<unsigned char> img((size_t)surf->width * surf->height * 4);
+    vkvg_status_t st = vkvg_surface_write_to_memory(surf, img.data());
+    if (st) return st;
+    return vkb_write_png(path, img.data(), surf->width, surf->height) ? VKVG_STATUS_WRITE_ERROR : VKVG_STATUS_SUCCESS;
+}
+const void *vkvg_b200_surface_device_pointer(VkvgSurface surf) { return vkvg_surface_status(surf) ? nullptr : vkb_surface_device_pixels(surf->impl); }
+
+// ====================================================================================================
+// patterns — reference src/vkvg_pattern.c (solid / linear / radial; surface patterns are out of scope)
+// ====================================================================================================
+vkvg_status_t vkvg_pattern_status(VkvgPattern pat) { return !pat ? VKVG_STATUS_NULL_POINTER : pat->status; }
+static VkvgPattern new_pattern(vkvg_pattern_type_t type) {
+    VkvgPattern pat = new _vkvg_pattern_t();
+    memset(pat, 0, sizeof *pat);
+    pat->type       = type;
+    pat->extend     = VKVG_EXTEND_NONE;
+    pat->references = 1;
+    return pat;
+}
+vkvg_status_t vkvg_pattern_edit_linear(VkvgPattern pat, float x0, float y0, float x1, float y1) {
+    if (vkvg_pattern_status(pat)) return vkvg_pattern_status(pat);
+    if (pat->type != VKVG_PATTERN_TYPE_LINEAR) return VKVG_STATUS_PATTERN_TYPE_MISMATCH;
+    pat->grad.cp[0][0] = x0; pat->grad.cp[0][1] = y0; pat->grad.cp[0][2] = x1; pat->grad.cp[0][3] = y1;
+    return VKVG_STATUS_SUCCESS;
+}
+VkvgPattern vkvg_pattern_create_linear(float x0, float y0, float x1, float y1) {
+    VkvgPattern pat = new_pattern(VKVG_PATTERN_TYPE_LINEAR);
+    vkvg_pattern_edit_linear(pat, x0, y0, x1, y1);
+    return pat;
+}
+vkvg_status_t vkvg_pattern_get_linear_points(VkvgPattern pat, float *x0, float *y0, float *x1, float *y1) {
+    if (vkvg_pattern_status(pat)) return vkvg_pattern_status(pat);
+    if (pat->type != VKVG_PATTERN_TYPE_LINEAR) return VKVG_STATUS_PATTERN_TYPE_MISMATCH;
+    *x0 = pat->grad.cp[0][0]; *y0 = pat->grad.cp[0][1]; *x1 = pat->grad.cp[0][2]; *y1 = pat->grad.cp[0][3];
+    return VKVG_STATUS_SUCCESS;
+}
+vkvg_status_t vkvg_pattern_edit_radial(VkvgPattern pat, float cx0, float cy0, float radius0, float cx1, float cy1, float radius1) {  // :95-118
+    if (vkvg_pattern_status(pat)) return vkvg_pattern_status(pat);
+    if (pat->type != VKVG_PATTERN_TYPE_RADIAL) return VKVG_STATUS_PATTERN_TYPE_MISMATCH;
+    float c0x = cx0, c0y = cy0;
+    if (radius0 > radius1 - 1.0f) radius0 = radius1 - 1.0f;
+    float ux = c0x - cx1, uy = c0y - cy1;
+    float l  = sqrtf(ux * ux + uy * uy);
+    if (l + radius0 + 1.0f >= radius1) {
+        float vx = ux / l, vy = uy / l, m = radius1 - radius0 - 1.0f;
+        c0x = cx1 + vx * m; c0y = cy1 + vy * m;
+    }
+    pat->grad.cp[0][0] = c0x; pat->grad.cp[0][1] = c0y; pat->grad.cp[0][2] = radius0; pat->grad.cp[0][3] = 0;
+    pat->grad.cp[1][0] = cx1; pat->grad.cp[1][1] = cy1; pat->grad.cp[1][2] = radius1; pat->grad.cp[1][3] = 0;
+    return VKVG_STATUS_SUCCESS;
+}
+VkvgPattern vkvg_pattern_create_radial(float cx0, float cy0, float radius0, float cx1, float cy1, float radius1) {
+    VkvgPattern pat = new_pattern(VKVG_PATTERN_TYPE_RADIAL);
+    vkvg_pattern_edit_radial(pat, cx0, cy0, radius0, cx1, cy1, radius1);
+    return pat;
+}
+VkvgPattern vkvg_pattern_reference(VkvgPattern pat) {
+    if (!vkvg_pattern_status(pat)) pat->references++;
+    return pat;
+}
+uint32_t vkvg_pattern_get_reference_count(VkvgPattern pat) { return vkvg_pattern_status(pat) ? 0 : pat->references; }
+void     vkvg_pattern_destroy(VkvgPattern pat) {
+    if (vkvg_pattern_status(pat)) return;
+    if (--pat->references > 0) return;
+    delete pat;
+}
+vkvg_status_t vkvg_pattern_add_color_stop(VkvgPattern pat, float offset, float r, float g, float b, float a) {  // :149-167
+    if (vkvg_pattern_status(pat)) return vkvg_pattern_status(pat);
+    if (pat->type == VKVG_PATTERN_TYPE_SURFACE || pat->type == VKVG_PATTERN_TYPE_SOLID) return VKVG_STATUS_PATTERN_TYPE_MISMATCH;
+    if (pat->grad.count >= 16) return VKVG_STATUS_INVALID_INDEX;  // the reference writes past its 16-entry arrays here
+    uint32_t i = pat->grad.count++;
+    pat->grad.colors[i][0] = a * r; pat->grad.colors[i][1] = a * g; pat->grad.colors[i][2] = a * b; pat->grad.colors[i][3] = a;
+    pat->grad.stops[i] = offset;
+    return VKVG_STATUS_SUCCESS;
+}
+void vkvg_pattern_set_extend(VkvgPattern pat, vkvg_extend_t extend) { if (!vkvg_pattern_status(pat)) pat->extend = extend; }
+void vkvg_pattern_set_filter(VkvgPattern pat, vkvg_filter_t filter) { if (!vkvg_pattern_status(pat)) pat->filter = filter; }
+vkvg_extend_t vkvg_pattern_get_extend(VkvgPattern pat) { return vkvg_pattern_status(pat) ? (vkvg_extend_t)0 : pat->extend; }
+vkvg_filter_t vkvg_pattern_get_filter(VkvgPattern pat) { return vkvg_pattern_status(pat) ? (vkvg_filter_t)0 : pat->filter; }
+vkvg_pattern_type_t vkvg_pattern_get_type(VkvgPattern pat) { return vkvg_pattern_status(pat) ? (vkvg_pattern_type_t)0 : pat->type; }
+vkvg_status_t vkvg_pattern_get_color_stop_count(VkvgPattern pat, uint32_t *count) {
+    if (vkvg_pattern_status(pat)) return vkvg_pattern_status(pat);
+    if (pat->type == VKVG_PATTERN_TYPE_SURFACE || pat->type == VKVG_PATTERN_TYPE_SOLID) return VKVG_STATUS_PATTERN_TYPE_MISMATCH;
+    *count = pat->grad.count;
+    return VKVG_STATUS_SUCCESS;
+}
+vkvg_status_t vkvg_pattern_get_color_stop_rgba(VkvgPattern pat, uint32_t index, float *offset, float *r, float *g, float *b, float *a) {
+    if (vkvg_pattern_status(pat)) return vkvg_pattern_status(pat);
+    if (pat->type == VKVG_PATTERN_TYPE_SURFACE || pat->type == VKVG_PATTERN_TYPE_SOLID) return VKVG_STATUS_PATTERN_TYPE_MISMATCH;
+    if (index >= pat->grad.count) return VKVG_STATUS_INVALID_INDEX;
+    *offset = pat->grad.stops[index];
+    *r = pat->grad.colors[index][0]; *g = pat->grad.colors[index][1]; *b = pat->grad.colors[index][2]; *a = pat->grad.colors[index][3];
+    return VKVG_STATUS_SUCCESS;
+}
+void vkvg_pattern_set_matrix(VkvgPattern pat, const vkvg_matrix_t *matrix) {
+    if (vkvg_pattern_status(pat)) return;
+    pat->matrix = *matrix; pat->hasMatrix = true;
+}
+void vkvg_pattern_get_matrix(VkvgPattern pat, vkvg_matrix_t *matrix) {
+    if (vkvg_pattern_status(pat)) return;
+    if (pat->hasMatrix) *matrix = pat->matrix;
+    else vkvg_matrix_init_identity(matrix);
+}
+
+// ====================================================================================================
+// context — reference src/vkvg_context.c
+// ====================================================================================================
+static void init_ctx(VkvgContext ctx) {  // _init_ctx :24-61
+    ctx->lineWidth = 1.f; ctx->miterLimit = 10.f;
+    ctx->op = VKVG_OPERATOR_OVER; ctx->fillRule = VKVG_FILL_RULE_NON_ZERO;
+    ctx->cap = VKVG_LINE_CAP_BUTT; ctx->join = VKVG_LINE_JOIN_MITER;
+    ctx->opacity = 1.0f;
+    vkvg_matrix_init_identity(&ctx->mat);
+    ctx->pattern = NULL; ctx->patType = VKB_PAT_SOLID; ctx->grad_slot = -1;
+    ctx->curColor = 0xff000000;
+    ctx->dashOffset = 0;
+    ctx->clear_pending = false;
+}
+static void clear_path(VkvgContext ctx) {  // _clear_path, internal.c:199-206
+    ctx->path_first_sp = (uint32_t)ctx->batch.subpaths.size();
+    ctx->sp_first_elem = (uint32_t)ctx->batch.elem_hdr.size();
+    ctx->sp_points = 0;
+    ctx->simpleConvex = false;
+}
+VkvgContext vkvg_create(VkvgSurface surf) {
+    if (vkvg_surface_status(surf)) return (VkvgContext)&s_invalid_surface;
+    if (vkvg_device_status(surf->dev)) return (VkvgContext)&s_device_error;
+    VkvgContext ctx = new _vkvg_context_t();
+    ctx->status     = VKVG_STATUS_SUCCESS;
+    ctx->references = 1;
+    ctx->dev = surf->dev; ctx->pSurf = surf;
+    init_ctx(ctx);
+    vkvg_surface_reference(surf);
+    clear_path(ctx);
+    return ctx;
+}
+vkvg_status_t vkvg_status(VkvgContext ctx) { return !ctx ? VKVG_STATUS_NULL_POINTER : ctx->status; }
+VkvgContext   vkvg_reference(VkvgContext ctx) {
+    if (!vkvg_status(ctx)) ctx->references++;
+    return ctx;
+}
+uint32_t vkvg_get_reference_count(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->references; }
+
+// ---- path bookkeeping ----
+static inline bool path_empty(VkvgContext ctx) { return ctx->sp_points == 0; }  // _current_path_is_empty, internal.c:132
+static void push_elem(VkvgContext ctx, uint32_t type_flags, const float *payload, int n) {
+    vkb_batch &b = ctx->batch;
+    b.elem_hdr.push_back(type_flags | ((uint32_t)b.elem_data.size() << VKB_EL_PAYLOAD_SHIFT));
+    b.elem_data.insert(b.elem_data.end(), payload, payload + n);
+}
+static void add_point(VkvgContext ctx, float x, float y, bool curved) {  // _add_point, internal.c:221-238
+    if (isnan(x) || isnan(y)) return;
+    float p[2] = {x, y};
+    push_elem(ctx, VKB_EL_POINT | (curved ? VKB_EL_CURVED : 0), p, 2);
+    if (ctx->sp_points == 0) { ctx->first_x = x; ctx->first_y = y; }
+    ctx->cur_x = x; ctx->cur_y = y;
+    ctx->sp_points++;
+}
+static void end_subpath(VkvgContext ctx, uint32_t flags) {
+    vkb_subpath sp = {ctx->sp_first_elem, (uint32_t)ctx->batch.elem_hdr.size() - ctx->sp_first_elem, flags, 0};
+    ctx->batch.subpaths.push_back(sp);
+    ctx->sp_first_elem = (uint32_t)ctx->batch.elem_hdr.size();
+    ctx->sp_points = 0;
+    ctx->simpleConvex = false;
+}
+static void finish_path(VkvgContext ctx, uint32_t flags = 0) {  // _finish_path, internal.c:163-197
+    if (ctx->sp_points == 0) return;
+    if (ctx->sp_points < 2) {  // only the current position is in the path: drop it
+        ctx->batch.elem_data.resize(ctx->batch.elem_hdr[ctx->sp_first_elem] >> VKB_EL_PAYLOAD_SHIFT);
+        ctx->batch.elem_hdr.resize(ctx->sp_first_elem);
+        ctx->sp_points = 0;
+        return;
+    }
+    if (ctx->path_first_sp == ctx->batch.subpaths.size() && ctx->simpleConvex) flags |= VKB_SP_CONVEX;
+    end_subpath(ctx, flags);
+}
+static void line_to_(VkvgContext ctx, float x, float y) {  // _line_to, internal.c:1463-1472
+    if (!path_empty(ctx) && EQUF(ctx->cur_x, x) && EQUF(ctx->cur_y, y)) return;
+    add_point(ctx, x, y, false);
+    ctx->simpleConvex = false;
+}
+void vkvg_new_sub_path(VkvgContext ctx) { if (!vkvg_status(ctx)) finish_path(ctx); }
+void vkvg_new_path(VkvgContext ctx) {
+    if (vkvg_status(ctx)) return;
+    // drop the elements of an unfinished sub-path; finished sub-paths may be referenced by recorded draws
+    if (ctx->sp_points) {
+        ctx->batch.elem_data.resize(ctx->batch.elem_hdr[ctx->sp_first_elem] >> VKB_EL_PAYLOAD_SHIFT);
+        ctx->batch.elem_hdr.resize(ctx->sp_first_elem);
+    }
+    clear_path(ctx);
+}
+void vkvg_close_path(VkvgContext ctx) {  // :350-373
+    if (vkvg_status(ctx)) return;
+    if (ctx->sp_points < 3) return;
+    uint32_t flags = VKB_SP_CLOSED;
+    if (EQUF(ctx->cur_x, ctx->first_x) && EQUF(ctx->cur_y, ctx->first_y)) {
+        if (ctx->sp_points < 4) return;
+        flags |= VKB_SP_DROP_LAST;  // _remove_last_point
+    }
+    finish_path(ctx, flags);
+}
+void vkvg_move_to(VkvgContext ctx, float x, float y) {  // :515-522
+    if (vkvg_status(ctx)) return;
+    finish_path(ctx);
+    add_point(ctx, x, y, false);
+}
+void vkvg_rel_move_to(VkvgContext ctx, float x, float y) {  // :504-514
+    if (vkvg_status(ctx)) return;
+    if (path_empty(ctx)) add_point(ctx, 0, 0, false);
+    float cx = ctx->cur_x, cy = ctx->cur_y;
+    finish_path(ctx);
+    add_point(ctx, cx + x, cy + y, false);
+}
+void vkvg_line_to(VkvgContext ctx, float x, float y) { if (!vkvg_status(ctx)) line_to_(ctx, x, y); }
+void vkvg_rel_line_to(VkvgContext ctx, float dx, float dy) {  // :374-385
+    if (vkvg_status(ctx)) return;
+    if (path_empty(ctx)) add_point(ctx, 0, 0, false);
+    line_to_(ctx, ctx->cur_x + dx, ctx->cur_y + dy);
+}
+bool vkvg_has_current_point(VkvgContext ctx) { return vkvg_status(ctx) ? false : !path_empty(ctx); }
+void vkvg_get_current_point(VkvgContext ctx, float *x, float *y) {  // :528-540
+    if (vkvg_status(ctx)) return;
+    if (path_empty(ctx)) { *x = *y = 0; return; }
+    *x = ctx->cur_x; *y = ctx->cur_y;
+}
+static float get_arc_step(VkvgContext ctx, float radius) {  // _get_arc_step, internal.c:245-252
+    float sx, sy;
+    vkvg_matrix_get_scale(&ctx->mat, &sx, &sy);
+    float r = radius * fabsf(fmaxf(sx, sy));
+    if (r < 30.0f) return fminf(M_PIF / 3.f, M_PIF / r);
+    return fminf(M_PIF / 3.f, M_PIF / (r * 0.4f));
+}
+static void arc_impl(VkvgContext ctx, float xc, float yc, float radius, float a1, float a2, bool negative) {  // :394-503
+    if (!negative) {
+        while (a2 < a1) a2 += 2.f * M_PIF;
+        if (a2 - a1 > 2.f * M_PIF) a2 = a1 + 2.f * M_PIF;
+    } else {
+        while (a2 > a1) a2 -= 2.f * M_PIF;
+        if (a1 - a2 > a1 + 2.f * M_PIF) a2 = a1 - 2.f * M_PIF;
+    }
+    float vx = cosf(a1) * radius + xc, vy = sinf(a1) * radius + yc;
+    float step = get_arc_step(ctx, radius);
+    float a    = a1;
+    if (path_empty(ctx)) {
+        add_point(ctx, vx, vy, true);  // inside _set_curve_start: the start point belongs to the curved segment
+        ctx->simpleConvex = ctx->path_first_sp == ctx->batch.subpaths.size();
+    } else {
+        line_to_(ctx, vx, vy);
+        ctx->simpleConvex = false;
+    }
+    if (!negative) a += step; else a -= step;
+    if (EQUF(a2, a1)) return;
+    // interior points are generated on the device; the host only needs their number for the 3/4-point tests
+    uint32_t n = 0;
+    float    t = a;
+    if (!negative) while (t < a2) { n++; t += step; }
+    else while (t > a2) { n++; t -= step; }
+    if (n) {
+        float p[6] = {xc, yc, radius, a, a2, negative ? -step : step};
+        push_elem(ctx, VKB_EL_ARC | VKB_EL_CURVED, p, 6);
+        ctx->sp_points += n;
+        // current point after the interior points (only observable through the full-circle close test below)
+        float la = negative ? t + step : t - step;
+        ctx->cur_x = cosf(la) * radius + xc; ctx->cur_y = sinf(la) * radius + yc;
+    }
+    if (EQUF(negative ? a1 - a2 : a2 - a1, M_PIF * 2.f)) {  // complete circle: last point == first one
+        vkvg_close_path(ctx);
+        return;
+    }
+    add_point(ctx, cosf(a2) * radius + xc, sinf(a2) * radius + yc, true);
+}
+void vkvg_arc(VkvgContext ctx, float xc, float yc, float radius, float a1, float a2) { if (!vkvg_status(ctx)) arc_impl(ctx, xc, yc, radius, a1, a2, false); }
+void vkvg_arc_negative(VkvgContext ctx, float xc, float yc, float radius, float a1, float a2) { if (!vkvg_status(ctx)) arc_impl(ctx, xc, yc, radius, a1, a2, true); }
+
+static void curve_to_(VkvgContext ctx, float x1, float y1, float x2, float y2, float x3, float y3) {  // _curve_to :541-566
+    if (EQUF(x1, x2) && EQUF(x2, x3) && EQUF(y1, y2) && EQUF(y2, y3)) {
+        if (path_empty(ctx) || (EQUF(ctx->cur_x, x1) && EQUF(ctx->cur_y, y1))) return;
+    }
+    if (!(isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2) && isfinite(x3) && isfinite(y3))) return;  // the reference recursion does not terminate on these
+    ctx->simpleConvex = false;
+    if (path_empty(ctx)) add_point(ctx, x1, y1, true);
+    float sx = 1, sy = 1;
+    vkvg_matrix_get_scale(&ctx->mat, &sx, &sy);
+    float tol  = fabs(0.25f / fmaxf(sx, sy));
+    float p[9] = {ctx->cur_x, ctx->cur_y, x1, y1, x2, y2, x3, y3, tol};
+    push_elem(ctx, VKB_EL_CUBIC | VKB_EL_CURVED, p, 9);
+    ctx->sp_points += 3;  // >= 2 recursion points (level 0 always splits) + the end point
+    ctx->cur_x = x3; ctx->cur_y = y3;
+}
+void vkvg_curve_to(VkvgContext ctx, float x1, float y1, float x2, float y2, float x3, float y3) { if (!vkvg_status(ctx)) curve_to_(ctx, x1, y1, x2, y2, x3, y3); }
+void vkvg_rel_curve_to(VkvgContext ctx, float x1, float y1, float x2, float y2, float x3, float y3) {  // :600-611
+    if (vkvg_status(ctx)) return;
+    if (path_empty(ctx)) { ctx->status = VKVG_STATUS_NO_CURRENT_POINT; return; }
+    float cx = ctx->cur_x, cy = ctx->cur_y;
+    curve_to_(ctx, cx + x1, cy + y1, cx + x2, cy + y2, cx + x3, cy + y3);
+}
+static void quadratic_to_(VkvgContext ctx, float x1, float y1, float x2, float y2) {  // _quadratic_to :567-577
+    const double qf = 2.0 / 3.0;
+    float x0, y0;
+    if (path_empty(ctx)) { x0 = x1; y0 = y1; }
+    else { x0 = ctx->cur_x; y0 = ctx->cur_y; }
+    curve_to_(ctx, x0 + (x1 - x0) * qf, y0 + (y1 - y0) * qf, x2 + (x1 - x2) * qf, y2 + (y1 - y2) * qf, x2, y2);
+}
+void vkvg_quadratic_to(VkvgContext ctx, float x1, float y1, float x2, float y2) { if (!vkvg_status(ctx)) quadratic_to_(ctx, x1, y1, x2, y2); }
+void vkvg_rel_quadratic_to(VkvgContext ctx, float x1, float y1, float x2, float y2) {
+    if (vkvg_status(ctx)) return;
+    float cx = ctx->cur_x, cy = ctx->cur_y;
+    quadratic_to_(ctx, cx + x1, cy + y1, cx + x2, cy + y2);
+}
+vkvg_status_t vkvg_rectangle(VkvgContext ctx, float x, float y, float w, float h) {  // :620-639
+    if (vkvg_status(ctx)) return ctx->status;
+    finish_path(ctx);
+    if (w <= 0 || h <= 0) return VKVG_STATUS_INVALID_RECT;
+    add_point(ctx, x, y, false);
+    add_point(ctx, x + w, y, false);
+    add_point(ctx, x + w, y + h, false);
+    add_point(ctx, x, y + h, false);
+    finish_path(ctx, VKB_SP_CLOSED | VKB_SP_CONVEX);
+    return VKVG_STATUS_SUCCESS;
+}
+vkvg_status_t vkvg_rounded_rectangle(VkvgContext ctx, float x, float y, float w, float h, float radius) {  // :640-664
+    if (vkvg_status(ctx)) return ctx->status;
+    finish_path(ctx);
+    if (w <= 0 || h <= 0) return VKVG_STATUS_INVALID_RECT;
+    if ((radius > w / 2.0f) || (radius > h / 2.0f)) radius = fmin(w / 2.0f, h / 2.0f);
+    vkvg_move_to(ctx, x, y + radius);
+    vkvg_arc(ctx, x + radius, y + radius, radius, M_PIF, -M_PIF_2);
+    vkvg_line_to(ctx, x + w - radius, y);
+    vkvg_arc(ctx, x + w - radius, y + radius, radius, -M_PIF_2, 0);
+    vkvg_line_to(ctx, x + w, y + h - radius);
+    vkvg_arc(ctx, x + w - radius, y + h - radius, radius, 0, M_PIF_2);
+    vkvg_line_to(ctx, x + radius, y + h);
+    vkvg_arc(ctx, x + radius, y + h - radius, radius, M_PIF_2, M_PIF);
+    vkvg_line_to(ctx, x, y + radius);
+    vkvg_close_path(ctx);
+    return VKVG_STATUS_SUCCESS;
+}
+void vkvg_ellipse(VkvgContext ctx, float radiusX, float radiusY, float x, float y, float rotationAngle) {  // :1605-1639
+    if (vkvg_status(ctx)) return;
+    float w23 = radiusX * 4 / 3;
+    float dx1 = sinf(rotationAngle) * radiusY, dy1 = cosf(rotationAngle) * radiusY;
+    float dx2 = cosf(rotationAngle) * w23, dy2 = sinf(rotationAngle) * w23;
+    float tcx = x - dx1, tcy = y + dy1, bcx = x + dx1, bcy = y - dy1;
+    finish_path(ctx);
+    add_point(ctx, bcx, bcy, false);
+    curve_to_(ctx, bcx + dx2, bcy + dy2, tcx + dx2, tcy + dy2, tcx, tcy);
+    curve_to_(ctx, tcx - dx2, tcy - dy2, bcx - dx2, bcy - dy2, bcx, bcy);
+    finish_path(ctx, VKB_SP_CLOSED);
+}
+
+// ---- state ----
+void  vkvg_set_opacity(VkvgContext ctx, float opacity) { if (!vkvg_status(ctx)) ctx->opacity = opacity; }
+float vkvg_get_opacity(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->opacity; }
+static uint32_t rgbaf(float r, float g, float b, float a) {  // CreateRgbaf, internal.h:60-62
+    return (((uint32_t)(a * 255.0f) & 0xFF) << 24) | (((uint32_t)(b * a * 255.0f) & 0xFF) << 16) | (((uint32_t)(g * a * 255.0f) & 0xFF) << 8) |
+           ((uint32_t)(r * a * 255.0f) & 0xFF);
+}
+static void set_solid(VkvgContext ctx, uint32_t c) {  // _update_cur_pattern(ctx, NULL), internal.c:682-832
+    ctx->curColor = c;
+    if (ctx->pattern) vkvg_pattern_destroy(ctx->pattern);
+    ctx->pattern = NULL; ctx->patType = VKB_PAT_SOLID; ctx->grad_slot = -1;
+}
+void vkvg_set_source_color(VkvgContext ctx, uint32_t c) { if (!vkvg_status(ctx)) set_solid(ctx, c); }
+void vkvg_set_source_rgb(VkvgContext ctx, float r, float g, float b) { if (!vkvg_status(ctx)) set_solid(ctx, rgbaf(r, g, b, 1)); }
+void vkvg_set_source_rgba(VkvgContext ctx, float r, float g, float b, float a) { if (!vkvg_status(ctx)) set_solid(ctx, rgbaf(r, g, b, a)); }
+static void update_cur_pattern(VkvgContext ctx, VkvgPattern pat) {  // gradient branch, internal.c:774-826
+    VkvgPattern last = ctx->pattern;
+    ctx->pattern     = pat;
+    vkb_gradient g   = pat->grad;
+    if (g.count < 2) {
+        ctx->status = VKVG_STATUS_PATTERN_INVALID_GRADIENT;
+        return;
+    }
+    vkvg_matrix_t mat;
+    if (pat->hasMatrix) {
+        mat = pat->matrix;
+        if (vkvg_matrix_invert(&mat) != VKVG_STATUS_SUCCESS) vkvg_matrix_init_identity(&mat);
+        vkvg_matrix_transform_point(&mat, &g.cp[0][0], &g.cp[0][1]);
+    }
+    vkvg_matrix_transform_point(&ctx->mat, &g.cp[0][0], &g.cp[0][1]);
+    if (pat->type == VKVG_PATTERN_TYPE_LINEAR) {
+        if (pat->hasMatrix) vkvg_matrix_transform_point(&mat, &g.cp[0][2], &g.cp[0][3]);
+        vkvg_matrix_transform_point(&ctx->mat, &g.cp[0][2], &g.cp[0][3]);
+    } else {
+        if (pat->hasMatrix) vkvg_matrix_transform_point(&mat, &g.cp[1][0], &g.cp[1][1]);
+        vkvg_matrix_transform_point(&ctx->mat, &g.cp[1][0], &g.cp[1][1]);
+        if (pat->hasMatrix) {
+            vkvg_matrix_transform_distance(&mat, &g.cp[0][2], &g.cp[0][3]);
+            vkvg_matrix_transform_distance(&mat, &g.cp[1][2], &g.cp[0][3]);
+        }
+        vkvg_matrix_transform_distance(&ctx->mat, &g.cp[0][2], &g.cp[0][3]);
+        vkvg_matrix_transform_distance(&ctx->mat, &g.cp[1][2], &g.cp[0][3]);
+    }
+    ctx->grad = g; ctx->grad_slot = -1;
+    ctx->patType = pat->type == VKVG_PATTERN_TYPE_LINEAR ? VKB_PAT_LINEAR : VKB_PAT_RADIAL;
+    if (last) vkvg_pattern_destroy(last);
+}
+void vkvg_set_source(VkvgContext ctx, VkvgPattern pat) {  // :1034-1040
+    if (vkvg_status(ctx) || vkvg_pattern_status(pat)) return;
+    if (pat->type != VKVG_PATTERN_TYPE_LINEAR && pat->type != VKVG_PATTERN_TYPE_RADIAL) return;  // surface patterns: out of scope
+    update_cur_pattern(ctx, pat);
+    vkvg_pattern_reference(pat);
+}
+VkvgPattern vkvg_get_source(VkvgContext ctx) {
+    if (vkvg_status(ctx)) return NULL;
+    vkvg_pattern_reference(ctx->pattern);
+    return ctx->pattern;
+}
+VkvgSurface vkvg_get_target(VkvgContext ctx) { return vkvg_status(ctx) ? NULL : ctx->pSurf; }
+void  vkvg_set_line_width(VkvgContext ctx, float width) { if (!vkvg_status(ctx)) ctx->lineWidth = width; }
+void  vkvg_set_miter_limit(VkvgContext ctx, float limit) { if (!vkvg_status(ctx)) ctx->miterLimit = limit; }
+void  vkvg_set_line_cap(VkvgContext ctx, vkvg_line_cap_t cap) { if (!vkvg_status(ctx)) ctx->cap = cap; }
+void  vkvg_set_line_join(VkvgContext ctx, vkvg_line_join_t join) { if (!vkvg_status(ctx)) ctx->join = join; }
+void  vkvg_set_operator(VkvgContext ctx, vkvg_operator_t op) { if (!vkvg_status(ctx)) ctx->op = op; }  // only OVER is rendered
+void  vkvg_set_fill_rule(VkvgContext ctx, vkvg_fill_rule_t fr) { if (!vkvg_status(ctx)) ctx->fillRule = fr; }
+float vkvg_get_line_width(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->lineWidth; }
+float vkvg_get_miter_limit(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->miterLimit; }
+vkvg_line_cap_t  vkvg_get_line_cap(VkvgContext ctx) { return vkvg_status(ctx) ? (vkvg_line_cap_t)0 : ctx->cap; }
+vkvg_line_join_t vkvg_get_line_join(VkvgContext ctx) { return vkvg_status(ctx) ? (vkvg_line_join_t)0 : ctx->join; }
+vkvg_operator_t  vkvg_get_operator(VkvgContext ctx) { return vkvg_status(ctx) ? VKVG_OPERATOR_OVER : ctx->op; }
+vkvg_fill_rule_t vkvg_get_fill_rule(VkvgContext ctx) { return vkvg_status(ctx) ? VKVG_FILL_RULE_NON_ZERO : ctx->fillRule; }
+void vkvg_set_dash(VkvgContext ctx, const float *dashes, uint32_t num_dashes, float offset) {  // :1103-1115
+    if (vkvg_status(ctx)) return;
+    ctx->dashOffset = offset;
+    ctx->dashes.assign(dashes, dashes + (dashes ? num_dashes : 0));
+}
+void vkvg_get_dash(VkvgContext ctx, const float *dashes, uint32_t *num_dashes, float *offset) {
+    if (vkvg_status(ctx)) return;
+    *num_dashes = (uint32_t)ctx->dashes.size();
+    *offset     = ctx->dashOffset;
+    if (ctx->dashes.empty() || dashes == NULL) return;
+    memcpy((float *)dashes, ctx->dashes.data(), sizeof(float) * ctx->dashes.size());
+}
+void vkvg_save(VkvgContext ctx) {  // :1251-1375 (clip state is out of scope)
+    if (vkvg_status(ctx)) return;
+    saved_state s;
+    s.lineWidth = ctx->lineWidth; s.miterLimit = ctx->miterLimit; s.dashOffset = ctx->dashOffset; s.dashes = ctx->dashes;
+    s.op = ctx->op; s.cap = ctx->cap; s.fillRule = ctx->fillRule; s.opacity = ctx->opacity; s.mat = ctx->mat;
+    s.curColor = ctx->curColor; s.pattern = ctx->pattern; s.patType = ctx->patType; s.grad = ctx->grad;
+    if (ctx->pattern) vkvg_pattern_reference(ctx->pattern);
+    ctx->saved.push_back(s);
+}
+void vkvg_restore(VkvgContext ctx) {  // :1376-1512
+    if (vkvg_status(ctx)) return;
+    if (ctx->saved.empty()) { ctx->status = VKVG_STATUS_INVALID_RESTORE; return; }
+    saved_state s = ctx->saved.back();
+    ctx->saved.pop_back();
+    ctx->mat = s.mat; ctx->opacity = s.opacity;
+    ctx->dashOffset = s.dashOffset; ctx->dashes = s.dashes;
+    ctx->lineWidth = s.lineWidth; ctx->miterLimit = s.miterLimit; ctx->op = s.op; ctx->cap = s.cap;
+    ctx->join     = VKVG_LINE_JOIN_MITER;  // the reference never saves lineJoin: restore reads a zeroed field (:1492)
+    ctx->fillRule = s.fillRule;
+    if (s.pattern) {  // :1501-1509: a different saved pattern is re-uploaded through the restored CTM
+        if (s.pattern != ctx->pattern) update_cur_pattern(ctx, s.pattern);
+        else vkvg_pattern_destroy(s.pattern);
+    } else
+        set_solid(ctx, s.curColor);
+}
+void vkvg_translate(VkvgContext ctx, float dx, float dy) { if (!vkvg_status(ctx)) vkvg_matrix_translate(&ctx->mat, dx, dy); }
+void vkvg_scale(VkvgContext ctx, float sx, float sy) { if (!vkvg_status(ctx)) vkvg_matrix_scale(&ctx->mat, sx, sy); }
+void vkvg_rotate(VkvgContext ctx, float radians) { if (!vkvg_status(ctx)) vkvg_matrix_rotate(&ctx->mat, radians); }
+void vkvg_transform(VkvgContext ctx, const vkvg_matrix_t *matrix) {
+    if (vkvg_status(ctx)) return;
+    vkvg_matrix_t res;
+    vkvg_matrix_multiply(&res, &ctx->mat, matrix);
+    ctx->mat = res;
+}
+void vkvg_identity_matrix(VkvgContext ctx) { if (!vkvg_status(ctx)) vkvg_matrix_init_identity(&ctx->mat); }
+void vkvg_set_matrix(VkvgContext ctx, const vkvg_matrix_t *matrix) { if (!vkvg_status(ctx)) ctx->mat = *matrix; }
+void vkvg_get_matrix(VkvgContext ctx, vkvg_matrix_t *const matrix) { if (!vkvg_status(ctx) && matrix) *matrix = ctx->mat; }
+
+// ---- draws ----
+static vkb_draw base_draw(VkvgContext ctx, uint32_t kind, uint32_t rule) {
+    vkb_draw d;
+    memset(&d, 0, sizeof d);
+    d.kind = kind; d.rule = rule;
+    d.first_subpath = ctx->path_first_sp;
+    d.n_subpaths    = (uint32_t)ctx->batch.subpaths.size() - ctx->path_first_sp;
+    memcpy(d.mat, &ctx->mat, sizeof d.mat);
+    d.color = ctx->curColor; d.pattern = ctx->patType; d.opacity = ctx->opacity;
+    if (ctx->patType != VKB_PAT_SOLID) {
+        if (ctx->grad_slot < 0) {
+            ctx->grad_slot = (int32_t)ctx->batch.grads.size();
+            ctx->batch.grads.push_back(ctx->grad);
+        }
+        d.gradient = (uint32_t)ctx->grad_slot;
+    }
+    return d;
+}
+static void fill_preserve_(VkvgContext ctx) {  // _fill_preserve :796-821
+    finish_path(ctx);
+    if (ctx->batch.subpaths.size() == ctx->path_first_sp) return;
+    ctx->batch.draws.push_back(base_draw(ctx, VKB_DRAW_FILL, ctx->fillRule == VKVG_FILL_RULE_EVEN_ODD ? VKB_RULE_EVEN_ODD : VKB_RULE_NON_ZERO));
+}
+static void stroke_preserve_(VkvgContext ctx) {  // _stroke_preserve :822-948
+    finish_path(ctx);
+    if (ctx->batch.subpaths.size() == ctx->path_first_sp) return;
+    vkb_draw d = base_draw(ctx, VKB_DRAW_STROKE, VKB_RULE_COUNT);
+    d.hw = ctx->lineWidth * 0.5f;
+    d.lhMax = ctx->miterLimit * ctx->lineWidth;
+    d.arcStep = get_arc_step(ctx, d.hw);
+    d.join = ctx->join; d.cap = ctx->cap;
+    if (!ctx->dashes.empty()) {
+        float tot = 0;
+        for (float v : ctx->dashes) tot += v;
+        if (tot == 0 || ctx->dashes.size() > VKB_MAX_DASHES) { ctx->status = VKVG_STATUS_INVALID_DASH; return; }
+        d.dash_first = (uint32_t)ctx->batch.dashes.size();
+        d.dash_count = (uint32_t)ctx->dashes.size();
+        d.dash_offset = ctx->dashOffset;
+        ctx->batch.dashes.insert(ctx->batch.dashes.end(), ctx->dashes.begin(), ctx->dashes.end());
+    }
+    ctx->batch.draws.push_back(d);
+}
+void vkvg_fill_preserve(VkvgContext ctx) { if (!vkvg_status(ctx)) fill_preserve_(ctx); }
+void vkvg_fill(VkvgContext ctx) {
+    if (vkvg_status(ctx)) return;
+    fill_preserve_(ctx);
+    clear_path(ctx);
+}
+void vkvg_stroke_preserve(VkvgContext ctx) { if (!vkvg_status(ctx)) stroke_preserve_(ctx); }
+void vkvg_stroke(VkvgContext ctx) {
+    if (vkvg_status(ctx)) return;
+    stroke_preserve_(ctx);
+    clear_path(ctx);
+}
+void vkvg_paint(VkvgContext ctx) {  // :990-1003
+    if (vkvg_status(ctx)) return;
+    finish_path(ctx);
+    if (ctx->batch.subpaths.size() != ctx->path_first_sp) { vkvg_fill(ctx); return; }
+    vkb_draw d = base_draw(ctx, VKB_DRAW_PAINT, VKB_RULE_NON_ZERO);
+    d.n_subpaths = 0;
+    ctx->batch.draws.push_back(d);
+}
+void vkvg_clear(VkvgContext ctx) {  // :734-753: everything drawn so far is wiped, so pending draws can be dropped
+    if (vkvg_status(ctx)) return;
+    ctx->batch.draws.clear();
+    ctx->batch.grads.clear(); ctx->grad_slot = -1;
+    ctx->batch.dashes.clear();
+    ctx->clear_pending = true;
+}
+
+// keep the current (preserved / under construction) path across a flush: compact it to the front of the batch
+static void carry_path_over(VkvgContext ctx) {
+    vkb_batch &b = ctx->batch;
+    vkb_batch  n;
+    uint32_t   e0 = ctx->path_first_sp < b.subpaths.size() ? b.subpaths[ctx->path_first_sp].first_elem : ctx->sp_first_elem;
+    uint32_t   d0 = e0 < b.elem_hdr.size() ? (b.elem_hdr[e0] >> VKB_EL_PAYLOAD_SHIFT) : (uint32_t)b.elem_data.size();
+    for (uint32_t i = e0; i < b.elem_hdr.size(); i++) {
+        uint32_t h = b.elem_hdr[i];
+        n.elem_hdr.push_back((h & ((1u << VKB_EL_PAYLOAD_SHIFT) - 1)) | (((h >> VKB_EL_PAYLOAD_SHIFT) - d0) << VKB_EL_PAYLOAD_SHIFT));
+    }
+    n.elem_data.assign(b.elem_data.begin() + d0, b.elem_data.end());
+    for (uint32_t i = ctx->path_first_sp; i < b.subpaths.size(); i++) {
+        vkb_subpath sp = b.subpaths[i];
+        sp.first_elem -= e0;
+        n.subpaths.push_back(sp);
+    }
+    ctx->sp_first_elem -= e0;
+    ctx->path_first_sp = 0;
+    ctx->grad_slot     = -1;
+    b = std::move(n);
+}
+static void flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident) {
+    VkvgDevice dev = ctx->dev;
+    {
+        std::lock_guard<std::mutex> lk(dev->mtx);
+        if (ctx->clear_pending) { vkb_surface_clear(ctx->pSurf->impl); ctx->clear_pending = false; }
+        if (!ctx->batch.draws.empty() || cap) {
+            vkb_stats st;
+            bool want_stats = dev->profiling;
+            if (vkb_render(dev->impl, ctx->pSurf->impl, dev->samples, ctx->batch, cap, want_stats ? &st : nullptr)) {
+                ctx->status = VKVG_STATUS_DEVICE_ERROR;
+                dev->status = VKVG_STATUS_DEVICE_ERROR;
+            }
+            if (want_stats) dev->last = st;
+        }
+    }
+    (void)keep_resident;
+    carry_path_over(ctx);
+}
+void vkvg_flush(VkvgContext ctx) {  // :180-184
+    if (vkvg_status(ctx)) return;
+    flush_impl(ctx, nullptr, false);
+}
+void vkvg_destroy(VkvgContext ctx) {  // :246-304
+    if (vkvg_status(ctx)) return;
+    if (--ctx->references > 0) return;
+    vkvg_flush(ctx);
+    if (ctx->pattern) vkvg_pattern_destroy(ctx->pattern);
+    for (saved_state &s : ctx->saved) if (s.pattern) vkvg_pattern_destroy(s.pattern);
+    vkvg_surface_destroy(ctx->pSurf);
+    delete ctx;
+}
+const char *vkvg_status_to_string(vkvg_status_t status) {  // :1647-1692
+    switch (status) {
+    case VKVG_STATUS_SUCCESS: return "no error has occurred";
+    case VKVG_STATUS_INVALID_RESTORE: return "vkvg_restore() without matching vkvg_save()";
+    case VKVG_STATUS_NO_CURRENT_POINT: return "no current point defined";
+    case VKVG_STATUS_INVALID_MATRIX: return "invalid matrix (not invertible)";
+    case VKVG_STATUS_INVALID_STATUS: return "invalid value for an input vkvg_status_t";
+    case VKVG_STATUS_INVALID_INDEX: return "invalid index passed to getter";
+    case VKVG_STATUS_NULL_POINTER: return "NULL pointer";
+    case VKVG_STATUS_WRITE_ERROR: return "error while writing to output stream";
+    case VKVG_STATUS_PATTERN_TYPE_MISMATCH: return "the pattern type is not appropriate for the operation";
+    case VKVG_STATUS_PATTERN_INVALID_GRADIENT: return "the stops count is zero";
+    case VKVG_STATUS_INVALID_FORMAT: return "invalid value for an input vkvg_format_t";
+    case VKVG_STATUS_FILE_NOT_FOUND: return "file not found";
+    case VKVG_STATUS_INVALID_DASH: return "invalid value for a dash setting";
+    case VKVG_STATUS_INVALID_RECT: return "a rectangle has the height or width equal to 0";
+    case VKVG_STATUS_TIMEOUT: return "waiting for a Vulkan operation to finish resulted in a fence timeout (5 seconds)";
+    case VKVG_STATUS_DEVICE_ERROR: return "the initialization of the device resulted in an error";
+    case VKVG_STATUS_INVALID_IMAGE: return "invalid image";
+    case VKVG_STATUS_INVALID_SURFACE: return "invalid surface";
+    case VKVG_STATUS_INVALID_FONT: return "unresolved font name";
+    default: return "<unknown error status>";
+    }
+}
+
+// ====================================================================================================
+// vkvg_b200.h extensions
+// ====================================================================================================
+extern unsigned long long g_vkb_launches;
+uint64_t vkvg_b200_launch_count(void) { return g_vkb_launches; }
+void     vkvg_b200_set_profiling(VkvgDevice dev, int on) { if (!vkvg_device_status(dev)) dev->profiling = on != 0; }
+void     vkvg_b200_last_stats(VkvgDevice dev, vkvg_b200_stats_t *out) {
+    if (vkvg_device_status(dev) || !out) return;
+    static_assert(sizeof(vkvg_b200_stats_t) == sizeof(vkb_stats), "stats layout");
+    memcpy(out, &dev->last, sizeof *out);
+}
+void vkvg_b200_device_synchronize(VkvgDevice dev) {
+    if (vkvg_device_status(dev)) return;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    vkb_device_sync(dev->impl);
+}
+int vkb_device_ordinal(vkb_device_impl *d);
+int vkvg_b200_device_ordinal(VkvgDevice dev) { return vkvg_device_status(dev) ? -1 : vkb_device_ordinal(dev->impl); }
+
+// a context's current path as a one-draw batch (the batch is copied: the context is left untouched)
+static bool path_batch(VkvgContext ctx, uint32_t kind, vkb_batch &out) {
+    finish_path(ctx);
+    if (ctx->batch.subpaths.size() == ctx->path_first_sp) return false;
+    vkb_batch saved_draws;
+    std::swap(saved_draws.draws, ctx->batch.draws);
+    std::swap(saved_draws.dashes, ctx->batch.dashes);
+    std::swap(saved_draws.grads, ctx->batch.grads);
+    int32_t slot = ctx->grad_slot;
+    ctx->grad_slot = -1;
+    if (kind == VKB_DRAW_STROKE) stroke_preserve_(ctx); else fill_preserve_(ctx);
+    out = ctx->batch;
+    std::swap(saved_draws.draws, ctx->batch.draws);
+    std::swap(saved_draws.dashes, ctx->batch.dashes);
+    std::swap(saved_draws.grads, ctx->batch.grads);
+    ctx->grad_slot = slot;
+    return !out.draws.empty();
+}
+static void run_geometry(VkvgContext ctx, const vkb_batch &b, vkb_capture &cap) {
+    cap.geometry_only = true;
+    std::lock_guard<std::mutex> lk(ctx->dev->mtx);
+    if (vkb_render(ctx->dev->impl, ctx->pSurf->impl, ctx->dev->samples, b, &cap, nullptr)) ctx->status = VKVG_STATUS_DEVICE_ERROR;
+}
+uint32_t vkvg_b200_flatten_path(VkvgContext ctx, float *xy, uint8_t *curved, uint32_t cap_points, uint32_t *sp_first, uint32_t *sp_count,
+                                uint32_t cap_subpaths, uint32_t *n_subpaths) {
+    if (n_subpaths) *n_subpaths = 0;
+    if (vkvg_status(ctx)) return 0;
+    vkb_batch b;
+    if (!path_batch(ctx, VKB_DRAW_FILL, b)) return 0;
+    std::vector<float> pts; std::vector<uint8_t> fl; std::vector<uint32_t> f, c;
+    vkb_capture cap;
+    cap.points = &pts; cap.ptflags = &fl; cap.sp_first = &f; cap.sp_count = &c;
+    run_geometry(ctx, b, cap);
+    // report only the sub-paths of the current path, points re-based to its first point
+    uint32_t s0 = b.draws[0].first_subpath, ns = b.draws[0].n_subpaths;
+    uint32_t p0 = ns ? f[s0] : 0, p1 = ns ? f[s0 + ns - 1] + c[s0 + ns - 1] : 0;
+    // a DROP_LAST sub-path keeps its dropped point in memory: walk sub-path by sub-path to produce a dense array
+    uint32_t n = 0;
+    for (uint32_t s = 0; s < ns; s++) {
+        if (s < cap_subpaths) { if (sp_first) sp_first[s] = n; if (sp_count) sp_count[s] = c[s0 + s]; }
+        for (uint32_t k = 0; k < c[s0 + s]; k++, n++)
+            if (n < cap_points) {
+                if (xy) { xy[2 * n] = pts[2 * (f[s0 + s] + k)]; xy[2 * n + 1] = pts[2 * (f[s0 + s] + k) + 1]; }
+                if (curved) curved[n] = fl[f[s0 + s] + k];
+            }
+    }
+    (void)p0; (void)p1;
+    if (n_subpaths) *n_subpaths = ns;
+    return n;
+}
+void vkvg_b200_stroke_geometry(VkvgContext ctx, float *xy, uint32_t cap_verts, uint32_t *n_verts, uint32_t *indices, uint32_t cap_indices,
+                               uint32_t *n_indices) {
+    if (n_verts) *n_verts = 0;
+    if (n_indices) *n_indices = 0;
+    if (vkvg_status(ctx)) return;
+    vkb_batch b;
+    if (!path_batch(ctx, VKB_DRAW_STROKE, b)) return;
+    // restrict the batch to this single draw so vertex numbering starts at 0
+    vkb_draw d = b.draws.back();
+    b.draws.assign(1, d);
+    std::vector<float> v; std::vector<uint32_t> ix;
+    vkb_capture cap;
+    cap.verts = &v; cap.inds = &ix;
+    run_geometry(ctx, b, cap);
+    if (n_verts) *n_verts = (uint32_t)(v.size() / 2);
+    if (n_indices) *n_indices = (uint32_t)ix.size();
+    if (xy) memcpy(xy, v.data(), sizeof(float) * (v.size() < 2ull * cap_verts ? v.size() : 2ull * cap_verts));
+    if (indices) memcpy(indices, ix.data(), 4 * (ix.size() < cap_indices ? ix.size() : (size_t)cap_indices));
+}
+uint64_t vkvg_b200_path_edges(VkvgContext ctx, int kind, int32_t *edges_xyxy, uint64_t cap_edges) {
+    if (vkvg_status(ctx)) return 0;
+    vkb_batch b;
+    if (!path_batch(ctx, kind ? VKB_DRAW_STROKE : VKB_DRAW_FILL, b)) return 0;
+    vkb_draw d = b.draws.back();
+    b.draws.assign(1, d);
+    std::vector<int32_t> e;
+    vkb_capture cap;
+    cap.edges = &e;
+    run_geometry(ctx, b, cap);
+    uint64_t n = e.size() / 4;
+    if (edges_xyxy) memcpy(edges_xyxy, e.data(), 16 * (n < cap_edges ? n : cap_edges));
+    return n;
+}
+void vkvg_b200_flush_capture_winding(VkvgContext ctx, int32_t *winding) {
+    if (vkvg_status(ctx)) return;
+    vkb_capture cap;
+    cap.winding = winding;
+    cap.winding_draw = ctx->batch.draws.empty() ? 0 : (uint32_t)ctx->batch.draws.size() - 1;
+    if (ctx->batch.draws.empty()) {
+        memset(winding, 0, (size_t)ctx->pSurf->width * ctx->pSurf->height * ctx->dev->samples * 4);
+        flush_impl(ctx, nullptr, false);
+        return;
+    }
+    flush_impl(ctx, &cap, false);
+}
+int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges, uint64_t n, uint32_t w, uint32_t h, int32_t *out);  // pipeline.cu
+vkvg_status_t vkvg_b200_winding(VkvgDevice dev, const int32_t *edges_xyxy, uint64_t n_edges, uint32_t width, uint32_t height, int32_t *winding) {
+    if (vkvg_device_status(dev)) return VKVG_STATUS_DEVICE_ERROR;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    return vkb_winding_raw(dev->impl, dev->samples, edges_xyxy, n_edges, width, height, winding) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
+}
+void vkvg_b200_flush_keep(VkvgContext ctx) { vkvg_flush(ctx); }  // the uploaded batch stays on the device until the next upload
+void vkvg_b200_replay_resident(VkvgDevice dev, VkvgSurface surf, int clear_first) {
+    if (vkvg_device_status(dev) || vkvg_surface_status(surf)) return;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    if (clear_first) vkb_surface_clear(surf->impl);
+    vkb_stats st;
+    if (vkb_render_resident(dev->impl, surf->impl, dev->samples, nullptr, dev->profiling ? &st : nullptr)) dev->status = VKVG_STATUS_DEVICE_ERROR;
+    if (dev->profiling) dev->last = st;
+}
+
+vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *a, uint64_t n_args) {
+    if (vkvg_status(ctx)) return vkvg_status(ctx);
+    uint64_t k = 0;
+#define NEED(n) if (k + (n) > n_args) return VKVG_STATUS_INVALID_INDEX
+    for (uint64_t i = 0; i < n_ops; i++) {
+        switch (ops[i]) {
+        case VKVG_B200_OP_MOVE_TO: NEED(2); vkvg_move_to(ctx, a[k], a[k + 1]); k += 2; break;
+        case VKVG_B200_OP_LINE_TO: NEED(2); vkvg_line_to(ctx, a[k], a[k + 1]); k += 2; break;
+        case VKVG_B200_OP_CURVE_TO: NEED(6); vkvg_curve_to(ctx, a[k], a[k + 1], a[k + 2], a[k + 3], a[k + 4], a[k + 5]); k += 6; break;
+        case VKVG_B200_OP_CLOSE_PATH: vkvg_close_path(ctx); break;
+        case VKVG_B200_OP_NEW_PATH: vkvg_new_path(ctx); break;
+        case VKVG_B200_OP_ARC: NEED(5); vkvg_arc(ctx, a[k], a[k + 1], a[k + 2], a[k + 3], a[k + 4]); k += 5; break;
+        case VKVG_B200_OP_ARC_NEGATIVE: NEED(5); vkvg_arc_negative(ctx, a[k], a[k + 1], a[k + 2], a[k + 3], a[k + 4]); k += 5; break;
+        case VKVG_B200_OP_RECTANGLE: NEED(4); vkvg_rectangle(ctx, a[k], a[k + 1], a[k + 2], a[k + 3]); k += 4; break;
+        case VKVG_B200_OP_FILL: vkvg_fill(ctx); break;
+        case VKVG_B200_OP_FILL_PRESERVE: vkvg_fill_preserve(ctx); break;
+        case VKVG_B200_OP_STROKE: vkvg_stroke(ctx); break;
+        case VKVG_B200_OP_STROKE_PRESERVE: vkvg_stroke_preserve(ctx); break;
+        case VKVG_B200_OP_PAINT: vkvg_paint(ctx); break;
+        case VKVG_B200_OP_SET_SOURCE_RGBA: NEED(4); vkvg_set_source_rgba(ctx, a[k], a[k + 1], a[k + 2], a[k + 3]); k += 4; break;
+        case VKVG_B200_OP_SET_LINE_WIDTH: NEED(1); vkvg_set_line_width(ctx, a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_LINE_CAP: NEED(1); vkvg_set_line_cap(ctx, (vkvg_line_cap_t)(int)a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_LINE_JOIN: NEED(1); vkvg_set_line_join(ctx, (vkvg_line_join_t)(int)a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_MITER_LIMIT: NEED(1); vkvg_set_miter_limit(ctx, a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_FILL_RULE: NEED(1); vkvg_set_fill_rule(ctx, (vkvg_fill_rule_t)(int)a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_DASH: {
+            NEED(2);
+            uint32_t n = (uint32_t)a[k];
+            NEED(2 + n);
+            vkvg_set_dash(ctx, a + k + 2, n, a[k + 1]);
+            k += 2 + n;
+            break;
+        }
+        case VKVG_B200_OP_SET_SOURCE_LINEAR:
+        case VKVG_B200_OP_SET_SOURCE_RADIAL: {
+            int np = ops[i] == VKVG_B200_OP_SET_SOURCE_LINEAR ? 4 : 6;
+            NEED(np + 1);
+            uint32_t ns = (uint32_t)a[k + np];
+            NEED(np + 1 + 5 * ns);
+            VkvgPattern pat = np == 4 ? vkvg_pattern_create_linear(a[k], a[k + 1], a[k + 2], a[k + 3])
+                                      : vkvg_pattern_create_radial(a[k], a[k + 1], a[k + 2], a[k + 3], a[k + 4], a[k + 5]);
+            const float *s = a + k + np + 1;
+            for (uint32_t j = 0; j < ns; j++) vkvg_pattern_add_color_stop(pat, s[5 * j], s[5 * j + 1], s[5 * j + 2], s[5 * j + 3], s[5 * j + 4]);
+            vkvg_set_source(ctx, pat);
+            vkvg_pattern_destroy(pat);
+            k += np + 1 + 5 * ns;
+            break;
+        }
+        case VKVG_B200_OP_TRANSLATE: NEED(2); vkvg_translate(ctx, a[k], a[k + 1]); k += 2; break;
+        case VKVG_B200_OP_SCALE: NEED(2); vkvg_scale(ctx, a[k], a[k + 1]); k += 2; break;
+        case VKVG_B200_OP_ROTATE: NEED(1); vkvg_rotate(ctx, a[k]); k += 1; break;
+        case VKVG_B200_OP_IDENTITY_MATRIX: vkvg_identity_matrix(ctx); break;
+        case VKVG_B200_OP_SAVE: vkvg_save(ctx); break;
+        case VKVG_B200_OP_RESTORE: vkvg_restore(ctx); break;
+        case VKVG_B200_OP_CLEAR: vkvg_clear(ctx); break;
+        case VKVG_B200_OP_SET_OPACITY: NEED(1); vkvg_set_opacity(ctx, a[k]); k += 1; break;
+        case VKVG_B200_OP_POLYLINE: {
+            NEED(1);
+            uint32_t nbits;
+            memcpy(&nbits, &a[k], 4);  // the point count travels as raw uint32 bits (a float cannot hold every count)
+            uint64_t n = nbits;
+            NEED(1 + 2 * n);
+            const float *p = a + k + 1;
+            if (n) vkvg_move_to(ctx, p[0], p[1]);
+            for (uint64_t j = 1; j < n; j++) vkvg_line_to(ctx, p[2 * j], p[2 * j + 1]);
+            k += 1 + 2 * n;
+            break;
+        }
+        case VKVG_B200_OP_FLUSH: vkvg_flush(ctx); break;
+        default: return VKVG_STATUS_INVALID_STATUS;
+        }
+        if (ctx->status) return ctx->status;
+    }
+#undef NEED
+    return ctx->status;
+}
