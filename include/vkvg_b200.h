@@ -54,6 +54,8 @@ typedef struct {
     uint64_t n_elems, n_points, n_fill_edges, n_stroke_items, n_verts, n_inds, n_edges, n_path_tiles, n_nonempty, n_tile_edges;
     float    ms_total, ms_fine;
     uint64_t h2d_bytes;
+    float    ms_stage[5]; /* flatten | job tables + stroke expansion | edge build | binning + sort | fine pass */
+    float    pad_;
 } vkvg_b200_stats_t;
 
 vkvg_public uint64_t vkvg_b200_launch_count(void);                          /* kernels launched by this library so far */
@@ -67,6 +69,11 @@ vkvg_public const void *vkvg_b200_surface_device_pointer(VkvgSurface surf); /* C
  * `vkvg_b200_replay_resident` re-runs the whole pipeline on it (no host->device traffic) onto surf. */
 vkvg_public void vkvg_b200_flush_keep(VkvgContext ctx);
 vkvg_public void vkvg_b200_replay_resident(VkvgDevice dev, VkvgSurface surf, int clear_first);
+/* bench support: run `steps` resident replays, each timed on its own with CUDA events on the library's stream (which is
+ * not torch's current stream); with flush_l2 a 256 MiB scratch buffer is overwritten before every step, outside the
+ * timed events.  `sum` receives the counters of the last step and the SUMS of ms_total / ms_fine / ms_stage. */
+vkvg_public vkvg_status_t vkvg_b200_time_resident(VkvgDevice dev, VkvgSurface surf, uint32_t steps, int clear_first, int flush_l2,
+                                                  vkvg_b200_stats_t *sum);
 
 /* ---- 3. packed command stream -------------------------------------------------------------------------- */
 enum {

@@ -1,0 +1,378 @@
+"""GPU: the CUDA pipeline (through the C ABI of libvkvg_b200.so) against the oracle and the reference goldens.
+Integer work (winding, coverage) is bit-exact; vertices within 1e-3 px; pixels within 1/255 at the 99.9th percentile
+(BASELINE.json north_star) — and in fact asserted exact wherever the oracle is exact."""
+import ctypes as C
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import vkvg_b200 as v
+from tests import scenes
+from tests.golden import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.dirname(os.path.abspath(mg.__file__))
+VERT_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def geo():
+    return np.load(os.path.join(GOLD, "geometry.npz"))
+
+
+@pytest.fixture(scope="module")
+def pix():
+    return np.load(os.path.join(GOLD, "pixels.npz"))
+
+
+def random_edges(rng, n, w, h, kind):
+    """n random CLOSED polygons (3..6 vertices) as directed 24.8 edges.  The winding of a closed curve is what the
+    rasteriser defines (fills are implicitly closed, stroke geometry is triangles); open edge soups have no winding."""
+    lo, hi = -40 * 256, (max(w, h) + 40) * 256
+    out = []
+    for _ in range(n):
+        k = int(rng.integers(3, 7))
+        if kind == "short":
+            c = rng.integers(0, [w * 256, h * 256], (1, 2))
+            p = c + rng.integers(-3000, 3000, (k, 2))
+        elif kind == "long":
+            p = rng.integers(lo, hi, (k, 2))
+        elif kind == "axis":  # rectangles whose sides sit on pixel / sample coordinates
+            x0, x1 = sorted(rng.integers(0, w, 2) * 256 + rng.choice([0, 32, 96, 128, 160, 224], 2))
+            y0, y1 = sorted(rng.integers(0, h, 2) * 256 + rng.choice([0, 32, 96, 128, 160, 224], 2))
+            p = np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]])
+            if rng.random() < 0.5:
+                p = p[::-1]
+        else:  # "grid": vertices on the 1/16-pixel sample grid so edges pass exactly through sample points
+            p = rng.integers(-2 * 16, (max(w, h) + 2) * 16, (k, 2)) * 16
+        out.append(np.concatenate([p, np.roll(p, -1, 0)], 1))
+    return np.concatenate(out).astype(np.int32)
+
+
+@pytest.mark.parametrize("samples", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("w,h", [(64, 64), (100, 70), (17, 133)])
+def test_winding_bit_exact(oracle_lib, samples, w, h):
+    dev = v.Device(samples)
+    rng = np.random.default_rng(samples * 1000 + w)
+    for kind, n in (("short", 100), ("long", 12), ("axis", 40), ("grid", 25)):
+        e = random_edges(rng, n, w, h, kind)
+        got = dev.winding(e, w, h)
+        ref = oracle_lib.winding_brute(e, w, h, samples)
+        assert np.array_equal(got, ref), (kind, int((got != ref).sum()))
+    dev.close()
+
+
+def test_winding_empty_and_degenerate(dev4, oracle_lib):
+    assert not dev4.winding(np.zeros((0, 4), np.int32), 40, 24).any()
+    # zero-length edge, a zero-area (two-edge) polygon, a triangle wholly outside the surface
+    e = np.array([[100, 100, 100, 100], [0, 300, 9000, 300], [9000, 300, 0, 300],
+                  [-50000, -50000, -40000, -45000], [-40000, -45000, -45000, -30000], [-45000, -30000, -50000, -50000]], np.int32)
+    got = dev4.winding(e, 40, 24)
+    assert np.array_equal(got, oracle_lib.winding_brute(e, 40, 24, 4)) and not got.any()
+
+
+def test_winding_closed_polygons_large(dev4, oracle_lib):
+    """closed self-intersecting polygons on a 512x384 surface (ragged tile edge: 384 = 24 tiles, 512 = 32)."""
+    polys, _ = scenes.polygons_c2(300, 512, 3)
+    es = []
+    for p in polys:
+        q = np.floor(p * 256 + 0.5).astype(np.int32)
+        es.append(np.concatenate([q, np.roll(q, -1, 0)], 1))
+    e = np.concatenate(es)
+    got = dev4.winding(e, 512, 384)
+    assert np.array_equal(got, oracle_lib.winding_brute(e, 512, 384, 4))
+    assert np.abs(got).max() >= 2  # self-intersections really produce |winding| > 1
+
+
+@pytest.mark.parametrize("seed", mg.GEOMETRY_SEEDS)
+def test_flatten_and_stroke_geometry_vs_reference_golden(dev4, geo, seed):
+    s = v.Surface(dev4, 256, 256)
+    c = v.Context(s)
+    mg.geometry_scene(c, seed)
+    pts = c.path_points()
+    ref = geo["pts_%d" % seed]
+    assert pts.shape == ref.shape
+    assert np.abs(pts - ref).max() <= VERT_TOL
+    first, cnt, curved = c.path_subpaths()
+    tab = geo["tab_%d" % seed]
+    # sub-path point counts equal the reference's `pathes` table (count bits of every path header)
+    hdr, i = [], 0
+    while i < len(tab):
+        n = int(tab[i] & 0x1FFFFFFF)
+        hdr.append(n)
+        i += 1
+        if tab[i - 1] & 0x40000000:  # HAS_CURVES: per-segment entries follow, summing to n
+            acc = 0
+            while acc < n:
+                acc += int(tab[i] & 0x1FFFFFFF)
+                i += 1
+    assert [int(x) for x in cnt if x > 1] == hdr
+    verts, inds = c.stroke_geometry()
+    rv, ri = geo["verts_%d" % seed], geo["inds_%d" % seed]
+    _match_stroke_geometry(verts, inds, rv, ri)
+    c.close()
+    s.close()
+
+
+def _match_stroke_geometry(verts, inds, rv, ri):
+    """Same vertex order within 1e-3 px and identical indices.  The reference sizes round joins / caps with float
+    `while (a < a1)` loops whose last comparison can sit on a knife edge (e.g. a + 3*(pi/3) against a + pi for a round
+    cap of half-width 1.5): a 1-ulp difference between glibc's and CUDA's acosf then adds or drops one arc vertex that
+    coincides with its neighbour.  When the counts differ the geometry is compared as matched point sets instead
+    (SURVEY.md §7 'Float reproducibility'): every vertex of one set lies within 1e-3 px of a vertex of the other, and the
+    two triangle lists cover the same area."""
+    if verts.shape == rv.shape and inds.shape == ri.shape:
+        assert np.array_equal(inds, ri)
+        assert np.abs(verts - rv).max() <= VERT_TOL
+        return
+    from scipy.spatial import cKDTree
+    assert abs(len(verts) - len(rv)) <= max(2, len(rv) // 200), (len(verts), len(rv))
+    assert cKDTree(rv).query(verts)[0].max() <= VERT_TOL
+    assert cKDTree(verts).query(rv)[0].max() <= VERT_TOL
+
+    def area(v, i):
+        t = v[i.reshape(-1, 3)].astype(np.float64)
+        return np.abs(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])).sum() / 2
+    assert abs(area(verts, inds) - area(rv, ri)) <= 1e-3 * max(1.0, area(rv, ri))
+
+
+def _pixel_check(a, b, exact=True):
+    d = np.abs(a.astype(int) - b.astype(int)).max(axis=2)
+    assert np.percentile(d, 99.9) <= 1, ("p99.9", float(np.percentile(d, 99.9)))
+    if exact:
+        assert int((d > 0).sum()) == 0, ("differing pixels", int((d > 0).sum()), int(d.max()))
+
+
+@pytest.mark.parametrize("name", mg.PIXEL_SCENES)
+def test_pixels_vs_reference_golden(dev4, pix, name):
+    for seed in range(3):
+        s = v.Surface(dev4, 128, 128)
+        c = v.Context(s)
+        mg.pixel_scene(c, name, seed)
+        c.flush()
+        _pixel_check(s.pixels(), pix["%s_%d" % (name, seed)])
+        c.close()
+        s.close()
+
+
+def test_tiger_1024_vs_reference_golden(dev4, pix, tmp_path):
+    w, h, shapes = scenes.load_nsvg(os.path.join(GOLD, "tiger.nsvg.bin"))
+    s = v.Surface(dev4, 1024, 1024)
+    c = v.Context(s)
+    c.clear()
+    scenes.render_nsvg(c, shapes)
+    c.flush()
+    img = s.pixels()
+    _pixel_check(img, pix["tiger_1024"])
+    # vkvg_surface_write_to_png: decode the file and compare with write_to_memory (un-premultiplied RGBA8)
+    path = str(tmp_path / "tiger.png")
+    assert s.write_to_png(path) == 0
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, dims = 8, b"", None
+    while pos < len(data):
+        n = int.from_bytes(data[pos:pos + 4], "big")
+        typ = data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + n]
+        assert zlib.crc32(typ + body) == int.from_bytes(data[pos + 8 + n:pos + 12 + n], "big")
+        if typ == b"IHDR":
+            dims = (int.from_bytes(body[:4], "big"), int.from_bytes(body[4:8], "big"), body[8], body[9])
+        if typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    assert dims == (1024, 1024, 8, 6)
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(1024, 1 + 4096)
+    assert not raw[:, 0].any()
+    assert np.array_equal(raw[:, 1:].reshape(1024, 1024, 4), s.write_to_memory())
+    c.close()
+    s.close()
+
+
+@pytest.mark.parametrize("rule", [0, 1])
+def test_fill_coverage_bit_exact_per_sample(dev4, oracle_lib, rule):
+    for seed in range(6):
+        o = oracle_lib.Oracle(160, 120, 4)
+        o.capture_coverage(True)
+        s = v.Surface(dev4, 160, 120)
+        c = v.Context(s)
+        for g in (o, c):
+            scenes.random_path(g, 40 + seed, size=120)
+            g.set_fill_rule(rule)
+            g.set_source_rgba(0.3, 0.4, 0.9, 0.7)
+            g.fill()
+        w = c.flush_capture_winding()
+        cov = o.last_coverage()
+        if rule == 0:
+            assert np.array_equal(w & 1, cov & 1)
+        else:
+            assert np.array_equal(w != 0, cov != 0)
+        assert np.array_equal(s.pixels(), o.pixels())
+
+
+def test_stroke_triangle_count_bit_exact_per_sample(dev4, oracle_lib):
+    for seed in range(6):
+        o = oracle_lib.Oracle(160, 120, 4)
+        o.capture_coverage(True)
+        s = v.Surface(dev4, 160, 120)
+        c = v.Context(s)
+        for g in (o, c):
+            scenes.random_path(g, 70 + seed, size=120)
+            g.set_source_rgba(0.9, 0.4, 0.1, 0.5)
+            g.set_line_width(5.0)
+            g.set_line_join(seed % 3)
+            g.set_line_cap(seed % 3)
+            if seed % 2:
+                g.set_dash([7, 4], 2.0)
+            g.stroke()
+        w = c.flush_capture_winding()
+        assert np.array_equal(np.abs(w), o.last_coverage())
+        assert np.array_equal(s.pixels(), o.pixels())
+
+
+def test_write_to_memory_unpremultiply(dev4, oracle_lib):
+    o = oracle_lib.Oracle(96, 96, 4)
+    s = v.Surface(dev4, 96, 96)
+    c = v.Context(s)
+    for g in (o, c):
+        mg.pixel_scene(g, "mixed", 2, size=96)
+    c.flush()
+    assert np.array_equal(s.write_to_memory(), o.write_to_memory())
+
+
+def test_cleared_surface_reads_back_zero(dev4):  # gunit_tests/surface.cpp:107-119
+    s = v.Surface(dev4, 37, 53)
+    assert not s.write_to_memory().any()
+    c = v.Context(s)
+    c.set_source_rgba(1, 0, 0, 1)
+    c.paint()
+    c.flush()
+    assert (s.pixels() == np.array([255, 0, 0, 255], np.uint8)).all()
+    s.clear()
+    assert not s.pixels().any()
+
+
+def test_context_refcounts_and_current_point(dev4):  # gunit_tests/context.cpp:44-71, :175-218
+    L = v.lib()
+    s = v.Surface(dev4, 64, 64)
+    base_dev = L.vkvg_device_get_reference_count(dev4.h)
+    ctx = L.vkvg_create(s.h)
+    assert L.vkvg_status(ctx) == 0
+    assert L.vkvg_get_reference_count(ctx) == 1
+    assert L.vkvg_surface_get_reference_count(s.h) == 2
+    assert L.vkvg_device_get_reference_count(dev4.h) == base_dev
+    L.vkvg_reference(ctx)
+    assert L.vkvg_get_reference_count(ctx) == 2
+    L.vkvg_destroy(ctx)
+    assert L.vkvg_get_reference_count(ctx) == 1
+
+    def cp():
+        a, b = C.c_float(-1), C.c_float(-1)
+        L.vkvg_get_current_point(ctx, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def no_cp():
+        return (not L.vkvg_has_current_point(ctx)) and cp() == (0, 0)
+
+    assert no_cp()
+    L.vkvg_new_path(ctx)
+    L.vkvg_close_path(ctx)
+    L.vkvg_new_sub_path(ctx)
+    assert no_cp()
+    L.vkvg_line_to(ctx, 50, 10)
+    assert cp() == (50, 10)
+    L.vkvg_move_to(ctx, 10, 50)
+    assert L.vkvg_has_current_point(ctx) and cp() == (10, 50)
+    L.vkvg_line_to(ctx, 50, 10)
+    assert cp() == (50, 10)
+    L.vkvg_rel_line_to(ctx, 10, 10)
+    assert cp() == (60, 20)
+    L.vkvg_close_path(ctx)
+    assert no_cp()
+    L.vkvg_line_to(ctx, 50, 10)
+    L.vkvg_rel_line_to(ctx, 10, 10)
+    L.vkvg_new_sub_path(ctx)
+    assert no_cp()
+    L.vkvg_line_to(ctx, 50, 10)
+    L.vkvg_rel_line_to(ctx, 10, 10)
+    L.vkvg_new_path(ctx)
+    assert no_cp()
+    L.vkvg_destroy(ctx)
+    assert L.vkvg_surface_get_reference_count(s.h) == 1
+
+
+def test_split_flushes_equal_single_flush(dev4):
+    """the second flush must read the destination back and composite over it exactly like one batch does."""
+    imgs = []
+    for split in (False, True):
+        s = v.Surface(dev4, 128, 128)
+        c = v.Context(s)
+        for k, name in enumerate(("eo", "stroke_alpha", "grad_radial", "stroke_dash")):
+            mg.pixel_scene(c, name, k)
+            if split:
+                c.flush()
+        c.flush()
+        imgs.append(s.pixels())
+    assert np.array_equal(imgs[0], imgs[1])
+
+
+def test_save_restore_and_ctm(dev4, oracle_lib):
+    o = oracle_lib.Oracle(128, 128, 4)
+    s = v.Surface(dev4, 128, 128)
+    c = v.Context(s)
+    for g in (o, c):
+        g.set_source_rgba(0, 0.5, 1, 0.8)
+        g.translate(30, 20)
+        g.rotate(0.3)
+        g.scale(1.5, 0.75)
+        g.rectangle(0, 0, 40, 40)
+        g.fill()
+        g.identity_matrix()
+        g.set_line_width(3)
+        g.arc(64, 64, 30, 0.0, 4.0)
+        g.stroke()
+    c.flush()
+    assert np.array_equal(s.pixels(), o.pixels())
+    L = v.lib()
+    c.set_line_width(7.0)
+    c.save()
+    c.set_line_width(2.0)
+    c.translate(5, 5)
+    c.restore()
+    assert L.vkvg_get_line_width(c.h) == 7.0
+    assert np.array_equal(c.get_matrix(), np.array([1, 0, 0, 1, 0, 0], np.float32))
+    c.restore()
+    assert c.status() == 3  # VKVG_STATUS_INVALID_RESTORE
+
+
+def test_command_stream_equals_direct_calls(dev4):
+    s1, s2 = v.Surface(dev4, 128, 128), v.Surface(dev4, 128, 128)
+    c1, c2 = v.Context(s1), v.Context(s2)
+    cs = v.CommandStream()
+    for g in (c1, cs):
+        mg.pixel_scene(g, "mixed", 5)
+    pts = scenes.polyline_c3(200, 128, 9, margin=4.0)
+    c1.move_to(*[float(x) for x in pts[0]])
+    for p in pts[1:]:
+        c1.line_to(float(p[0]), float(p[1]))
+    c1.stroke()
+    cs.polyline(pts)
+    cs.stroke()
+    assert c2.replay(*cs.arrays()) == 0
+    c1.flush()
+    c2.flush()
+    assert np.array_equal(s1.pixels(), s2.pixels())
+
+
+def test_invalid_dash_and_gradient_status(dev4):
+    s = v.Surface(dev4, 32, 32)
+    c = v.Context(s)
+    c.set_dash([0.0, 0.0])
+    c.move_to(1, 1)
+    c.line_to(20, 20)
+    c.stroke()
+    assert c.status() == 13  # VKVG_STATUS_INVALID_DASH, src/vkvg_context.c:860-863
+    c2 = v.Context(s)
+    c2.set_source_linear(0, 0, 10, 10, [(0, 1, 0, 0, 1)])  # one stop: count < 2 (internal.c:792-795)
+    assert c2.status() == 10  # VKVG_STATUS_PATTERN_INVALID_GRADIENT

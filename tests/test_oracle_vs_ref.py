@@ -1,0 +1,88 @@
+"""CPU: the oracle restatement against the reference's own object code (oracle/_ref/libvkvg_ref.so, built from
+the unmodified sources under /root/reference by `make -C oracle ref`).  Skipped where that library is absent."""
+import numpy as np
+import pytest
+
+from tests import scenes
+from tests.golden import make_golden as mg
+
+
+@pytest.fixture(scope="module")
+def ref_oracle(oracle_lib):
+    if not oracle_lib.ref_available():
+        pytest.skip("oracle/_ref/libvkvg_ref.so not built (no /root/reference here)")
+    return oracle_lib
+
+
+@pytest.mark.parametrize("seed", range(100, 160))
+def test_geometry_fuzz(ref_oracle, seed):
+    o, r = ref_oracle.Oracle(256, 256, 4), ref_oracle.Ref(256, 256, 4)
+    for g in (o, r):
+        scenes.random_path(g, seed)
+        g.set_line_width(0.3 + (seed % 11) * 0.9)
+        g.set_miter_limit(1.5 if seed % 5 == 0 else 10.0)
+        g.set_line_join(seed % 3)
+        g.set_line_cap((seed // 3) % 3)
+        if seed % 2:
+            g.set_dash([3 + seed % 9, 2 + seed % 4], float(seed % 7))
+    assert np.array_equal(o.path_points(), r.path_points())
+    assert np.array_equal(o.path_table(), r.path_table())
+    for g in (o, r):
+        g.stroke_preserve()
+    assert np.array_equal(o.last_vertices(), r.cached_vertices())
+    assert np.array_equal(o.last_indices(), r.cached_indices())
+
+
+def test_geometry_under_ctm(ref_oracle):
+    for seed in range(8):
+        o, r = ref_oracle.Oracle(256, 256, 4), ref_oracle.Ref(256, 256, 4)
+        for g in (o, r):
+            g.translate(20.0, 10.0)
+            g.scale(1.5 + seed * 0.25, 0.75)
+            g.rotate(0.1 * seed)
+            scenes.random_path(g, seed, size=128)
+            g.set_line_width(4.0)
+            g.set_line_join(1)
+            g.set_line_cap(1)
+            g.stroke_preserve()
+        assert np.array_equal(o.path_points(), r.path_points())
+        assert np.array_equal(o.last_vertices(), r.cached_vertices())
+        assert np.array_equal(o.last_indices(), r.cached_indices())
+
+
+@pytest.mark.parametrize("name", [n for n in mg.PIXEL_SCENES])
+def test_pixels_exact(ref_oracle, name):
+    for seed in range(3, 9):
+        o, r, o2 = ref_oracle.Oracle(128, 128, 4), ref_oracle.Ref(128, 128, 4), ref_oracle.Oracle(128, 128, 4)
+        mg.pixel_scene(o, name, seed)
+        mg.pixel_scene(r, name, seed)
+        r.render_with(o2)
+        assert np.array_equal(o.pixels(), o2.pixels()), (name, seed)
+
+
+def test_non_zero_self_intersecting_within_tolerance(ref_oracle):
+    """NON_ZERO on self-intersecting paths: the reference blends libtess triangles whose intersection vertices are new
+    floats, the oracle (and the CUDA rasteriser) evaluates winding != 0 on the original edges.  Coverage differs only
+    at isolated samples next to intersections: <= 1/255 at the 99.9th percentile, as north_star requires."""
+    diffs = []
+    for seed in range(30):
+        o, r, o2 = ref_oracle.Oracle(256, 256, 4), ref_oracle.Ref(256, 256, 4), ref_oracle.Oracle(256, 256, 4)
+        for g in (o, r):
+            scenes.random_path(g, seed)
+            g.set_fill_rule(1)
+            g.set_source_rgba(1, 0.5, 0.2, 0.6)
+            g.fill()
+        r.render_with(o2)
+        diffs.append(np.abs(o.pixels().astype(int) - o2.pixels().astype(int)).max(axis=2).ravel())
+    d = np.concatenate(diffs)
+    assert np.percentile(d, 99.9) <= 1
+    assert (d > 1).mean() < 1e-3
+
+
+@pytest.mark.parametrize("samples", [1, 4, 8])
+def test_sample_counts(ref_oracle, samples):
+    o, r, o2 = (ref_oracle.Oracle(96, 96, samples), ref_oracle.Ref(96, 96, samples), ref_oracle.Oracle(96, 96, samples))
+    mg.pixel_scene(o, "mixed", 1, size=96)
+    mg.pixel_scene(r, "mixed", 1, size=96)
+    r.render_with(o2)
+    assert np.array_equal(o.pixels(), o2.pixels())

@@ -38,10 +38,14 @@ class Stats(C.Structure):
     """vkvg_b200_stats_t (include/vkvg_b200.h)."""
     _fields_ = [(n, C.c_uint64) for n in ("n_elems", "n_points", "n_fill_edges", "n_stroke_items", "n_verts", "n_inds", "n_edges",
                                           "n_path_tiles", "n_nonempty", "n_tile_edges")] + [("ms_total", _f), ("ms_fine", _f),
-                                                                                           ("h2d_bytes", C.c_uint64)]
+                                                                                           ("h2d_bytes", C.c_uint64),
+                                                                                           ("ms_stage", _f * 5), ("pad_", _f)]
+    STAGES = ("flatten", "stroke", "edges", "binning", "fine")
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("ms_stage", "pad_")}
+        d["ms_stage"] = dict(zip(self.STAGES, [float(x) for x in self.ms_stage]))
+        return d
 
 
 _SIGS = {
@@ -98,6 +102,7 @@ _SIGS = {
     "vkvg_b200_device_ordinal": (_i, [_p]), "vkvg_b200_surface_device_pointer": (_p, [_p]),
     "vkvg_b200_flush_keep": (None, [_p]), "vkvg_b200_replay_resident": (None, [_p, _p, _i]),
     "vkvg_b200_replay": (_i, [_p, _p, C.c_uint64, _p, C.c_uint64]),
+    "vkvg_b200_time_resident": (_i, [_p, _p, _u, _i, _i, C.POINTER(Stats)]),
 }
 
 _lib = None
@@ -160,6 +165,14 @@ class Device:
 
     def synchronize(self):
         lib().vkvg_b200_device_synchronize(self.h)
+
+    def time_resident(self, surf, steps, clear_first=True, flush_l2=True):
+        """re-run the pipeline `steps` times on the batch kept by the last flush; returns summed stats (ms) as a dict."""
+        s = Stats()
+        st = lib().vkvg_b200_time_resident(self.h, surf.h, steps, int(clear_first), int(flush_l2), C.byref(s))
+        if st:
+            raise VkvgError("vkvg_b200_time_resident: status %d" % st)
+        return s.as_dict()
 
     def winding(self, edges, width, height):
         """per-sample integer winding of raw 24.8 edges through the tile rasteriser: (H, W, samples) int32."""

@@ -13,6 +13,8 @@ struct vkb_device_impl {
     int          ordinal = 0;
     cudaStream_t stream  = nullptr;
     cudaEvent_t  ev_begin = nullptr, ev_end = nullptr, ev_fine0 = nullptr, ev_fine1 = nullptr;
+    cudaEvent_t  ev_stage[VKB_N_STAGES + 1] = {};  // boundaries between pipeline stages (profiling)
+    DevBuf       l2_flush;
     // pinned staging
     uint8_t *stage     = nullptr;
     size_t   stage_cap = 0;
@@ -38,6 +40,7 @@ struct vkb_surface_impl {
     vkb_device_impl *dev;
     uint32_t         w, h;
     DevBuf           image;
+    DevBuf           ms_image, tile_ms;  // per-sample plane + per-tile validity flags (allocated by the first render)
     bool             known_clear;
 };
 
@@ -53,6 +56,7 @@ vkb_device_impl *vkb_device_open(int ordinal) {
     VKB_CUDA_OK(cudaEventCreate(&d->ev_end));
     VKB_CUDA_OK(cudaEventCreate(&d->ev_fine0));
     VKB_CUDA_OK(cudaEventCreate(&d->ev_fine1));
+    for (cudaEvent_t &e : d->ev_stage) VKB_CUDA_OK(cudaEventCreate(&e));
     VKB_CUDA_OK(cudaHostAlloc((void **)&d->readback, 16 * sizeof(uint64_t), cudaHostAllocDefault));
     if (g_cuda_failed) { delete d; return nullptr; }
     return d;
@@ -70,6 +74,8 @@ void vkb_device_close(vkb_device_impl *d) {
     for (DevBuf *b : bufs) b->release();
     if (d->stage) cudaFreeHost(d->stage);
     cudaFreeHost(d->readback);
+    for (cudaEvent_t &e : d->ev_stage) cudaEventDestroy(e);
+    d->l2_flush.release();
     cudaEventDestroy(d->ev_begin); cudaEventDestroy(d->ev_end); cudaEventDestroy(d->ev_fine0); cudaEventDestroy(d->ev_fine1);
     cudaStreamDestroy(d->stream);
     delete d;
@@ -94,6 +100,8 @@ void vkb_surface_free(vkb_surface_impl *s) {
     cudaSetDevice(s->dev->ordinal);
     cudaStreamSynchronize(s->dev->stream);
     s->image.release();
+    s->ms_image.release();
+    s->tile_ms.release();
     delete s;
 }
 void vkb_surface_clear(vkb_surface_impl *s) {
@@ -239,6 +247,7 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     vkb_edge *edges = d->edges.as<vkb_edge>();
     uint32_t *edraw = d->edge_draw.as<uint32_t>();
     // ---- 5. binning ----
+    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[3], st));
     const uint32_t n_tiles = sd.tiles_x * sd.tiles_y;
     d->draw_bbox.ensure((size_t)nd * 16, st);
     d->draw_rect.ensure((size_t)nd * 16, st);
@@ -312,6 +321,13 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     fa.hdr = d->hdr.as<int4>(); fa.tile_edges = d->tile_edges.as<vkb_edge>();
     fa.paints = d->paints.as<vkb_paint>(); fa.grads = d->grads.as<vkb_gradient>();
     fa.image = surf->image.as<uint32_t>();
+    {
+        bool fresh = surf->tile_ms.p == nullptr;
+        surf->ms_image.ensure((size_t)n_tiles * 256 * samples * 4, st);
+        surf->tile_ms.ensure((size_t)n_tiles + 16, st);
+        if (fresh || surf->known_clear) VKB_CUDA_OK(cudaMemsetAsync(surf->tile_ms.p, 0, n_tiles, st));
+    }
+    fa.ms_image = surf->ms_image.as<uint32_t>(); fa.tile_ms = surf->tile_ms.as<uint8_t>();
     fa.dst_is_clear = surf->known_clear ? 1 : 0;
     fa.winding_out = nullptr; fa.winding_draw = 0;
     DevBuf wbuf;
@@ -321,9 +337,11 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
         VKB_CUDA_OK(cudaMemsetAsync(wbuf.p, 0, wb, st));
         fa.winding_out = wbuf.as<int32_t>(); fa.winding_draw = cap->winding_draw;
     }
+    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[4], st));
     VKB_CUDA_OK(cudaEventRecord(d->ev_fine0, st));
     vkb_launch_fine(fa, st);
     VKB_CUDA_OK(cudaEventRecord(d->ev_fine1, st));
+    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[5], st));
     surf->known_clear = false;
     VKB_CUDA_OK(cudaEventRecord(d->ev_end, st));
     if (cap && cap->winding) {
@@ -335,6 +353,8 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
         VKB_CUDA_OK(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&S.ms_total, d->ev_begin, d->ev_end);
         cudaEventElapsedTime(&S.ms_fine, d->ev_fine0, d->ev_fine1);
+        if (S.ms_stage[0] >= 0.f)
+            for (int i = 0; i < VKB_N_STAGES; i++) cudaEventElapsedTime(&S.ms_stage[i], d->ev_stage[i], d->ev_stage[i + 1]);
         *stats = S;
     }
     return g_cuda_failed;
@@ -348,6 +368,7 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
     S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes;
     SurfaceDesc sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE};
     VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
+    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[0], st));
     d->totals.ensure(16 * 8, st);
     uint64_t *totals = d->totals.as<uint64_t>();
 
@@ -375,6 +396,7 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
         download(d, cap->sp_count, d->sp_count.p, d->n_sp);
     }
 
+    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[1], st));
     // ---- 2. job sizes: fill jobs need > 2 points, stroke jobs >= 2 ----
     uint32_t n_fill = 0, n_sitems = 0;
     d->fjob_base.ensure((size_t)(d->n_fjobs + 1) * 4, st);
@@ -427,6 +449,7 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
     S.n_verts = n_verts; S.n_inds = n_inds;
 
     // ---- 4. edges ----
+    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[2], st));
     const uint32_t n_tris  = n_inds / 3;
     const uint64_t n_edges = (uint64_t)n_fill + 3ull * n_tris + d->n_extra;
     S.n_edges = n_edges;
@@ -494,9 +517,34 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
     cap.winding = out; cap.winding_draw = 0;
     vkb_stats S;
     memset(&S, 0, sizeof S);
+    S.ms_stage[0] = -1.f;
     VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
     int r = bin_and_fine(d, surf, sd, 1, n, &cap, S, nullptr);
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     vkb_surface_free(surf);
     return r;
+}
+
+// bench support: `steps` resident replays, each timed on its own with CUDA events on the pipeline stream; between
+// steps (outside the timed events) a 256 MiB scratch buffer is overwritten so that no step starts with its inputs in L2.
+int vkb_time_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, uint32_t steps, bool clear_first, bool flush_l2, vkb_stats *sum) {
+    cudaSetDevice(d->ordinal);
+    vkb_stats acc;
+    memset(&acc, 0, sizeof acc);
+    for (uint32_t i = 0; i < steps; i++) {
+        if (flush_l2) {
+            d->l2_flush.ensure((size_t)256 << 20, d->stream);
+            VKB_CUDA_OK(cudaMemsetAsync(d->l2_flush.p, (int)(i & 0xff), (size_t)256 << 20, d->stream));
+        }
+        if (clear_first) vkb_surface_clear(s);
+        vkb_stats st;
+        if (vkb_render_resident(d, s, samples, nullptr, &st)) return 1;
+        float tot = acc.ms_total + st.ms_total, fine = acc.ms_fine + st.ms_fine, stage[VKB_N_STAGES];
+        for (int k = 0; k < VKB_N_STAGES; k++) stage[k] = acc.ms_stage[k] + st.ms_stage[k];
+        acc = st;
+        acc.ms_total = tot; acc.ms_fine = fine;
+        for (int k = 0; k < VKB_N_STAGES; k++) acc.ms_stage[k] = stage[k];
+    }
+    if (sum) *sum = acc;
+    return g_cuda_failed;
 }

@@ -482,111 +482,197 @@ __device__ void eval_paint(uint32_t pattern, const vkb_gradient *g, float W, flo
 #pragma unroll
     for (int k = 0; k < 4; k++) out[k] = c[k] * opacity;
 }
-__device__ __forceinline__ uint32_t unorm8(float v) {
-    float q = v * 255.0f + 0.5f;
-    if (!(q > 0.0f)) return 0;
-    if (q >= 255.5f) return 255;
-    return (uint32_t)q;
-}
-// premultiplied OVER per channel with UNORM8 store, src/vkvg_device_internal.c:203-209
-__device__ __forceinline__ uint32_t blend_over(uint32_t dst, const float s[4]) {
+// UNORM8 store conversion: round to nearest of v*255, clamped (NaN -> 0)
+__device__ __forceinline__ uint32_t unorm8(float v) { return (uint32_t)fminf(fmaxf(v * 255.0f + 0.5f, 0.0f), 255.0f); }
+// premultiplied OVER per channel with UNORM8 store, src/vkvg_device_internal.c:203-209.  `lut[i]` holds the exactly
+// rounded float i / 255.0f (a table look-up instead of an IEEE division per channel per sample).
+__device__ __forceinline__ uint32_t blend_over(uint32_t dst, const float s[4], float ia, const float *lut) {
     uint32_t out = 0;
-    float    ia  = 1.0f - s[3];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        float d = (float)((dst >> (8 * k)) & 0xFF) / 255.0f;
+        float d = lut[(dst >> (8 * k)) & 0xFF];
         float r = s[k] + d * ia;
         out |= unorm8(r) << (8 * k);
     }
     return out;
 }
 
+// sign of (2*q - r) without forming it: > 0 <=> q > floor(r/2), < 0 <=> q < ceil(r/2)
+__device__ __forceinline__ bool twice_gt(int32_t q, int32_t r) { return q > (r >> 1); }
+__device__ __forceinline__ bool twice_lt(int32_t q, int32_t r) { return q < ((r + 1) >> 1); }
+
+// One edge against the S samples of this thread's pixel, all in TILE-RELATIVE 24.8 coordinates (origin = tile corner,
+// virtual column L at x = 1/2, virtual sample C at (1/2, 1/2)).  NEAR edges have every coordinate in [-16384, 20479],
+// so each product below fits 32 bits (|dx|,|dy| <= 36863, |sample - endpoint| <= 20479: products < 7.6e8, sums < 1.6e9).
+template <int S>
+__device__ __forceinline__ void edge_near(int32_t ax, int32_t ay, int32_t bx, int32_t by, bool crossL, const int32_t (&sx)[S], const int32_t (&sy)[S],
+                                          int32_t (&w)[S]) {
+    const int32_t dx = bx - ax, dy = by - ay;
+    const int32_t K  = dy * ax - dx * ay;  // m(y) = dx*y + K = dx*(y - ay) + dy*ax ;  E(L,y)*2 = 2*m - dy ;  E(s) = m - dy*sx
+    if (dy > 0) {
+        const int32_t h = dy >> 1;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if ((ay <= sy[s]) != (by <= sy[s])) {
+                const int32_t m = dx * sy[s] + K;
+                w[s] += (int)(m - dy * sx[s] <= 0) - (int)(m <= h);
+            }
+    } else if (dy < 0) {
+        const int32_t h = (dy + 1) >> 1;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if ((ay <= sy[s]) != (by <= sy[s])) {
+                const int32_t m = dx * sy[s] + K;
+                w[s] -= (int)(m - dy * sx[s] >= 0) - (int)(m >= h);
+            }
+    }
+    if (crossL) {  // V term: crossings of the vertical segment from C down to (L, sample y)
+        const bool tie = dy == 0 || ((dx > 0) != (dy > 0));
+        const int32_t rc = dy - dx;  // E(C)*1 = 2*K - rc
+        if (dx > 0) {
+            const int belowC = twice_gt(K, rc) || (!twice_lt(K, rc) && tie);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int32_t m = dx * sy[s] + K;
+                w[s] -= (int)(twice_gt(m, dy) || (!twice_lt(m, dy) && tie)) - belowC;
+            }
+        } else {
+            const int belowC = twice_lt(K, rc) || (!twice_gt(K, rc) && tie);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int32_t m = dx * sy[s] + K;
+                w[s] += (int)(twice_lt(m, dy) || (!twice_gt(m, dy) && tie)) - belowC;
+            }
+        }
+    }
+}
+// same arithmetic in 64 bits for edges that reach far from the tile (coordinates are clamped to +-2^28 by vs_snap, so
+// every difference fits int32 and every product is one 32x32->64 multiply)
+template <int S>
+__device__ __forceinline__ void edge_far(int32_t ax, int32_t ay, int32_t bx, int32_t by, bool crossL, const int32_t (&sx)[S], const int32_t (&sy)[S],
+                                         int32_t (&w)[S]) {
+    const int32_t   dx = bx - ax, dy = by - ay;
+    const int       sdy = dy > 0 ? 1 : (dy < 0 ? -1 : 0), sdx = dx > 0 ? 1 : (dx < 0 ? -1 : 0);
+    const long long kL  = (long long)dy * (1 - 2 * ax);  // E2(L, y) = 2*dx*(y - ay) - kL
+    int             belowC = 0;
+    if (crossL) {
+        long long EC = (long long)dx * (1 - 2 * ay) - kL;
+        belowC       = (sdx > 0 ? EC > 0 : EC < 0) || (EC == 0 && (dy == 0 || sdx != sdy));
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int32_t   ys = sy[s];
+        const long long t  = (long long)dx * (ys - ay);
+        const long long EL = 2 * t - kL;
+        if ((ay <= ys) != (by <= ys)) {  // H term: crossing strictly right of L and at or left of the sample
+            const long long Es = t - (long long)dy * (sx[s] - ax);
+            const int       ls = dy > 0 ? (Es <= 0) : (Es >= 0);
+            const int       lL = dy > 0 ? (EL <= 0) : (EL >= 0);
+            w[s] += sdy * (ls - lL);
+        }
+        if (crossL) {
+            const int below = (sdx > 0 ? EL > 0 : EL < 0) || (EL == 0 && (dy == 0 || sdx != sdy));
+            w[s] -= sdx * (below - belowC);
+        }
+    }
+}
+
 template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
     const uint32_t tile  = blockIdx.x;
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) return;  // no draw of this batch touches the tile: the stored pixels stay as they are
+    __shared__ float lut[256];
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
     const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
-    const uint32_t px = tx * VKB_TILE + (threadIdx.x & 15), py = ty * VKB_TILE + (threadIdx.x >> 4);
+    const uint32_t lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
     const bool     inside = px < a.sd.width && py < a.sd.height;
     const size_t   pix    = (size_t)py * a.sd.width + px;
+    const size_t   mspix  = ((size_t)tile * 256 + threadIdx.x) * S;  // per-sample plane is tile-major
 
     uint32_t col[S];
-    {
+    if (!a.dst_is_clear && a.tile_ms[tile]) {  // samples of this tile differed after an earlier flush
+#pragma unroll
+        for (int s = 0; s < S; s++) col[s] = a.ms_image[mspix + s];
+    } else {
         uint32_t c = (!a.dst_is_clear && inside) ? a.image[pix] : 0u;
 #pragma unroll
         for (int s = 0; s < S; s++) col[s] = c;
     }
-    const int32_t   X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
-    const long long L2 = 2ll * X0 + 1, C2 = 2ll * Y0 + 1;
-    int32_t         sx[S], sy[S];
+    const int32_t X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
+    int32_t       sx[S], sy[S];  // tile-relative sample coordinates
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        sx[s] = (int32_t)px * 256 + SamplePos<S>::x(s) * 16;
-        sy[s] = (int32_t)py * 256 + SamplePos<S>::y(s) * 16;
+        sx[s] = (int32_t)lx * 256 + SamplePos<S>::x(s) * 16;
+        sy[s] = (int32_t)ly * 256 + SamplePos<S>::y(s) * 16;
     }
+    // sample rows of this warp (two pixel rows): an edge whose y-range misses them and that does not cross L adds nothing
+    const int32_t wy_lo = (int32_t)(threadIdx.x >> 5) * 512, wy_hi = wy_lo + 511;
+    __syncthreads();
 
+    int4 h = a.hdr[first];
     for (uint32_t p = first; p < end; p++) {
-        const int4 h = a.hdr[p];
-        int32_t    w[S];
+        const int4      hn = p + 1 < end ? a.hdr[p + 1] : h;
+        const vkb_paint pt = a.paints[h.x];
+        int32_t         w[S];
 #pragma unroll
         for (int s = 0; s < S; s++) w[s] = h.y;
         const vkb_edge *ep = a.tile_edges + (uint32_t)h.z;
         for (uint32_t k = 0; k < (uint32_t)h.w; k++) {
-            // coordinates are clamped to +-2^28 by vs_snap, so every difference fits int32 and every product
-            // below is one 32x32->64 multiply (IMAD.WIDE)
-            const int4      ev = __ldg((const int4 *)(ep + k));
-            const int32_t   ax = ev.x, ay = ev.y, bx = ev.z, by = ev.w;
-            const int32_t   dx = bx - ax, dy = by - ay;
-            const int       sdy = dy > 0 ? 1 : (dy < 0 ? -1 : 0), sdx = dx > 0 ? 1 : (dx < 0 ? -1 : 0);
-            const bool      crossL = (ax <= X0) != (bx <= X0);
-            const long long kL     = (long long)dy * (int32_t)(L2 - 2ll * ax);  // E2(L, y) = 2*dx*(y - ay) - kL
-            int             belowC = 0;
-            if (crossL) {
-                long long EC = (long long)dx * (int32_t)(C2 - 2ll * ay) - kL;
-                belowC       = (sdx > 0 ? EC > 0 : EC < 0) || (EC == 0 && (dy == 0 || sdx != sdy));
-            }
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int32_t   ys = sy[s];
-                const long long t  = (long long)dx * (ys - ay);
-                const long long EL = 2 * t - kL;
-                if ((ay <= ys) != (by <= ys)) {  // H term: crossing strictly right of L and at or left of the sample
-                    const long long Es = t - (long long)dy * (sx[s] - ax);
-                    const int       ls = dy > 0 ? (Es <= 0) : (Es >= 0);
-                    const int       lL = dy > 0 ? (EL <= 0) : (EL >= 0);
-                    w[s] += sdy * (ls - lL);
-                }
-                if (crossL) {  // V term
-                    const int below = (sdx > 0 ? EL > 0 : EL < 0) || (EL == 0 && (dy == 0 || sdx != sdy));
-                    w[s] -= sdx * (below - belowC);
-                }
-            }
+            const int4    ev = __ldg((const int4 *)(ep + k));
+            const int32_t ax = ev.x - X0, ay = ev.y - Y0, bx = ev.z - X0, by = ev.w - Y0;
+            const bool    crossL = (ax <= 0) != (bx <= 0);
+            if (!crossL && (max(ay, by) <= wy_lo || min(ay, by) > wy_hi)) continue;  // warp-uniform
+            const bool near = (uint32_t)(ax + 16384) < 36864u && (uint32_t)(ay + 16384) < 36864u && (uint32_t)(bx + 16384) < 36864u &&
+                              (uint32_t)(by + 16384) < 36864u;
+            if (near) edge_near<S>(ax, ay, bx, by, crossL, sx, sy, w);
+            else edge_far<S>(ax, ay, bx, by, crossL, sx, sy, w);
         }
         if (a.winding_out && (uint32_t)h.x == a.winding_draw && inside) {
 #pragma unroll
             for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
         }
-        const vkb_paint pt      = a.paints[h.x];
-        const uint32_t  rule    = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
-        uint32_t        any     = 0;
-        int32_t         n[S];
+        const uint32_t rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
+        uint32_t       any = 0;
+        int32_t        n[S];
+        bool           same = true;
 #pragma unroll
         for (int s = 0; s < S; s++) {
             int32_t v = w[s];
             n[s]      = rule == VKB_RULE_EVEN_ODD ? (v & 1) : (rule == VKB_RULE_NON_ZERO ? (v != 0) : (v < 0 ? -v : v));
             any |= (uint32_t)n[s];
+            same = same && n[s] == n[0] && col[s] == col[0];
         }
         if (any) {
             float src[4];
             eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src);
-            const bool opaque = src[3] >= 1.0f;  // repeated OVER of an opaque source is idempotent
+            const float ia     = 1.0f - src[3];
+            const bool  opaque = src[3] >= 1.0f;  // repeated OVER of an opaque source is idempotent
+            if (same) {  // interior pixel: every sample holds the same colour and gets the same number of blends
+                uint32_t c = col[0];
+                int32_t  reps = opaque ? 1 : n[0];
+                for (int32_t r = 0; r < reps; r++) c = blend_over(c, src, ia, lut);
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-                int32_t reps = opaque ? (n[s] ? 1 : 0) : n[s];
-                for (int32_t r = 0; r < reps; r++) col[s] = blend_over(col[s], src);
+                for (int s = 0; s < S; s++) col[s] = c;
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    int32_t reps = opaque ? (n[s] ? 1 : 0) : n[s];
+                    for (int32_t r = 0; r < reps; r++) col[s] = blend_over(col[s], src, ia, lut);
+                }
             }
         }
+        h = hn;
     }
+    bool differ = false;
+#pragma unroll
+    for (int s = 1; s < S; s++) differ = differ || col[s] != col[0];
+    const int tile_differs = __syncthreads_or(differ);
+    if (tile_differs) {
+#pragma unroll
+        for (int s = 0; s < S; s++) a.ms_image[mspix + s] = col[s];
+    }
+    if (threadIdx.x == 0) a.tile_ms[tile] = tile_differs ? 1 : 0;
     if (inside) {
         uint32_t out = 0;
 #pragma unroll

@@ -35,10 +35,13 @@ struct vkb_capture {
     bool                   geometry_only = false;  // stop before binning / fine
 };
 
+#define VKB_N_STAGES 5  // flatten, stroke, edges, binning, fine
 struct vkb_stats {            // filled by every render
     uint64_t n_elems, n_points, n_fill_edges, n_stroke_items, n_verts, n_inds, n_edges, n_path_tiles, n_nonempty, n_tile_edges;
     float    ms_total, ms_fine;  // CUDA-event durations on the device stream
     uint64_t h2d_bytes;
+    float    ms_stage[VKB_N_STAGES];  // flatten | job tables + stroke expansion | edge build | binning + sort | fine pass
+    float    pad_;
 };
 
 struct vkb_device_impl;
@@ -61,3 +64,4 @@ int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const 
 // upload only (bench: inputs resident in HBM); then vkb_render_resident re-runs the pipeline on that batch
 int vkb_upload(vkb_device_impl *d, const vkb_batch &b);
 int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, vkb_capture *cap, vkb_stats *stats);
+int vkb_time_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, uint32_t steps, bool clear_first, bool flush_l2, vkb_stats *sum);

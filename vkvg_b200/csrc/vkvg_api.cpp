@@ -1030,6 +1030,17 @@ void vkvg_b200_replay_resident(VkvgDevice dev, VkvgSurface surf, int clear_first
     if (vkb_render_resident(dev->impl, surf->impl, dev->samples, nullptr, dev->profiling ? &st : nullptr)) dev->status = VKVG_STATUS_DEVICE_ERROR;
     if (dev->profiling) dev->last = st;
 }
+vkvg_status_t vkvg_b200_time_resident(VkvgDevice dev, VkvgSurface surf, uint32_t steps, int clear_first, int flush_l2, vkvg_b200_stats_t *sum) {
+    if (vkvg_device_status(dev) || vkvg_surface_status(surf)) return VKVG_STATUS_DEVICE_ERROR;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    vkb_stats st;
+    if (vkb_time_resident(dev->impl, surf->impl, dev->samples, steps, clear_first != 0, flush_l2 != 0, &st)) {
+        dev->status = VKVG_STATUS_DEVICE_ERROR;
+        return VKVG_STATUS_DEVICE_ERROR;
+    }
+    if (sum) memcpy(sum, &st, sizeof st);
+    return VKVG_STATUS_SUCCESS;
+}
 
 vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *a, uint64_t n_args) {
     if (vkvg_status(ctx)) return vkvg_status(ctx);
