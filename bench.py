@@ -289,12 +289,21 @@ def run_ours(args):
     out_t = torch.empty((size, size, 4), dtype=torch.uint8).pin_memory()
     L = v.lib()
 
+    parts = [0.0, 0.0, 0.0]
+
     def e2e_step():
+        t0 = time.perf_counter()
         L.vkvg_clear(ctx.h)
         st = L.vkvg_b200_replay(ctx.h, ops_t.data_ptr(), ops_t.numel(), args_t.data_ptr(), args_t.numel())
         assert st == 0, st
+        t1 = time.perf_counter()
         L.vkvg_flush(ctx.h)
+        t2 = time.perf_counter()
         assert L.vkvg_b200_surface_read_premultiplied(surf.h, out_t.data_ptr()) == 0
+        t3 = time.perf_counter()
+        parts[0] += t1 - t0
+        parts[1] += t2 - t1
+        parts[2] += t3 - t2
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -313,6 +322,7 @@ def run_ours(args):
     ms_step = max_over_ranks(st["ms_total"] / args.steps)
     # ---- end to end through the C ABI with host buffers ----
     barrier()
+    parts[:] = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
@@ -334,9 +344,11 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[w], "rule": args.rule, "samples": 4, "sharding": "one independent canvas per rank",
                    "l2": "256 MiB scratch overwritten between timed steps", **info, "n_edges": int(n_edges),
-                   "n_tile_edges": int(st["n_tile_edges"]), "n_points": int(st["n_points"])},
+                   "n_tile_edges": int(st["n_tile_edges"]), "n_points": int(st["n_points"]), "n_path_tiles": int(st["n_nonempty"])},
         "e2e": {"value": world * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()),
-                "d2h_bytes_per_step": int(out_t.numel()), "ms_per_step": e2e_s * 1e3},
+                "d2h_bytes_per_step": int(out_t.numel()), "ms_per_step": e2e_s * 1e3,
+                "host_record_ms": parts[0] / args.steps * 1e3, "upload_render_ms": parts[1] / args.steps * 1e3,
+                "readback_ms": parts[2] / args.steps * 1e3},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "fine_k<4>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "algorithmic_bytes": int(alg_bytes), "kernel_ms": fine_ms, "peak_source": peak_src,

@@ -114,8 +114,8 @@ def curves_c4(n, size, seed):
     for i in range(n):
         cx, cy = u[i, 0] * size, u[i, 1] * size
         k = 4 + int(u[i, 2] * 5)
-        rr = 16 + 80 * u[i, 3:3 + 6 * k]
-        aa = 2 * math.pi * u[i, 51:51 + 6 * k]
+        rr = 16 + 80 * u[i, 3:3 + 3 * k]
+        aa = 2 * math.pi * u[i, 51:51 + 3 * k]
         px, py = cx + rr * np.cos(aa), cy + rr * np.sin(aa)
         pts = np.stack([px, py], 1).astype(np.float32).reshape(k, 3, 2)
         alpha = 1.0 if (i // 2) % 2 == 0 else 0.5

@@ -427,7 +427,8 @@ __device__ __forceinline__ void mix4(float *c, const float *b, float t) {
 }
 // shaders/vkvg_main.frag:68-157 (SOLID / LINEAR / RADIAL) at the pixel centre; identical arithmetic to
 // oracle/vkvg_oracle.c: eval_paint
-__device__ void eval_paint(uint32_t pattern, const vkb_gradient *g, float W, float H, uint32_t solid, float opacity, float fx, float fy, float out[4]) {
+__device__ void eval_paint(uint32_t pattern, const vkb_gradient *g, float W, float H, uint32_t solid, float opacity, float fx, float fy, float out[4],
+                           const float *lut) {
     float c[4];
     if (pattern == VKB_PAT_LINEAR) {
         float p0x = g->cp[0][0] / W, p0y = g->cp[0][1] / H;
@@ -474,16 +475,22 @@ __device__ void eval_paint(uint32_t pattern, const vkb_gradient *g, float W, flo
         mix4(c, g->colors[1], smoothstepf(g->stops[0], g->stops[1], grad));
         for (uint32_t i = 2; i < g->count; i++) mix4(c, g->colors[i], smoothstepf(g->stops[i - 1], g->stops[i], grad));
     } else {
-        c[0] = (float)(solid & 0xFF) / 255.0f;
-        c[1] = (float)((solid >> 8) & 0xFF) / 255.0f;
-        c[2] = (float)((solid >> 16) & 0xFF) / 255.0f;
-        c[3] = (float)((solid >> 24) & 0xFF) / 255.0f;
+        c[0] = lut[solid & 0xFF];  // lut[i] == (float)i / 255.0f exactly
+        c[1] = lut[(solid >> 8) & 0xFF];
+        c[2] = lut[(solid >> 16) & 0xFF];
+        c[3] = lut[solid >> 24];
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) out[k] = c[k] * opacity;
 }
 // UNORM8 store conversion: round to nearest of v*255, clamped (NaN -> 0)
-__device__ __forceinline__ uint32_t unorm8(float v) { return (uint32_t)fminf(fmaxf(v * 255.0f + 0.5f, 0.0f), 255.0f); }
+// (one saturating truncating convert: F2IP.U8.F32.TRUNC; NaN and negatives give 0, >= 255.5 gives 255)
+__device__ __forceinline__ uint32_t unorm8(float v) {
+    uint32_t r;
+    float    q = v * 255.0f + 0.5f;
+    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(q));
+    return r;
+}
 // premultiplied OVER per channel with UNORM8 store, src/vkvg_device_internal.c:203-209.  `lut[i]` holds the exactly
 // rounded float i / 255.0f (a table look-up instead of an IEEE division per channel per sample).
 __device__ __forceinline__ uint32_t blend_over(uint32_t dst, const float s[4], float ia, const float *lut) {
@@ -618,11 +625,13 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
 #pragma unroll
         for (int s = 0; s < S; s++) w[s] = h.y;
         const vkb_edge *ep = a.tile_edges + (uint32_t)h.z;
+        bool touched = h.y != 0;
         for (uint32_t k = 0; k < (uint32_t)h.w; k++) {
             const int4    ev = __ldg((const int4 *)(ep + k));
             const int32_t ax = ev.x - X0, ay = ev.y - Y0, bx = ev.z - X0, by = ev.w - Y0;
             const bool    crossL = (ax <= 0) != (bx <= 0);
             if (!crossL && (max(ay, by) <= wy_lo || min(ay, by) > wy_hi)) continue;  // warp-uniform
+            touched = true;
             const bool near = (uint32_t)(ax + 16384) < 36864u && (uint32_t)(ay + 16384) < 36864u && (uint32_t)(bx + 16384) < 36864u &&
                               (uint32_t)(by + 16384) < 36864u;
             if (near) edge_near<S>(ax, ay, bx, by, crossL, sx, sy, w);
@@ -632,34 +641,43 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
 #pragma unroll
             for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
         }
+        int32_t wor = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) wor |= w[s];
+        if (!touched || !__any_sync(0xffffffffu, wor != 0)) {  // nothing of this draw reaches the two pixel rows of this warp
+            h = hn;
+            continue;
+        }
         const uint32_t rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
-        uint32_t       any = 0;
-        int32_t        n[S];
-        bool           same = true;
+        int32_t        n[S], nmax = 0;
+        bool           uni = true, two = true;
 #pragma unroll
         for (int s = 0; s < S; s++) {
             int32_t v = w[s];
             n[s]      = rule == VKB_RULE_EVEN_ODD ? (v & 1) : (rule == VKB_RULE_NON_ZERO ? (v != 0) : (v < 0 ? -v : v));
-            any |= (uint32_t)n[s];
-            same = same && n[s] == n[0] && col[s] == col[0];
+            nmax      = max(nmax, n[s]);
+            uni       = uni && col[s] == col[0];
         }
-        if (any) {
+        if (nmax) {
             float src[4];
-            eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src);
-            const float ia     = 1.0f - src[3];
-            const bool  opaque = src[3] >= 1.0f;  // repeated OVER of an opaque source is idempotent
-            if (same) {  // interior pixel: every sample holds the same colour and gets the same number of blends
-                uint32_t c = col[0];
-                int32_t  reps = opaque ? 1 : n[0];
-                for (int32_t r = 0; r < reps; r++) c = blend_over(c, src, ia, lut);
+            eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src, lut);
+            const float ia = 1.0f - src[3];
+            if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
+                nmax = 1;
 #pragma unroll
-                for (int s = 0; s < S; s++) col[s] = c;
+                for (int s = 0; s < S; s++) n[s] = n[s] ? 1 : 0;
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) two = two && (n[s] == 0 || n[s] == nmax);
+            if (uni && two) {  // every sample holds the same colour and is blended either nmax times or not at all: blend once
+                uint32_t c = col[0];
+                for (int32_t r = 0; r < nmax; r++) c = blend_over(c, src, ia, lut);
+#pragma unroll
+                for (int s = 0; s < S; s++) col[s] = n[s] ? c : col[s];
             } else {
 #pragma unroll
-                for (int s = 0; s < S; s++) {
-                    int32_t reps = opaque ? (n[s] ? 1 : 0) : n[s];
-                    for (int32_t r = 0; r < reps; r++) col[s] = blend_over(col[s], src, ia, lut);
-                }
+                for (int s = 0; s < S; s++)
+                    for (int32_t r = 0; r < n[s]; r++) col[s] = blend_over(col[s], src, ia, lut);
             }
         }
         h = hn;

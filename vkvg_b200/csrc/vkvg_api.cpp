@@ -433,13 +433,46 @@ static void push_elem(VkvgContext ctx, uint32_t type_flags, const float *payload
     b.elem_hdr.push_back(type_flags | ((uint32_t)b.elem_data.size() << VKB_EL_PAYLOAD_SHIFT));
     b.elem_data.insert(b.elem_data.end(), payload, payload + n);
 }
-static void add_point(VkvgContext ctx, float x, float y, bool curved) {  // _add_point, internal.c:221-238
+static inline void add_point(VkvgContext ctx, float x, float y, bool curved) {  // _add_point, internal.c:221-238
     if (isnan(x) || isnan(y)) return;
-    float p[2] = {x, y};
-    push_elem(ctx, VKB_EL_POINT | (curved ? VKB_EL_CURVED : 0), p, 2);
+    vkb_batch &b = ctx->batch;
+    b.elem_hdr.push_back(VKB_EL_POINT | (curved ? VKB_EL_CURVED : 0) | ((uint32_t)b.elem_data.size() << VKB_EL_PAYLOAD_SHIFT));
+    b.elem_data.push_back(x);
+    b.elem_data.push_back(y);
     if (ctx->sp_points == 0) { ctx->first_x = x; ctx->first_y = y; }
     ctx->cur_x = x; ctx->cur_y = y;
     ctx->sp_points++;
+}
+static void finish_path(VkvgContext ctx, uint32_t flags = 0);
+// move_to(p[0]) followed by line_to(p[1..n-1]) with the same NaN / duplicate-point rules, written in bulk
+static void add_polyline(VkvgContext ctx, const float *p, uint64_t n) {
+    if (!n) return;
+    finish_path(ctx, 0);
+    vkb_batch &b = ctx->batch;
+    const size_t h0 = b.elem_hdr.size(), d0 = b.elem_data.size();
+    b.elem_hdr.resize(h0 + n);
+    b.elem_data.resize(d0 + 2 * n);
+    uint32_t *hdr = b.elem_hdr.data() + h0;
+    float    *dat = b.elem_data.data() + d0;
+    uint64_t  k = 0;
+    float     cx = 0, cy = 0;
+    for (uint64_t j = 0; j < n; j++) {
+        const float x = p[2 * j], y = p[2 * j + 1];
+        if (isnan(x) || isnan(y)) continue;                       // _add_point
+        if (k && j && EQUF(cx, x) && EQUF(cy, y)) continue;         // _line_to (the first call is move_to: no test)
+        hdr[k] = VKB_EL_POINT | ((uint32_t)(d0 + 2 * k) << VKB_EL_PAYLOAD_SHIFT);
+        dat[2 * k] = x; dat[2 * k + 1] = y;
+        cx = x; cy = y;
+        k++;
+    }
+    b.elem_hdr.resize(h0 + k);
+    b.elem_data.resize(d0 + 2 * k);
+    if (k) {
+        ctx->first_x = dat[0]; ctx->first_y = dat[1];
+        ctx->cur_x = cx; ctx->cur_y = cy;
+        ctx->sp_points = (uint32_t)k;
+        ctx->simpleConvex = false;
+    }
 }
 static void end_subpath(VkvgContext ctx, uint32_t flags) {
     vkb_subpath sp = {ctx->sp_first_elem, (uint32_t)ctx->batch.elem_hdr.size() - ctx->sp_first_elem, flags, 0};
@@ -448,7 +481,7 @@ static void end_subpath(VkvgContext ctx, uint32_t flags) {
     ctx->sp_points = 0;
     ctx->simpleConvex = false;
 }
-static void finish_path(VkvgContext ctx, uint32_t flags = 0) {  // _finish_path, internal.c:163-197
+static void finish_path(VkvgContext ctx, uint32_t flags) {  // _finish_path, internal.c:163-197
     if (ctx->sp_points == 0) return;
     if (ctx->sp_points < 2) {  // only the current position is in the path: drop it
         ctx->batch.elem_data.resize(ctx->batch.elem_hdr[ctx->sp_first_elem] >> VKB_EL_PAYLOAD_SHIFT);
@@ -827,23 +860,29 @@ void vkvg_clear(VkvgContext ctx) {  // :734-753: everything drawn so far is wipe
 // keep the current (preserved / under construction) path across a flush: compact it to the front of the batch
 static void carry_path_over(VkvgContext ctx) {
     vkb_batch &b = ctx->batch;
-    vkb_batch  n;
     uint32_t   e0 = ctx->path_first_sp < b.subpaths.size() ? b.subpaths[ctx->path_first_sp].first_elem : ctx->sp_first_elem;
     uint32_t   d0 = e0 < b.elem_hdr.size() ? (b.elem_hdr[e0] >> VKB_EL_PAYLOAD_SHIFT) : (uint32_t)b.elem_data.size();
-    for (uint32_t i = e0; i < b.elem_hdr.size(); i++) {
-        uint32_t h = b.elem_hdr[i];
-        n.elem_hdr.push_back((h & ((1u << VKB_EL_PAYLOAD_SHIFT) - 1)) | (((h >> VKB_EL_PAYLOAD_SHIFT) - d0) << VKB_EL_PAYLOAD_SHIFT));
+    // in place (the vectors keep their capacity from flush to flush: steady-state recording never reallocates)
+    size_t nh = b.elem_hdr.size() - e0;
+    for (size_t i = 0; i < nh; i++) {
+        uint32_t h = b.elem_hdr[e0 + i];
+        b.elem_hdr[i] = (h & ((1u << VKB_EL_PAYLOAD_SHIFT) - 1)) | (((h >> VKB_EL_PAYLOAD_SHIFT) - d0) << VKB_EL_PAYLOAD_SHIFT);
     }
-    n.elem_data.assign(b.elem_data.begin() + d0, b.elem_data.end());
-    for (uint32_t i = ctx->path_first_sp; i < b.subpaths.size(); i++) {
-        vkb_subpath sp = b.subpaths[i];
+    b.elem_hdr.resize(nh);
+    size_t nd = b.elem_data.size() - d0;
+    if (nd && d0) memmove(b.elem_data.data(), b.elem_data.data() + d0, nd * sizeof(float));
+    b.elem_data.resize(nd);
+    size_t ns = b.subpaths.size() - ctx->path_first_sp;
+    for (size_t i = 0; i < ns; i++) {
+        vkb_subpath sp = b.subpaths[ctx->path_first_sp + i];
         sp.first_elem -= e0;
-        n.subpaths.push_back(sp);
+        b.subpaths[i] = sp;
     }
+    b.subpaths.resize(ns);
+    b.draws.clear(); b.grads.clear(); b.dashes.clear();
     ctx->sp_first_elem -= e0;
     ctx->path_first_sp = 0;
     ctx->grad_slot     = -1;
-    b = std::move(n);
 }
 static void flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident) {
     VkvgDevice dev = ctx->dev;
@@ -1104,9 +1143,7 @@ vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_o
             memcpy(&nbits, &a[k], 4);  // the point count travels as raw uint32 bits (a float cannot hold every count)
             uint64_t n = nbits;
             NEED(1 + 2 * n);
-            const float *p = a + k + 1;
-            if (n) vkvg_move_to(ctx, p[0], p[1]);
-            for (uint64_t j = 1; j < n; j++) vkvg_line_to(ctx, p[2 * j], p[2 * j + 1]);
+            add_polyline(ctx, a + k + 1, n);
             k += 1 + 2 * n;
             break;
         }
