@@ -40,7 +40,7 @@ struct vkb_surface_impl {
     vkb_device_impl *dev;
     uint32_t         w, h;
     DevBuf           image;
-    DevBuf           ms_image, tile_ms;  // per-sample plane + per-tile validity flags (allocated by the first render)
+    DevBuf           ms_image, tile_ms, ms_mask;  // per-sample plane + per-tile validity flags (allocated by the first render)
     bool             known_clear;
 };
 
@@ -102,6 +102,7 @@ void vkb_surface_free(vkb_surface_impl *s) {
     s->image.release();
     s->ms_image.release();
     s->tile_ms.release();
+    s->ms_mask.release();
     delete s;
 }
 void vkb_surface_clear(vkb_surface_impl *s) {
@@ -325,9 +326,10 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
         bool fresh = surf->tile_ms.p == nullptr;
         surf->ms_image.ensure((size_t)n_tiles * 256 * samples * 4, st);
         surf->tile_ms.ensure((size_t)n_tiles + 16, st);
+        surf->ms_mask.ensure((size_t)n_tiles * 32 + 16, st);
         if (fresh || surf->known_clear) VKB_CUDA_OK(cudaMemsetAsync(surf->tile_ms.p, 0, n_tiles, st));
     }
-    fa.ms_image = surf->ms_image.as<uint32_t>(); fa.tile_ms = surf->tile_ms.as<uint8_t>();
+    fa.ms_image = surf->ms_image.as<uint32_t>(); fa.tile_ms = surf->tile_ms.as<uint8_t>(); fa.ms_mask = surf->ms_mask.as<uint32_t>();
     fa.dst_is_clear = surf->known_clear ? 1 : 0;
     fa.winding_out = nullptr; fa.winding_draw = 0;
     DevBuf wbuf;

@@ -78,6 +78,7 @@ struct FineArgs {
     uint32_t           *image;       // width*height premultiplied RGBA8 (resolved)
     uint32_t           *ms_image;    // per-sample colours, tile-major [tile][256][S]; valid for tiles whose tile_ms flag is set
     uint8_t            *tile_ms;     // per tile: 1 when the samples of some pixel differ (the resolved image alone would lose them)
+    uint32_t           *ms_mask;     // per tile: 8 words (one per warp = two pixel rows), bit = that pixel's samples are in ms_image
     int                 dst_is_clear;  // destination known to be transparent black: do not read it
     int32_t            *winding_out; // optional: per-sample winding of the LAST draw touching each sample (parity tests), or null
     uint32_t            winding_draw; // draw index captured into winding_out

@@ -504,192 +504,318 @@ __device__ __forceinline__ uint32_t blend_over(uint32_t dst, const float s[4], f
     return out;
 }
 
-// sign of (2*q - r) without forming it: > 0 <=> q > floor(r/2), < 0 <=> q < ceil(r/2)
-__device__ __forceinline__ bool twice_gt(int32_t q, int32_t r) { return q > (r >> 1); }
-__device__ __forceinline__ bool twice_lt(int32_t q, int32_t r) { return q < ((r + 1) >> 1); }
+// ----------------------------------------------------------------------------------------------------
+// fine pass, "row-delta" formulation.
+//
+// A tile holds 16*S sample rows (pixel row ly, sample s: all 16 samples of a row share one y and one x offset).
+// For one edge and one sample row the H term is a step function of the pixel column c:
+//     dy > 0:  +[c >= c0] - [crossing at or left of L]          dy < 0:  -[c >= c0] + [crossing at or left of L]
+// with c0 = the first column whose sample is at or right of the crossing, and the V term is constant along the row.
+// So instead of testing every sample against every edge (16*S*16 tests per edge), one lane per sample row finds c0
+// exactly (integer binary search), adds +-1 to a per-column DELTA and folds the row constants into a BASE; a prefix sum
+// over the 16 columns at the end gives the partial winding of every sample of the row.  The work is organised in TASKS
+// (a path-tile, or a chunk of at most FINE_CH of its edges): each of the 8 warps of the block turns one task into
+// 16*S rows x 16 biased int8 partial windings in shared memory (phase A); then every thread, which owns one pixel,
+// walks the tasks in order, adds its samples' partials into integer accumulators and, at the last task of a path-tile,
+// applies the fill rule and blends (phase B).  Winding stays exact: same predicates as edge_winding() in the oracle.
+// ----------------------------------------------------------------------------------------------------
+#define FINE_SLOTS 8     // tasks per group = warps per block
+#define FINE_CH 32       // edges per task: |partial winding| <= 3*FINE_CH = 96 fits the biased int8
+#define FINE_STRIDE 20   // bytes per sample row in shared memory (16 columns + pad: lanes hit distinct banks)
+#define FINE_DBIAS 40u   // bias of the packed per-column deltas (4 per register): bytes stay in [8, 72]
 
-// One edge against the S samples of this thread's pixel, all in TILE-RELATIVE 24.8 coordinates (origin = tile corner,
-// virtual column L at x = 1/2, virtual sample C at (1/2, 1/2)).  NEAR edges have every coordinate in [-16384, 20479],
-// so each product below fits 32 bits (|dx|,|dy| <= 36863, |sample - endpoint| <= 20479: products < 7.6e8, sums < 1.6e9).
-template <int S>
-__device__ __forceinline__ void edge_near(int32_t ax, int32_t ay, int32_t bx, int32_t by, bool crossL, const int32_t (&sx)[S], const int32_t (&sy)[S],
-                                          int32_t (&w)[S]) {
+template <int S> __device__ __forceinline__ void sample_pos16(int s, int32_t &x16, int32_t &y16) {
+    // (runtime sample index: a select chain over the compile-time tables; used once per lane per pass)
+    int x = 0, y = 0;
+#pragma unroll
+    for (int k = 0; k < S; k++)
+        if (k == s) { x = SamplePos<S>::x(k); y = SamplePos<S>::y(k); }
+    x16 = x * 16; y16 = y * 16;
+}
+
+struct FineTask {
+    uint32_t eoff;   // first edge in tile_edges
+    int32_t  n;      // edges in this task (0: backdrop-only)
+    int32_t  draw;
+    int32_t  bd;     // backdrop, added by the first task of a path-tile
+    uint32_t last;   // 1: the path-tile is complete after this task
+};
+
+// sign of (2*q - r) without forming it: > 0 <=> q > floor(r/2), < 0 <=> q < ceil(r/2)
+template <class T> __device__ __forceinline__ bool twice_gt(T q, int32_t r) { return q > (T)(r >> 1); }
+template <class T> __device__ __forceinline__ bool twice_lt(T q, int32_t r) { return q < (T)((r + 1) >> 1); }
+
+__device__ __forceinline__ void delta_add(uint32_t (&d)[4], int c0, int sgn) {  // column c0 (1..15) += sgn; c0 = 16: none
+    const uint32_t inc = (uint32_t)sgn << ((c0 & 3) * 8);
+    const int      t   = c0 >> 2;
+    d[0] += t == 0 ? inc : 0u;
+    d[1] += t == 1 ? inc : 0u;
+    d[2] += t == 2 ? inc : 0u;
+    d[3] += t == 3 ? inc : 0u;
+}
+
+// One edge (tile-relative 24.8 coordinates; L at x = 1/2, C at (1/2, 1/2)) against P sample rows of this lane.
+// T = int32_t when every coordinate lies in [-16384, 20479] (products < 7.6e8, sums < 1.6e9), else long long.
+template <int P, class T>
+__device__ __forceinline__ void row_edge(int32_t ax, int32_t ay, int32_t bx, int32_t by, bool crossL, const int32_t (&ry)[P], const int32_t (&rxo)[P],
+                                         uint32_t (&d)[P][4], int32_t (&base)[P]) {
     const int32_t dx = bx - ax, dy = by - ay;
-    const int32_t K  = dy * ax - dx * ay;  // m(y) = dx*y + K = dx*(y - ay) + dy*ax ;  E(L,y)*2 = 2*m - dy ;  E(s) = m - dy*sx
-    if (dy > 0) {
-        const int32_t h = dy >> 1;
+    const T       K  = (T)dy * ax - (T)dx * ay;  // m(y) = dx*y + K ;  2*E(L,y) = 2*m - dy ;  E(sample) = m - dy*sx
+    if (dy != 0) {
+        const int     sgn = dy > 0 ? 1 : -1;
+        const int32_t h   = dy > 0 ? (dy >> 1) : ((dy + 1) >> 1);
+        const T       D   = (T)256 * (dy > 0 ? dy : -dy);
 #pragma unroll
-        for (int s = 0; s < S; s++)
-            if ((ay <= sy[s]) != (by <= sy[s])) {
-                const int32_t m = dx * sy[s] + K;
-                w[s] += (int)(m - dy * sx[s] <= 0) - (int)(m <= h);
+        for (int j = 0; j < P; j++) {
+            const int32_t y = ry[j];
+            if ((ay <= y) != (by <= y)) {
+                const T m = (T)dx * y + K;
+                // at or left of L: dy > 0: m <= h, dy < 0: m >= h
+                if (dy > 0 ? (m <= (T)h) : (m >= (T)h)) base[j] -= sgn;
+                // first column c with E(sample c) on the "left of sample" side: 256*|dy|*c >= qq
+                T qq = m - (T)dy * rxo[j];
+                if (dy < 0) qq = -qq;
+                if (qq <= 0) base[j] += sgn;
+                else {
+                    int c = 0;
+                    T   Dc = 0;
+                    if (D * 8 < qq) { c = 8; Dc = D * 8; }
+                    if (Dc + D * 4 < qq) { c += 4; Dc += D * 4; }
+                    if (Dc + D * 2 < qq) { c += 2; Dc += D * 2; }
+                    if (Dc + D < qq) { c += 1; }
+                    delta_add(d[j], c + 1, sgn);  // c = last column still left of the crossing
+                }
             }
-    } else if (dy < 0) {
-        const int32_t h = (dy + 1) >> 1;
-#pragma unroll
-        for (int s = 0; s < S; s++)
-            if ((ay <= sy[s]) != (by <= sy[s])) {
-                const int32_t m = dx * sy[s] + K;
-                w[s] -= (int)(m - dy * sx[s] >= 0) - (int)(m >= h);
-            }
+        }
     }
-    if (crossL) {  // V term: crossings of the vertical segment from C down to (L, sample y)
-        const bool tie = dy == 0 || ((dx > 0) != (dy > 0));
-        const int32_t rc = dy - dx;  // E(C)*1 = 2*K - rc
+    if (crossL) {  // V term: crossings of the vertical segment from C down to (L, y)
+        const bool    tie = dy == 0 || ((dx > 0) != (dy > 0));
+        const int32_t rc  = dy - dx;  // 2*E(C) = 2*K - rc
         if (dx > 0) {
-            const int belowC = twice_gt(K, rc) || (!twice_lt(K, rc) && tie);
+            const int belowC = twice_gt<T>(K, rc) || (!twice_lt<T>(K, rc) && tie);
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int32_t m = dx * sy[s] + K;
-                w[s] -= (int)(twice_gt(m, dy) || (!twice_lt(m, dy) && tie)) - belowC;
+            for (int j = 0; j < P; j++) {
+                const T m = (T)dx * ry[j] + K;
+                base[j] -= (int)(twice_gt<T>(m, dy) || (!twice_lt<T>(m, dy) && tie)) - belowC;
             }
         } else {
-            const int belowC = twice_lt(K, rc) || (!twice_gt(K, rc) && tie);
+            const int belowC = twice_lt<T>(K, rc) || (!twice_gt<T>(K, rc) && tie);
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int32_t m = dx * sy[s] + K;
-                w[s] += (int)(twice_lt(m, dy) || (!twice_gt(m, dy) && tie)) - belowC;
+            for (int j = 0; j < P; j++) {
+                const T m = (T)dx * ry[j] + K;
+                base[j] += (int)(twice_lt<T>(m, dy) || (!twice_gt<T>(m, dy) && tie)) - belowC;
             }
-        }
-    }
-}
-// same arithmetic in 64 bits for edges that reach far from the tile (coordinates are clamped to +-2^28 by vs_snap, so
-// every difference fits int32 and every product is one 32x32->64 multiply)
-template <int S>
-__device__ __forceinline__ void edge_far(int32_t ax, int32_t ay, int32_t bx, int32_t by, bool crossL, const int32_t (&sx)[S], const int32_t (&sy)[S],
-                                         int32_t (&w)[S]) {
-    const int32_t   dx = bx - ax, dy = by - ay;
-    const int       sdy = dy > 0 ? 1 : (dy < 0 ? -1 : 0), sdx = dx > 0 ? 1 : (dx < 0 ? -1 : 0);
-    const long long kL  = (long long)dy * (1 - 2 * ax);  // E2(L, y) = 2*dx*(y - ay) - kL
-    int             belowC = 0;
-    if (crossL) {
-        long long EC = (long long)dx * (1 - 2 * ay) - kL;
-        belowC       = (sdx > 0 ? EC > 0 : EC < 0) || (EC == 0 && (dy == 0 || sdx != sdy));
-    }
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        const int32_t   ys = sy[s];
-        const long long t  = (long long)dx * (ys - ay);
-        const long long EL = 2 * t - kL;
-        if ((ay <= ys) != (by <= ys)) {  // H term: crossing strictly right of L and at or left of the sample
-            const long long Es = t - (long long)dy * (sx[s] - ax);
-            const int       ls = dy > 0 ? (Es <= 0) : (Es >= 0);
-            const int       lL = dy > 0 ? (EL <= 0) : (EL >= 0);
-            w[s] += sdy * (ls - lL);
-        }
-        if (crossL) {
-            const int below = (sdx > 0 ? EL > 0 : EL < 0) || (EL == 0 && (dy == 0 || sdx != sdy));
-            w[s] -= sdx * (below - belowC);
         }
     }
 }
 
 template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
+    constexpr int ROWS   = 16 * S;
+    constexpr int P      = ROWS >= 64 ? 2 : 1;                 // sample rows per lane per pass
+    constexpr int PASSES = (ROWS + 32 * P - 1) / (32 * P);
     const uint32_t tile  = blockIdx.x;
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) return;  // no draw of this batch touches the tile: the stored pixels stay as they are
-    __shared__ float lut[256];
+
+    __shared__ float    lut[256];
+    __shared__ uint32_t cnt[FINE_SLOTS * ROWS * (FINE_STRIDE / 4)];
+    __shared__ FineTask tasks[FINE_SLOTS];
+    __shared__ uint32_t s_p, s_k, s_nslots;
+
     lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
     const uint32_t lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
     const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
     const bool     inside = px < a.sd.width && py < a.sd.height;
     const size_t   pix    = (size_t)py * a.sd.width + px;
     const size_t   mspix  = ((size_t)tile * 256 + threadIdx.x) * S;  // per-sample plane is tile-major
+    const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
 
     uint32_t col[S];
-    if (!a.dst_is_clear && a.tile_ms[tile]) {  // samples of this tile differed after an earlier flush
+    {
+        bool ms = false;
+        if (!a.dst_is_clear && a.tile_ms[tile]) ms = (a.ms_mask[tile * 8 + warp] >> lane) & 1u;
+        if (ms) {  // this pixel's samples differed after an earlier flush
 #pragma unroll
-        for (int s = 0; s < S; s++) col[s] = a.ms_image[mspix + s];
-    } else {
-        uint32_t c = (!a.dst_is_clear && inside) ? a.image[pix] : 0u;
+            for (int s = 0; s < S; s++) col[s] = a.ms_image[mspix + s];
+        } else {
+            uint32_t c = (!a.dst_is_clear && inside) ? a.image[pix] : 0u;
 #pragma unroll
-        for (int s = 0; s < S; s++) col[s] = c;
+            for (int s = 0; s < S; s++) col[s] = c;
+        }
     }
-    const int32_t X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
-    int32_t       sx[S], sy[S];  // tile-relative sample coordinates
+    int32_t wacc[S];
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-        sx[s] = (int32_t)lx * 256 + SamplePos<S>::x(s) * 16;
-        sy[s] = (int32_t)ly * 256 + SamplePos<S>::y(s) * 16;
-    }
-    // sample rows of this warp (two pixel rows): an edge whose y-range misses them and that does not cross L adds nothing
-    const int32_t wy_lo = (int32_t)(threadIdx.x >> 5) * 512, wy_hi = wy_lo + 511;
+    for (int s = 0; s < S; s++) wacc[s] = 0;
+    if (threadIdx.x == 0) { s_p = first; s_k = 0; }
     __syncthreads();
 
-    int4 h = a.hdr[first];
-    for (uint32_t p = first; p < end; p++) {
-        const int4      hn = p + 1 < end ? a.hdr[p + 1] : h;
-        const vkb_paint pt = a.paints[h.x];
-        int32_t         w[S];
+    for (;;) {
+        // ---- build the next group of tasks (warp 0, one path-tile per lane) ----
+        if (warp == 0) {
+            const uint32_t p0 = s_p, k0 = s_k;
+            __syncwarp();
+            const uint32_t p  = p0 + lane;
+            const bool     ok = lane < FINE_SLOTS && p < end;
+            int4           h  = ok ? a.hdr[p] : make_int4(0, 0, 0, 0);
+            const int      kk = lane == 0 ? (int)k0 : 0;  // edges of path-tile p0 consumed by earlier groups
+            const int      nt = ok ? max(1, (h.w - kk + FINE_CH - 1) / FINE_CH) : 0;
+            int            incl = nt;
 #pragma unroll
-        for (int s = 0; s < S; s++) w[s] = h.y;
-        const vkb_edge *ep = a.tile_edges + (uint32_t)h.z;
-        bool touched = h.y != 0;
-        for (uint32_t k = 0; k < (uint32_t)h.w; k++) {
-            const int4    ev = __ldg((const int4 *)(ep + k));
-            const int32_t ax = ev.x - X0, ay = ev.y - Y0, bx = ev.z - X0, by = ev.w - Y0;
-            const bool    crossL = (ax <= 0) != (bx <= 0);
-            if (!crossL && (max(ay, by) <= wy_lo || min(ay, by) > wy_hi)) continue;  // warp-uniform
-            touched = true;
-            const bool near = (uint32_t)(ax + 16384) < 36864u && (uint32_t)(ay + 16384) < 36864u && (uint32_t)(bx + 16384) < 36864u &&
-                              (uint32_t)(by + 16384) < 36864u;
-            if (near) edge_near<S>(ax, ay, bx, by, crossL, sx, sy, w);
-            else edge_far<S>(ax, ay, bx, by, crossL, sx, sy, w);
-        }
-        if (a.winding_out && (uint32_t)h.x == a.winding_draw && inside) {
-#pragma unroll
-            for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
-        }
-        int32_t wor = 0;
-#pragma unroll
-        for (int s = 0; s < S; s++) wor |= w[s];
-        if (!touched || !__any_sync(0xffffffffu, wor != 0)) {  // nothing of this draw reaches the two pixel rows of this warp
-            h = hn;
-            continue;
-        }
-        const uint32_t rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
-        int32_t        n[S], nmax = 0;
-        bool           uni = true, two = true;
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            int32_t v = w[s];
-            n[s]      = rule == VKB_RULE_EVEN_ODD ? (v & 1) : (rule == VKB_RULE_NON_ZERO ? (v != 0) : (v < 0 ? -v : v));
-            nmax      = max(nmax, n[s]);
-            uni       = uni && col[s] == col[0];
-        }
-        if (nmax) {
-            float src[4];
-            eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src, lut);
-            const float ia = 1.0f - src[3];
-            if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
-                nmax = 1;
-#pragma unroll
-                for (int s = 0; s < S; s++) n[s] = n[s] ? 1 : 0;
+            for (int o = 1; o < FINE_SLOTS; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
             }
-#pragma unroll
-            for (int s = 0; s < S; s++) two = two && (n[s] == 0 || n[s] == nmax);
-            if (uni && two) {  // every sample holds the same colour and is blended either nmax times or not at all: blend once
-                uint32_t c = col[0];
-                for (int32_t r = 0; r < nmax; r++) c = blend_over(c, src, ia, lut);
-#pragma unroll
-                for (int s = 0; s < S; s++) col[s] = n[s] ? c : col[s];
-            } else {
-#pragma unroll
-                for (int s = 0; s < S; s++)
-                    for (int32_t r = 0; r < n[s]; r++) col[s] = blend_over(col[s], src, ia, lut);
+            const int start = incl - nt;
+            for (int t = 0; t < nt && start + t < FINE_SLOTS; t++) {
+                FineTask ft;
+                const int e0 = kk + t * FINE_CH;
+                ft.eoff = (uint32_t)h.z + (uint32_t)e0;
+                ft.n    = min(FINE_CH, h.w - e0);
+                ft.draw = h.x;
+                ft.bd   = e0 == 0 ? h.y : 0;
+                ft.last = e0 + ft.n >= h.w ? 1u : 0u;
+                tasks[start + t] = ft;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, FINE_SLOTS - 1);
+            // cursor after this group: the path-tile that owns slot FINE_SLOTS-1 (or the first one not started)
+            if (ok && start < FINE_SLOTS && start + nt >= FINE_SLOTS) {
+                const int done = FINE_SLOTS - start;             // tasks of this path-tile issued in this group
+                const int e1   = kk + done * FINE_CH;
+                if (e1 >= h.w) { s_p = p + 1; s_k = 0; }
+                else { s_p = p; s_k = (uint32_t)e1; }
+            }
+            if (lane == 0) {
+                s_nslots = (uint32_t)min(total, FINE_SLOTS);
+                if (total < FINE_SLOTS) { s_p = end; s_k = 0; }
             }
         }
-        h = hn;
+        __syncthreads();
+        const uint32_t nslots = s_nslots;
+
+        // ---- phase A: warp w turns task w into per-row partial windings ----
+        if (warp < nslots && tasks[warp].n > 0) {
+            const FineTask  ft = tasks[warp];
+            const vkb_edge *ep = a.tile_edges + ft.eoff;
+#pragma unroll 1
+            for (int ps = 0; ps < PASSES; ps++) {
+                int32_t  ry[P], rxo[P], base[P];
+                uint32_t d[P][4];
+                int      row[P];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    row[j] = ps * 32 * P + j * 32 + (int)lane;   // rows of one lane are 32 apart: conflict-free stores
+                    const int r = min(row[j], ROWS - 1);
+                    int32_t   x16, y16;
+                    sample_pos16<S>(r % S, x16, y16);
+                    ry[j]  = (r / S) * 256 + y16;
+                    rxo[j] = x16;
+                    base[j] = 0;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) d[j][w4] = FINE_DBIAS * 0x01010101u;
+                }
+                for (int k = 0; k < ft.n; k++) {
+                    const int4    ev = __ldg((const int4 *)(ep + k));
+                    const int32_t ax = ev.x - X0, ay = ev.y - Y0, bx = ev.z - X0, by = ev.w - Y0;
+                    const bool    crossL = (ax <= 0) != (bx <= 0);
+                    const bool    near = (uint32_t)(ax + 16384) < 36864u && (uint32_t)(ay + 16384) < 36864u && (uint32_t)(bx + 16384) < 36864u &&
+                                         (uint32_t)(by + 16384) < 36864u;
+                    if (near) row_edge<P, int32_t>(ax, ay, bx, by, crossL, ry, rxo, d, base);
+                    else row_edge<P, long long>(ax, ay, bx, by, crossL, ry, rxo, d, base);
+                }
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    if (row[j] < ROWS) {
+                        int       run = 128 + base[j];
+                        uint32_t *dst = cnt + ((size_t)warp * ROWS + row[j]) * (FINE_STRIDE / 4);
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; w4++) {
+                            const uint32_t x = d[j][w4];
+                            const int v0 = run + (int)(x & 0xFF) - (int)FINE_DBIAS;
+                            const int v1 = v0 + (int)((x >> 8) & 0xFF) - (int)FINE_DBIAS;
+                            const int v2 = v1 + (int)((x >> 16) & 0xFF) - (int)FINE_DBIAS;
+                            const int v3 = v2 + (int)(x >> 24) - (int)FINE_DBIAS;
+                            run          = v3;
+                            dst[w4]      = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase B: every thread owns one pixel; tasks in order ----
+        const uint8_t *cb = (const uint8_t *)cnt;
+        for (uint32_t g = 0; g < nslots; g++) {
+            const FineTask ft = tasks[g];
+            if (ft.n > 0) {
+#pragma unroll
+                for (int s = 0; s < S; s++) wacc[s] += (int)cb[((size_t)g * ROWS + ly * S + s) * FINE_STRIDE + lx] - 128;
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) wacc[s] += ft.bd;  // the backdrop rides on the first task of a path-tile (0 on the others)
+            if (!ft.last) continue;
+            int32_t w[S], wor = 0;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                w[s]    = wacc[s];
+                wacc[s] = 0;
+                wor |= w[s];
+            }
+            if (a.winding_out && (uint32_t)ft.draw == a.winding_draw && inside) {
+#pragma unroll
+                for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
+            }
+            if (!__any_sync(0xffffffffu, wor != 0)) continue;  // nothing of this draw reaches the two pixel rows of this warp
+            const vkb_paint pt   = a.paints[ft.draw];
+            const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
+            int32_t         n[S], nmax = 0;
+            bool            uni = true, two = true;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                int32_t v = w[s];
+                n[s]      = rule == VKB_RULE_EVEN_ODD ? (v & 1) : (rule == VKB_RULE_NON_ZERO ? (v != 0) : (v < 0 ? -v : v));
+                nmax      = max(nmax, n[s]);
+                uni       = uni && col[s] == col[0];
+            }
+            if (nmax) {
+                float src[4];
+                eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src, lut);
+                const float ia = 1.0f - src[3];
+                if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
+                    nmax = 1;
+#pragma unroll
+                    for (int s = 0; s < S; s++) n[s] = n[s] ? 1 : 0;
+                }
+#pragma unroll
+                for (int s = 0; s < S; s++) two = two && (n[s] == 0 || n[s] == nmax);
+                if (uni && two) {  // every sample holds the same colour and is blended either nmax times or not at all: blend once
+                    uint32_t c = col[0];
+                    for (int32_t r = 0; r < nmax; r++) c = blend_over(c, src, ia, lut);
+#pragma unroll
+                    for (int s = 0; s < S; s++) col[s] = n[s] ? c : col[s];
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; s++)
+                        for (int32_t r = 0; r < n[s]; r++) col[s] = blend_over(col[s], src, ia, lut);
+                }
+            }
+        }
+        if (s_p >= end) break;   // (written before the barrier that precedes phase A: stable here)
+        __syncthreads();         // phase B reads of cnt / tasks are done before the next group overwrites them
     }
+
     bool differ = false;
 #pragma unroll
     for (int s = 1; s < S; s++) differ = differ || col[s] != col[0];
+    const uint32_t dmask = __ballot_sync(0xffffffffu, differ);
     const int tile_differs = __syncthreads_or(differ);
-    if (tile_differs) {
+    if (differ) {
 #pragma unroll
         for (int s = 0; s < S; s++) a.ms_image[mspix + s] = col[s];
     }
+    if (tile_differs && lane == 0) a.ms_mask[tile * 8 + warp] = dmask;
     if (threadIdx.x == 0) a.tile_ms[tile] = tile_differs ? 1 : 0;
     if (inside) {
         uint32_t out = 0;
