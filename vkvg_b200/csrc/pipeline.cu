@@ -286,7 +286,7 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     d->vals.ensure((size_t)(n_ne + 1) * 4, st);
     d->pt_draw.ensure((size_t)(n_ne + 1) * 4, st);
     d->cursor.ensure((size_t)(n_ne + 1) * 4, st);
-    d->hdr.ensure((size_t)(n_ne + 1) * 16, st);
+    d->hdr.ensure((size_t)(n_ne + 1) * 32, st);
     d->tile_first.ensure((size_t)n_tiles * 4 + 16, st);
     d->tile_end.ensure((size_t)n_tiles * 4 + 16, st);
     vkb_launch_pt_compact(d->pt_flags.as<uint32_t>(), flag_scan, n_pt, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), nd, sd,
@@ -310,7 +310,7 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     VKB_CUDA_OK(cudaMemsetAsync(d->tile_first.p, 0, (size_t)n_tiles * 4, st));
     VKB_CUDA_OK(cudaMemsetAsync(d->tile_end.p, 0, (size_t)n_tiles * 4, st));
     vkb_launch_headers(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), n_ne, d->pt_draw.as<uint32_t>(), flag_scan, d->pt_backdrop.as<int32_t>(),
-                       d->pt_count.as<uint32_t>(), eoff, d->hdr.as<int4>(), d->tile_first.as<uint32_t>(), d->tile_end.as<uint32_t>(), st);
+                       d->pt_count.as<uint32_t>(), eoff, d->paints.as<vkb_paint>(), d->hdr.as<int4>(), d->tile_first.as<uint32_t>(), d->tile_end.as<uint32_t>(), st);
     VKB_CUDA_OK(cudaMemsetAsync(cur2.p, 0, (size_t)n_ne * 4, st));
     vkb_launch_bin_scatter(edges, edraw, n_edges, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_slot.as<uint32_t>(), eoff,
                            cur2.as<uint32_t>(), d->tile_edges.as<vkb_edge>(), st);

@@ -63,7 +63,8 @@ void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uin
                            uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
 void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot, cudaStream_t s);
 void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
-                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, int4 *hdr, uint32_t *tile_first,
+                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
+                        uint32_t *tile_first,
                         uint32_t *tile_end, cudaStream_t s);
 void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
                             const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s);
@@ -71,7 +72,7 @@ void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, ui
 struct FineArgs {
     SurfaceDesc         sd;
     const uint32_t     *tile_first, *tile_end;
-    const int4         *hdr;         // per sorted path-tile: draw, backdrop, edge offset, edge count
+    const int4         *hdr;         // per sorted path-tile, 2 x int4: {draw, backdrop, edge offset, edge count}, {vkb_paint of the draw}
     const vkb_edge     *tile_edges;
     const vkb_paint    *paints;      // per draw
     const vkb_gradient *grads;

@@ -377,20 +377,22 @@ void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t n_ne, const uint32_
 }
 // pt_draw_by_flagpos: draw of the path-tile at compaction position flag_scan[pt] (pt_compact_k output)
 __global__ void headers_k(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
-                          const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, int4 *hdr, uint32_t *tile_first,
-                          uint32_t *tile_end) {
+                          const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
+                          uint32_t *tile_first, uint32_t *tile_end) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_ne) return;
     uint32_t pt = vals[p], key = keys[p];
-    hdr[p]      = make_int4((int)pt_draw_by_flagpos[flag_scan[pt]], pt_backdrop[pt], (int)eoff[p], (int)pt_count[pt]);
+    uint32_t dr = pt_draw_by_flagpos[flag_scan[pt]];
+    hdr[2 * p]     = make_int4((int)dr, pt_backdrop[pt], (int)eoff[p], (int)pt_count[pt]);
+    hdr[2 * p + 1] = *(const int4 *)(paints + dr);  // the fine pass reads one 32-byte record per path-tile
     if (p == 0 || keys[p - 1] != key) tile_first[key] = p;
     if (p == n_ne - 1 || keys[p + 1] != key) tile_end[key] = p + 1;
 }
 void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
-                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, int4 *hdr, uint32_t *tile_first,
-                        uint32_t *tile_end, cudaStream_t s) {
+                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
+                        uint32_t *tile_first, uint32_t *tile_end, cudaStream_t s) {
     if (!n_ne) return;
-    headers_k<<<vkb_div_up(n_ne, 256), 256, 0, s>>>(keys, vals, n_ne, pt_draw_by_flagpos, flag_scan, pt_backdrop, pt_count, eoff, hdr, tile_first, tile_end);
+    headers_k<<<vkb_div_up(n_ne, 256), 256, 0, s>>>(keys, vals, n_ne, pt_draw_by_flagpos, flag_scan, pt_backdrop, pt_count, eoff, paints, hdr, tile_first, tile_end);
     VKB_LAUNCHED();
 }
 
@@ -534,11 +536,12 @@ template <int S> __device__ __forceinline__ void sample_pos16(int s, int32_t &x1
 }
 
 struct FineTask {
-    uint32_t eoff;   // first edge in tile_edges
-    int32_t  n;      // edges in this task (0: backdrop-only)
-    int32_t  draw;
-    int32_t  bd;     // backdrop, added by the first task of a path-tile
-    uint32_t last;   // 1: the path-tile is complete after this task
+    uint32_t  eoff;   // first edge in tile_edges
+    int32_t   n;      // edges in this task (0: backdrop-only)
+    int32_t   draw;
+    int32_t   bd;     // backdrop, added by the first task of a path-tile
+    uint32_t  last;   // 1: the path-tile is complete after this task
+    vkb_paint paint;
 };
 
 // sign of (2*q - r) without forming it: > 0 <=> q > floor(r/2), < 0 <=> q < ceil(r/2)
@@ -609,7 +612,7 @@ __device__ __forceinline__ void row_edge(int32_t ax, int32_t ay, int32_t bx, int
     }
 }
 
-template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
+template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
     constexpr int ROWS   = 16 * S;
     constexpr int P      = ROWS >= 64 ? 2 : 1;                 // sample rows per lane per pass
     constexpr int PASSES = (ROWS + 32 * P - 1) / (32 * P);
@@ -625,11 +628,15 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
     lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
-    const uint32_t lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    // warp 0 keeps the headers of the next group in registers, fetched while the current group is processed
+    int4 nh0 = make_int4(0, 0, 0, 0), nh1 = nh0;
+    if (warp == 0 && lane < FINE_SLOTS && first + lane < end) { nh0 = a.hdr[2 * (first + lane)]; nh1 = a.hdr[2 * (first + lane) + 1]; }
+    // a warp owns an 8x4 pixel block (more often wholly inside or wholly outside a shape than a 16x2 strip)
+    const uint32_t lx = (lane & 7) + 8 * (warp & 1), ly = (lane >> 3) + 4 * (warp >> 1);
     const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
     const bool     inside = px < a.sd.width && py < a.sd.height;
     const size_t   pix    = (size_t)py * a.sd.width + px;
-    const size_t   mspix  = ((size_t)tile * 256 + threadIdx.x) * S;  // per-sample plane is tile-major
+    const size_t   mspix  = ((size_t)tile * 256 + threadIdx.x) * S;  // per-sample plane is tile-major, in thread order
     const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
 
     uint32_t col[S];
@@ -658,7 +665,7 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
             __syncwarp();
             const uint32_t p  = p0 + lane;
             const bool     ok = lane < FINE_SLOTS && p < end;
-            int4           h  = ok ? a.hdr[p] : make_int4(0, 0, 0, 0);
+            const int4     h  = nh0, hp = nh1;
             const int      kk = lane == 0 ? (int)k0 : 0;  // edges of path-tile p0 consumed by earlier groups
             const int      nt = ok ? max(1, (h.w - kk + FINE_CH - 1) / FINE_CH) : 0;
             int            incl = nt;
@@ -676,6 +683,7 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
                 ft.draw = h.x;
                 ft.bd   = e0 == 0 ? h.y : 0;
                 ft.last = e0 + ft.n >= h.w ? 1u : 0u;
+                ft.paint = vkb_paint{(uint32_t)hp.x, (uint32_t)hp.y, __int_as_float(hp.z), (uint32_t)hp.w};
                 tasks[start + t] = ft;
             }
             const int total = __shfl_sync(0xffffffffu, incl, FINE_SLOTS - 1);
@@ -693,6 +701,10 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
         }
         __syncthreads();
         const uint32_t nslots = s_nslots;
+        if (warp == 0) {  // prefetch the headers the next group starts from (cursor already advanced)
+            const uint32_t p = s_p + lane;
+            if (lane < FINE_SLOTS && p < end) { nh0 = a.hdr[2 * p]; nh1 = a.hdr[2 * p + 1]; }
+        }
 
         // ---- phase A: warp w turns task w into per-row partial windings ----
         if (warp < nslots && tasks[warp].n > 0) {
@@ -763,23 +775,33 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
                 wacc[s] = 0;
                 wor |= w[s];
             }
-            if (a.winding_out && (uint32_t)ft.draw == a.winding_draw && inside) {
+            if (CAPTURE) {
+                if ((uint32_t)ft.draw == a.winding_draw && inside) {
 #pragma unroll
-                for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
+                    for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
+                }
             }
-            if (!__any_sync(0xffffffffu, wor != 0)) continue;  // nothing of this draw reaches the two pixel rows of this warp
-            const vkb_paint pt   = a.paints[ft.draw];
+            if (!__any_sync(0xffffffffu, wor != 0)) continue;  // nothing of this draw reaches the pixel block of this warp
+            const vkb_paint pt   = ft.paint;
             const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
             int32_t         n[S], nmax = 0;
             bool            uni = true, two = true;
+            if (rule == VKB_RULE_EVEN_ODD) {
+#pragma unroll
+                for (int s = 0; s < S; s++) n[s] = w[s] & 1;
+            } else if (rule == VKB_RULE_NON_ZERO) {
+#pragma unroll
+                for (int s = 0; s < S; s++) n[s] = w[s] != 0;
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; s++) n[s] = abs(w[s]);
+            }
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                int32_t v = w[s];
-                n[s]      = rule == VKB_RULE_EVEN_ODD ? (v & 1) : (rule == VKB_RULE_NON_ZERO ? (v != 0) : (v < 0 ? -v : v));
-                nmax      = max(nmax, n[s]);
-                uni       = uni && col[s] == col[0];
+                nmax = max(nmax, n[s]);
+                uni  = uni && col[s] == col[0];
             }
-            if (nmax) {
+            if (__any_sync(0xffffffffu, nmax != 0)) {
                 float src[4];
                 eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src, lut);
                 const float ia = 1.0f - src[3];
@@ -790,7 +812,8 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
                 }
 #pragma unroll
                 for (int s = 0; s < S; s++) two = two && (n[s] == 0 || n[s] == nmax);
-                if (uni && two) {  // every sample holds the same colour and is blended either nmax times or not at all: blend once
+                // warp-uniform choice (a divergent one would make the warp execute both variants)
+                if (__all_sync(0xffffffffu, uni && two)) {  // every sample holds the same colour and is blended nmax times or not at all
                     uint32_t c = col[0];
                     for (int32_t r = 0; r < nmax; r++) c = blend_over(c, src, ia, lut);
 #pragma unroll
@@ -832,12 +855,13 @@ template <int S> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s) {
     uint32_t tiles = a.sd.tiles_x * a.sd.tiles_y;
     if (!tiles) return;
+    const bool cap = a.winding_out != nullptr;
     switch (a.sd.samples) {
-    case 1: fine_k<1><<<tiles, 256, 0, s>>>(a); break;
-    case 2: fine_k<2><<<tiles, 256, 0, s>>>(a); break;
-    case 4: fine_k<4><<<tiles, 256, 0, s>>>(a); break;
-    case 8: fine_k<8><<<tiles, 256, 0, s>>>(a); break;
-    case 16: fine_k<16><<<tiles, 256, 0, s>>>(a); break;
+    case 1: if (cap) fine_k<1, true><<<tiles, 256, 0, s>>>(a); else fine_k<1, false><<<tiles, 256, 0, s>>>(a); break;
+    case 2: if (cap) fine_k<2, true><<<tiles, 256, 0, s>>>(a); else fine_k<2, false><<<tiles, 256, 0, s>>>(a); break;
+    case 4: if (cap) fine_k<4, true><<<tiles, 256, 0, s>>>(a); else fine_k<4, false><<<tiles, 256, 0, s>>>(a); break;
+    case 8: if (cap) fine_k<8, true><<<tiles, 256, 0, s>>>(a); else fine_k<8, false><<<tiles, 256, 0, s>>>(a); break;
+    case 16: if (cap) fine_k<16, true><<<tiles, 256, 0, s>>>(a); else fine_k<16, false><<<tiles, 256, 0, s>>>(a); break;
     default: return;
     }
     VKB_LAUNCHED();
