@@ -289,7 +289,7 @@ def run_ours(args):
     out_t = torch.empty((size, size, 4), dtype=torch.uint8).pin_memory()
     L = v.lib()
 
-    parts = [0.0, 0.0, 0.0]
+    parts = [0.0] * 5
 
     def e2e_step():
         t0 = time.perf_counter()
@@ -299,6 +299,8 @@ def run_ours(args):
         t1 = time.perf_counter()
         L.vkvg_flush(ctx.h)
         t2 = time.perf_counter()
+        parts[3] += dev.last_stats()["ms_host_upload"]
+        parts[4] += dev.last_stats()["ms_total"]
         assert L.vkvg_b200_surface_read_premultiplied(surf.h, out_t.data_ptr()) == 0
         t3 = time.perf_counter()
         parts[0] += t1 - t0
@@ -322,7 +324,7 @@ def run_ours(args):
     ms_step = max_over_ranks(st["ms_total"] / args.steps)
     # ---- end to end through the C ABI with host buffers ----
     barrier()
-    parts[:] = [0.0, 0.0, 0.0]
+    parts[:] = [0.0] * 5
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
@@ -348,7 +350,8 @@ def run_ours(args):
         "e2e": {"value": world * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()),
                 "d2h_bytes_per_step": int(out_t.numel()), "ms_per_step": e2e_s * 1e3,
                 "host_record_ms": parts[0] / args.steps * 1e3, "upload_render_ms": parts[1] / args.steps * 1e3,
-                "readback_ms": parts[2] / args.steps * 1e3},
+                "readback_ms": parts[2] / args.steps * 1e3, "host_upload_ms": parts[3] / args.steps,
+                "device_ms_in_flush": parts[4] / args.steps, "h2d_bytes_wire": int(st["h2d_bytes"])},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "fine_k<4>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "algorithmic_bytes": int(alg_bytes), "kernel_ms": fine_ms, "peak_source": peak_src,

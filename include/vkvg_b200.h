@@ -55,7 +55,7 @@ typedef struct {
     float    ms_total, ms_fine;
     uint64_t h2d_bytes;
     float    ms_stage[5]; /* flatten | job tables + stroke expansion | edge build | binning + sort | fine pass */
-    float    pad_;
+    float    ms_host_upload; /* wall clock of the host side of the last upload */
 } vkvg_b200_stats_t;
 
 vkvg_public uint64_t vkvg_b200_launch_count(void);                          /* kernels launched by this library so far */

@@ -39,11 +39,11 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_elems", "n_points", "n_fill_edges", "n_stroke_items", "n_verts", "n_inds", "n_edges",
                                           "n_path_tiles", "n_nonempty", "n_tile_edges")] + [("ms_total", _f), ("ms_fine", _f),
                                                                                            ("h2d_bytes", C.c_uint64),
-                                                                                           ("ms_stage", _f * 5), ("pad_", _f)]
+                                                                                           ("ms_stage", _f * 5), ("ms_host_upload", _f)]
     STAGES = ("flatten", "stroke", "edges", "binning", "fine")
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("ms_stage", "pad_")}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "ms_stage"}
         d["ms_stage"] = dict(zip(self.STAGES, [float(x) for x in self.ms_stage]))
         return d
 

@@ -4,6 +4,7 @@
 #include "renderer.h"
 #include <string.h>
 #include <vector>
+#include <chrono>
 
 unsigned long long g_vkb_launches = 0;
 static int         g_cuda_failed  = 0;
@@ -20,12 +21,13 @@ struct vkb_device_impl {
     size_t   stage_cap = 0;
     uint64_t *readback = nullptr;  // pinned, 16 slots
     // batch (device)
-    DevBuf   elem_hdr, elem_data, subpaths, draws, grads, dashes, paints;
-    DevBuf   fjob_draw, fjob_sp, sjob_draw, sjob_sp, sdraw_id, sdraw_first_item, extra_edges, extra_edge_draw;
+    DevBuf   elem_hdr, elem_data, subpaths, draws, xforms, strokes, grads, dashes, paints, fcnt, scnt, pcnt, srank;
+    cudaEvent_t ev_h2d = nullptr;
+    DevBuf   fjob_draw, fjob_sp, sjob_draw, sjob_sp, sdraw_id, sdraw_first_job, sdraw_first_item, extra_edges, extra_edge_draw;
     uint32_t n_elems = 0, n_sp = 0, n_draws = 0, n_fjobs = 0, n_sjobs = 0, n_sdraws = 0, n_extra = 0;
     bool     any_dash = false;
     uint64_t h2d_bytes = 0;
-    std::vector<uint32_t> h_sdraw_first_job;
+    float    ms_host_upload = 0;
     // intermediates
     DevBuf elem_cnt, totals, pts, ptflags, sp_first, sp_count;
     DevBuf fjob_base, sjob_base, seglen, cum, item_counts, verts, inds, job_inverse;
@@ -56,6 +58,7 @@ vkb_device_impl *vkb_device_open(int ordinal) {
     VKB_CUDA_OK(cudaEventCreate(&d->ev_end));
     VKB_CUDA_OK(cudaEventCreate(&d->ev_fine0));
     VKB_CUDA_OK(cudaEventCreate(&d->ev_fine1));
+    VKB_CUDA_OK(cudaEventCreateWithFlags(&d->ev_h2d, cudaEventDisableTiming));
     for (cudaEvent_t &e : d->ev_stage) VKB_CUDA_OK(cudaEventCreate(&e));
     VKB_CUDA_OK(cudaHostAlloc((void **)&d->readback, 16 * sizeof(uint64_t), cudaHostAllocDefault));
     if (g_cuda_failed) { delete d; return nullptr; }
@@ -65,7 +68,7 @@ void vkb_device_close(vkb_device_impl *d) {
     if (!d) return;
     cudaSetDevice(d->ordinal);
     cudaStreamSynchronize(d->stream);
-    DevBuf *bufs[] = {&d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
+    DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
                       &d->sp_first, &d->sp_count, &d->fjob_base, &d->sjob_base, &d->seglen, &d->cum, &d->item_counts, &d->verts, &d->inds, &d->job_inverse,
                       &d->edges, &d->edge_draw, &d->draw_bbox, &d->draw_rect, &d->draw_counts, &d->draw_ptbase, &d->draw_rowbase, &d->pt_count,
@@ -76,6 +79,7 @@ void vkb_device_close(vkb_device_impl *d) {
     cudaFreeHost(d->readback);
     for (cudaEvent_t &e : d->ev_stage) cudaEventDestroy(e);
     d->l2_flush.release();
+    cudaEventDestroy(d->ev_h2d);
     cudaEventDestroy(d->ev_begin); cudaEventDestroy(d->ev_end); cudaEventDestroy(d->ev_fine0); cudaEventDestroy(d->ev_fine1);
     cudaStreamDestroy(d->stream);
     delete d;
@@ -152,64 +156,153 @@ struct Uploader {
     }
 };
 
+// ---- per-draw tables built on the device (the host only uploads what it recorded) ----
+__global__ void draw_tables_k(const vkb_draw *draws, uint32_t n, vkb_paint *paints, uint32_t *fcnt, uint32_t *scnt, uint32_t *pcnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vkb_draw d = draws[i];
+    paints[i]  = vkb_paint{d.rule_pattern, d.color, d.opacity, d.gradient};
+    fcnt[i]    = d.kind == VKB_DRAW_FILL ? d.n_subpaths : 0u;
+    scnt[i]    = d.kind == VKB_DRAW_STROKE ? d.n_subpaths : 0u;
+    pcnt[i]    = d.kind == VKB_DRAW_PAINT ? 1u : 0u;
+}
+// job j of a kind = (draw, sub-path): the draw is the last one whose exclusive job base is <= j and that has jobs
+__global__ void expand_jobs_k(const vkb_draw *draws, const uint32_t *base, uint32_t n_draws, uint32_t n_jobs, uint32_t *job_draw, uint32_t *job_sp) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    uint32_t lo = 0, hi = n_draws;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (base[mid] <= j) lo = mid; else hi = mid;
+    }
+    job_draw[j] = lo;
+    job_sp[j]   = draws[lo].first_subpath + (j - base[lo]);
+}
+// stroke draws in order (ids + their first job) and paint draws (ids, four rectangle edges each)
+__global__ void list_draws_k(const vkb_draw *draws, const uint32_t *sbase, const uint32_t *pbase, uint32_t n, uint32_t *sdraw_id, uint32_t *sdraw_first_job,
+                             const uint32_t *sdraw_rank, uint32_t *extra_edge_draw) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vkb_draw d = draws[i];
+    if (d.kind == VKB_DRAW_STROKE && d.n_subpaths) {
+        uint32_t r = sdraw_rank[i];
+        sdraw_id[r] = i; sdraw_first_job[r] = sbase[i];
+    }
+    if (d.kind == VKB_DRAW_PAINT) {
+        uint32_t r = pbase[i];
+        for (int k = 0; k < 4; k++) extra_edge_draw[4 * r + k] = i;
+    }
+}
+__global__ void stroke_flags_k(const vkb_draw *draws, const vkb_stroke *strokes, uint32_t n, uint32_t *is_sdraw, uint32_t *any_dash) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vkb_draw d = draws[i];
+    bool     s = d.kind == VKB_DRAW_STROKE && d.n_subpaths;
+    is_sdraw[i] = s ? 1u : 0u;
+    if (s && strokes[d.xform_stroke >> 16].dash_count) *any_dash = 1u;
+}
+
 int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
+    const auto t_begin = std::chrono::steady_clock::now();
     cudaSetDevice(d->ordinal);
     cudaStream_t st = d->stream;
     // the previous flush may still be reading the staging area
     VKB_CUDA_OK(cudaStreamSynchronize(st));
-    // job tables (host): one job per (draw, sub-path)
-    std::vector<uint32_t> fjd, fjs, sjd, sjs, sdid, extra_draw;
-    std::vector<vkb_paint> paints(b.draws.size());
-    std::vector<int32_t>   extra;
-    d->h_sdraw_first_job.clear();
-    d->any_dash = false;
-    for (uint32_t i = 0; i < b.draws.size(); i++) {
-        const vkb_draw &dr = b.draws[i];
-        paints[i]          = vkb_paint{dr.rule | (dr.pattern << 8), dr.color, dr.opacity, dr.gradient};
-        if (dr.kind == VKB_DRAW_FILL) {
-            for (uint32_t s = 0; s < dr.n_subpaths; s++) { fjd.push_back(i); fjs.push_back(dr.first_subpath + s); }
-        } else if (dr.kind == VKB_DRAW_STROKE) {
-            if (dr.n_subpaths) {
-                sdid.push_back(i);
-                d->h_sdraw_first_job.push_back((uint32_t)sjd.size());
-            }
-            for (uint32_t s = 0; s < dr.n_subpaths; s++) { sjd.push_back(i); sjs.push_back(dr.first_subpath + s); }
-            if (dr.dash_count) d->any_dash = true;
-        } else {  // whole-surface paint: a rectangle well outside the surface, filled non-zero; the exact size is
-                  // irrelevant as long as it encloses every sample (internal.c:1919-1952 draws an oversized triangle)
-            extra_draw.insert(extra_draw.end(), 4, i);
-            extra.insert(extra.end(), 16, 0);  // patched with the surface size at render time
-        }
-    }
     d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
-    d->n_fjobs = (uint32_t)fjd.size(); d->n_sjobs = (uint32_t)sjd.size(); d->n_sdraws = (uint32_t)sdid.size(); d->n_extra = (uint32_t)extra_draw.size();
 
-    struct Src { DevBuf *dst; const void *p; size_t bytes; };
+    struct Src { DevBuf *dst; const void *p; size_t bytes; bool pinned; };
     Src srcs[] = {
-        {&d->elem_hdr, b.elem_hdr.data(), b.elem_hdr.size() * 4},       {&d->elem_data, b.elem_data.data(), b.elem_data.size() * 4},
-        {&d->subpaths, b.subpaths.data(), b.subpaths.size() * sizeof(vkb_subpath)}, {&d->draws, b.draws.data(), b.draws.size() * sizeof(vkb_draw)},
-        {&d->grads, b.grads.data(), b.grads.size() * sizeof(vkb_gradient)}, {&d->dashes, b.dashes.data(), b.dashes.size() * 4},
-        {&d->paints, paints.data(), paints.size() * sizeof(vkb_paint)}, {&d->fjob_draw, fjd.data(), fjd.size() * 4},
-        {&d->fjob_sp, fjs.data(), fjs.size() * 4},                       {&d->sjob_draw, sjd.data(), sjd.size() * 4},
-        {&d->sjob_sp, sjs.data(), sjs.size() * 4},                       {&d->sdraw_id, sdid.data(), sdid.size() * 4},
-        {&d->extra_edge_draw, extra_draw.data(), extra_draw.size() * 4},
+        {&d->elem_hdr, b.elem_hdr.data(), b.elem_hdr.size() * 4, true},   // recorded straight into pinned memory: no staging copy
+        {&d->elem_data, b.elem_data.data(), b.elem_data.size() * 4, true},
+        {&d->subpaths, b.subpaths.data(), b.subpaths.size() * sizeof(vkb_subpath), false},
+        {&d->draws, b.draws.data(), b.draws.size() * sizeof(vkb_draw), false},
+        {&d->xforms, b.xforms.data(), b.xforms.size() * sizeof(vkb_xform), false},
+        {&d->strokes, b.strokes.data(), b.strokes.size() * sizeof(vkb_stroke), false},
+        {&d->grads, b.grads.data(), b.grads.size() * sizeof(vkb_gradient), false},
+        {&d->dashes, b.dashes.data(), b.dashes.size() * 4, false},
     };
     size_t total = 0;
-    for (Src &s : srcs) total += (s.bytes + 255) & ~(size_t)255;
+    for (Src &s : srcs) if (!s.pinned) total += (s.bytes + 255) & ~(size_t)255;
     uint8_t *stg = stage_reserve(d, total + 256);
     size_t   off = 0;
+    d->h2d_bytes = 0;
     for (Src &s : srcs) {
         s.dst->ensure(s.bytes + 16, st);
-        if (s.bytes) {
+        d->h2d_bytes += s.bytes;
+        if (!s.bytes) continue;
+        if (s.pinned) {
+            VKB_CUDA_OK(cudaMemcpyAsync(s.dst->p, s.p, s.bytes, cudaMemcpyHostToDevice, st));
+        } else {
             memcpy(stg + off, s.p, s.bytes);
             VKB_CUDA_OK(cudaMemcpyAsync(s.dst->p, stg + off, s.bytes, cudaMemcpyHostToDevice, st));
+            off += (s.bytes + 255) & ~(size_t)255;
         }
-        off += (s.bytes + 255) & ~(size_t)255;
+    }
+    VKB_CUDA_OK(cudaEventRecord(d->ev_h2d, st));
+
+    // ---- job tables on the device ----
+    const uint32_t nd = d->n_draws;
+    d->paints.ensure((size_t)(nd + 1) * sizeof(vkb_paint), st);
+    d->fcnt.ensure((size_t)(nd + 1) * 4, st); d->scnt.ensure((size_t)(nd + 1) * 4, st); d->pcnt.ensure((size_t)(nd + 1) * 4, st);
+    d->srank.ensure((size_t)(nd + 1) * 4, st);
+    d->totals.ensure(16 * 8, st);
+    uint32_t *tot = d->totals.as<uint32_t>();  // [24..28) as u32: fill jobs, stroke jobs, paint draws, stroke draws, any dash
+    VKB_CUDA_OK(cudaMemsetAsync(tot + 24, 0, 5 * 4, st));
+    d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
+    d->any_dash = false;
+    if (nd) {
+        draw_tables_k<<<vkb_div_up(nd, 256), 256, 0, st>>>(d->draws.as<vkb_draw>(), nd, d->paints.as<vkb_paint>(), d->fcnt.as<uint32_t>(),
+                                                          d->scnt.as<uint32_t>(), d->pcnt.as<uint32_t>());
+        VKB_LAUNCHED();
+        stroke_flags_k<<<vkb_div_up(nd, 256), 256, 0, st>>>(d->draws.as<vkb_draw>(), d->strokes.as<vkb_stroke>(), nd, d->srank.as<uint32_t>(), tot + 28);
+        VKB_LAUNCHED();
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->fcnt.as<uint32_t>(), d->fcnt.as<uint32_t>(), nd, tot + 24, d->scan, st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->scnt.as<uint32_t>(), d->scnt.as<uint32_t>(), nd, tot + 25, d->scan, st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->pcnt.as<uint32_t>(), d->pcnt.as<uint32_t>(), nd, tot + 26, d->scan, st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->srank.as<uint32_t>(), d->srank.as<uint32_t>(), nd, tot + 27, d->scan, st);
+        VKB_CUDA_OK(cudaMemcpyAsync(d->readback, tot + 24, 5 * 4, cudaMemcpyDeviceToHost, st));
+        VKB_CUDA_OK(cudaStreamSynchronize(st));
+        const uint32_t *rb = (const uint32_t *)d->readback;
+        d->n_fjobs = rb[0]; d->n_sjobs = rb[1]; d->n_extra = rb[2] * 4; d->n_sdraws = rb[3]; d->any_dash = rb[4] != 0;
+        d->fjob_draw.ensure((size_t)(d->n_fjobs + 1) * 4, st); d->fjob_sp.ensure((size_t)(d->n_fjobs + 1) * 4, st);
+        d->sjob_draw.ensure((size_t)(d->n_sjobs + 1) * 4, st); d->sjob_sp.ensure((size_t)(d->n_sjobs + 1) * 4, st);
+        d->sdraw_id.ensure((size_t)(d->n_sdraws + 1) * 4, st); d->sdraw_first_job.ensure((size_t)(d->n_sdraws + 1) * 4, st);
+        d->extra_edge_draw.ensure((size_t)d->n_extra * 4 + 16, st);
+        if (d->n_fjobs) {
+            expand_jobs_k<<<vkb_div_up(d->n_fjobs, 256), 256, 0, st>>>(d->draws.as<vkb_draw>(), d->fcnt.as<uint32_t>(), nd, d->n_fjobs,
+                                                                      d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>());
+            VKB_LAUNCHED();
+        }
+        if (d->n_sjobs) {
+            expand_jobs_k<<<vkb_div_up(d->n_sjobs, 256), 256, 0, st>>>(d->draws.as<vkb_draw>(), d->scnt.as<uint32_t>(), nd, d->n_sjobs,
+                                                                      d->sjob_draw.as<uint32_t>(), d->sjob_sp.as<uint32_t>());
+            VKB_LAUNCHED();
+        }
+        if (d->n_sdraws || d->n_extra) {
+            list_draws_k<<<vkb_div_up(nd, 256), 256, 0, st>>>(d->draws.as<vkb_draw>(), d->scnt.as<uint32_t>(), d->pcnt.as<uint32_t>(), nd,
+                                                             d->sdraw_id.as<uint32_t>(), d->sdraw_first_job.as<uint32_t>(), d->srank.as<uint32_t>(),
+                                                             d->extra_edge_draw.as<uint32_t>());
+            VKB_LAUNCHED();
+        }
+    } else {
+        VKB_CUDA_OK(cudaEventSynchronize(d->ev_h2d));
     }
     d->extra_edges.ensure((size_t)d->n_extra * 16 + 16, st);
-    d->h2d_bytes = 0;
-    for (Src &s : srcs) d->h2d_bytes += s.bytes;
+    d->ms_host_upload = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return g_cuda_failed;
+}
+
+// pinned host memory for the recorder's element arrays (PodVec in renderer.h)
+void *vkb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return malloc(bytes); }
+    return p;
+}
+void vkb_host_free(void *p) {
+    if (!p) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) cudaFreeHost(p);
+    else { cudaGetLastError(); free(p); }
 }
 
 static uint64_t read_total(vkb_device_impl *d, const void *dev_ptr, size_t bytes) {
@@ -367,7 +460,7 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
     cudaStream_t st = d->stream;
     vkb_stats    S;
     memset(&S, 0, sizeof S);
-    S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes;
+    S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes; S.ms_host_upload = d->ms_host_upload;
     SurfaceDesc sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE};
     VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
     VKB_CUDA_OK(cudaEventRecord(d->ev_stage[0], st));
@@ -422,7 +515,7 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
     // ---- 3. strokes: (dash phase scan) -> count -> scan -> emit ----
     uint32_t n_verts = 0, n_inds = 0;
     if (n_sitems) {
-        StrokeArgs sa = {d->pts.as<float2>(), d->ptflags.as<uint8_t>(), d->draws.as<vkb_draw>(), d->dashes.as<float>(), d->sjob_draw.as<uint32_t>(),
+        StrokeArgs sa = {d->pts.as<float2>(), d->ptflags.as<uint8_t>(), d->draws.as<vkb_draw>(), d->strokes.as<vkb_stroke>(), d->dashes.as<float>(), d->sjob_draw.as<uint32_t>(),
                          d->sjob_sp.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(),
                          d->subpaths.as<vkb_subpath>(), nullptr, n_sitems};
         if (d->any_dash) {
@@ -459,17 +552,15 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
     d->edge_draw.ensure((n_edges + 1) * 4, st);
     vkb_edge *edges = d->edges.as<vkb_edge>();
     uint32_t *edraw = d->edge_draw.as<uint32_t>();
-    vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
+    vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
                           d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), n_fill, sd, edges, edraw, st);
     if (n_tris) {
         // first work item of every stroke draw (to map a triangle back to its draw)
         d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
-        d->keys.ensure((size_t)d->n_sdraws * 4 + 16, st);
-        VKB_CUDA_OK(cudaMemcpyAsync(d->keys.p, d->h_sdraw_first_job.data(), (size_t)d->n_sdraws * 4, cudaMemcpyHostToDevice, st));
-        gather_first_items_k<<<vkb_div_up(d->n_sdraws, 256), 256, 0, st>>>(d->keys.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
+        gather_first_items_k<<<vkb_div_up(d->n_sdraws, 256), 256, 0, st>>>(d->sdraw_first_job.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
                                                                           d->sdraw_first_item.as<uint32_t>());
         VKB_LAUNCHED();
-        vkb_launch_tri_edges(d->verts.as<float2>(), n_verts, d->inds.as<uint32_t>(), n_tris, d->draws.as<vkb_draw>(), d->sdraw_id.as<uint32_t>(),
+        vkb_launch_tri_edges(d->verts.as<float2>(), n_verts, d->inds.as<uint32_t>(), n_tris, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
                              d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges + n_fill, edraw + n_fill, st);
     }
     if (d->n_extra) {

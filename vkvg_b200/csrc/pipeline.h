@@ -19,6 +19,7 @@ struct StrokeArgs {
     const float2      *pts;
     const uint8_t     *ptflags;
     const vkb_draw    *draws;
+    const vkb_stroke  *strokes;
     const float       *dash_table;
     const uint32_t    *job_draw, *job_sp, *job_base;
     uint32_t           n_jobs;
@@ -37,10 +38,10 @@ struct SurfaceDesc {
     uint32_t width, height, samples;
     uint32_t tiles_x, tiles_y;
 };
-void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
+void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges,
                            uint32_t *edge_draw, cudaStream_t s);
-void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws,
+void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
                           const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
                           SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
 

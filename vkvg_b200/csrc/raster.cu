@@ -64,32 +64,33 @@ void vkb_launch_job_counts(const uint32_t *job_sp, uint32_t n_jobs, const uint32
 // ---- fill: one edge per point of every sub-path with > 2 points (the fan of _poly_fill covers exactly the
 //      implicitly closed polygon, internal.c:1617-1642) ----
 __global__ void __launch_bounds__(256)
-fill_edges_k(const float2 *pts, const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs,
+fill_edges_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs,
              const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw) {
     uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n_items) return;
     uint32_t j = find_job(job_base, n_jobs, item), k = item - job_base[j];
     uint32_t s = job_sp[j], first = sp_first[s], n = sp_count[s], d = job_draw[j];
     float2   a = pts[first + k], b = pts[first + (k + 1 == n ? 0 : k + 1)];
-    const float *m = draws[d].mat;
+    const float *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
     vkb_edge e;
     vs_snap(m, (float)sd.width, (float)sd.height, a.x, a.y, e.x0, e.y0);
     vs_snap(m, (float)sd.width, (float)sd.height, b.x, b.y, e.x1, e.y1);
     edges[item]     = e;
     edge_draw[item] = d;
 }
-void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
+void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges,
                            uint32_t *edge_draw, cudaStream_t s) {
     if (!n_items) return;
-    fill_edges_k<<<vkb_div_up(n_items, 256), 256, 0, s>>>(pts, draws, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, n_items, sd, edges, edge_draw);
+    fill_edges_k<<<vkb_div_up(n_items, 256), 256, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, n_items, sd, edges, edge_draw);
     VKB_LAUNCHED();
 }
 
 // ---- stroke: three edges per triangle, oriented to wind +1 (so the sum over triangles is the number of
 //      triangles covering the sample, which is how many times the reference blends it) ----
 __global__ void __launch_bounds__(256)
-tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const uint32_t *sdraw_id,
+tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
+            const uint32_t *sdraw_id,
             const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges,
             uint32_t *edge_draw) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,7 +105,7 @@ tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_
     uint32_t ia = inds[3 * t], ib = inds[3 * t + 1], ic = inds[3 * t + 2];
     vkb_edge e0 = {0, 0, 0, 0}, e1 = e0, e2 = e0;
     if (ia < n_verts && ib < n_verts && ic < n_verts) {
-        const float *m = draws[d].mat;
+        const float *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
         float2       a = verts[ia], b = verts[ib], c = verts[ic];
         int32_t      ax, ay, bx, by, cx, cy;
         vs_snap(m, (float)sd.width, (float)sd.height, a.x, a.y, ax, ay);
@@ -124,11 +125,11 @@ tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_
     edges[3 * t] = e0; edges[3 * t + 1] = e1; edges[3 * t + 2] = e2;
     edge_draw[3 * t] = d; edge_draw[3 * t + 1] = d; edge_draw[3 * t + 2] = d;
 }
-void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws,
+void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
                           const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
                           SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
     if (!n_tris) return;
-    tri_edges_k<<<vkb_div_up(n_tris, 256), 256, 0, s>>>(verts, n_verts, inds, n_tris, draws, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, edges, edge_draw);
+    tri_edges_k<<<vkb_div_up(n_tris, 256), 256, 0, s>>>(verts, n_verts, inds, n_tris, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, edges, edge_draw);
     VKB_LAUNCHED();
 }
 

@@ -1,23 +1,62 @@
 // Host-side C++ interface of the CUDA pipeline, used by the C API layer (vkvg_api.cpp).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "vkb_types.h"
 
+// Growable array of plain data that never value-initialises (std::vector::resize would write every element of a
+// 1M-point polyline twice) and keeps its capacity across clear().
+void *vkb_host_alloc(size_t bytes);  // pinned when a CUDA device is present (pipeline.cu)
+void  vkb_host_free(void *p);
+template <class T> struct PodVec {
+    T     *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+    PodVec() {}
+    PodVec(const PodVec &o) { assign(o.p_, o.p_ + o.n_); }
+    PodVec &operator=(const PodVec &o) { if (this != &o) assign(o.p_, o.p_ + o.n_); return *this; }
+    ~PodVec() { vkb_host_free(p_); }
+    void reserve(size_t c) {
+        if (c <= cap_) return;
+        size_t nc = cap_ ? cap_ : 1024;
+        while (nc < c) nc *= 2;
+        T *np = (T *)vkb_host_alloc(nc * sizeof(T));
+        if (n_) memcpy(np, p_, n_ * sizeof(T));
+        vkb_host_free(p_);
+        p_   = np;
+        cap_ = nc;
+    }
+    void   resize(size_t n) { reserve(n); n_ = n; }  // new elements are uninitialised
+    void   clear() { n_ = 0; }
+    size_t size() const { return n_; }
+    bool   empty() const { return n_ == 0; }
+    T     *data() { return p_; }
+    const T *data() const { return p_; }
+    T       &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    T       *begin() { return p_; }
+    T       *end() { return p_ + n_; }
+    const T *begin() const { return p_; }
+    const T *end() const { return p_ + n_; }
+    void     push_back(const T &v) { if (n_ == cap_) reserve(n_ + 1); p_[n_++] = v; }
+    void     append(const T *a, const T *b) { size_t k = (size_t)(b - a); reserve(n_ + k); memcpy(p_ + n_, a, k * sizeof(T)); n_ += k; }
+    void     assign(const T *a, const T *b) { n_ = 0; append(a, b); }
+};
+
 // One flush worth of recorded work (host memory).  See vkb_types.h for the record formats.
 struct vkb_batch {
-    std::vector<uint32_t>     elem_hdr;
-    std::vector<float>        elem_data;
+    PodVec<uint32_t>          elem_hdr;
+    PodVec<float>             elem_data;
     std::vector<vkb_subpath>  subpaths;
     std::vector<vkb_draw>     draws;
+    std::vector<vkb_xform>    xforms;
+    std::vector<vkb_stroke>   strokes;
     std::vector<vkb_gradient> grads;
     std::vector<float>        dashes;
+    void clear_draws() { draws.clear(); xforms.clear(); strokes.clear(); grads.clear(); dashes.clear(); }
     void clear() {
-        elem_hdr.clear(); elem_data.clear(); subpaths.clear(); draws.clear(); grads.clear(); dashes.clear();
-    }
-    size_t upload_bytes() const {
-        return elem_hdr.size() * 4 + elem_data.size() * 4 + subpaths.size() * sizeof(vkb_subpath) + draws.size() * sizeof(vkb_draw) +
-               grads.size() * sizeof(vkb_gradient) + dashes.size() * 4;
+        elem_hdr.clear(); elem_data.clear(); subpaths.clear(); clear_draws();
     }
 };
 
@@ -41,7 +80,7 @@ struct vkb_stats {            // filled by every render
     float    ms_total, ms_fine;  // CUDA-event durations on the device stream
     uint64_t h2d_bytes;
     float    ms_stage[VKB_N_STAGES];  // flatten | job tables + stroke expansion | edge build | binning + sort | fine pass
-    float    pad_;
+    float    ms_host_upload;          // wall clock of the host side of the last upload (job tables, staging copy, H2D enqueue)
 };
 
 struct vkb_device_impl;

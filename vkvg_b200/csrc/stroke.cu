@@ -250,7 +250,7 @@ struct StrokeJob {
 
 template <bool EMIT>
 __global__ void __launch_bounds__(128)
-stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws, const float *dash_table, const uint32_t *job_draw,
+stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws, const vkb_stroke *strokes, const float *dash_table, const uint32_t *job_draw,
                const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count,
                const vkb_subpath *sps, const double *cum, uint32_t n_items, unsigned long long *counts, const unsigned long long *offsets,
                float2 *verts, uint32_t *inds, uint32_t *job_inverse) {
@@ -266,7 +266,7 @@ stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws,
     const uint32_t s = job_sp[j];
     const uint32_t first = sp_first[s], n = sp_count[s];
     const bool     closed = sps[s].flags & VKB_SP_CLOSED;
-    const vkb_draw &d = draws[job_draw[j]];
+    const vkb_stroke &d = strokes[draws[job_draw[j]].xform_stroke >> 16];
     StrokeParams   sp = {d.hw, d.lhMax, d.arcStep, d.join, d.cap};
 
     Out<EMIT> o;
@@ -358,13 +358,13 @@ __global__ void stroke_seglen_k(const float2 *pts, const uint32_t *job_sp, const
 
 // closed, undashed sub-paths: redirect the forward references of the closing quad to the first two
 // vertices of the sub-path (vkvg_context.c:921-931)
-__global__ void stroke_patch_closed_k(const vkb_draw *draws, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
+__global__ void stroke_patch_closed_k(const vkb_draw *draws, const vkb_stroke *strokes, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                                       uint32_t n_jobs, const vkb_subpath *sps, const uint32_t *sp_count, const unsigned long long *offsets,
                                       uint32_t n_items, unsigned long long total, const uint32_t *job_inverse, uint32_t *inds) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     uint32_t s = job_sp[j];
-    if (!(sps[s].flags & VKB_SP_CLOSED) || draws[job_draw[j]].dash_count != 0 || sp_count[s] < 2) return;
+    if (!(sps[s].flags & VKB_SP_CLOSED) || strokes[draws[job_draw[j]].xform_stroke >> 16].dash_count != 0 || sp_count[s] < 2) return;
     unsigned long long a = offsets[job_base[j]];
     uint32_t           e = job_base[j] + sp_count[s];
     unsigned long long b = e < n_items ? offsets[e] : total;
@@ -380,16 +380,16 @@ void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s
     VKB_LAUNCHED();
 }
 void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s) {
-    stroke_items_k<false><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
+    stroke_items_k<false><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
                                                                    a.sp_first, a.sp_count, a.sps, a.cum, a.n_items, counts, nullptr, nullptr, nullptr, nullptr);
     VKB_LAUNCHED();
 }
 void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, unsigned long long total, float2 *verts, uint32_t *inds,
                             uint32_t *job_inverse, cudaStream_t s) {
-    stroke_items_k<true><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
+    stroke_items_k<true><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
                                                                   a.sp_first, a.sp_count, a.sps, a.cum, a.n_items, nullptr, offsets, verts, inds, job_inverse);
     VKB_LAUNCHED();
-    stroke_patch_closed_k<<<vkb_div_up(a.n_jobs, 128), 128, 0, s>>>(a.draws, a.job_draw, a.job_sp, a.job_base, a.n_jobs, a.sps, a.sp_count, offsets,
+    stroke_patch_closed_k<<<vkb_div_up(a.n_jobs, 128), 128, 0, s>>>(a.draws, a.strokes, a.job_draw, a.job_sp, a.job_base, a.n_jobs, a.sps, a.sp_count, offsets,
                                                                    a.n_items, total, job_inverse, inds);
     VKB_LAUNCHED();
 }

@@ -44,16 +44,23 @@ enum : uint32_t {
 };
 enum : uint32_t { VKB_PAT_SOLID = 0, VKB_PAT_LINEAR = 2, VKB_PAT_RADIAL = 3 };  // vkvg_pattern_type_t values
 
+// A draw is 32 bytes; what rarely changes between draws (CTM, stroke state) lives in side tables that grow only when
+// the state differs from the previous entry (100k fills under one CTM upload 3.2 MB of draws, not 11 MB).
 struct vkb_draw {
     uint32_t kind;       // VKB_DRAW_*
-    uint32_t rule;       // VKB_RULE_*
+    uint32_t rule_pattern;  // VKB_RULE_* | VKB_PAT_* << 8
     uint32_t first_subpath, n_subpaths;
-    float    mat[6];     // CTM at draw time: xx yx xy yy x0 y0
     uint32_t color;      // premultiplied RGBA8, R in byte 0 (CreateRgbaf, src/vkvg_context_internal.h:60-62)
-    uint32_t pattern;    // VKB_PAT_*
-    uint32_t gradient;   // index into the batch's gradient table
     float    opacity;
-    // stroke parameters (src/vkvg_context.c:830-832, internal.c:245-252)
+    uint32_t gradient;   // index into the batch's gradient table
+    uint32_t xform_stroke;  // xform index | stroke-state index << 16  (both tables are capped at 65535 entries per batch)
+};
+static_assert(sizeof(vkb_draw) == 32, "vkb_draw layout");
+struct vkb_xform {       // CTM at draw time: xx yx xy yy x0 y0
+    float mat[6];
+    float pad[2];
+};
+struct vkb_stroke {      // stroke parameters (src/vkvg_context.c:830-832, internal.c:245-252)
     float    hw, lhMax, arcStep;
     uint32_t join, cap;
     uint32_t dash_first, dash_count;  // into the batch's dash table

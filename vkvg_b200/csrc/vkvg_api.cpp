@@ -431,7 +431,7 @@ static inline bool path_empty(VkvgContext ctx) { return ctx->sp_points == 0; }  
 static void push_elem(VkvgContext ctx, uint32_t type_flags, const float *payload, int n) {
     vkb_batch &b = ctx->batch;
     b.elem_hdr.push_back(type_flags | ((uint32_t)b.elem_data.size() << VKB_EL_PAYLOAD_SHIFT));
-    b.elem_data.insert(b.elem_data.end(), payload, payload + n);
+    b.elem_data.append(payload, payload + n);
 }
 static inline void add_point(VkvgContext ctx, float x, float y, bool curved) {  // _add_point, internal.c:221-238
     if (isnan(x) || isnan(y)) return;
@@ -790,12 +790,19 @@ void vkvg_get_matrix(VkvgContext ctx, vkvg_matrix_t *const matrix) { if (!vkvg_s
 // ---- draws ----
 static vkb_draw base_draw(VkvgContext ctx, uint32_t kind, uint32_t rule) {
     vkb_draw d;
-    memset(&d, 0, sizeof d);
-    d.kind = kind; d.rule = rule;
+    d.kind = kind;
+    d.rule_pattern = rule | (ctx->patType << 8);
     d.first_subpath = ctx->path_first_sp;
     d.n_subpaths    = (uint32_t)ctx->batch.subpaths.size() - ctx->path_first_sp;
-    memcpy(d.mat, &ctx->mat, sizeof d.mat);
-    d.color = ctx->curColor; d.pattern = ctx->patType; d.opacity = ctx->opacity;
+    d.color = ctx->curColor; d.opacity = ctx->opacity; d.gradient = 0;
+    std::vector<vkb_xform> &xf = ctx->batch.xforms;
+    if (xf.empty() || memcmp(xf.back().mat, &ctx->mat, sizeof(float) * 6) != 0) {
+        vkb_xform x;
+        memcpy(x.mat, &ctx->mat, sizeof(float) * 6);
+        x.pad[0] = x.pad[1] = 0;
+        xf.push_back(x);
+    }
+    d.xform_stroke = (uint32_t)xf.size() - 1;
     if (ctx->patType != VKB_PAT_SOLID) {
         if (ctx->grad_slot < 0) {
             ctx->grad_slot = (int32_t)ctx->batch.grads.size();
@@ -805,28 +812,51 @@ static vkb_draw base_draw(VkvgContext ctx, uint32_t kind, uint32_t rule) {
     }
     return d;
 }
+// side tables are addressed with 16 bits: start a new batch before they overflow
+static void flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident);
+static void reserve_draw_tables(VkvgContext ctx) {
+    if (ctx->batch.xforms.size() >= 65000 || ctx->batch.strokes.size() >= 65000) flush_impl(ctx, nullptr, false);
+}
 static void fill_preserve_(VkvgContext ctx) {  // _fill_preserve :796-821
     finish_path(ctx);
     if (ctx->batch.subpaths.size() == ctx->path_first_sp) return;
+    reserve_draw_tables(ctx);
     ctx->batch.draws.push_back(base_draw(ctx, VKB_DRAW_FILL, ctx->fillRule == VKVG_FILL_RULE_EVEN_ODD ? VKB_RULE_EVEN_ODD : VKB_RULE_NON_ZERO));
 }
 static void stroke_preserve_(VkvgContext ctx) {  // _stroke_preserve :822-948
     finish_path(ctx);
     if (ctx->batch.subpaths.size() == ctx->path_first_sp) return;
-    vkb_draw d = base_draw(ctx, VKB_DRAW_STROKE, VKB_RULE_COUNT);
-    d.hw = ctx->lineWidth * 0.5f;
-    d.lhMax = ctx->miterLimit * ctx->lineWidth;
-    d.arcStep = get_arc_step(ctx, d.hw);
-    d.join = ctx->join; d.cap = ctx->cap;
+    reserve_draw_tables(ctx);
+    vkb_stroke st;
+    memset(&st, 0, sizeof st);
+    st.hw = ctx->lineWidth * 0.5f;
+    st.lhMax = ctx->miterLimit * ctx->lineWidth;
+    st.arcStep = get_arc_step(ctx, st.hw);
+    st.join = ctx->join; st.cap = ctx->cap;
     if (!ctx->dashes.empty()) {
         float tot = 0;
         for (float v : ctx->dashes) tot += v;
         if (tot == 0 || ctx->dashes.size() > VKB_MAX_DASHES) { ctx->status = VKVG_STATUS_INVALID_DASH; return; }
-        d.dash_first = (uint32_t)ctx->batch.dashes.size();
-        d.dash_count = (uint32_t)ctx->dashes.size();
-        d.dash_offset = ctx->dashOffset;
-        ctx->batch.dashes.insert(ctx->batch.dashes.end(), ctx->dashes.begin(), ctx->dashes.end());
+        // reuse the previous stroke's dash table entry when the pattern is unchanged
+        std::vector<float> &dt = ctx->batch.dashes;
+        bool same = false;
+        if (!ctx->batch.strokes.empty()) {
+            const vkb_stroke &pv = ctx->batch.strokes.back();
+            same = pv.dash_count == ctx->dashes.size() && pv.dash_first + pv.dash_count <= dt.size() &&
+                   memcmp(dt.data() + pv.dash_first, ctx->dashes.data(), sizeof(float) * pv.dash_count) == 0;
+            if (same) st.dash_first = pv.dash_first;
+        }
+        if (!same) {
+            st.dash_first = (uint32_t)dt.size();
+            dt.insert(dt.end(), ctx->dashes.begin(), ctx->dashes.end());
+        }
+        st.dash_count  = (uint32_t)ctx->dashes.size();
+        st.dash_offset = ctx->dashOffset;
     }
+    vkb_draw d = base_draw(ctx, VKB_DRAW_STROKE, VKB_RULE_COUNT);
+    std::vector<vkb_stroke> &sv = ctx->batch.strokes;
+    if (sv.empty() || memcmp(&sv.back(), &st, sizeof st) != 0) sv.push_back(st);
+    d.xform_stroke |= ((uint32_t)sv.size() - 1) << 16;
     ctx->batch.draws.push_back(d);
 }
 void vkvg_fill_preserve(VkvgContext ctx) { if (!vkvg_status(ctx)) fill_preserve_(ctx); }
@@ -851,9 +881,8 @@ void vkvg_paint(VkvgContext ctx) {  // :990-1003
 }
 void vkvg_clear(VkvgContext ctx) {  // :734-753: everything drawn so far is wiped, so pending draws can be dropped
     if (vkvg_status(ctx)) return;
-    ctx->batch.draws.clear();
-    ctx->batch.grads.clear(); ctx->grad_slot = -1;
-    ctx->batch.dashes.clear();
+    ctx->batch.clear_draws();
+    ctx->grad_slot = -1;
     ctx->clear_pending = true;
 }
 
@@ -879,7 +908,7 @@ static void carry_path_over(VkvgContext ctx) {
         b.subpaths[i] = sp;
     }
     b.subpaths.resize(ns);
-    b.draws.clear(); b.grads.clear(); b.dashes.clear();
+    b.clear_draws();
     ctx->sp_first_elem -= e0;
     ctx->path_first_sp = 0;
     ctx->grad_slot     = -1;
@@ -964,16 +993,19 @@ static bool path_batch(VkvgContext ctx, uint32_t kind, vkb_batch &out) {
     finish_path(ctx);
     if (ctx->batch.subpaths.size() == ctx->path_first_sp) return false;
     vkb_batch saved_draws;
-    std::swap(saved_draws.draws, ctx->batch.draws);
-    std::swap(saved_draws.dashes, ctx->batch.dashes);
-    std::swap(saved_draws.grads, ctx->batch.grads);
+    auto swap_tables = [&]() {
+        std::swap(saved_draws.draws, ctx->batch.draws);
+        std::swap(saved_draws.xforms, ctx->batch.xforms);
+        std::swap(saved_draws.strokes, ctx->batch.strokes);
+        std::swap(saved_draws.dashes, ctx->batch.dashes);
+        std::swap(saved_draws.grads, ctx->batch.grads);
+    };
+    swap_tables();
     int32_t slot = ctx->grad_slot;
     ctx->grad_slot = -1;
     if (kind == VKB_DRAW_STROKE) stroke_preserve_(ctx); else fill_preserve_(ctx);
     out = ctx->batch;
-    std::swap(saved_draws.draws, ctx->batch.draws);
-    std::swap(saved_draws.dashes, ctx->batch.dashes);
-    std::swap(saved_draws.grads, ctx->batch.grads);
+    swap_tables();
     ctx->grad_slot = slot;
     return !out.draws.empty();
 }
