@@ -29,14 +29,15 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-SIZES = {"c1": 1024, "c2": 4096, "c3": 4096, "c4": 8192}
+SIZES = {"c1": 1024, "c2": 4096, "c3": 4096, "c4": 8192, "c5a": 16384}
 UNITS = {"c1": ("tiger_frames_per_s", "frames/s"), "c2": ("fill_Mpix_per_s", "Mpix/s"), "c3": ("stroke_Msegments_per_s", "Msegments/s"),
-         "c4": ("fill_Mpix_per_s", "Mpix/s")}
+         "c4": ("fill_Mpix_per_s", "Mpix/s"), "c5a": ("fill_Mpix_per_s", "Mpix/s")}
 WORKLOAD_NAMES = {
     "c1": "C1 tiger.svg via nanoSVG, 1024x1024, 4 samples, even-odd fills + miter strokes",
     "c2": "C2 100k random self-intersecting polygons, one fill each, 4096x4096, 4 samples",
     "c3": "C3 1M-segment polyline stroke, width 3, round joins/caps, dash {10,6}, 4096x4096, 4 samples",
     "c4": "C4 50k cubic-Bezier paths, linear/radial gradient fills, OVER, 8192x8192, 4 samples",
+    "c5a": "C5a 16384x16384 surface, 5M-segment mix (C2-style polygons + C3-style dashed polylines), sharded by tile-row stripes, NCCL all-gather",
 }
 
 
@@ -91,6 +92,29 @@ def build_scene(workload, seed, rule, n_limit=None, first=0):
                 g.close_path()
                 g.fill()
         return emit, size * size / 1e6, dict(n_paths=len(paths), n_segments=int(sum(len(p[0]) for p in paths)))
+    if workload == "c5a":
+        n_poly = 238000 if not n_limit else n_limit
+        polys, cols = scenes.polygons_c2(n_poly, size, seed)
+        # polygons_c2 draws radii for a 4096 canvas; keep them (small shapes on a huge surface), plus 25 polylines of 100k segments
+        lines = [scenes.polyline_c3(100001, size, seed * 100 + i) for i in range(25 if not n_limit else 1)]
+
+        def emit(g):
+            g.set_fill_rule(1)
+            for p, c in zip(polys, cols):
+                g.set_source_rgba(*[float(x) for x in c])
+                poly(g, p)
+                g.close_path()
+                g.fill()
+            g.set_line_width(3.0)
+            g.set_line_join(1)
+            g.set_line_cap(1)
+            g.set_dash([10.0, 6.0], 0.0)
+            for i, pts in enumerate(lines):
+                g.set_source_rgba(0.1 + 0.03 * i, 0.2, 0.8 - 0.02 * i, 1.0)
+                poly(g, pts)
+                g.stroke()
+        nseg = int(sum(len(p) for p in polys)) + sum(len(l) - 1 for l in lines)
+        return emit, size * size / 1e6, dict(n_paths=len(polys) + len(lines), n_segments=nseg)
     if workload == "c1":
         w, h, shapes = scenes.load_nsvg(os.path.join(ROOT, "tests", "golden", "tiger.nsvg.bin"))
         if n_limit:
@@ -188,8 +212,8 @@ def _ref_worker(args):
     return dt, info, kind
 
 
-SAMPLE = {"c1": None, "c2": 1500, "c3": 40000, "c4": 200}  # units of work per host thread per step (paths / segments)
-FULL = {"c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000}
+SAMPLE = {"c1": None, "c2": 1500, "c3": 40000, "c4": 200, "c5a": 1000}  # units of work per host thread per step (paths / segments)
+FULL = {"c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000, "c5a": 476000}
 
 
 def reference_step(workload, seed, rule, cores, pool):
@@ -239,7 +263,7 @@ def run_reference(args):
 
 
 def build_units(workload):
-    return {"c1": 1.0, "c2": 4096 * 4096 / 1e6, "c3": 1.0, "c4": 8192 * 8192 / 1e6}[workload]
+    return {"c1": 1.0, "c2": 4096 * 4096 / 1e6, "c3": 1.0, "c4": 8192 * 8192 / 1e6, "c5a": 16384 * 16384 / 1e6}[workload]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -277,17 +301,38 @@ def run_ours(args):
     size = SIZES[w]
     os.environ.setdefault("VKVG_B200_DEVICE", str(local))
     dev = v.Device(4)
-    surf = v.Surface(dev, size, size)
+    striped = w == "c5a"
+    if striped:   # strong scaling: every rank replays the same scene onto its own tile-row stripe
+        from vkvg_b200 import sharding
+        y0, sh = sharding.stripe_rows(size, world)[rank]
+        surf = v.Surface(dev, size, sh, full_height=size, origin_y=y0)
+        emit, units, info = build_scene(w, 1, args.rule)
+    else:
+        surf = v.Surface(dev, size, size)
+        emit, units, info = build_scene(w, 1 + rank, args.rule)
     ctx = v.Context(surf)
-    emit, units, info = build_scene(w, 1 + rank, args.rule)
     cs = v.CommandStream()
     emit(cs)
     ops_np, args_np = cs.arrays()
     # host buffers of the end-to-end path live in pinned memory
     ops_t = torch.from_numpy(ops_np.copy()).pin_memory()
     args_t = torch.from_numpy(args_np.copy()).pin_memory()
-    out_t = torch.empty((size, size, 4), dtype=torch.uint8).pin_memory()
+    out_t = torch.empty((surf.height, size, 4), dtype=torch.uint8).pin_memory()
     L = v.lib()
+    gather_ms = [0.0]
+
+    def gather():   # striped surfaces only: reassemble on every rank with one NCCL all-gather of contiguous rows
+        if not striped or dist is None:
+            return None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        local_t = torch.empty((surf.height, size, 4), dtype=torch.uint8, device="cuda")
+        surf.copy_to_device(local_t.data_ptr())
+        e0.record()
+        full = sharding.gather_stripes(local_t, size)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms[0] += e0.elapsed_time(e1)
+        return full
 
     parts = [0.0] * 5
 
@@ -301,6 +346,7 @@ def run_ours(args):
         t2 = time.perf_counter()
         parts[3] += dev.last_stats()["ms_host_upload"]
         parts[4] += dev.last_stats()["ms_total"]
+        gather()
         assert L.vkvg_b200_surface_read_premultiplied(surf.h, out_t.data_ptr()) == 0
         t3 = time.perf_counter()
         parts[0] += t1 - t0
@@ -320,8 +366,12 @@ def run_ours(args):
     l0 = L.vkvg_b200_launch_count()
     st = dev.time_resident(surf, args.steps, True, True)
     launches = L.vkvg_b200_launch_count() - l0
+    gather_ms[0] = 0.0
+    for _ in range(args.steps if striped else 0):
+        gather()
     barrier()
-    ms_step = max_over_ranks(st["ms_total"] / args.steps)
+    ms_step = max_over_ranks((st["ms_total"] + gather_ms[0]) / args.steps)
+    gather_step_ms = gather_ms[0] / args.steps
     # ---- end to end through the C ABI with host buffers ----
     barrier()
     parts[:] = [0.0] * 5
@@ -336,18 +386,18 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (fine pass: winding + paint + OVER + resolve, one launch per step) ----
     peak, peak_src = measured_peak_hbm()
     n_edges, n_draws = st["n_edges"], info["n_paths"]
-    alg_bytes = 16 * n_edges + 32 * n_draws + 4 * size * size
+    alg_bytes = 16 * n_edges + 32 * n_draws + 4 * size * surf.height
     fine_ms = st["ms_fine"] / args.steps
     achieved = alg_bytes / (fine_ms * 1e-3) / 1e9
     stage = {k: val / args.steps for k, val in st["ms_stage"].items()}
     name, unit = UNITS[w]
     line = {
-        "metric": name, "value": world * units / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[w], "rule": args.rule, "samples": 4, "sharding": "one independent canvas per rank",
+        "metric": name, "value": (1 if striped else world) * units / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if striped else "weak", "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[w], "rule": args.rule, "samples": 4, "sharding": ("tile-row stripes of one surface, %.3f ms all-gather per step" % gather_step_ms) if striped else "one independent canvas per rank",
                    "l2": "256 MiB scratch overwritten between timed steps", **info, "n_edges": int(n_edges),
                    "n_tile_edges": int(st["n_tile_edges"]), "n_points": int(st["n_points"]), "n_path_tiles": int(st["n_nonempty"])},
-        "e2e": {"value": world * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()),
+        "e2e": {"value": (1 if striped else world) * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()),
                 "d2h_bytes_per_step": int(out_t.numel()), "ms_per_step": e2e_s * 1e3,
                 "host_record_ms": parts[0] / args.steps * 1e3, "upload_render_ms": parts[1] / args.steps * 1e3,
                 "readback_ms": parts[2] / args.steps * 1e3, "host_upload_ms": parts[3] / args.steps,

@@ -75,6 +75,16 @@ vkvg_public void vkvg_b200_replay_resident(VkvgDevice dev, VkvgSurface surf, int
 vkvg_public vkvg_status_t vkvg_b200_time_resident(VkvgDevice dev, VkvgSurface surf, uint32_t steps, int clear_first, int flush_l2,
                                                   vkvg_b200_stats_t *sum);
 
+/* ---- 2b. multi-GPU sharding ---------------------------------------------------------------- */
+/* A surface that is the tile-row stripe [origin_y, origin_y + height) of a logical width x full_height surface
+ * (origin_y a multiple of 16).  Drawing the SAME calls on it as on the whole surface leaves exactly the pixels those
+ * rows of the whole surface would hold (the vertex stage and the paint evaluation use the logical size), so ranks can
+ * render disjoint stripes with no exchange and gather the rows afterwards. */
+vkvg_public VkvgSurface   vkvg_b200_surface_create_stripe(VkvgDevice dev, uint32_t width, uint32_t full_height, uint32_t origin_y, uint32_t height);
+/* device-to-device copy of the premultiplied RGBA8 rows into caller-owned device memory (e.g. a buffer handed to an
+ * NCCL gather); synchronous */
+vkvg_public vkvg_status_t vkvg_b200_surface_copy_to_device(VkvgSurface surf, void *device_dst);
+
 /* ---- 3. packed command stream -------------------------------------------------------------------------- */
 enum {
     VKVG_B200_OP_MOVE_TO = 1,   /* x y */

@@ -119,3 +119,49 @@ def test_c3_million_segment_dashed_stroke_properties(dev4):
     v2, i2 = c2.stroke_geometry()
     k = len(v2) - 64  # all but the tail (end cap of the shorter line)
     assert np.abs(verts[:k] - v2[:k]).max() <= 1e-3
+
+
+def test_stripe_surfaces_equal_rows_of_the_whole_surface(dev4):
+    """C5a's sharding unit: tile-row stripes rendered independently (vkvg_b200_surface_create_stripe) hold exactly the
+    rows of the unsharded render — fills, gradients, dashed round strokes, arbitrary float coordinates."""
+    from tests.golden import make_golden as mg
+    from vkvg_b200 import sharding
+    W, H = 640, 1000  # 62.5 tile rows: ragged
+
+    def emit(c):
+        polys, cols = scenes.polygons_c2(400, W, 5)
+        for i, (p, col) in enumerate(zip(polys, cols)):
+            p = p * np.array([1.0, H / W], np.float32)
+            if i % 3 == 0:
+                c.set_source_linear(0.0, 0.0, float(W), float(H), [(0, 1, 0, 0, 1), (0.5, 0, 1, 0, 0.5), (1, 0, 0, 1, 1)])
+            elif i % 3 == 1:
+                c.set_source_radial(W / 2, H / 2, 10.0, W / 2 + 20, H / 2 - 30, 400.0, [(0, 1, 1, 0, 1), (1, 0, 0, 1, 0.6)])
+            else:
+                c.set_source_rgba(*[float(x) for x in col])
+            c.set_fill_rule(i % 2)
+            c.move_to(float(p[0, 0]), float(p[0, 1]))
+            for q in p[1:]:
+                c.line_to(float(q[0]), float(q[1]))
+            c.close_path()
+            c.fill()
+        pts = scenes.polyline_c3(3000, W, 2) * np.array([1.0, H / W], np.float32)
+        c.set_source_rgba(0.1, 0.1, 0.1, 0.6)
+        c.set_line_width(2.5)
+        c.set_line_join(1)
+        c.set_line_cap(1)
+        c.set_dash([9.0, 4.0], 1.0)
+        c.move_to(float(pts[0, 0]), float(pts[0, 1]))
+        for q in pts[1:]:
+            c.line_to(float(q[0]), float(q[1]))
+        c.stroke()
+
+    s = v.Surface(dev4, W, H)
+    c = v.Context(s)
+    emit(c)
+    c.flush()
+    full = s.pixels()
+    for world in (2, 3, 8):
+        for rank in range(world):
+            surf, y0, h = sharding.render_striped(dev4, W, H, emit, rank, world)
+            assert np.array_equal(surf.pixels()[:h], full[y0:y0 + h]), (world, rank)
+            surf.close()

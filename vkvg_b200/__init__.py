@@ -103,6 +103,7 @@ _SIGS = {
     "vkvg_b200_flush_keep": (None, [_p]), "vkvg_b200_replay_resident": (None, [_p, _p, _i]),
     "vkvg_b200_replay": (_i, [_p, _p, C.c_uint64, _p, C.c_uint64]),
     "vkvg_b200_time_resident": (_i, [_p, _p, _u, _i, _i, C.POINTER(Stats)]),
+    "vkvg_b200_surface_create_stripe": (_p, [_p, _u, _u, _u, _u]), "vkvg_b200_surface_copy_to_device": (_i, [_p, _p]),
 }
 
 _lib = None
@@ -185,10 +186,15 @@ class Device:
 
 
 class Surface:
-    def __init__(self, dev, width, height):
+    def __init__(self, dev, width, height, full_height=None, origin_y=0):
+        """full_height / origin_y: this surface is the stripe [origin_y, origin_y + height) of a taller logical surface."""
         self.dev = dev
         self.width, self.height = width, height
-        self.h = lib().vkvg_surface_create(dev.h, width, height)
+        self.full_height, self.origin_y = full_height or height, origin_y
+        if full_height is None:
+            self.h = lib().vkvg_surface_create(dev.h, width, height)
+        else:
+            self.h = lib().vkvg_b200_surface_create_stripe(dev.h, width, full_height, origin_y, height)
         st = lib().vkvg_surface_status(self.h)
         if st:
             raise VkvgError("vkvg_surface_create: status %d" % st)
@@ -223,6 +229,12 @@ class Surface:
         if st:
             raise VkvgError("vkvg_surface_write_to_memory: status %d" % st)
         return out
+
+    def copy_to_device(self, device_ptr):
+        """premultiplied RGBA8 rows into caller-owned device memory (int pointer, e.g. torch.Tensor.data_ptr())."""
+        st = lib().vkvg_b200_surface_copy_to_device(self.h, device_ptr)
+        if st:
+            raise VkvgError("vkvg_b200_surface_copy_to_device: status %d" % st)
 
     def write_to_png(self, path):
         return lib().vkvg_surface_write_to_png(self.h, path.encode())

@@ -41,6 +41,7 @@ struct vkb_device_impl {
 struct vkb_surface_impl {
     vkb_device_impl *dev;
     uint32_t         w, h;
+    uint32_t         full_h, origin_y;  // logical surface this one is a stripe of (full_h == h, origin_y == 0 otherwise)
     DevBuf           image;
     DevBuf           ms_image, tile_ms, ms_mask;  // per-sample plane + per-tile validity flags (allocated by the first render)
     bool             known_clear;
@@ -90,10 +91,11 @@ void vkb_device_sync(vkb_device_impl *d) {
     VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
 }
 
-vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h) {
+vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, uint32_t full_h, uint32_t origin_y) {
     cudaSetDevice(d->ordinal);
     vkb_surface_impl *s = new vkb_surface_impl();
     s->dev = d; s->w = w; s->h = h;
+    s->full_h = full_h ? full_h : h; s->origin_y = origin_y;
     s->image.ensure((size_t)w * h * 4 + 16, d->stream);
     VKB_CUDA_OK(cudaMemsetAsync(s->image.p, 0, (size_t)w * h * 4, d->stream));
     s->known_clear = true;
@@ -115,6 +117,13 @@ void vkb_surface_clear(vkb_surface_impl *s) {
     s->known_clear = true;
 }
 const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s) { return s->image.as<uint32_t>(); }
+// device-to-device copy of the premultiplied pixels (e.g. into a tensor handed to an NCCL gather); synchronous
+int vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst) {
+    cudaSetDevice(s->dev->ordinal);
+    VKB_CUDA_OK(cudaMemcpyAsync(dst, s->image.p, (size_t)s->w * s->h * 4, cudaMemcpyDeviceToDevice, s->dev->stream));
+    VKB_CUDA_OK(cudaStreamSynchronize(s->dev->stream));
+    return g_cuda_failed;
+}
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) {
     vkb_device_impl *d = s->dev;
     cudaSetDevice(d->ordinal);
@@ -461,7 +470,7 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
     vkb_stats    S;
     memset(&S, 0, sizeof S);
     S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes; S.ms_host_upload = d->ms_host_upload;
-    SurfaceDesc sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE};
+    SurfaceDesc sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE, surf->full_h, surf->origin_y};
     VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
     VKB_CUDA_OK(cudaEventRecord(d->ev_stage[0], st));
     d->totals.ensure(16 * 8, st);
@@ -594,8 +603,8 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
     cudaSetDevice(d->ordinal);
     cudaStream_t st = d->stream;
     VKB_CUDA_OK(cudaStreamSynchronize(st));
-    vkb_surface_impl *surf = vkb_surface_new(d, w, h);
-    SurfaceDesc sd = {w, h, samples, (w + VKB_TILE - 1) / VKB_TILE, (h + VKB_TILE - 1) / VKB_TILE};
+    vkb_surface_impl *surf = vkb_surface_new(d, w, h, h, 0);
+    SurfaceDesc sd = {w, h, samples, (w + VKB_TILE - 1) / VKB_TILE, (h + VKB_TILE - 1) / VKB_TILE, h, 0};
     d->totals.ensure(16 * 8, st);
     d->edges.ensure((n + 1) * 16, st);
     d->edge_draw.ensure((n + 1) * 4, st);

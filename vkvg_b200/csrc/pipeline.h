@@ -37,6 +37,10 @@ void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offse
 struct SurfaceDesc {
     uint32_t width, height, samples;
     uint32_t tiles_x, tiles_y;
+    // a stripe of a larger logical surface (multi-GPU tile-row sharding): the vertex stage and the paint evaluation use
+    // the logical height, and snapped y coordinates are shifted by origin_y pixels (a multiple of the tile size), so a
+    // stripe holds exactly the pixels the same rows of the whole surface would hold
+    uint32_t full_height, origin_y;
 };
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges,

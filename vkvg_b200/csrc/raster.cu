@@ -73,8 +73,9 @@ fill_edges_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, 
     float2   a = pts[first + k], b = pts[first + (k + 1 == n ? 0 : k + 1)];
     const float *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
     vkb_edge e;
-    vs_snap(m, (float)sd.width, (float)sd.height, a.x, a.y, e.x0, e.y0);
-    vs_snap(m, (float)sd.width, (float)sd.height, b.x, b.y, e.x1, e.y1);
+    vs_snap(m, (float)sd.width, (float)sd.full_height, a.x, a.y, e.x0, e.y0);
+    vs_snap(m, (float)sd.width, (float)sd.full_height, b.x, b.y, e.x1, e.y1);
+    e.y0 -= (int32_t)sd.origin_y * 256; e.y1 -= (int32_t)sd.origin_y * 256;
     edges[item]     = e;
     edge_draw[item] = d;
 }
@@ -108,9 +109,10 @@ tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_
         const float *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
         float2       a = verts[ia], b = verts[ib], c = verts[ic];
         int32_t      ax, ay, bx, by, cx, cy;
-        vs_snap(m, (float)sd.width, (float)sd.height, a.x, a.y, ax, ay);
-        vs_snap(m, (float)sd.width, (float)sd.height, b.x, b.y, bx, by);
-        vs_snap(m, (float)sd.width, (float)sd.height, c.x, c.y, cx, cy);
+        vs_snap(m, (float)sd.width, (float)sd.full_height, a.x, a.y, ax, ay);
+        vs_snap(m, (float)sd.width, (float)sd.full_height, b.x, b.y, bx, by);
+        vs_snap(m, (float)sd.width, (float)sd.full_height, c.x, c.y, cx, cy);
+        ay -= (int32_t)sd.origin_y * 256; by -= (int32_t)sd.origin_y * 256; cy -= (int32_t)sd.origin_y * 256;
         long long area = (long long)(bx - ax) * (cy - ay) - (long long)(cx - ax) * (by - ay);
         if (area > 0) {  // cross > 0 winds -1 under our convention: flip
             int32_t tx = bx, ty = by;
@@ -804,7 +806,8 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
             }
             if (__any_sync(0xffffffffu, nmax != 0)) {
                 float src[4];
-                eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.height, pt.color, pt.opacity, (float)px + 0.5f, (float)py + 0.5f, src, lut);
+                eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
+                           (float)(py + a.sd.origin_y) + 0.5f, src, lut);
                 const float ia = 1.0f - src[3];
                 if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
                     nmax = 1;

@@ -91,7 +91,8 @@ void             vkb_device_close(vkb_device_impl *d);
 int              vkb_device_failed(vkb_device_impl *d);
 void             vkb_device_sync(vkb_device_impl *d);
 
-vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h);
+vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, uint32_t full_h, uint32_t origin_y);
+int               vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst);
 void              vkb_surface_free(vkb_surface_impl *s);
 void              vkb_surface_clear(vkb_surface_impl *s);
 // premultiplied RGBA8 rows, or un-premultiplied as vkvg_surface_write_to_memory does; synchronous

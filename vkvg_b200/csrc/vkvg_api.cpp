@@ -225,7 +225,7 @@ void vkvg_device_set_context_cache_size(VkvgDevice, uint32_t) {}  // contexts ho
 // ====================================================================================================
 // surface — reference src/vkvg_surface.c
 // ====================================================================================================
-VkvgSurface vkvg_surface_create(VkvgDevice dev, uint32_t width, uint32_t height) {
+static VkvgSurface create_surface(VkvgDevice dev, uint32_t width, uint32_t height, uint32_t full_height, uint32_t origin_y) {
     if (vkvg_device_status(dev)) return (VkvgSurface)&s_device_error;  // _create_surface, surface_internal.c:213-224
     VkvgSurface surf = new _vkvg_surface_t();
     surf->status     = VKVG_STATUS_SUCCESS;
@@ -235,11 +235,21 @@ VkvgSurface vkvg_surface_create(VkvgDevice dev, uint32_t width, uint32_t height)
     surf->height     = height > 1 ? height : 1;
     {
         std::lock_guard<std::mutex> lk(dev->mtx);
-        surf->impl = vkb_surface_new(dev->impl, surf->width, surf->height);
+        surf->impl = vkb_surface_new(dev->impl, surf->width, surf->height, full_height ? full_height : surf->height, origin_y);
     }
     if (!surf->impl || vkb_device_failed(dev->impl)) surf->status = VKVG_STATUS_DEVICE_ERROR;
     vkvg_device_reference(dev);
     return surf;
+}
+VkvgSurface vkvg_surface_create(VkvgDevice dev, uint32_t width, uint32_t height) { return create_surface(dev, width, height, 0, 0); }
+VkvgSurface vkvg_b200_surface_create_stripe(VkvgDevice dev, uint32_t width, uint32_t full_height, uint32_t origin_y, uint32_t height) {
+    if (origin_y % VKB_TILE != 0 || origin_y + height > full_height) return (VkvgSurface)&s_invalid_surface;
+    return create_surface(dev, width, height, full_height, origin_y);
+}
+vkvg_status_t vkvg_b200_surface_copy_to_device(VkvgSurface surf, void *device_dst) {
+    if (vkvg_surface_status(surf) || !device_dst) return VKVG_STATUS_INVALID_SURFACE;
+    std::lock_guard<std::mutex> lk(surf->dev->mtx);
+    return vkb_surface_copy_to_device(surf->impl, device_dst) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
 }
 vkvg_status_t vkvg_surface_status(VkvgSurface surf) { return !surf ? VKVG_STATUS_NULL_POINTER : surf->status; }
 VkvgSurface   vkvg_surface_reference(VkvgSurface surf) {
