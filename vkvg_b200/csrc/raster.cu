@@ -88,12 +88,42 @@ void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_x
 }
 
 // ---- stroke: three edges per triangle, oriented to wind +1 (so the sum over triangles is the number of
-//      triangles covering the sample, which is how many times the reference blends it) ----
+//      triangles covering the sample, which is how many times the reference blends it).
+//      An edge shared by two consecutive triangles of the index list that traverse it in opposite directions
+//      contributes exactly zero winding to every sample (quad diagonals, fan spokes, the seam between a quad and the
+//      next join): both copies are dropped here, which roughly halves what the rasteriser has to look at. ----
+struct TriV {
+    uint32_t i[3];
+    int32_t  x[3], y[3];
+    int      sign;  // +1: index order is kept, -1: reversed, 0: degenerate / invalid (emits nothing)
+};
+__device__ __forceinline__ bool tri_has(const uint32_t (&i)[3], uint32_t u, uint32_t v) {
+    return (i[0] == u || i[1] == u || i[2] == u) && (i[0] == v || i[1] == v || i[2] == v);
+}
+// +1 if u is followed by v in the cyclic index order of i, -1 if v is followed by u
+__device__ __forceinline__ int tri_dir(const uint32_t (&i)[3], uint32_t u, uint32_t v) {
+    return ((i[0] == u && i[1] == v) || (i[1] == u && i[2] == v) || (i[2] == u && i[0] == v)) ? 1 : -1;
+}
+__device__ __forceinline__ void tri_idx(const uint32_t *inds, uint32_t n_tris, long long t, uint32_t (&i)[3]) {
+    if (t < 0 || t >= (long long)n_tris) { i[0] = i[1] = i[2] = 0xffffffffu; return; }
+    i[0] = inds[3 * t]; i[1] = inds[3 * t + 1]; i[2] = inds[3 * t + 2];
+}
+__device__ __forceinline__ int tri_sign(const float2 *verts, uint32_t n_verts, const uint32_t (&i)[3], const float *m, SurfaceDesc sd, int32_t (&x)[3],
+                                        int32_t (&y)[3]) {
+    if (i[0] >= n_verts || i[1] >= n_verts || i[2] >= n_verts) return 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float2 p = verts[i[k]];
+        vs_snap(m, (float)sd.width, (float)sd.full_height, p.x, p.y, x[k], y[k]);
+        y[k] -= (int32_t)sd.origin_y * 256;
+    }
+    long long area = (long long)(x[1] - x[0]) * (y[2] - y[0]) - (long long)(x[2] - x[0]) * (y[1] - y[0]);
+    return area > 0 ? -1 : (area < 0 ? 1 : 0);  // cross > 0 winds -1 under our convention: such a triangle is reversed
+}
 __global__ void __launch_bounds__(256)
 tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
-            const uint32_t *sdraw_id,
-            const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges,
-            uint32_t *edge_draw) {
+            const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd,
+            vkb_edge *edges, uint32_t *edge_draw) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tris) return;
     // stroke draw owning index 3t: last q whose first item's index offset <= 3t
@@ -102,29 +132,41 @@ tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_
         uint32_t mid = (lo + hi) >> 1;
         if ((uint32_t)(item_offsets[sdraw_first_item[mid]] >> 32) <= 3 * t) lo = mid; else hi = mid;
     }
-    uint32_t d  = sdraw_id[lo];
-    uint32_t ia = inds[3 * t], ib = inds[3 * t + 1], ic = inds[3 * t + 2];
-    vkb_edge e0 = {0, 0, 0, 0}, e1 = e0, e2 = e0;
-    if (ia < n_verts && ib < n_verts && ic < n_verts) {
-        const float *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
-        float2       a = verts[ia], b = verts[ib], c = verts[ic];
-        int32_t      ax, ay, bx, by, cx, cy;
-        vs_snap(m, (float)sd.width, (float)sd.full_height, a.x, a.y, ax, ay);
-        vs_snap(m, (float)sd.width, (float)sd.full_height, b.x, b.y, bx, by);
-        vs_snap(m, (float)sd.width, (float)sd.full_height, c.x, c.y, cx, cy);
-        ay -= (int32_t)sd.origin_y * 256; by -= (int32_t)sd.origin_y * 256; cy -= (int32_t)sd.origin_y * 256;
-        long long area = (long long)(bx - ax) * (cy - ay) - (long long)(cx - ax) * (by - ay);
-        if (area > 0) {  // cross > 0 winds -1 under our convention: flip
-            int32_t tx = bx, ty = by;
-            bx = cx; by = cy; cx = tx; cy = ty;
+    const uint32_t d = sdraw_id[lo];
+    const float   *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
+    uint32_t       i0[3], ip1[3], ip2[3], im1[3], im2[3];
+    tri_idx(inds, n_tris, (long long)t, i0);
+    tri_idx(inds, n_tris, (long long)t + 1, ip1);
+    tri_idx(inds, n_tris, (long long)t + 2, ip2);
+    tri_idx(inds, n_tris, (long long)t - 1, im1);
+    tri_idx(inds, n_tris, (long long)t - 2, im2);
+    int32_t x[3], y[3], nx[3], ny[3];
+    const int sg = tri_sign(verts, n_verts, i0, m, sd, x, y);
+    int       sg_next = 2, sg_prev = 2;  // 2: not evaluated yet (vertices of a neighbour share this draw's matrix: shared indices)
+    vkb_edge  e[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        e[k] = vkb_edge{0, 0, 0, 0};
+        if (sg == 0) continue;
+        // k-th edge in normalised orientation: kept order a->b, b->c, c->a; reversed a->c, c->b, b->a
+        const int ka = sg > 0 ? k : (3 - k) % 3, kb = sg > 0 ? (k + 1) % 3 : (5 - k) % 3;
+        const uint32_t u = i0[ka], v = i0[kb];
+        bool           drop = false;
+        if (tri_has(ip1, u, v)) {
+            if (!tri_has(im1, u, v) && !tri_has(ip2, u, v)) {
+                if (sg_next == 2) sg_next = tri_sign(verts, n_verts, ip1, m, sd, nx, ny);
+                // direction of u->v inside the neighbour after ITS normalisation; opposite to ours (which is u->v) cancels
+                drop = sg_next != 0 && tri_dir(ip1, u, v) * sg_next < 0;
+            }
+        } else if (tri_has(im1, u, v)) {
+            if (!tri_has(im2, u, v)) {
+                if (sg_prev == 2) sg_prev = tri_sign(verts, n_verts, im1, m, sd, nx, ny);
+                drop = sg_prev != 0 && tri_dir(im1, u, v) * sg_prev < 0;
+            }
         }
-        if (area != 0) {
-            e0 = vkb_edge{ax, ay, bx, by};
-            e1 = vkb_edge{bx, by, cx, cy};
-            e2 = vkb_edge{cx, cy, ax, ay};
-        }
+        if (!drop) e[k] = vkb_edge{x[ka], y[ka], x[kb], y[kb]};
     }
-    edges[3 * t] = e0; edges[3 * t + 1] = e1; edges[3 * t + 2] = e2;
+    edges[3 * t] = e[0]; edges[3 * t + 1] = e[1]; edges[3 * t + 2] = e[2];
     edge_draw[3 * t] = d; edge_draw[3 * t + 1] = d; edge_draw[3 * t + 2] = d;
 }
 void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
@@ -670,7 +712,12 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
             const bool     ok = lane < FINE_SLOTS && p < end;
             const int4     h  = nh0, hp = nh1;
             const int      kk = lane == 0 ? (int)k0 : 0;  // edges of path-tile p0 consumed by earlier groups
-            const int      nt = ok ? max(1, (h.w - kk + FINE_CH - 1) / FINE_CH) : 0;
+            // chunk size of a path-tile: one task up to 16 edges; up to 128 edges chunks of <= 16; beyond that a whole
+            // number of groups of FINE_SLOTS equal chunks (<= FINE_CH) so that no warp idles while one finishes a long list
+            int chunk = FINE_CH;
+            if (h.w <= 128) { const int q = max(1, (h.w + 15) / 16); chunk = max(1, (h.w + q - 1) / q); }
+            else { const int q = FINE_SLOTS * ((h.w + FINE_SLOTS * FINE_CH - 1) / (FINE_SLOTS * FINE_CH)); chunk = (h.w + q - 1) / q; }
+            const int      nt = ok ? max(1, (h.w - kk + chunk - 1) / chunk) : 0;
             int            incl = nt;
 #pragma unroll
             for (int o = 1; o < FINE_SLOTS; o <<= 1) {
@@ -680,9 +727,9 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
             const int start = incl - nt;
             for (int t = 0; t < nt && start + t < FINE_SLOTS; t++) {
                 FineTask ft;
-                const int e0 = kk + t * FINE_CH;
+                const int e0 = kk + t * chunk;
                 ft.eoff = (uint32_t)h.z + (uint32_t)e0;
-                ft.n    = min(FINE_CH, h.w - e0);
+                ft.n    = min(chunk, h.w - e0);
                 ft.draw = h.x;
                 ft.bd   = e0 == 0 ? h.y : 0;
                 ft.last = e0 + ft.n >= h.w ? 1u : 0u;
@@ -693,7 +740,7 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
             // cursor after this group: the path-tile that owns slot FINE_SLOTS-1 (or the first one not started)
             if (ok && start < FINE_SLOTS && start + nt >= FINE_SLOTS) {
                 const int done = FINE_SLOTS - start;             // tasks of this path-tile issued in this group
-                const int e1   = kk + done * FINE_CH;
+                const int e1   = kk + done * chunk;
                 if (e1 >= h.w) { s_p = p + 1; s_k = 0; }
                 else { s_p = p; s_k = (uint32_t)e1; }
             }
