@@ -300,7 +300,7 @@ def run_ours(args):
     w = args.workload
     size = SIZES[w]
     os.environ.setdefault("VKVG_B200_DEVICE", str(local))
-    dev = v.Device(4)
+    dev = v.Device(4, analytic=args.coverage == "analytic")
     striped = w == "c5a"
     if striped:   # strong scaling: every rank replays the same scene onto its own tile-row stripe
         from vkvg_b200 import sharding
@@ -394,7 +394,8 @@ def run_ours(args):
     line = {
         "metric": name, "value": (1 if striped else world) * units / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if striped else "weak", "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[w], "rule": args.rule, "samples": 4, "sharding": ("tile-row stripes of one surface, %.3f ms all-gather per step" % gather_step_ms) if striped else "one independent canvas per rank",
+        "config": {"workload": WORKLOAD_NAMES[w] if args.coverage == "msaa" else WORKLOAD_NAMES[w].replace("4 samples", "analytic coverage"),
+                   "rule": args.rule, "samples": 4 if args.coverage == "msaa" else 0, "coverage": args.coverage, "sharding": ("tile-row stripes of one surface, %.3f ms all-gather per step" % gather_step_ms) if striped else "one independent canvas per rank",
                    "l2": "256 MiB scratch overwritten between timed steps", **info, "n_edges": int(n_edges),
                    "n_tile_edges": int(st["n_tile_edges"]), "n_points": int(st["n_points"]), "n_path_tiles": int(st["n_nonempty"])},
         "e2e": {"value": (1 if striped else world) * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()),
@@ -403,7 +404,7 @@ def run_ours(args):
                 "readback_ms": parts[2] / args.steps * 1e3, "host_upload_ms": parts[3] / args.steps,
                 "device_ms_in_flush": parts[4] / args.steps, "h2d_bytes_wire": int(st["h2d_bytes"])},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "fine_k<4>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": "fine_k<4>" if args.coverage == "msaa" else "fine_analytic_k", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "algorithmic_bytes": int(alg_bytes), "kernel_ms": fine_ms, "peak_source": peak_src,
                      "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
         "stage_ms": stage,
@@ -439,6 +440,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(SIZES))
     ap.add_argument("--rule", default="nz", choices=["nz", "eo"])
+    ap.add_argument("--coverage", default="msaa", choices=["msaa", "analytic"],
+                    help="msaa: 4-sample mode, bit-exact with the reference's rasterisation (default); analytic: exact-area coverage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

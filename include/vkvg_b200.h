@@ -17,6 +17,18 @@
 extern "C" {
 #endif
 
+/* ---- 0. coverage mode -------------------------------------------------------------------------------------- */
+/* MSAA (default): per-sample integer winding at the sample positions of the device's sample count, per-sample blend and
+ * box resolve — the mode that is bit-exact with the reference's rasterisation.
+ * ANALYTIC: coverage of a pixel = exact area of the shape inside it (integral of the winding number over the pixel
+ * square, then the fill rule), one colour per pixel, the paint scaled by the coverage blended once.  Not bit-comparable
+ * with the reference (it has no such mode); strokes cover the UNION of their triangles, so self-overlapping translucent
+ * strokes are not double-blended as the reference does.  Select it once, before the first draw on the device's surfaces
+ * (or set VKVG_B200_COVERAGE=analytic in the environment of an unmodified vkvg client). */
+enum { VKVG_B200_COVERAGE_MSAA = 0, VKVG_B200_COVERAGE_ANALYTIC = 1 };
+vkvg_public vkvg_status_t vkvg_b200_device_set_coverage_mode(VkvgDevice dev, int mode);
+vkvg_public int           vkvg_b200_device_get_coverage_mode(VkvgDevice dev);
+
 /* ---- 1. stage introspection ------------------------------------------------------------------------- */
 
 /* Flatten the context's current path on the GPU (replaces _recursive_bezier + arc loops,
@@ -38,11 +50,13 @@ vkvg_public void vkvg_b200_stroke_geometry(VkvgContext ctx, float *xy, uint32_t 
 vkvg_public uint64_t vkvg_b200_path_edges(VkvgContext ctx, int kind, int32_t *edges_xyxy, uint64_t cap_edges);
 
 /* Flush the context; additionally copy the per-sample integer winding computed by the tile rasteriser for the
- * LAST draw of the flushed batch into winding (height*width*samples int32, 0 where that draw has no tile). */
+ * LAST draw of the flushed batch into winding (height*width*samples int32, 0 where that draw has no tile).
+ * In ANALYTIC coverage mode the buffer receives height*width floats instead: the area integral A of that draw. */
 vkvg_public void vkvg_b200_flush_capture_winding(VkvgContext ctx, int32_t *winding);
 
 /* Run binning + fine pass on raw directed edges as one draw and return the per-sample winding
- * (height*width*samples).  This is the integer core that must match oracle ovk_winding_brute bit for bit. */
+ * (height*width*samples).  This is the integer core that must match oracle ovk_winding_brute bit for bit.
+ * In ANALYTIC coverage mode: height*width floats, the area integral A per pixel (oracle: ovk_area_brute). */
 vkvg_public vkvg_status_t vkvg_b200_winding(VkvgDevice dev, const int32_t *edges_xyxy, uint64_t n_edges, uint32_t width, uint32_t height,
                                             int32_t *winding);
 

@@ -88,18 +88,26 @@ class Oracle(_Base):
             L.ovk_get_matrix.argtypes = [_p, _p]
             L.ovk_write_to_memory.argtypes = [_p, _p]
             L.ovk_set_capture_coverage.argtypes = [_p, _i]
+            L.ovk_set_coverage_mode.argtypes = [_p, _i]
+            L.ovk_last_area.restype = _p
+            L.ovk_last_area.argtypes = [_p]
+            L.ovk_area_brute.argtypes = [_p, C.c_uint64, _u, _u, _p]
             for n in ("ovk_path_points", "ovk_path_table", "ovk_last_vertices", "ovk_last_indices"):
                 getattr(L, n).restype = _u
                 getattr(L, n).argtypes = [_p, C.POINTER(_p)]
             cls._libh = L
         return cls._libh
 
-    def __init__(self, width, height, samples=4):
+    def __init__(self, width, height, samples=4, analytic=False):
         self._lib = self.lib()
+        if analytic:
+            samples = 1   # analytic-coverage mode keeps one colour per pixel
         self.width, self.height, self.samples = width, height, samples
         self._ctx = self._lib.ovk_create(width, height, samples)
         if not self._ctx:
             raise ValueError("unsupported sample count %r" % samples)
+        if analytic:
+            self._lib.ovk_set_coverage_mode(self._ctx, 1)
 
     def close(self):
         if self._ctx:
@@ -179,6 +187,12 @@ class Oracle(_Base):
         buf = (C.c_int32 * (self.width * self.height * self.samples)).from_address(ptr)
         return np.frombuffer(buf, np.int32).reshape(self.height, self.width, self.samples).copy()
 
+    def last_area(self):
+        """analytic mode: integral of the winding number over each pixel for the last draw, (H, W) float64."""
+        ptr = self._lib.ovk_last_area(self._ctx)
+        buf = (C.c_double * (self.width * self.height)).from_address(ptr)
+        return np.frombuffer(buf, np.float64).reshape(self.height, self.width).copy()
+
     def raster_ref_drawlist(self, draws_ptr, n, blob_ptr):
         self._lib.ovk_raster_ref_drawlist(self._ctx, draws_ptr, n, blob_ptr)
 
@@ -190,6 +204,14 @@ def flatten_cubic(p, tol):
     n = L.ovk_flatten_cubic(*args, None, 0)
     out = np.zeros((n, 2), np.float32)
     L.ovk_flatten_cubic(*args, out.ctypes.data, n)
+    return out
+
+
+def area_brute(edges, width, height):
+    """analytic mode: integral of the winding number of directed 24.8 edges over each pixel square, (H, W) float64."""
+    e = np.ascontiguousarray(edges, np.int32).reshape(-1, 4)
+    out = np.zeros((height, width), np.float64)
+    Oracle.lib().ovk_area_brute(e.ctypes.data, len(e), width, height, out.ctypes.data)
     return out
 
 

@@ -83,6 +83,8 @@ struct ovk_ctx {
     bool      resolved_dirty;
     int32_t  *coverage; /* optional capture */
     int       capture;
+    int       analytic; /* 1: analytic-coverage mode (one colour per pixel, exact area coverage), see analytic_draw */
+    double   *area;     /* analytic mode: integral of the winding number over each pixel, last draw (W*H) */
     /* path storage, the reference's encoding (src/vkvg_context_internal.h:184-196) */
     v2       *points;
     uint32_t  pointCount, sizePoints;
@@ -317,6 +319,95 @@ void ovk_winding_brute(const int32_t *e, uint64_t n, uint32_t W, uint32_t H, uin
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* analytic-coverage mode (north_star: "with an analytic-coverage mode alongside"; no counterpart in the      */
+/* reference, whose coverage is the ICD's MSAA).  Definition, shared with the CUDA fine pass:                 */
+/*   A(px,py) = integral over the pixel square of the winding number W(x,y) of the draw's directed edges      */
+/*            = sum_e sign(dy_e) * integral_{y in span_e, py <= y <= py+1} clamp(px + 1 - x_e(y), 0, 1) dy     */
+/*   coverage = min(|A|, 1) for NON_ZERO and for strokes (union of the triangles), 1 - |A mod 2 - 1| for       */
+/*   EVEN_ODD; the pixel (one colour, no samples) is blended once with the paint scaled by the coverage.      */
+/* Evaluated here edge by edge in double precision over the whole surface (no tiles, no backdrop), i.e. by a  */
+/* different decomposition than the CUDA path's backdrop + V + H split.                                       */
+/* ------------------------------------------------------------------ */
+static inline double clampd(double x, double a, double b) { return x < a ? a : (x > b ? b : x); }
+/* mean over t in [0,1] of clamp(lo + (hi - lo) t, 0, 1), lo <= hi */
+static inline double mean_clamp01(double lo, double hi) {
+    double d = hi - lo;
+    if (d < 1e-300) return clampd(lo, 0.0, 1.0);
+    double t0 = clampd(-lo / d, 0.0, 1.0), t1 = clampd((hi - 1.0) / d, 0.0, 1.0);
+    double clo = lo > 0.0 ? lo : 0.0, chi = hi < 1.0 ? hi : 1.0;
+    return t1 + (1.0 - t0 - t1) * 0.5 * (clo + chi);
+}
+void ovk_area_brute(const int32_t *e, uint64_t n, uint32_t W, uint32_t H, double *out) {
+    size_t  stride = (size_t)W + 1;
+    double *acc    = (double *)calloc(stride * H, sizeof(double)); /* per-row deltas: prefix sum along x gives A */
+    for (uint64_t i = 0; i < n; i++) {
+        double ax = e[4 * i] / 256.0, ay = e[4 * i + 1] / 256.0, bx = e[4 * i + 2] / 256.0, by = e[4 * i + 3] / 256.0;
+        if (ay == by) continue;
+        double sgn = by > ay ? 1.0 : -1.0;
+        double xt = by > ay ? ax : bx, yt = by > ay ? ay : by, xb = by > ay ? bx : ax, yb = by > ay ? by : ay;
+        double slope = (xb - xt) / (yb - yt);
+        int64_t r0 = (int64_t)floor(yt), r1 = (int64_t)ceil(yb) - 1;
+        if (r0 < 0) r0 = 0;
+        if (r1 > (int64_t)H - 1) r1 = (int64_t)H - 1;
+        for (int64_t r = r0; r <= r1; r++) {
+            double ys = yt > (double)r ? yt : (double)r, ye = yb < (double)(r + 1) ? yb : (double)(r + 1);
+            if (ye <= ys) continue;
+            double xs = xt + (ys - yt) * slope, xe = xt + (ye - yt) * slope, h = ye - ys;
+            double xmin = xs < xe ? xs : xe, xmax = xs < xe ? xe : xs;
+            double *row = acc + (size_t)r * stride;
+            if (xmin >= (double)W) continue;
+            int64_t c0 = (int64_t)floor(xmin), c1 = (int64_t)floor(xmax);
+            if (c0 < 0) c0 = 0;
+            if (c1 > (int64_t)W - 1) c1 = (int64_t)W - 1;
+            double prev = 0.0;
+            for (int64_t c = c0; c <= c1; c++) {
+                double a = h * mean_clamp01((double)(c + 1) - xmax, (double)(c + 1) - xmin);
+                row[c] += sgn * (a - prev);
+                prev = a;
+            }
+            /* every pixel right of the last one the edge touches is covered over the whole height h
+             * (an edge wholly left of the surface, c1 < 0, covers from column 0) */
+            int64_t cn = c1 < c0 ? c0 : c1 + 1;
+            if (cn < (int64_t)W) row[cn] += sgn * (h - prev);
+        }
+    }
+    for (uint32_t y = 0; y < H; y++) {
+        double run = 0.0;
+        for (uint32_t x = 0; x < W; x++) {
+            run += acc[(size_t)y * stride + x];
+            out[(size_t)y * W + x] = run;
+        }
+    }
+    free(acc);
+}
+static inline float analytic_coverage(double A, int rule) {
+    if (rule == OVK_RULE_EVEN_ODD) {
+        double t = A - 2.0 * floor(A * 0.5);
+        return (float)(1.0 - fabs(t - 1.0));
+    }
+    double a = fabs(A);
+    return (float)(a < 1.0 ? a : 1.0);
+}
+/* one draw in analytic mode: edges -> A -> coverage -> paint * coverage OVER the single colour of the pixel */
+static void analytic_draw(ovk_ctx *c, const int32_t *e, uint64_t n, int rule, int patType, const grad_t *grad, uint32_t solid, float opacity) {
+    if (!c->area) c->area = (double *)calloc((size_t)c->W * c->H, sizeof(double));
+    ovk_area_brute(e, n, c->W, c->H, c->area);
+    for (uint32_t py = 0; py < c->H; py++)
+        for (uint32_t px = 0; px < c->W; px++) {
+            float cov = analytic_coverage(c->area[(size_t)py * c->W + px], rule);
+            if (!(cov > 0.0f)) continue;
+            float col[4], s[4];
+            eval_paint(patType, grad, (float)c->W, (float)c->H, solid, opacity, (float)px + 0.5f, (float)py + 0.5f, col);
+            for (int k = 0; k < 4; k++) s[k] = col[k] * cov;
+            size_t base = ((size_t)py * c->W + px) * c->S;
+            for (uint32_t q = 0; q < c->S; q++) c->samples[base + q] = blend_over(c->samples[base + q], s);
+        }
+    c->resolved_dirty = true;
+}
+void ovk_set_coverage_mode(ovk_ctx *c, int analytic) { c->analytic = analytic; }
+const double *ovk_last_area(ovk_ctx *c) { return c->area; }
+
 static void cov_add(ovk_ctx *c, uint32_t px, uint32_t py, uint32_t s, int32_t v) {
     if (c->capture) c->coverage[((size_t)py * c->W + px) * c->S + s] += v;
 }
@@ -411,7 +502,7 @@ ovk_ctx *ovk_create(uint32_t W, uint32_t H, uint32_t S) {
 }
 void ovk_destroy(ovk_ctx *c) {
     if (!c) return;
-    free(c->samples); free(c->stencil); free(c->resolved); free(c->coverage);
+    free(c->samples); free(c->stencil); free(c->resolved); free(c->coverage); free(c->area);
     free(c->points); free(c->pathes); free(c->verts); free(c->inds); free(c->dashes);
     free(c);
 }
@@ -1068,6 +1159,22 @@ static void draw_indexed(ovk_ctx *c, const v2 *verts, uint32_t nv, const uint32_
     int32_t *fx = (int32_t *)malloc((size_t)nv * 8 + 8);
     snap_all(c, verts, nv, fx);
     paint_t    p = cur_paint(c);
+    if (c->analytic) { /* every triangle oriented to wind +1: A = total triangle area inside the pixel, coverage = min(A, 1) */
+        int32_t *e = (int32_t *)malloc((size_t)(ni / 3 + 1) * 3 * 16);
+        uint64_t n = 0;
+        for (uint32_t t = 0; t + 2 < ni; t += 3) {
+            if (inds[t] >= nv || inds[t + 1] >= nv || inds[t + 2] >= nv) continue;
+            const int32_t *a = fx + 2 * inds[t], *b = fx + 2 * inds[t + 1], *d = fx + 2 * inds[t + 2];
+            int64_t area = (int64_t)(b[0] - a[0]) * (d[1] - a[1]) - (int64_t)(d[0] - a[0]) * (b[1] - a[1]);
+            if (area == 0) continue;
+            if (area > 0) { const int32_t *tmp = b; b = d; d = tmp; } /* cross > 0 winds -1 under W's convention: reverse */
+            const int32_t *v[4] = {a, b, d, a};
+            for (int k = 0; k < 3; k++, n++) { e[4 * n] = v[k][0]; e[4 * n + 1] = v[k][1]; e[4 * n + 2] = v[k + 1][0]; e[4 * n + 3] = v[k + 1][1]; }
+        }
+        analytic_draw(c, e, n, OVK_RULE_COUNT, p.patType, &p.grad, p.solid, p.opacity);
+        free(e); free(fx);
+        return;
+    }
     blend_user u = {&p, 0x2};
     cov_reset(c);
     for (uint32_t t = 0; t + 2 < ni; t += 3) {
@@ -1132,6 +1239,13 @@ static void fill_preserve_(ovk_ctx *c) { /* vkvg_context.c:796-821 */
     if (!c->pathPtr) return;
     paint_t p = cur_paint(c);
     cov_reset(c);
+    if (c->analytic) { /* polygon edges of every sub-path with > 2 points, either rule */
+        nz_user u = {(int32_t *)malloc((size_t)c->pointCount * 16 + 16), 0, INT64_MAX, INT64_MAX, INT64_MIN, INT64_MIN};
+        for_each_subpath(c, nz_collect, &u);
+        if (u.n) analytic_draw(c, u.e, u.n, c->fillRule == OVK_FILL_EVEN_ODD ? OVK_RULE_EVEN_ODD : OVK_RULE_NON_ZERO, p.patType, &p.grad, p.solid, p.opacity);
+        free(u.e);
+        return;
+    }
     if (c->fillRule == OVK_FILL_EVEN_ODD) {
         eo_user u = {FLT_MAX, FLT_MAX, FLT_MIN, FLT_MIN, (int32_t *)malloc((size_t)c->pointCount * 8 + 8)};
         for_each_subpath(c, eo_fan, &u);
@@ -1191,6 +1305,12 @@ void ovk_paint(ovk_ctx *c) { /* vkvg_context.c:990-1003 */
     if (c->pathPtr) { ovk_fill(c); return; }
     paint_t p = cur_paint(c);
     cov_reset(c);
+    if (c->analytic) {
+        int32_t x1 = (int32_t)c->W * 256 + 4096, y1 = (int32_t)c->H * 256 + 4096;
+        int32_t e[16] = {-4096, -4096, x1, -4096, x1, -4096, x1, y1, x1, y1, -4096, y1, -4096, y1, -4096, -4096};
+        analytic_draw(c, e, 4, OVK_RULE_NON_ZERO, p.patType, &p.grad, p.solid, p.opacity);
+        return;
+    }
     cover_rect(c, full_rect(c), &p, 0x2);
 }
 

@@ -112,6 +112,12 @@ uint32_t ovk_flatten_cubic(float x0, float y0, float x1, float y1, float x2, flo
  * This is the definition the tile-binned CUDA rasteriser must reproduce bit-for-bit. */
 void ovk_winding_brute(const int32_t *edges_xyxy, uint64_t n_edges, uint32_t width, uint32_t height, uint32_t samples,
                        int32_t *out);
+/* analytic-coverage mode: A = integral of the winding number of the directed 24.8 edges over each pixel square,
+ * out[y*width+x], evaluated edge by edge in double precision over the whole surface (no tiles, no backdrop) */
+void ovk_area_brute(const int32_t *edges_xyxy, uint64_t n_edges, uint32_t width, uint32_t height, double *out);
+/* analytic != 0: every later draw uses exact area coverage (one colour per pixel; create the context with 1 sample) */
+void          ovk_set_coverage_mode(ovk_ctx *c, int analytic);
+const double *ovk_last_area(ovk_ctx *c); /* A of the last draw, height*width */
 /* the vertex-shader + viewport + snap chain: user space -> 24.8 window coordinates */
 void ovk_transform_snap(const float m[6], uint32_t width, uint32_t height, const float *xy, uint64_t n, int32_t *out_xy);
 /* sample positions (in 1/16 pixel) for a sample count; returns 0 if unsupported */

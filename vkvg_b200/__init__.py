@@ -103,6 +103,7 @@ _SIGS = {
     "vkvg_b200_flush_keep": (None, [_p]), "vkvg_b200_replay_resident": (None, [_p, _p, _i]),
     "vkvg_b200_replay": (_i, [_p, _p, C.c_uint64, _p, C.c_uint64]),
     "vkvg_b200_time_resident": (_i, [_p, _p, _u, _i, _i, C.POINTER(Stats)]),
+    "vkvg_b200_device_set_coverage_mode": (_i, [_p, _i]), "vkvg_b200_device_get_coverage_mode": (_i, [_p]),
     "vkvg_b200_surface_create_stripe": (_p, [_p, _u, _u, _u, _u]), "vkvg_b200_surface_copy_to_device": (_i, [_p, _p]),
 }
 
@@ -133,8 +134,12 @@ class VkvgError(RuntimeError):
     pass
 
 
+COVERAGE_MSAA, COVERAGE_ANALYTIC = 0, 1
+
+
 class Device:
-    def __init__(self, samples=4):
+    def __init__(self, samples=4, analytic=False):
+        """analytic=True selects the analytic-coverage mode (include/vkvg_b200.h §0) instead of MSAA."""
         L = lib()
         info = DeviceCreateInfo(samples=samples)
         self.h = L.vkvg_device_create(C.byref(info))
@@ -144,6 +149,9 @@ class Device:
             raise VkvgError("vkvg_device_create failed: %s (no CUDA device? this library has no CPU path)" %
                             L.vkvg_status_to_string(st).decode())
         self.samples = samples
+        self.analytic = bool(analytic)
+        if analytic and L.vkvg_b200_device_set_coverage_mode(self.h, COVERAGE_ANALYTIC):
+            raise VkvgError("vkvg_b200_device_set_coverage_mode failed")
 
     def close(self):
         if self.h:
@@ -178,11 +186,16 @@ class Device:
     def winding(self, edges, width, height):
         """per-sample integer winding of raw 24.8 edges through the tile rasteriser: (H, W, samples) int32."""
         e = np.ascontiguousarray(edges, np.int32).reshape(-1, 4)
-        out = np.zeros((height, width, self.samples), np.int32)
+        out = np.zeros((height, width) if self.analytic else (height, width, self.samples), np.int32)
         st = lib().vkvg_b200_winding(self.h, e.ctypes.data, len(e), width, height, out.ctypes.data)
         if st:
             raise VkvgError("vkvg_b200_winding: status %d" % st)
-        return out
+        return out.view(np.float32) if self.analytic else out
+
+    def area(self, edges, width, height):
+        """analytic mode: integral of the winding number over each pixel, (H, W) float32, through the tile rasteriser."""
+        assert self.analytic
+        return self.winding(edges, width, height)
 
 
 class Surface:
@@ -345,9 +358,9 @@ class Context:
 
     def flush_capture_winding(self):
         d = self.surf.dev
-        out = np.zeros((self.surf.height, self.surf.width, d.samples), np.int32)
+        out = np.zeros((self.surf.height, self.surf.width) if d.analytic else (self.surf.height, self.surf.width, d.samples), np.int32)
         lib().vkvg_b200_flush_capture_winding(self.h, out.ctypes.data)
-        return out
+        return out.view(np.float32) if d.analytic else out   # analytic mode: the area integral A of the last draw
 
     def replay(self, ops, args):
         ops = np.ascontiguousarray(ops, np.uint8)

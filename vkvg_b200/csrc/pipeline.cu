@@ -424,7 +424,7 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     fa.hdr = d->hdr.as<int4>(); fa.tile_edges = d->tile_edges.as<vkb_edge>();
     fa.paints = d->paints.as<vkb_paint>(); fa.grads = d->grads.as<vkb_gradient>();
     fa.image = surf->image.as<uint32_t>();
-    {
+    if (samples) {  // (analytic mode, samples == 0, keeps one colour per pixel: no per-sample plane)
         bool fresh = surf->tile_ms.p == nullptr;
         surf->ms_image.ensure((size_t)n_tiles * 256 * samples * 4, st);
         surf->tile_ms.ensure((size_t)n_tiles + 16, st);
@@ -436,7 +436,7 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     fa.winding_out = nullptr; fa.winding_draw = 0;
     DevBuf wbuf;
     if (cap && cap->winding) {
-        size_t wb = (size_t)sd.width * sd.height * samples * 4;
+        size_t wb = (size_t)sd.width * sd.height * (samples ? samples : 1) * 4;  // analytic mode: one float area per pixel
         wbuf.ensure(wb, st);
         VKB_CUDA_OK(cudaMemsetAsync(wbuf.p, 0, wb, st));
         fa.winding_out = wbuf.as<int32_t>(); fa.winding_draw = cap->winding_draw;
@@ -449,7 +449,7 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     surf->known_clear = false;
     VKB_CUDA_OK(cudaEventRecord(d->ev_end, st));
     if (cap && cap->winding) {
-        VKB_CUDA_OK(cudaMemcpyAsync(cap->winding, wbuf.p, (size_t)sd.width * sd.height * samples * 4, cudaMemcpyDeviceToHost, st));
+        VKB_CUDA_OK(cudaMemcpyAsync(cap->winding, wbuf.p, (size_t)sd.width * sd.height * (samples ? samples : 1) * 4, cudaMemcpyDeviceToHost, st));
         VKB_CUDA_OK(cudaStreamSynchronize(st));
         wbuf.release();
     }

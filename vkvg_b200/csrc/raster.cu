@@ -657,6 +657,54 @@ __device__ __forceinline__ void row_edge(int32_t ax, int32_t ay, int32_t bx, int
     }
 }
 
+// Warp 0 turns the next path-tiles of the tile (headers prefetched in nh0 / nh1, one per lane) into at most FINE_SLOTS
+// tasks, advances the cursor (s_p = path-tile, s_k = edges of it already consumed) and publishes the task count.
+__device__ __forceinline__ void fine_build_group(uint32_t lane, uint32_t end, uint32_t &s_p, uint32_t &s_k, uint32_t &s_nslots, FineTask *tasks,
+                                                 const int4 &nh0, const int4 &nh1) {
+    const uint32_t p0 = s_p, k0 = s_k;
+    __syncwarp();
+    const uint32_t p  = p0 + lane;
+    const bool     ok = lane < FINE_SLOTS && p < end;
+    const int4     h  = nh0, hp = nh1;
+    const int      kk = lane == 0 ? (int)k0 : 0;  // edges of path-tile p0 consumed by earlier groups
+    // chunk size of a path-tile: one task up to 16 edges; up to 128 edges chunks of <= 16; beyond that a whole
+    // number of groups of FINE_SLOTS equal chunks (<= FINE_CH) so that no warp idles while one finishes a long list
+    int chunk = FINE_CH;
+    if (h.w <= 128) { const int q = max(1, (h.w + 15) / 16); chunk = max(1, (h.w + q - 1) / q); }
+    else { const int q = FINE_SLOTS * ((h.w + FINE_SLOTS * FINE_CH - 1) / (FINE_SLOTS * FINE_CH)); chunk = (h.w + q - 1) / q; }
+    const int      nt = ok ? max(1, (h.w - kk + chunk - 1) / chunk) : 0;
+    int            incl = nt;
+#pragma unroll
+    for (int o = 1; o < FINE_SLOTS; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    const int start = incl - nt;
+    for (int t = 0; t < nt && start + t < FINE_SLOTS; t++) {
+        FineTask ft;
+        const int e0 = kk + t * chunk;
+        ft.eoff = (uint32_t)h.z + (uint32_t)e0;
+        ft.n    = min(chunk, h.w - e0);
+        ft.draw = h.x;
+        ft.bd   = e0 == 0 ? h.y : 0;
+        ft.last = e0 + ft.n >= h.w ? 1u : 0u;
+        ft.paint = vkb_paint{(uint32_t)hp.x, (uint32_t)hp.y, __int_as_float(hp.z), (uint32_t)hp.w};
+        tasks[start + t] = ft;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, FINE_SLOTS - 1);
+    // cursor after this group: the path-tile that owns slot FINE_SLOTS-1 (or the first one not started)
+    if (ok && start < FINE_SLOTS && start + nt >= FINE_SLOTS) {
+        const int done = FINE_SLOTS - start;             // tasks of this path-tile issued in this group
+        const int e1   = kk + done * chunk;
+        if (e1 >= h.w) { s_p = p + 1; s_k = 0; }
+        else { s_p = p; s_k = (uint32_t)e1; }
+    }
+    if (lane == 0) {
+        s_nslots = (uint32_t)min(total, FINE_SLOTS);
+        if (total < FINE_SLOTS) { s_p = end; s_k = 0; }
+    }
+}
+
 template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
     constexpr int ROWS   = 16 * S;
     constexpr int P      = ROWS >= 64 ? 2 : 1;                 // sample rows per lane per pass
@@ -705,50 +753,7 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
 
     for (;;) {
         // ---- build the next group of tasks (warp 0, one path-tile per lane) ----
-        if (warp == 0) {
-            const uint32_t p0 = s_p, k0 = s_k;
-            __syncwarp();
-            const uint32_t p  = p0 + lane;
-            const bool     ok = lane < FINE_SLOTS && p < end;
-            const int4     h  = nh0, hp = nh1;
-            const int      kk = lane == 0 ? (int)k0 : 0;  // edges of path-tile p0 consumed by earlier groups
-            // chunk size of a path-tile: one task up to 16 edges; up to 128 edges chunks of <= 16; beyond that a whole
-            // number of groups of FINE_SLOTS equal chunks (<= FINE_CH) so that no warp idles while one finishes a long list
-            int chunk = FINE_CH;
-            if (h.w <= 128) { const int q = max(1, (h.w + 15) / 16); chunk = max(1, (h.w + q - 1) / q); }
-            else { const int q = FINE_SLOTS * ((h.w + FINE_SLOTS * FINE_CH - 1) / (FINE_SLOTS * FINE_CH)); chunk = (h.w + q - 1) / q; }
-            const int      nt = ok ? max(1, (h.w - kk + chunk - 1) / chunk) : 0;
-            int            incl = nt;
-#pragma unroll
-            for (int o = 1; o < FINE_SLOTS; o <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)lane >= o) incl += v;
-            }
-            const int start = incl - nt;
-            for (int t = 0; t < nt && start + t < FINE_SLOTS; t++) {
-                FineTask ft;
-                const int e0 = kk + t * chunk;
-                ft.eoff = (uint32_t)h.z + (uint32_t)e0;
-                ft.n    = min(chunk, h.w - e0);
-                ft.draw = h.x;
-                ft.bd   = e0 == 0 ? h.y : 0;
-                ft.last = e0 + ft.n >= h.w ? 1u : 0u;
-                ft.paint = vkb_paint{(uint32_t)hp.x, (uint32_t)hp.y, __int_as_float(hp.z), (uint32_t)hp.w};
-                tasks[start + t] = ft;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, FINE_SLOTS - 1);
-            // cursor after this group: the path-tile that owns slot FINE_SLOTS-1 (or the first one not started)
-            if (ok && start < FINE_SLOTS && start + nt >= FINE_SLOTS) {
-                const int done = FINE_SLOTS - start;             // tasks of this path-tile issued in this group
-                const int e1   = kk + done * chunk;
-                if (e1 >= h.w) { s_p = p + 1; s_k = 0; }
-                else { s_p = p; s_k = (uint32_t)e1; }
-            }
-            if (lane == 0) {
-                s_nslots = (uint32_t)min(total, FINE_SLOTS);
-                if (total < FINE_SLOTS) { s_p = end; s_k = 0; }
-            }
-        }
+        if (warp == 0) fine_build_group(lane, end, s_p, s_k, s_nslots, tasks, nh0, nh1);
         __syncthreads();
         const uint32_t nslots = s_nslots;
         if (warp == 0) {  // prefetch the headers the next group starts from (cursor already advanced)
@@ -903,11 +908,151 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
         a.image[pix] = out;
     }
 }
+// ----------------------------------------------------------------------------------------------------
+// fine pass, analytic-coverage mode (sd.samples == 0): one colour per pixel, coverage = exact area.
+//   A(pixel) = integral of the winding number over the pixel square = B + integral of V + integral of H, with the same
+//   backdrop B (winding at C = (1/2, 1/2) fixed-point units inside the tile corner), the same L (x = 1/2 unit) and the same
+//   binned edge lists as the MSAA pass:
+//     V(y): crossings of L between C and y        -> per pixel row   (r + 1 - clamp(vc, r, r + 1)) - [vc < C.y]
+//     H(x,y): crossings of the row between L and x -> the part of the edge right of L, clipped to the pixel row, adds the
+//             area to the right of it inside each pixel it touches and its full height to every pixel further right;
+//             stored as differences along the row so that one prefix sum per row yields all 16 areas (signed-area
+//             accumulation as in font-rs / vello's fine stage).
+//   coverage = min(|A|, 1) (NON_ZERO, strokes) or 1 - |A mod 2 - 1| (EVEN_ODD); the paint scaled by the coverage is
+//   blended once.  Same definition as the oracle's area_brute / analytic_draw in oracle/vkvg_oracle.c (double precision,
+//   whole surface, no tiles); float rounding here bounds the difference at ~1e-5 of a pixel for edges near the tile.
+// A task is handled by one warp: lanes 0-15 take the even edges, lanes 16-31 the odd ones, one pixel row per lane.
+// Areas are accumulated in 2^-20 fixed point: integer sums do not depend on the order in which the binning kernel's
+// atomics happened to place the edges of a tile, so the output is deterministic.
+// ----------------------------------------------------------------------------------------------------
+#define FA_STRIDE 17
+#define FA_ONE 1048576.0f
+template <bool CAPTURE> __global__ void __launch_bounds__(256) fine_analytic_k(FineArgs a) {
+    const uint32_t tile  = blockIdx.x;
+    const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
+    if (first == end) return;
+
+    __shared__ float    lut[256];
+    __shared__ int32_t  acc[FINE_SLOTS][2][16][FA_STRIDE];
+    __shared__ FineTask tasks[FINE_SLOTS];
+    __shared__ uint32_t s_p, s_k, s_nslots;
+
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
+    int4 nh0 = make_int4(0, 0, 0, 0), nh1 = nh0;
+    if (warp == 0 && lane < FINE_SLOTS && first + lane < end) { nh0 = a.hdr[2 * (first + lane)]; nh1 = a.hdr[2 * (first + lane) + 1]; }
+    const uint32_t lx = (lane & 7) + 8 * (warp & 1), ly = (lane >> 3) + 4 * (warp >> 1);
+    const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
+    const bool     inside = px < a.sd.width && py < a.sd.height;
+    const size_t   pix    = (size_t)py * a.sd.width + px;
+    const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
+
+    uint32_t col  = (!a.dst_is_clear && inside) ? a.image[pix] : 0u;
+    int32_t  wacc = 0;
+    if (threadIdx.x == 0) { s_p = first; s_k = 0; }
+    __syncthreads();
+
+    for (;;) {
+        if (warp == 0) fine_build_group(lane, end, s_p, s_k, s_nslots, tasks, nh0, nh1);
+        __syncthreads();
+        const uint32_t nslots = s_nslots;
+        if (warp == 0) {
+            const uint32_t p = s_p + lane;
+            if (lane < FINE_SLOTS && p < end) { nh0 = a.hdr[2 * p]; nh1 = a.hdr[2 * p + 1]; }
+        }
+
+        // ---- phase A: warp w accumulates the row differences of task w ----
+        if (warp < nslots && tasks[warp].n > 0) {
+            const int       n    = tasks[warp].n;
+            const vkb_edge *ep   = a.tile_edges + tasks[warp].eoff;
+            const int       half = (int)(lane >> 4), r = (int)(lane & 15);
+            const float     rr   = (float)r;
+            int32_t        *D    = &acc[warp][half][r][0];
+#pragma unroll
+            for (int c = 0; c < 16; c++) D[c] = 0;
+            int32_t     base = 0;
+            const float DL   = 1.0f / 512.0f;  // L and C sit half a fixed-point unit inside the tile corner
+            for (int k = half; k < n; k += 2) {
+                const int4    ev  = __ldg((const int4 *)(ep + k));
+                const int32_t axi = ev.x - X0, bxi = ev.z - X0;
+                float ax = (float)axi * (1.0f / 256.0f), ay = (float)(ev.y - Y0) * (1.0f / 256.0f);
+                float bx = (float)bxi * (1.0f / 256.0f), by = (float)(ev.w - Y0) * (1.0f / 256.0f);
+                const bool la = axi <= 0, lb = bxi <= 0;
+                if (la != lb) {  // crosses L: V term, then keep the part right of L
+                    const float vc = ay + (DL - ax) * __fdividef(by - ay, bx - ax);
+                    const float sv = bx > ax ? -1.0f : 1.0f;
+                    base += __float2int_rn(sv * ((rr + 1.0f - fminf(fmaxf(vc, rr), rr + 1.0f)) - (vc < DL ? 1.0f : 0.0f)) * FA_ONE);
+                    if (la) { ax = DL; ay = vc; } else { bx = DL; by = vc; }
+                } else if (la) continue;
+                if (ay == by) continue;
+                const bool  down = by > ay;
+                const int   sgn = down ? 1 : -1;
+                const float xt = down ? ax : bx, yt = down ? ay : by, xb = down ? bx : ax, yb = down ? by : ay;
+                const float ys = fmaxf(yt, rr), ye = fminf(yb, rr + 1.0f);
+                if (ye <= ys) continue;
+                const float slope = __fdividef(xb - xt, yb - yt);
+                const float xs = xt + (ys - yt) * slope, xe = xt + (ye - yt) * slope, h = ye - ys;
+                const float xmin = fminf(xs, xe), xmax = fmaxf(xs, xe);
+                if (xmin >= 16.0f) continue;
+                const float rd = __fdividef(1.0f, fmaxf(xmax - xmin, 1e-20f));
+                const int   c0 = max(0, (int)floorf(xmin)), c1 = min(15, (int)floorf(xmax));
+                int         prev = 0;
+                for (int c = c0; c <= c1; c++) {
+                    const float hi = (float)(c + 1) - xmin, lo = (float)(c + 1) - xmax;
+                    const float t0 = __saturatef(-lo * rd), t1 = __saturatef((hi - 1.0f) * rd);
+                    const int   ar = __float2int_rn(h * (t1 + (1.0f - t0 - t1) * 0.5f * (fmaxf(lo, 0.0f) + fminf(hi, 1.0f))) * FA_ONE);
+                    D[c] += sgn * (ar - prev);
+                    prev = ar;
+                }
+                const int cn = c1 < c0 ? c0 : c1 + 1;
+                if (cn < 16) D[cn] += sgn * (__float2int_rn(h * FA_ONE) - prev);
+            }
+            int32_t run = base;
+#pragma unroll
+            for (int c = 0; c < 16; c++) { run += D[c]; D[c] = run; }
+        }
+        __syncthreads();
+
+        // ---- phase B: every thread owns one pixel; tasks in order ----
+        for (uint32_t g = 0; g < nslots; g++) {
+            const FineTask ft = tasks[g];
+            if (ft.n > 0) wacc += acc[g][0][ly][lx] + acc[g][1][ly][lx];
+            wacc += ft.bd * 1048576;
+            if (!ft.last) continue;
+            const float A = (float)wacc * (1.0f / FA_ONE);
+            wacc = 0;
+            if (CAPTURE) {
+                if ((uint32_t)ft.draw == a.winding_draw && inside) a.winding_out[pix] = __float_as_int(A);
+            }
+            const vkb_paint pt   = ft.paint;
+            const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
+            float           cov;
+            if (rule == VKB_RULE_EVEN_ODD) {
+                const float t = A - 2.0f * floorf(A * 0.5f);
+                cov = 1.0f - fabsf(t - 1.0f);
+            } else cov = fminf(fabsf(A), 1.0f);
+            if (!__any_sync(0xffffffffu, cov > 0.0f)) continue;
+            float src[4];
+            eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
+                       (float)(py + a.sd.origin_y) + 0.5f, src, lut);
+            if (cov > 0.0f) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) src[k] *= cov;
+                col = blend_over(col, src, 1.0f - src[3], lut);
+            }
+        }
+        if (s_p >= end) break;
+        __syncthreads();
+    }
+    if (inside) a.image[pix] = col;
+}
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s) {
     uint32_t tiles = a.sd.tiles_x * a.sd.tiles_y;
     if (!tiles) return;
     const bool cap = a.winding_out != nullptr;
     switch (a.sd.samples) {
+    case 0: if (cap) fine_analytic_k<true><<<tiles, 256, 0, s>>>(a); else fine_analytic_k<false><<<tiles, 256, 0, s>>>(a); break;
     case 1: if (cap) fine_k<1, true><<<tiles, 256, 0, s>>>(a); else fine_k<1, false><<<tiles, 256, 0, s>>>(a); break;
     case 2: if (cap) fine_k<2, true><<<tiles, 256, 0, s>>>(a); else fine_k<2, false><<<tiles, 256, 0, s>>>(a); break;
     case 4: if (cap) fine_k<4, true><<<tiles, 256, 0, s>>>(a); else fine_k<4, false><<<tiles, 256, 0, s>>>(a); break;

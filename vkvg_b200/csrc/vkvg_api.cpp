@@ -30,6 +30,8 @@ struct _vkvg_device_t {
     vkvg_status_t    status;
     uint32_t         references;
     uint32_t         samples;
+    bool             analytic;  // vkvg_b200_device_set_coverage_mode: exact-area coverage, one colour per pixel
+    uint32_t         raster_samples() const { return analytic ? 0u : samples; }  // what the pipeline is asked for
     int              hdpi, vdpi;
     bool             threadAware;
     vkb_device_impl *impl;
@@ -193,6 +195,10 @@ VkvgDevice vkvg_device_create(vkvg_device_create_info_t *info) {
     dev->status      = VKVG_STATUS_SUCCESS;
     dev->references  = 1;
     dev->samples     = samples;
+    {
+        const char *cm = getenv("VKVG_B200_COVERAGE");
+        dev->analytic  = cm && !strcmp(cm, "analytic");
+    }
     dev->hdpi = dev->vdpi = 96;
     dev->threadAware = info ? info->threadAware : false;
     dev->impl        = impl;
@@ -931,7 +937,7 @@ static void flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident) {
         if (!ctx->batch.draws.empty() || cap) {
             vkb_stats st;
             bool want_stats = dev->profiling;
-            if (vkb_render(dev->impl, ctx->pSurf->impl, dev->samples, ctx->batch, cap, want_stats ? &st : nullptr)) {
+            if (vkb_render(dev->impl, ctx->pSurf->impl, dev->raster_samples(), ctx->batch, cap, want_stats ? &st : nullptr)) {
                 ctx->status = VKVG_STATUS_DEVICE_ERROR;
                 dev->status = VKVG_STATUS_DEVICE_ERROR;
             }
@@ -1022,7 +1028,7 @@ static bool path_batch(VkvgContext ctx, uint32_t kind, vkb_batch &out) {
 static void run_geometry(VkvgContext ctx, const vkb_batch &b, vkb_capture &cap) {
     cap.geometry_only = true;
     std::lock_guard<std::mutex> lk(ctx->dev->mtx);
-    if (vkb_render(ctx->dev->impl, ctx->pSurf->impl, ctx->dev->samples, b, &cap, nullptr)) ctx->status = VKVG_STATUS_DEVICE_ERROR;
+    if (vkb_render(ctx->dev->impl, ctx->pSurf->impl, ctx->dev->raster_samples(), b, &cap, nullptr)) ctx->status = VKVG_STATUS_DEVICE_ERROR;
 }
 uint32_t vkvg_b200_flatten_path(VkvgContext ctx, float *xy, uint8_t *curved, uint32_t cap_points, uint32_t *sp_first, uint32_t *sp_count,
                                 uint32_t cap_subpaths, uint32_t *n_subpaths) {
@@ -1090,7 +1096,7 @@ void vkvg_b200_flush_capture_winding(VkvgContext ctx, int32_t *winding) {
     cap.winding = winding;
     cap.winding_draw = ctx->batch.draws.empty() ? 0 : (uint32_t)ctx->batch.draws.size() - 1;
     if (ctx->batch.draws.empty()) {
-        memset(winding, 0, (size_t)ctx->pSurf->width * ctx->pSurf->height * ctx->dev->samples * 4);
+        memset(winding, 0, (size_t)ctx->pSurf->width * ctx->pSurf->height * (ctx->dev->analytic ? 1 : ctx->dev->samples) * 4);
         flush_impl(ctx, nullptr, false);
         return;
     }
@@ -1100,7 +1106,17 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges, 
 vkvg_status_t vkvg_b200_winding(VkvgDevice dev, const int32_t *edges_xyxy, uint64_t n_edges, uint32_t width, uint32_t height, int32_t *winding) {
     if (vkvg_device_status(dev)) return VKVG_STATUS_DEVICE_ERROR;
     std::lock_guard<std::mutex> lk(dev->mtx);
-    return vkb_winding_raw(dev->impl, dev->samples, edges_xyxy, n_edges, width, height, winding) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
+    return vkb_winding_raw(dev->impl, dev->raster_samples(), edges_xyxy, n_edges, width, height, winding) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
+}
+vkvg_status_t vkvg_b200_device_set_coverage_mode(VkvgDevice dev, int mode) {
+    if (vkvg_device_status(dev)) return VKVG_STATUS_DEVICE_ERROR;
+    if (mode != VKVG_B200_COVERAGE_MSAA && mode != VKVG_B200_COVERAGE_ANALYTIC) return VKVG_STATUS_INVALID_STATUS;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    dev->analytic = mode == VKVG_B200_COVERAGE_ANALYTIC;
+    return VKVG_STATUS_SUCCESS;
+}
+int vkvg_b200_device_get_coverage_mode(VkvgDevice dev) {
+    return (!vkvg_device_status(dev) && dev->analytic) ? VKVG_B200_COVERAGE_ANALYTIC : VKVG_B200_COVERAGE_MSAA;
 }
 void vkvg_b200_flush_keep(VkvgContext ctx) { vkvg_flush(ctx); }  // the uploaded batch stays on the device until the next upload
 void vkvg_b200_replay_resident(VkvgDevice dev, VkvgSurface surf, int clear_first) {
@@ -1108,14 +1124,14 @@ void vkvg_b200_replay_resident(VkvgDevice dev, VkvgSurface surf, int clear_first
     std::lock_guard<std::mutex> lk(dev->mtx);
     if (clear_first) vkb_surface_clear(surf->impl);
     vkb_stats st;
-    if (vkb_render_resident(dev->impl, surf->impl, dev->samples, nullptr, dev->profiling ? &st : nullptr)) dev->status = VKVG_STATUS_DEVICE_ERROR;
+    if (vkb_render_resident(dev->impl, surf->impl, dev->raster_samples(), nullptr, dev->profiling ? &st : nullptr)) dev->status = VKVG_STATUS_DEVICE_ERROR;
     if (dev->profiling) dev->last = st;
 }
 vkvg_status_t vkvg_b200_time_resident(VkvgDevice dev, VkvgSurface surf, uint32_t steps, int clear_first, int flush_l2, vkvg_b200_stats_t *sum) {
     if (vkvg_device_status(dev) || vkvg_surface_status(surf)) return VKVG_STATUS_DEVICE_ERROR;
     std::lock_guard<std::mutex> lk(dev->mtx);
     vkb_stats st;
-    if (vkb_time_resident(dev->impl, surf->impl, dev->samples, steps, clear_first != 0, flush_l2 != 0, &st)) {
+    if (vkb_time_resident(dev->impl, surf->impl, dev->raster_samples(), steps, clear_first != 0, flush_l2 != 0, &st)) {
         dev->status = VKVG_STATUS_DEVICE_ERROR;
         return VKVG_STATUS_DEVICE_ERROR;
     }
