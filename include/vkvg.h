@@ -175,6 +175,13 @@ vkvg_public void vkvg_rel_quadratic_to(VkvgContext ctx, float x1, float y1, floa
 vkvg_public vkvg_status_t vkvg_rectangle(VkvgContext ctx, float x, float y, float w, float h);
 vkvg_public vkvg_status_t vkvg_rounded_rectangle(VkvgContext ctx, float x, float y, float w, float h, float radius);
 vkvg_public void vkvg_ellipse(VkvgContext ctx, float radiusX, float radiusY, float x, float y, float rotationAngle);
+/* reference include/vkvg.h:1184: rectangle whose corners are quarter ellipses of radii rx, ry */
+vkvg_public void vkvg_rounded_rectangle2(VkvgContext ctx, float x, float y, float w, float h, float rx, float ry);
+/* reference include/vkvg.h:1219, :1235: SVG-style elliptical arc from the current point (phi in radians) */
+vkvg_public void vkvg_elliptic_arc_to(VkvgContext ctx, float x, float y, bool large_arc_flag, bool sweep_flag, float rx, float ry, float phi);
+vkvg_public void vkvg_rel_elliptic_arc_to(VkvgContext ctx, float x, float y, bool large_arc_flag, bool sweep_flag, float rx, float ry, float phi);
+/* reference include/vkvg.h:989: user-space bounding box of the flattened current path (0,0,0,0 without a path) */
+vkvg_public void vkvg_path_extents(VkvgContext ctx, float *const x1, float *const y1, float *const x2, float *const y2);
 
 /* ---- drawing: reference include/vkvg.h:1246-1291 ---- */
 vkvg_public void vkvg_stroke(VkvgContext ctx);

@@ -138,6 +138,14 @@ enum {
  * corresponding vkvg_* calls one by one (it does exactly that).  Returns the context status. */
 vkvg_public vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *args, uint64_t n_args);
 
+/* ---- SVG parser introspection (parity tests against nanoSVG dumps, tests/test_svg.py) ----
+ * Flat dump of a document parsed by vkvg_svg_load (include/vkvg-svg.h), byte-compatible with what oracle/nsvg_dump.c
+ * writes for the reference's nanoSVG: "NSVG" f32 width f32 height u32 nshapes, then per shape u32 fillType fillColor
+ * strokeType strokeColor, f32 opacity strokeWidth, u32 npaths, then per path u32 npts u32 closed f32 xy[2*npts].
+ * Returns the dump size in bytes and writes at most cap of them to out (out may be NULL). */
+struct _vkvg_svg_t;
+vkvg_public uint64_t vkvg_b200_svg_serialize(struct _vkvg_svg_t *svg, uint8_t *out, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

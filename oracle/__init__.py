@@ -40,6 +40,9 @@ _PATH_API = {
     "set_fill_rule": [_i], "set_opacity": [_f], "set_source_rgba": [_f] * 4, "set_source_color": [_u],
     "translate": [_f] * 2, "scale": [_f] * 2, "rotate": [_f], "identity_matrix": [],
     "fill": [], "fill_preserve": [], "stroke": [], "stroke_preserve": [], "paint": [],
+    "ellipse": [_f] * 5, "rounded_rectangle": [_f] * 5, "rounded_rectangle2": [_f] * 6, "rel_quadratic_to": [_f] * 4,
+    "elliptic_arc_to": [_f, _f, C.c_bool, C.c_bool, _f, _f, _f], "rel_elliptic_arc_to": [_f, _f, C.c_bool, C.c_bool, _f, _f, _f],
+    "clip": [], "clip_preserve": [], "reset_clip": [], "save": [], "restore": [],
 }
 
 

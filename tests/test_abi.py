@@ -27,23 +27,23 @@ def _declared(header):
     return sorted(set(re.findall(r"vkvg_public[^;(]*?\b(vkvg_\w+)\s*\(", src)))
 
 
-@pytest.mark.parametrize("header", ["vkvg.h", "vkvg_b200.h"])
+@pytest.mark.parametrize("header", ["vkvg.h", "vkvg-svg.h", "vkvg_b200.h"])
 def test_every_declared_symbol_is_exported(L, header):
     names = _declared(header)
-    assert len(names) > (100 if header == "vkvg.h" else 10)
+    assert len(names) > {"vkvg.h": 100, "vkvg_b200.h": 10, "vkvg-svg.h": 6}[header]
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
 
 
 def test_python_binding_table_matches_header(L):
-    declared = set(_declared("vkvg.h")) | set(_declared("vkvg_b200.h"))
+    declared = set(_declared("vkvg.h")) | set(_declared("vkvg_b200.h")) | set(_declared("vkvg-svg.h"))
     assert set(v.exported_symbols()) <= declared
 
 
 def test_headers_compile_as_c(tmp_path):
     import subprocess
     src = tmp_path / "t.c"
-    src.write_text('#include "vkvg.h"\n#include "vkvg_b200.h"\nint main(void){vkvg_matrix_t m; vkvg_matrix_init_identity(&m); return (int)m.x0;}\n')
+    src.write_text('#include "vkvg.h"\n#include "vkvg-svg.h"\n#include "vkvg_b200.h"\nint main(void){vkvg_matrix_t m; vkvg_matrix_init_identity(&m); return (int)m.x0;}\n')
     r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

@@ -376,3 +376,37 @@ def test_invalid_dash_and_gradient_status(dev4):
     c2 = v.Context(s)
     c2.set_source_linear(0, 0, 10, 10, [(0, 1, 0, 0, 1)])  # one stop: count < 2 (internal.c:792-795)
     assert c2.status() == 10  # VKVG_STATUS_PATTERN_INVALID_GRADIENT
+
+
+# ---- elliptical arcs, rounded_rectangle2, ellipse, path_extents (reference object code goldens: make_golden2.py) ----
+from tests.golden import make_golden2 as mg2  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ell():
+    return np.load(os.path.join(GOLD, "elliptic.npz"))
+
+
+@pytest.mark.parametrize("seed", mg2.ELLIPTIC_SEEDS)
+def test_elliptic_arcs_and_path_extents_vs_reference_golden(dev4, ell, seed):
+    s = v.Surface(dev4, 256, 256)
+    c = v.Context(s)
+    mg2.elliptic_scene(c, seed)
+    ext = np.array(c.path_extents(), np.float32)
+    pts = c.path_points()
+    ref = ell["pts_%d" % seed]
+    assert pts.shape == ref.shape, (pts.shape, ref.shape)
+    assert np.abs(pts - ref).max() <= VERT_TOL
+    assert np.abs(ext - ell["ext_%d" % seed]).max() <= VERT_TOL
+    c.close()
+    s.close()
+
+
+def test_path_extents_without_a_path(dev4, ell):
+    s = v.Surface(dev4, 64, 64)
+    c = v.Context(s)
+    assert np.array_equal(np.array(c.path_extents(), np.float32), ell["ext_empty"])
+    c.move_to(5, 5)   # a lone point is not a path (src/vkvg_context_internal.c:166-172)
+    assert c.path_extents() == (0.0, 0.0, 0.0, 0.0)
+    c.close()
+    s.close()

@@ -65,6 +65,10 @@ _SIGS = {
     "vkvg_curve_to": (None, [_p] + [_f] * 6), "vkvg_rel_curve_to": (None, [_p] + [_f] * 6),
     "vkvg_quadratic_to": (None, [_p] + [_f] * 4), "vkvg_rel_quadratic_to": (None, [_p] + [_f] * 4),
     "vkvg_rectangle": (_i, [_p] + [_f] * 4), "vkvg_rounded_rectangle": (_i, [_p] + [_f] * 5), "vkvg_ellipse": (None, [_p] + [_f] * 5),
+    "vkvg_rounded_rectangle2": (None, [_p] + [_f] * 6),
+    "vkvg_elliptic_arc_to": (None, [_p, _f, _f, C.c_bool, C.c_bool, _f, _f, _f]),
+    "vkvg_rel_elliptic_arc_to": (None, [_p, _f, _f, C.c_bool, C.c_bool, _f, _f, _f]),
+    "vkvg_path_extents": (None, [_p] + [C.POINTER(_f)] * 4),
     "vkvg_stroke": (None, [_p]), "vkvg_stroke_preserve": (None, [_p]), "vkvg_fill": (None, [_p]), "vkvg_fill_preserve": (None, [_p]),
     "vkvg_paint": (None, [_p]), "vkvg_clear": (None, [_p]),
     "vkvg_set_opacity": (None, [_p, _f]), "vkvg_get_opacity": (_f, [_p]), "vkvg_set_source_color": (None, [_p, _u]),
@@ -90,6 +94,11 @@ _SIGS = {
     "vkvg_pattern_add_color_stop": (_i, [_p] + [_f] * 5), "vkvg_pattern_get_color_stop_count": (_i, [_p, C.POINTER(_u)]),
     "vkvg_pattern_get_type": (_i, [_p]), "vkvg_pattern_set_matrix": (None, [_p, _p]), "vkvg_pattern_get_matrix": (None, [_p, _p]),
     "vkvg_pattern_set_extend": (None, [_p, _i]), "vkvg_pattern_get_extend": (_i, [_p]),
+    # vkvg-svg.h
+    "vkvg_svg_load": (_p, [C.c_char_p]), "vkvg_svg_load_fragment": (_p, [C.c_char_p]), "vkvg_svg_destroy": (None, [_p]),
+    "vkvg_svg_get_dimensions": (None, [_p, C.POINTER(_u), C.POINTER(_u)]), "vkvg_svg_render": (None, [_p, _p, C.c_char_p]),
+    "vkvg_surface_create_from_svg": (_p, [_p, _u, _u, C.c_char_p]), "vkvg_surface_create_from_svg_fragment": (_p, [_p, _u, _u, C.c_char_p]),
+    "vkvg_b200_svg_serialize": (C.c_uint64, [_p, _p, C.c_uint64]),
     # vkvg_b200.h
     "vkvg_b200_flatten_path": (_u, [_p, _p, _p, _u, _p, _p, _u, C.POINTER(_u)]),
     "vkvg_b200_stroke_geometry": (None, [_p, _p, _u, C.POINTER(_u), _p, _u, C.POINTER(_u)]),
@@ -254,7 +263,7 @@ class Surface:
 
 
 _CTX_CALLS = ["new_path", "close_path", "new_sub_path", "line_to", "rel_line_to", "move_to", "rel_move_to", "arc", "arc_negative",
-              "curve_to", "rel_curve_to", "quadratic_to", "rel_quadratic_to", "rectangle", "rounded_rectangle", "ellipse", "stroke",
+              "curve_to", "rel_curve_to", "quadratic_to", "rel_quadratic_to", "rectangle", "rounded_rectangle", "rounded_rectangle2", "elliptic_arc_to", "rel_elliptic_arc_to", "ellipse", "stroke",
               "stroke_preserve", "fill", "fill_preserve", "paint", "clear", "set_opacity", "set_source_color", "set_source_rgba",
               "set_source_rgb", "set_line_width", "set_miter_limit", "set_line_cap", "set_line_join", "set_operator", "set_fill_rule",
               "save", "restore", "translate", "scale", "rotate", "identity_matrix", "flush"]
@@ -322,6 +331,14 @@ class Context:
     def set_source_radial(self, cx0, cy0, r0, cx1, cy1, r1, stops):
         self._grad(lib().vkvg_pattern_create_radial(cx0, cy0, r0, cx1, cy1, r1), stops)
 
+    def path_extents(self):
+        x1, y1, x2, y2 = _f(), _f(), _f(), _f()
+        lib().vkvg_path_extents(self.h, C.byref(x1), C.byref(y1), C.byref(x2), C.byref(y2))
+        return x1.value, y1.value, x2.value, y2.value
+
+    def render_svg(self, svg, sub_id=None):
+        lib().vkvg_svg_render(svg.h, self.h, sub_id.encode() if sub_id else None)
+
     # ---- stage introspection (vkvg_b200.h) ----
     def path_points(self):
         """flattened points of the current path, computed by the CUDA flatten kernels: (n,2) float32."""
@@ -366,6 +383,40 @@ class Context:
         ops = np.ascontiguousarray(ops, np.uint8)
         args = np.ascontiguousarray(args, np.float32)
         return lib().vkvg_b200_replay(self.h, ops.ctypes.data, len(ops), args.ctypes.data, len(args))
+
+
+class Svg:
+    """vkvg-svg.h: a parsed SVG document (host only: no device is needed to load or inspect one)."""
+
+    def __init__(self, path=None, fragment=None):
+        L = lib()
+        self.h = L.vkvg_svg_load(os.fsencode(path)) if path is not None else L.vkvg_svg_load_fragment(fragment.encode() if isinstance(fragment, str) else fragment)
+        if not self.h:
+            raise VkvgError("vkvg_svg_load failed: %r" % (path,))
+
+    def close(self):
+        if self.h:
+            lib().vkvg_svg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dimensions(self):
+        w, h = _u(), _u()
+        lib().vkvg_svg_get_dimensions(self.h, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def serialize(self):
+        """flat shape dump in the layout of oracle/nsvg_dump.c (bytes)."""
+        L = lib()
+        n = L.vkvg_b200_svg_serialize(self.h, None, 0)
+        buf = np.zeros(n, np.uint8)
+        L.vkvg_b200_svg_serialize(self.h, buf.ctypes.data, n)
+        return buf.tobytes()
 
 
 class CommandStream:

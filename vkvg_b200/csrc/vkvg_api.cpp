@@ -681,6 +681,99 @@ void vkvg_ellipse(VkvgContext ctx, float radiusX, float radiusY, float x, float 
     curve_to_(ctx, tcx - dx2, tcy - dy2, bcx - dx2, bcy - dy2, bcx, bcy);
     finish_path(ctx, VKB_SP_CLOSED);
 }
+// SVG-style elliptical arc, flattened on the host at a tenth of the circular arc step like the reference
+// (_elliptic_arc, src/vkvg_context_internal.c:1473-1580; float / double mix kept as it is there)
+static void elliptic_arc(VkvgContext ctx, float x1, float y1, float x2, float y2, bool largeArc, bool counterClockWise, float _rx, float _ry, float phi) {
+    if (_rx == 0 || _ry == 0) {
+        if (path_empty(ctx)) vkvg_move_to(ctx, x1, y1);
+        vkvg_line_to(ctx, x2, y2);
+        return;
+    }
+    float rx = fabsf(_rx), ry = fabsf(_ry);
+    const float cphi = cosf(phi), sphi = sinf(phi);
+    // midpoint vector rotated into the ellipse frame
+    float hx = (x1 - x2) / 2, hy = (y1 - y2) / 2;
+    float p1x = (cphi * hx) + (sphi * hy), p1y = (-sphi * hx) + (cphi * hy);
+    double lambda = powf(p1x, 2) / powf(rx, 2) + powf(p1y, 2) / powf(ry, 2);
+    if (lambda > 1) {  // radii too small for the chord: scale them up
+        lambda = sqrtf(lambda);
+        rx *= lambda;
+        ry *= lambda;
+    }
+    float qx = rx * p1y / ry, qy = -ry * p1x / rx;
+    float k  = sqrtf(fabsf((powf(rx, 2) * powf(ry, 2) - powf(rx, 2) * powf(p1y, 2) - powf(ry, 2) * powf(p1x, 2)) /
+                           (powf(rx, 2) * powf(p1y, 2) + powf(ry, 2) * powf(p1x, 2))));
+    float cpx = qx * k, cpy = qy * k;
+    if (largeArc == counterClockWise) { cpx = -cpx; cpy = -cpy; }
+    // centre back in user space
+    float mx = (x1 + x2) / 2, my = (y1 + y2) / 2;
+    float cx = ((cphi * cpx) + (-sphi * cpy)) + mx, cy = ((sphi * cpx) + (cphi * cpy)) + my;
+    auto angle = [](float ux, float uy, float vx, float vy) {
+        double a = acosf(((ux * vx) + (uy * vy)) / (fabsf(sqrtf(vx * vx + vy * vy)) * fabsf(sqrtf(ux * ux + uy * uy))));
+        if (isnan(a)) a = M_PIF;
+        if (ux * vy - uy * vx < 0) a = -a;
+        return a;
+    };
+    float  ux = 1.f, uy = 0, vx = (p1x - cpx) / rx, vy = (p1y - cpy) / ry;
+    double sa = angle(ux, uy, vx, vy);
+    ux = vx; uy = vy;
+    vx = (-p1x - cpx) / rx; vy = (-p1y - cpy) / ry;
+    double delta_theta = angle(ux, uy, vx, vy);
+    if (counterClockWise) {
+        if (delta_theta < 0) delta_theta += M_PIF * 2.0;
+    } else if (delta_theta > 0)
+        delta_theta -= M_PIF * 2.0;
+    double theta = sa, ea = sa + delta_theta;
+    float  step  = fmaxf(0.001f, fminf(M_PIF, get_arc_step(ctx, fminf(rx, ry)) * 0.1f));
+    auto point_at = [&](double t, float &x, float &y) {
+        float ex = rx * cosf(t), ey = ry * sinf(t);
+        x = ((cphi * ex) + (-sphi * ey)) + cx;
+        y = ((sphi * ex) + (cphi * ey)) + cy;
+    };
+    float x, y;
+    point_at(theta, x, y);
+    if (path_empty(ctx)) {
+        add_point(ctx, x, y, true);
+        ctx->simpleConvex = ctx->path_first_sp == ctx->batch.subpaths.size();
+    } else {
+        line_to_(ctx, x, y);
+        ctx->simpleConvex = false;
+    }
+    if (sa < ea) {
+        theta += step;
+        while (theta < ea) { point_at(theta, x, y); add_point(ctx, x, y, true); theta += step; }
+    } else {
+        theta -= step;
+        while (theta > ea) { point_at(theta, x, y); add_point(ctx, x, y, true); theta -= step; }
+    }
+    point_at(ea, x, y);
+    add_point(ctx, x, y, true);
+}
+void vkvg_elliptic_arc_to(VkvgContext ctx, float x2, float y2, bool largeArc, bool sweepFlag, float rx, float ry, float phi) {  // :1579-1590
+    if (vkvg_status(ctx)) return;
+    float x1 = 0, y1 = 0;
+    vkvg_get_current_point(ctx, &x1, &y1);
+    elliptic_arc(ctx, x1, y1, x2, y2, largeArc, sweepFlag, rx, ry, phi);
+}
+void vkvg_rel_elliptic_arc_to(VkvgContext ctx, float x2, float y2, bool largeArc, bool sweepFlag, float rx, float ry, float phi) {  // :1591-1603
+    if (vkvg_status(ctx)) return;
+    float x1 = 0, y1 = 0;
+    vkvg_get_current_point(ctx, &x1, &y1);
+    elliptic_arc(ctx, x1, y1, x2 + x1, y2 + y1, largeArc, sweepFlag, rx, ry, phi);
+}
+void vkvg_rounded_rectangle2(VkvgContext ctx, float x, float y, float w, float h, float rx, float ry) {  // :665-683
+    if (vkvg_status(ctx)) return;
+    vkvg_move_to(ctx, x + rx, y);
+    vkvg_line_to(ctx, x + w - rx, y);
+    vkvg_elliptic_arc_to(ctx, x + w, y + ry, false, true, rx, ry, 0);
+    vkvg_line_to(ctx, x + w, y + h - ry);
+    vkvg_elliptic_arc_to(ctx, x + w - rx, y + h, false, true, rx, ry, 0);
+    vkvg_line_to(ctx, x + rx, y + h);
+    vkvg_elliptic_arc_to(ctx, x, y + h - ry, false, true, rx, ry, 0);
+    vkvg_line_to(ctx, x, y + ry);
+    vkvg_elliptic_arc_to(ctx, x + rx, y, false, true, rx, ry, 0);
+    vkvg_close_path(ctx);
+}
 
 // ---- state ----
 void  vkvg_set_opacity(VkvgContext ctx, float opacity) { if (!vkvg_status(ctx)) ctx->opacity = opacity; }
@@ -1056,6 +1149,29 @@ uint32_t vkvg_b200_flatten_path(VkvgContext ctx, float *xy, uint8_t *curved, uin
     (void)p0; (void)p1;
     if (n_subpaths) *n_subpaths = ns;
     return n;
+}
+// bounding box of the flattened current path in user space (vkvg_path_extents :684-696, _vkvg_path_extents
+// internal.c:1879-1917: the maxima start from FLT_MIN as they do there).  Curves are flattened on the device, so this
+// runs the geometry stages once.
+void vkvg_path_extents(VkvgContext ctx, float *const x1, float *const y1, float *const x2, float *const y2) {
+    if (vkvg_status(ctx)) return;
+    vkb_batch b;
+    if (!path_batch(ctx, VKB_DRAW_FILL, b)) { *x1 = *x2 = *y1 = *y2 = 0; return; }
+    std::vector<float> pts; std::vector<uint32_t> f, c;
+    vkb_capture cap;
+    cap.points = &pts; cap.sp_first = &f; cap.sp_count = &c;
+    run_geometry(ctx, b, cap);
+    float xMin = FLT_MAX, yMin = FLT_MAX, xMax = FLT_MIN, yMax = FLT_MIN;
+    const uint32_t s0 = b.draws[0].first_subpath, ns = b.draws[0].n_subpaths;
+    for (uint32_t s = 0; s < ns; s++)
+        for (uint32_t k = 0; k < c[s0 + s]; k++) {
+            const float px = pts[2 * (f[s0 + s] + k)], py = pts[2 * (f[s0 + s] + k) + 1];
+            if (px < xMin) xMin = px;
+            if (px > xMax) xMax = px;
+            if (py < yMin) yMin = py;
+            if (py > yMax) yMax = py;
+        }
+    *x1 = xMin; *x2 = xMax; *y1 = yMin; *y2 = yMax;
 }
 void vkvg_b200_stroke_geometry(VkvgContext ctx, float *xy, uint32_t cap_verts, uint32_t *n_verts, uint32_t *indices, uint32_t cap_indices,
                                uint32_t *n_indices) {
