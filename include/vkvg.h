@@ -190,6 +190,11 @@ vkvg_public void vkvg_fill(VkvgContext ctx);
 vkvg_public void vkvg_fill_preserve(VkvgContext ctx);
 vkvg_public void vkvg_paint(VkvgContext ctx);
 vkvg_public void vkvg_clear(VkvgContext ctx);
+/* clipping: reference include/vkvg.h:1299-1325.  The clip region is the intersection of every path clipped so far (with
+ * the fill rule current at each call); it is part of the state vkvg_save / vkvg_restore stack. */
+vkvg_public void vkvg_reset_clip(VkvgContext ctx);
+vkvg_public void vkvg_clip(VkvgContext ctx);
+vkvg_public void vkvg_clip_preserve(VkvgContext ctx);
 
 /* ---- sources and stroke/fill state: reference include/vkvg.h:1334-1555 ---- */
 vkvg_public void  vkvg_set_opacity(VkvgContext ctx, float opacity);

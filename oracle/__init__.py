@@ -124,7 +124,8 @@ class Oracle(_Base):
             pass
 
     def clear(self):
-        self._lib.ovk_clear(self._ctx)
+        self._lib.ovk_clear_ctx.argtypes = [_p]
+        self._lib.ovk_clear_ctx(self._ctx)   # vkvg_clear: surface + stencil wiped, clip-state bookkeeping updated
 
     def status(self):
         return self._lib.ovk_status(self._ctx)

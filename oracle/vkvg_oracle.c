@@ -73,6 +73,17 @@ typedef struct {
     uint32_t count;
 } grad_t; /* src/vkvg_pattern.h:38-47 (scalar block layout) */
 
+struct ovk_save { /* vkvg_context_save_t, src/vkvg_context_internal.h:101-125 */
+    struct ovk_save *next;
+    float    lineWidth, miterLimit, dashOffset, *dashes, opacity;
+    uint32_t dashCount;
+    int      lineCap, fillRule, clippingState;
+    uint32_t curColor;
+    int      patType;
+    grad_t   grad;
+    mat_t    mat;
+};
+
 struct ovk_ctx {
     uint32_t W, H, S;
     int      status;
@@ -104,6 +115,12 @@ struct ovk_ctx {
     uint32_t  vertCount, sizeVerts;
     uint32_t *inds;
     uint32_t  indCount, sizeInds;
+    /* clip bookkeeping of the reference context (src/vkvg_context_internal.h:93-99, :123, :225-226) */
+    int              curClipState; /* 0 none, 1 clear, 2 clip (6 = clip_saved, only in saved entries) */
+    uint32_t         curSavBit;
+    struct ovk_save *saved;
+    uint8_t        **spills; /* whole-stencil copies taken every 6 nested clip saves (vkvg_context.c:1268-1318) */
+    uint32_t         nspills;
 };
 
 /* ------------------------------------------------------------------ */
@@ -397,6 +414,7 @@ static void analytic_draw(ovk_ctx *c, const int32_t *e, uint64_t n, int rule, in
         for (uint32_t px = 0; px < c->W; px++) {
             float cov = analytic_coverage(c->area[(size_t)py * c->W + px], rule);
             if (!(cov > 0.0f)) continue;
+            if (c->stencil[((size_t)py * c->W + px) * c->S] & 0x2) continue; /* clipped out (analytic mode: one flag per pixel) */
             float col[4], s[4];
             eval_paint(patType, grad, (float)c->W, (float)c->H, solid, opacity, (float)px + 0.5f, (float)py + 0.5f, col);
             for (int k = 0; k < 4; k++) s[k] = col[k] * cov;
@@ -504,6 +522,9 @@ void ovk_destroy(ovk_ctx *c) {
     if (!c) return;
     free(c->samples); free(c->stencil); free(c->resolved); free(c->coverage); free(c->area);
     free(c->points); free(c->pathes); free(c->verts); free(c->inds); free(c->dashes);
+    while (c->saved) { struct ovk_save *n = c->saved->next; free(c->saved->dashes); free(c->saved); c->saved = n; }
+    for (uint32_t i = 0; i < c->nspills; i++) free(c->spills[i]);
+    free(c->spills);
     free(c);
 }
 int  ovk_status(ovk_ctx *c) { return c->status; }
@@ -1314,6 +1335,144 @@ void ovk_paint(ovk_ctx *c) { /* vkvg_context.c:990-1003 */
     cover_rect(c, full_rect(c), &p, 0x2);
 }
 
+
+/* ------------------------------------------------------------------ */
+/* clipping and save / restore                                         */
+/* ------------------------------------------------------------------ */
+/* pipelineClipping: stencil test EQUAL on (ref & cmp) vs (stencil & cmp); pass -> REPLACE, fail -> ZERO, both under
+ * the write mask; colour writes off (clipingOpState, src/vkvg_device_internal.c:233-239, dynamic ref / masks) */
+static inline uint8_t clip_stencil_op(uint8_t st, uint32_t ref, uint32_t cmp, uint32_t write) {
+    bool pass = (ref & cmp) == (st & cmp);
+    return (uint8_t)(pass ? ((st & ~write) | (ref & write)) : (st & ~write));
+}
+typedef struct { uint32_t ref, cmp, write; } clip_user;
+static void px_clip(ovk_ctx *c, uint32_t px, uint32_t py, uint32_t mask, void *user) {
+    clip_user *u   = (clip_user *)user;
+    size_t     base = ((size_t)py * c->W + px) * c->S;
+    for (uint32_t s = 0; s < c->S; s++)
+        if (mask & (1u << s)) c->stencil[base + s] = clip_stencil_op(c->stencil[base + s], u->ref, u->cmp, u->write);
+}
+static void stencil_quad(ovk_ctx *c, rect_i sc, uint32_t ref, uint32_t cmp, uint32_t write) { /* _draw_full_screen_quad under pipelineClipping */
+    clip_user u = {ref, cmp, write};
+    for (int32_t py = sc.y0; py < sc.y1; py++)
+        for (int32_t px = sc.x0; px < sc.x1; px++) px_clip(c, (uint32_t)px, (uint32_t)py, (1u << c->S) - 1, &u);
+}
+static void clip_preserve_(ovk_ctx *c) { /* _clip_preserve, src/vkvg_context.c:754-795 */
+    finish_path(c);
+    if (!c->pathPtr) return;
+    if (c->analytic) { /* one flag per pixel: inside where the coverage of the clip path exceeds one half */
+        nz_user u = {(int32_t *)malloc((size_t)c->pointCount * 16 + 16), 0, INT64_MAX, INT64_MAX, INT64_MIN, INT64_MIN};
+        for_each_subpath(c, nz_collect, &u);
+        if (!c->area) c->area = (double *)calloc((size_t)c->W * c->H, sizeof(double));
+        ovk_area_brute(u.e, u.n, c->W, c->H, c->area);
+        for (size_t i = 0; i < (size_t)c->W * c->H; i++) {
+            float cov = analytic_coverage(c->area[i], c->fillRule == OVK_FILL_EVEN_ODD ? OVK_RULE_EVEN_ODD : OVK_RULE_NON_ZERO);
+            if (!(cov > 0.5f))
+                for (uint32_t s = 0; s < c->S; s++) c->stencil[i * c->S + s] |= 0x2;
+        }
+        free(u.e);
+        c->curClipState = 2;
+        return;
+    }
+    if (c->fillRule == OVK_FILL_EVEN_ODD) { /* fan inverts FILL where not yet clipped */
+        eo_user u = {FLT_MAX, FLT_MAX, FLT_MIN, FLT_MIN, (int32_t *)malloc((size_t)c->pointCount * 8 + 8)};
+        for_each_subpath(c, eo_fan, &u);
+        free(u.fx);
+    } else { /* non-zero: libtess triangles through pipelineClipping with ref FILL, compare CLIP, write FILL
+              * (set FILL inside where not clipped); restated like fill_preserve_ as winding != 0 on the polygon edges */
+        nz_user u = {(int32_t *)malloc((size_t)c->pointCount * 16 + 16), 0, INT64_MAX, INT64_MAX, INT64_MIN, INT64_MIN};
+        for_each_subpath(c, nz_collect, &u);
+        if (u.n) {
+            const int8_t(*sp)[2] = sample_table(c->S);
+            rect_i    r = clip_rect(c, u.minx >> 8, u.miny >> 8, ((u.maxx >> 8) + 1) - (u.minx >> 8), ((u.maxy >> 8) + 1) - (u.miny >> 8));
+            clip_user cu = {0x1, 0x2, 0x1};
+            for (int32_t py = r.y0; py < r.y1; py++)
+                for (int32_t px = r.x0; px < r.x1; px++) {
+                    uint32_t mask = 0;
+                    for (uint32_t s = 0; s < c->S; s++) {
+                        int32_t w = 0;
+                        int64_t sx = (int64_t)px * 256 + sp[s][0] * 16, sy = (int64_t)py * 256 + sp[s][1] * 16;
+                        for (uint64_t i = 0; i < u.n; i++) w += edge_winding(u.e[4 * i], u.e[4 * i + 1], u.e[4 * i + 2], u.e[4 * i + 3], sx, sy);
+                        if (w) mask |= 1u << s;
+                    }
+                    if (mask) px_clip(c, (uint32_t)px, (uint32_t)py, mask, &cu);
+                }
+        }
+        free(u.e);
+    }
+    /* cover: ref CLIP, compare FILL, write ALL: FILL set -> 0 (kept), FILL clear -> CLIP */
+    stencil_quad(c, full_rect(c), 0x2, 0x1, 0x3);
+    c->curClipState = 2;
+}
+void ovk_clip_preserve(ovk_ctx *c) { if (!c->status) clip_preserve_(c); }
+void ovk_clip(ovk_ctx *c) { if (c->status) return; clip_preserve_(c); clear_path(c); }
+
+static int previous_clip_state(ovk_ctx *c) { return c->saved ? c->saved->clippingState : 1; } /* :698-702 */
+void ovk_reset_clip(ovk_ctx *c) { /* :719-733; the clear wipes the whole stencil, save bits included (:706-717) */
+    if (c->status) return;
+    if (c->curClipState == 1) return;
+    c->curClipState = previous_clip_state(c) == 1 ? 0 : 1;
+    memset(c->stencil, 0, (size_t)c->W * c->H * c->S);
+}
+void ovk_clear_ctx(ovk_ctx *c) { /* vkvg_clear :734-753: clip state bookkeeping + colour and stencil wiped */
+    if (c->status) return;
+    c->curClipState = previous_clip_state(c) == 1 ? 0 : 1;
+    ovk_clear(c);
+}
+void ovk_save(ovk_ctx *c) { /* :1251-1375 */
+    if (c->status) return;
+    struct ovk_save *sav = (struct ovk_save *)calloc(1, sizeof *sav);
+    if (c->curClipState == 2) {
+        sav->clippingState = 6;
+        if (c->curSavBit > 0 && c->curSavBit % 6 == 0) { /* all six save bits in use: park the whole stencil */
+            c->spills = (uint8_t **)realloc(c->spills, (c->nspills + 1) * sizeof(uint8_t *));
+            c->spills[c->nspills] = (uint8_t *)malloc((size_t)c->W * c->H * c->S);
+            memcpy(c->spills[c->nspills++], c->stencil, (size_t)c->W * c->H * c->S);
+        }
+        uint32_t bit = 1u << (c->curSavBit % 6 + 2);
+        stencil_quad(c, full_rect(c), 0x2 | bit, 0x2, bit); /* save bit := CLIP */
+        c->curSavBit++;
+    } else if (c->curClipState == 0)
+        sav->clippingState = previous_clip_state(c) & 0x03;
+    else
+        sav->clippingState = 1;
+    sav->lineWidth = c->lineWidth; sav->miterLimit = c->miterLimit; sav->dashOffset = c->dashOffset; sav->dashCount = c->dashCount;
+    if (c->dashCount) { sav->dashes = (float *)malloc(sizeof(float) * c->dashCount); memcpy(sav->dashes, c->dashes, sizeof(float) * c->dashCount); }
+    sav->lineCap = c->lineCap; sav->fillRule = c->fillRule; sav->opacity = c->opacity; sav->mat = c->mat;
+    sav->curColor = c->curColor; sav->patType = c->patType; sav->grad = c->grad;
+    sav->next = c->saved;
+    c->saved  = sav;
+}
+void ovk_restore(ovk_ctx *c) { /* :1376-1512 */
+    if (c->status) return;
+    if (!c->saved) { c->status = 3; /* VKVG_STATUS_INVALID_RESTORE */ return; }
+    struct ovk_save *sav = c->saved;
+    c->saved             = sav->next;
+    if (c->curClipState) {
+        if (c->curClipState == 2 && sav->clippingState == 1) memset(c->stencil, 0, (size_t)c->W * c->H * c->S); /* _reset_clip */
+        else {
+            uint32_t bit = 1u << ((c->curSavBit - 1) % 6 + 2);
+            stencil_quad(c, full_rect(c), 0x2 | bit, bit, 0x2); /* CLIP := save bit */
+        }
+    }
+    if (sav->clippingState == 6) {
+        c->curSavBit--;
+        if (c->curSavBit > 0 && c->curSavBit % 6 == 0) { /* the parked stencil comes back whole */
+            memcpy(c->stencil, c->spills[--c->nspills], (size_t)c->W * c->H * c->S);
+            free(c->spills[c->nspills]);
+        }
+    }
+    c->curClipState = 0;
+    c->dashOffset = sav->dashOffset;
+    free(c->dashes);
+    c->dashes = sav->dashes; c->dashCount = sav->dashCount;
+    c->lineWidth = sav->lineWidth; c->miterLimit = sav->miterLimit; c->lineCap = sav->lineCap;
+    c->lineJoin = OVK_JOIN_MITER; /* sav->lineJoint is never written by vkvg_save: restore reads the calloc'ed 0 (:1492) */
+    c->fillRule = sav->fillRule; c->opacity = sav->opacity; c->mat = sav->mat;
+    c->curColor = sav->curColor; c->patType = sav->patType; c->grad = sav->grad;
+    free(sav);
+}
+
 uint32_t ovk_path_points(ovk_ctx *c, const float **pts) { finish_path(c); *pts = (const float *)c->points; return c->pointCount; }
 uint32_t ovk_path_table(ovk_ctx *c, const uint32_t **t) { finish_path(c); *t = c->pathes; return c->pathPtr; }
 uint32_t ovk_last_vertices(ovk_ctx *c, const float **xy) { *xy = (const float *)c->verts; return c->vertCount; }
@@ -1364,9 +1523,21 @@ void ovk_raster_ref_drawlist(ovk_ctx *c, const void *draws_v, uint32_t n, const 
                 raster_tri(c, v, sc, px_invert, NULL);
             }
             free(fx);
+        } else if (d->kind == REF_DRAW_ARRAYS && d->pipeline == REF_PIPE_CLIPPING) { /* clip cover / save / restore quad */
+            stencil_quad(c, sc, d->ref, d->cmpMask, d->writeMask);
         } else if (d->kind == REF_DRAW_ARRAYS) { /* full-screen triangle, FULLSCREEN_BIT set (internal.c:1939-1942) */
             p.solid = vb[d->first].color;
             cover_rect(c, sc, &p, d->cmpMask);
+        } else if (d->pipeline == REF_PIPE_CLIPPING) { /* non-zero clip: libtess triangles set FILL where not clipped */
+            clip_user cu = {d->ref, d->cmpMask, d->writeMask};
+            for (uint32_t t = 0; t + 2 < d->count; t += 3) {
+                int32_t v[6];
+                for (int k = 0; k < 3; k++) {
+                    const ref_vertex *a = &vb[d->vertexOffset + (int64_t)ib[d->first + t + k]];
+                    vs_chain(&M, (float)c->W, (float)c->H, a->x, a->y, &v[2 * k], &v[2 * k + 1]);
+                }
+                raster_tri(c, v, sc, px_clip, &cu);
+            }
         } else {
             blend_user u = {&p, d->cmpMask};
             for (uint32_t t = 0; t + 2 < d->count; t += 3) {

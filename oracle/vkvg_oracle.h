@@ -84,6 +84,13 @@ void ovk_fill_preserve(ovk_ctx *c);
 void ovk_stroke(ovk_ctx *c);
 void ovk_stroke_preserve(ovk_ctx *c);
 void ovk_paint(ovk_ctx *c);
+/* clipping (src/vkvg_context.c:698-795) and the graphics-state stack (:1251-1512) with the reference's clip-state bookkeeping */
+void ovk_clip(ovk_ctx *c);
+void ovk_clip_preserve(ovk_ctx *c);
+void ovk_reset_clip(ovk_ctx *c);
+void ovk_save(ovk_ctx *c);
+void ovk_restore(ovk_ctx *c);
+void ovk_clear_ctx(ovk_ctx *c); /* vkvg_clear as a context call (ovk_clear only wipes the surface) */
 
 /* ---- introspection used by the parity tests ---- */
 /* current path as the reference stores it: points (user space) and the `pathes` table; finishes the open sub-path */

@@ -50,6 +50,148 @@ def elliptic_scene(g, seed):
     g.ellipse(r.uniform(10, 40), r.uniform(10, 40), r.uniform(60, 200), r.uniform(60, 200), r.uniform(0, 3))
 
 
+CLIP_SCENES = ["rect_eo", "circle_nz", "nested", "save_restore", "reset", "preserve_stroke", "deep_stack", "restore_quirk", "clear_inside"]
+
+
+def _blob(g, r, n, size):
+    """a few overlapping translucent shapes covering most of the surface"""
+    for k in range(n):
+        g.set_source_rgba(r.u(), r.u(), r.u(), 0.35 + 0.6 * r.u())
+        if k % 3 == 0:
+            g.rectangle(r.uniform(-10, size * 0.6), r.uniform(-10, size * 0.6), r.uniform(20, size), r.uniform(20, size))
+            g.fill()
+        elif k % 3 == 1:
+            g.arc(r.uniform(0, size), r.uniform(0, size), r.uniform(10, size * 0.5), 0.0, 6.2831855)
+            g.fill()
+        else:
+            g.set_line_width(r.uniform(2, 9))
+            g.move_to(r.uniform(0, size), r.uniform(0, size))
+            g.line_to(r.uniform(0, size), r.uniform(0, size))
+            g.line_to(r.uniform(0, size), r.uniform(0, size))
+            g.stroke()
+
+
+def _star(g, cx, cy, ro, ri, n=5):
+    import math
+    for i in range(2 * n):
+        a = math.pi * i / n
+        rr = ro if i % 2 == 0 else ri
+        (g.move_to if i == 0 else g.line_to)(cx + rr * math.sin(a), cy - rr * math.cos(a))
+    g.close_path()
+
+
+def clip_scene(g, name, seed, size=128):
+    """scenes exercising vkvg_clip / clip_preserve / reset_clip and the clip part of save / restore, including the
+    reference's bookkeeping quirks (src/vkvg_context.c:698-795, :1251-1512); drawn on any of Ref / Oracle / Context."""
+    r = scenes.SplitMix64(8800 + seed)
+    s = float(size)
+    if name == "rect_eo":
+        g.set_fill_rule(0)
+        g.rectangle(s * 0.2 + seed, s * 0.15, s * 0.55, s * 0.6)
+        g.rectangle(s * 0.35, s * 0.3 + seed, s * 0.2, s * 0.2)     # hole under even-odd
+        g.clip()
+        _blob(g, r, 5, size)
+    elif name == "circle_nz":
+        g.set_fill_rule(1)
+        g.arc(s * 0.5, s * 0.5, s * 0.33 + seed, 0.0, 6.2831855)
+        g.clip()
+        g.set_source_linear(0, 0, s, s, [(0, 1, 0, 0, 1), (0.5, 0, 1, 0, 0.6), (1, 0, 0, 1, 1)])
+        g.paint()
+        _blob(g, r, 3, size)
+    elif name == "nested":
+        g.set_fill_rule(1)
+        _star(g, s * 0.5, s * 0.5, s * 0.48, s * 0.2)
+        g.clip()
+        _blob(g, r, 2, size)
+        g.set_fill_rule(0)
+        g.rectangle(s * 0.1, s * 0.4, s * 0.8, s * 0.35)
+        g.clip()                                               # intersection of star and rectangle
+        g.set_source_rgba(0.1, 0.1, 0.9, 0.8)
+        g.paint()
+    elif name == "save_restore":
+        g.rectangle(s * 0.1, s * 0.1, s * 0.8, s * 0.8)
+        g.clip()
+        g.save()
+        g.arc(s * 0.5, s * 0.5, s * 0.25, 0.0, 6.2831855)
+        g.clip()
+        g.set_source_rgba(0.9, 0.2, 0.1, 0.7)
+        g.paint()
+        g.restore()                                            # back to the rectangle
+        g.set_source_rgba(0.1, 0.8, 0.2, 0.4)
+        g.paint()
+        _blob(g, r, 2, size)
+    elif name == "reset":
+        g.rectangle(s * 0.3, s * 0.3, s * 0.3, s * 0.3)
+        g.clip()
+        _blob(g, r, 2, size)
+        g.reset_clip()
+        g.set_source_rgba(0.2, 0.2, 0.8, 0.3)
+        g.paint()
+        g.reset_clip()                                         # second reset is a no-op
+        _blob(g, r, 2, size)
+    elif name == "preserve_stroke":
+        g.set_fill_rule(0)
+        _star(g, s * 0.5, s * 0.5, s * 0.45, s * 0.18, 7)
+        g.clip_preserve()
+        g.set_source_rgba(0.8, 0.7, 0.1, 1.0)
+        g.set_line_width(9.0)
+        g.stroke()                                             # only the inner half of the stroke survives
+        g.set_source_rgba(0.1, 0.3, 0.7, 0.5)
+        g.rectangle(0, s * 0.45, s, s * 0.2)
+        g.fill()
+    elif name == "deep_stack":
+        for k in range(5):                                     # five nested clip saves: save bits 2..6
+            g.rectangle(s * 0.04 * (k + 1), s * 0.03 * (k + 1), s * (0.92 - 0.08 * k), s * (0.94 - 0.06 * k))
+            g.clip()
+            g.save()
+        g.arc(s * 0.5, s * 0.5, s * 0.2, 0.0, 6.2831855)
+        g.clip()
+        g.set_source_rgba(1, 0, 0, 0.6)
+        g.paint()
+        for k in range(5):
+            g.restore()
+            g.set_source_rgba(0.2 * k, 1 - 0.2 * k, 0.5, 0.35)
+            g.paint()
+    elif name == "restore_quirk":
+        # after a restore the context believes no clip is active: a later save / clip / restore pair wipes the stencil
+        g.rectangle(s * 0.2, s * 0.2, s * 0.6, s * 0.6)
+        g.clip()
+        g.save()
+        g.restore()
+        g.save()
+        g.arc(s * 0.5, s * 0.5, s * 0.2, 0.0, 6.2831855)
+        g.clip()
+        g.set_source_rgba(0.9, 0.1, 0.1, 0.8)
+        g.paint()
+        g.restore()
+        g.set_source_rgba(0.1, 0.1, 0.9, 0.4)
+        g.paint()                                              # unclipped in the reference
+    elif name == "clear_inside":
+        g.rectangle(s * 0.25, s * 0.25, s * 0.5, s * 0.5)
+        g.clip()
+        _blob(g, r, 2, size)
+        g.clear()                                              # wipes colour and the clip
+        g.set_source_rgba(0.3, 0.9, 0.3, 0.5)
+        g.arc(s * 0.5, s * 0.5, s * 0.45, 0.0, 6.2831855)
+        g.fill()
+    else:
+        raise KeyError(name)
+
+
+def main_clip():
+    pix = {}
+    for name in CLIP_SCENES:
+        for seed in range(2):
+            r, o = Ref(128, 128, 4), Oracle(128, 128, 4)
+            clip_scene(r, name, seed)
+            r.render_with(o)
+            pix["%s_%d" % (name, seed)] = o.pixels()
+            r.close()
+            o.close()
+    np.savez_compressed(os.path.join(HERE, "clip.npz"), **pix)
+    print("clip.npz", os.path.getsize(os.path.join(HERE, "clip.npz")), "bytes")
+
+
 def ref_path_extents(r):
     f = C.c_float
     x1, y1, x2, y2 = f(), f(), f(), f()

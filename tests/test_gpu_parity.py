@@ -410,3 +410,91 @@ def test_path_extents_without_a_path(dev4, ell):
     assert c.path_extents() == (0.0, 0.0, 0.0, 0.0)
     c.close()
     s.close()
+
+
+# ---- clipping + the clip part of save / restore ----
+@pytest.fixture(scope="module")
+def clipgold():
+    return np.load(os.path.join(GOLD, "clip.npz"))
+
+
+@pytest.mark.parametrize("name", mg2.CLIP_SCENES)
+def test_clip_scenes_match_reference_drawlist_golden(dev4, clipgold, name):
+    """pixels of the reference's recorded stencil + colour draws (oracle raster) for clip / reset_clip / save / restore"""
+    for seed in range(2):
+        s = v.Surface(dev4, 128, 128)
+        c = v.Context(s)
+        mg2.clip_scene(c, name, seed)
+        c.flush()
+        assert c.status() == 0
+        got, ref = s.pixels(), clipgold["%s_%d" % (name, seed)]
+        assert np.array_equal(got, ref), (name, seed, int((got != ref).any(axis=2).sum()))
+        c.close()
+        s.close()
+
+
+@pytest.mark.parametrize("samples", [1, 2, 8, 16])
+def test_clip_other_sample_counts_vs_oracle(oracle_lib, samples):
+    dev = v.Device(samples)
+    for name in ("nested", "save_restore", "deep_stack", "preserve_stroke"):
+        s = v.Surface(dev, 100, 70)
+        c = v.Context(s)
+        o = oracle_lib.Oracle(100, 70, samples)
+        for g in (c, o):
+            mg2.clip_scene(g, name, 3, size=90)
+        c.flush()
+        got, ref = s.pixels(), o.pixels()
+        assert np.array_equal(got, ref), (samples, name, int((got != ref).any(axis=2).sum()))
+        c.close()
+        s.close()
+        o.close()
+    dev.close()
+
+
+def test_clip_survives_flushes_and_deep_save_stack(dev4, oracle_lib):
+    """clip state lives on the surface between flushes; more than six nested clip saves spill the stencil plane"""
+    s = v.Surface(dev4, 96, 96)
+    c = v.Context(s)
+    o = oracle_lib.Oracle(96, 96, 4)
+    for g in (c, o):
+        g.set_fill_rule(1)
+        for k in range(9):                          # nine nested clip saves: two spills (at depth 6 and ... 12 is not reached)
+            g.rectangle(2.0 + 3 * k, 1.5 + 2 * k, 90.0 - 5 * k, 92.0 - 4 * k)
+            g.clip()
+            g.save()
+            if g is c and k % 2:
+                c.flush()
+        g.arc(48.0, 48.0, 14.0, 0.0, 6.2831855)
+        g.clip()
+        g.set_source_rgba(1, 0, 0, 0.7)
+        g.paint()
+        for k in range(9):
+            g.restore()
+            if g is c and k % 3 == 0:
+                c.flush()
+            g.set_source_rgba(0.1 * k, 1 - 0.1 * k, 0.4, 0.3)
+            g.paint()
+    c.flush()
+    got, ref = s.pixels(), o.pixels()
+    assert np.array_equal(got, ref), int((got != ref).any(axis=2).sum())
+    assert c.status() == 0
+    # a second context on the same surface starts unclipped (its first render pass clears the stencil)
+    c2 = v.Context(s)
+    c2.set_source_rgba(0, 0, 1, 1)
+    c2.paint()
+    c2.flush()
+    assert (s.pixels()[..., 2] == 255).all()
+
+
+def test_clip_analytic_mode_vs_oracle(oracle_lib):
+    dev = v.Device(4, analytic=True)
+    s = v.Surface(dev, 128, 128)
+    c = v.Context(s)
+    o = oracle_lib.Oracle(128, 128, 4, analytic=True)
+    for g in (c, o):
+        mg2.clip_scene(g, "save_restore", 0)
+    c.flush()
+    got, ref = s.pixels().astype(int), o.pixels().astype(int)
+    d = np.abs(got - ref)
+    assert np.percentile(d, 99.9) <= 1 and (d > 1).mean() < 1e-3
+    dev.close()

@@ -86,3 +86,21 @@ def test_sample_counts(ref_oracle, samples):
     mg.pixel_scene(r, "mixed", 1, size=96)
     r.render_with(o2)
     assert np.array_equal(o.pixels(), o2.pixels())
+
+
+# ---- clipping and the clip part of save / restore: oracle restatement vs the reference's recorded stencil draws ----
+from tests.golden import make_golden2 as mg2  # noqa: E402
+
+
+@pytest.mark.parametrize("name", mg2.CLIP_SCENES)
+def test_clip_scenes_oracle_equals_reference_drawlist(ref_oracle, name):
+    for seed in range(2):
+        r, o, o2 = ref_oracle.Ref(128, 128, 4), ref_oracle.Oracle(128, 128, 4), ref_oracle.Oracle(128, 128, 4)
+        mg2.clip_scene(r, name, seed)
+        r.render_with(o)
+        mg2.clip_scene(o2, name, seed)
+        assert r.status() == 0 and o2.status() == 0
+        a, b = o.pixels(), o2.pixels()
+        assert np.array_equal(a, b), (name, seed, int((a != b).any(axis=2).sum()))
+        assert (a[..., 3] > 0).sum() > 1000
+        r.close()

@@ -71,6 +71,7 @@ _SIGS = {
     "vkvg_path_extents": (None, [_p] + [C.POINTER(_f)] * 4),
     "vkvg_stroke": (None, [_p]), "vkvg_stroke_preserve": (None, [_p]), "vkvg_fill": (None, [_p]), "vkvg_fill_preserve": (None, [_p]),
     "vkvg_paint": (None, [_p]), "vkvg_clear": (None, [_p]),
+    "vkvg_clip": (None, [_p]), "vkvg_clip_preserve": (None, [_p]), "vkvg_reset_clip": (None, [_p]),
     "vkvg_set_opacity": (None, [_p, _f]), "vkvg_get_opacity": (_f, [_p]), "vkvg_set_source_color": (None, [_p, _u]),
     "vkvg_set_source_rgba": (None, [_p] + [_f] * 4), "vkvg_set_source_rgb": (None, [_p] + [_f] * 3), "vkvg_set_source": (None, [_p, _p]),
     "vkvg_set_line_width": (None, [_p, _f]), "vkvg_set_miter_limit": (None, [_p, _f]), "vkvg_get_miter_limit": (_f, [_p]),
@@ -264,7 +265,7 @@ class Surface:
 
 _CTX_CALLS = ["new_path", "close_path", "new_sub_path", "line_to", "rel_line_to", "move_to", "rel_move_to", "arc", "arc_negative",
               "curve_to", "rel_curve_to", "quadratic_to", "rel_quadratic_to", "rectangle", "rounded_rectangle", "rounded_rectangle2", "elliptic_arc_to", "rel_elliptic_arc_to", "ellipse", "stroke",
-              "stroke_preserve", "fill", "fill_preserve", "paint", "clear", "set_opacity", "set_source_color", "set_source_rgba",
+              "stroke_preserve", "fill", "fill_preserve", "paint", "clear", "clip", "clip_preserve", "reset_clip", "set_opacity", "set_source_color", "set_source_rgba",
               "set_source_rgb", "set_line_width", "set_miter_limit", "set_line_cap", "set_line_join", "set_operator", "set_fill_rule",
               "save", "restore", "translate", "scale", "rotate", "identity_matrix", "flush"]
 

@@ -26,6 +26,8 @@ struct vkb_device_impl {
     DevBuf   fjob_draw, fjob_sp, sjob_draw, sjob_sp, sdraw_id, sdraw_first_job, sdraw_first_item, extra_edges, extra_edge_draw;
     uint32_t n_elems = 0, n_sp = 0, n_draws = 0, n_fjobs = 0, n_sjobs = 0, n_sdraws = 0, n_extra = 0;
     bool     any_dash = false;
+    bool     has_clip_draws = false, has_stencil_ops = false;  // the uploaded batch holds VKB_DRAW_CLIP / any stencil-writing draw
+    int      stencil_after = 0;                                // 0: batch leaves the stencil as it found it, 1: possibly non-zero, 2: all zero
     uint64_t h2d_bytes = 0;
     float    ms_host_upload = 0;
     // intermediates
@@ -44,6 +46,10 @@ struct vkb_surface_impl {
     uint32_t         full_h, origin_y;  // logical surface this one is a stripe of (full_h == h, origin_y == 0 otherwise)
     DevBuf           image;
     DevBuf           ms_image, tile_ms, ms_mask;  // per-sample plane + per-tile validity flags (allocated by the first render)
+    DevBuf           stencil;                     // per-sample clip / save bits (allocated by the first flush that clips)
+    bool             stencil_live = false;        // the plane may hold non-zero bytes
+    uint32_t         stencil_samples = 0;         // sample count the plane was laid out for
+    std::vector<DevBuf> stencil_spills;           // whole-plane copies, one per six nested clip saves
     bool             known_clear;
 };
 
@@ -109,12 +115,44 @@ void vkb_surface_free(vkb_surface_impl *s) {
     s->ms_image.release();
     s->tile_ms.release();
     s->ms_mask.release();
+    s->stencil.release();
+    for (DevBuf &b : s->stencil_spills) b.release();
     delete s;
 }
 void vkb_surface_clear(vkb_surface_impl *s) {
     cudaSetDevice(s->dev->ordinal);
     if (!s->known_clear) VKB_CUDA_OK(cudaMemsetAsync(s->image.p, 0, (size_t)s->w * s->h * 4, s->dev->stream));
     s->known_clear = true;
+    s->stencil_live = false;  // vkvg_clear wipes the stencil attachment too (src/vkvg_context.c:745-752)
+}
+void vkb_surface_stencil_reset(vkb_surface_impl *s) { s->stencil_live = false; }
+static size_t stencil_bytes(const vkb_surface_impl *s, uint32_t samples) {
+    const size_t tiles = (size_t)((s->w + VKB_TILE - 1) / VKB_TILE) * ((s->h + VKB_TILE - 1) / VKB_TILE);
+    return tiles * 256 * ((((size_t)(samples ? samples : 1)) + 3) / 4) * 4;
+}
+// the reference parks the whole stencil image in a spare one every six nested clip saves and copies it back on the matching
+// restore (src/vkvg_context.c:1268-1318, :1425-1470); same here with the stencil plane.  Both run after a flush.
+int vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples) {
+    cudaSetDevice(s->dev->ordinal);
+    const size_t bytes = stencil_bytes(s, samples);
+    s->stencil_spills.emplace_back();
+    DevBuf &b = s->stencil_spills.back();
+    b.ensure(bytes, s->dev->stream);
+    if (s->stencil_live && s->stencil.p) VKB_CUDA_OK(cudaMemcpyAsync(b.p, s->stencil.p, bytes, cudaMemcpyDeviceToDevice, s->dev->stream));
+    else VKB_CUDA_OK(cudaMemsetAsync(b.p, 0, bytes, s->dev->stream));
+    return g_cuda_failed;
+}
+int vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples) {
+    cudaSetDevice(s->dev->ordinal);
+    if (s->stencil_spills.empty()) return 1;
+    const size_t bytes = stencil_bytes(s, samples);
+    s->stencil.ensure(bytes, s->dev->stream);
+    VKB_CUDA_OK(cudaMemcpyAsync(s->stencil.p, s->stencil_spills.back().p, bytes, cudaMemcpyDeviceToDevice, s->dev->stream));
+    VKB_CUDA_OK(cudaStreamSynchronize(s->dev->stream));
+    s->stencil_spills.back().release();
+    s->stencil_spills.pop_back();
+    s->stencil_live = true;
+    return g_cuda_failed;
 }
 const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s) { return s->image.as<uint32_t>(); }
 // device-to-device copy of the premultiplied pixels (e.g. into a tensor handed to an NCCL gather); synchronous
@@ -171,9 +209,9 @@ __global__ void draw_tables_k(const vkb_draw *draws, uint32_t n, vkb_paint *pain
     if (i >= n) return;
     vkb_draw d = draws[i];
     paints[i]  = vkb_paint{d.rule_pattern, d.color, d.opacity, d.gradient};
-    fcnt[i]    = d.kind == VKB_DRAW_FILL ? d.n_subpaths : 0u;
+    fcnt[i]    = (d.kind == VKB_DRAW_FILL || d.kind == VKB_DRAW_CLIP) ? d.n_subpaths : 0u;
     scnt[i]    = d.kind == VKB_DRAW_STROKE ? d.n_subpaths : 0u;
-    pcnt[i]    = d.kind == VKB_DRAW_PAINT ? 1u : 0u;
+    pcnt[i]    = (d.kind == VKB_DRAW_PAINT || d.kind == VKB_DRAW_STENCIL) ? 1u : 0u;  // both cover the surface with a rectangle
 }
 // job j of a kind = (draw, sub-path): the draw is the last one whose exclusive job base is <= j and that has jobs
 __global__ void expand_jobs_k(const vkb_draw *draws, const uint32_t *base, uint32_t n_draws, uint32_t n_jobs, uint32_t *job_draw, uint32_t *job_sp) {
@@ -197,7 +235,7 @@ __global__ void list_draws_k(const vkb_draw *draws, const uint32_t *sbase, const
         uint32_t r = sdraw_rank[i];
         sdraw_id[r] = i; sdraw_first_job[r] = sbase[i];
     }
-    if (d.kind == VKB_DRAW_PAINT) {
+    if (d.kind == VKB_DRAW_PAINT || d.kind == VKB_DRAW_STENCIL) {
         uint32_t r = pbase[i];
         for (int k = 0; k < 4; k++) extra_edge_draw[4 * r + k] = i;
     }
@@ -218,6 +256,15 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     // the previous flush may still be reading the staging area
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
+    d->has_clip_draws = d->has_stencil_ops = false;
+    d->stencil_after = 0;
+    for (const vkb_draw &dr : b.draws) {
+        if (dr.kind == VKB_DRAW_CLIP) { d->has_clip_draws = d->has_stencil_ops = true; d->stencil_after = 1; }
+        else if (dr.kind == VKB_DRAW_STENCIL) {
+            d->has_stencil_ops = true;
+            d->stencil_after   = (dr.rule_pattern & 0xFF) == VKB_RULE_ST_CLEAR ? 2 : 1;
+        }
+    }
 
     struct Src { DevBuf *dst; const void *p; size_t bytes; bool pinned; };
     Src srcs[] = {
@@ -343,7 +390,7 @@ __global__ void paint_rect_edges_k(vkb_edge *e, uint32_t n_rects, int32_t W, int
 
 // binning + fine pass over d->edges / d->edge_draw (n_edges entries, nd draws, paints/grads already on the device)
 static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc sd, uint32_t nd, uint64_t n_edges, vkb_capture *cap, vkb_stats &S,
-                        vkb_stats *stats) {
+                        vkb_stats *stats, const vkb_draw *draws) {  // draws: device pointer, or null for a raw edge list (no clip draws then)
     cudaStream_t st     = d->stream;
     uint64_t    *totals = d->totals.as<uint64_t>();
     const uint32_t samples = sd.samples;
@@ -359,7 +406,8 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     d->draw_rowbase.ensure((size_t)(nd + 1) * 4, st);
     vkb_launch_draw_bbox(edges, edraw, n_edges, nd, d->draw_bbox.as<int32_t>(), st);
     unsigned long long *dc = d->draw_counts.as<unsigned long long>();
-    vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), nd, sd, d->draw_rect.as<int32_t>(), dc, st);
+    const bool clip_draws = draws && d->has_clip_draws, stencil_ops = draws && d->has_stencil_ops;
+    vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), clip_draws ? draws : nullptr, nd, sd, d->draw_rect.as<int32_t>(), dc, st);
     vkb_exclusive_scan<unsigned long long, unsigned long long>(dc, dc, nd, (unsigned long long *)(totals + 4), d->scan, st);
     vkb_launch_split_bases(dc, nd, d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), st);
     unsigned long long tr = read_total(d, totals + 4, 8);
@@ -376,7 +424,8 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
                          d->pt_backdrop.as<int32_t>(), st);
     vkb_launch_backdrop_prefix(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd,
                                (unsigned long long *)(totals + 4), d->pt_backdrop.as<int32_t>(), st);
-    vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), n_pt, d->pt_flags.as<uint32_t>(), st);
+    vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), n_pt, draws, d->draw_ptbase.as<uint32_t>(), nd, clip_draws,
+                        d->pt_flags.as<uint32_t>(), st);
     // pt_slot doubles as the exclusive scan of the flags until the sorted slots overwrite it
     d->sorted_cnt.ensure((size_t)(n_pt + 1) * 4, st);
     uint32_t *flag_scan = d->sorted_cnt.as<uint32_t>();
@@ -433,6 +482,15 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
     }
     fa.ms_image = surf->ms_image.as<uint32_t>(); fa.tile_ms = surf->tile_ms.as<uint8_t>(); fa.ms_mask = surf->ms_mask.as<uint32_t>();
     fa.dst_is_clear = surf->known_clear ? 1 : 0;
+    // clip / save bits: the stencil-aware kernel variant only runs when this batch writes them or earlier ones left some behind
+    fa.stencil = nullptr; fa.stencil_in = 0;
+    if (stencil_ops || surf->stencil_live) {
+        if (surf->stencil_samples != samples) { surf->stencil_live = false; surf->stencil_samples = samples; }  // coverage mode changed: layout differs
+        surf->stencil.ensure(stencil_bytes(surf, samples), st);
+        fa.stencil    = surf->stencil.as<uint32_t>();
+        fa.stencil_in = surf->stencil_live ? 1 : 0;
+        if (stencil_ops && d->stencil_after) surf->stencil_live = d->stencil_after == 1;
+    }
     fa.winding_out = nullptr; fa.winding_draw = 0;
     DevBuf wbuf;
     if (cap && cap->winding) {
@@ -588,7 +646,7 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
         if (stats) *stats = S;
         return g_cuda_failed;
     }
-    return bin_and_fine(d, surf, sd, d->n_draws, n_edges, cap, S, stats);
+    return bin_and_fine(d, surf, sd, d->n_draws, n_edges, cap, S, stats, d->draws.as<vkb_draw>());
 }
 
 int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const vkb_batch &b, vkb_capture *cap, vkb_stats *stats) {
@@ -621,7 +679,7 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
     memset(&S, 0, sizeof S);
     S.ms_stage[0] = -1.f;
     VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
-    int r = bin_and_fine(d, surf, sd, 1, n, &cap, S, nullptr);
+    int r = bin_and_fine(d, surf, sd, 1, n, &cap, S, nullptr, nullptr);
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     vkb_surface_free(surf);
     return r;

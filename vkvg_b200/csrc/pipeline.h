@@ -56,14 +56,17 @@ struct BinBuffers {  // all device pointers
     uint32_t *draw_rowbase; // n_draws (+1): first path-tile row of the draw
 };
 void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s);
-void vkb_launch_draw_rects(const int32_t *draw_bbox, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect, unsigned long long *tile_row_counts,
-                           cudaStream_t s);
+// draws may be null (raw edge lists); a VKB_DRAW_CLIP draw takes the whole surface as its rectangle
+void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
+                           unsigned long long *tile_row_counts, cudaStream_t s);
 void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s);
 void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
                           uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s);
 void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
                                 const unsigned long long *totals, int32_t *pt_backdrop, cudaStream_t s);
-void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, uint32_t *flags, cudaStream_t s);
+// keep_clip: the batch holds VKB_DRAW_CLIP draws, whose path-tiles are all kept (an empty one means "clipped out")
+void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, const vkb_draw *draws, const uint32_t *draw_ptbase,
+                         uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s);
 void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
                            uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
 void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot, cudaStream_t s);
@@ -86,6 +89,8 @@ struct FineArgs {
     uint8_t            *tile_ms;     // per tile: 1 when the samples of some pixel differ (the resolved image alone would lose them)
     uint32_t           *ms_mask;     // per tile: 8 words (one per warp = two pixel rows), bit = that pixel's samples are in ms_image
     int                 dst_is_clear;  // destination known to be transparent black: do not read it
+    uint32_t           *stencil;     // per-sample stencil bytes (clip bit + save bits), tile-major [tile][256][ceil(S/4)] words; null: no clip in play
+    int                 stencil_in;  // the plane holds state from earlier flushes (else it is taken as all zero)
     int32_t            *winding_out; // optional: per-sample winding of the LAST draw touching each sample (parity tests), or null
     uint32_t            winding_draw; // draw index captured into winding_out
 };

@@ -236,12 +236,14 @@ __device__ __forceinline__ int32_t floor_div(int32_t a, int32_t b) {  // b > 0
     return (a % b < 0) ? q - 1 : q;
 }
 // tile rectangle of each draw (clipped to the surface) and its path-tile / row counts packed as lo | hi<<32
-__global__ void draw_rects_k(const int32_t *bbox, uint32_t n_draws, SurfaceDesc sd, int32_t *rect, unsigned long long *counts) {
+__global__ void draw_rects_k(const int32_t *bbox, const vkb_draw *draws, uint32_t n_draws, SurfaceDesc sd, int32_t *rect, unsigned long long *counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_draws) return;
     int32_t mnx = bbox[4 * i], mny = bbox[4 * i + 1], mxx = bbox[4 * i + 2], mxy = bbox[4 * i + 3];
     int32_t tx0 = 0, ty0 = 0, tw = 0, th = 0;
-    if (mnx <= mxx && mxx >= 0 && mxy >= 0 && mnx < (int32_t)sd.width * 256 && mny < (int32_t)sd.height * 256) {
+    if (draws && draws[i].kind == VKB_DRAW_CLIP) {  // everything outside the clip path is affected too
+        tw = (int32_t)sd.tiles_x; th = (int32_t)sd.tiles_y;
+    } else if (mnx <= mxx && mxx >= 0 && mxy >= 0 && mnx < (int32_t)sd.width * 256 && mny < (int32_t)sd.height * 256) {
         tx0         = max(floor_div(mnx, VKB_TILE_FX), 0);
         ty0         = max(floor_div(mny, VKB_TILE_FX), 0);
         int32_t tx1 = min(floor_div(mxx, VKB_TILE_FX), (int32_t)sd.tiles_x - 1);
@@ -252,8 +254,9 @@ __global__ void draw_rects_k(const int32_t *bbox, uint32_t n_draws, SurfaceDesc 
     rect[4 * i] = tx0; rect[4 * i + 1] = ty0; rect[4 * i + 2] = tw; rect[4 * i + 3] = th;
     counts[i] = (unsigned long long)((uint32_t)(tw * th)) | ((unsigned long long)(uint32_t)th << 32);
 }
-void vkb_launch_draw_rects(const int32_t *draw_bbox, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect, unsigned long long *tile_row_counts, cudaStream_t s) {
-    draw_rects_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, n_draws, sd, draw_rect, tile_row_counts);
+void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
+                           unsigned long long *tile_row_counts, cudaStream_t s) {
+    draw_rects_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, draws, n_draws, sd, draw_rect, tile_row_counts);
     VKB_LAUNCHED();
 }
 __global__ void split_bases_k(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi) {
@@ -379,14 +382,22 @@ void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_p
 }
 
 // ---- compaction of non-empty path-tiles and the per-tile ordered lists ----
-__global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, uint32_t *flags) {
+__global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, const vkb_draw *draws, const uint32_t *draw_ptbase,
+                           uint32_t n_draws, bool keep_clip, uint32_t *flags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pt) return;
-    flags[i] = (pt_count[i] != 0 || pt_backdrop[i] != 0) ? 1u : 0u;
+    bool keep = pt_count[i] != 0 || pt_backdrop[i] != 0;
+    if (!keep && keep_clip) {  // an empty path-tile of a clip draw still clips its whole tile out
+        uint32_t d = find_job(draw_ptbase, n_draws, i);
+        while (d + 1 < n_draws && draw_ptbase[d + 1] <= i) d++;
+        keep = draws[d].kind == VKB_DRAW_CLIP;
+    }
+    flags[i] = keep ? 1u : 0u;
 }
-void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, uint32_t *flags, cudaStream_t s) {
+void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, const vkb_draw *draws, const uint32_t *draw_ptbase,
+                         uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s) {
     if (!n_pt) return;
-    pt_flags_k<<<vkb_div_up(n_pt, 256), 256, 0, s>>>(pt_count, pt_backdrop, n_pt, flags);
+    pt_flags_k<<<vkb_div_up(n_pt, 256), 256, 0, s>>>(pt_count, pt_backdrop, n_pt, draws, draw_ptbase, n_draws, keep_clip && draws, flags);
     VKB_LAUNCHED();
 }
 __global__ void pt_compact_k(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
@@ -705,7 +716,23 @@ __device__ __forceinline__ void fine_build_group(uint32_t lane, uint32_t end, ui
     }
 }
 
-template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
+// Per-sample stencil bytes packed four to a word (sample s = byte s & 3 of word s >> 2): bit 1 = clipped out, bits 2-7 =
+// save levels — the reference's stencil attachment layout (src/vkvg_device_internal.h:28-30) minus its transient FILL bit.
+// Clip / save / restore are whole-surface stencil passes there (pipelineClipping, src/vkvg_device_internal.c:233-239;
+// src/vkvg_context.c:754-795, :1320-1336, :1402-1418); here they are ordinary entries of the per-tile draw lists.
+template <int SW> __device__ __forceinline__ void stencil_word_op(uint32_t (&st)[SW], uint32_t rule, uint32_t arg) {
+    const uint32_t bit = arg & 0xFF, sh = (arg >> 8) & 0xFF;
+#pragma unroll
+    for (int k = 0; k < SW; k++) {
+        uint32_t w = st[k];
+        if (rule == VKB_RULE_ST_CLEAR) w = 0u;
+        else if (rule == VKB_RULE_ST_SAVE) w = (w & ~(bit * 0x01010101u)) | (((w & 0x02020202u) >> 1) * bit);
+        else w = (w & ~0x02020202u) | ((((w & (bit * 0x01010101u)) >> sh) & 0x01010101u) << 1);
+        st[k] = w;
+    }
+}
+
+template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_k(FineArgs a) {
     constexpr int ROWS   = 16 * S;
     constexpr int P      = ROWS >= 64 ? 2 : 1;                 // sample rows per lane per pass
     constexpr int PASSES = (ROWS + 32 * P - 1) / (32 * P);
@@ -745,6 +772,10 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
             for (int s = 0; s < S; s++) col[s] = c;
         }
     }
+    constexpr int SW = (S + 3) / 4;
+    uint32_t      stw[SW];
+#pragma unroll
+    for (int k = 0; k < SW; k++) stw[k] = (CLIP && a.stencil_in) ? a.stencil[((size_t)tile * 256 + threadIdx.x) * SW + k] : 0u;
     int32_t wacc[S];
 #pragma unroll
     for (int s = 0; s < S; s++) wacc[s] = 0;
@@ -836,9 +867,19 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
                     for (int s = 0; s < S; s++) a.winding_out[pix * S + s] = w[s];
                 }
             }
-            if (!__any_sync(0xffffffffu, wor != 0)) continue;  // nothing of this draw reaches the pixel block of this warp
             const vkb_paint pt   = ft.paint;
             const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
+            if (CLIP && rule >= VKB_RULE_CLIP_EO) {  // stencil-only entries (warp uniform: the rule belongs to the draw)
+                if (rule <= VKB_RULE_CLIP_NZ) {
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        const bool in = rule == VKB_RULE_CLIP_EO ? (w[s] & 1) != 0 : w[s] != 0;
+                        if (!in) stw[s >> 2] |= VKB_STENCIL_CLIP << (8 * (s & 3));
+                    }
+                } else stencil_word_op<SW>(stw, rule, pt.color);
+                continue;
+            }
+            if (!__any_sync(0xffffffffu, wor != 0)) continue;  // nothing of this draw reaches the pixel block of this warp
             int32_t         n[S], nmax = 0;
             bool            uni = true, two = true;
             if (rule == VKB_RULE_EVEN_ODD) {
@@ -850,6 +891,11 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
             } else {
 #pragma unroll
                 for (int s = 0; s < S; s++) n[s] = abs(w[s]);
+            }
+            if (CLIP) {
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if ((stw[s >> 2] >> (8 * (s & 3))) & VKB_STENCIL_CLIP) n[s] = 0;  // stencil test of every colour pipeline: CLIP bit clear
             }
 #pragma unroll
             for (int s = 0; s < S; s++) {
@@ -885,6 +931,10 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
         __syncthreads();         // phase B reads of cnt / tasks are done before the next group overwrites them
     }
 
+    if (CLIP) {
+#pragma unroll
+        for (int k = 0; k < SW; k++) a.stencil[((size_t)tile * 256 + threadIdx.x) * SW + k] = stw[k];
+    }
     bool differ = false;
 #pragma unroll
     for (int s = 1; s < S; s++) differ = differ || col[s] != col[0];
@@ -927,7 +977,7 @@ template <int S, bool CAPTURE> __global__ void __launch_bounds__(256) fine_k(Fin
 // ----------------------------------------------------------------------------------------------------
 #define FA_STRIDE 17
 #define FA_ONE 1048576.0f
-template <bool CAPTURE> __global__ void __launch_bounds__(256) fine_analytic_k(FineArgs a) {
+template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_analytic_k(FineArgs a) {
     const uint32_t tile  = blockIdx.x;
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) return;
@@ -949,6 +999,7 @@ template <bool CAPTURE> __global__ void __launch_bounds__(256) fine_analytic_k(F
     const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
 
     uint32_t col  = (!a.dst_is_clear && inside) ? a.image[pix] : 0u;
+    uint32_t stw[1] = {(CLIP && a.stencil_in) ? a.stencil[(size_t)tile * 256 + threadIdx.x] : 0u};  // one stencil byte per pixel in this mode
     int32_t  wacc = 0;
     if (threadIdx.x == 0) { s_p = first; s_k = 0; }
     __syncthreads();
@@ -1032,6 +1083,15 @@ template <bool CAPTURE> __global__ void __launch_bounds__(256) fine_analytic_k(F
                 const float t = A - 2.0f * floorf(A * 0.5f);
                 cov = 1.0f - fabsf(t - 1.0f);
             } else cov = fminf(fabsf(A), 1.0f);
+            if (CLIP && rule >= VKB_RULE_CLIP_EO) {
+                if (rule <= VKB_RULE_CLIP_NZ) {  // inside where more than half of the pixel is covered by the clip path
+                    const float t = A - 2.0f * floorf(A * 0.5f);
+                    const float c = rule == VKB_RULE_CLIP_EO ? 1.0f - fabsf(t - 1.0f) : fminf(fabsf(A), 1.0f);
+                    if (!(c > 0.5f)) stw[0] |= VKB_STENCIL_CLIP;
+                } else stencil_word_op<1>(stw, rule, pt.color);
+                continue;
+            }
+            if (CLIP && (stw[0] & VKB_STENCIL_CLIP)) cov = 0.0f;
             if (!__any_sync(0xffffffffu, cov > 0.0f)) continue;
             float src[4];
             eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
@@ -1045,19 +1105,28 @@ template <bool CAPTURE> __global__ void __launch_bounds__(256) fine_analytic_k(F
         if (s_p >= end) break;
         __syncthreads();
     }
+    if (CLIP) a.stencil[(size_t)tile * 256 + threadIdx.x] = stw[0];
     if (inside) a.image[pix] = col;
+}
+template <int S> static void launch_fine_s(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
+    const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
+    if (cap) { if (clip) fine_k<S, true, true><<<tiles, 256, 0, s>>>(a); else fine_k<S, true, false><<<tiles, 256, 0, s>>>(a); }
+    else { if (clip) fine_k<S, false, true><<<tiles, 256, 0, s>>>(a); else fine_k<S, false, false><<<tiles, 256, 0, s>>>(a); }
 }
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s) {
     uint32_t tiles = a.sd.tiles_x * a.sd.tiles_y;
     if (!tiles) return;
-    const bool cap = a.winding_out != nullptr;
+    const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
     switch (a.sd.samples) {
-    case 0: if (cap) fine_analytic_k<true><<<tiles, 256, 0, s>>>(a); else fine_analytic_k<false><<<tiles, 256, 0, s>>>(a); break;
-    case 1: if (cap) fine_k<1, true><<<tiles, 256, 0, s>>>(a); else fine_k<1, false><<<tiles, 256, 0, s>>>(a); break;
-    case 2: if (cap) fine_k<2, true><<<tiles, 256, 0, s>>>(a); else fine_k<2, false><<<tiles, 256, 0, s>>>(a); break;
-    case 4: if (cap) fine_k<4, true><<<tiles, 256, 0, s>>>(a); else fine_k<4, false><<<tiles, 256, 0, s>>>(a); break;
-    case 8: if (cap) fine_k<8, true><<<tiles, 256, 0, s>>>(a); else fine_k<8, false><<<tiles, 256, 0, s>>>(a); break;
-    case 16: if (cap) fine_k<16, true><<<tiles, 256, 0, s>>>(a); else fine_k<16, false><<<tiles, 256, 0, s>>>(a); break;
+    case 0:
+        if (cap) { if (clip) fine_analytic_k<true, true><<<tiles, 256, 0, s>>>(a); else fine_analytic_k<true, false><<<tiles, 256, 0, s>>>(a); }
+        else { if (clip) fine_analytic_k<false, true><<<tiles, 256, 0, s>>>(a); else fine_analytic_k<false, false><<<tiles, 256, 0, s>>>(a); }
+        break;
+    case 1: launch_fine_s<1>(a, tiles, s); break;
+    case 2: launch_fine_s<2>(a, tiles, s); break;
+    case 4: launch_fine_s<4>(a, tiles, s); break;
+    case 8: launch_fine_s<8>(a, tiles, s); break;
+    case 16: launch_fine_s<16>(a, tiles, s); break;
     default: return;
     }
     VKB_LAUNCHED();

@@ -95,6 +95,11 @@ vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, ui
 int               vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst);
 void              vkb_surface_free(vkb_surface_impl *s);
 void              vkb_surface_clear(vkb_surface_impl *s);
+// clip support: forget the stencil plane (a new context clears the stencil attachment with its first render pass,
+// src/vkvg_context.c:44-49) and the whole-plane spill used every six nested clip saves
+void              vkb_surface_stencil_reset(vkb_surface_impl *s);
+int               vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples);
+int               vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples);
 // premultiplied RGBA8 rows, or un-premultiplied as vkvg_surface_write_to_memory does; synchronous
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply);
 const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s);

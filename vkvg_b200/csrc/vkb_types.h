@@ -36,12 +36,22 @@ enum : uint32_t {
     VKB_DRAW_FILL   = 0,  // polygon edges of every sub-path with > 2 points
     VKB_DRAW_STROKE = 1,  // stroke triangles
     VKB_DRAW_PAINT  = 2,  // whole-surface paint
+    VKB_DRAW_CLIP   = 3,  // vkvg_clip: polygon edges like a fill, applied to the whole surface (outside the path = clipped out)
+    VKB_DRAW_STENCIL = 4, // whole-surface stencil bookkeeping of reset_clip / save / restore (no geometry, like a paint)
 };
 enum : uint32_t {
     VKB_RULE_EVEN_ODD = 0,  // blend once where winding is odd      (stencil INVERT fan + cover)
     VKB_RULE_NON_ZERO = 1,  // blend once where winding != 0        (libtess triangles, non-overlapping)
     VKB_RULE_COUNT    = 2,  // blend |winding| times                (stroke triangles blended one by one)
+    // rules >= VKB_RULE_CLIP_EO write the per-sample stencil byte instead of colour.  Bit 1 of that byte is the
+    // reference's STENCIL_CLIP_BIT (set = clipped out), bits 2-7 its six save levels (src/vkvg_device_internal.h:28-30)
+    VKB_RULE_CLIP_EO    = 3,  // CLIP |= !(winding odd)
+    VKB_RULE_CLIP_NZ    = 4,  // CLIP |= !(winding != 0)
+    VKB_RULE_ST_CLEAR   = 5,  // stencil := 0 (vkvg_reset_clip: the reference clears the whole attachment, save bits included)
+    VKB_RULE_ST_SAVE    = 6,  // save bit := CLIP     (draw.color = bit | log2(bit) << 8)
+    VKB_RULE_ST_RESTORE = 7,  // CLIP := save bit
 };
+#define VKB_STENCIL_CLIP 0x2u
 enum : uint32_t { VKB_PAT_SOLID = 0, VKB_PAT_LINEAR = 2, VKB_PAT_RADIAL = 3 };  // vkvg_pattern_type_t values
 
 // A draw is 32 bytes; what rarely changes between draws (CTM, stroke state) lives in side tables that grow only when

@@ -68,7 +68,9 @@ struct saved_state {  // vkvg_context_save_t, src/vkvg_context_internal.h:101-12
     VkvgPattern        pattern;
     uint32_t           patType;
     vkb_gradient       grad;
+    int                clippingState;  // vkvg_clip_state_t of the entry (src/vkvg_context_internal.h:93-99, :123)
 };
+enum { CLIP_STATE_NONE = 0, CLIP_STATE_CLEAR = 1, CLIP_STATE_CLIP = 2, CLIP_STATE_CLIP_SAVED = 6 };
 
 struct _vkvg_context_t {
     vkvg_status_t status;
@@ -99,6 +101,10 @@ struct _vkvg_context_t {
     int32_t            grad_slot; // index of `grad` in batch.grads, or -1
     bool               clear_pending;
     std::vector<saved_state> saved;
+    // clip bookkeeping exactly as the reference keeps it (src/vkvg_context_internal.h:225-226): what the context believes
+    // about the stencil relative to the last saved state, and how many clip saves are stacked
+    int                curClipState;
+    uint32_t           curSavBit;
 };
 
 // ====================================================================================================
@@ -416,6 +422,8 @@ static void init_ctx(VkvgContext ctx) {  // _init_ctx :24-61
     ctx->curColor = 0xff000000;
     ctx->dashOffset = 0;
     ctx->clear_pending = false;
+    ctx->curClipState = CLIP_STATE_NONE;
+    ctx->curSavBit = 0;
 }
 static void clear_path(VkvgContext ctx) {  // _clear_path, internal.c:199-206
     ctx->path_first_sp = (uint32_t)ctx->batch.subpaths.size();
@@ -433,6 +441,10 @@ VkvgContext vkvg_create(VkvgSurface surf) {
     init_ctx(ctx);
     vkvg_surface_reference(surf);
     clear_path(ctx);
+    {   // the first render pass of a new context clears the stencil attachment (src/vkvg_context.c:44-49)
+        std::lock_guard<std::mutex> lk(surf->dev->mtx);
+        vkb_surface_stencil_reset(surf->impl);
+    }
     return ctx;
 }
 vkvg_status_t vkvg_status(VkvgContext ctx) { return !ctx ? VKVG_STATUS_NULL_POINTER : ctx->status; }
@@ -858,9 +870,62 @@ void vkvg_get_dash(VkvgContext ctx, const float *dashes, uint32_t *num_dashes, f
     if (ctx->dashes.empty() || dashes == NULL) return;
     memcpy((float *)dashes, ctx->dashes.data(), sizeof(float) * ctx->dashes.size());
 }
-void vkvg_save(VkvgContext ctx) {  // :1251-1375 (clip state is out of scope)
+// ---- clipping: src/vkvg_context.c:698-795.  The stencil work becomes entries of the draw list (VKB_DRAW_CLIP /
+//      VKB_DRAW_STENCIL) that the fine pass applies per sample, in submission order with the colour draws. ----
+static vkb_draw base_draw(VkvgContext ctx, uint32_t kind, uint32_t rule);
+static void     flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident);
+static void     reserve_draw_tables(VkvgContext ctx);
+static void     finish_path(VkvgContext ctx, uint32_t flags);
+static void stencil_op(VkvgContext ctx, uint32_t rule, uint32_t bit) {
+    vkb_draw d;
+    memset(&d, 0, sizeof d);
+    d.kind = VKB_DRAW_STENCIL;
+    d.rule_pattern = rule;
+    uint32_t sh = 0;
+    while (bit >> (sh + 1)) sh++;
+    d.color = bit | (sh << 8);
+    d.opacity = 1.0f;
+    ctx->batch.draws.push_back(d);
+}
+static int previous_clip_state(VkvgContext ctx) { return ctx->saved.empty() ? CLIP_STATE_CLEAR : ctx->saved.back().clippingState; }  // :698-702
+static void clip_preserve_(VkvgContext ctx) {  // _clip_preserve :754-795
+    finish_path(ctx, 0);
+    if (ctx->batch.subpaths.size() == ctx->path_first_sp) return;  // nothing to clip
+    reserve_draw_tables(ctx);
+    vkb_draw d = base_draw(ctx, VKB_DRAW_CLIP, ctx->fillRule == VKVG_FILL_RULE_EVEN_ODD ? VKB_RULE_CLIP_EO : VKB_RULE_CLIP_NZ);
+    d.rule_pattern &= 0xFF;  // no paint
+    d.gradient = 0;
+    ctx->batch.draws.push_back(d);
+    ctx->curClipState = CLIP_STATE_CLIP;
+}
+void vkvg_clip_preserve(VkvgContext ctx) { if (!vkvg_status(ctx)) clip_preserve_(ctx); }
+void vkvg_clip(VkvgContext ctx) {
+    if (vkvg_status(ctx)) return;
+    clip_preserve_(ctx);
+    clear_path(ctx);
+}
+void vkvg_reset_clip(VkvgContext ctx) {  // :719-733; _reset_clip clears the whole stencil attachment, save bits included (:706-717)
+    if (vkvg_status(ctx)) return;
+    if (ctx->curClipState == CLIP_STATE_CLEAR) return;
+    ctx->curClipState = previous_clip_state(ctx) == CLIP_STATE_CLEAR ? CLIP_STATE_NONE : CLIP_STATE_CLEAR;
+    stencil_op(ctx, VKB_RULE_ST_CLEAR, 0);
+}
+void vkvg_save(VkvgContext ctx) {  // :1251-1375
     if (vkvg_status(ctx)) return;
     saved_state s;
+    if (ctx->curClipState == CLIP_STATE_CLIP) {
+        s.clippingState = CLIP_STATE_CLIP_SAVED;
+        if (ctx->curSavBit > 0 && ctx->curSavBit % 6 == 0) {  // the six save bits are taken: park the whole stencil plane (:1268-1318)
+            flush_impl(ctx, nullptr, false);
+            std::lock_guard<std::mutex> lk(ctx->dev->mtx);
+            if (vkb_surface_stencil_push(ctx->pSurf->impl, ctx->dev->raster_samples())) ctx->status = VKVG_STATUS_DEVICE_ERROR;
+        }
+        stencil_op(ctx, VKB_RULE_ST_SAVE, 1u << (ctx->curSavBit % 6 + 2));
+        ctx->curSavBit++;
+    } else if (ctx->curClipState == CLIP_STATE_NONE)
+        s.clippingState = previous_clip_state(ctx) & 0x03;
+    else
+        s.clippingState = CLIP_STATE_CLEAR;
     s.lineWidth = ctx->lineWidth; s.miterLimit = ctx->miterLimit; s.dashOffset = ctx->dashOffset; s.dashes = ctx->dashes;
     s.op = ctx->op; s.cap = ctx->cap; s.fillRule = ctx->fillRule; s.opacity = ctx->opacity; s.mat = ctx->mat;
     s.curColor = ctx->curColor; s.pattern = ctx->pattern; s.patType = ctx->patType; s.grad = ctx->grad;
@@ -872,6 +937,19 @@ void vkvg_restore(VkvgContext ctx) {  // :1376-1512
     if (ctx->saved.empty()) { ctx->status = VKVG_STATUS_INVALID_RESTORE; return; }
     saved_state s = ctx->saved.back();
     ctx->saved.pop_back();
+    if (ctx->curClipState != CLIP_STATE_NONE) {  // :1398-1424
+        if (ctx->curClipState == CLIP_STATE_CLIP && s.clippingState == CLIP_STATE_CLEAR) stencil_op(ctx, VKB_RULE_ST_CLEAR, 0);
+        else stencil_op(ctx, VKB_RULE_ST_RESTORE, 1u << ((ctx->curSavBit - 1) % 6 + 2));
+    }
+    if (s.clippingState == CLIP_STATE_CLIP_SAVED) {  // :1425-1470
+        ctx->curSavBit--;
+        if (ctx->curSavBit > 0 && ctx->curSavBit % 6 == 0) {
+            flush_impl(ctx, nullptr, false);
+            std::lock_guard<std::mutex> lk(ctx->dev->mtx);
+            if (vkb_surface_stencil_pop(ctx->pSurf->impl, ctx->dev->raster_samples())) ctx->status = VKVG_STATUS_DEVICE_ERROR;
+        }
+    }
+    ctx->curClipState = CLIP_STATE_NONE;
     ctx->mat = s.mat; ctx->opacity = s.opacity;
     ctx->dashOffset = s.dashOffset; ctx->dashes = s.dashes;
     ctx->lineWidth = s.lineWidth; ctx->miterLimit = s.miterLimit; ctx->op = s.op; ctx->cap = s.cap;
@@ -990,6 +1068,7 @@ void vkvg_paint(VkvgContext ctx) {  // :990-1003
 }
 void vkvg_clear(VkvgContext ctx) {  // :734-753: everything drawn so far is wiped, so pending draws can be dropped
     if (vkvg_status(ctx)) return;
+    ctx->curClipState = previous_clip_state(ctx) == CLIP_STATE_CLEAR ? CLIP_STATE_NONE : CLIP_STATE_CLEAR;  // :740-743
     ctx->batch.clear_draws();
     ctx->grad_slot = -1;
     ctx->clear_pending = true;
