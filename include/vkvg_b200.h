@@ -138,6 +138,18 @@ enum {
  * corresponding vkvg_* calls one by one (it does exactly that).  Returns the context status. */
 vkvg_public vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *args, uint64_t n_args);
 
+/* ---- execution model knobs ----
+ * A flush queues its ~40 kernels without any host round trip (counts that are only known on the device stay there; see
+ * vkvg_b200/csrc/dev_util.cuh: vkb_counts) and returns; the next call that needs the result waits for it.  When two
+ * consecutive flushes have the same structure (same numbers of path elements, sub-paths and draws, same surface) the
+ * second is captured into a CUDA graph and later ones replay it with one launch.
+ *   set_graphs(0)        plain launches only
+ *   set_stage_timing(1)  (default) flushes that produce statistics record CUDA events between the pipeline stages, which
+ *                        needs plain launches; with 0 they may replay the graph and report only ms_total and ms_fine */
+vkvg_public void     vkvg_b200_device_set_graphs(VkvgDevice dev, int on);
+vkvg_public void     vkvg_b200_device_set_stage_timing(VkvgDevice dev, int on);
+vkvg_public uint64_t vkvg_b200_device_graph_replays(VkvgDevice dev);
+
 /* ---- SVG parser introspection (parity tests against nanoSVG dumps, tests/test_svg.py) ----
  * Flat dump of a document parsed by vkvg_svg_load (include/vkvg-svg.h), byte-compatible with what oracle/nsvg_dump.c
  * writes for the reference's nanoSVG: "NSVG" f32 width f32 height u32 nshapes, then per shape u32 fillType fillColor

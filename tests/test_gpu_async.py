@@ -1,0 +1,112 @@
+"""GPU: the execution model around the kernels — device-side counts with capacity overflow + replay, asynchronous flushes,
+and CUDA graph replay of structurally identical frames — never changes a pixel."""
+import numpy as np
+import pytest
+
+import vkvg_b200 as v
+from tests import scenes
+from tests.golden import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(g, k, size):
+    """same structure for every k (same number of elements, sub-paths and draws), different coordinates and colours"""
+    r = scenes.SplitMix64(4242)
+    for i in range(40):
+        g.set_source_rgba(r.u(), r.u(), r.u(), 0.4 + 0.5 * r.u())
+        x, y = r.uniform(5, size - 40), r.uniform(5, size - 40)
+        g.move_to(x + k, y)
+        g.curve_to(x + 30, y - 10 + k, x + 35 + k, y + 30, x + 5, y + 35)
+        g.line_to(x - 8, y + 12 + 0.5 * k)
+        g.close_path()
+        if i % 3:
+            g.fill()
+        else:
+            g.set_line_width(2.0 + i % 4)
+            g.stroke()
+
+
+def test_graph_replay_of_repeated_frames_is_bit_exact(oracle_lib):
+    dev = v.Device(4)
+    surf = v.Surface(dev, 160, 160)
+    ctx = v.Context(surf)
+    r0 = dev.graph_replays()
+    for k in range(7):
+        ctx.clear()
+        _frame(ctx, k, 160)
+        ctx.flush()
+        o = oracle_lib.Oracle(160, 160, 4)
+        _frame(o, k, 160)
+        got, ref = surf.pixels(), o.pixels()
+        assert np.array_equal(got, ref), (k, int((got != ref).any(axis=2).sum()))
+        o.close()
+    assert dev.graph_replays() - r0 >= 3   # frames 0-1 launch directly, frame 2 captures, later ones replay
+    # a frame of a different structure falls back to plain launches and is still right
+    ctx.clear()
+    mg.pixel_scene(ctx, "mixed", 1, 160)
+    ctx.flush()
+    o = oracle_lib.Oracle(160, 160, 4)
+    mg.pixel_scene(o, "mixed", 1, 160)
+    assert np.array_equal(surf.pixels(), o.pixels())
+    dev.close()
+
+
+def test_graphs_off_gives_the_same_pixels(oracle_lib):
+    dev = v.Device(4)
+    dev.set_graphs(False)
+    surf = v.Surface(dev, 160, 160)
+    ctx = v.Context(surf)
+    for k in range(4):
+        ctx.clear()
+        _frame(ctx, k, 160)
+        ctx.flush()
+    o = oracle_lib.Oracle(160, 160, 4)
+    _frame(o, 3, 160)
+    assert np.array_equal(surf.pixels(), o.pixels())
+    assert dev.graph_replays() == 0
+    dev.close()
+
+
+def test_capacity_overflow_replays_the_batch(oracle_lib):
+    """a fresh device sizes its intermediates from guesses; a scene that needs far more (long dashed stroke: ~40 vertices per
+    input point; thousands of path-tiles) overflows them, nothing reaches the surface, and the replay with room is exact"""
+    dev = v.Device(4)
+    surf = v.Surface(dev, 256, 256)
+    ctx = v.Context(surf)
+    o = oracle_lib.Oracle(256, 256, 4)
+    pts = scenes.polyline_c3(400, 256, 5)
+    for g in (ctx, o):
+        g.set_source_rgba(0.2, 0.4, 0.9, 0.6)
+        g.paint()
+        g.set_source_rgba(0.9, 0.3, 0.1, 0.8)
+        g.set_line_width(3.0)
+        g.set_line_join(1)
+        g.set_line_cap(1)
+        g.set_dash([2.0, 1.5], 0.0)
+        g.move_to(float(pts[0, 0]), float(pts[0, 1]))
+        for p in pts[1:]:
+            g.line_to(float(p[0]), float(p[1]))
+        g.stroke()
+        for i in range(300):
+            g.set_source_rgba(0.1, 0.8, 0.3, 0.3)
+            g.rectangle(3.0 + (i % 20) * 12, 2.0 + (i // 20) * 16, 30.0, 40.0)
+            g.fill()
+    ctx.flush()
+    got, ref = surf.pixels(), o.pixels()
+    assert np.array_equal(got, ref), int((got != ref).any(axis=2).sum())
+    dev.close()
+
+
+def test_flush_is_asynchronous_but_ordered(oracle_lib):
+    """several flushes queued back to back without reading anything in between, then one read"""
+    dev = v.Device(4)
+    surf = v.Surface(dev, 128, 128)
+    ctx = v.Context(surf)
+    o = oracle_lib.Oracle(128, 128, 4)
+    for name in ("eo", "stroke_alpha", "grad_linear", "stroke_dash", "grad_radial"):
+        mg.pixel_scene(ctx, name, 2)
+        ctx.flush()
+        mg.pixel_scene(o, name, 2)
+    assert np.array_equal(surf.pixels(), o.pixels())
+    dev.close()

@@ -113,6 +113,8 @@ _SIGS = {
     "vkvg_b200_flush_keep": (None, [_p]), "vkvg_b200_replay_resident": (None, [_p, _p, _i]),
     "vkvg_b200_replay": (_i, [_p, _p, C.c_uint64, _p, C.c_uint64]),
     "vkvg_b200_time_resident": (_i, [_p, _p, _u, _i, _i, C.POINTER(Stats)]),
+    "vkvg_b200_device_set_graphs": (None, [_p, _i]), "vkvg_b200_device_set_stage_timing": (None, [_p, _i]),
+    "vkvg_b200_device_graph_replays": (C.c_uint64, [_p]),
     "vkvg_b200_device_set_coverage_mode": (_i, [_p, _i]), "vkvg_b200_device_get_coverage_mode": (_i, [_p]),
     "vkvg_b200_surface_create_stripe": (_p, [_p, _u, _u, _u, _u]), "vkvg_b200_surface_copy_to_device": (_i, [_p, _p]),
 }
@@ -181,6 +183,15 @@ class Device:
         s = Stats()
         lib().vkvg_b200_last_stats(self.h, C.byref(s))
         return s.as_dict()
+
+    def set_graphs(self, on=True):
+        lib().vkvg_b200_device_set_graphs(self.h, int(on))
+
+    def set_stage_timing(self, on=True):
+        lib().vkvg_b200_device_set_stage_timing(self.h, int(on))
+
+    def graph_replays(self):
+        return int(lib().vkvg_b200_device_graph_replays(self.h))
 
     def synchronize(self):
         lib().vkvg_b200_device_synchronize(self.h)

@@ -25,11 +25,13 @@ static inline uint32_t vkb_div_up(uint64_t a, uint64_t b) { return (uint32_t)((a
 
 // A device allocation that only ever grows (by doubling) and is reused flush after flush, so the steady
 // state does no cudaMalloc.  Contents are NOT preserved across a growth unless keep=true.
+extern unsigned long long g_vkb_alloc_generation;  // bumped whenever a DevBuf changes address: cached CUDA graphs bake pointers in
 struct DevBuf {
     void  *p   = nullptr;
     size_t cap = 0;
     void   ensure(size_t bytes, cudaStream_t s, bool keep = false) {
         if (bytes <= cap) return;
+        g_vkb_alloc_generation++;
         size_t ncap = cap ? cap : 4096;
         while (ncap < bytes) ncap *= 2;
         void *np = nullptr;
@@ -43,12 +45,50 @@ struct DevBuf {
         cap = ncap;
     }
     void release() {
+        if (p) g_vkb_alloc_generation++;
         if (p) cudaFree(p);
         p   = nullptr;
         cap = 0;
     }
     template <class T> T *as() const { return (T *)p; }
 };
+
+// ----------------------------------------------------------------------------------------------------
+// Counts that live on the device.
+// How many points a batch flattens to, how many stroke vertices, path-tiles, tile edges ... is only known after the
+// kernel that produces them.  Reading each one back would stall the stream eight times per flush, so the host never
+// does: it sizes buffers and grids from CAPACITIES (what earlier flushes needed, or a guess), kernels read the real
+// count from this block, and a one-thread commit kernel after each producing scan checks it against the capacity.
+// If a count does not fit, `overflow` is set and every later kernel of the flush returns at once — nothing is written
+// past a buffer and the surface is left untouched; the host sees the flag when it next synchronises, grows the
+// capacities from `need` and replays the batch (which is still resident).  Steady state: zero host round trips.
+// ----------------------------------------------------------------------------------------------------
+enum {
+    VKC_POINTS = 0,  // flattened points
+    VKC_FILL,        // fill / clip polygon edges
+    VKC_SITEMS,      // stroke work items (points of stroked sub-paths)
+    VKC_VERTS,       // stroke vertices
+    VKC_INDS,        // stroke indices
+    VKC_TRIS,        // stroke triangles
+    VKC_EDGES,       // all device-space edges
+    VKC_PT,          // path-tiles (draw x tile of its rectangle)
+    VKC_ROWS,        // path-tile rows
+    VKC_NE,          // non-empty path-tiles
+    VKC_TE,          // edges copied into tile lists
+    VKC_N
+};
+struct vkb_counts {
+    uint32_t n[16];     // committed counts (0 for one that overflowed)
+    uint32_t cap[16];   // capacities this flush was launched with
+    uint32_t need[16];  // raw totals, valid for every count up to and including the first one that overflowed
+    uint32_t overflow;  // bit i: count i did not fit
+    uint32_t pad[3];
+};
+__device__ __forceinline__ void vkc_commit(vkb_counts *C, int idx, uint32_t raw) {
+    C->need[idx] = raw;
+    if (raw > C->cap[idx]) { C->overflow |= 1u << idx; C->n[idx] = 0; }
+    else C->n[idx] = raw;
+}
 
 // ----------------------------------------------------------------------------------------------------
 // warp / block scans
@@ -89,7 +129,9 @@ template <class T, int BLOCK> __device__ __forceinline__ T block_excl_scan(T v, 
 #define VKB_SCAN_ITEMS 8
 #define VKB_SCAN_CHUNK (VKB_SCAN_BLOCK * VKB_SCAN_ITEMS)
 
-template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) scan_reduce_k(const TI *in, T *sums, uint64_t n) {
+// n = n_add (+ C->n[idx] when C is given: a count that lives on the device, see vkb_counts)
+template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) scan_reduce_k(const TI *in, T *sums, uint64_t n, const vkb_counts *C, int idx) {
+    if (C) { if (C->overflow) return; n += C->n[idx]; }
     uint64_t base = (uint64_t)blockIdx.x * VKB_SCAN_CHUNK;
     T        acc  = 0;
 #pragma unroll
@@ -101,7 +143,8 @@ template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) s
     block_excl_scan<T, VKB_SCAN_BLOCK>(acc, total);
     if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
-template <class T> __global__ void __launch_bounds__(1024) scan_sums_k(T *sums, uint32_t m, T *total_out) {
+template <class T> __global__ void __launch_bounds__(1024) scan_sums_k(T *sums, uint32_t m, T *total_out, vkb_counts *C, int commit_idx) {
+    if (C && C->overflow) return;
     __shared__ T carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
@@ -115,8 +158,41 @@ template <class T> __global__ void __launch_bounds__(1024) scan_sums_k(T *sums, 
         __syncthreads();
     }
     if (threadIdx.x == 0 && total_out) *total_out = carry;
+    if (threadIdx.x == 0 && commit_idx >= 0) vkc_commit(C, commit_idx, (uint32_t)carry);  // the total is itself a device-side count
 }
-template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) scan_apply_k(const TI *in, T *out, const T *sums, uint64_t n) {
+// short inputs (everything a 1024^2 frame of a few hundred paths produces): one block does the whole scan in one launch
+#define VKB_SCAN_SMALL (1024 * 8 * 8)
+template <class TI, class T> __global__ void __launch_bounds__(1024) scan_small_k(const TI *in, T *out, uint64_t n, T *total_out, vkb_counts *C, int idx, int commit_idx) {
+    if (C) { if (C->overflow) return; if (idx >= 0) n += C->n[idx]; }
+    __shared__ T carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024 * 8) {
+        const uint64_t b0 = base + (uint64_t)threadIdx.x * 8;
+        T v[8], acc = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = b0 + k < n ? (T)in[b0 + k] : T(0);
+            acc += v[k];
+        }
+        T tot;
+        T e = block_excl_scan<T, 1024>(acc, tot) + carry_s;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (b0 + k < n) out[b0 + k] = e;
+            e += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (total_out) *total_out = carry_s;
+        if (commit_idx >= 0) vkc_commit(C, commit_idx, (uint32_t)carry_s);
+    }
+}
+template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) scan_apply_k(const TI *in, T *out, const T *sums, uint64_t n, const vkb_counts *C, int idx) {
+    if (C) { if (C->overflow) return; n += C->n[idx]; }
     // each thread owns VKB_SCAN_ITEMS consecutive items so the order of summation is the input order
     uint64_t base = (uint64_t)blockIdx.x * VKB_SCAN_CHUNK + (uint64_t)threadIdx.x * VKB_SCAN_ITEMS;
     T        v[VKB_SCAN_ITEMS], acc = 0;
@@ -141,19 +217,29 @@ template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) s
 struct ScanScratch {
     DevBuf sums;
 };
+// host-known length n; with C the length is n + C->n[idx] and `cap` bounds it (grid and scratch are sized for cap)
+// commit_idx >= 0: the total is committed as count commit_idx of C (checked against its capacity)
 template <class TI, class T>
-static inline void vkb_exclusive_scan(const TI *in, T *out, uint64_t n, T *total_dev, ScanScratch &sc, cudaStream_t s) {
-    if (n == 0) {
+static inline void vkb_exclusive_scan(const TI *in, T *out, uint64_t n, T *total_dev, ScanScratch &sc, cudaStream_t s, vkb_counts *C = nullptr,
+                                      int idx = -1, uint64_t cap = 0, int commit_idx = -1) {
+    const uint64_t bound = (C && idx >= 0) ? cap : n;
+    if (bound == 0) {
         if (total_dev) VKB_CUDA_OK(cudaMemsetAsync(total_dev, 0, sizeof(T), s));
+        return;  // (a committed count keeps the zero the reset gave it)
+    }
+    if (bound <= VKB_SCAN_SMALL) {
+        scan_small_k<TI, T><<<1, 1024, 0, s>>>(in, out, n, total_dev, C, idx, commit_idx);
+        VKB_LAUNCHED();
         return;
     }
-    uint32_t chunks = vkb_div_up(n, VKB_SCAN_CHUNK);
+    const vkb_counts *Cn = (C && idx >= 0) ? C : nullptr;
+    uint32_t chunks = vkb_div_up(bound, VKB_SCAN_CHUNK);
     sc.sums.ensure((size_t)chunks * sizeof(T), s);
-    scan_reduce_k<TI, T><<<chunks, VKB_SCAN_BLOCK, 0, s>>>(in, sc.sums.as<T>(), n);
+    scan_reduce_k<TI, T><<<chunks, VKB_SCAN_BLOCK, 0, s>>>(in, sc.sums.as<T>(), n, Cn, idx);
     VKB_LAUNCHED();
-    scan_sums_k<T><<<1, 1024, 0, s>>>(sc.sums.as<T>(), chunks, total_dev);
+    scan_sums_k<T><<<1, 1024, 0, s>>>(sc.sums.as<T>(), chunks, total_dev, C, commit_idx);
     VKB_LAUNCHED();
-    scan_apply_k<TI, T><<<chunks, VKB_SCAN_BLOCK, 0, s>>>(in, out, sc.sums.as<T>(), n);
+    scan_apply_k<TI, T><<<chunks, VKB_SCAN_BLOCK, 0, s>>>(in, out, sc.sums.as<T>(), n, Cn, idx);
     VKB_LAUNCHED();
 }
 
@@ -176,7 +262,9 @@ __device__ __forceinline__ void sort_warp_hist(const uint32_t *keys, uint64_t n,
         __syncwarp();
     }
 }
-static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_hist_k(const uint32_t *keys, uint64_t n, int shift, uint32_t *hist, uint32_t nblocks) {
+static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_hist_k(const uint32_t *keys, uint64_t n, int shift, uint32_t *hist, uint32_t nblocks,
+                                                                     const vkb_counts *C, int idx) {
+    if (C) { if (C->overflow) return; n = C->n[idx]; }
     __shared__ uint32_t wc[VKB_SORT_BLOCK / 32][256];
     for (int i = threadIdx.x; i < (VKB_SORT_BLOCK / 32) * 256; i += VKB_SORT_BLOCK) (&wc[0][0])[i] = 0;
     __syncthreads();
@@ -188,7 +276,8 @@ static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_hist_k(const uint3
     hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = sum;  // digit-major so one scan yields global offsets
 }
 static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_scatter_k(const uint32_t *keys, const uint32_t *vals, uint32_t *okeys, uint32_t *ovals,
-                                                                uint64_t n, int shift, const uint32_t *hist_scan, uint32_t nblocks) {
+                                                                uint64_t n, int shift, const uint32_t *hist_scan, uint32_t nblocks, const vkb_counts *C, int idx) {
+    if (C) { if (C->overflow) return; n = C->n[idx]; }
     __shared__ uint32_t wc[VKB_SORT_BLOCK / 32][256];
     for (int i = threadIdx.x; i < (VKB_SORT_BLOCK / 32) * 256; i += VKB_SORT_BLOCK) (&wc[0][0])[i] = 0;
     __syncthreads();
@@ -226,8 +315,10 @@ struct SortScratch {
     DevBuf      hist, k2, v2;
     ScanScratch scan;
 };
-// sorts in place (result ends in keys/vals); `bits` = number of significant key bits
-static inline void vkb_radix_sort(uint32_t *keys, uint32_t *vals, uint64_t n, int bits, SortScratch &sc, cudaStream_t s) {
+// sorts in place (result ends in keys/vals); `bits` = number of significant key bits.  With C the number of pairs is
+// C->n[idx] (<= n, which then is the capacity the launch is sized for).
+static inline void vkb_radix_sort(uint32_t *keys, uint32_t *vals, uint64_t n, int bits, SortScratch &sc, cudaStream_t s, vkb_counts *C = nullptr,
+                                  int idx = 0) {
     if (n < 2) return;
     uint32_t nblocks = vkb_div_up(n, VKB_SORT_CHUNK);
     sc.hist.ensure((size_t)256 * nblocks * 4, s);
@@ -237,10 +328,10 @@ static inline void vkb_radix_sort(uint32_t *keys, uint32_t *vals, uint64_t n, in
     int       passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
     for (int p = 0; p < passes; p++) {
-        sort_hist_k<<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks);
+        sort_hist_k<<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
         VKB_LAUNCHED();
         vkb_exclusive_scan<uint32_t, uint32_t>(sc.hist.as<uint32_t>(), sc.hist.as<uint32_t>(), (uint64_t)256 * nblocks, nullptr, sc.scan, s);
-        sort_scatter_k<<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, va, kb, vb, n, p * 8, sc.hist.as<uint32_t>(), nblocks);
+        sort_scatter_k<<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, va, kb, vb, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
         VKB_LAUNCHED();
         uint32_t *t;
         t = ka; ka = kb; kb = t;

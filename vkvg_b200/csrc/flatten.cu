@@ -122,9 +122,10 @@ __device__ __forceinline__ void flatten_arc(PointSink &s, const float *e) {
 
 template <bool EMIT>
 __global__ void __launch_bounds__(128) flatten_k(const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, uint32_t *counts,
-                                                const uint32_t *offsets, float2 *pts, uint8_t *flags) {
+                                                const uint32_t *offsets, float2 *pts, uint8_t *flags, const vkb_counts *C) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_elems) return;
+    if (EMIT && C->overflow) return;  // the points do not fit the buffers of this attempt (dev_util.cuh: vkb_counts)
     const uint32_t hdr = elem_hdr[i];
     const float   *e   = elem_data + (hdr >> VKB_EL_PAYLOAD_SHIFT);
     PointSink s;
@@ -160,13 +161,13 @@ __global__ void subpath_ranges_k(const vkb_subpath *sps, uint32_t n_sp, const ui
 
 void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, cudaStream_t s) {
     if (!n) return;
-    flatten_k<false><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, nullptr, nullptr, nullptr);
+    flatten_k<false><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, nullptr, nullptr, nullptr, nullptr);
     VKB_LAUNCHED();
 }
 void vkb_launch_flatten_emit(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, const uint32_t *offsets, float2 *pts, uint8_t *flags,
-                             cudaStream_t s) {
+                             const vkb_counts *C, cudaStream_t s) {
     if (!n) return;
-    flatten_k<true><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, nullptr, offsets, pts, flags);
+    flatten_k<true><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, nullptr, offsets, pts, flags, C);
     VKB_LAUNCHED();
 }
 void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_off, uint32_t n_elems, const uint32_t *total,

@@ -7,8 +7,13 @@
 #include <chrono>
 
 unsigned long long g_vkb_launches = 0;
+unsigned long long g_vkb_alloc_generation = 0;
 static int         g_cuda_failed  = 0;
 void               vkb_note_cuda_error(cudaError_t) { g_cuda_failed = 1; }
+
+struct SurfFlags { bool known_clear, stencil_live; uint32_t stencil_samples; };  // surface state a flush attempt changes
+struct vkb_device_impl;
+static int finish_pending(vkb_device_impl *d);
 
 struct vkb_device_impl {
     int          ordinal = 0;
@@ -36,10 +41,30 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image;
+    DevBuf winding, tmp_image, cursor2;
     ScanScratch scan;
     SortScratch sort;
+    // counts that live on the device (dev_util.cuh: vkb_counts) and the flush that may still be in flight
+    DevBuf            counts;
+    vkb_counts       *counts_host = nullptr;  // pinned
+    uint32_t          capv[16] = {};           // grow-only capacities
+    bool              pending = false;
+    vkb_surface_impl *pending_surf = nullptr;
+    uint32_t          pending_samples = 0;
+    SurfFlags         pending_before = {};
+    // CUDA graph of one whole flush, reused while everything that shapes the launches stays the same (FlushKey)
+    bool              capturing = false;
+    bool              stage_timing = true;   // stats carry per-stage times (forces plain launches: events between kernels)
+    bool              graphs_enabled = true;
+    uint8_t           last_key[256] = {}, graph_key[256] = {};
+    bool              have_last_key = false;
+    cudaGraphExec_t   graph_exec = nullptr;
+    unsigned long long graph_launches = 0;   // kernels in the cached graph (bench: gpu_launches)
+    unsigned long long n_graph_replays = 0;
+    SurfFlags         graph_after = {};       // surface flags a flush of the cached graph leaves behind
+    bool              graph_fine_events = false;  // the cached graph records ev_fine0 / ev_fine1 as external event nodes
 };
+#define VKB_EVENT_RECORD(d, ev) do { if (!(d)->capturing) VKB_CUDA_OK(cudaEventRecord((ev), (d)->stream)); } while (0)
 struct vkb_surface_impl {
     vkb_device_impl *dev;
     uint32_t         w, h;
@@ -68,13 +93,18 @@ vkb_device_impl *vkb_device_open(int ordinal) {
     VKB_CUDA_OK(cudaEventCreateWithFlags(&d->ev_h2d, cudaEventDisableTiming));
     for (cudaEvent_t &e : d->ev_stage) VKB_CUDA_OK(cudaEventCreate(&e));
     VKB_CUDA_OK(cudaHostAlloc((void **)&d->readback, 16 * sizeof(uint64_t), cudaHostAllocDefault));
+    VKB_CUDA_OK(cudaHostAlloc((void **)&d->counts_host, sizeof(vkb_counts), cudaHostAllocDefault));
+    if (d->counts_host) memset(d->counts_host, 0, sizeof(vkb_counts));
     if (g_cuda_failed) { delete d; return nullptr; }
     return d;
 }
 void vkb_device_close(vkb_device_impl *d) {
     if (!d) return;
     cudaSetDevice(d->ordinal);
+    finish_pending(d);
     cudaStreamSynchronize(d->stream);
+    d->counts.release(); d->cursor2.release();
+    if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
                       &d->sp_first, &d->sp_count, &d->fjob_base, &d->sjob_base, &d->seglen, &d->cum, &d->item_counts, &d->verts, &d->inds, &d->job_inverse,
@@ -85,6 +115,7 @@ void vkb_device_close(vkb_device_impl *d) {
     if (d->stage) cudaFreeHost(d->stage);
     cudaFreeHost(d->readback);
     for (cudaEvent_t &e : d->ev_stage) cudaEventDestroy(e);
+    if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
     d->l2_flush.release();
     cudaEventDestroy(d->ev_h2d);
     cudaEventDestroy(d->ev_begin); cudaEventDestroy(d->ev_end); cudaEventDestroy(d->ev_fine0); cudaEventDestroy(d->ev_fine1);
@@ -94,6 +125,7 @@ void vkb_device_close(vkb_device_impl *d) {
 int  vkb_device_failed(vkb_device_impl *) { return g_cuda_failed; }
 void vkb_device_sync(vkb_device_impl *d) {
     cudaSetDevice(d->ordinal);
+    finish_pending(d);
     VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
 }
 
@@ -110,6 +142,7 @@ vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, ui
 void vkb_surface_free(vkb_surface_impl *s) {
     if (!s) return;
     cudaSetDevice(s->dev->ordinal);
+    finish_pending(s->dev);
     cudaStreamSynchronize(s->dev->stream);
     s->image.release();
     s->ms_image.release();
@@ -121,11 +154,15 @@ void vkb_surface_free(vkb_surface_impl *s) {
 }
 void vkb_surface_clear(vkb_surface_impl *s) {
     cudaSetDevice(s->dev->ordinal);
+    finish_pending(s->dev);
     if (!s->known_clear) VKB_CUDA_OK(cudaMemsetAsync(s->image.p, 0, (size_t)s->w * s->h * 4, s->dev->stream));
     s->known_clear = true;
     s->stencil_live = false;  // vkvg_clear wipes the stencil attachment too (src/vkvg_context.c:745-752)
 }
-void vkb_surface_stencil_reset(vkb_surface_impl *s) { s->stencil_live = false; }
+void vkb_surface_stencil_reset(vkb_surface_impl *s) {
+    if (s->stencil_live) finish_pending(s->dev);
+    s->stencil_live = false;
+}
 static size_t stencil_bytes(const vkb_surface_impl *s, uint32_t samples) {
     const size_t tiles = (size_t)((s->w + VKB_TILE - 1) / VKB_TILE) * ((s->h + VKB_TILE - 1) / VKB_TILE);
     return tiles * 256 * ((((size_t)(samples ? samples : 1)) + 3) / 4) * 4;
@@ -134,6 +171,7 @@ static size_t stencil_bytes(const vkb_surface_impl *s, uint32_t samples) {
 // restore (src/vkvg_context.c:1268-1318, :1425-1470); same here with the stencil plane.  Both run after a flush.
 int vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples) {
     cudaSetDevice(s->dev->ordinal);
+    finish_pending(s->dev);
     const size_t bytes = stencil_bytes(s, samples);
     s->stencil_spills.emplace_back();
     DevBuf &b = s->stencil_spills.back();
@@ -144,6 +182,7 @@ int vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples) {
 }
 int vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples) {
     cudaSetDevice(s->dev->ordinal);
+    finish_pending(s->dev);
     if (s->stencil_spills.empty()) return 1;
     const size_t bytes = stencil_bytes(s, samples);
     s->stencil.ensure(bytes, s->dev->stream);
@@ -158,6 +197,7 @@ const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s) { return s->image
 // device-to-device copy of the premultiplied pixels (e.g. into a tensor handed to an NCCL gather); synchronous
 int vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst) {
     cudaSetDevice(s->dev->ordinal);
+    finish_pending(s->dev);
     VKB_CUDA_OK(cudaMemcpyAsync(dst, s->image.p, (size_t)s->w * s->h * 4, cudaMemcpyDeviceToDevice, s->dev->stream));
     VKB_CUDA_OK(cudaStreamSynchronize(s->dev->stream));
     return g_cuda_failed;
@@ -165,6 +205,7 @@ int vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst) {
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) {
     vkb_device_impl *d = s->dev;
     cudaSetDevice(d->ordinal);
+    if (finish_pending(d)) return 1;
     size_t          bytes = (size_t)s->w * s->h * 4;
     const uint32_t *src   = s->image.as<uint32_t>();
     if (unpremultiply) {
@@ -176,6 +217,11 @@ int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) 
     VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
     return g_cuda_failed;
 }
+
+// ---- pending (asynchronous) flush bookkeeping ----
+static SurfFlags surf_flags(const vkb_surface_impl *s) { return SurfFlags{s->known_clear, s->stencil_live, s->stencil_samples}; }
+static void      surf_restore(vkb_surface_impl *s, SurfFlags f) { s->known_clear = f.known_clear; s->stencil_live = f.stencil_live; s->stencil_samples = f.stencil_samples; }
+static int  run_flush(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats, bool allow_async);
 
 // ---- upload ----
 static uint8_t *stage_reserve(vkb_device_impl *d, size_t bytes) {
@@ -191,20 +237,9 @@ static uint8_t *stage_reserve(vkb_device_impl *d, size_t bytes) {
     }
     return d->stage;
 }
-struct Uploader {
-    vkb_device_impl *d;
-    size_t           off = 0;
-    struct Item { DevBuf *dst; size_t off, bytes; };
-    std::vector<Item> items;
-    size_t total = 0;
-    void   plan(DevBuf *dst, size_t bytes) {
-        items.push_back({dst, total, bytes});
-        total += (bytes + 255) & ~(size_t)255;
-    }
-};
 
 // ---- per-draw tables built on the device (the host only uploads what it recorded) ----
-__global__ void draw_tables_k(const vkb_draw *draws, uint32_t n, vkb_paint *paints, uint32_t *fcnt, uint32_t *scnt, uint32_t *pcnt) {
+__global__ void draw_tables_k(const vkb_draw *draws, uint32_t n, vkb_paint *paints, uint32_t *fcnt, uint32_t *scnt, uint32_t *pcnt, uint32_t *is_sdraw) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     vkb_draw d = draws[i];
@@ -212,6 +247,7 @@ __global__ void draw_tables_k(const vkb_draw *draws, uint32_t n, vkb_paint *pain
     fcnt[i]    = (d.kind == VKB_DRAW_FILL || d.kind == VKB_DRAW_CLIP) ? d.n_subpaths : 0u;
     scnt[i]    = d.kind == VKB_DRAW_STROKE ? d.n_subpaths : 0u;
     pcnt[i]    = (d.kind == VKB_DRAW_PAINT || d.kind == VKB_DRAW_STENCIL) ? 1u : 0u;  // both cover the surface with a rectangle
+    is_sdraw[i] = (d.kind == VKB_DRAW_STROKE && d.n_subpaths) ? 1u : 0u;
 }
 // job j of a kind = (draw, sub-path): the draw is the last one whose exclusive job base is <= j and that has jobs
 __global__ void expand_jobs_k(const vkb_draw *draws, const uint32_t *base, uint32_t n_draws, uint32_t n_jobs, uint32_t *job_draw, uint32_t *job_sp) {
@@ -225,7 +261,7 @@ __global__ void expand_jobs_k(const vkb_draw *draws, const uint32_t *base, uint3
     job_draw[j] = lo;
     job_sp[j]   = draws[lo].first_subpath + (j - base[lo]);
 }
-// stroke draws in order (ids + their first job) and paint draws (ids, four rectangle edges each)
+// stroke draws in order (ids + their first job) and whole-surface draws (ids, four rectangle edges each)
 __global__ void list_draws_k(const vkb_draw *draws, const uint32_t *sbase, const uint32_t *pbase, uint32_t n, uint32_t *sdraw_id, uint32_t *sdraw_first_job,
                              const uint32_t *sdraw_rank, uint32_t *extra_edge_draw) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,30 +276,34 @@ __global__ void list_draws_k(const vkb_draw *draws, const uint32_t *sbase, const
         for (int k = 0; k < 4; k++) extra_edge_draw[4 * r + k] = i;
     }
 }
-__global__ void stroke_flags_k(const vkb_draw *draws, const vkb_stroke *strokes, uint32_t n, uint32_t *is_sdraw, uint32_t *any_dash) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    vkb_draw d = draws[i];
-    bool     s = d.kind == VKB_DRAW_STROKE && d.n_subpaths;
-    is_sdraw[i] = s ? 1u : 0u;
-    if (s && strokes[d.xform_stroke >> 16].dash_count) *any_dash = 1u;
-}
 
 int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     const auto t_begin = std::chrono::steady_clock::now();
     cudaSetDevice(d->ordinal);
     cudaStream_t st = d->stream;
+    finish_pending(d);
     // the previous flush may still be reading the staging area
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
+    // what the job tables will hold is a function of the recorded draws alone: counted here, no read-back
     d->has_clip_draws = d->has_stencil_ops = false;
     d->stencil_after = 0;
+    d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
+    d->any_dash = false;
     for (const vkb_draw &dr : b.draws) {
         if (dr.kind == VKB_DRAW_CLIP) { d->has_clip_draws = d->has_stencil_ops = true; d->stencil_after = 1; }
         else if (dr.kind == VKB_DRAW_STENCIL) {
             d->has_stencil_ops = true;
             d->stencil_after   = (dr.rule_pattern & 0xFF) == VKB_RULE_ST_CLEAR ? 2 : 1;
         }
+        if (dr.kind == VKB_DRAW_FILL || dr.kind == VKB_DRAW_CLIP) d->n_fjobs += dr.n_subpaths;
+        else if (dr.kind == VKB_DRAW_STROKE) {
+            d->n_sjobs += dr.n_subpaths;
+            if (dr.n_subpaths) {
+                d->n_sdraws++;
+                if (b.strokes[dr.xform_stroke >> 16].dash_count) d->any_dash = true;
+            }
+        } else d->n_extra += 4;
     }
 
     struct Src { DevBuf *dst; const void *p; size_t bytes; bool pinned; };
@@ -302,24 +342,16 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     d->fcnt.ensure((size_t)(nd + 1) * 4, st); d->scnt.ensure((size_t)(nd + 1) * 4, st); d->pcnt.ensure((size_t)(nd + 1) * 4, st);
     d->srank.ensure((size_t)(nd + 1) * 4, st);
     d->totals.ensure(16 * 8, st);
-    uint32_t *tot = d->totals.as<uint32_t>();  // [24..28) as u32: fill jobs, stroke jobs, paint draws, stroke draws, any dash
-    VKB_CUDA_OK(cudaMemsetAsync(tot + 24, 0, 5 * 4, st));
-    d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
-    d->any_dash = false;
     if (nd) {
         draw_tables_k<<<vkb_div_up(nd, 256), 256, 0, st>>>(d->draws.as<vkb_draw>(), nd, d->paints.as<vkb_paint>(), d->fcnt.as<uint32_t>(),
-                                                          d->scnt.as<uint32_t>(), d->pcnt.as<uint32_t>());
+                                                          d->scnt.as<uint32_t>(), d->pcnt.as<uint32_t>(), d->srank.as<uint32_t>());
         VKB_LAUNCHED();
-        stroke_flags_k<<<vkb_div_up(nd, 256), 256, 0, st>>>(d->draws.as<vkb_draw>(), d->strokes.as<vkb_stroke>(), nd, d->srank.as<uint32_t>(), tot + 28);
-        VKB_LAUNCHED();
-        vkb_exclusive_scan<uint32_t, uint32_t>(d->fcnt.as<uint32_t>(), d->fcnt.as<uint32_t>(), nd, tot + 24, d->scan, st);
-        vkb_exclusive_scan<uint32_t, uint32_t>(d->scnt.as<uint32_t>(), d->scnt.as<uint32_t>(), nd, tot + 25, d->scan, st);
-        vkb_exclusive_scan<uint32_t, uint32_t>(d->pcnt.as<uint32_t>(), d->pcnt.as<uint32_t>(), nd, tot + 26, d->scan, st);
-        vkb_exclusive_scan<uint32_t, uint32_t>(d->srank.as<uint32_t>(), d->srank.as<uint32_t>(), nd, tot + 27, d->scan, st);
-        VKB_CUDA_OK(cudaMemcpyAsync(d->readback, tot + 24, 5 * 4, cudaMemcpyDeviceToHost, st));
-        VKB_CUDA_OK(cudaStreamSynchronize(st));
-        const uint32_t *rb = (const uint32_t *)d->readback;
-        d->n_fjobs = rb[0]; d->n_sjobs = rb[1]; d->n_extra = rb[2] * 4; d->n_sdraws = rb[3]; d->any_dash = rb[4] != 0;
+        if (d->n_fjobs) vkb_exclusive_scan<uint32_t, uint32_t>(d->fcnt.as<uint32_t>(), d->fcnt.as<uint32_t>(), nd, nullptr, d->scan, st);
+        if (d->n_sjobs) {
+            vkb_exclusive_scan<uint32_t, uint32_t>(d->scnt.as<uint32_t>(), d->scnt.as<uint32_t>(), nd, nullptr, d->scan, st);
+            vkb_exclusive_scan<uint32_t, uint32_t>(d->srank.as<uint32_t>(), d->srank.as<uint32_t>(), nd, nullptr, d->scan, st);
+        }
+        if (d->n_extra) vkb_exclusive_scan<uint32_t, uint32_t>(d->pcnt.as<uint32_t>(), d->pcnt.as<uint32_t>(), nd, nullptr, d->scan, st);
         d->fjob_draw.ensure((size_t)(d->n_fjobs + 1) * 4, st); d->fjob_sp.ensure((size_t)(d->n_fjobs + 1) * 4, st);
         d->sjob_draw.ensure((size_t)(d->n_sjobs + 1) * 4, st); d->sjob_sp.ensure((size_t)(d->n_sjobs + 1) * 4, st);
         d->sdraw_id.ensure((size_t)(d->n_sdraws + 1) * 4, st); d->sdraw_first_job.ensure((size_t)(d->n_sdraws + 1) * 4, st);
@@ -340,10 +372,7 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
                                                              d->extra_edge_draw.as<uint32_t>());
             VKB_LAUNCHED();
         }
-    } else {
-        VKB_CUDA_OK(cudaEventSynchronize(d->ev_h2d));
     }
-    d->extra_edges.ensure((size_t)d->n_extra * 16 + 16, st);
     d->ms_host_upload = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return g_cuda_failed;
 }
@@ -361,12 +390,6 @@ void vkb_host_free(void *p) {
     else { cudaGetLastError(); free(p); }
 }
 
-static uint64_t read_total(vkb_device_impl *d, const void *dev_ptr, size_t bytes) {
-    d->readback[0] = 0;
-    VKB_CUDA_OK(cudaMemcpyAsync(d->readback, dev_ptr, bytes, cudaMemcpyDeviceToHost, d->stream));
-    VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
-    return d->readback[0];
-}
 template <class T> static void download(vkb_device_impl *d, std::vector<T> *out, const void *src, size_t n) {
     if (!out) return;
     out->resize(n);
@@ -378,97 +401,162 @@ __global__ void gather_first_items_k(const uint32_t *first_job, const uint32_t *
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = job_base[first_job[i]];
 }
-__global__ void paint_rect_edges_k(vkb_edge *e, uint32_t n_rects, int32_t W, int32_t H) {
+// the four edges of a rectangle one tile larger than the surface for every whole-surface draw; they follow the fill and
+// stroke edges, whose number only the device knows
+__global__ void extra_rect_edges_k(vkb_edge *edges, uint32_t *edge_draw, const uint32_t *extra_edge_draw, uint32_t n_rects, int32_t W, int32_t H,
+                                   const vkb_counts *C) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rects) return;
-    const int32_t x0 = -VKB_TILE_FX, y0 = -VKB_TILE_FX, x1 = W * 256 + VKB_TILE_FX, y1 = H * 256 + VKB_TILE_FX;
+    if (i >= n_rects || C->overflow) return;
+    const uint32_t base = C->n[VKC_FILL] + 3u * C->n[VKC_TRIS];
+    vkb_edge      *e    = edges + base;
+    const int32_t  x0 = -VKB_TILE_FX, y0 = -VKB_TILE_FX, x1 = W * 256 + VKB_TILE_FX, y1 = H * 256 + VKB_TILE_FX;
     e[4 * i]     = vkb_edge{x0, y0, x1, y0};
     e[4 * i + 1] = vkb_edge{x1, y0, x1, y1};
     e[4 * i + 2] = vkb_edge{x1, y1, x0, y1};
     e[4 * i + 3] = vkb_edge{x0, y1, x0, y0};
+    for (int k = 0; k < 4; k++) edge_draw[base + 4 * i + k] = extra_edge_draw[4 * i + k];
 }
 
-// binning + fine pass over d->edges / d->edge_draw (n_edges entries, nd draws, paints/grads already on the device)
-static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc sd, uint32_t nd, uint64_t n_edges, vkb_capture *cap, vkb_stats &S,
-                        vkb_stats *stats, const vkb_draw *draws) {  // draws: device pointer, or null for a raw edge list (no clip draws then)
+// ---- commit kernels: one thread turns the raw totals of a producing scan into checked counts (dev_util.cuh: vkb_counts) ----
+__global__ void commit_flatten_k(vkb_counts *C, const uint64_t *totals, uint32_t has_fill, uint32_t has_stroke) {
+    if (C->overflow) return;
+    vkc_commit(C, VKC_POINTS, (uint32_t)totals[0]);
+    vkc_commit(C, VKC_FILL, has_fill ? (uint32_t)totals[1] : 0u);
+    vkc_commit(C, VKC_SITEMS, has_stroke ? (uint32_t)totals[2] : 0u);
+}
+__global__ void commit_stroke_k(vkb_counts *C, const uint64_t *totals, uint32_t has_stroke, uint32_t n_extra) {
+    if (C->overflow) return;
+    const unsigned long long tot = has_stroke ? totals[3] : 0ull;
+    const uint32_t nv = (uint32_t)(tot & 0xffffffffull), ni = (uint32_t)(tot >> 32);
+    vkc_commit(C, VKC_VERTS, nv);
+    vkc_commit(C, VKC_INDS, ni);
+    vkc_commit(C, VKC_TRIS, ni / 3);
+    vkc_commit(C, VKC_EDGES, C->n[VKC_FILL] + 3u * (ni / 3) + n_extra);
+}
+__global__ void commit_pt_k(vkb_counts *C, const uint64_t *totals) {
+    if (C->overflow) return;
+    vkc_commit(C, VKC_PT, (uint32_t)(totals[4] & 0xffffffffull));
+    vkc_commit(C, VKC_ROWS, (uint32_t)(totals[4] >> 32));
+}
+__global__ void commit_one_k(vkb_counts *C, int idx, const uint32_t *raw) {
+    if (C->overflow) return;
+    vkc_commit(C, idx, *raw);
+}
+__global__ void set_edge_count_k(vkb_counts *C, uint32_t n) {  // raw edge lists (vkb_winding_raw)
+    for (int i = 0; i < VKC_N; i++) { C->n[i] = 0; C->need[i] = 0; }
+    C->overflow = 0;
+    C->n[VKC_EDGES] = n;
+}
+
+// Capacities are grow-only per device: whatever an earlier flush needed (plus slack) is what the next one is launched
+// with, so a steady stream of similar frames never overflows; the first flush of a new kind starts from guesses.
+static void plan_caps(vkb_device_impl *d, const SurfaceDesc &sd) {
+    uint32_t *c = d->capv;
+    auto up = [&](int i, uint64_t v) { if (v > 0xfffffff0ull) v = 0xfffffff0ull; if (c[i] < v) c[i] = (uint32_t)v; };
+    up(VKC_POINTS, (uint64_t)d->n_elems * 2 + 4096);
+    if (d->n_fjobs) up(VKC_FILL, (uint64_t)c[VKC_POINTS]);
+    if (d->n_sjobs) {
+        up(VKC_SITEMS, (uint64_t)c[VKC_POINTS]);
+        up(VKC_VERTS, (uint64_t)c[VKC_SITEMS] * 6 + 64);
+        up(VKC_INDS, (uint64_t)c[VKC_SITEMS] * 18 + 192);
+    }
+    up(VKC_TRIS, (uint64_t)c[VKC_INDS] / 3);
+    up(VKC_EDGES, (uint64_t)c[VKC_FILL] + 3ull * c[VKC_TRIS] + d->n_extra);
+    const uint64_t n_tiles = (uint64_t)sd.tiles_x * sd.tiles_y;
+    up(VKC_PT, (uint64_t)d->n_draws * 8 + ((uint64_t)d->n_extra / 4 + (d->has_clip_draws ? 2 : 0)) * n_tiles + 1024);
+    up(VKC_ROWS, c[VKC_PT]);
+    up(VKC_NE, c[VKC_PT]);   // a subset of the path-tiles: cannot overflow on its own
+    up(VKC_TE, (uint64_t)c[VKC_EDGES] * 2 + 1024);
+}
+static void grow_caps_from_need(vkb_device_impl *d, const vkb_counts &h) {
+    for (int i = 0; i < VKC_N; i++)
+        if (h.overflow & (1u << i)) {
+            uint64_t v = (uint64_t)h.need[i] + h.need[i] / 4 + 64;
+            if (v > 0xfffffff0ull) v = 0xfffffff0ull;
+            if (d->capv[i] < v) d->capv[i] = (uint32_t)v;
+        }
+}
+
+// binning + fine pass over d->edges / d->edge_draw (count C->n[VKC_EDGES], nd draws, paints / grads already on the device)
+static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc sd, uint32_t nd, vkb_capture *cap, const vkb_draw *draws,
+                                 DevBuf &wbuf) {  // draws: device pointer, or null for a raw edge list (no clip draws then)
     cudaStream_t st     = d->stream;
     uint64_t    *totals = d->totals.as<uint64_t>();
+    vkb_counts  *C      = d->counts.as<vkb_counts>();
+    const uint32_t *cv  = d->capv;
     const uint32_t samples = sd.samples;
     vkb_edge *edges = d->edges.as<vkb_edge>();
     uint32_t *edraw = d->edge_draw.as<uint32_t>();
     // ---- 5. binning ----
-    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[3], st));
+    VKB_EVENT_RECORD(d, d->ev_stage[3]);
     const uint32_t n_tiles = sd.tiles_x * sd.tiles_y;
     d->draw_bbox.ensure((size_t)nd * 16, st);
     d->draw_rect.ensure((size_t)nd * 16, st);
     d->draw_counts.ensure((size_t)(nd + 1) * 8, st);
     d->draw_ptbase.ensure((size_t)(nd + 1) * 4, st);
     d->draw_rowbase.ensure((size_t)(nd + 1) * 4, st);
-    vkb_launch_draw_bbox(edges, edraw, n_edges, nd, d->draw_bbox.as<int32_t>(), st);
+    vkb_launch_draw_bbox(edges, edraw, cv[VKC_EDGES], C, nd, d->draw_bbox.as<int32_t>(), st);
     unsigned long long *dc = d->draw_counts.as<unsigned long long>();
     const bool clip_draws = draws && d->has_clip_draws, stencil_ops = draws && d->has_stencil_ops;
     vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), clip_draws ? draws : nullptr, nd, sd, d->draw_rect.as<int32_t>(), dc, st);
     vkb_exclusive_scan<unsigned long long, unsigned long long>(dc, dc, nd, (unsigned long long *)(totals + 4), d->scan, st);
     vkb_launch_split_bases(dc, nd, d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), st);
-    unsigned long long tr = read_total(d, totals + 4, 8);
-    const uint32_t     n_pt = (uint32_t)(tr & 0xffffffffull);
-    S.n_path_tiles = n_pt;
+    commit_pt_k<<<1, 1, 0, st>>>(C, totals);
+    VKB_LAUNCHED();
 
-    d->pt_count.ensure((size_t)(n_pt + 1) * 4, st);
-    d->pt_backdrop.ensure((size_t)(n_pt + 1) * 4, st);
-    d->pt_flags.ensure((size_t)(n_pt + 1) * 4, st);
-    d->pt_slot.ensure((size_t)(n_pt + 1) * 4, st);
-    VKB_CUDA_OK(cudaMemsetAsync(d->pt_count.p, 0, (size_t)n_pt * 4, st));
-    VKB_CUDA_OK(cudaMemsetAsync(d->pt_backdrop.p, 0, (size_t)n_pt * 4, st));
-    vkb_launch_bin_count(edges, edraw, n_edges, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_count.as<uint32_t>(),
+    const uint32_t cap_pt = cv[VKC_PT], cap_ne = cv[VKC_NE];
+    d->pt_count.ensure((size_t)(cap_pt + 1) * 4, st);
+    d->pt_backdrop.ensure((size_t)(cap_pt + 1) * 4, st);
+    d->pt_flags.ensure((size_t)(cap_pt + 1) * 4, st);
+    d->pt_slot.ensure((size_t)(cap_pt + 1) * 4, st);
+    VKB_CUDA_OK(cudaMemsetAsync(d->pt_count.p, 0, (size_t)cap_pt * 4, st));
+    VKB_CUDA_OK(cudaMemsetAsync(d->pt_backdrop.p, 0, (size_t)cap_pt * 4, st));
+    vkb_launch_bin_count(edges, edraw, cv[VKC_EDGES], C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_count.as<uint32_t>(),
                          d->pt_backdrop.as<int32_t>(), st);
-    vkb_launch_backdrop_prefix(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd,
-                               (unsigned long long *)(totals + 4), d->pt_backdrop.as<int32_t>(), st);
-    vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), n_pt, draws, d->draw_ptbase.as<uint32_t>(), nd, clip_draws,
+    vkb_launch_backdrop_prefix(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd, cv[VKC_ROWS], C,
+                               d->pt_backdrop.as<int32_t>(), st);
+    vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), cap_pt, C, draws, d->draw_ptbase.as<uint32_t>(), nd, clip_draws,
                         d->pt_flags.as<uint32_t>(), st);
     // pt_slot doubles as the exclusive scan of the flags until the sorted slots overwrite it
-    d->sorted_cnt.ensure((size_t)(n_pt + 1) * 4, st);
+    d->sorted_cnt.ensure((size_t)(cap_pt + 1) * 4, st);
     uint32_t *flag_scan = d->sorted_cnt.as<uint32_t>();
-    vkb_exclusive_scan<uint32_t, uint32_t>(d->pt_flags.as<uint32_t>(), flag_scan, n_pt, (uint32_t *)(totals + 5), d->scan, st);
-    const uint32_t n_ne = n_pt ? (uint32_t)read_total(d, totals + 5, 4) : 0;
-    S.n_nonempty = n_ne;
+    vkb_exclusive_scan<uint32_t, uint32_t>(d->pt_flags.as<uint32_t>(), flag_scan, 0, (uint32_t *)(totals + 5), d->scan, st, C, VKC_PT, cap_pt, VKC_NE);
 
-    d->keys.ensure((size_t)(n_ne + 1) * 4, st);
-    d->vals.ensure((size_t)(n_ne + 1) * 4, st);
-    d->pt_draw.ensure((size_t)(n_ne + 1) * 4, st);
-    d->cursor.ensure((size_t)(n_ne + 1) * 4, st);
-    d->hdr.ensure((size_t)(n_ne + 1) * 32, st);
+    d->keys.ensure((size_t)(cap_ne + 1) * 4, st);
+    d->vals.ensure((size_t)(cap_ne + 1) * 4, st);
+    d->pt_draw.ensure((size_t)(cap_ne + 1) * 4, st);
+    d->cursor.ensure((size_t)(cap_ne + 1) * 4, st);
+    d->hdr.ensure((size_t)(cap_ne + 1) * 32, st);
     d->tile_first.ensure((size_t)n_tiles * 4 + 16, st);
     d->tile_end.ensure((size_t)n_tiles * 4 + 16, st);
-    vkb_launch_pt_compact(d->pt_flags.as<uint32_t>(), flag_scan, n_pt, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), nd, sd,
+    vkb_launch_pt_compact(d->pt_flags.as<uint32_t>(), flag_scan, cap_pt, C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), nd, sd,
                           d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), d->pt_draw.as<uint32_t>(), st);
     int bits = 1;
     while ((1u << bits) < n_tiles && bits < 32) bits++;
-    vkb_radix_sort(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), n_ne, bits, d->sort, st);
+    vkb_radix_sort(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), cap_ne, bits, d->sort, st, C, VKC_NE);
     // edge offsets in sorted (tile-major, draw-ordered) order
     uint32_t *eoff = d->cursor.as<uint32_t>();  // scan output; cursor proper is a separate zeroed array below
-    DevBuf   &cur2 = d->winding;                // reuse: winding capture buffer is only needed after scatter
-    cur2.ensure((size_t)(n_ne + 1) * 4, st);
+    DevBuf   &cur2 = d->cursor2;
+    cur2.ensure((size_t)(cap_ne + 1) * 4, st);
     {
         // sorted_cnt currently holds flag_scan which headers_k still needs: put the sorted counts in pt_flags instead
         uint32_t *scnt = d->pt_flags.as<uint32_t>();
-        vkb_launch_sorted_counts(d->vals.as<uint32_t>(), n_ne, d->pt_count.as<uint32_t>(), scnt, d->pt_slot.as<uint32_t>(), st);
-        vkb_exclusive_scan<uint32_t, uint32_t>(scnt, eoff, n_ne, (uint32_t *)(totals + 6), d->scan, st);
+        vkb_launch_sorted_counts(d->vals.as<uint32_t>(), cap_ne, C, d->pt_count.as<uint32_t>(), scnt, d->pt_slot.as<uint32_t>(), st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(scnt, eoff, 0, (uint32_t *)(totals + 6), d->scan, st, C, VKC_NE, cap_ne, VKC_TE);
     }
-    const uint32_t n_te = n_ne ? (uint32_t)read_total(d, totals + 6, 4) : 0;
-    S.n_tile_edges = n_te;
-    d->tile_edges.ensure((size_t)(n_te + 1) * 16, st);
+    d->tile_edges.ensure((size_t)(cv[VKC_TE] + 1) * 16, st);
     VKB_CUDA_OK(cudaMemsetAsync(d->tile_first.p, 0, (size_t)n_tiles * 4, st));
     VKB_CUDA_OK(cudaMemsetAsync(d->tile_end.p, 0, (size_t)n_tiles * 4, st));
-    vkb_launch_headers(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), n_ne, d->pt_draw.as<uint32_t>(), flag_scan, d->pt_backdrop.as<int32_t>(),
+    vkb_launch_headers(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), cap_ne, C, d->pt_draw.as<uint32_t>(), flag_scan, d->pt_backdrop.as<int32_t>(),
                        d->pt_count.as<uint32_t>(), eoff, d->paints.as<vkb_paint>(), d->hdr.as<int4>(), d->tile_first.as<uint32_t>(), d->tile_end.as<uint32_t>(), st);
-    VKB_CUDA_OK(cudaMemsetAsync(cur2.p, 0, (size_t)n_ne * 4, st));
-    vkb_launch_bin_scatter(edges, edraw, n_edges, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_slot.as<uint32_t>(), eoff,
+    VKB_CUDA_OK(cudaMemsetAsync(cur2.p, 0, (size_t)cap_ne * 4, st));
+    vkb_launch_bin_scatter(edges, edraw, cv[VKC_EDGES], C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_slot.as<uint32_t>(), eoff,
                            cur2.as<uint32_t>(), d->tile_edges.as<vkb_edge>(), st);
 
     // ---- 6. fine pass ----
     FineArgs fa;
     fa.sd = sd;
+    fa.counts = C;
     fa.tile_first = d->tile_first.as<uint32_t>(); fa.tile_end = d->tile_end.as<uint32_t>();
     fa.hdr = d->hdr.as<int4>(); fa.tile_edges = d->tile_edges.as<vkb_edge>();
     fa.paints = d->paints.as<vkb_paint>(); fa.grads = d->grads.as<vkb_gradient>();
@@ -492,77 +580,64 @@ static int bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc 
         if (stencil_ops && d->stencil_after) surf->stencil_live = d->stencil_after == 1;
     }
     fa.winding_out = nullptr; fa.winding_draw = 0;
-    DevBuf wbuf;
     if (cap && cap->winding) {
         size_t wb = (size_t)sd.width * sd.height * (samples ? samples : 1) * 4;  // analytic mode: one float area per pixel
         wbuf.ensure(wb, st);
         VKB_CUDA_OK(cudaMemsetAsync(wbuf.p, 0, wb, st));
         fa.winding_out = wbuf.as<int32_t>(); fa.winding_draw = cap->winding_draw;
     }
-    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[4], st));
-    VKB_CUDA_OK(cudaEventRecord(d->ev_fine0, st));
+    VKB_EVENT_RECORD(d, d->ev_stage[4]);
+    if (d->capturing) d->graph_fine_events = cudaEventRecordWithFlags(d->ev_fine0, st, cudaEventRecordExternal) == cudaSuccess;
+    else VKB_EVENT_RECORD(d, d->ev_fine0);
     vkb_launch_fine(fa, st);
-    VKB_CUDA_OK(cudaEventRecord(d->ev_fine1, st));
-    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[5], st));
+    if (d->capturing) d->graph_fine_events = d->graph_fine_events && cudaEventRecordWithFlags(d->ev_fine1, st, cudaEventRecordExternal) == cudaSuccess;
+    else VKB_EVENT_RECORD(d, d->ev_fine1);
+    VKB_EVENT_RECORD(d, d->ev_stage[5]);
     surf->known_clear = false;
-    VKB_CUDA_OK(cudaEventRecord(d->ev_end, st));
-    if (cap && cap->winding) {
-        VKB_CUDA_OK(cudaMemcpyAsync(cap->winding, wbuf.p, (size_t)sd.width * sd.height * (samples ? samples : 1) * 4, cudaMemcpyDeviceToHost, st));
-        VKB_CUDA_OK(cudaStreamSynchronize(st));
-        wbuf.release();
-    }
-    if (stats) {
-        VKB_CUDA_OK(cudaStreamSynchronize(st));
-        cudaEventElapsedTime(&S.ms_total, d->ev_begin, d->ev_end);
-        cudaEventElapsedTime(&S.ms_fine, d->ev_fine0, d->ev_fine1);
-        if (S.ms_stage[0] >= 0.f)
-            for (int i = 0; i < VKB_N_STAGES; i++) cudaEventElapsedTime(&S.ms_stage[i], d->ev_stage[i], d->ev_stage[i + 1]);
-        *stats = S;
-    }
-    return g_cuda_failed;
 }
 
-int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats) {
-    cudaSetDevice(d->ordinal);
+// the capacities of this attempt travel as kernel arguments (no staging copy to wait on); every count starts at zero
+struct CapArgs { uint32_t v[16]; };
+__global__ void counts_reset_k(vkb_counts *C, CapArgs caps) {
+    const uint32_t i = threadIdx.x;
+    if (i < 16) { C->n[i] = 0; C->need[i] = 0; C->cap[i] = caps.v[i]; }
+    if (i == 0) C->overflow = 0;
+}
+static void enqueue_counts_reset(vkb_device_impl *d) {
+    d->counts.ensure(sizeof(vkb_counts), d->stream);
+    CapArgs a;
+    memcpy(a.v, d->capv, sizeof a.v);
+    counts_reset_k<<<1, 32, 0, d->stream>>>(d->counts.as<vkb_counts>(), a);
+    VKB_LAUNCHED();
+}
+
+// one attempt at the whole pipeline for the resident batch; no host round trip
+static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc sd, vkb_capture *cap, DevBuf &wbuf) {
     cudaStream_t st = d->stream;
-    vkb_stats    S;
-    memset(&S, 0, sizeof S);
-    S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes; S.ms_host_upload = d->ms_host_upload;
-    SurfaceDesc sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE, surf->full_h, surf->origin_y};
-    VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
-    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[0], st));
+    plan_caps(d, sd);
+    const uint32_t *cv = d->capv;
+    enqueue_counts_reset(d);
+    vkb_counts *C = d->counts.as<vkb_counts>();
+    VKB_EVENT_RECORD(d, d->ev_stage[0]);
     d->totals.ensure(16 * 8, st);
     uint64_t *totals = d->totals.as<uint64_t>();
+    VKB_CUDA_OK(cudaMemsetAsync(totals, 0, 16 * 8, st));
 
     // ---- 1. flatten: count -> scan -> emit ----
-    uint32_t n_points = 0;
     d->elem_cnt.ensure((size_t)(d->n_elems + 1) * 4, st);
     d->sp_first.ensure((size_t)(d->n_sp + 1) * 4, st);
     d->sp_count.ensure((size_t)(d->n_sp + 1) * 4, st);
+    d->pts.ensure((size_t)(cv[VKC_POINTS] + 1) * 8, st);
+    d->ptflags.ensure((size_t)cv[VKC_POINTS] + 16, st);
+    d->fjob_base.ensure((size_t)(d->n_fjobs + 1) * 4, st);
+    d->sjob_base.ensure((size_t)(d->n_sjobs + 1) * 4, st);
     if (d->n_elems) {
         vkb_launch_flatten_count(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->elem_cnt.as<uint32_t>(), d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals, d->scan, st);
-        n_points = (uint32_t)read_total(d, totals, 4);
-        d->pts.ensure((size_t)(n_points + 1) * 8, st);
-        d->ptflags.ensure((size_t)n_points + 16, st);
-        vkb_launch_flatten_emit(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), d->pts.as<float2>(),
-                                d->ptflags.as<uint8_t>(), st);
         vkb_launch_subpath_ranges(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals,
                                   d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), st);
     }
-    S.n_points = n_points;
-    if (cap) {
-        download(d, cap->points, d->pts.p, (size_t)n_points * 2);
-        download(d, cap->ptflags, d->ptflags.p, (size_t)n_points);
-        download(d, cap->sp_first, d->sp_first.p, d->n_sp);
-        download(d, cap->sp_count, d->sp_count.p, d->n_sp);
-    }
-
-    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[1], st));
-    // ---- 2. job sizes: fill jobs need > 2 points, stroke jobs >= 2 ----
-    uint32_t n_fill = 0, n_sitems = 0;
-    d->fjob_base.ensure((size_t)(d->n_fjobs + 1) * 4, st);
-    d->sjob_base.ensure((size_t)(d->n_sjobs + 1) * 4, st);
+    // ---- 2. job sizes: fill jobs need > 2 points, stroke jobs >= 2 (point counts come from the count scan alone) ----
     if (d->n_fjobs) {
         vkb_launch_job_counts(d->fjob_sp.as<uint32_t>(), d->n_fjobs, d->sp_count.as<uint32_t>(), 3, d->fjob_base.as<uint32_t>(), st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->fjob_base.as<uint32_t>(), d->fjob_base.as<uint32_t>(), d->n_fjobs, (uint32_t *)(totals + 1), d->scan, st);
@@ -571,87 +646,231 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
         vkb_launch_job_counts(d->sjob_sp.as<uint32_t>(), d->n_sjobs, d->sp_count.as<uint32_t>(), 2, d->sjob_base.as<uint32_t>(), st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->sjob_base.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, (uint32_t *)(totals + 2), d->scan, st);
     }
-    if (d->n_fjobs || d->n_sjobs) {
-        VKB_CUDA_OK(cudaMemcpyAsync(d->readback, totals, 24, cudaMemcpyDeviceToHost, st));
-        VKB_CUDA_OK(cudaStreamSynchronize(st));
-        n_fill   = d->n_fjobs ? (uint32_t)d->readback[1] : 0;
-        n_sitems = d->n_sjobs ? (uint32_t)d->readback[2] : 0;
-    }
-    S.n_fill_edges = n_fill; S.n_stroke_items = n_sitems;
+    commit_flatten_k<<<1, 1, 0, st>>>(C, totals, d->n_fjobs ? 1u : 0u, d->n_sjobs ? 1u : 0u);
+    VKB_LAUNCHED();
+    if (d->n_elems)
+        vkb_launch_flatten_emit(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), d->pts.as<float2>(),
+                                d->ptflags.as<uint8_t>(), C, st);
+    VKB_EVENT_RECORD(d, d->ev_stage[1]);
 
     // ---- 3. strokes: (dash phase scan) -> count -> scan -> emit ----
-    uint32_t n_verts = 0, n_inds = 0;
-    if (n_sitems) {
+    const uint32_t cap_items = d->n_sjobs ? cv[VKC_SITEMS] : 0;
+    if (cap_items) {
         StrokeArgs sa = {d->pts.as<float2>(), d->ptflags.as<uint8_t>(), d->draws.as<vkb_draw>(), d->strokes.as<vkb_stroke>(), d->dashes.as<float>(), d->sjob_draw.as<uint32_t>(),
                          d->sjob_sp.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(),
-                         d->subpaths.as<vkb_subpath>(), nullptr, n_sitems};
+                         d->subpaths.as<vkb_subpath>(), nullptr, cap_items, C};
         if (d->any_dash) {
-            d->seglen.ensure((size_t)(n_sitems + 1) * 4, st);
-            d->cum.ensure((size_t)(n_sitems + 1) * 8, st);
+            d->seglen.ensure((size_t)(cap_items + 1) * 4, st);
+            d->cum.ensure((size_t)(cap_items + 1) * 8, st);
             vkb_launch_stroke_seglen(sa, d->seglen.as<float>(), st);
-            vkb_exclusive_scan<float, double>(d->seglen.as<float>(), d->cum.as<double>(), (uint64_t)n_sitems + 1, nullptr, d->scan, st);
+            vkb_exclusive_scan<float, double>(d->seglen.as<float>(), d->cum.as<double>(), 1, nullptr, d->scan, st, C, VKC_SITEMS, (uint64_t)cap_items + 1);
             sa.cum = d->cum.as<double>();
         }
-        d->item_counts.ensure((size_t)(n_sitems + 1) * 8, st);
+        d->item_counts.ensure((size_t)(cap_items + 1) * 8, st);
         d->job_inverse.ensure((size_t)(d->n_sjobs + 1) * 4, st);
         VKB_CUDA_OK(cudaMemsetAsync(d->job_inverse.p, 0, (size_t)d->n_sjobs * 4, st));
         unsigned long long *ic = d->item_counts.as<unsigned long long>();
         vkb_launch_stroke_count(sa, ic, st);
-        vkb_exclusive_scan<unsigned long long, unsigned long long>(ic, ic, n_sitems, (unsigned long long *)(totals + 3), d->scan, st);
-        unsigned long long tot = read_total(d, totals + 3, 8);
-        n_verts = (uint32_t)(tot & 0xffffffffull); n_inds = (uint32_t)(tot >> 32);
-        d->verts.ensure((size_t)(n_verts + 1) * 8, st);
-        d->inds.ensure((size_t)(n_inds + 3) * 4, st);
-        vkb_launch_stroke_emit(sa, ic, tot, d->verts.as<float2>(), d->inds.as<uint32_t>(), d->job_inverse.as<uint32_t>(), st);
-        if (cap) {
-            download(d, cap->verts, d->verts.p, (size_t)n_verts * 2);
-            download(d, cap->inds, d->inds.p, (size_t)n_inds);
-        }
+        vkb_exclusive_scan<unsigned long long, unsigned long long>(ic, ic, 0, (unsigned long long *)(totals + 3), d->scan, st, C, VKC_SITEMS, cap_items);
+        commit_stroke_k<<<1, 1, 0, st>>>(C, totals, 1u, d->n_extra);
+        VKB_LAUNCHED();
+        d->verts.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
+        d->inds.ensure((size_t)(cv[VKC_INDS] + 3) * 4, st);
+        vkb_launch_stroke_emit(sa, ic, d->verts.as<float2>(), d->inds.as<uint32_t>(), d->job_inverse.as<uint32_t>(), st);
+    } else {
+        commit_stroke_k<<<1, 1, 0, st>>>(C, totals, 0u, d->n_extra);
+        VKB_LAUNCHED();
     }
-    S.n_verts = n_verts; S.n_inds = n_inds;
 
     // ---- 4. edges ----
-    VKB_CUDA_OK(cudaEventRecord(d->ev_stage[2], st));
-    const uint32_t n_tris  = n_inds / 3;
-    const uint64_t n_edges = (uint64_t)n_fill + 3ull * n_tris + d->n_extra;
-    S.n_edges = n_edges;
-    d->edges.ensure((n_edges + 1) * 16, st);
-    d->edge_draw.ensure((n_edges + 1) * 4, st);
+    VKB_EVENT_RECORD(d, d->ev_stage[2]);
+    d->edges.ensure(((size_t)cv[VKC_EDGES] + 1) * 16, st);
+    d->edge_draw.ensure(((size_t)cv[VKC_EDGES] + 1) * 4, st);
     vkb_edge *edges = d->edges.as<vkb_edge>();
     uint32_t *edraw = d->edge_draw.as<uint32_t>();
     vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
-                          d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), n_fill, sd, edges, edraw, st);
-    if (n_tris) {
+                          d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->n_fjobs ? cv[VKC_FILL] : 0, C, sd, edges, edraw, st);
+    if (cap_items && d->n_sdraws) {
         // first work item of every stroke draw (to map a triangle back to its draw)
         d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
         gather_first_items_k<<<vkb_div_up(d->n_sdraws, 256), 256, 0, st>>>(d->sdraw_first_job.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
                                                                           d->sdraw_first_item.as<uint32_t>());
         VKB_LAUNCHED();
-        vkb_launch_tri_edges(d->verts.as<float2>(), n_verts, d->inds.as<uint32_t>(), n_tris, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
-                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges + n_fill, edraw + n_fill, st);
+        vkb_launch_tri_edges(d->verts.as<float2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
+                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, st);
     }
     if (d->n_extra) {
-        paint_rect_edges_k<<<vkb_div_up(d->n_extra / 4, 64), 64, 0, st>>>(edges + n_fill + 3ull * n_tris, d->n_extra / 4, (int32_t)sd.width, (int32_t)sd.height);
+        extra_rect_edges_k<<<vkb_div_up(d->n_extra / 4, 64), 64, 0, st>>>(edges, edraw, d->extra_edge_draw.as<uint32_t>(), d->n_extra / 4, (int32_t)sd.width,
+                                                                         (int32_t)sd.height, C);
         VKB_LAUNCHED();
-        VKB_CUDA_OK(cudaMemcpyAsync(edraw + n_fill + 3ull * n_tris, d->extra_edge_draw.p, (size_t)d->n_extra * 4, cudaMemcpyDeviceToDevice, st));
     }
-    if (cap) {
-        download(d, cap->edges, edges, (size_t)n_edges * 4);
-        download(d, cap->edge_draw, edraw, (size_t)n_edges);
+    if ((cap && cap->geometry_only) || d->n_draws == 0) return;
+    enqueue_bin_and_fine(d, surf, sd, d->n_draws, cap, d->draws.as<vkb_draw>(), wbuf);
+}
+
+// Everything that shapes the launches of a flush besides the data in the buffers.  Two flushes with equal keys issue the
+// same kernels with the same arguments, so the second one can be a replay of a CUDA graph captured from the first: a frame
+// loop that redraws a scene of the same structure pays one graph launch per frame instead of ~40 kernel launches.
+struct FlushKey {
+    uint32_t n_elems, n_sp, n_draws, n_fjobs, n_sjobs, n_sdraws, n_extra;
+    uint32_t flags;  // any_dash | has_clip_draws << 1 | has_stencil_ops << 2 | stencil_after << 3
+    uint32_t capv[16];
+    const void *surf;
+    uint32_t w, h, samples, full_h, origin_y;
+    uint32_t known_clear, stencil_live, stencil_samples, tile_ms_allocated;
+    unsigned long long alloc_generation;
+};
+static_assert(sizeof(FlushKey) <= 256, "FlushKey");
+static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc sd, vkb_capture *cap, DevBuf &wbuf, bool stage_timing) {
+    cudaStream_t st = d->stream;
+    VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
+    if (cap || stage_timing || !d->graphs_enabled) {  // captures download intermediates, stage timing needs events between the kernels
+        enqueue_flush(d, surf, sd, cap, wbuf);
+        d->have_last_key = false;
+        return;
     }
-    if ((cap && cap->geometry_only) || d->n_draws == 0) {
+    plan_caps(d, sd);
+    uint8_t  kbuf[256];
+    memset(kbuf, 0, sizeof kbuf);
+    FlushKey k;
+    memset(&k, 0, sizeof k);
+    k.n_elems = d->n_elems; k.n_sp = d->n_sp; k.n_draws = d->n_draws; k.n_fjobs = d->n_fjobs; k.n_sjobs = d->n_sjobs; k.n_sdraws = d->n_sdraws; k.n_extra = d->n_extra;
+    k.flags = (d->any_dash ? 1u : 0u) | (d->has_clip_draws ? 2u : 0u) | (d->has_stencil_ops ? 4u : 0u) | ((uint32_t)d->stencil_after << 3);
+    memcpy(k.capv, d->capv, sizeof k.capv);
+    k.surf = surf; k.w = sd.width; k.h = sd.height; k.samples = sd.samples; k.full_h = sd.full_height; k.origin_y = sd.origin_y;
+    k.known_clear = surf->known_clear; k.stencil_live = surf->stencil_live; k.stencil_samples = surf->stencil_samples;
+    k.tile_ms_allocated = surf->tile_ms.p != nullptr;
+    k.alloc_generation = g_vkb_alloc_generation;
+    memcpy(kbuf, &k, sizeof k);
+    if (d->graph_exec && !memcmp(kbuf, d->graph_key, sizeof kbuf)) {
+        // replay; the host-side effects of enqueue_flush on the surface flags are re-applied by hand
+        VKB_CUDA_OK(cudaGraphLaunch(d->graph_exec, st));
+        g_vkb_launches += d->graph_launches;
+        d->n_graph_replays++;
+        surf_restore(surf, d->graph_after);
+        return;
+    }
+    if (d->have_last_key && !memcmp(kbuf, d->last_key, sizeof kbuf)) {
+        // second flush of this shape: every buffer already has its size, so nothing allocates while the stream is capturing
+        if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
+        const unsigned long long l0 = g_vkb_launches, gen0 = g_vkb_alloc_generation;
+        const SurfFlags          f0 = surf_flags(surf);
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            d->capturing = true;
+            enqueue_flush(d, surf, sd, nullptr, wbuf);
+            d->capturing = false;
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (e == cudaSuccess && g && gen0 == g_vkb_alloc_generation && cudaGraphInstantiate(&d->graph_exec, g, 0) == cudaSuccess) {
+                d->graph_launches = g_vkb_launches - l0;
+                g_vkb_launches    = l0;
+                d->graph_after    = surf_flags(surf);
+                memcpy(d->graph_key, kbuf, sizeof kbuf);
+                cudaGraphDestroy(g);
+                VKB_CUDA_OK(cudaGraphLaunch(d->graph_exec, st));
+                g_vkb_launches += d->graph_launches;
+                memcpy(d->last_key, kbuf, sizeof kbuf);
+                return;
+            }
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            d->graph_exec = nullptr;
+            g_vkb_launches = l0;
+            surf_restore(surf, f0);
+        } else cudaGetLastError();
+    }
+    enqueue_flush(d, surf, sd, nullptr, wbuf);
+    memcpy(d->last_key, kbuf, sizeof kbuf);
+    d->have_last_key = true;
+}
+
+static void fill_stats(vkb_device_impl *d, const vkb_counts &h, vkb_stats &S, bool with_stages) {
+    S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes; S.ms_host_upload = d->ms_host_upload;
+    S.n_points = h.n[VKC_POINTS]; S.n_fill_edges = h.n[VKC_FILL]; S.n_stroke_items = h.n[VKC_SITEMS];
+    S.n_verts = h.n[VKC_VERTS]; S.n_inds = h.n[VKC_INDS]; S.n_edges = h.n[VKC_EDGES];
+    S.n_path_tiles = h.n[VKC_PT]; S.n_nonempty = h.n[VKC_NE]; S.n_tile_edges = h.n[VKC_TE];
+    cudaEventElapsedTime(&S.ms_total, d->ev_begin, d->ev_end);
+    if (!with_stages && d->graph_exec && d->graph_fine_events) {  // graph replay: only the fine kernel is bracketed (external event nodes)
+        if (cudaEventElapsedTime(&S.ms_fine, d->ev_fine0, d->ev_fine1) != cudaSuccess) { cudaGetLastError(); S.ms_fine = 0.f; }
+    }
+    if (with_stages) {
+        cudaEventElapsedTime(&S.ms_fine, d->ev_fine0, d->ev_fine1);
+        for (int i = 0; i < VKB_N_STAGES; i++) cudaEventElapsedTime(&S.ms_stage[i], d->ev_stage[i], d->ev_stage[i + 1]);
+    }
+}
+
+// Runs the resident batch onto surf.  allow_async: return right after the work is queued; the overflow check (and the
+// replay it may ask for) then happens in finish_pending, which every entry point that touches the device calls first.
+static int run_flush(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats, bool allow_async) {
+    cudaStream_t st = d->stream;
+    SurfaceDesc  sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE, surf->full_h, surf->origin_y};
+    const SurfFlags before = surf_flags(surf);
+    const bool      geometry_only = (cap && cap->geometry_only) || d->n_draws == 0;
+    for (int attempt = 0; attempt < 16; attempt++) {
+        DevBuf wbuf;
+        surf_restore(surf, before);
+        enqueue_flush_maybe_graph(d, surf, sd, cap, wbuf, stats != nullptr && d->stage_timing);
         VKB_CUDA_OK(cudaEventRecord(d->ev_end, st));
+        VKB_CUDA_OK(cudaMemcpyAsync(d->counts_host, d->counts.p, sizeof(vkb_counts), cudaMemcpyDeviceToHost, st));
+        if (allow_async && !cap && !stats) {
+            d->pending = true; d->pending_surf = surf; d->pending_samples = samples; d->pending_before = before;
+            return g_cuda_failed;
+        }
         VKB_CUDA_OK(cudaStreamSynchronize(st));
-        cudaEventElapsedTime(&S.ms_total, d->ev_begin, d->ev_end);
-        if (stats) *stats = S;
+        const vkb_counts &h = *d->counts_host;
+        if (h.overflow) {
+            grow_caps_from_need(d, h);
+            wbuf.release();
+            if (g_cuda_failed) return 1;
+            continue;
+        }
+        if (cap) {
+            download(d, cap->points, d->pts.p, (size_t)h.n[VKC_POINTS] * 2);
+            download(d, cap->ptflags, d->ptflags.p, (size_t)h.n[VKC_POINTS]);
+            download(d, cap->sp_first, d->sp_first.p, d->n_sp);
+            download(d, cap->sp_count, d->sp_count.p, d->n_sp);
+            download(d, cap->verts, d->verts.p, (size_t)h.n[VKC_VERTS] * 2);
+            download(d, cap->inds, d->inds.p, (size_t)h.n[VKC_INDS]);
+            download(d, cap->edges, d->edges.p, (size_t)h.n[VKC_EDGES] * 4);
+            download(d, cap->edge_draw, d->edge_draw.p, (size_t)h.n[VKC_EDGES]);
+            if (cap->winding && !geometry_only) {
+                VKB_CUDA_OK(cudaMemcpyAsync(cap->winding, wbuf.p, (size_t)sd.width * sd.height * (samples ? samples : 1) * 4, cudaMemcpyDeviceToHost, st));
+                VKB_CUDA_OK(cudaStreamSynchronize(st));
+            }
+        }
+        wbuf.release();
+        if (stats) {
+            vkb_stats S;
+            memset(&S, 0, sizeof S);
+            fill_stats(d, h, S, !geometry_only && d->stage_timing);
+            *stats = S;
+        }
         return g_cuda_failed;
     }
-    return bin_and_fine(d, surf, sd, d->n_draws, n_edges, cap, S, stats, d->draws.as<vkb_draw>());
+    fprintf(stderr, "vkvg_b200: intermediate buffers still overflow after 16 attempts\n");
+    return 1;
+}
+static int finish_pending(vkb_device_impl *d) {
+    if (!d->pending) return g_cuda_failed;
+    d->pending = false;
+    VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
+    if (d->counts_host->overflow) {  // rare: first flush of a new kind of scene.  Nothing was written to the surface; replay with room.
+        grow_caps_from_need(d, *d->counts_host);
+        surf_restore(d->pending_surf, d->pending_before);
+        return run_flush(d, d->pending_surf, d->pending_samples, nullptr, nullptr, false);
+    }
+    return g_cuda_failed;
+}
+
+int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats) {
+    cudaSetDevice(d->ordinal);
+    finish_pending(d);
+    return run_flush(d, surf, samples, cap, stats, false);
 }
 
 int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const vkb_batch &b, vkb_capture *cap, vkb_stats *stats) {
     if (vkb_upload(d, b)) return 1;
-    return vkb_render_resident(d, s, samples, cap, stats);
+    return run_flush(d, s, samples, cap, stats, true);
 }
 
 int vkb_device_ordinal(vkb_device_impl *d) { return d->ordinal; }
@@ -660,6 +879,7 @@ int vkb_device_ordinal(vkb_device_impl *d) { return d->ordinal; }
 int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h, uint64_t n, uint32_t w, uint32_t h, int32_t *out) {
     cudaSetDevice(d->ordinal);
     cudaStream_t st = d->stream;
+    finish_pending(d);
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     vkb_surface_impl *surf = vkb_surface_new(d, w, h, h, 0);
     SurfaceDesc sd = {w, h, samples, (w + VKB_TILE - 1) / VKB_TILE, (h + VKB_TILE - 1) / VKB_TILE, h, 0};
@@ -675,12 +895,33 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     vkb_capture cap;
     cap.winding = out; cap.winding_draw = 0;
-    vkb_stats S;
-    memset(&S, 0, sizeof S);
-    S.ms_stage[0] = -1.f;
-    VKB_CUDA_OK(cudaEventRecord(d->ev_begin, st));
-    int r = bin_and_fine(d, surf, sd, 1, n, &cap, S, nullptr, nullptr);
-    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    const SurfFlags before = surf_flags(surf);
+    int r = 1;
+    for (int attempt = 0; attempt < 16; attempt++) {
+        surf_restore(surf, before);
+        // capacities for the binning stages only; the edge count is given
+        uint32_t *c = d->capv;
+        if (c[VKC_EDGES] < n) c[VKC_EDGES] = (uint32_t)n;
+        const uint64_t n_tiles = (uint64_t)sd.tiles_x * sd.tiles_y;
+        if (c[VKC_PT] < n_tiles + 1024) c[VKC_PT] = (uint32_t)(n_tiles + 1024);
+        if (c[VKC_ROWS] < c[VKC_PT]) c[VKC_ROWS] = c[VKC_PT];
+        if (c[VKC_NE] < c[VKC_PT]) c[VKC_NE] = c[VKC_PT];
+        if (c[VKC_TE] < 2 * n + 1024) c[VKC_TE] = (uint32_t)(2 * n + 1024);
+        enqueue_counts_reset(d);
+        set_edge_count_k<<<1, 1, 0, st>>>(d->counts.as<vkb_counts>(), (uint32_t)n);
+        VKB_LAUNCHED();
+        VKB_CUDA_OK(cudaMemsetAsync(d->totals.p, 0, 16 * 8, st));
+        DevBuf wbuf;
+        enqueue_bin_and_fine(d, surf, sd, 1, &cap, nullptr, wbuf);
+        VKB_CUDA_OK(cudaMemcpyAsync(d->counts_host, d->counts.p, sizeof(vkb_counts), cudaMemcpyDeviceToHost, st));
+        VKB_CUDA_OK(cudaStreamSynchronize(st));
+        if (d->counts_host->overflow) { grow_caps_from_need(d, *d->counts_host); wbuf.release(); continue; }
+        VKB_CUDA_OK(cudaMemcpyAsync(out, wbuf.p, (size_t)w * h * (samples ? samples : 1) * 4, cudaMemcpyDeviceToHost, st));
+        VKB_CUDA_OK(cudaStreamSynchronize(st));
+        wbuf.release();
+        r = g_cuda_failed;
+        break;
+    }
     vkb_surface_free(surf);
     return r;
 }
@@ -689,6 +930,7 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
 // steps (outside the timed events) a 256 MiB scratch buffer is overwritten so that no step starts with its inputs in L2.
 int vkb_time_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, uint32_t steps, bool clear_first, bool flush_l2, vkb_stats *sum) {
     cudaSetDevice(d->ordinal);
+    finish_pending(d);
     vkb_stats acc;
     memset(&acc, 0, sizeof acc);
     for (uint32_t i = 0; i < steps; i++) {
@@ -708,3 +950,9 @@ int vkb_time_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples,
     if (sum) *sum = acc;
     return g_cuda_failed;
 }
+
+// stage timing on: every stats-producing flush records events between its stages (plain launches).  Off: such flushes may
+// replay the cached CUDA graph and report only the whole-flush time (and the fine kernel's, when the graph carries events).
+void vkb_device_set_stage_timing(vkb_device_impl *d, bool on) { d->stage_timing = on; }
+void vkb_device_set_graphs(vkb_device_impl *d, bool on) { d->graphs_enabled = on; }
+unsigned long long vkb_device_graph_replays(vkb_device_impl *d) { return d->n_graph_replays; }

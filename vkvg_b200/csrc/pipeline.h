@@ -7,7 +7,7 @@
 // ---- flatten.cu ----
 void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, cudaStream_t s);
 void vkb_launch_flatten_emit(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, const uint32_t *offsets, float2 *pts, uint8_t *flags,
-                             cudaStream_t s);
+                             const vkb_counts *C, cudaStream_t s);
 void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_off, uint32_t n_elems, const uint32_t *total,
                                uint32_t *sp_first, uint32_t *sp_count, cudaStream_t s);
 
@@ -26,12 +26,12 @@ struct StrokeArgs {
     const uint32_t    *sp_first, *sp_count;
     const vkb_subpath *sps;
     const double      *cum;  // exclusive scan of segment lengths over all stroke items (+1), or null if nothing is dashed
-    uint32_t           n_items;
+    uint32_t           n_items;  // CAPACITY of the item space (grid size); the count is C->n[VKC_SITEMS]
+    const vkb_counts  *C;
 };
 void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s);
 void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s);
-void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, unsigned long long total, float2 *verts, uint32_t *inds,
-                            uint32_t *job_inverse, cudaStream_t s);
+void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, float2 *verts, uint32_t *inds, uint32_t *job_inverse, cudaStream_t s);
 
 // ---- raster.cu ----
 struct SurfaceDesc {
@@ -43,9 +43,10 @@ struct SurfaceDesc {
     uint32_t full_height, origin_y;
 };
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
-                           uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges,
-                           uint32_t *edge_draw, cudaStream_t s);
-void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
+                           uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
+                           vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
+// edges / edge_draw: start of the edge arrays (the kernel skips the C->n[VKC_FILL] fill edges itself)
+void vkb_launch_tri_edges(const float2 *verts, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms,
                           const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
                           SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
 
@@ -55,30 +56,33 @@ struct BinBuffers {  // all device pointers
     uint32_t *draw_ptbase;  // n_draws (+1): first path-tile of the draw
     uint32_t *draw_rowbase; // n_draws (+1): first path-tile row of the draw
 };
-void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s);
+// every launcher below sizes its grid for a capacity (cap_*) and reads the count from C (dev_util.cuh: vkb_counts)
+void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
+                          cudaStream_t s);
 // draws may be null (raw edge lists); a VKB_DRAW_CLIP draw takes the whole surface as its rectangle
 void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
                            unsigned long long *tile_row_counts, cudaStream_t s);
 void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s);
-void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
-                          uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s);
+void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
+                          const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s);
 void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
-                                const unsigned long long *totals, int32_t *pt_backdrop, cudaStream_t s);
+                                uint32_t cap_rows, const vkb_counts *C, int32_t *pt_backdrop, cudaStream_t s);
 // keep_clip: the batch holds VKB_DRAW_CLIP draws, whose path-tiles are all kept (an empty one means "clipped out")
-void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, const vkb_draw *draws, const uint32_t *draw_ptbase,
-                         uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s);
-void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
-                           uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
-void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot, cudaStream_t s);
-void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
-                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
-                        uint32_t *tile_first,
-                        uint32_t *tile_end, cudaStream_t s);
-void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
-                            const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s);
+void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t cap_pt, const vkb_counts *C, const vkb_draw *draws,
+                         const uint32_t *draw_ptbase, uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s);
+void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t cap_pt, const vkb_counts *C, const int32_t *draw_rect,
+                           const uint32_t *draw_ptbase, uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
+void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot,
+                              cudaStream_t s);
+void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_draw_by_flagpos,
+                        const uint32_t *flag_scan, const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
+                        uint32_t *tile_first, uint32_t *tile_end, cudaStream_t s);
+void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
+                            const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s);
 
 struct FineArgs {
     SurfaceDesc         sd;
+    const vkb_counts   *counts;      // the fine pass only runs when no intermediate overflowed
     const uint32_t     *tile_first, *tile_end;
     const int4         *hdr;         // per sorted path-tile, 2 x int4: {draw, backdrop, edge offset, edge count}, {vkb_paint of the draw}
     const vkb_edge     *tile_edges;

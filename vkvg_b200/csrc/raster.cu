@@ -65,9 +65,9 @@ void vkb_launch_job_counts(const uint32_t *job_sp, uint32_t n_jobs, const uint32
 //      implicitly closed polygon, internal.c:1617-1642) ----
 __global__ void __launch_bounds__(256)
 fill_edges_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs,
-             const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw) {
+             const uint32_t *sp_first, const uint32_t *sp_count, const vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw) {
     uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= n_items) return;
+    if (C->overflow || item >= C->n[VKC_FILL]) return;
     uint32_t j = find_job(job_base, n_jobs, item), k = item - job_base[j];
     uint32_t s = job_sp[j], first = sp_first[s], n = sp_count[s], d = job_draw[j];
     float2   a = pts[first + k], b = pts[first + (k + 1 == n ? 0 : k + 1)];
@@ -80,10 +80,10 @@ fill_edges_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, 
     edge_draw[item] = d;
 }
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
-                           uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t n_items, SurfaceDesc sd, vkb_edge *edges,
-                           uint32_t *edge_draw, cudaStream_t s) {
-    if (!n_items) return;
-    fill_edges_k<<<vkb_div_up(n_items, 256), 256, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, n_items, sd, edges, edge_draw);
+                           uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
+                           vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
+    if (!cap_items || !n_jobs) return;
+    fill_edges_k<<<vkb_div_up(cap_items, 256), 256, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, C, sd, edges, edge_draw);
     VKB_LAUNCHED();
 }
 
@@ -121,11 +121,14 @@ __device__ __forceinline__ int tri_sign(const float2 *verts, uint32_t n_verts, c
     return area > 0 ? -1 : (area < 0 ? 1 : 0);  // cross > 0 winds -1 under our convention: such a triangle is reversed
 }
 __global__ void __launch_bounds__(256)
-tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
+tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms,
             const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd,
             vkb_edge *edges, uint32_t *edge_draw) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (C->overflow) return;
+    const uint32_t n_tris = C->n[VKC_TRIS], n_verts = C->n[VKC_VERTS];
     if (t >= n_tris) return;
+    edges += C->n[VKC_FILL]; edge_draw += C->n[VKC_FILL];  // stroke edges follow the fill edges
     // stroke draw owning index 3t: last q whose first item's index offset <= 3t
     uint32_t lo = 0, hi = n_sdraws;
     while (hi - lo > 1) {
@@ -169,11 +172,11 @@ tri_edges_k(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_
     edges[3 * t] = e[0]; edges[3 * t + 1] = e[1]; edges[3 * t + 2] = e[2];
     edge_draw[3 * t] = d; edge_draw[3 * t + 1] = d; edge_draw[3 * t + 2] = d;
 }
-void vkb_launch_tri_edges(const float2 *verts, uint32_t n_verts, const uint32_t *inds, uint32_t n_tris, const vkb_draw *draws, const vkb_xform *xforms,
+void vkb_launch_tri_edges(const float2 *verts, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms,
                           const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
                           SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
-    if (!n_tris) return;
-    tri_edges_k<<<vkb_div_up(n_tris, 256), 256, 0, s>>>(verts, n_verts, inds, n_tris, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, edges, edge_draw);
+    if (!cap_tris || !n_sdraws) return;
+    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(verts, inds, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, edges, edge_draw);
     VKB_LAUNCHED();
 }
 
@@ -185,7 +188,10 @@ __global__ void draw_bbox_init_k(int32_t *bbox, uint32_t n_draws) {
     if (i >= n_draws) return;
     bbox[4 * i] = INT32_MAX; bbox[4 * i + 1] = INT32_MAX; bbox[4 * i + 2] = INT32_MIN; bbox[4 * i + 3] = INT32_MIN;
 }
-__global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, int32_t *bbox) {
+__global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, int32_t *bbox) {
+    if (C->overflow) return;
+    const uint64_t n_edges = C->n[VKC_EDGES];
+    if ((uint64_t)blockIdx.x * blockDim.x >= n_edges) return;  // (whole block: the barriers below stay uniform)
     uint64_t i  = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool     ok = i < n_edges;
     vkb_edge e  = ok ? edges[i] : vkb_edge{0, 0, 0, 0};
@@ -223,11 +229,12 @@ __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const 
         atomicMin(&bbox[4 * d], mnx); atomicMin(&bbox[4 * d + 1], mny); atomicMax(&bbox[4 * d + 2], mxx); atomicMax(&bbox[4 * d + 3], mxy);
     }
 }
-void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s) {
+void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
+                          cudaStream_t s) {
     draw_bbox_init_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, n_draws);
     VKB_LAUNCHED();
-    if (!n_edges) return;
-    draw_bbox_k<<<vkb_div_up(n_edges, 256), 256, 0, s>>>(edges, edge_draw, n_edges, draw_bbox);
+    if (!cap_edges) return;
+    draw_bbox_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_bbox);
     VKB_LAUNCHED();
 }
 
@@ -316,26 +323,26 @@ template <class F> __device__ __forceinline__ void for_each_tile_of_edge(const v
         for (int32_t c = c0; c <= c1; c++) f_tile(ptbase + (uint32_t)(r - ty0) * tw + (uint32_t)(c - tx0));
     }
 }
-__global__ void __launch_bounds__(256) bin_count_k(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect,
+__global__ void __launch_bounds__(256) bin_count_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
                                                   const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_edges) return;
+    if (C->overflow || i >= C->n[VKC_EDGES]) return;
     vkb_edge e = edges[i];
     if (edge_degenerate(e)) return;
     uint32_t d = edge_draw[i];
     for_each_tile_of_edge(e, draw_rect + 4 * d, [&](uint32_t pt) { atomicAdd(&pt_count[pt], 1u); }, true, pt_backdrop, draw_ptbase[d]);
 }
-void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
-                          uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s) {
-    if (!n_edges) return;
-    bin_count_k<<<vkb_div_up(n_edges, 256), 256, 0, s>>>(edges, edge_draw, n_edges, draw_rect, draw_ptbase, pt_count, pt_backdrop);
+void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
+                          const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s) {
+    if (!cap_edges) return;
+    bin_count_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop);
     VKB_LAUNCHED();
 }
-__global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect,
+__global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
                                                     const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor,
                                                     vkb_edge *tile_edges) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_edges) return;
+    if (C->overflow || i >= C->n[VKC_EDGES]) return;
     vkb_edge e = edges[i];
     if (edge_degenerate(e)) return;
     uint32_t d = edge_draw[i];
@@ -348,17 +355,18 @@ __global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, cons
         },
         false, nullptr, draw_ptbase[d]);
 }
-void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t n_edges, const int32_t *draw_rect, const uint32_t *draw_ptbase,
-                            const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s) {
-    if (!n_edges) return;
-    bin_scatter_k<<<vkb_div_up(n_edges, 256), 256, 0, s>>>(edges, edge_draw, n_edges, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges);
+void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
+                            const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s) {
+    if (!cap_edges) return;
+    bin_scatter_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges);
     VKB_LAUNCHED();
 }
 
 // ---- backdrop: inclusive prefix sum along every path-tile row; one warp per row, grid-stride over rows ----
 __global__ void __launch_bounds__(256) backdrop_prefix_k(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase,
-                                                        uint32_t n_draws, const unsigned long long *totals, int32_t *pt_backdrop) {
-    const uint32_t n_rows = (uint32_t)(*totals >> 32);
+                                                        uint32_t n_draws, const vkb_counts *C, int32_t *pt_backdrop) {
+    if (C->overflow) return;
+    const uint32_t n_rows = C->n[VKC_ROWS];
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
         uint32_t d = find_job(draw_rowbase, n_draws, row);
@@ -376,16 +384,18 @@ __global__ void __launch_bounds__(256) backdrop_prefix_k(const int32_t *draw_rec
     }
 }
 void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
-                                const unsigned long long *totals, int32_t *pt_backdrop, cudaStream_t s) {
-    backdrop_prefix_k<<<148 * 4, 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, n_draws, totals, pt_backdrop);
+                                uint32_t cap_rows, const vkb_counts *C, int32_t *pt_backdrop, cudaStream_t s) {
+    if (!cap_rows) return;
+    const uint32_t blocks = cap_rows / 8 + 1 < 148 * 4 ? cap_rows / 8 + 1 : 148 * 4;  // one warp per row, grid-stride
+    backdrop_prefix_k<<<blocks, 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, n_draws, C, pt_backdrop);
     VKB_LAUNCHED();
 }
 
 // ---- compaction of non-empty path-tiles and the per-tile ordered lists ----
-__global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, const vkb_draw *draws, const uint32_t *draw_ptbase,
+__global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop, const vkb_counts *C, const vkb_draw *draws, const uint32_t *draw_ptbase,
                            uint32_t n_draws, bool keep_clip, uint32_t *flags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pt) return;
+    if (C->overflow || i >= C->n[VKC_PT]) return;
     bool keep = pt_count[i] != 0 || pt_backdrop[i] != 0;
     if (!keep && keep_clip) {  // an empty path-tile of a clip draw still clips its whole tile out
         uint32_t d = find_job(draw_ptbase, n_draws, i);
@@ -394,16 +404,16 @@ __global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop,
     }
     flags[i] = keep ? 1u : 0u;
 }
-void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t n_pt, const vkb_draw *draws, const uint32_t *draw_ptbase,
-                         uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s) {
-    if (!n_pt) return;
-    pt_flags_k<<<vkb_div_up(n_pt, 256), 256, 0, s>>>(pt_count, pt_backdrop, n_pt, draws, draw_ptbase, n_draws, keep_clip && draws, flags);
+void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t cap_pt, const vkb_counts *C, const vkb_draw *draws,
+                         const uint32_t *draw_ptbase, uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s) {
+    if (!cap_pt) return;
+    pt_flags_k<<<vkb_div_up(cap_pt, 256), 256, 0, s>>>(pt_count, pt_backdrop, C, draws, draw_ptbase, n_draws, keep_clip && draws, flags);
     VKB_LAUNCHED();
 }
-__global__ void pt_compact_k(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
+__global__ void pt_compact_k(const uint32_t *flags, const uint32_t *flag_scan, const vkb_counts *C, const int32_t *draw_rect, const uint32_t *draw_ptbase,
                              uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pt || !flags[i]) return;
+    if (C->overflow || i >= C->n[VKC_PT] || !flags[i]) return;
     uint32_t d = find_job(draw_ptbase, n_draws, i);
     while (d + 1 < n_draws && draw_ptbase[d + 1] <= i) d++;
     uint32_t tw = (uint32_t)draw_rect[4 * d + 2], local = i - draw_ptbase[d];
@@ -413,29 +423,32 @@ __global__ void pt_compact_k(const uint32_t *flags, const uint32_t *flag_scan, u
     vals[p]    = i;
     pt_draw[p] = d;  // in compaction order == path-tile order; re-read through vals after the sort
 }
-void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t n_pt, const int32_t *draw_rect, const uint32_t *draw_ptbase,
-                           uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s) {
-    if (!n_pt) return;
-    pt_compact_k<<<vkb_div_up(n_pt, 256), 256, 0, s>>>(flags, flag_scan, n_pt, draw_rect, draw_ptbase, n_draws, sd, keys, vals, pt_draw);
+void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t cap_pt, const vkb_counts *C, const int32_t *draw_rect,
+                           const uint32_t *draw_ptbase, uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s) {
+    if (!cap_pt) return;
+    pt_compact_k<<<vkb_div_up(cap_pt, 256), 256, 0, s>>>(flags, flag_scan, C, draw_rect, draw_ptbase, n_draws, sd, keys, vals, pt_draw);
     VKB_LAUNCHED();
 }
-__global__ void sorted_counts_k(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot) {
+__global__ void sorted_counts_k(const uint32_t *vals, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_ne) return;
+    if (C->overflow || p >= C->n[VKC_NE]) return;
     uint32_t pt   = vals[p];
     sorted_cnt[p] = pt_count[pt];
     pt_slot[pt]   = p;
 }
-void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot, cudaStream_t s) {
-    if (!n_ne) return;
-    sorted_counts_k<<<vkb_div_up(n_ne, 256), 256, 0, s>>>(vals, n_ne, pt_count, sorted_cnt, pt_slot);
+void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot,
+                              cudaStream_t s) {
+    if (!cap_ne) return;
+    sorted_counts_k<<<vkb_div_up(cap_ne, 256), 256, 0, s>>>(vals, C, pt_count, sorted_cnt, pt_slot);
     VKB_LAUNCHED();
 }
 // pt_draw_by_flagpos: draw of the path-tile at compaction position flag_scan[pt] (pt_compact_k output)
-__global__ void headers_k(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
+__global__ void headers_k(const uint32_t *keys, const uint32_t *vals, const vkb_counts *C, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
                           const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
                           uint32_t *tile_first, uint32_t *tile_end) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (C->overflow) return;
+    const uint32_t n_ne = C->n[VKC_NE];
     if (p >= n_ne) return;
     uint32_t pt = vals[p], key = keys[p];
     uint32_t dr = pt_draw_by_flagpos[flag_scan[pt]];
@@ -444,11 +457,11 @@ __global__ void headers_k(const uint32_t *keys, const uint32_t *vals, uint32_t n
     if (p == 0 || keys[p - 1] != key) tile_first[key] = p;
     if (p == n_ne - 1 || keys[p + 1] != key) tile_end[key] = p + 1;
 }
-void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t n_ne, const uint32_t *pt_draw_by_flagpos, const uint32_t *flag_scan,
-                        const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
+void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_draw_by_flagpos,
+                        const uint32_t *flag_scan, const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
                         uint32_t *tile_first, uint32_t *tile_end, cudaStream_t s) {
-    if (!n_ne) return;
-    headers_k<<<vkb_div_up(n_ne, 256), 256, 0, s>>>(keys, vals, n_ne, pt_draw_by_flagpos, flag_scan, pt_backdrop, pt_count, eoff, paints, hdr, tile_first, tile_end);
+    if (!cap_ne) return;
+    headers_k<<<vkb_div_up(cap_ne, 256), 256, 0, s>>>(keys, vals, C, pt_draw_by_flagpos, flag_scan, pt_backdrop, pt_count, eoff, paints, hdr, tile_first, tile_end);
     VKB_LAUNCHED();
 }
 
@@ -737,6 +750,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
     constexpr int P      = ROWS >= 64 ? 2 : 1;                 // sample rows per lane per pass
     constexpr int PASSES = (ROWS + 32 * P - 1) / (32 * P);
     const uint32_t tile  = blockIdx.x;
+    if (a.counts->overflow) return;  // some intermediate did not fit this attempt's buffers: the host replays the batch (vkb_counts)
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) return;  // no draw of this batch touches the tile: the stored pixels stay as they are
 
@@ -979,6 +993,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
 #define FA_ONE 1048576.0f
 template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_analytic_k(FineArgs a) {
     const uint32_t tile  = blockIdx.x;
+    if (a.counts->overflow) return;
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) return;
 

@@ -90,6 +90,9 @@ vkb_device_impl *vkb_device_open(int ordinal);  // nullptr when no usable CUDA d
 void             vkb_device_close(vkb_device_impl *d);
 int              vkb_device_failed(vkb_device_impl *d);
 void             vkb_device_sync(vkb_device_impl *d);
+void             vkb_device_set_stage_timing(vkb_device_impl *d, bool on);
+void             vkb_device_set_graphs(vkb_device_impl *d, bool on);
+unsigned long long vkb_device_graph_replays(vkb_device_impl *d);
 
 vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, uint32_t full_h, uint32_t origin_y);
 int               vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst);

@@ -252,9 +252,11 @@ template <bool EMIT>
 __global__ void __launch_bounds__(128)
 stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws, const vkb_stroke *strokes, const float *dash_table, const uint32_t *job_draw,
                const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count,
-               const vkb_subpath *sps, const double *cum, uint32_t n_items, unsigned long long *counts, const unsigned long long *offsets,
+               const vkb_subpath *sps, const double *cum, const vkb_counts *C, unsigned long long *counts, const unsigned long long *offsets,
                float2 *verts, uint32_t *inds, uint32_t *job_inverse) {
     uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (C->overflow) return;
+    const uint32_t n_items = C->n[VKC_SITEMS];
     if (item >= n_items) return;
     // locate the job (sub-path of a stroke draw) this point belongs to: last j with job_base[j] <= item
     uint32_t lo = 0, hi = n_jobs;
@@ -338,8 +340,10 @@ stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws,
 
 // float segment lengths for the dash phase scan (one per stroke item; 0 where there is no segment)
 __global__ void stroke_seglen_k(const float2 *pts, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first,
-                                const uint32_t *sp_count, const vkb_subpath *sps, uint32_t n_items, float *seglen) {
+                                const uint32_t *sp_count, const vkb_subpath *sps, const vkb_counts *C, float *seglen) {
     uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (C->overflow) return;
+    const uint32_t n_items = C->n[VKC_SITEMS];
     if (item > n_items) return;
     if (item == n_items) { seglen[item] = 0.f; return; }
     uint32_t lo = 0, hi = n_jobs;
@@ -360,9 +364,11 @@ __global__ void stroke_seglen_k(const float2 *pts, const uint32_t *job_sp, const
 // vertices of the sub-path (vkvg_context.c:921-931)
 __global__ void stroke_patch_closed_k(const vkb_draw *draws, const vkb_stroke *strokes, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                                       uint32_t n_jobs, const vkb_subpath *sps, const uint32_t *sp_count, const unsigned long long *offsets,
-                                      uint32_t n_items, unsigned long long total, const uint32_t *job_inverse, uint32_t *inds) {
+                                      const vkb_counts *C, const uint32_t *job_inverse, uint32_t *inds) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
+    if (j >= n_jobs || C->overflow) return;
+    const uint32_t           n_items = C->n[VKC_SITEMS];
+    const unsigned long long total   = (unsigned long long)C->n[VKC_VERTS] | ((unsigned long long)C->n[VKC_INDS] << 32);
     uint32_t s = job_sp[j];
     if (!(sps[s].flags & VKB_SP_CLOSED) || strokes[draws[job_draw[j]].xform_stroke >> 16].dash_count != 0 || sp_count[s] < 2) return;
     unsigned long long a = offsets[job_base[j]];
@@ -375,21 +381,21 @@ __global__ void stroke_patch_closed_k(const vkb_draw *draws, const vkb_stroke *s
     else { t[1] = ii; t[4] = ii; t[5] = ii + 1; }
 }
 
+// a.n_items is the CAPACITY of the item space (grids are sized for it); the item count is a.C->n[VKC_SITEMS]
 void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s) {
-    stroke_seglen_k<<<vkb_div_up(a.n_items + 1, 256), 256, 0, s>>>(a.pts, a.job_sp, a.job_base, a.n_jobs, a.sp_first, a.sp_count, a.sps, a.n_items, seglen);
+    stroke_seglen_k<<<vkb_div_up(a.n_items + 1, 256), 256, 0, s>>>(a.pts, a.job_sp, a.job_base, a.n_jobs, a.sp_first, a.sp_count, a.sps, a.C, seglen);
     VKB_LAUNCHED();
 }
 void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s) {
     stroke_items_k<false><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
-                                                                   a.sp_first, a.sp_count, a.sps, a.cum, a.n_items, counts, nullptr, nullptr, nullptr, nullptr);
+                                                                   a.sp_first, a.sp_count, a.sps, a.cum, a.C, counts, nullptr, nullptr, nullptr, nullptr);
     VKB_LAUNCHED();
 }
-void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, unsigned long long total, float2 *verts, uint32_t *inds,
-                            uint32_t *job_inverse, cudaStream_t s) {
+void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, float2 *verts, uint32_t *inds, uint32_t *job_inverse, cudaStream_t s) {
     stroke_items_k<true><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
-                                                                  a.sp_first, a.sp_count, a.sps, a.cum, a.n_items, nullptr, offsets, verts, inds, job_inverse);
+                                                                  a.sp_first, a.sp_count, a.sps, a.cum, a.C, nullptr, offsets, verts, inds, job_inverse);
     VKB_LAUNCHED();
     stroke_patch_closed_k<<<vkb_div_up(a.n_jobs, 128), 128, 0, s>>>(a.draws, a.strokes, a.job_draw, a.job_sp, a.job_base, a.n_jobs, a.sps, a.sp_count, offsets,
-                                                                   a.n_items, total, job_inverse, inds);
+                                                                   a.C, job_inverse, inds);
     VKB_LAUNCHED();
 }

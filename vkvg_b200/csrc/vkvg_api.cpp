@@ -1173,6 +1173,17 @@ void vkvg_b200_device_synchronize(VkvgDevice dev) {
     std::lock_guard<std::mutex> lk(dev->mtx);
     vkb_device_sync(dev->impl);
 }
+void vkvg_b200_device_set_stage_timing(VkvgDevice dev, int on) {
+    if (vkvg_device_status(dev)) return;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    vkb_device_set_stage_timing(dev->impl, on != 0);
+}
+void vkvg_b200_device_set_graphs(VkvgDevice dev, int on) {
+    if (vkvg_device_status(dev)) return;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    vkb_device_set_graphs(dev->impl, on != 0);
+}
+uint64_t vkvg_b200_device_graph_replays(VkvgDevice dev) { return vkvg_device_status(dev) ? 0 : vkb_device_graph_replays(dev->impl); }
 int vkb_device_ordinal(vkb_device_impl *d);
 int vkvg_b200_device_ordinal(VkvgDevice dev) { return vkvg_device_status(dev) ? -1 : vkb_device_ordinal(dev->impl); }
 
