@@ -248,13 +248,12 @@ static inline void vkb_exclusive_scan(const TI *in, T *out, uint64_t n, T *total
 // Each block owns a contiguous chunk of 4096 pairs; each warp a contiguous 512 of those, walked in 16
 // rounds of 32, so "earlier in memory" == "earlier (warp, round, lane)" and ranks are stable.
 // ----------------------------------------------------------------------------------------------------
+// ROUNDS = 16 for large inputs (few, long blocks); 2 for short ones, where the sequential rounds of a block are pure latency
 #define VKB_SORT_BLOCK 256
-#define VKB_SORT_ROUNDS 16
-#define VKB_SORT_CHUNK (VKB_SORT_BLOCK * VKB_SORT_ROUNDS)
 
-__device__ __forceinline__ void sort_warp_hist(const uint32_t *keys, uint64_t n, uint64_t warp_base, int shift, uint32_t *wc) {
+template <int ROUNDS> __device__ __forceinline__ void sort_warp_hist(const uint32_t *keys, uint64_t n, uint64_t warp_base, int shift, uint32_t *wc) {
     const unsigned lane = threadIdx.x & 31;
-    for (int r = 0; r < VKB_SORT_ROUNDS; r++) {
+    for (int r = 0; r < ROUNDS; r++) {
         uint64_t i     = warp_base + (uint64_t)r * 32 + lane;
         uint32_t d     = i < n ? ((keys[i] >> shift) & 0xFF) : 256u;
         unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -262,28 +261,32 @@ __device__ __forceinline__ void sort_warp_hist(const uint32_t *keys, uint64_t n,
         __syncwarp();
     }
 }
+template <int ROUNDS>
 static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_hist_k(const uint32_t *keys, uint64_t n, int shift, uint32_t *hist, uint32_t nblocks,
                                                                      const vkb_counts *C, int idx) {
+    constexpr int VKB_SORT_ROUNDS = ROUNDS, VKB_SORT_CHUNK = VKB_SORT_BLOCK * ROUNDS;
     if (C) { if (C->overflow) return; n = C->n[idx]; }
     __shared__ uint32_t wc[VKB_SORT_BLOCK / 32][256];
     for (int i = threadIdx.x; i < (VKB_SORT_BLOCK / 32) * 256; i += VKB_SORT_BLOCK) (&wc[0][0])[i] = 0;
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5;
-    sort_warp_hist(keys, n, (uint64_t)blockIdx.x * VKB_SORT_CHUNK + (uint64_t)warp * 32 * VKB_SORT_ROUNDS, shift, wc[warp]);
+    sort_warp_hist<ROUNDS>(keys, n, (uint64_t)blockIdx.x * VKB_SORT_CHUNK + (uint64_t)warp * 32 * VKB_SORT_ROUNDS, shift, wc[warp]);
     __syncthreads();
     uint32_t sum = 0;
     for (int w = 0; w < VKB_SORT_BLOCK / 32; w++) sum += wc[w][threadIdx.x];
     hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = sum;  // digit-major so one scan yields global offsets
 }
+template <int ROUNDS>
 static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_scatter_k(const uint32_t *keys, const uint32_t *vals, uint32_t *okeys, uint32_t *ovals,
                                                                 uint64_t n, int shift, const uint32_t *hist_scan, uint32_t nblocks, const vkb_counts *C, int idx) {
+    constexpr int VKB_SORT_ROUNDS = ROUNDS, VKB_SORT_CHUNK = VKB_SORT_BLOCK * ROUNDS;
     if (C) { if (C->overflow) return; n = C->n[idx]; }
     __shared__ uint32_t wc[VKB_SORT_BLOCK / 32][256];
     for (int i = threadIdx.x; i < (VKB_SORT_BLOCK / 32) * 256; i += VKB_SORT_BLOCK) (&wc[0][0])[i] = 0;
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t warp_base = (uint64_t)blockIdx.x * VKB_SORT_CHUNK + (uint64_t)warp * 32 * VKB_SORT_ROUNDS;
-    sort_warp_hist(keys, n, warp_base, shift, wc[warp]);
+    sort_warp_hist<ROUNDS>(keys, n, warp_base, shift, wc[warp]);
     __syncthreads();
     {   // thread d: turn per-warp counts into global start offsets for (digit d, this block, warp w)
         uint32_t run = hist_scan[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
@@ -320,7 +323,8 @@ struct SortScratch {
 static inline void vkb_radix_sort(uint32_t *keys, uint32_t *vals, uint64_t n, int bits, SortScratch &sc, cudaStream_t s, vkb_counts *C = nullptr,
                                   int idx = 0) {
     if (n < 2) return;
-    uint32_t nblocks = vkb_div_up(n, VKB_SORT_CHUNK);
+    const bool small   = n <= 65536;
+    uint32_t   nblocks = vkb_div_up(n, VKB_SORT_BLOCK * (small ? 2 : 16));
     sc.hist.ensure((size_t)256 * nblocks * 4, s);
     sc.k2.ensure(n * 4, s);
     sc.v2.ensure(n * 4, s);
@@ -328,10 +332,12 @@ static inline void vkb_radix_sort(uint32_t *keys, uint32_t *vals, uint64_t n, in
     int       passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
     for (int p = 0; p < passes; p++) {
-        sort_hist_k<<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
+        if (small) sort_hist_k<2><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
+        else sort_hist_k<16><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
         VKB_LAUNCHED();
         vkb_exclusive_scan<uint32_t, uint32_t>(sc.hist.as<uint32_t>(), sc.hist.as<uint32_t>(), (uint64_t)256 * nblocks, nullptr, sc.scan, s);
-        sort_scatter_k<<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, va, kb, vb, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
+        if (small) sort_scatter_k<2><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, va, kb, vb, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
+        else sort_scatter_k<16><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, va, kb, vb, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
         VKB_LAUNCHED();
         uint32_t *t;
         t = ka; ka = kb; kb = t;

@@ -41,7 +41,8 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image, cursor2;
+    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner;
+    uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
     ScanScratch scan;
     SortScratch sort;
     // counts that live on the device (dev_util.cuh: vkb_counts) and the flush that may still be in flight
@@ -103,7 +104,7 @@ void vkb_device_close(vkb_device_impl *d) {
     cudaSetDevice(d->ordinal);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -285,6 +286,7 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     // the previous flush may still be reading the staging area
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
+    d->n_curves = b.n_curves;
     // what the job tables will hold is a function of the recorded draws alone: counted here, no read-back
     d->has_clip_draws = d->has_stencil_ops = false;
     d->stencil_after = 0;
@@ -509,13 +511,17 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->pt_backdrop.ensure((size_t)(cap_pt + 1) * 4, st);
     d->pt_flags.ensure((size_t)(cap_pt + 1) * 4, st);
     d->pt_slot.ensure((size_t)(cap_pt + 1) * 4, st);
+    d->pt_owner.ensure((size_t)(cap_pt + 1) * 4, st);
+    d->row_owner.ensure((size_t)(cv[VKC_ROWS] + 1) * 4, st);
+    vkb_launch_owners(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd, C, d->pt_owner.as<uint32_t>(),
+                      d->row_owner.as<uint32_t>(), st);
     VKB_CUDA_OK(cudaMemsetAsync(d->pt_count.p, 0, (size_t)cap_pt * 4, st));
     VKB_CUDA_OK(cudaMemsetAsync(d->pt_backdrop.p, 0, (size_t)cap_pt * 4, st));
     vkb_launch_bin_count(edges, edraw, cv[VKC_EDGES], C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_count.as<uint32_t>(),
                          d->pt_backdrop.as<int32_t>(), st);
-    vkb_launch_backdrop_prefix(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd, cv[VKC_ROWS], C,
-                               d->pt_backdrop.as<int32_t>(), st);
-    vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), cap_pt, C, draws, d->draw_ptbase.as<uint32_t>(), nd, clip_draws,
+    vkb_launch_backdrop_prefix(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), d->row_owner.as<uint32_t>(),
+                               cv[VKC_ROWS], C, d->pt_backdrop.as<int32_t>(), st);
+    vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), cap_pt, C, draws, d->pt_owner.as<uint32_t>(), clip_draws,
                         d->pt_flags.as<uint32_t>(), st);
     // pt_slot doubles as the exclusive scan of the flags until the sorted slots overwrite it
     d->sorted_cnt.ensure((size_t)(cap_pt + 1) * 4, st);
@@ -529,7 +535,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->hdr.ensure((size_t)(cap_ne + 1) * 32, st);
     d->tile_first.ensure((size_t)n_tiles * 4 + 16, st);
     d->tile_end.ensure((size_t)n_tiles * 4 + 16, st);
-    vkb_launch_pt_compact(d->pt_flags.as<uint32_t>(), flag_scan, cap_pt, C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), nd, sd,
+    vkb_launch_pt_compact(d->pt_flags.as<uint32_t>(), flag_scan, cap_pt, C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_owner.as<uint32_t>(), sd,
                           d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), d->pt_draw.as<uint32_t>(), st);
     int bits = 1;
     while ((1u << bits) < n_tiles && bits < 32) bits++;
@@ -631,8 +637,14 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     d->ptflags.ensure((size_t)cv[VKC_POINTS] + 16, st);
     d->fjob_base.ensure((size_t)(d->n_fjobs + 1) * 4, st);
     d->sjob_base.ensure((size_t)(d->n_sjobs + 1) * 4, st);
+    // curve-heavy batches keep the first 16 points of every element from the counting pass (16 * 8 B per element)
+    float2 *fcache = nullptr;
+    if (d->n_curves && (uint64_t)d->n_curves * 8 >= d->n_elems) {
+        d->flat_cache.ensure((size_t)d->n_elems * 16 * 8, st);
+        fcache = d->flat_cache.as<float2>();
+    }
     if (d->n_elems) {
-        vkb_launch_flatten_count(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), st);
+        vkb_launch_flatten_count(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), fcache, st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->elem_cnt.as<uint32_t>(), d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals, d->scan, st);
         vkb_launch_subpath_ranges(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals,
                                   d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), st);
@@ -650,7 +662,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     VKB_LAUNCHED();
     if (d->n_elems)
         vkb_launch_flatten_emit(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), d->pts.as<float2>(),
-                                d->ptflags.as<uint8_t>(), C, st);
+                                d->ptflags.as<uint8_t>(), C, fcache, st);
     VKB_EVENT_RECORD(d, d->ev_stage[1]);
 
     // ---- 3. strokes: (dash phase scan) -> count -> scan -> emit ----
@@ -712,7 +724,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
 // same kernels with the same arguments, so the second one can be a replay of a CUDA graph captured from the first: a frame
 // loop that redraws a scene of the same structure pays one graph launch per frame instead of ~40 kernel launches.
 struct FlushKey {
-    uint32_t n_elems, n_sp, n_draws, n_fjobs, n_sjobs, n_sdraws, n_extra;
+    uint32_t n_elems, n_sp, n_draws, n_fjobs, n_sjobs, n_sdraws, n_extra, n_curves;
     uint32_t flags;  // any_dash | has_clip_draws << 1 | has_stencil_ops << 2 | stencil_after << 3
     uint32_t capv[16];
     const void *surf;
@@ -734,6 +746,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     memset(kbuf, 0, sizeof kbuf);
     FlushKey k;
     memset(&k, 0, sizeof k);
+    k.n_curves = d->n_curves;
     k.n_elems = d->n_elems; k.n_sp = d->n_sp; k.n_draws = d->n_draws; k.n_fjobs = d->n_fjobs; k.n_sjobs = d->n_sjobs; k.n_sdraws = d->n_sdraws; k.n_extra = d->n_extra;
     k.flags = (d->any_dash ? 1u : 0u) | (d->has_clip_draws ? 2u : 0u) | (d->has_stencil_ops ? 4u : 0u) | ((uint32_t)d->stencil_after << 3);
     memcpy(k.capv, d->capv, sizeof k.capv);

@@ -5,9 +5,10 @@
 #include "vkb_types.h"
 
 // ---- flatten.cu ----
-void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, cudaStream_t s);
+// cache: n * VKB_FLAT_CACHE points kept by the counting pass for the emitting pass (null: every curve is walked twice)
+void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, float2 *cache, cudaStream_t s);
 void vkb_launch_flatten_emit(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, const uint32_t *offsets, float2 *pts, uint8_t *flags,
-                             const vkb_counts *C, cudaStream_t s);
+                             const vkb_counts *C, float2 *cache, cudaStream_t s);
 void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_off, uint32_t n_elems, const uint32_t *total,
                                uint32_t *sp_first, uint32_t *sp_count, cudaStream_t s);
 
@@ -65,13 +66,16 @@ void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, uint
 void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s);
 void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
                           const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s);
-void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
+// pt_owner[path-tile] / row_owner[path-tile row] = draw index
+void vkb_launch_owners(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws, const vkb_counts *C,
+                       uint32_t *pt_owner, uint32_t *row_owner, cudaStream_t s);
+void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, const uint32_t *row_owner,
                                 uint32_t cap_rows, const vkb_counts *C, int32_t *pt_backdrop, cudaStream_t s);
 // keep_clip: the batch holds VKB_DRAW_CLIP draws, whose path-tiles are all kept (an empty one means "clipped out")
 void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t cap_pt, const vkb_counts *C, const vkb_draw *draws,
-                         const uint32_t *draw_ptbase, uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s);
+                         const uint32_t *pt_owner, bool keep_clip, uint32_t *flags, cudaStream_t s);
 void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t cap_pt, const vkb_counts *C, const int32_t *draw_rect,
-                           const uint32_t *draw_ptbase, uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
+                           const uint32_t *draw_ptbase, const uint32_t *pt_owner, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
 void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot,
                               cudaStream_t s);
 void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_draw_by_flagpos,

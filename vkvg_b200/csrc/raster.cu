@@ -362,16 +362,33 @@ void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, ui
     VKB_LAUNCHED();
 }
 
+// ---- which draw owns a path-tile / a path-tile row: written once per draw (one warp each) so that the per-path-tile and
+//      per-row kernels below read one word instead of binary-searching the draw table ----
+__global__ void __launch_bounds__(256) owners_k(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
+                                               const vkb_counts *C, uint32_t *pt_owner, uint32_t *row_owner) {
+    if (C->overflow) return;
+    const uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (d >= n_draws) return;
+    const uint32_t tw = (uint32_t)draw_rect[4 * d + 2], th = (uint32_t)draw_rect[4 * d + 3];
+    uint32_t *po = pt_owner + draw_ptbase[d], *ro = row_owner + draw_rowbase[d];
+    for (uint32_t k = lane; k < tw * th; k += 32) po[k] = d;
+    for (uint32_t k = lane; k < th; k += 32) ro[k] = d;
+}
+void vkb_launch_owners(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws, const vkb_counts *C,
+                       uint32_t *pt_owner, uint32_t *row_owner, cudaStream_t s) {
+    if (!n_draws) return;
+    owners_k<<<vkb_div_up((uint64_t)n_draws * 32, 256), 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, n_draws, C, pt_owner, row_owner);
+    VKB_LAUNCHED();
+}
+
 // ---- backdrop: inclusive prefix sum along every path-tile row; one warp per row, grid-stride over rows ----
 __global__ void __launch_bounds__(256) backdrop_prefix_k(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase,
-                                                        uint32_t n_draws, const vkb_counts *C, int32_t *pt_backdrop) {
+                                                        const uint32_t *row_owner, const vkb_counts *C, int32_t *pt_backdrop) {
     if (C->overflow) return;
     const uint32_t n_rows = C->n[VKC_ROWS];
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
-        uint32_t d = find_job(draw_rowbase, n_draws, row);
-        // skip draws with zero rows that share the same base
-        while (d + 1 < n_draws && draw_rowbase[d + 1] <= row) d++;
+        const uint32_t d = row_owner[row];
         uint32_t tw   = (uint32_t)draw_rect[4 * d + 2];
         int32_t *p    = pt_backdrop + draw_ptbase[d] + (row - draw_rowbase[d]) * tw;
         int32_t  carry = 0;
@@ -383,39 +400,34 @@ __global__ void __launch_bounds__(256) backdrop_prefix_k(const int32_t *draw_rec
         }
     }
 }
-void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
+void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, const uint32_t *row_owner,
                                 uint32_t cap_rows, const vkb_counts *C, int32_t *pt_backdrop, cudaStream_t s) {
     if (!cap_rows) return;
-    const uint32_t blocks = cap_rows / 8 + 1 < 148 * 4 ? cap_rows / 8 + 1 : 148 * 4;  // one warp per row, grid-stride
-    backdrop_prefix_k<<<blocks, 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, n_draws, C, pt_backdrop);
+    const uint32_t blocks = cap_rows / 8 + 1 < 148 * 16 ? cap_rows / 8 + 1 : 148 * 16;  // one warp per row, grid-stride
+    backdrop_prefix_k<<<blocks, 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, row_owner, C, pt_backdrop);
     VKB_LAUNCHED();
 }
 
 // ---- compaction of non-empty path-tiles and the per-tile ordered lists ----
-__global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop, const vkb_counts *C, const vkb_draw *draws, const uint32_t *draw_ptbase,
-                           uint32_t n_draws, bool keep_clip, uint32_t *flags) {
+__global__ void pt_flags_k(const uint32_t *pt_count, const int32_t *pt_backdrop, const vkb_counts *C, const vkb_draw *draws, const uint32_t *pt_owner,
+                           bool keep_clip, uint32_t *flags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow || i >= C->n[VKC_PT]) return;
     bool keep = pt_count[i] != 0 || pt_backdrop[i] != 0;
-    if (!keep && keep_clip) {  // an empty path-tile of a clip draw still clips its whole tile out
-        uint32_t d = find_job(draw_ptbase, n_draws, i);
-        while (d + 1 < n_draws && draw_ptbase[d + 1] <= i) d++;
-        keep = draws[d].kind == VKB_DRAW_CLIP;
-    }
+    if (!keep && keep_clip) keep = draws[pt_owner[i]].kind == VKB_DRAW_CLIP;  // an empty path-tile of a clip draw still clips its whole tile out
     flags[i] = keep ? 1u : 0u;
 }
 void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, uint32_t cap_pt, const vkb_counts *C, const vkb_draw *draws,
-                         const uint32_t *draw_ptbase, uint32_t n_draws, bool keep_clip, uint32_t *flags, cudaStream_t s) {
+                         const uint32_t *pt_owner, bool keep_clip, uint32_t *flags, cudaStream_t s) {
     if (!cap_pt) return;
-    pt_flags_k<<<vkb_div_up(cap_pt, 256), 256, 0, s>>>(pt_count, pt_backdrop, C, draws, draw_ptbase, n_draws, keep_clip && draws, flags);
+    pt_flags_k<<<vkb_div_up(cap_pt, 256), 256, 0, s>>>(pt_count, pt_backdrop, C, draws, pt_owner, keep_clip && draws, flags);
     VKB_LAUNCHED();
 }
 __global__ void pt_compact_k(const uint32_t *flags, const uint32_t *flag_scan, const vkb_counts *C, const int32_t *draw_rect, const uint32_t *draw_ptbase,
-                             uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw) {
+                             const uint32_t *pt_owner, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow || i >= C->n[VKC_PT] || !flags[i]) return;
-    uint32_t d = find_job(draw_ptbase, n_draws, i);
-    while (d + 1 < n_draws && draw_ptbase[d + 1] <= i) d++;
+    const uint32_t d = pt_owner[i];
     uint32_t tw = (uint32_t)draw_rect[4 * d + 2], local = i - draw_ptbase[d];
     uint32_t tx = (uint32_t)draw_rect[4 * d] + local % tw, ty = (uint32_t)draw_rect[4 * d + 1] + local / tw;
     uint32_t p = flag_scan[i];
@@ -424,9 +436,9 @@ __global__ void pt_compact_k(const uint32_t *flags, const uint32_t *flag_scan, c
     pt_draw[p] = d;  // in compaction order == path-tile order; re-read through vals after the sort
 }
 void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t cap_pt, const vkb_counts *C, const int32_t *draw_rect,
-                           const uint32_t *draw_ptbase, uint32_t n_draws, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s) {
+                           const uint32_t *draw_ptbase, const uint32_t *pt_owner, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s) {
     if (!cap_pt) return;
-    pt_compact_k<<<vkb_div_up(cap_pt, 256), 256, 0, s>>>(flags, flag_scan, C, draw_rect, draw_ptbase, n_draws, sd, keys, vals, pt_draw);
+    pt_compact_k<<<vkb_div_up(cap_pt, 256), 256, 0, s>>>(flags, flag_scan, C, draw_rect, draw_ptbase, pt_owner, sd, keys, vals, pt_draw);
     VKB_LAUNCHED();
 }
 __global__ void sorted_counts_k(const uint32_t *vals, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot) {

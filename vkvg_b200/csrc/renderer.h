@@ -54,9 +54,10 @@ struct vkb_batch {
     std::vector<vkb_stroke>   strokes;
     std::vector<vkb_gradient> grads;
     std::vector<float>        dashes;
+    uint32_t                  n_curves = 0;  // cubic / arc elements among elem_hdr (sizing hint for the flatten stage)
     void clear_draws() { draws.clear(); xforms.clear(); strokes.clear(); grads.clear(); dashes.clear(); }
     void clear() {
-        elem_hdr.clear(); elem_data.clear(); subpaths.clear(); clear_draws();
+        elem_hdr.clear(); elem_data.clear(); subpaths.clear(); clear_draws(); n_curves = 0;
     }
 };
 

@@ -460,6 +460,7 @@ static void push_elem(VkvgContext ctx, uint32_t type_flags, const float *payload
     vkb_batch &b = ctx->batch;
     b.elem_hdr.push_back(type_flags | ((uint32_t)b.elem_data.size() << VKB_EL_PAYLOAD_SHIFT));
     b.elem_data.append(payload, payload + n);
+    if ((type_flags & VKB_EL_TYPE_MASK) != VKB_EL_POINT) b.n_curves++;
 }
 static inline void add_point(VkvgContext ctx, float x, float y, bool curved) {  // _add_point, internal.c:221-238
     if (isnan(x) || isnan(y)) return;
@@ -1086,6 +1087,9 @@ static void carry_path_over(VkvgContext ctx) {
         b.elem_hdr[i] = (h & ((1u << VKB_EL_PAYLOAD_SHIFT) - 1)) | (((h >> VKB_EL_PAYLOAD_SHIFT) - d0) << VKB_EL_PAYLOAD_SHIFT);
     }
     b.elem_hdr.resize(nh);
+    b.n_curves = 0;
+    for (size_t i = 0; i < nh; i++)
+        if ((b.elem_hdr[i] & VKB_EL_TYPE_MASK) != VKB_EL_POINT) b.n_curves++;
     size_t nd = b.elem_data.size() - d0;
     if (nd && d0) memmove(b.elem_data.data(), b.elem_data.data() + d0, nd * sizeof(float));
     b.elem_data.resize(nd);
