@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvkvg_b200.so")
+LIB_PATH = os.environ.get("VKVG_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvkvg_b200.so")
 _f, _u, _i, _p = C.c_float, C.c_uint32, C.c_int, C.c_void_p
 
 # vkvg.h enum values

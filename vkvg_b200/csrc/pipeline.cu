@@ -41,7 +41,8 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner;
+    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep;
+    uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
     ScanScratch scan;
     SortScratch sort;
@@ -104,7 +105,7 @@ void vkb_device_close(vkb_device_impl *d) {
     cudaSetDevice(d->ordinal);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -287,6 +288,7 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
     d->n_curves = b.n_curves;
+    d->n_grads  = (uint32_t)b.grads.size();
     // what the job tables will hold is a function of the recorded draws alone: counted here, no read-back
     d->has_clip_draws = d->has_stencil_ops = false;
     d->stencil_after = 0;
@@ -566,6 +568,9 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     fa.tile_first = d->tile_first.as<uint32_t>(); fa.tile_end = d->tile_end.as<uint32_t>();
     fa.hdr = d->hdr.as<int4>(); fa.tile_edges = d->tile_edges.as<vkb_edge>();
     fa.paints = d->paints.as<vkb_paint>(); fa.grads = d->grads.as<vkb_gradient>();
+    d->gprep.ensure((size_t)(d->n_grads + 1) * 16 * 4, st);
+    vkb_launch_grad_prep(fa.grads, draws ? d->n_grads : 0, (float)sd.width, (float)sd.full_height, d->gprep.as<float>(), st);
+    fa.gprep = d->gprep.as<float>();
     fa.image = surf->image.as<uint32_t>();
     if (samples) {  // (analytic mode, samples == 0, keeps one colour per pixel: no per-sample plane)
         bool fresh = surf->tile_ms.p == nullptr;
@@ -724,7 +729,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
 // same kernels with the same arguments, so the second one can be a replay of a CUDA graph captured from the first: a frame
 // loop that redraws a scene of the same structure pays one graph launch per frame instead of ~40 kernel launches.
 struct FlushKey {
-    uint32_t n_elems, n_sp, n_draws, n_fjobs, n_sjobs, n_sdraws, n_extra, n_curves;
+    uint32_t n_elems, n_sp, n_draws, n_fjobs, n_sjobs, n_sdraws, n_extra, n_curves, n_grads;
     uint32_t flags;  // any_dash | has_clip_draws << 1 | has_stencil_ops << 2 | stencil_after << 3
     uint32_t capv[16];
     const void *surf;
@@ -746,7 +751,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     memset(kbuf, 0, sizeof kbuf);
     FlushKey k;
     memset(&k, 0, sizeof k);
-    k.n_curves = d->n_curves;
+    k.n_curves = d->n_curves; k.n_grads = d->n_grads;
     k.n_elems = d->n_elems; k.n_sp = d->n_sp; k.n_draws = d->n_draws; k.n_fjobs = d->n_fjobs; k.n_sjobs = d->n_sjobs; k.n_sdraws = d->n_sdraws; k.n_extra = d->n_extra;
     k.flags = (d->any_dash ? 1u : 0u) | (d->has_clip_draws ? 2u : 0u) | (d->has_stencil_ops ? 4u : 0u) | ((uint32_t)d->stencil_after << 3);
     memcpy(k.capv, d->capv, sizeof k.capv);

@@ -92,6 +92,7 @@ struct FineArgs {
     const vkb_edge     *tile_edges;
     const vkb_paint    *paints;      // per draw
     const vkb_gradient *grads;
+    const float        *gprep;       // per gradient: VKB_GPREP_FLOATS position-independent terms of the paint evaluation (grad_prep_k)
     uint32_t           *image;       // width*height premultiplied RGBA8 (resolved)
     uint32_t           *ms_image;    // per-sample colours, tile-major [tile][256][S]; valid for tiles whose tile_ms flag is set
     uint8_t            *tile_ms;     // per tile: 1 when the samples of some pixel differ (the resolved image alone would lose them)
@@ -102,6 +103,7 @@ struct FineArgs {
     int32_t            *winding_out; // optional: per-sample winding of the LAST draw touching each sample (parity tests), or null
     uint32_t            winding_draw; // draw index captured into winding_out
 };
+void vkb_launch_grad_prep(const vkb_gradient *grads, uint32_t n, float W, float H, float *out, cudaStream_t s);
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s);
 
 void vkb_launch_unpremultiply(const uint32_t *image, uint64_t n_pixels, uint32_t *out, cudaStream_t s);

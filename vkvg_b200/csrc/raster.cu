@@ -509,43 +509,63 @@ __device__ __forceinline__ void mix4(float *c, const float *b, float t) {
     for (int k = 0; k < 4; k++) c[k] = c[k] * (1.0f - t) + b[k] * t;
 }
 // shaders/vkvg_main.frag:68-157 (SOLID / LINEAR / RADIAL) at the pixel centre; identical arithmetic to
-// oracle/vkvg_oracle.c: eval_paint
-__device__ void eval_paint(uint32_t pattern, const vkb_gradient *g, float W, float H, uint32_t solid, float opacity, float fx, float fy, float out[4],
-                           const float *lut) {
-    float c[4];
-    if (pattern == VKB_PAT_LINEAR) {
+// oracle/vkvg_oracle.c: eval_paint.  Everything the shader derives from the gradient record alone (normalised control
+// points, axis direction, line slope ...) is evaluated once per gradient by grad_prep_k with the same float operations in
+// the same order, so a pixel only pays for what depends on its position.
+#define VKB_GPREP_FLOATS 16
+__global__ void grad_prep_k(const vkb_gradient *grads, uint32_t n, float W, float H, float *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vkb_gradient *g = grads + i;
+    float *o = out + (size_t)i * VKB_GPREP_FLOATS;
+    {   // linear (frag :84-107)
         float p0x = g->cp[0][0] / W, p0y = g->cp[0][1] / H;
         float p1x = g->cp[0][2] / W, p1y = g->cp[0][3] / H;
-        float px = fx / W, py = fy / H;
         float dx = p1x - p0x, dy = p1y - p0y;
         float l  = sqrtf(dx * dx + dy * dy);
         float ux = dx / l, uy = dy / l;
+        float m  = -ux / uy;
+        float bb = p0y - m * p0x;
+        o[0] = p0x; o[1] = l; o[2] = ux; o[3] = uy; o[4] = m; o[5] = bb; o[6] = sqrtf(1.0f + m * m);
+    }
+    {   // radial (frag :109-144)
+        float c0x = g->cp[0][0] / W, c0y = g->cp[0][1] / H;
+        float c1x = g->cp[1][0] / W, c1y = g->cp[1][1] / H;
+        float r0 = g->cp[0][2] / W, r1 = g->cp[1][2] / W;
+        float dfx = c0x - c1x, dfy = c0y - c1y;
+        o[8] = c0x; o[9] = c0y; o[10] = r0; o[11] = dfx; o[12] = dfy; o[13] = (dfx * dfx + dfy * dfy) - r1 * r1;
+    }
+}
+void vkb_launch_grad_prep(const vkb_gradient *grads, uint32_t n, float W, float H, float *out, cudaStream_t s) {
+    if (!n) return;
+    grad_prep_k<<<vkb_div_up(n, 128), 128, 0, s>>>(grads, n, W, H, out);
+    VKB_LAUNCHED();
+}
+__device__ __noinline__ void eval_gradient(uint32_t pattern, const vkb_gradient *g, const float *gp, float W, float H, float fx, float fy, float c[4]) {
+    if (pattern == VKB_PAT_LINEAR) {
+        const float p0x = gp[0], l = gp[1], ux = gp[2], uy = gp[3];
+        float px = fx / W, py = fy / H;
         float dist;
         if (uy == 0.0f) {
             if (ux < 0.0f) dist = -(px - p0x) / l;
             else dist = (px - p0x) / l;
         } else {
-            float m  = -ux / uy;
-            float bb = p0y - m * p0x;
-            dist     = ((py - m * px - bb) / sqrtf(1.0f + m * m)) / l;
+            const float m = gp[4], bb = gp[5], sq = gp[6];
+            dist = ((py - m * px - bb) / sq) / l;
             if (uy < 0.0f) dist = -dist;
         }
         for (int k = 0; k < 4; k++) c[k] = g->colors[0][k];
         mix4(c, g->colors[1], smoothstepf(g->stops[0], g->stops[1], dist));
         for (uint32_t i = 1; i + 1 < g->count; ++i) mix4(c, g->colors[i + 1], smoothstepf(g->stops[i], g->stops[i + 1], dist));
-    } else if (pattern == VKB_PAT_RADIAL) {
+    } else {
+        const float c0x = gp[8], c0y = gp[9], r0 = gp[10], dfx = gp[11], dfy = gp[12], cc = gp[13];
         float px = fx / W, py = fy / H;
-        float c0x = g->cp[0][0] / W, c0y = g->cp[0][1] / H;
-        float c1x = g->cp[1][0] / W, c1y = g->cp[1][1] / H;
-        float r0 = g->cp[0][2] / W, r1 = g->cp[1][2] / W;
         float gradLength = 1.0f;
-        float dfx = c0x - c1x, dfy = c0y - c1y;
         float rx = px - c0x, ry = py - c0y;
         float rl = sqrtf(rx * rx + ry * ry);
         float rdx = rx / rl, rdy = ry / rl;
         float a    = rdx * rdx + rdy * rdy;
         float b    = 2.0f * (rdx * dfx + rdy * dfy);
-        float cc   = (dfx * dfx + dfy * dfy) - r1 * r1;
         float disc = b * b - 4.0f * a * cc;
         if (disc >= 0.0f) {
             float t   = (-b + sqrtf(fabsf(disc))) / (2.0f * a);
@@ -557,7 +577,13 @@ __device__ void eval_paint(uint32_t pattern, const vkb_gradient *g, float W, flo
         for (int k = 0; k < 4; k++) c[k] = g->colors[0][k];
         mix4(c, g->colors[1], smoothstepf(g->stops[0], g->stops[1], grad));
         for (uint32_t i = 2; i < g->count; i++) mix4(c, g->colors[i], smoothstepf(g->stops[i - 1], g->stops[i], grad));
-    } else {
+    }
+}
+__device__ __forceinline__ void eval_paint(uint32_t pattern, const vkb_gradient *g, const float *gp, float W, float H, uint32_t solid, float opacity, float fx,
+                                           float fy, float out[4], const float *lut) {
+    float c[4];
+    if (pattern == VKB_PAT_LINEAR || pattern == VKB_PAT_RADIAL) eval_gradient(pattern, g, gp, W, H, fx, fy, c);  // out of line: keeps the solid-colour loop small
+    else {
         c[0] = lut[solid & 0xFF];  // lut[i] == (float)i / 255.0f exactly
         c[1] = lut[(solid >> 8) & 0xFF];
         c[2] = lut[(solid >> 16) & 0xFF];
@@ -930,7 +956,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
             }
             if (__any_sync(0xffffffffu, nmax != 0)) {
                 float src[4];
-                eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
+                eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
                            (float)(py + a.sd.origin_y) + 0.5f, src, lut);
                 const float ia = 1.0f - src[3];
                 if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
@@ -1121,7 +1147,7 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
             if (CLIP && (stw[0] & VKB_STENCIL_CLIP)) cov = 0.0f;
             if (!__any_sync(0xffffffffu, cov > 0.0f)) continue;
             float src[4];
-            eval_paint(pattern, a.grads + pt.gradient, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
+            eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
                        (float)(py + a.sd.origin_y) + 0.5f, src, lut);
             if (cov > 0.0f) {
 #pragma unroll
