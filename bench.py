@@ -406,6 +406,13 @@ def run_ours(args):
         fine_src = "events around the kernel in %d plain-launch steps run before the timed region" % args.steps
     achieved = alg_bytes / (fine_ms * 1e-3) / 1e9
     stage = {k: val / args.steps for k, val in st_stages["ms_stage"].items()}
+    traffic = None   # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture of this workload
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if w in tj and args.coverage == "msaa" and world == 1:
+            traffic = int(tj[w]["dram_bytes_per_launch"])
+    except Exception:
+        pass
     name, unit = UNITS[w]
     line = {
         "metric": name, "value": (1 if striped else world) * units / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -421,7 +428,7 @@ def run_ours(args):
                 "readback_ms": parts[2] / args.steps * 1e3, "h2d_bytes_wire": int(st["h2d_bytes"])},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "fine_k<4>" if args.coverage == "msaa" else "fine_analytic_k", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "algorithmic_bytes": int(alg_bytes), "kernel_ms": fine_ms, "kernel_ms_source": fine_src, "peak_source": peak_src,
+                     "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "kernel_ms": fine_ms, "kernel_ms_source": fine_src, "peak_source": peak_src,
                      "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
         "stage_ms": stage, "stage_ms_note": "plain launches with events between stages: %.3f ms per step" % (st_stages["ms_total"] / args.steps),
     }

@@ -967,7 +967,8 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
 #pragma unroll
                 for (int s = 0; s < S; s++) two = two && (n[s] == 0 || n[s] == nmax);
                 // warp-uniform choice (a divergent one would make the warp execute both variants)
-                if (__all_sync(0xffffffffu, uni && two)) {  // every sample holds the same colour and is blended nmax times or not at all
+                const bool opaque = src[3] >= 1.0f;  // dst * (1 - 1) vanishes: the result does not depend on what a sample holds
+                if (__all_sync(0xffffffffu, (uni || opaque) && two)) {  // one result per pixel: same colour in every sample (or an opaque source), blended nmax times or not at all
                     uint32_t c = col[0];
                     for (int32_t r = 0; r < nmax; r++) c = blend_over(c, src, ia, lut);
 #pragma unroll
