@@ -29,14 +29,16 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-SIZES = {"c1": 1024, "c2": 4096, "c3": 4096, "c4": 8192, "c5a": 16384}
+SIZES = {"c1": 1024, "c2": 4096, "c3": 4096, "c4": 8192, "c5a": 16384, "c5b": 1024}
+C5B_CANVASES, C5B_BATCH = 1024, 16   # 1024 independent 1024^2 canvases, 16 per flush (one batch surface of 1024 x 16384)
 UNITS = {"c1": ("tiger_frames_per_s", "frames/s"), "c2": ("fill_Mpix_per_s", "Mpix/s"), "c3": ("stroke_Msegments_per_s", "Msegments/s"),
-         "c4": ("fill_Mpix_per_s", "Mpix/s"), "c5a": ("fill_Mpix_per_s", "Mpix/s")}
+         "c4": ("fill_Mpix_per_s", "Mpix/s"), "c5a": ("fill_Mpix_per_s", "Mpix/s"), "c5b": ("tiger_frames_per_s", "frames/s")}
 WORKLOAD_NAMES = {
     "c1": "C1 tiger.svg via nanoSVG, 1024x1024, 4 samples, even-odd fills + miter strokes",
     "c2": "C2 100k random self-intersecting polygons, one fill each, 4096x4096, 4 samples",
     "c3": "C3 1M-segment polyline stroke, width 3, round joins/caps, dash {10,6}, 4096x4096, 4 samples",
     "c4": "C4 50k cubic-Bezier paths, linear/radial gradient fills, OVER, 8192x8192, 4 samples",
+    "c5b": "C5b batch of 1024 independent 1024x1024 tiger canvases (per-canvas affine jitter), 16 canvases per flush in one batch surface, canvases split across ranks",
     "c5a": "C5a 16384x16384 surface, 5M-segment mix (C2-style polygons + C3-style dashed polylines), sharded by tile-row stripes, NCCL all-gather",
 }
 
@@ -115,6 +117,19 @@ def build_scene(workload, seed, rule, n_limit=None, first=0):
                 g.stroke()
         nseg = int(sum(len(p) for p in polys)) + sum(len(l) - 1 for l in lines)
         return emit, size * size / 1e6, dict(n_paths=len(polys) + len(lines), n_segments=nseg)
+    if workload == "c5b":   # one flush worth of canvases; the step replays it for every batch this rank owns
+        w, h, shapes = scenes.load_nsvg(os.path.join(ROOT, "tests", "golden", "tiger.nsvg.bin"))
+        r = scenes.SplitMix64(900 + seed)
+        jit = [(r.uniform(-2, 2), r.uniform(-2, 2)) for _ in range(C5B_BATCH)]
+
+        def emit(g):
+            for i, (jx, jy) in enumerate(jit):
+                if hasattr(g, "set_canvas"):
+                    g.set_canvas(i)
+                g.identity_matrix()
+                g.translate(jx, jy)
+                scenes.render_nsvg(g, shapes)
+        return emit, float(C5B_BATCH), dict(n_paths=len(shapes) * C5B_BATCH, n_segments=int(sum((len(p) - 1) // 3 for s in shapes for p, _ in s["paths"])) * C5B_BATCH)
     if workload == "c1":
         w, h, shapes = scenes.load_nsvg(os.path.join(ROOT, "tests", "golden", "tiger.nsvg.bin"))
         if n_limit:
@@ -212,13 +227,16 @@ def _ref_worker(args):
     return dt, info, kind
 
 
-SAMPLE = {"c1": None, "c2": 1500, "c3": 40000, "c4": 200, "c5a": 1000}  # units of work per host thread per step (paths / segments)
-FULL = {"c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000, "c5a": 476000}
+SAMPLE = {"c5b": None, "c1": None, "c2": 1500, "c3": 40000, "c4": 200, "c5a": 1000}  # units of work per host thread per step (paths / segments)
+FULL = {"c5b": 239 * C5B_CANVASES, "c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000, "c5a": 476000}
 
 
 def reference_step(workload, seed, rule, cores, pool):
     """one bounded step on `cores` host processes; returns (seconds, fraction of the full scene processed, kind)."""
     n = SAMPLE[workload]
+    if workload == "c5b":  # independent canvases: one whole tiger canvas per host process
+        res = pool.map(_ref_worker, [("c1", seed, rule, None, 0) for _ in range(cores)])
+        return max(r[0] for r in res), cores / float(C5B_CANVASES), res[0][2]
     if workload == "c3":   # one polyline: a single context is strictly serial in the reference; threads get separate lines
         jobs = [(workload, seed + i, rule, n, 0) for i in range(cores)]
     elif n is None:
@@ -263,7 +281,7 @@ def run_reference(args):
 
 
 def build_units(workload):
-    return {"c1": 1.0, "c2": 4096 * 4096 / 1e6, "c3": 1.0, "c4": 8192 * 8192 / 1e6, "c5a": 16384 * 16384 / 1e6}[workload]
+    return {"c5b": float(C5B_CANVASES), "c1": 1.0, "c2": 4096 * 4096 / 1e6, "c3": 1.0, "c4": 8192 * 8192 / 1e6, "c5a": 16384 * 16384 / 1e6}[workload]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -307,9 +325,18 @@ def run_ours(args):
         y0, sh = sharding.stripe_rows(size, world)[rank]
         surf = v.Surface(dev, size, sh, full_height=size, origin_y=y0)
         emit, units, info = build_scene(w, 1, args.rule)
+    elif w == "c5b":   # strong scaling: the 1024 canvases are split across the ranks, C5B_BATCH canvases per flush
+        surf = v.Surface(dev, size, size, batch=C5B_BATCH)
+        emit, units, info = build_scene(w, 1 + rank, args.rule)
+        assert (C5B_CANVASES // C5B_BATCH) % world == 0, "world size must divide %d batches" % (C5B_CANVASES // C5B_BATCH)
+        reps = C5B_CANVASES // C5B_BATCH // world
+        units = float(C5B_CANVASES)
     else:
         surf = v.Surface(dev, size, size)
         emit, units, info = build_scene(w, 1 + rank, args.rule)
+    strong = striped or w == "c5b"
+    if w != "c5b":
+        reps = 1
     ctx = v.Context(surf)
     cs = v.CommandStream()
     emit(cs)
@@ -353,12 +380,17 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
+    e2e_one = e2e_step
+
+    def e2e_step():   # noqa: F811  (a step covers every batch this rank owns)
+        for _ in range(reps):
+            e2e_one()
     checksum = int(out_t.numpy().view(np.uint32).sum(dtype=np.uint64))
     dev.set_profiling(True)
     dev.set_stage_timing(True)
     dev.time_resident(surf, 2, True, True)   # warm the resident path (buffers sized, L2 scratch allocated)
     # ---- per-stage breakdown: plain launches with CUDA events between the stages (not the headline timing) ----
-    st_stages = dev.time_resident(surf, args.steps, True, True)
+    st_stages = dev.time_resident(surf, args.steps * reps, True, True)
     dev.set_stage_timing(False)
     use_graph = not args.no_graph
     dev.set_graphs(use_graph)
@@ -370,7 +402,7 @@ def run_ours(args):
     barrier()
     l0 = L.vkvg_b200_launch_count()
     g0 = dev.graph_replays()
-    st = dev.time_resident(surf, args.steps, True, True)
+    st = dev.time_resident(surf, args.steps * reps, True, True)
     launches = L.vkvg_b200_launch_count() - l0
     graph_replays = dev.graph_replays() - g0
     gather_ms[0] = 0.0
@@ -400,12 +432,12 @@ def run_ours(args):
     # the fine kernel's duration: CUDA events recorded around it inside the timed region (external event nodes of the replayed
     # graph); if the driver did not time those, the per-stage pass above (same kernel, plain launch) supplies it
     fine_src = "events around the kernel inside the timed graph replays"
-    fine_ms = st["ms_fine"] / args.steps
+    fine_ms = st["ms_fine"] / (args.steps * reps)   # per launch
     if not fine_ms > 0:
-        fine_ms = st_stages["ms_fine"] / args.steps
+        fine_ms = st_stages["ms_fine"] / (args.steps * reps)
         fine_src = "events around the kernel in %d plain-launch steps run before the timed region" % args.steps
     achieved = alg_bytes / (fine_ms * 1e-3) / 1e9
-    stage = {k: val / args.steps for k, val in st_stages["ms_stage"].items()}
+    stage = {k: val / (args.steps * reps) for k, val in st_stages["ms_stage"].items()}   # per flush
     traffic = None   # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture of this workload
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -415,22 +447,22 @@ def run_ours(args):
         pass
     name, unit = UNITS[w]
     line = {
-        "metric": name, "value": (1 if striped else world) * units / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if striped else "weak", "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic",
+        "metric": name, "value": (1 if strong else world) * units / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[w] if args.coverage == "msaa" else WORKLOAD_NAMES[w].replace("4 samples", "analytic coverage"),
-                   "rule": args.rule, "samples": 4 if args.coverage == "msaa" else 0, "coverage": args.coverage, "sharding": ("tile-row stripes of one surface, %.3f ms all-gather per step" % gather_step_ms) if striped else "one independent canvas per rank",
-                   "l2": "256 MiB scratch overwritten between timed steps", "launch": ("one CUDA graph replay per step (%d of %d steps)" % (graph_replays, args.steps)) if use_graph else "plain kernel launches",
+                   "rule": args.rule, "samples": 4 if args.coverage == "msaa" else 0, "coverage": args.coverage, "sharding": ("tile-row stripes of one surface, %.3f ms all-gather per step" % gather_step_ms) if striped else ("%d canvases per rank in %d flushes of %d" % (C5B_CANVASES // world, reps, C5B_BATCH) if w == "c5b" else "one independent canvas per rank"),
+                   "l2": "256 MiB scratch overwritten between timed steps", "launch": ("one CUDA graph replay per flush (%d of %d flushes)" % (graph_replays, args.steps * reps)) if use_graph else "plain kernel launches",
                    **info, "n_edges": int(n_edges),
                    "n_tile_edges": int(st["n_tile_edges"]), "n_points": int(st["n_points"]), "n_path_tiles": int(st["n_nonempty"])},
-        "e2e": {"value": (1 if striped else world) * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()),
-                "d2h_bytes_per_step": int(out_t.numel()), "ms_per_step": e2e_s * 1e3,
+        "e2e": {"value": (1 if strong else world) * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()) * reps,
+                "d2h_bytes_per_step": int(out_t.numel()) * reps, "ms_per_step": e2e_s * 1e3,
                 "host_record_ms": parts[0] / args.steps * 1e3, "upload_render_ms": parts[1] / args.steps * 1e3,
                 "readback_ms": parts[2] / args.steps * 1e3, "h2d_bytes_wire": int(st["h2d_bytes"])},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "fine_k<4>" if args.coverage == "msaa" else "fine_analytic_k", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "kernel_ms": fine_ms, "kernel_ms_source": fine_src, "peak_source": peak_src,
-                     "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
-        "stage_ms": stage, "stage_ms_note": "plain launches with events between stages: %.3f ms per step" % (st_stages["ms_total"] / args.steps),
+                     "whole_step_frac": alg_bytes * reps / (ms_step * 1e-3) / 1e9 / peak},
+        "stage_ms": stage, "stage_ms_note": "per flush, plain launches with events between stages: %.3f ms per flush" % (st_stages["ms_total"] / (args.steps * reps)),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, args.rule)
@@ -447,8 +479,8 @@ def cpu_baseline(workload, rule):
     if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
         oracle.build(ref=False)
     n = SAMPLE[workload]
-    dt, info, kind = _ref_worker((workload, 1, rule, n, 0))
-    frac = 1.0 if n is None else n / FULL[workload]
+    dt, info, kind = _ref_worker(("c1" if workload == "c5b" else workload, 1, rule, n, 0))
+    frac = (1.0 / C5B_CANVASES) if workload == "c5b" else (1.0 if n is None else n / FULL[workload])
     name, unit = UNITS[workload]
     return {"value": build_units(workload) * frac / dt, "unit": unit, "cores": 1, "kind": kind, "seconds": dt,
             "sample": ("the whole scene" if n is None else "first %d of %d units of the scene" % (n, FULL[workload])) +

@@ -133,10 +133,22 @@ enum {
     VKVG_B200_OP_SET_OPACITY,       /* opacity */
     VKVG_B200_OP_POLYLINE,          /* n x0 y0 .. : move_to the first point, line_to the others; n is a uint32 stored in the float slot bit for bit */
     VKVG_B200_OP_FLUSH,
+    VKVG_B200_OP_SET_CANVAS,        /* index (batch surfaces) */
+    VKVG_B200_OP_CLIP,
+    VKVG_B200_OP_CLIP_PRESERVE,
+    VKVG_B200_OP_RESET_CLIP,
 };
 /* ops[i] selects the call; its float arguments are consumed from args in order.  Equivalent to issuing the
  * corresponding vkvg_* calls one by one (it does exactly that).  Returns the context status. */
 vkvg_public vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *args, uint64_t n_args);
+
+/* ---- batches of independent canvases (BASELINE config C5b; SURVEY.md §8e "independent canvases") ----
+ * One surface holds `count` canvases of width x height stacked vertically (height a multiple of 16).  Draws recorded after
+ * vkvg_b200_set_canvas(ctx, i) go to canvas i: coordinates, gradients and clipping are those of a width x height surface of
+ * its own, so every canvas is bit-identical to rendering it alone — but one flush (one set of kernel launches, or one CUDA
+ * graph replay) renders all of them.  Rows [i * height, (i + 1) * height) of the surface read-back are canvas i. */
+vkvg_public VkvgSurface   vkvg_b200_surface_create_batch(VkvgDevice dev, uint32_t width, uint32_t height, uint32_t count);
+vkvg_public vkvg_status_t vkvg_b200_set_canvas(VkvgContext ctx, uint32_t index);
 
 /* ---- execution model knobs ----
  * A flush queues its ~40 kernels without any host round trip (counts that are only known on the device stay there; see

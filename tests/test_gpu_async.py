@@ -110,3 +110,40 @@ def test_flush_is_asynchronous_but_ordered(oracle_lib):
         mg.pixel_scene(o, name, 2)
     assert np.array_equal(surf.pixels(), o.pixels())
     dev.close()
+
+
+def test_batch_of_canvases_equals_separate_surfaces(oracle_lib):
+    """C5b building block: n canvases in one surface, one flush; every band equals the canvas rendered on its own"""
+    from tests.golden import make_golden2 as mg2
+    dev = v.Device(4)
+    names = ["mixed", "grad_radial", "stroke_dash", "paint", "eo", "grad_linear"]
+    surf = v.Surface(dev, 128, 128, batch=len(names) + 2)
+    ctx = v.Context(surf)
+    refs = []
+    for i, name in enumerate(names):
+        ctx.set_canvas(i)
+        ctx.identity_matrix()
+        ctx.translate(0.25 * i, -0.5 * i)      # per-canvas jitter as in the C5b configuration
+        mg.pixel_scene(ctx, name, 1)
+        o = oracle_lib.Oracle(128, 128, 4)
+        o.translate(0.25 * i, -0.5 * i)
+        mg.pixel_scene(o, name, 1)
+        refs.append(o.pixels())
+        o.close()
+    # canvas 6: clipping stays inside its canvas; canvas 7 stays empty
+    ctx.set_canvas(6)
+    ctx.identity_matrix()
+    mg2.clip_scene(ctx, "nested", 0)
+    o = oracle_lib.Oracle(128, 128, 4)
+    mg2.clip_scene(o, "nested", 0)
+    refs.append(o.pixels())
+    refs.append(np.zeros((128, 128, 4), np.uint8))
+    ctx.flush()
+    got = surf.pixels()
+    assert got.shape == (128 * 8, 128, 4)
+    for i, ref in enumerate(refs):
+        band = got[128 * i:128 * (i + 1)]
+        assert np.array_equal(band, ref), (i, int((band != ref).any(axis=2).sum()))
+    with pytest.raises(v.VkvgError):
+        ctx.set_canvas(8)
+    dev.close()

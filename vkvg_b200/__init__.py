@@ -25,7 +25,7 @@ OPS = {name: i + 1 for i, name in enumerate([
     "MOVE_TO", "LINE_TO", "CURVE_TO", "CLOSE_PATH", "NEW_PATH", "ARC", "ARC_NEGATIVE", "RECTANGLE", "FILL", "FILL_PRESERVE",
     "STROKE", "STROKE_PRESERVE", "PAINT", "SET_SOURCE_RGBA", "SET_LINE_WIDTH", "SET_LINE_CAP", "SET_LINE_JOIN",
     "SET_MITER_LIMIT", "SET_FILL_RULE", "SET_DASH", "SET_SOURCE_LINEAR", "SET_SOURCE_RADIAL", "TRANSLATE", "SCALE", "ROTATE",
-    "IDENTITY_MATRIX", "SAVE", "RESTORE", "CLEAR", "SET_OPACITY", "POLYLINE", "FLUSH"])}
+    "IDENTITY_MATRIX", "SAVE", "RESTORE", "CLEAR", "SET_OPACITY", "POLYLINE", "FLUSH", "SET_CANVAS", "CLIP", "CLIP_PRESERVE", "RESET_CLIP"])}
 
 
 class DeviceCreateInfo(C.Structure):
@@ -116,6 +116,7 @@ _SIGS = {
     "vkvg_b200_device_set_graphs": (None, [_p, _i]), "vkvg_b200_device_set_stage_timing": (None, [_p, _i]),
     "vkvg_b200_device_graph_replays": (C.c_uint64, [_p]),
     "vkvg_b200_device_set_coverage_mode": (_i, [_p, _i]), "vkvg_b200_device_get_coverage_mode": (_i, [_p]),
+    "vkvg_b200_surface_create_batch": (_p, [_p, _u, _u, _u]), "vkvg_b200_set_canvas": (_i, [_p, _u]),
     "vkvg_b200_surface_create_stripe": (_p, [_p, _u, _u, _u, _u]), "vkvg_b200_surface_copy_to_device": (_i, [_p, _p]),
 }
 
@@ -220,12 +221,17 @@ class Device:
 
 
 class Surface:
-    def __init__(self, dev, width, height, full_height=None, origin_y=0):
-        """full_height / origin_y: this surface is the stripe [origin_y, origin_y + height) of a taller logical surface."""
+    def __init__(self, dev, width, height, full_height=None, origin_y=0, batch=None):
+        """full_height / origin_y: this surface is the stripe [origin_y, origin_y + height) of a taller logical surface.
+        batch=n: n independent width x height canvases stacked in one surface (pixels() returns (n * height, width, 4))."""
         self.dev = dev
         self.width, self.height = width, height
         self.full_height, self.origin_y = full_height or height, origin_y
-        if full_height is None:
+        self.batch = batch
+        if batch:
+            self.h = lib().vkvg_b200_surface_create_batch(dev.h, width, height, batch)
+            self.height = height * batch
+        elif full_height is None:
             self.h = lib().vkvg_surface_create(dev.h, width, height)
         else:
             self.h = lib().vkvg_b200_surface_create_stripe(dev.h, width, full_height, origin_y, height)
@@ -342,6 +348,11 @@ class Context:
 
     def set_source_radial(self, cx0, cy0, r0, cx1, cy1, r1, stops):
         self._grad(lib().vkvg_pattern_create_radial(cx0, cy0, r0, cx1, cy1, r1), stops)
+
+    def set_canvas(self, index):
+        st = lib().vkvg_b200_set_canvas(self.h, index)
+        if st:
+            raise VkvgError("vkvg_b200_set_canvas: status %d" % st)
 
     def path_extents(self):
         x1, y1, x2, y2 = _f(), _f(), _f(), _f()

@@ -71,6 +71,7 @@ struct vkb_surface_impl {
     vkb_device_impl *dev;
     uint32_t         w, h;
     uint32_t         full_h, origin_y;  // logical surface this one is a stripe of (full_h == h, origin_y == 0 otherwise)
+    uint32_t         band_h = 0;        // batch surface: height of one canvas (full_h == band_h), 0 otherwise
     DevBuf           image;
     DevBuf           ms_image, tile_ms, ms_mask;  // per-sample plane + per-tile validity flags (allocated by the first render)
     DevBuf           stencil;                     // per-sample clip / save bits (allocated by the first flush that clips)
@@ -161,6 +162,7 @@ void vkb_surface_clear(vkb_surface_impl *s) {
     s->known_clear = true;
     s->stencil_live = false;  // vkvg_clear wipes the stencil attachment too (src/vkvg_context.c:745-752)
 }
+void vkb_surface_set_band_height(vkb_surface_impl *s, uint32_t band_h) { s->band_h = band_h; }
 void vkb_surface_stencil_reset(vkb_surface_impl *s) {
     if (s->stencil_live) finish_pending(s->dev);
     s->stencil_live = false;
@@ -502,7 +504,8 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     vkb_launch_draw_bbox(edges, edraw, cv[VKC_EDGES], C, nd, d->draw_bbox.as<int32_t>(), st);
     unsigned long long *dc = d->draw_counts.as<unsigned long long>();
     const bool clip_draws = draws && d->has_clip_draws, stencil_ops = draws && d->has_stencil_ops;
-    vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), clip_draws ? draws : nullptr, nd, sd, d->draw_rect.as<int32_t>(), dc, st);
+    vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), (clip_draws || sd.band_tiles) ? draws : nullptr, d->xforms.as<vkb_xform>(), nd, sd,
+                          d->draw_rect.as<int32_t>(), dc, st);
     vkb_exclusive_scan<unsigned long long, unsigned long long>(dc, dc, nd, (unsigned long long *)(totals + 4), d->scan, st);
     vkb_launch_split_bases(dc, nd, d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), st);
     commit_pt_k<<<1, 1, 0, st>>>(C, totals);
@@ -821,7 +824,8 @@ static void fill_stats(vkb_device_impl *d, const vkb_counts &h, vkb_stats &S, bo
 // replay it may ask for) then happens in finish_pending, which every entry point that touches the device calls first.
 static int run_flush(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats, bool allow_async) {
     cudaStream_t st = d->stream;
-    SurfaceDesc  sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE, surf->full_h, surf->origin_y};
+    SurfaceDesc  sd = {surf->w, surf->h, samples, (surf->w + VKB_TILE - 1) / VKB_TILE, (surf->h + VKB_TILE - 1) / VKB_TILE, surf->full_h, surf->origin_y,
+                       surf->band_h / VKB_TILE};
     const SurfFlags before = surf_flags(surf);
     const bool      geometry_only = (cap && cap->geometry_only) || d->n_draws == 0;
     for (int attempt = 0; attempt < 16; attempt++) {
@@ -900,7 +904,7 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
     finish_pending(d);
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     vkb_surface_impl *surf = vkb_surface_new(d, w, h, h, 0);
-    SurfaceDesc sd = {w, h, samples, (w + VKB_TILE - 1) / VKB_TILE, (h + VKB_TILE - 1) / VKB_TILE, h, 0};
+    SurfaceDesc sd = {w, h, samples, (w + VKB_TILE - 1) / VKB_TILE, (h + VKB_TILE - 1) / VKB_TILE, h, 0, 0};
     d->totals.ensure(16 * 8, st);
     d->edges.ensure((n + 1) * 16, st);
     d->edge_draw.ensure((n + 1) * 4, st);

@@ -42,6 +42,10 @@ struct SurfaceDesc {
     // the logical height, and snapped y coordinates are shifted by origin_y pixels (a multiple of the tile size), so a
     // stripe holds exactly the pixels the same rows of the whole surface would hold
     uint32_t full_height, origin_y;
+    // a batch of independent canvases stacked vertically in one surface (vkvg_b200_surface_create_batch): canvas b owns the
+    // band_tiles tile rows from b * band_tiles; every draw carries its canvas (vkb_xform.band), its geometry is snapped in
+    // canvas coordinates (so each canvas holds exactly the pixels it would hold alone) and shifted by whole tiles.  0: no bands
+    uint32_t band_tiles;
 };
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
@@ -61,7 +65,7 @@ struct BinBuffers {  // all device pointers
 void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
                           cudaStream_t s);
 // draws may be null (raw edge lists); a VKB_DRAW_CLIP draw takes the whole surface as its rectangle
-void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
+void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, const vkb_xform *xforms, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
                            unsigned long long *tile_row_counts, cudaStream_t s);
 void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s);
 void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,

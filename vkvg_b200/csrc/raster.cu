@@ -71,11 +71,13 @@ fill_edges_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, 
     uint32_t j = find_job(job_base, n_jobs, item), k = item - job_base[j];
     uint32_t s = job_sp[j], first = sp_first[s], n = sp_count[s], d = job_draw[j];
     float2   a = pts[first + k], b = pts[first + (k + 1 == n ? 0 : k + 1)];
-    const float *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
+    const vkb_xform &xf = xforms[draws[d].xform_stroke & 0xFFFF];
+    const float     *m  = xf.mat;
     vkb_edge e;
     vs_snap(m, (float)sd.width, (float)sd.full_height, a.x, a.y, e.x0, e.y0);
     vs_snap(m, (float)sd.width, (float)sd.full_height, b.x, b.y, e.x1, e.y1);
-    e.y0 -= (int32_t)sd.origin_y * 256; e.y1 -= (int32_t)sd.origin_y * 256;
+    const int32_t yoff = (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256;
+    e.y0 += yoff; e.y1 += yoff;
     edges[item]     = e;
     edge_draw[item] = d;
 }
@@ -108,14 +110,14 @@ __device__ __forceinline__ void tri_idx(const uint32_t *inds, uint32_t n_tris, l
     if (t < 0 || t >= (long long)n_tris) { i[0] = i[1] = i[2] = 0xffffffffu; return; }
     i[0] = inds[3 * t]; i[1] = inds[3 * t + 1]; i[2] = inds[3 * t + 2];
 }
-__device__ __forceinline__ int tri_sign(const float2 *verts, uint32_t n_verts, const uint32_t (&i)[3], const float *m, SurfaceDesc sd, int32_t (&x)[3],
-                                        int32_t (&y)[3]) {
+__device__ __forceinline__ int tri_sign(const float2 *verts, uint32_t n_verts, const uint32_t (&i)[3], const float *m, int32_t yoff, SurfaceDesc sd,
+                                        int32_t (&x)[3], int32_t (&y)[3]) {
     if (i[0] >= n_verts || i[1] >= n_verts || i[2] >= n_verts) return 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         float2 p = verts[i[k]];
         vs_snap(m, (float)sd.width, (float)sd.full_height, p.x, p.y, x[k], y[k]);
-        y[k] -= (int32_t)sd.origin_y * 256;
+        y[k] += yoff;
     }
     long long area = (long long)(x[1] - x[0]) * (y[2] - y[0]) - (long long)(x[2] - x[0]) * (y[1] - y[0]);
     return area > 0 ? -1 : (area < 0 ? 1 : 0);  // cross > 0 winds -1 under our convention: such a triangle is reversed
@@ -135,8 +137,10 @@ tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, cons
         uint32_t mid = (lo + hi) >> 1;
         if ((uint32_t)(item_offsets[sdraw_first_item[mid]] >> 32) <= 3 * t) lo = mid; else hi = mid;
     }
-    const uint32_t d = sdraw_id[lo];
-    const float   *m = xforms[draws[d].xform_stroke & 0xFFFF].mat;
+    const uint32_t   d  = sdraw_id[lo];
+    const vkb_xform &xf = xforms[draws[d].xform_stroke & 0xFFFF];
+    const float     *m  = xf.mat;
+    const int32_t    yoff = (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256;
     uint32_t       i0[3], ip1[3], ip2[3], im1[3], im2[3];
     tri_idx(inds, n_tris, (long long)t, i0);
     tri_idx(inds, n_tris, (long long)t + 1, ip1);
@@ -144,7 +148,7 @@ tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, cons
     tri_idx(inds, n_tris, (long long)t - 1, im1);
     tri_idx(inds, n_tris, (long long)t - 2, im2);
     int32_t x[3], y[3], nx[3], ny[3];
-    const int sg = tri_sign(verts, n_verts, i0, m, sd, x, y);
+    const int sg = tri_sign(verts, n_verts, i0, m, yoff, sd, x, y);
     int       sg_next = 2, sg_prev = 2;  // 2: not evaluated yet (vertices of a neighbour share this draw's matrix: shared indices)
     vkb_edge  e[3];
 #pragma unroll
@@ -157,13 +161,13 @@ tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, cons
         bool           drop = false;
         if (tri_has(ip1, u, v)) {
             if (!tri_has(im1, u, v) && !tri_has(ip2, u, v)) {
-                if (sg_next == 2) sg_next = tri_sign(verts, n_verts, ip1, m, sd, nx, ny);
+                if (sg_next == 2) sg_next = tri_sign(verts, n_verts, ip1, m, yoff, sd, nx, ny);
                 // direction of u->v inside the neighbour after ITS normalisation; opposite to ours (which is u->v) cancels
                 drop = sg_next != 0 && tri_dir(ip1, u, v) * sg_next < 0;
             }
         } else if (tri_has(im1, u, v)) {
             if (!tri_has(im2, u, v)) {
-                if (sg_prev == 2) sg_prev = tri_sign(verts, n_verts, im1, m, sd, nx, ny);
+                if (sg_prev == 2) sg_prev = tri_sign(verts, n_verts, im1, m, yoff, sd, nx, ny);
                 drop = sg_prev != 0 && tri_dir(im1, u, v) * sg_prev < 0;
             }
         }
@@ -243,27 +247,36 @@ __device__ __forceinline__ int32_t floor_div(int32_t a, int32_t b) {  // b > 0
     return (a % b < 0) ? q - 1 : q;
 }
 // tile rectangle of each draw (clipped to the surface) and its path-tile / row counts packed as lo | hi<<32
-__global__ void draw_rects_k(const int32_t *bbox, const vkb_draw *draws, uint32_t n_draws, SurfaceDesc sd, int32_t *rect, unsigned long long *counts) {
+__global__ void draw_rects_k(const int32_t *bbox, const vkb_draw *draws, const vkb_xform *xforms, uint32_t n_draws, SurfaceDesc sd, int32_t *rect,
+                             unsigned long long *counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_draws) return;
     int32_t mnx = bbox[4 * i], mny = bbox[4 * i + 1], mxx = bbox[4 * i + 2], mxy = bbox[4 * i + 3];
     int32_t tx0 = 0, ty0 = 0, tw = 0, th = 0;
+    // rows the draw may touch: the whole surface, or the band of its canvas on a batch surface
+    int32_t row_lo = 0, row_hi = (int32_t)sd.tiles_y - 1;
+    if (sd.band_tiles && draws) {
+        const uint32_t band = xforms[draws[i].xform_stroke & 0xFFFF].band;
+        row_lo = (int32_t)(band * sd.band_tiles);
+        row_hi = min(row_hi, row_lo + (int32_t)sd.band_tiles - 1);
+    }
     if (draws && draws[i].kind == VKB_DRAW_CLIP) {  // everything outside the clip path is affected too
-        tw = (int32_t)sd.tiles_x; th = (int32_t)sd.tiles_y;
+        tw = (int32_t)sd.tiles_x; ty0 = row_lo; th = max(row_hi - row_lo + 1, 0);
+        if (th == 0) tw = 0;
     } else if (mnx <= mxx && mxx >= 0 && mxy >= 0 && mnx < (int32_t)sd.width * 256 && mny < (int32_t)sd.height * 256) {
         tx0         = max(floor_div(mnx, VKB_TILE_FX), 0);
-        ty0         = max(floor_div(mny, VKB_TILE_FX), 0);
+        ty0         = max(floor_div(mny, VKB_TILE_FX), row_lo);
         int32_t tx1 = min(floor_div(mxx, VKB_TILE_FX), (int32_t)sd.tiles_x - 1);
-        int32_t ty1 = min(floor_div(mxy, VKB_TILE_FX), (int32_t)sd.tiles_y - 1);
+        int32_t ty1 = min(floor_div(mxy, VKB_TILE_FX), row_hi);
         tw = tx1 - tx0 + 1; th = ty1 - ty0 + 1;
         if (tw <= 0 || th <= 0) tw = th = 0;
     }
     rect[4 * i] = tx0; rect[4 * i + 1] = ty0; rect[4 * i + 2] = tw; rect[4 * i + 3] = th;
     counts[i] = (unsigned long long)((uint32_t)(tw * th)) | ((unsigned long long)(uint32_t)th << 32);
 }
-void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
+void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, const vkb_xform *xforms, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
                            unsigned long long *tile_row_counts, cudaStream_t s) {
-    draw_rects_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, draws, n_draws, sd, draw_rect, tile_row_counts);
+    draw_rects_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, draws, xforms, n_draws, sd, draw_rect, tile_row_counts);
     VKB_LAUNCHED();
 }
 __global__ void split_bases_k(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi) {
@@ -810,6 +823,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
     const size_t   pix    = (size_t)py * a.sd.width + px;
     const size_t   mspix  = ((size_t)tile * 256 + threadIdx.x) * S;  // per-sample plane is tile-major, in thread order
     const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
+    const uint32_t band_y0 = a.sd.band_tiles ? (ty / a.sd.band_tiles) * a.sd.band_tiles * VKB_TILE : 0u;  // first pixel row of this tile's canvas
 
     uint32_t col[S];
     {
@@ -957,7 +971,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
             if (__any_sync(0xffffffffu, nmax != 0)) {
                 float src[4];
                 eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
-                           (float)(py + a.sd.origin_y) + 0.5f, src, lut);
+                           (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut);
                 const float ia = 1.0f - src[3];
                 if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
                     nmax = 1;
@@ -1051,6 +1065,7 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
     const bool     inside = px < a.sd.width && py < a.sd.height;
     const size_t   pix    = (size_t)py * a.sd.width + px;
     const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
+    const uint32_t band_y0 = a.sd.band_tiles ? (ty / a.sd.band_tiles) * a.sd.band_tiles * VKB_TILE : 0u;  // first pixel row of this tile's canvas
 
     uint32_t col  = (!a.dst_is_clear && inside) ? a.image[pix] : 0u;
     uint32_t stw[1] = {(CLIP && a.stencil_in) ? a.stencil[(size_t)tile * 256 + threadIdx.x] : 0u};  // one stencil byte per pixel in this mode
@@ -1149,7 +1164,7 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
             if (!__any_sync(0xffffffffu, cov > 0.0f)) continue;
             float src[4];
             eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
-                       (float)(py + a.sd.origin_y) + 0.5f, src, lut);
+                       (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut);
             if (cov > 0.0f) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) src[k] *= cov;

@@ -102,6 +102,7 @@ void              vkb_surface_clear(vkb_surface_impl *s);
 // clip support: forget the stencil plane (a new context clears the stencil attachment with its first render pass,
 // src/vkvg_context.c:44-49) and the whole-plane spill used every six nested clip saves
 void              vkb_surface_stencil_reset(vkb_surface_impl *s);
+void              vkb_surface_set_band_height(vkb_surface_impl *s, uint32_t band_h);  // batch of canvases stacked in one surface
 int               vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples);
 int               vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples);
 // premultiplied RGBA8 rows, or un-premultiplied as vkvg_surface_write_to_memory does; synchronous

@@ -67,8 +67,9 @@ struct vkb_draw {
 };
 static_assert(sizeof(vkb_draw) == 32, "vkb_draw layout");
 struct vkb_xform {       // CTM at draw time: xx yx xy yy x0 y0
-    float mat[6];
-    float pad[2];
+    float    mat[6];
+    uint32_t band;       // canvas of a batch surface the draw goes to (0 on ordinary surfaces)
+    uint32_t pad;
 };
 struct vkb_stroke {      // stroke parameters (src/vkvg_context.c:830-832, internal.c:245-252)
     float    hw, lhMax, arcStep;

@@ -45,6 +45,7 @@ struct _vkvg_surface_t {
     VkvgDevice        dev;
     uint32_t          width, height;
     vkb_surface_impl *impl;
+    uint32_t          canvas_height, n_canvases;  // batch surfaces (vkvg_b200_surface_create_batch); 0 otherwise
 };
 struct _vkvg_pattern_t {
     vkvg_status_t       status;
@@ -105,6 +106,7 @@ struct _vkvg_context_t {
     // about the stencil relative to the last saved state, and how many clip saves are stacked
     int                curClipState;
     uint32_t           curSavBit;
+    uint32_t           canvas;  // batch surfaces: the canvas later draws go to (vkvg_b200_set_canvas)
 };
 
 // ====================================================================================================
@@ -245,6 +247,7 @@ static VkvgSurface create_surface(VkvgDevice dev, uint32_t width, uint32_t heigh
     surf->dev        = dev;
     surf->width      = width > 1 ? width : 1;
     surf->height     = height > 1 ? height : 1;
+    surf->canvas_height = surf->n_canvases = 0;
     {
         std::lock_guard<std::mutex> lk(dev->mtx);
         surf->impl = vkb_surface_new(dev->impl, surf->width, surf->height, full_height ? full_height : surf->height, origin_y);
@@ -254,6 +257,24 @@ static VkvgSurface create_surface(VkvgDevice dev, uint32_t width, uint32_t heigh
     return surf;
 }
 VkvgSurface vkvg_surface_create(VkvgDevice dev, uint32_t width, uint32_t height) { return create_surface(dev, width, height, 0, 0); }
+// `count` independent canvases of width x height stacked in one surface of height count * height: draws recorded after
+// vkvg_b200_set_canvas(ctx, i) land in canvas i exactly as they would on a surface of their own (same snapping, same
+// gradients, clipped to the canvas), and one flush renders them all
+VkvgSurface vkvg_b200_surface_create_batch(VkvgDevice dev, uint32_t width, uint32_t height, uint32_t count) {
+    if (height == 0 || height % VKB_TILE != 0 || count == 0 || (uint64_t)height * count > 0x7fffffu) return (VkvgSurface)&s_invalid_surface;
+    VkvgSurface surf = create_surface(dev, width, height * count, height, 0);
+    if (vkvg_surface_status(surf)) return surf;
+    surf->canvas_height = height; surf->n_canvases = count;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    vkb_surface_set_band_height(surf->impl, height);
+    return surf;
+}
+vkvg_status_t vkvg_b200_set_canvas(VkvgContext ctx, uint32_t index) {
+    if (vkvg_status(ctx)) return vkvg_status(ctx);
+    if (!ctx->pSurf->n_canvases ? index != 0 : index >= ctx->pSurf->n_canvases) return VKVG_STATUS_INVALID_INDEX;
+    ctx->canvas = index;
+    return VKVG_STATUS_SUCCESS;
+}
 VkvgSurface vkvg_b200_surface_create_stripe(VkvgDevice dev, uint32_t width, uint32_t full_height, uint32_t origin_y, uint32_t height) {
     if (origin_y % VKB_TILE != 0 || origin_y + height > full_height) return (VkvgSurface)&s_invalid_surface;
     return create_surface(dev, width, height, full_height, origin_y);
@@ -424,6 +445,7 @@ static void init_ctx(VkvgContext ctx) {  // _init_ctx :24-61
     ctx->clear_pending = false;
     ctx->curClipState = CLIP_STATE_NONE;
     ctx->curSavBit = 0;
+    ctx->canvas = 0;
 }
 static void clear_path(VkvgContext ctx) {  // _clear_path, internal.c:199-206
     ctx->path_first_sp = (uint32_t)ctx->batch.subpaths.size();
@@ -878,9 +900,9 @@ static void     flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident
 static void     reserve_draw_tables(VkvgContext ctx);
 static void     finish_path(VkvgContext ctx, uint32_t flags);
 static void stencil_op(VkvgContext ctx, uint32_t rule, uint32_t bit) {
-    vkb_draw d;
-    memset(&d, 0, sizeof d);
-    d.kind = VKB_DRAW_STENCIL;
+    reserve_draw_tables(ctx);
+    vkb_draw d = base_draw(ctx, VKB_DRAW_STENCIL, rule);  // (registers the transform entry that carries the canvas of a batch surface)
+    d.n_subpaths = 0; d.gradient = 0;
     d.rule_pattern = rule;
     uint32_t sh = 0;
     while (bit >> (sh + 1)) sh++;
@@ -984,10 +1006,10 @@ static vkb_draw base_draw(VkvgContext ctx, uint32_t kind, uint32_t rule) {
     d.n_subpaths    = (uint32_t)ctx->batch.subpaths.size() - ctx->path_first_sp;
     d.color = ctx->curColor; d.opacity = ctx->opacity; d.gradient = 0;
     std::vector<vkb_xform> &xf = ctx->batch.xforms;
-    if (xf.empty() || memcmp(xf.back().mat, &ctx->mat, sizeof(float) * 6) != 0) {
+    if (xf.empty() || memcmp(xf.back().mat, &ctx->mat, sizeof(float) * 6) != 0 || xf.back().band != ctx->canvas) {
         vkb_xform x;
         memcpy(x.mat, &ctx->mat, sizeof(float) * 6);
-        x.pad[0] = x.pad[1] = 0;
+        x.band = ctx->canvas; x.pad = 0;
         xf.push_back(x);
     }
     d.xform_stroke = (uint32_t)xf.size() - 1;
@@ -1416,6 +1438,10 @@ vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_o
             break;
         }
         case VKVG_B200_OP_FLUSH: vkvg_flush(ctx); break;
+        case VKVG_B200_OP_SET_CANVAS: NEED(1); if (vkvg_b200_set_canvas(ctx, (uint32_t)a[k])) return VKVG_STATUS_INVALID_INDEX; k += 1; break;
+        case VKVG_B200_OP_CLIP: vkvg_clip(ctx); break;
+        case VKVG_B200_OP_CLIP_PRESERVE: vkvg_clip_preserve(ctx); break;
+        case VKVG_B200_OP_RESET_CLIP: vkvg_reset_clip(ctx); break;
         default: return VKVG_STATUS_INVALID_STATUS;
         }
         if (ctx->status) return ctx->status;
