@@ -145,6 +145,10 @@ vkvg_public uint32_t      vkvg_surface_get_width(VkvgSurface surf);
 vkvg_public uint32_t      vkvg_surface_get_height(VkvgSurface surf);
 vkvg_public vkvg_status_t vkvg_surface_write_to_png(VkvgSurface surf, const char *path);
 vkvg_public vkvg_status_t vkvg_surface_write_to_memory(VkvgSurface surf, unsigned char *const bitmap);
+/* reference include/vkvg.h:735, :752: a surface initialised from an image file (PNG here; the reference uses stb_image) or
+ * from width*height RGBA8 pixels, taken as they are (premultiplied when used as a source) */
+vkvg_public VkvgSurface vkvg_surface_create_from_image(VkvgDevice dev, const char *filePath);
+vkvg_public VkvgSurface vkvg_surface_create_from_bitmap(VkvgDevice dev, unsigned char *img, uint32_t width, uint32_t height);
 vkvg_public void          vkvg_surface_resolve(VkvgSurface surf);
 
 /* ---- context life cycle: reference include/vkvg.h:906-952 ---- */
@@ -190,6 +194,8 @@ vkvg_public void vkvg_fill(VkvgContext ctx);
 vkvg_public void vkvg_fill_preserve(VkvgContext ctx);
 vkvg_public void vkvg_paint(VkvgContext ctx);
 vkvg_public void vkvg_clear(VkvgContext ctx);
+/* a surface as paint: reference include/vkvg.h:1386 (source drawn with its origin at x, y in device pixels) */
+vkvg_public void vkvg_set_source_surface(VkvgContext ctx, VkvgSurface surf, float x, float y);
 /* clipping: reference include/vkvg.h:1299-1325.  The clip region is the intersection of every path clipped so far (with
  * the fill rule current at each call); it is part of the state vkvg_save / vkvg_restore stack. */
 vkvg_public void vkvg_reset_clip(VkvgContext ctx);
@@ -239,6 +245,9 @@ vkvg_public VkvgPattern   vkvg_pattern_create_linear(float x0, float y0, float x
 vkvg_public vkvg_status_t vkvg_pattern_edit_linear(VkvgPattern pat, float x0, float y0, float x1, float y1);
 vkvg_public vkvg_status_t vkvg_pattern_get_linear_points(VkvgPattern pat, float *x0, float *y0, float *x1, float *y1);
 vkvg_public VkvgPattern   vkvg_pattern_create_radial(float cx0, float cy0, float radius0, float cx1, float cy1, float radius1);
+/* reference include/vkvg.h:1790: the surface as a paint; extend NONE / REPEAT / REFLECT / PAD and nearest or bilinear filtering
+ * through vkvg_pattern_set_extend / set_filter, placed by the pattern matrix and the CTM */
+vkvg_public VkvgPattern   vkvg_pattern_create_for_surface(VkvgSurface surf);
 vkvg_public vkvg_status_t vkvg_pattern_edit_radial(VkvgPattern pat, float cx0, float cy0, float radius0, float cx1, float cy1,
                                                    float radius1);
 vkvg_public vkvg_status_t vkvg_pattern_get_color_stop_count(VkvgPattern pat, uint32_t *count);

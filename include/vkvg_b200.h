@@ -142,6 +142,10 @@ enum {
  * corresponding vkvg_* calls one by one (it does exactly that).  Returns the context status. */
 vkvg_public vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *args, uint64_t n_args);
 
+/* parity tests: the surface-paint state a draw issued now would use — source x, y, width, height and the inverse matrix
+ * (xx yx xy yy x0 y0), i.e. pushConsts.source / pushConsts.matInv of the reference (src/vkvg_context_internal.h:74-81) */
+vkvg_public void vkvg_b200_get_source_push(VkvgContext ctx, float out[10]);
+
 /* ---- batches of independent canvases (BASELINE config C5b; SURVEY.md §8e "independent canvases") ----
  * One surface holds `count` canvases of width x height stacked vertically (height a multiple of 16).  Draws recorded after
  * vkvg_b200_set_canvas(ctx, i) go to canvas i: coordinates, gradients and clipping are those of a width x height surface of

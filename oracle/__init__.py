@@ -147,6 +147,28 @@ class Oracle(_Base):
         s = np.asarray(stops, np.float32).reshape(-1, 5)
         self._lib.ovk_set_source_radial(self._ctx, cx0, cy0, r0, cx1, cy1, r1, s.ctypes.data, len(s))
 
+    def set_source_surface(self, src, x=0.0, y=0.0, extend=None, filter=None, matrix=None):
+        """src: (H, W, 4) uint8 premultiplied pixels or another Oracle; same call shapes as vkvg_b200.Context.set_source_surface"""
+        img = src.pixels() if isinstance(src, Oracle) else np.ascontiguousarray(src, np.uint8)
+        self._src_keep = img   # the oracle samples the caller's buffer
+        L = self._lib
+        L.ovk_set_source_surface.argtypes = [_p, _p, _u, _u, _f, _f, _i, _i, _p, _i]
+        h, w = img.shape[:2]
+        if extend is None and filter is None and matrix is None:
+            L.ovk_set_source_surface(self._ctx, img.ctypes.data, w, h, x, y, 0, 0, None, 0)
+            return
+        L.ovk_set_source_surface(self._ctx, img.ctypes.data, w, h, x, y, 0, 0, None, 0)
+        m = None if matrix is None else np.asarray(matrix, np.float32)
+        self._mat_keep = m
+        linear = 1 if filter in (2, 4) else 0     # VKVG_FILTER_BEST, VKVG_FILTER_BILINEAR
+        L.ovk_set_source_surface(self._ctx, img.ctypes.data, w, h, 0.0, 0.0, int(extend or 0), linear, None if m is None else m.ctypes.data, 1)
+
+    def source_push(self):
+        out = np.zeros(10, np.float32)
+        self._lib.ovk_get_source_push.argtypes = [_p, _p]
+        self._lib.ovk_get_source_push(self._ctx, out.ctypes.data)
+        return out
+
     def _arr(self, fn, dtype, per):
         ptr = _p()
         n = fn(self._ctx, C.byref(ptr))

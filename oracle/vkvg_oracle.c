@@ -73,6 +73,12 @@ typedef struct {
     uint32_t count;
 } grad_t; /* src/vkvg_pattern.h:38-47 (scalar block layout) */
 
+typedef struct {
+    const uint32_t *img; /* premultiplied RGBA8, R in the low byte */
+    uint32_t        w, h, linear, extend; /* extend: vkvg_extend_t (NONE, REPEAT, REFLECT, PAD) */
+    float           sx, sy;
+    mat_t           minv;
+} surf_src;
 struct ovk_save { /* vkvg_context_save_t, src/vkvg_context_internal.h:101-125 */
     struct ovk_save *next;
     float    lineWidth, miterLimit, dashOffset, *dashes, opacity;
@@ -81,7 +87,8 @@ struct ovk_save { /* vkvg_context_save_t, src/vkvg_context_internal.h:101-125 */
     uint32_t curColor;
     int      patType;
     grad_t   grad;
-    mat_t    mat;
+    mat_t    mat, matInv;
+    surf_src surf;
 };
 
 struct ovk_ctx {
@@ -116,6 +123,8 @@ struct ovk_ctx {
     uint32_t *inds;
     uint32_t  indCount, sizeInds;
     /* clip bookkeeping of the reference context (src/vkvg_context_internal.h:93-99, :123, :225-226) */
+    mat_t            matInv;  /* pushConsts.matInv: recomputed on every CTM change (src/vkvg_context_internal.c:672-676) */
+    surf_src         surf;    /* current surface source (patType 1) */
     int              curClipState; /* 0 none, 1 clear, 2 clip (6 = clip_saved, only in saved entries) */
     uint32_t         curSavBit;
     struct ovk_save *saved;
@@ -182,6 +191,49 @@ static inline float smoothstepf(float e0, float e1, float x) {
 static inline void mix4(float *c, const float *b, float t) {
     for (int k = 0; k < 4; k++) c[k] = c[k] * (1.0f - t) + b[k] * t;
 }
+/* A surface as paint: what the fragment shader receives (push constants source.xy / matInv, the bound image and its sampler:
+ * src/vkvg_context_internal.c:705-773) and texture(source, uv) of shaders/vkvg_main.frag:72-82 under the Vulkan
+ * texel-addressing rules (nearest / linear on unnormalised coordinates, REPEAT / MIRRORED_REPEAT / CLAMP_TO_EDGE /
+ * CLAMP_TO_BORDER with a transparent-black border).  Like the rasterisation rules this lives in the ICD, not in the reference
+ * tree: defined here from the specification. */
+static const surf_src *g_surf_src; /* source of the draw being rasterised (set by cur_paint; the oracle is single threaded) */
+static int tex_wrap(int i, int n, uint32_t mode, bool *border) {
+    if (mode == 1) { i %= n; return i < 0 ? i + n : i; }
+    if (mode == 2) {
+        int m = i % (2 * n);
+        if (m < 0) m += 2 * n;
+        m -= n;
+        return (n - 1) - (m >= 0 ? m : -(1 + m));
+    }
+    if (mode == 3) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    *border = *border || i < 0 || i >= n;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+static void tex_fetch(const surf_src *s, int i, int j, float t[4]) {
+    bool border = false;
+    i = tex_wrap(i, (int)s->w, s->extend, &border);
+    j = tex_wrap(j, (int)s->h, s->extend, &border);
+    uint32_t p = border ? 0u : s->img[(size_t)j * s->w + i];
+    for (int k = 0; k < 4; k++) t[k] = (float)((p >> (8 * k)) & 0xFF) / 255.0f;
+}
+static void sample_surface(const surf_src *s, float fx, float fy, float c[4]) {
+    float px = fx - s->sx, py = fy - s->sy;
+    float u = (s->minv.xx * px + s->minv.xy * py + s->minv.x0) / (float)s->w;
+    float v = (s->minv.yx * px + s->minv.yy * py + s->minv.y0) / (float)s->h;
+    float U = u * (float)s->w, V = v * (float)s->h;
+    if (!(fabsf(U) < 1.0e9f) || !(fabsf(V) < 1.0e9f)) { c[0] = c[1] = c[2] = c[3] = 0.0f; return; }
+    if (!s->linear) { tex_fetch(s, (int)floorf(U), (int)floorf(V), c); return; }
+    U -= 0.5f; V -= 0.5f;
+    float fi = floorf(U), fj = floorf(V);
+    float al = U - fi, be = V - fj;
+    float t00[4], t10[4], t01[4], t11[4];
+    tex_fetch(s, (int)fi, (int)fj, t00);
+    tex_fetch(s, (int)fi + 1, (int)fj, t10);
+    tex_fetch(s, (int)fi, (int)fj + 1, t01);
+    tex_fetch(s, (int)fi + 1, (int)fj + 1, t11);
+    for (int k = 0; k < 4; k++)
+        c[k] = ((1.0f - al) * (1.0f - be)) * t00[k] + (al * (1.0f - be)) * t10[k] + ((1.0f - al) * be) * t01[k] + (al * be) * t11[k];
+}
 /* shaders/vkvg_main.frag:68-157 for pattern types SOLID / LINEAR / RADIAL at fragment centre (fx,fy).
  * `src` is pc.source = (W, H, 0, 0) for gradients (src/vkvg_context_internal.c:783-787). */
 static void eval_paint(int patType, const grad_t *g, float W, float H, uint32_t solid, float opacity, float fx, float fy,
@@ -231,6 +283,9 @@ static void eval_paint(int patType, const grad_t *g, float W, float H, uint32_t 
         for (int k = 0; k < 4; k++) c[k] = g->colors[0][k];
         mix4(c, g->colors[1], smoothstepf(g->stops[0], g->stops[1], grad));
         for (uint32_t i = 2; i < g->count; i++) mix4(c, g->colors[i], smoothstepf(g->stops[i - 1], g->stops[i], grad));
+    } else if (patType == 1 /* SURFACE */) {
+        if (g_surf_src) sample_surface(g_surf_src, fx, fy, c);
+        else c[0] = c[1] = c[2] = c[3] = 0.0f;
     } else { /* SOLID: vertex colour, R8G8B8A8_UNORM attribute (src/vkvg_device_internal.c:282-284) */
         c[0] = (float)(solid & 0xFF) / 255.0f;
         c[1] = (float)((solid >> 8) & 0xFF) / 255.0f;
@@ -515,7 +570,7 @@ ovk_ctx *ovk_create(uint32_t W, uint32_t H, uint32_t S) {
     /* src/vkvg_context.c:24-61 */
     c->lineWidth = 1.f; c->miterLimit = 10.f; c->fillRule = OVK_FILL_NON_ZERO;
     c->lineCap = OVK_CAP_BUTT; c->lineJoin = OVK_JOIN_MITER;
-    c->curColor = 0xff000000; c->patType = PAT_SOLID; c->opacity = 1.0f; c->mat = MAT_ID;
+    c->curColor = 0xff000000; c->patType = PAT_SOLID; c->opacity = 1.0f; c->mat = MAT_ID; c->matInv = MAT_ID;
     return c;
 }
 void ovk_destroy(ovk_ctx *c) {
@@ -884,12 +939,45 @@ void ovk_set_source_radial(ovk_ctx *c, float cx0, float cy0, float r0, float cx1
     mat_distance(&c->mat, &g.cp[1][2], &g.cp[0][3]);
     c->grad = g; c->patType = PAT_RADIAL;
 }
-void ovk_translate(ovk_ctx *c, float dx, float dy) { mat_t t = {1, 0, 0, 1, dx, dy}; c->mat = mat_mul(&t, &c->mat); }
-void ovk_scale(ovk_ctx *c, float sx, float sy) { mat_t t = {sx, 0, 0, sy, 0, 0}; c->mat = mat_mul(&t, &c->mat); }
-void ovk_rotate(ovk_ctx *c, float r) { float s = sinf(r), co = cosf(r); mat_t t = {co, s, -s, co, 0, 0}; c->mat = mat_mul(&t, &c->mat); }
-void ovk_set_matrix(ovk_ctx *c, const float m[6]) { c->mat = (mat_t){m[0], m[1], m[2], m[3], m[4], m[5]}; }
+static void mat_invert(mat_t *m) { /* vkvg_matrix_invert, src/vkvg_matrix.c:107-147 */
+    if (m->xy == 0. && m->yx == 0.) {
+        m->x0 = -m->x0; m->y0 = -m->y0;
+        if (m->xx != 1.f) { if (m->xx == 0.) return; m->xx = 1.f / m->xx; m->x0 *= m->xx; }
+        if (m->yy != 1.f) { if (m->yy == 0.) return; m->yy = 1.f / m->yy; m->y0 *= m->yy; }
+        return;
+    }
+    float det = m->xx * m->yy - m->yx * m->xy;
+    if (!((det) * (det) >= 0.) || det == 0) return;
+    float a = m->xx, b = m->yx, c = m->xy, d = m->yy, tx = m->x0, ty = m->y0;
+    *m = (mat_t){d, -b, -c, a, c * ty - d * tx, b * tx - a * ty};
+    float s = 1 / det;
+    m->xx *= s; m->yx *= s; m->xy *= s; m->yy *= s; m->x0 *= s; m->y0 *= s;
+}
+static void set_mat_inv(ovk_ctx *c) { c->matInv = c->mat; mat_invert(&c->matInv); } /* internal.c:672-676 */
+void ovk_translate(ovk_ctx *c, float dx, float dy) { mat_t t = {1, 0, 0, 1, dx, dy}; c->mat = mat_mul(&t, &c->mat); set_mat_inv(c); }
+void ovk_scale(ovk_ctx *c, float sx, float sy) { mat_t t = {sx, 0, 0, sy, 0, 0}; c->mat = mat_mul(&t, &c->mat); set_mat_inv(c); }
+void ovk_rotate(ovk_ctx *c, float r) { float s = sinf(r), co = cosf(r); mat_t t = {co, s, -s, co, 0, 0}; c->mat = mat_mul(&t, &c->mat); set_mat_inv(c); }
+void ovk_set_matrix(ovk_ctx *c, const float m[6]) { c->mat = (mat_t){m[0], m[1], m[2], m[3], m[4], m[5]}; set_mat_inv(c); }
+/* vkvg_set_source_surface (src/vkvg_context.c:1025-1033) / vkvg_set_source with a surface pattern (:1034-1040): img is the
+ * source surface's premultiplied RGBA8 pixels (kept by the caller), (x, y) the source offset, extend a vkvg_extend_t, linear 0/1,
+ * pat_matrix the pattern matrix or NULL.  keep_offset != 0: only the pattern changes (vkvg_set_source keeps source.xy). */
+void ovk_set_source_surface(ovk_ctx *c, const uint32_t *img, uint32_t w, uint32_t h, float x, float y, int extend, int linear, const float *pat_matrix,
+                            int keep_offset) {
+    if (!keep_offset) { c->surf.sx = x; c->surf.sy = y; }
+    c->surf.img = img; c->surf.w = w; c->surf.h = h; c->surf.extend = (uint32_t)extend; c->surf.linear = (uint32_t)linear;
+    if (pat_matrix) { /* internal.c:762-770: folded into matInv until the next CTM change recomputes it */
+        mat_t m = {pat_matrix[0], pat_matrix[1], pat_matrix[2], pat_matrix[3], pat_matrix[4], pat_matrix[5]};
+        c->matInv = mat_mul(&c->matInv, &m);
+    }
+    c->patType = 1;
+}
 void ovk_get_matrix(ovk_ctx *c, float m[6]) { memcpy(m, &c->mat, sizeof(mat_t)); }
-void ovk_identity_matrix(ovk_ctx *c) { c->mat = MAT_ID; }
+void ovk_identity_matrix(ovk_ctx *c) { c->mat = MAT_ID; set_mat_inv(c); }
+/* the surface-paint part of the push constants a draw issued now would carry: source.xywh, matInv (xx yx xy yy x0 y0) */
+void ovk_get_source_push(ovk_ctx *c, float out[10]) {
+    out[0] = c->surf.sx; out[1] = c->surf.sy; out[2] = (float)c->surf.w; out[3] = (float)c->surf.h;
+    memcpy(out + 4, &c->matInv, sizeof(mat_t));
+}
 
 /* ------------------------------------------------------------------ */
 /* tessellation output                                                */
@@ -1169,6 +1257,8 @@ static void tessellate_stroke(ovk_ctx *c) {
 /* ------------------------------------------------------------------ */
 static paint_t cur_paint(ovk_ctx *c) {
     paint_t p;
+    g_surf_src = c->patType == 1 ? &c->surf : NULL;
+    if (g_surf_src) { c->surf.minv = c->matInv; }
     p.patType = c->patType; p.grad = c->grad; p.solid = c->curColor; p.opacity = c->opacity;
     return p;
 }
@@ -1439,7 +1529,7 @@ void ovk_save(ovk_ctx *c) { /* :1251-1375 */
     sav->lineWidth = c->lineWidth; sav->miterLimit = c->miterLimit; sav->dashOffset = c->dashOffset; sav->dashCount = c->dashCount;
     if (c->dashCount) { sav->dashes = (float *)malloc(sizeof(float) * c->dashCount); memcpy(sav->dashes, c->dashes, sizeof(float) * c->dashCount); }
     sav->lineCap = c->lineCap; sav->fillRule = c->fillRule; sav->opacity = c->opacity; sav->mat = c->mat;
-    sav->curColor = c->curColor; sav->patType = c->patType; sav->grad = c->grad;
+    sav->curColor = c->curColor; sav->patType = c->patType; sav->grad = c->grad; sav->matInv = c->matInv; sav->surf = c->surf;
     sav->next = c->saved;
     c->saved  = sav;
 }
@@ -1469,7 +1559,7 @@ void ovk_restore(ovk_ctx *c) { /* :1376-1512 */
     c->lineWidth = sav->lineWidth; c->miterLimit = sav->miterLimit; c->lineCap = sav->lineCap;
     c->lineJoin = OVK_JOIN_MITER; /* sav->lineJoint is never written by vkvg_save: restore reads the calloc'ed 0 (:1492) */
     c->fillRule = sav->fillRule; c->opacity = sav->opacity; c->mat = sav->mat;
-    c->curColor = sav->curColor; c->patType = sav->patType; c->grad = sav->grad;
+    c->curColor = sav->curColor; c->patType = sav->patType; c->grad = sav->grad; c->matInv = sav->matInv; c->surf = sav->surf;
     free(sav);
 }
 

@@ -71,6 +71,9 @@ void ovk_set_source_color(ovk_ctx *c, uint32_t rgba);
 void ovk_set_source_linear(ovk_ctx *c, float x0, float y0, float x1, float y1, const float *stops, uint32_t n);
 void ovk_set_source_radial(ovk_ctx *c, float cx0, float cy0, float r0, float cx1, float cy1, float r1, const float *stops,
                            uint32_t n);
+void ovk_set_source_surface(ovk_ctx *c, const uint32_t *rgba_premultiplied, uint32_t w, uint32_t h, float x, float y, int extend, int linear,
+                            const float *pattern_matrix, int keep_offset);
+void ovk_get_source_push(ovk_ctx *c, float out[10]);
 void ovk_translate(ovk_ctx *c, float dx, float dy);
 void ovk_scale(ovk_ctx *c, float sx, float sy);
 void ovk_rotate(ovk_ctx *c, float radians);

@@ -192,6 +192,44 @@ def main_clip():
     print("clip.npz", os.path.getsize(os.path.join(HERE, "clip.npz")), "bytes")
 
 
+SURF_SEQS = list(range(8))
+
+
+def checker(w, h, seed=0):
+    """premultiplied RGBA8 test image: coloured checker with a translucent diagonal band"""
+    y, x = np.mgrid[0:h, 0:w]
+    a = np.where((x + y + seed) % 7 < 2, 128, 255).astype(np.float32)
+    rgb = np.stack([(x * 37 + seed * 11) % 256, (y * 53) % 256, ((x // 3 + y // 3) % 2) * 200 + 30], -1).astype(np.float32)
+    img = np.concatenate([np.floor(rgb * a[..., None] / 255.0), a[..., None]], -1)
+    return np.ascontiguousarray(img.astype(np.uint8))
+
+
+def surface_sequence(g, seed, set_source):
+    """a sequence of CTM changes, set_source_surface and pattern-matrix calls; set_source(g, **kw) applies the source.  Returns
+    after every step what the caller wants to record (the test reads the push state through its own accessor)."""
+    r = scenes.SplitMix64(6600 + seed)
+    steps = []
+    g.translate(r.uniform(-5, 20), r.uniform(-5, 20))
+    steps.append("t")
+    if seed % 2:
+        g.rotate(r.uniform(-1, 1))
+    set_source(g, x=r.uniform(-10, 30), y=r.uniform(-10, 30))
+    steps.append("s")
+    g.scale(r.uniform(0.5, 2.5), r.uniform(0.5, 2.5))
+    steps.append("c")
+    set_source(g, x=r.uniform(-10, 30), y=r.uniform(-10, 30), extend=seed % 4, filter=4 if seed % 3 == 0 else 3,
+               matrix=[r.uniform(0.5, 2), r.uniform(-0.3, 0.3), r.uniform(-0.3, 0.3), r.uniform(0.5, 2), r.uniform(-8, 8), r.uniform(-8, 8)])
+    steps.append("p")
+    if seed % 3 == 1:
+        g.save()
+        g.translate(3.0, -2.0)
+        g.restore()
+    else:
+        g.translate(r.uniform(-3, 3), 1.0)   # a CTM change drops the pattern matrix from matInv (reference behaviour)
+    steps.append("e")
+    return steps
+
+
 def ref_path_extents(r):
     f = C.c_float
     x1, y1, x2, y2 = f(), f(), f(), f()

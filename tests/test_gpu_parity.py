@@ -498,3 +498,103 @@ def test_clip_analytic_mode_vs_oracle(oracle_lib):
     d = np.abs(got - ref)
     assert np.percentile(d, 99.9) <= 1 and (d > 1).mean() < 1e-3
     dev.close()
+
+
+# ---- surfaces as paint: set_source_surface, pattern_create_for_surface, extend / filter / matrix ----
+def _src_surface(dev, w=20, h=10, seed=0):
+    img = mg2.checker(w, h, seed)
+    L = v.lib()
+    hsurf = L.vkvg_surface_create_from_bitmap(dev.h, img.ctypes.data, w, h)
+    assert hsurf and L.vkvg_surface_status(hsurf) == 0
+    s = v.Surface.__new__(v.Surface)
+    s.dev, s.width, s.height, s.full_height, s.origin_y, s.batch, s.h = dev, w, h, h, 0, None, hsurf
+    return s, img
+
+
+@pytest.mark.parametrize("seed", mg2.SURF_SEQS)
+def test_surface_paint_push_state_equals_oracle(dev4, oracle_lib, seed):
+    src, img = _src_surface(dev4)
+    s = v.Surface(dev4, 64, 64)
+    c = v.Context(s)
+    o = oracle_lib.Oracle(64, 64, 4)
+    mg2.surface_sequence(c, seed, lambda g, **kw: g.set_source_surface(src, **kw))
+    mg2.surface_sequence(o, seed, lambda g, **kw: g.set_source_surface(img, **kw))
+    assert np.array_equal(c.source_push().view(np.uint32), o.source_push().view(np.uint32))
+    c.close()
+
+
+def test_create_from_bitmap_keeps_the_bytes(dev4):
+    src, img = _src_surface(dev4, 37, 23, 3)
+    assert np.array_equal(src.pixels(), img)
+
+
+@pytest.mark.parametrize("filt", [3, 4])          # VKVG_FILTER_NEAREST, VKVG_FILTER_BILINEAR
+@pytest.mark.parametrize("extend", [0, 1, 2, 3])  # NONE, REPEAT, REFLECT, PAD
+def test_surface_paint_pixels_vs_oracle(dev4, oracle_lib, filt, extend):
+    src, img = _src_surface(dev4, 24, 16, extend)
+    s = v.Surface(dev4, 128, 96)
+    c = v.Context(s)
+    o = oracle_lib.Oracle(128, 96, 4)
+    for g, source in ((c, src), (o, img)):
+        g.set_source_rgba(0.2, 0.2, 0.25, 1.0)
+        g.paint()
+        # plain offset blit through a rectangle
+        g.set_source_surface(source, 10.0, 8.0)
+        g.rectangle(4.0, 4.0, 50.0, 40.0)
+        g.fill()
+        # rotated / scaled CTM, explicit pattern with a matrix, filtered, extended; stroke and fill sample the same pattern
+        g.translate(64.0, 48.0)
+        g.rotate(0.35)
+        g.scale(1.7, 1.3)
+        g.set_source_surface(source, 3.0, -2.0, extend=extend, filter=filt, matrix=[0.8, 0.1, -0.2, 1.1, 2.0, 1.0])
+        g.set_opacity(0.8)
+        g.arc(0.0, 0.0, 26.0, 0.0, 6.2831855)
+        g.fill()
+        g.set_line_width(5.0)
+        g.move_to(-30.0, -25.0)
+        g.line_to(30.0, -20.0)
+        g.line_to(-10.0, 28.0)
+        g.stroke()
+        g.set_opacity(1.0)
+        g.identity_matrix()
+        g.set_source_surface(source, 90.0, 70.0, extend=extend, filter=filt)
+        g.paint()
+    c.flush()
+    got, ref = s.pixels(), o.pixels()
+    assert np.array_equal(got, ref), (filt, extend, int((got != ref).any(axis=2).sum()))
+    assert (got[..., 3] > 0).all()
+    c.close()
+
+
+def test_surface_as_layer_and_png_roundtrip(dev4, oracle_lib, tmp_path):
+    """render a layer, use it as the source of a second surface (the layer-compositing idiom), write / reload as PNG"""
+    layer = v.Surface(dev4, 64, 64)
+    lc = v.Context(layer)
+    ol = oracle_lib.Oracle(64, 64, 4)
+    for g in (lc, ol):
+        mg.pixel_scene(g, "stroke_alpha", 1, 64)
+    lc.flush()
+    dst = v.Surface(dev4, 128, 128)
+    dc = v.Context(dst)
+    od = oracle_lib.Oracle(128, 128, 4)
+    for g, source in ((dc, layer), (od, ol.pixels())):
+        g.set_source_rgba(1, 1, 1, 1)
+        g.paint()
+        for k in range(3):
+            g.set_source_surface(source, 10.0 + 25 * k, 5.0 + 30 * k)
+            g.paint()
+    dc.flush()
+    assert np.array_equal(dst.pixels(), od.pixels())
+    # PNG: the opaque result survives write_to_png -> surface_create_from_image byte for byte
+    path = str(tmp_path / "layer.png")
+    dst.write_to_png(path)
+    L = v.lib()
+    h = L.vkvg_surface_create_from_image(dev4.h, path.encode())
+    assert h and L.vkvg_surface_status(h) == 0 and (L.vkvg_surface_get_width(h), L.vkvg_surface_get_height(h)) == (128, 128)
+    back = np.zeros((128, 128, 4), np.uint8)
+    assert L.vkvg_b200_surface_read_premultiplied(h, back.ctypes.data) == 0
+    assert np.array_equal(back, dst.pixels())
+    L.vkvg_surface_destroy(h)
+    assert L.vkvg_surface_status(L.vkvg_surface_create_from_image(dev4.h, b"/no/such/file.png")) != 0
+    lc.close()
+    dc.close()

@@ -104,3 +104,48 @@ def test_clip_scenes_oracle_equals_reference_drawlist(ref_oracle, name):
         assert np.array_equal(a, b), (name, seed, int((a != b).any(axis=2).sum()))
         assert (a[..., 3] > 0).sum() > 1000
         r.close()
+
+
+# ---- surface paints: the push constants the reference builds (source offset / size, matInv with the pattern matrix folded in) ----
+def _ref_set_source(r, holder):
+    import ctypes as C
+    L = r._lib
+    L.vkvg_set_source_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+    L.vkvg_pattern_create_for_surface.restype = C.c_void_p
+    L.vkvg_pattern_create_for_surface.argtypes = [C.c_void_p]
+    for n in ("vkvg_pattern_set_matrix",):
+        getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+    L.vkvg_pattern_set_extend.argtypes = [C.c_void_p, C.c_int]
+    L.vkvg_pattern_set_filter.argtypes = [C.c_void_p, C.c_int]
+    src = L.ref_surface_create(r._dev, 20, 10)
+    holder.append(src)
+
+    def set_source(g, x=0.0, y=0.0, extend=None, filter=None, matrix=None):
+        L.vkvg_set_source_surface(g._ctx, src, x, y)
+        if extend is None and filter is None and matrix is None:
+            return
+        pat = L.vkvg_pattern_create_for_surface(src)
+        L.vkvg_pattern_set_extend(pat, extend)
+        L.vkvg_pattern_set_filter(pat, filter)
+        m = np.asarray(matrix, np.float32)
+        L.vkvg_pattern_set_matrix(pat, m.ctypes.data)
+        L.vkvg_set_source(g._ctx, pat)
+        L.vkvg_pattern_destroy(pat)
+    return set_source
+
+
+@pytest.mark.parametrize("seed", mg2.SURF_SEQS)
+def test_surface_paint_push_constants_oracle_equals_reference(ref_oracle, seed):
+    r, o = ref_oracle.Ref(64, 64, 4), ref_oracle.Oracle(64, 64, 4)
+    img = mg2.checker(20, 10)
+    mg2.surface_sequence(r, seed, _ref_set_source(r, []))
+    mg2.surface_sequence(o, seed, lambda g, **kw: g.set_source_surface(img, **kw))
+    for g in (r, o):
+        g.rectangle(1.0, 1.0, 30.0, 30.0)
+        g.fill()
+    r.flush()
+    dl = r.drawlist()
+    pushes = [np.frombuffer(bytes(dl.draws[i].push), np.float32) for i in range(dl.n_draws) if dl.draws[i].kind in (1, 2)]
+    ref = np.concatenate([pushes[-1][0:4], pushes[-1][14:20]])
+    assert np.array_equal(ref.view(np.uint32), o.source_push().view(np.uint32)), (ref, o.source_push())
+    r.close()

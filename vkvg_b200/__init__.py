@@ -95,6 +95,9 @@ _SIGS = {
     "vkvg_pattern_add_color_stop": (_i, [_p] + [_f] * 5), "vkvg_pattern_get_color_stop_count": (_i, [_p, C.POINTER(_u)]),
     "vkvg_pattern_get_type": (_i, [_p]), "vkvg_pattern_set_matrix": (None, [_p, _p]), "vkvg_pattern_get_matrix": (None, [_p, _p]),
     "vkvg_pattern_set_extend": (None, [_p, _i]), "vkvg_pattern_get_extend": (_i, [_p]),
+    "vkvg_pattern_set_filter": (None, [_p, _i]), "vkvg_pattern_get_filter": (_i, [_p]),
+    "vkvg_pattern_create_for_surface": (_p, [_p]), "vkvg_set_source_surface": (None, [_p, _p, _f, _f]),
+    "vkvg_surface_create_from_image": (_p, [_p, C.c_char_p]), "vkvg_surface_create_from_bitmap": (_p, [_p, _p, _u, _u]),
     # vkvg-svg.h
     "vkvg_svg_load": (_p, [C.c_char_p]), "vkvg_svg_load_fragment": (_p, [C.c_char_p]), "vkvg_svg_destroy": (None, [_p]),
     "vkvg_svg_get_dimensions": (None, [_p, C.POINTER(_u), C.POINTER(_u)]), "vkvg_svg_render": (None, [_p, _p, C.c_char_p]),
@@ -116,6 +119,7 @@ _SIGS = {
     "vkvg_b200_device_set_graphs": (None, [_p, _i]), "vkvg_b200_device_set_stage_timing": (None, [_p, _i]),
     "vkvg_b200_device_graph_replays": (C.c_uint64, [_p]),
     "vkvg_b200_device_set_coverage_mode": (_i, [_p, _i]), "vkvg_b200_device_get_coverage_mode": (_i, [_p]),
+    "vkvg_b200_get_source_push": (None, [_p, _p]),
     "vkvg_b200_surface_create_batch": (_p, [_p, _u, _u, _u]), "vkvg_b200_set_canvas": (_i, [_p, _u]),
     "vkvg_b200_surface_create_stripe": (_p, [_p, _u, _u, _u, _u]), "vkvg_b200_surface_copy_to_device": (_i, [_p, _p]),
 }
@@ -348,6 +352,30 @@ class Context:
 
     def set_source_radial(self, cx0, cy0, r0, cx1, cy1, r1, stops):
         self._grad(lib().vkvg_pattern_create_radial(cx0, cy0, r0, cx1, cy1, r1), stops)
+
+    def set_source_surface(self, src, x=0.0, y=0.0, extend=None, filter=None, matrix=None):
+        """src: Surface.  With extend / filter / matrix the source goes through an explicit pattern (vkvg_pattern_create_for_surface
+        + vkvg_set_source), otherwise through vkvg_set_source_surface(ctx, surf, x, y)."""
+        L = lib()
+        if extend is None and filter is None and matrix is None:
+            L.vkvg_set_source_surface(self.h, src.h, x, y)
+            return
+        L.vkvg_set_source_surface(self.h, src.h, x, y)      # sets the source offset
+        pat = L.vkvg_pattern_create_for_surface(src.h)
+        if extend is not None:
+            L.vkvg_pattern_set_extend(pat, extend)
+        if filter is not None:
+            L.vkvg_pattern_set_filter(pat, filter)
+        if matrix is not None:
+            m = np.asarray(matrix, np.float32)
+            L.vkvg_pattern_set_matrix(pat, m.ctypes.data)
+        L.vkvg_set_source(self.h, pat)
+        L.vkvg_pattern_destroy(pat)
+
+    def source_push(self):
+        out = np.zeros(10, np.float32)
+        lib().vkvg_b200_get_source_push(self.h, out.ctypes.data)
+        return out
 
     def set_canvas(self, index):
         st = lib().vkvg_b200_set_canvas(self.h, index)

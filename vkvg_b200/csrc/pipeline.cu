@@ -26,7 +26,7 @@ struct vkb_device_impl {
     size_t   stage_cap = 0;
     uint64_t *readback = nullptr;  // pinned, 16 slots
     // batch (device)
-    DevBuf   elem_hdr, elem_data, subpaths, draws, xforms, strokes, grads, dashes, paints, fcnt, scnt, pcnt, srank;
+    DevBuf   elem_hdr, elem_data, subpaths, draws, xforms, strokes, grads, dashes, paints, fcnt, scnt, pcnt, srank, surfpats;
     cudaEvent_t ev_h2d = nullptr;
     DevBuf   fjob_draw, fjob_sp, sjob_draw, sjob_sp, sdraw_id, sdraw_first_job, sdraw_first_item, extra_edges, extra_edge_draw;
     uint32_t n_elems = 0, n_sp = 0, n_draws = 0, n_fjobs = 0, n_sjobs = 0, n_sdraws = 0, n_extra = 0;
@@ -106,7 +106,7 @@ void vkb_device_close(vkb_device_impl *d) {
     cudaSetDevice(d->ordinal);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -198,6 +198,16 @@ int vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples) {
     return g_cuda_failed;
 }
 const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s) { return s->image.as<uint32_t>(); }
+// replace the contents of the surface by width*height premultiplied RGBA8 pixels from the host (vkvg_surface_create_from_bitmap)
+int vkb_surface_upload(vkb_surface_impl *s, const uint8_t *rgba) {
+    cudaSetDevice(s->dev->ordinal);
+    finish_pending(s->dev);
+    VKB_CUDA_OK(cudaMemcpyAsync(s->image.p, rgba, (size_t)s->w * s->h * 4, cudaMemcpyHostToDevice, s->dev->stream));
+    VKB_CUDA_OK(cudaStreamSynchronize(s->dev->stream));
+    s->known_clear = false;
+    if (s->tile_ms.p) VKB_CUDA_OK(cudaMemsetAsync(s->tile_ms.p, 0, (size_t)((s->w + VKB_TILE - 1) / VKB_TILE) * ((s->h + VKB_TILE - 1) / VKB_TILE), s->dev->stream));
+    return g_cuda_failed;
+}
 // device-to-device copy of the premultiplied pixels (e.g. into a tensor handed to an NCCL gather); synchronous
 int vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst) {
     cudaSetDevice(s->dev->ordinal);
@@ -322,6 +332,7 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
         {&d->strokes, b.strokes.data(), b.strokes.size() * sizeof(vkb_stroke), false},
         {&d->grads, b.grads.data(), b.grads.size() * sizeof(vkb_gradient), false},
         {&d->dashes, b.dashes.data(), b.dashes.size() * 4, false},
+        {&d->surfpats, b.surfpats.data(), b.surfpats.size() * sizeof(vkb_surfpat), false},
     };
     size_t total = 0;
     for (Src &s : srcs) if (!s.pinned) total += (s.bytes + 255) & ~(size_t)255;
@@ -574,6 +585,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->gprep.ensure((size_t)(d->n_grads + 1) * 16 * 4, st);
     vkb_launch_grad_prep(fa.grads, draws ? d->n_grads : 0, (float)sd.width, (float)sd.full_height, d->gprep.as<float>(), st);
     fa.gprep = d->gprep.as<float>();
+    fa.surfpats = d->surfpats.as<vkb_surfpat>();
     fa.image = surf->image.as<uint32_t>();
     if (samples) {  // (analytic mode, samples == 0, keeps one colour per pixel: no per-sample plane)
         bool fresh = surf->tile_ms.p == nullptr;

@@ -96,6 +96,7 @@ struct FineArgs {
     const vkb_edge     *tile_edges;
     const vkb_paint    *paints;      // per draw
     const vkb_gradient *grads;
+    const vkb_surfpat  *surfpats;    // surface paints of the batch
     const float        *gprep;       // per gradient: VKB_GPREP_FLOATS position-independent terms of the paint evaluation (grad_prep_k)
     uint32_t           *image;       // width*height premultiplied RGBA8 (resolved)
     uint32_t           *ms_image;    // per-sample colours, tile-major [tile][256][S]; valid for tiles whose tile_ms flag is set

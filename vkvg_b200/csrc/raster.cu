@@ -592,10 +592,58 @@ __device__ __noinline__ void eval_gradient(uint32_t pattern, const vkb_gradient 
         for (uint32_t i = 2; i < g->count; i++) mix4(c, g->colors[i], smoothstepf(g->stops[i - 1], g->stops[i], grad));
     }
 }
+// texture(source, uv) of shaders/vkvg_main.frag:72-82 with the sampler src/vkvg_context_internal.c:730-755 builds: nearest or
+// linear filtering of the unnormalised coordinate, address mode per vkvg_extend_t, transparent-black border — the Vulkan
+// texel-addressing rules restated (same arithmetic as oracle/vkvg_oracle.c: sample_surface).
+__device__ __forceinline__ int tex_wrap(int i, int n, uint32_t mode, bool &border) {
+    if (mode == VKB_TEX_REPEAT) { i %= n; return i < 0 ? i + n : i; }
+    if (mode == VKB_TEX_MIRROR) {
+        int m = i % (2 * n);
+        if (m < 0) m += 2 * n;
+        m -= n;
+        return (n - 1) - (m >= 0 ? m : -(1 + m));
+    }
+    if (mode == VKB_TEX_EDGE) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    border = border || i < 0 || i >= n;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+__device__ __forceinline__ void tex_fetch(const vkb_surfpat &sp, int i, int j, uint32_t mode, const float *lut, float t[4]) {
+    bool border = false;
+    i = tex_wrap(i, (int)sp.width, mode, border);
+    j = tex_wrap(j, (int)sp.height, mode, border);
+    const uint32_t p = border ? 0u : ((const uint32_t *)sp.image)[(size_t)j * sp.width + i];
+#pragma unroll
+    for (int k = 0; k < 4; k++) t[k] = lut[(p >> (8 * k)) & 0xFF];
+}
+__device__ __noinline__ void eval_surface(const vkb_surfpat *spp, float fx, float fy, float c[4], const float *lut) {
+    const vkb_surfpat sp = *spp;
+    const float px = fx - sp.sx, py = fy - sp.sy;
+    float u = (sp.minv[0] * px + sp.minv[2] * py + sp.minv[4]) / (float)sp.width;
+    float v = (sp.minv[1] * px + sp.minv[3] * py + sp.minv[5]) / (float)sp.height;
+    const uint32_t mode = sp.filter_extend >> 8;
+    float U = u * (float)sp.width, V = v * (float)sp.height;
+    if (!(fabsf(U) < 1.0e9f) || !(fabsf(V) < 1.0e9f)) { c[0] = c[1] = c[2] = c[3] = 0.0f; return; }  // NaN / far outside: border
+    if ((sp.filter_extend & 0xFF) == VKB_TEX_NEAREST) {
+        tex_fetch(sp, (int)floorf(U), (int)floorf(V), mode, lut, c);
+        return;
+    }
+    U -= 0.5f; V -= 0.5f;
+    const float fi = floorf(U), fj = floorf(V);
+    const float al = U - fi, be = V - fj;
+    float t00[4], t10[4], t01[4], t11[4];
+    tex_fetch(sp, (int)fi, (int)fj, mode, lut, t00);
+    tex_fetch(sp, (int)fi + 1, (int)fj, mode, lut, t10);
+    tex_fetch(sp, (int)fi, (int)fj + 1, mode, lut, t01);
+    tex_fetch(sp, (int)fi + 1, (int)fj + 1, mode, lut, t11);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        c[k] = ((1.0f - al) * (1.0f - be)) * t00[k] + (al * (1.0f - be)) * t10[k] + ((1.0f - al) * be) * t01[k] + (al * be) * t11[k];
+}
 __device__ __forceinline__ void eval_paint(uint32_t pattern, const vkb_gradient *g, const float *gp, float W, float H, uint32_t solid, float opacity, float fx,
-                                           float fy, float out[4], const float *lut) {
+                                           float fy, float out[4], const float *lut, const vkb_surfpat *surfpats = nullptr, uint32_t slot = 0) {
     float c[4];
     if (pattern == VKB_PAT_LINEAR || pattern == VKB_PAT_RADIAL) eval_gradient(pattern, g, gp, W, H, fx, fy, c);  // out of line: keeps the solid-colour loop small
+    else if (pattern == VKB_PAT_SURFACE) eval_surface(surfpats + slot, fx, fy, c, lut);
     else {
         c[0] = lut[solid & 0xFF];  // lut[i] == (float)i / 255.0f exactly
         c[1] = lut[(solid >> 8) & 0xFF];
@@ -971,7 +1019,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
             if (__any_sync(0xffffffffu, nmax != 0)) {
                 float src[4];
                 eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
-                           (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut);
+                           (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut, a.surfpats, pt.gradient);
                 const float ia = 1.0f - src[3];
                 if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
                     nmax = 1;
@@ -1164,7 +1212,7 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
             if (!__any_sync(0xffffffffu, cov > 0.0f)) continue;
             float src[4];
             eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
-                       (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut);
+                       (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut, a.surfpats, pt.gradient);
             if (cov > 0.0f) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) src[k] *= cov;

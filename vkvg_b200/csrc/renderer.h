@@ -54,8 +54,9 @@ struct vkb_batch {
     std::vector<vkb_stroke>   strokes;
     std::vector<vkb_gradient> grads;
     std::vector<float>        dashes;
+    std::vector<vkb_surfpat>  surfpats;
     uint32_t                  n_curves = 0;  // cubic / arc elements among elem_hdr (sizing hint for the flatten stage)
-    void clear_draws() { draws.clear(); xforms.clear(); strokes.clear(); grads.clear(); dashes.clear(); }
+    void clear_draws() { draws.clear(); xforms.clear(); strokes.clear(); grads.clear(); dashes.clear(); surfpats.clear(); }
     void clear() {
         elem_hdr.clear(); elem_data.clear(); subpaths.clear(); clear_draws(); n_curves = 0;
     }
@@ -108,6 +109,7 @@ int               vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples)
 // premultiplied RGBA8 rows, or un-premultiplied as vkvg_surface_write_to_memory does; synchronous
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply);
 const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s);
+int             vkb_surface_upload(vkb_surface_impl *s, const uint8_t *rgba);
 
 // upload `b` and render it onto `s`.  Returns 0 on success.
 int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const vkb_batch &b, vkb_capture *cap, vkb_stats *stats);

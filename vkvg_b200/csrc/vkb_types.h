@@ -52,7 +52,7 @@ enum : uint32_t {
     VKB_RULE_ST_RESTORE = 7,  // CLIP := save bit
 };
 #define VKB_STENCIL_CLIP 0x2u
-enum : uint32_t { VKB_PAT_SOLID = 0, VKB_PAT_LINEAR = 2, VKB_PAT_RADIAL = 3 };  // vkvg_pattern_type_t values
+enum : uint32_t { VKB_PAT_SOLID = 0, VKB_PAT_SURFACE = 1, VKB_PAT_LINEAR = 2, VKB_PAT_RADIAL = 3 };  // vkvg_pattern_type_t values
 
 // A draw is 32 bytes; what rarely changes between draws (CTM, stroke state) lives in side tables that grow only when
 // the state differs from the previous entry (100k fills under one CTM upload 3.2 MB of draws, not 11 MB).
@@ -86,6 +86,21 @@ struct vkb_gradient {  // vkvg_gradient_t in scalar block layout, src/vkvg_patte
     uint32_t pad[3];
 };
 static_assert(sizeof(vkb_gradient) == 368, "vkb_gradient layout");
+
+// A surface used as paint (vkvg_set_source_surface / vkvg_pattern_create_for_surface): what the fragment shader gets through
+// its push constants and sampler (shaders/vkvg_main.frag:72-82, src/vkvg_context_internal.c:705-773).  draw.gradient indexes
+// this table when the pattern is VKB_PAT_SURFACE.
+enum : uint32_t { VKB_TEX_NEAREST = 0, VKB_TEX_LINEAR = 1 };
+enum : uint32_t { VKB_TEX_BORDER = 0, VKB_TEX_REPEAT = 1, VKB_TEX_MIRROR = 2, VKB_TEX_EDGE = 3 };  // vkvg_extend_t order: NONE, REPEAT, REFLECT, PAD
+struct vkb_surfpat {
+    uint64_t image;         // device address of the source surface's resolved premultiplied RGBA8 pixels
+    uint32_t width, height;
+    uint32_t filter_extend; // VKB_TEX_* filter | address mode << 8
+    float    sx, sy;        // pushConsts.source.xy: the offset given to vkvg_set_source_surface (device pixels)
+    float    minv[6];       // pushConsts.matInv (inverse CTM, times the pattern matrix): xx yx xy yy x0 y0
+    uint32_t pad;
+};
+static_assert(sizeof(vkb_surfpat) == 56, "vkb_surfpat layout");
 
 // what the fine pass reads per draw (16 B)
 struct vkb_paint {

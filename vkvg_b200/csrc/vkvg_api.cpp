@@ -25,6 +25,8 @@ static vkvg_status_t s_null_pointer    = VKVG_STATUS_NULL_POINTER; // (kept for 
 static vkvg_status_t s_invalid_dev_ci  = VKVG_STATUS_INVALID_DEVICE_CREATE_INFO;
 static vkvg_status_t s_device_error    = VKVG_STATUS_DEVICE_ERROR;
 static vkvg_status_t s_invalid_surface = VKVG_STATUS_INVALID_SURFACE;
+static vkvg_status_t s_invalid_image   = VKVG_STATUS_INVALID_IMAGE;
+static vkvg_status_t s_file_not_found  = VKVG_STATUS_FILE_NOT_FOUND;
 
 struct _vkvg_device_t {
     vkvg_status_t    status;
@@ -56,6 +58,7 @@ struct _vkvg_pattern_t {
     vkvg_matrix_t       matrix;
     bool                hasMatrix;
     vkb_gradient        grad;
+    VkvgSurface         surf;  // VKVG_PATTERN_TYPE_SURFACE: the source (referenced)
 };
 
 struct saved_state {  // vkvg_context_save_t, src/vkvg_context_internal.h:101-125
@@ -70,6 +73,8 @@ struct saved_state {  // vkvg_context_save_t, src/vkvg_context_internal.h:101-12
     uint32_t           patType;
     vkb_gradient       grad;
     int                clippingState;  // vkvg_clip_state_t of the entry (src/vkvg_context_internal.h:93-99, :123)
+    vkvg_matrix_t      matInv;         // the rest of the reference's push constants (src/vkvg_context_internal.h:74-81)
+    float              src[4];
 };
 enum { CLIP_STATE_NONE = 0, CLIP_STATE_CLEAR = 1, CLIP_STATE_CLIP = 2, CLIP_STATE_CLIP_SAVED = 6 };
 
@@ -107,6 +112,10 @@ struct _vkvg_context_t {
     int                curClipState;
     uint32_t           curSavBit;
     uint32_t           canvas;  // batch surfaces: the canvas later draws go to (vkvg_b200_set_canvas)
+    // surface paints: pushConsts.matInv / .source of the reference (recomputed on every CTM change, src/vkvg_context_internal.c:672-676)
+    vkvg_matrix_t      matInv;
+    float              src[4];  // x, y (vkvg_set_source_surface offset), width, height of the source
+    std::vector<VkvgSurface> held, held_prev;  // sources referenced by recorded / in-flight draws
 };
 
 // ====================================================================================================
@@ -331,6 +340,26 @@ vkvg_status_t vkvg_surface_write_to_png(VkvgSurface surf, const char *path) {  /
     if (st) return st;
     return vkb_write_png(path, img.data(), surf->width, surf->height) ? VKVG_STATUS_WRITE_ERROR : VKVG_STATUS_SUCCESS;
 }
+int vkb_read_png(const char *path, std::vector<unsigned char> &rgba, uint32_t &w, uint32_t &h);  // png.cpp
+VkvgSurface vkvg_surface_create_from_bitmap(VkvgDevice dev, unsigned char *img, uint32_t width, uint32_t height) {  // :81-170
+    if (vkvg_device_status(dev)) return (VkvgSurface)&s_device_error;
+    if (!img || width == 0 || height == 0) return (VkvgSurface)&s_invalid_image;
+    VkvgSurface surf = create_surface(dev, width, height, 0, 0);
+    if (vkvg_surface_status(surf)) return surf;
+    // the reference paints the bitmap onto the cleared surface through the OVER pipeline, which leaves exactly these bytes
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    if (vkb_surface_upload(surf->impl, img)) surf->status = VKVG_STATUS_DEVICE_ERROR;
+    return surf;
+}
+VkvgSurface vkvg_surface_create_from_image(VkvgDevice dev, const char *filePath) {  // :171-186 (stb_image there; PNG only here)
+    if (vkvg_device_status(dev)) return (VkvgSurface)&s_device_error;
+    std::vector<unsigned char> rgba;
+    uint32_t w = 0, h = 0;
+    int      r = vkb_read_png(filePath, rgba, w, h);
+    if (r == 1) return (VkvgSurface)&s_file_not_found;
+    if (r) return (VkvgSurface)&s_invalid_image;
+    return vkvg_surface_create_from_bitmap(dev, rgba.data(), w, h);
+}
 const void *vkvg_b200_surface_device_pointer(VkvgSurface surf) { return vkvg_surface_status(surf) ? nullptr : vkb_surface_device_pixels(surf->impl); }
 
 // ====================================================================================================
@@ -390,7 +419,16 @@ uint32_t vkvg_pattern_get_reference_count(VkvgPattern pat) { return vkvg_pattern
 void     vkvg_pattern_destroy(VkvgPattern pat) {
     if (vkvg_pattern_status(pat)) return;
     if (--pat->references > 0) return;
+    if (pat->type == VKVG_PATTERN_TYPE_SURFACE && pat->surf) vkvg_surface_destroy(pat->surf);
     delete pat;
+}
+VkvgPattern vkvg_pattern_create_for_surface(VkvgSurface surf) {  // src/vkvg_pattern.c:28-50
+    if (!surf) return (VkvgPattern)&s_null_pointer;
+    VkvgPattern pat = new_pattern(VKVG_PATTERN_TYPE_SURFACE);
+    pat->surf = surf;
+    vkvg_surface_reference(surf);
+    if (vkvg_surface_status(surf)) { pat->status = VKVG_STATUS_INVALID_SURFACE; pat->surf = NULL; }
+    return pat;
 }
 vkvg_status_t vkvg_pattern_add_color_stop(VkvgPattern pat, float offset, float r, float g, float b, float a) {  // :149-167
     if (vkvg_pattern_status(pat)) return vkvg_pattern_status(pat);
@@ -446,6 +484,8 @@ static void init_ctx(VkvgContext ctx) {  // _init_ctx :24-61
     ctx->curClipState = CLIP_STATE_NONE;
     ctx->curSavBit = 0;
     ctx->canvas = 0;
+    vkvg_matrix_init_identity(&ctx->matInv);
+    ctx->src[0] = ctx->src[1] = ctx->src[2] = ctx->src[3] = 0;
 }
 static void clear_path(VkvgContext ctx) {  // _clear_path, internal.c:199-206
     ctx->path_first_sp = (uint32_t)ctx->batch.subpaths.size();
@@ -825,9 +865,20 @@ static void set_solid(VkvgContext ctx, uint32_t c) {  // _update_cur_pattern(ctx
 void vkvg_set_source_color(VkvgContext ctx, uint32_t c) { if (!vkvg_status(ctx)) set_solid(ctx, c); }
 void vkvg_set_source_rgb(VkvgContext ctx, float r, float g, float b) { if (!vkvg_status(ctx)) set_solid(ctx, rgbaf(r, g, b, 1)); }
 void vkvg_set_source_rgba(VkvgContext ctx, float r, float g, float b, float a) { if (!vkvg_status(ctx)) set_solid(ctx, rgbaf(r, g, b, a)); }
-static void update_cur_pattern(VkvgContext ctx, VkvgPattern pat) {  // gradient branch, internal.c:774-826
+static void update_cur_pattern(VkvgContext ctx, VkvgPattern pat) {  // surface branch internal.c:705-773, gradient branch :774-826
     VkvgPattern last = ctx->pattern;
     ctx->pattern     = pat;
+    if (pat->type == VKVG_PATTERN_TYPE_SURFACE) {
+        ctx->src[2] = (float)pat->surf->width;
+        ctx->src[3] = (float)pat->surf->height;
+        if (pat->hasMatrix) {  // :762-770: folded into matInv until the next CTM change recomputes it
+            vkvg_matrix_t m = pat->matrix;
+            vkvg_matrix_multiply(&ctx->matInv, &ctx->matInv, &m);
+        }
+        ctx->patType = VKB_PAT_SURFACE; ctx->grad_slot = -1;
+        if (last) vkvg_pattern_destroy(last);
+        return;
+    }
     vkb_gradient g   = pat->grad;
     if (g.count < 2) {
         ctx->status = VKVG_STATUS_PATTERN_INVALID_GRADIENT;
@@ -859,9 +910,14 @@ static void update_cur_pattern(VkvgContext ctx, VkvgPattern pat) {  // gradient 
 }
 void vkvg_set_source(VkvgContext ctx, VkvgPattern pat) {  // :1034-1040
     if (vkvg_status(ctx) || vkvg_pattern_status(pat)) return;
-    if (pat->type != VKVG_PATTERN_TYPE_LINEAR && pat->type != VKVG_PATTERN_TYPE_RADIAL) return;  // surface patterns: out of scope
+    if (pat->type != VKVG_PATTERN_TYPE_LINEAR && pat->type != VKVG_PATTERN_TYPE_RADIAL && pat->type != VKVG_PATTERN_TYPE_SURFACE) return;
     update_cur_pattern(ctx, pat);
     vkvg_pattern_reference(pat);
+}
+void vkvg_set_source_surface(VkvgContext ctx, VkvgSurface surf, float x, float y) {  // :1025-1033
+    if (vkvg_status(ctx) || vkvg_surface_status(surf)) return;
+    ctx->src[0] = x; ctx->src[1] = y;
+    update_cur_pattern(ctx, vkvg_pattern_create_for_surface(surf));  // the context owns the pattern's only reference
 }
 VkvgPattern vkvg_get_source(VkvgContext ctx) {
     if (vkvg_status(ctx)) return NULL;
@@ -952,6 +1008,7 @@ void vkvg_save(VkvgContext ctx) {  // :1251-1375
     s.lineWidth = ctx->lineWidth; s.miterLimit = ctx->miterLimit; s.dashOffset = ctx->dashOffset; s.dashes = ctx->dashes;
     s.op = ctx->op; s.cap = ctx->cap; s.fillRule = ctx->fillRule; s.opacity = ctx->opacity; s.mat = ctx->mat;
     s.curColor = ctx->curColor; s.pattern = ctx->pattern; s.patType = ctx->patType; s.grad = ctx->grad;
+    s.matInv = ctx->matInv; memcpy(s.src, ctx->src, sizeof s.src);
     if (ctx->pattern) vkvg_pattern_reference(ctx->pattern);
     ctx->saved.push_back(s);
 }
@@ -974,6 +1031,7 @@ void vkvg_restore(VkvgContext ctx) {  // :1376-1512
     }
     ctx->curClipState = CLIP_STATE_NONE;
     ctx->mat = s.mat; ctx->opacity = s.opacity;
+    ctx->matInv = s.matInv; memcpy(ctx->src, s.src, sizeof s.src);  // pushConsts restored wholesale (:1395)
     ctx->dashOffset = s.dashOffset; ctx->dashes = s.dashes;
     ctx->lineWidth = s.lineWidth; ctx->miterLimit = s.miterLimit; ctx->op = s.op; ctx->cap = s.cap;
     ctx->join     = VKVG_LINE_JOIN_MITER;  // the reference never saves lineJoin: restore reads a zeroed field (:1492)
@@ -984,17 +1042,22 @@ void vkvg_restore(VkvgContext ctx) {  // :1376-1512
     } else
         set_solid(ctx, s.curColor);
 }
-void vkvg_translate(VkvgContext ctx, float dx, float dy) { if (!vkvg_status(ctx)) vkvg_matrix_translate(&ctx->mat, dx, dy); }
-void vkvg_scale(VkvgContext ctx, float sx, float sy) { if (!vkvg_status(ctx)) vkvg_matrix_scale(&ctx->mat, sx, sy); }
-void vkvg_rotate(VkvgContext ctx, float radians) { if (!vkvg_status(ctx)) vkvg_matrix_rotate(&ctx->mat, radians); }
+static void set_mat_inv(VkvgContext ctx) {  // _set_mat_inv_and_vkCmdPush, internal.c:672-676 (a pattern matrix folded in earlier is dropped, as there)
+    ctx->matInv = ctx->mat;
+    vkvg_matrix_invert(&ctx->matInv);
+}
+void vkvg_translate(VkvgContext ctx, float dx, float dy) { if (!vkvg_status(ctx)) { vkvg_matrix_translate(&ctx->mat, dx, dy); set_mat_inv(ctx); } }
+void vkvg_scale(VkvgContext ctx, float sx, float sy) { if (!vkvg_status(ctx)) { vkvg_matrix_scale(&ctx->mat, sx, sy); set_mat_inv(ctx); } }
+void vkvg_rotate(VkvgContext ctx, float radians) { if (!vkvg_status(ctx)) { vkvg_matrix_rotate(&ctx->mat, radians); set_mat_inv(ctx); } }
 void vkvg_transform(VkvgContext ctx, const vkvg_matrix_t *matrix) {
     if (vkvg_status(ctx)) return;
     vkvg_matrix_t res;
     vkvg_matrix_multiply(&res, &ctx->mat, matrix);
     ctx->mat = res;
+    set_mat_inv(ctx);
 }
-void vkvg_identity_matrix(VkvgContext ctx) { if (!vkvg_status(ctx)) vkvg_matrix_init_identity(&ctx->mat); }
-void vkvg_set_matrix(VkvgContext ctx, const vkvg_matrix_t *matrix) { if (!vkvg_status(ctx)) ctx->mat = *matrix; }
+void vkvg_identity_matrix(VkvgContext ctx) { if (!vkvg_status(ctx)) { vkvg_matrix_init_identity(&ctx->mat); set_mat_inv(ctx); } }
+void vkvg_set_matrix(VkvgContext ctx, const vkvg_matrix_t *matrix) { if (!vkvg_status(ctx)) { ctx->mat = *matrix; set_mat_inv(ctx); } }
 void vkvg_get_matrix(VkvgContext ctx, vkvg_matrix_t *const matrix) { if (!vkvg_status(ctx) && matrix) *matrix = ctx->mat; }
 
 // ---- draws ----
@@ -1013,7 +1076,23 @@ static vkb_draw base_draw(VkvgContext ctx, uint32_t kind, uint32_t rule) {
         xf.push_back(x);
     }
     d.xform_stroke = (uint32_t)xf.size() - 1;
-    if (ctx->patType != VKB_PAT_SOLID) {
+    if (ctx->patType == VKB_PAT_SURFACE) {
+        vkb_surfpat sp;
+        memset(&sp, 0, sizeof sp);
+        VkvgSurface src = ctx->pattern->surf;
+        sp.image  = (uint64_t)(uintptr_t)vkb_surface_device_pixels(src->impl);
+        sp.width  = src->width; sp.height = src->height;
+        const uint32_t filter = (ctx->pattern->filter == VKVG_FILTER_BILINEAR || ctx->pattern->filter == VKVG_FILTER_BEST) ? VKB_TEX_LINEAR : VKB_TEX_NEAREST;
+        sp.filter_extend = filter | ((uint32_t)ctx->pattern->extend << 8);  // vkvg_extend_t order == VKB_TEX_* address modes
+        sp.sx = ctx->src[0]; sp.sy = ctx->src[1];
+        memcpy(sp.minv, &ctx->matInv, sizeof(float) * 6);
+        std::vector<vkb_surfpat> &tab = ctx->batch.surfpats;
+        if (tab.empty() || memcmp(&tab.back(), &sp, sizeof sp) != 0) {
+            tab.push_back(sp);
+            ctx->held.push_back(vkvg_surface_reference(src));  // stays alive until the draws that sample it have run
+        }
+        d.gradient = (uint32_t)tab.size() - 1;
+    } else if (ctx->patType != VKB_PAT_SOLID) {
         if (ctx->grad_slot < 0) {
             ctx->grad_slot = (int32_t)ctx->batch.grads.size();
             ctx->batch.grads.push_back(ctx->grad);
@@ -1143,6 +1222,10 @@ static void flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident) {
         }
     }
     (void)keep_resident;
+    // sources sampled by the flush before this one are no longer in flight (the upload of this one waited for it)
+    for (VkvgSurface s : ctx->held_prev) vkvg_surface_destroy(s);
+    ctx->held_prev.swap(ctx->held);
+    ctx->held.clear();
     carry_path_over(ctx);
 }
 void vkvg_flush(VkvgContext ctx) {  // :180-184
@@ -1153,6 +1236,11 @@ void vkvg_destroy(VkvgContext ctx) {  // :246-304
     if (vkvg_status(ctx)) return;
     if (--ctx->references > 0) return;
     vkvg_flush(ctx);
+    if (!ctx->held_prev.empty() || !ctx->held.empty()) {
+        vkvg_b200_device_synchronize(ctx->dev);
+        for (VkvgSurface s : ctx->held_prev) vkvg_surface_destroy(s);
+        for (VkvgSurface s : ctx->held) vkvg_surface_destroy(s);
+    }
     if (ctx->pattern) vkvg_pattern_destroy(ctx->pattern);
     for (saved_state &s : ctx->saved) if (s.pattern) vkvg_pattern_destroy(s.pattern);
     vkvg_surface_destroy(ctx->pSurf);
@@ -1210,6 +1298,11 @@ void vkvg_b200_device_set_graphs(VkvgDevice dev, int on) {
     vkb_device_set_graphs(dev->impl, on != 0);
 }
 uint64_t vkvg_b200_device_graph_replays(VkvgDevice dev) { return vkvg_device_status(dev) ? 0 : vkb_device_graph_replays(dev->impl); }
+void vkvg_b200_get_source_push(VkvgContext ctx, float out[10]) {  // what the reference keeps in pushConsts.source / .matInv
+    if (vkvg_status(ctx) || !out) return;
+    memcpy(out, ctx->src, sizeof(float) * 4);
+    memcpy(out + 4, &ctx->matInv, sizeof(float) * 6);
+}
 int vkb_device_ordinal(vkb_device_impl *d);
 int vkvg_b200_device_ordinal(VkvgDevice dev) { return vkvg_device_status(dev) ? -1 : vkb_device_ordinal(dev->impl); }
 
