@@ -29,16 +29,18 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-SIZES = {"c1": 1024, "c2": 4096, "c3": 4096, "c4": 8192, "c5a": 16384, "c5b": 1024}
+SIZES = {"c1": 1024, "c2": 4096, "c3": 4096, "c4": 8192, "c5a": 16384, "c5b": 1024, "blit": 4096}
 C5B_CANVASES, C5B_BATCH = 1024, 16   # 1024 independent 1024^2 canvases, 16 per flush (one batch surface of 1024 x 16384)
 UNITS = {"c1": ("tiger_frames_per_s", "frames/s"), "c2": ("fill_Mpix_per_s", "Mpix/s"), "c3": ("stroke_Msegments_per_s", "Msegments/s"),
-         "c4": ("fill_Mpix_per_s", "Mpix/s"), "c5a": ("fill_Mpix_per_s", "Mpix/s"), "c5b": ("tiger_frames_per_s", "frames/s")}
+         "c4": ("fill_Mpix_per_s", "Mpix/s"), "c5a": ("fill_Mpix_per_s", "Mpix/s"), "c5b": ("tiger_frames_per_s", "frames/s"),
+         "blit": ("fill_Mpix_per_s", "Mpix/s")}
 WORKLOAD_NAMES = {
     "c1": "C1 tiger.svg via nanoSVG, 1024x1024, 4 samples, even-odd fills + miter strokes",
     "c2": "C2 100k random self-intersecting polygons, one fill each, 4096x4096, 4 samples",
     "c3": "C3 1M-segment polyline stroke, width 3, round joins/caps, dash {10,6}, 4096x4096, 4 samples",
     "c4": "C4 50k cubic-Bezier paths, linear/radial gradient fills, OVER, 8192x8192, 4 samples",
     "c5b": "C5b batch of 1024 independent 1024x1024 tiger canvases (per-canvas affine jitter), 16 canvases per flush in one batch surface, canvases split across ranks",
+    "blit": "layer compositing: 8 translucent 2048x2048 surface sources (bilinear, rotated) painted over a 4096x4096 surface (SURVEY §8f rank 2)",
     "c5a": "C5a 16384x16384 surface, 5M-segment mix (C2-style polygons + C3-style dashed polylines), sharded by tile-row stripes, NCCL all-gather",
 }
 
@@ -117,6 +119,21 @@ def build_scene(workload, seed, rule, n_limit=None, first=0):
                 g.stroke()
         nseg = int(sum(len(p) for p in polys)) + sum(len(l) - 1 for l in lines)
         return emit, size * size / 1e6, dict(n_paths=len(polys) + len(lines), n_segments=nseg)
+    if workload == "blit":
+        n_layers = n_limit or 8
+
+        def emit(g):
+            g.set_source_rgba(0.1, 0.1, 0.12, 1.0)
+            g.paint()
+            for k in range(n_layers):
+                g.identity_matrix()
+                g.translate(300.0 * k + 100.0, 180.0 * k + 60.0)
+                g.rotate(0.11 * k)
+                g.set_opacity(0.6 + 0.05 * k)
+                g.set_source_layer(4 if k % 2 else 3)   # bilinear / nearest
+                g.rectangle(0.0, 0.0, 2048.0, 2048.0)
+                g.fill()
+        return emit, size * size / 1e6, dict(n_paths=n_layers + 1, n_segments=4 * n_layers)
     if workload == "c5b":   # one flush worth of canvases; the step replays it for every batch this rank owns
         w, h, shapes = scenes.load_nsvg(os.path.join(ROOT, "tests", "golden", "tiger.nsvg.bin"))
         r = scenes.SplitMix64(900 + seed)
@@ -139,6 +156,24 @@ def build_scene(workload, seed, rule, n_limit=None, first=0):
             scenes.render_nsvg(g, shapes)
         return emit, 1.0, dict(n_paths=len(shapes), n_segments=int(sum((len(p) - 1) // 3 for s in shapes for p, _ in s["paths"])))
     raise SystemExit("unknown workload " + workload)
+
+
+class LayerSource:
+    """adds set_source_layer(filter) to a drawing object: the 2048x2048 layer of the blit workload as a surface paint"""
+
+    def __init__(self, g, source):
+        self._g, self._source = g, source
+
+    def __getattr__(self, name):
+        return getattr(self._g, name)
+
+    def set_source_layer(self, filt):
+        self._g.set_source_surface(self._source, 0.0, 0.0, extend=0, filter=filt)
+
+
+def layer_image():
+    from tests.golden import make_golden2 as mg2
+    return mg2.checker(2048, 2048, 5)
 
 
 def poly(g, pts):
@@ -212,6 +247,11 @@ def _ref_worker(args):
     size = SIZES[workload]
     emit, units, info = build_scene(workload, seed, rule, n_limit=n_limit, first=first)
     kind = "reference" if oracle.ref_available() else "port"
+    if workload == "blit":   # textures do not travel through the recorded draw list of the reference build: oracle port only
+        kind = "port"
+        inner = emit
+        img = layer_image()
+        emit = lambda g: inner(LayerSource(g, img))  # noqa: E731
     t0 = time.perf_counter()
     o = Oracle(size, size, 4)
     if kind == "reference":
@@ -227,8 +267,8 @@ def _ref_worker(args):
     return dt, info, kind
 
 
-SAMPLE = {"c5b": None, "c1": None, "c2": 1500, "c3": 40000, "c4": 200, "c5a": 1000}  # units of work per host thread per step (paths / segments)
-FULL = {"c5b": 239 * C5B_CANVASES, "c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000, "c5a": 476000}
+SAMPLE = {"blit": 1, "c5b": None, "c1": None, "c2": 1500, "c3": 40000, "c4": 200, "c5a": 1000}  # units of work per host thread per step (paths / segments)
+FULL = {"blit": 8, "c5b": 239 * C5B_CANVASES, "c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000, "c5a": 476000}
 
 
 def reference_step(workload, seed, rule, cores, pool):
@@ -281,7 +321,7 @@ def run_reference(args):
 
 
 def build_units(workload):
-    return {"c5b": float(C5B_CANVASES), "c1": 1.0, "c2": 4096 * 4096 / 1e6, "c3": 1.0, "c4": 8192 * 8192 / 1e6, "c5a": 16384 * 16384 / 1e6}[workload]
+    return {"blit": 4096 * 4096 / 1e6, "c5b": float(C5B_CANVASES), "c1": 1.0, "c2": 4096 * 4096 / 1e6, "c3": 1.0, "c4": 8192 * 8192 / 1e6, "c5a": 16384 * 16384 / 1e6}[workload]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -339,7 +379,15 @@ def run_ours(args):
         reps = 1
     ctx = v.Context(surf)
     cs = v.CommandStream()
-    emit(cs)
+    direct = None
+    if w == "blit":   # surface sources are handles, not numbers: this workload drives the C API call by call instead of a command stream
+        img = layer_image()
+        hlayer = v.lib().vkvg_surface_create_from_bitmap(dev.h, img.ctypes.data, 2048, 2048)
+        layer = v.Surface.__new__(v.Surface)
+        layer.dev, layer.width, layer.height, layer.full_height, layer.origin_y, layer.batch, layer.h = dev, 2048, 2048, 2048, 0, None, hlayer
+        direct = LayerSource(ctx, layer)
+    else:
+        emit(cs)
     ops_np, args_np = cs.arrays()
     # host buffers of the end-to-end path live in pinned memory
     ops_t = torch.from_numpy(ops_np.copy()).pin_memory()
@@ -366,7 +414,13 @@ def run_ours(args):
     def e2e_step():
         t0 = time.perf_counter()
         L.vkvg_clear(ctx.h)
-        st = L.vkvg_b200_replay(ctx.h, ops_t.data_ptr(), ops_t.numel(), args_t.data_ptr(), args_t.numel())
+        if direct is not None:
+            emit(direct)
+            ctx.identity_matrix()
+            ctx.set_opacity(1.0)
+            st = 0
+        else:
+            st = L.vkvg_b200_replay(ctx.h, ops_t.data_ptr(), ops_t.numel(), args_t.data_ptr(), args_t.numel())
         assert st == 0, st
         t1 = time.perf_counter()
         L.vkvg_flush(ctx.h)   # queues the upload and the whole pipeline (a CUDA graph replay once the frame structure repeats) and returns
@@ -429,6 +483,8 @@ def run_ours(args):
     peak, peak_src = measured_peak_hbm()
     n_edges, n_draws = st["n_edges"], info["n_paths"]
     alg_bytes = 16 * n_edges + 32 * n_draws + 4 * size * surf.height
+    if w == "blit":   # + every source texel a layer covers, read once per layer (4 B x 2048^2 x 8 layers)
+        alg_bytes += 4 * 2048 * 2048 * 8
     # the fine kernel's duration: CUDA events recorded around it inside the timed region (external event nodes of the replayed
     # graph); if the driver did not time those, the per-stage pass above (same kernel, plain launch) supplies it
     fine_src = "events around the kernel inside the timed graph replays"

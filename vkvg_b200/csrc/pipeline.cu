@@ -41,7 +41,7 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep;
+    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges;
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
     ScanScratch scan;
@@ -106,7 +106,7 @@ void vkb_device_close(vkb_device_impl *d) {
     cudaSetDevice(d->ordinal);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -533,8 +533,10 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
                       d->row_owner.as<uint32_t>(), st);
     VKB_CUDA_OK(cudaMemsetAsync(d->pt_count.p, 0, (size_t)cap_pt * 4, st));
     VKB_CUDA_OK(cudaMemsetAsync(d->pt_backdrop.p, 0, (size_t)cap_pt * 4, st));
+    d->long_edges.ensure(((size_t)cv[VKC_EDGES] + 1) * 4, st);
+    uint32_t *long_n = (uint32_t *)(totals + 8);  // (zeroed with the other totals when the flush starts)
     vkb_launch_bin_count(edges, edraw, cv[VKC_EDGES], C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_count.as<uint32_t>(),
-                         d->pt_backdrop.as<int32_t>(), st);
+                         d->pt_backdrop.as<int32_t>(), d->long_edges.as<uint32_t>(), long_n, st);
     vkb_launch_backdrop_prefix(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), d->row_owner.as<uint32_t>(),
                                cv[VKC_ROWS], C, d->pt_backdrop.as<int32_t>(), st);
     vkb_launch_pt_flags(d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), cap_pt, C, draws, d->pt_owner.as<uint32_t>(), clip_draws,
@@ -573,7 +575,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
                        d->pt_count.as<uint32_t>(), eoff, d->paints.as<vkb_paint>(), d->hdr.as<int4>(), d->tile_first.as<uint32_t>(), d->tile_end.as<uint32_t>(), st);
     VKB_CUDA_OK(cudaMemsetAsync(cur2.p, 0, (size_t)cap_ne * 4, st));
     vkb_launch_bin_scatter(edges, edraw, cv[VKC_EDGES], C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_slot.as<uint32_t>(), eoff,
-                           cur2.as<uint32_t>(), d->tile_edges.as<vkb_edge>(), st);
+                           cur2.as<uint32_t>(), d->tile_edges.as<vkb_edge>(), d->long_edges.as<uint32_t>(), long_n, st);
 
     // ---- 6. fine pass ----
     FineArgs fa;

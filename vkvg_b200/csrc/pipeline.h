@@ -69,7 +69,7 @@ void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, cons
                            unsigned long long *tile_row_counts, cudaStream_t s);
 void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s);
 void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
-                          const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s);
+                          const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, uint32_t *long_list, uint32_t *long_n, cudaStream_t s);
 // pt_owner[path-tile] / row_owner[path-tile row] = draw index
 void vkb_launch_owners(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws, const vkb_counts *C,
                        uint32_t *pt_owner, uint32_t *row_owner, cudaStream_t s);
@@ -86,7 +86,8 @@ void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t cap
                         const uint32_t *flag_scan, const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
                         uint32_t *tile_first, uint32_t *tile_end, cudaStream_t s);
 void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
-                            const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s);
+                            const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges,
+                            const uint32_t *long_list, const uint32_t *long_n, cudaStream_t s);
 
 struct FineArgs {
     SurfaceDesc         sd;

@@ -308,17 +308,32 @@ __device__ __forceinline__ long long backdrop_first_col(const vkb_edge &e, int32
     if (n2 % 8192 > 0) t++;                   // (for negative n2 truncation already rounds toward +inf)
     return t;
 }
+// number of tile rows + tile columns of the edge's bounding box inside the draw rectangle: edges above VKB_LONG_EDGE go to a
+// list that one warp per edge walks cooperatively (a 4096-pixel side of a rectangle touches 256 tiles: one thread would visit
+// them one after the other while the rest of the grid has long finished)
+#define VKB_LONG_EDGE 40
+__device__ __forceinline__ int32_t edge_tile_span(const vkb_edge &e, const int32_t *rect) {
+    const int32_t tx0 = rect[0], ty0 = rect[1], tw = rect[2], th = rect[3];
+    if (tw <= 0) return 0;
+    int32_t r0 = max(floor_div(min(e.y0, e.y1), VKB_TILE_FX), ty0), r1 = min(floor_div(max(e.y0, e.y1), VKB_TILE_FX), ty0 + th - 1);
+    int32_t c0 = max(floor_div(min(e.x0, e.x1), VKB_TILE_FX), tx0), c1 = min(floor_div(max(e.x0, e.x1), VKB_TILE_FX), tx0 + tw - 1);
+    if (r1 < r0) return 0;
+    return (r1 - r0 + 1) + max(c1 - c0 + 1, 0);
+}
+// rows r0 + row_off, + row_step ...; in each row columns c0 + col_off, + col_step ... (1 thread: 0,1,0,1; a warp on a steep edge:
+// lane,32,0,1; on a shallow one: 0,1,lane,32)
 template <class F> __device__ __forceinline__ void for_each_tile_of_edge(const vkb_edge &e, const int32_t *rect, F &&f_tile, bool want_backdrop,
-                                                                        int32_t *pt_backdrop, uint32_t ptbase) {
+                                                                        int32_t *pt_backdrop, uint32_t ptbase, int32_t row_off = 0, int32_t row_step = 1,
+                                                                        int32_t col_off = 0, int32_t col_step = 1) {
     const int32_t tx0 = rect[0], ty0 = rect[1], tw = rect[2], th = rect[3];
     if (tw <= 0) return;
     const int32_t ymin = min(e.y0, e.y1), ymax = max(e.y0, e.y1);
     int32_t r0 = max(floor_div(ymin, VKB_TILE_FX), ty0), r1 = min(floor_div(ymax, VKB_TILE_FX), ty0 + th - 1);
     const double dxdy = (e.y1 != e.y0) ? ((double)e.x1 - (double)e.x0) / ((double)e.y1 - (double)e.y0) : 0.0;
     const int    sgn  = e.y1 > e.y0 ? 1 : -1;
-    for (int32_t r = r0; r <= r1; r++) {
+    for (int32_t r = r0 + row_off; r <= r1; r += row_step) {
         const int32_t Y0 = r * VKB_TILE_FX;
-        if (want_backdrop && e.y0 != e.y1 && ((e.y0 <= Y0) != (e.y1 <= Y0))) {
+        if (want_backdrop && col_off == 0 && e.y0 != e.y1 && ((e.y0 <= Y0) != (e.y1 <= Y0))) {
             long long tc = backdrop_first_col(e, Y0);
             if (tc < tx0) tc = tx0;
             if (tc < tx0 + tw) atomicAdd(&pt_backdrop[ptbase + (uint32_t)(r - ty0) * tw + (uint32_t)(tc - tx0)], sgn);
@@ -333,22 +348,41 @@ template <class F> __device__ __forceinline__ void for_each_tile_of_edge(const v
         }
         double  xl = floor(fmin(xa, xb)) - 1.0, xh = ceil(fmax(xa, xb)) + 1.0;
         int32_t c0 = (int32_t)fmax(floor(xl / VKB_TILE_FX), (double)tx0), c1 = (int32_t)fmin(floor(xh / VKB_TILE_FX), (double)(tx0 + tw - 1));
-        for (int32_t c = c0; c <= c1; c++) f_tile(ptbase + (uint32_t)(r - ty0) * tw + (uint32_t)(c - tx0));
+        for (int32_t c = c0 + col_off; c <= c1; c += col_step) f_tile(ptbase + (uint32_t)(r - ty0) * tw + (uint32_t)(c - tx0));
     }
 }
+__device__ __forceinline__ bool edge_is_shallow(const vkb_edge &e) { return llabs((long long)e.x1 - e.x0) >= llabs((long long)e.y1 - e.y0); }
 __global__ void __launch_bounds__(256) bin_count_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
-                                                  const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop) {
+                                                  const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, uint32_t *long_list,
+                                                  uint32_t *long_n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow || i >= C->n[VKC_EDGES]) return;
     vkb_edge e = edges[i];
     if (edge_degenerate(e)) return;
     uint32_t d = edge_draw[i];
+    if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) { long_list[atomicAdd(long_n, 1u)] = (uint32_t)i; return; }
     for_each_tile_of_edge(e, draw_rect + 4 * d, [&](uint32_t pt) { atomicAdd(&pt_count[pt], 1u); }, true, pt_backdrop, draw_ptbase[d]);
 }
+// one warp per long edge (grid-stride over the list)
+__global__ void __launch_bounds__(256) bin_count_long_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
+                                                       const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, const uint32_t *long_list,
+                                                       const uint32_t *long_n) {
+    if (C->overflow) return;
+    const uint32_t n = *long_n, lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+        const uint32_t i = long_list[k], d = edge_draw[i];
+        const vkb_edge e = edges[i];
+        const bool     sh = edge_is_shallow(e);
+        for_each_tile_of_edge(e, draw_rect + 4 * d, [&](uint32_t pt) { atomicAdd(&pt_count[pt], 1u); }, true, pt_backdrop, draw_ptbase[d],
+                              sh ? 0 : (int32_t)lane, sh ? 1 : 32, sh ? (int32_t)lane : 0, sh ? 32 : 1);
+    }
+}
 void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
-                          const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s) {
+                          const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, uint32_t *long_list, uint32_t *long_n, cudaStream_t s) {
     if (!cap_edges) return;
-    bin_count_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop);
+    bin_count_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop, long_list, long_n);
+    VKB_LAUNCHED();
+    bin_count_long_k<<<148 * 2, 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop, long_list, long_n);
     VKB_LAUNCHED();
 }
 __global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
@@ -359,6 +393,7 @@ __global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, cons
     vkb_edge e = edges[i];
     if (edge_degenerate(e)) return;
     uint32_t d = edge_draw[i];
+    if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) return;  // on the long list, see bin_scatter_long_k
     for_each_tile_of_edge(
         e, draw_rect + 4 * d,
         [&](uint32_t pt) {
@@ -368,10 +403,32 @@ __global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, cons
         },
         false, nullptr, draw_ptbase[d]);
 }
+__global__ void __launch_bounds__(256) bin_scatter_long_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
+                                                         const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor,
+                                                         vkb_edge *tile_edges, const uint32_t *long_list, const uint32_t *long_n) {
+    if (C->overflow) return;
+    const uint32_t n = *long_n, lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+        const uint32_t i = long_list[k], d = edge_draw[i];
+        const vkb_edge e = edges[i];
+        const bool     sh = edge_is_shallow(e);
+        for_each_tile_of_edge(
+            e, draw_rect + 4 * d,
+            [&](uint32_t pt) {
+                uint32_t p   = pt_slot[pt];
+                uint32_t pos = eoff[p] + atomicAdd(&cursor[p], 1u);
+                tile_edges[pos] = e;
+            },
+            false, nullptr, draw_ptbase[d], sh ? 0 : (int32_t)lane, sh ? 1 : 32, sh ? (int32_t)lane : 0, sh ? 32 : 1);
+    }
+}
 void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
-                            const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges, cudaStream_t s) {
+                            const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges,
+                            const uint32_t *long_list, const uint32_t *long_n, cudaStream_t s) {
     if (!cap_edges) return;
     bin_scatter_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges);
+    VKB_LAUNCHED();
+    bin_scatter_long_k<<<148 * 2, 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges, long_list, long_n);
     VKB_LAUNCHED();
 }
 
