@@ -37,7 +37,7 @@ _PATH_API = {
     "curve_to": [_f] * 6, "rel_curve_to": [_f] * 6, "quadratic_to": [_f] * 4,
     "arc": [_f] * 5, "arc_negative": [_f] * 5, "rectangle": [_f] * 4,
     "set_line_width": [_f], "set_miter_limit": [_f], "set_line_cap": [_i], "set_line_join": [_i],
-    "set_fill_rule": [_i], "set_opacity": [_f], "set_source_rgba": [_f] * 4, "set_source_color": [_u],
+    "set_fill_rule": [_i], "set_opacity": [_f], "set_operator": [_i], "set_source_rgba": [_f] * 4, "set_source_color": [_u],
     "translate": [_f] * 2, "scale": [_f] * 2, "rotate": [_f], "identity_matrix": [],
     "fill": [], "fill_preserve": [], "stroke": [], "stroke_preserve": [], "paint": [],
     "ellipse": [_f] * 5, "rounded_rectangle": [_f] * 5, "rounded_rectangle2": [_f] * 6, "rel_quadratic_to": [_f] * 4,

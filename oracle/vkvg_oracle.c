@@ -125,6 +125,7 @@ struct ovk_ctx {
     /* clip bookkeeping of the reference context (src/vkvg_context_internal.h:93-99, :123, :225-226) */
     mat_t            matInv;  /* pushConsts.matInv: recomputed on every CTM change (src/vkvg_context_internal.c:672-676) */
     surf_src         surf;    /* current surface source (patType 1) */
+    int              op;      /* 0 OVER (and every operator without a pipeline of its own), 1 CLEAR, 2 DIFFERENCE */
     int              curClipState; /* 0 none, 1 clear, 2 clip (6 = clip_saved, only in saved entries) */
     uint32_t         curSavBit;
     struct ovk_save *saved;
@@ -301,9 +302,23 @@ static inline uint32_t unorm8(float v) {
     return (uint32_t)q;
 }
 /* premultiplied OVER, src/vkvg_device_internal.c:203-209: dst = src*ONE + dst*(1-src.a), RGB and A alike */
+static int g_blend_op; /* operator of the draw being rasterised (set with the paint; single threaded like g_surf_src):
+                        * 0 pipe_OVER, 1 pipe_CLEAR (logic op CLEAR: zeros), 2 pipe_SUB (blend op SUBTRACT, same factors):
+                        * src/vkvg_device_internal.c:358-373 */
+static inline uint32_t blend_general(uint32_t dst, const float s[4], float ia) { /* r = src + dst * ia per channel, UNORM8 store */
+    uint32_t out = 0;
+    for (int k = 0; k < 4; k++) {
+        float d = (float)((dst >> (8 * k)) & 0xFF) / 255.0f;
+        float r = s[k] + d * ia;
+        out |= unorm8(r) << (8 * k);
+    }
+    return out;
+}
 static inline uint32_t blend_over(uint32_t dst, const float s[4]) {
     uint32_t out = 0;
     float    ia  = 1.0f - s[3];
+    if (g_blend_op == 1) return 0;
+    if (g_blend_op == 2) ia = -ia; /* src - dst * (1 - src.a); the UNORM store clamps at 0 */
     for (int k = 0; k < 4; k++) {
         float d = (float)((dst >> (8 * k)) & 0xFF) / 255.0f;
         float r = s[k] + d * ia;
@@ -320,6 +335,7 @@ typedef struct {
     grad_t   grad;
     uint32_t solid;
     float    opacity;
+    int      op;
 } paint_t;
 
 typedef struct { int32_t x0, y0, x1, y1; } rect_i; /* pixel scissor, half open */
@@ -474,6 +490,11 @@ static void analytic_draw(ovk_ctx *c, const int32_t *e, uint64_t n, int rule, in
             eval_paint(patType, grad, (float)c->W, (float)c->H, solid, opacity, (float)px + 0.5f, (float)py + 0.5f, col);
             for (int k = 0; k < 4; k++) s[k] = col[k] * cov;
             size_t base = ((size_t)py * c->W + px) * c->S;
+            if (g_blend_op == 1) { /* analytic CLEAR: the covered part of the pixel is wiped */
+                const float z[4] = {0, 0, 0, 0};
+                for (uint32_t q = 0; q < c->S; q++) c->samples[base + q] = blend_general(c->samples[base + q], z, 1.0f - cov);
+                continue;
+            }
             for (uint32_t q = 0; q < c->S; q++) c->samples[base + q] = blend_over(c->samples[base + q], s);
         }
     c->resolved_dirty = true;
@@ -887,6 +908,7 @@ void ovk_set_line_cap(ovk_ctx *c, int cap) { c->lineCap = cap; }
 void ovk_set_line_join(ovk_ctx *c, int j) { c->lineJoin = j; }
 void ovk_set_fill_rule(ovk_ctx *c, int r) { c->fillRule = r; }
 void ovk_set_opacity(ovk_ctx *c, float o) { c->opacity = o; }
+void ovk_set_operator(ovk_ctx *c, int op) { c->op = op == 0 ? 1 : (op == 3 ? 2 : 0); } /* vkvg_operator_t: CLEAR 0, SOURCE 1, OVER 2, DIFFERENCE 3 */
 void ovk_set_dash(ovk_ctx *c, const float *d, uint32_t n, float off) { /* vkvg_context.c:1103-1115 */
     free(c->dashes); c->dashes = NULL;
     c->dashCount = n; c->dashOffset = off;
@@ -1260,6 +1282,7 @@ static paint_t cur_paint(ovk_ctx *c) {
     g_surf_src = c->patType == 1 ? &c->surf : NULL;
     if (g_surf_src) { c->surf.minv = c->matInv; }
     p.patType = c->patType; p.grad = c->grad; p.solid = c->curColor; p.opacity = c->opacity;
+    p.op = g_blend_op = c->op;
     return p;
 }
 static void snap_all(ovk_ctx *c, const v2 *pts, uint32_t n, int32_t *out) {
@@ -1600,6 +1623,8 @@ void ovk_raster_ref_drawlist(ovk_ctx *c, const void *draws_v, uint32_t n, const 
         paint_t p;
         p.patType = fsq_pat & 0xFF;
         p.opacity = pcf[7];
+        p.op = g_blend_op = d->pipeline == REF_PIPE_CLEAR ? 1 : (d->pipeline == REF_PIPE_SUB ? 2 : 0);
+        g_surf_src = NULL; /* textures do not travel through the recorded draw list */
         memcpy(&p.grad, blob + (size_t)d->ubo * 16, sizeof(grad_t));
         rect_i sc = clip_rect(c, d->sc_x, d->sc_y, d->sc_w, d->sc_h);
         mat_t  saved = c->mat;

@@ -65,6 +65,7 @@ void ovk_set_line_join(ovk_ctx *c, int join);
 void ovk_set_dash(ovk_ctx *c, const float *dashes, uint32_t n, float offset);
 void ovk_set_fill_rule(ovk_ctx *c, int rule);
 void ovk_set_opacity(ovk_ctx *c, float o);
+void ovk_set_operator(ovk_ctx *c, int vkvg_operator); /* CLEAR and DIFFERENCE have pipelines of their own, the rest is OVER */
 void ovk_set_source_rgba(ovk_ctx *c, float r, float g, float b, float a);
 void ovk_set_source_color(ovk_ctx *c, uint32_t rgba);
 /* gradient sources: stops = n x {offset, r, g, b, a}; control points in user space at the time of the call */

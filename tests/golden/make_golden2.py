@@ -50,7 +50,8 @@ def elliptic_scene(g, seed):
     g.ellipse(r.uniform(10, 40), r.uniform(10, 40), r.uniform(60, 200), r.uniform(60, 200), r.uniform(0, 3))
 
 
-CLIP_SCENES = ["rect_eo", "circle_nz", "nested", "save_restore", "reset", "preserve_stroke", "deep_stack", "restore_quirk", "clear_inside"]
+CLIP_SCENES = ["rect_eo", "circle_nz", "nested", "save_restore", "reset", "preserve_stroke", "deep_stack", "restore_quirk", "clear_inside",
+               "op_clear", "op_difference", "op_mixed"]
 
 
 def _blob(g, r, n, size):
@@ -174,6 +175,27 @@ def clip_scene(g, name, seed, size=128):
         g.set_source_rgba(0.3, 0.9, 0.3, 0.5)
         g.arc(s * 0.5, s * 0.5, s * 0.45, 0.0, 6.2831855)
         g.fill()
+    elif name in ("op_clear", "op_difference", "op_mixed"):
+        # vkvg_set_operator: CLEAR (0) and DIFFERENCE (3) have pipelines of their own, SOURCE (1) draws like OVER (2)
+        g.set_source_rgba(0.2, 0.5, 0.8, 1.0)
+        g.paint()
+        _blob(g, r, 3, size)
+        ops = {"op_clear": [0], "op_difference": [3], "op_mixed": [3, 0, 1, 2]}[name]
+        for i, op in enumerate(ops):
+            g.set_operator(op)
+            g.set_source_rgba(0.9 - 0.2 * i, 0.3 + 0.1 * i, 0.2, 0.55 + 0.15 * (i % 2))
+            g.arc(s * (0.3 + 0.15 * i), s * (0.35 + 0.1 * i), s * 0.22, 0.0, 6.2831855)
+            g.fill()
+            g.set_line_width(6.0)
+            g.move_to(s * 0.1, s * (0.2 + 0.2 * i))
+            g.line_to(s * 0.9, s * (0.3 + 0.15 * i))
+            g.stroke()
+            if seed:
+                g.set_fill_rule(0)
+                _star(g, s * 0.6, s * 0.6, s * 0.3, s * 0.12)
+                g.fill()
+                g.set_fill_rule(1)
+        g.set_operator(2)
     else:
         raise KeyError(name)
 

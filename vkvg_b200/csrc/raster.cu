@@ -1039,7 +1039,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
                 }
             }
             const vkb_paint pt   = ft.paint;
-            const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
+            const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = (pt.rule_pattern >> 8) & 0xFF, op = (pt.rule_pattern >> 16) & 0xFF;
             if (CLIP && rule >= VKB_RULE_CLIP_EO) {  // stencil-only entries (warp uniform: the rule belongs to the draw)
                 if (rule <= VKB_RULE_CLIP_NZ) {
 #pragma unroll
@@ -1077,8 +1077,12 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
                 float src[4];
                 eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color, pt.opacity, (float)px + 0.5f,
                            (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut, a.surfpats, pt.gradient);
-                const float ia = 1.0f - src[3];
-                if (src[3] >= 1.0f) {  // repeated OVER of an opaque source is idempotent
+                // every operator is r = src + dst * ia per channel with UNORM8 store (negatives and > 1 saturate): OVER ia = 1 - a,
+                // DIFFERENCE (blend op SUBTRACT) ia = -(1 - a), CLEAR (logic op CLEAR) src = 0, ia = 0
+                float ia = 1.0f - src[3];
+                if (op == VKB_OP_SUB) ia = -ia;
+                else if (op == VKB_OP_CLEAR) { src[0] = src[1] = src[2] = src[3] = 0.0f; ia = 0.0f; }
+                if (ia == 0.0f) {  // the result does not depend on the destination: repeating the blend changes nothing
                     nmax = 1;
 #pragma unroll
                     for (int s = 0; s < S; s++) n[s] = n[s] ? 1 : 0;
@@ -1086,7 +1090,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
 #pragma unroll
                 for (int s = 0; s < S; s++) two = two && (n[s] == 0 || n[s] == nmax);
                 // warp-uniform choice (a divergent one would make the warp execute both variants)
-                const bool opaque = src[3] >= 1.0f;  // dst * (1 - 1) vanishes: the result does not depend on what a sample holds
+                const bool opaque = ia == 0.0f;  // dst * 0 vanishes: the result does not depend on what a sample holds
                 if (__all_sync(0xffffffffu, (uni || opaque) && two)) {  // one result per pixel: same colour in every sample (or an opaque source), blended nmax times or not at all
                     uint32_t c = col[0];
                     for (int32_t r = 0; r < nmax; r++) c = blend_over(c, src, ia, lut);
@@ -1251,7 +1255,7 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
                 if ((uint32_t)ft.draw == a.winding_draw && inside) a.winding_out[pix] = __float_as_int(A);
             }
             const vkb_paint pt   = ft.paint;
-            const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = pt.rule_pattern >> 8;
+            const uint32_t  rule = pt.rule_pattern & 0xFF, pattern = (pt.rule_pattern >> 8) & 0xFF, op = (pt.rule_pattern >> 16) & 0xFF;
             float           cov;
             if (rule == VKB_RULE_EVEN_ODD) {
                 const float t = A - 2.0f * floorf(A * 0.5f);
@@ -1273,7 +1277,10 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
             if (cov > 0.0f) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) src[k] *= cov;
-                col = blend_over(col, src, 1.0f - src[3], lut);
+                float ia = 1.0f - src[3];
+                if (op == VKB_OP_SUB) ia = -ia;
+                else if (op == VKB_OP_CLEAR) { src[0] = src[1] = src[2] = src[3] = 0.0f; ia = 1.0f - cov; }  // the covered part of the pixel is wiped
+                col = blend_over(col, src, ia, lut);
             }
         }
         if (s_p >= end) break;

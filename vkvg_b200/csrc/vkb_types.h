@@ -52,13 +52,16 @@ enum : uint32_t {
     VKB_RULE_ST_RESTORE = 7,  // CLIP := save bit
 };
 #define VKB_STENCIL_CLIP 0x2u
+// blend operator of a colour draw, bits 16-23 of rule_pattern: the three pipelines the reference builds (pipe_OVER, pipe_CLEAR,
+// pipe_SUB: src/vkvg_device_internal.c:358-373; _bind_draw_pipeline, src/vkvg_context_internal.c:606-621)
+enum : uint32_t { VKB_OP_OVER = 0, VKB_OP_CLEAR = 1, VKB_OP_SUB = 2 };
 enum : uint32_t { VKB_PAT_SOLID = 0, VKB_PAT_SURFACE = 1, VKB_PAT_LINEAR = 2, VKB_PAT_RADIAL = 3 };  // vkvg_pattern_type_t values
 
 // A draw is 32 bytes; what rarely changes between draws (CTM, stroke state) lives in side tables that grow only when
 // the state differs from the previous entry (100k fills under one CTM upload 3.2 MB of draws, not 11 MB).
 struct vkb_draw {
     uint32_t kind;       // VKB_DRAW_*
-    uint32_t rule_pattern;  // VKB_RULE_* | VKB_PAT_* << 8
+    uint32_t rule_pattern;  // VKB_RULE_* | VKB_PAT_* << 8 | VKB_OP_* << 16
     uint32_t first_subpath, n_subpaths;
     uint32_t color;      // premultiplied RGBA8, R in byte 0 (CreateRgbaf, src/vkvg_context_internal.h:60-62)
     float    opacity;

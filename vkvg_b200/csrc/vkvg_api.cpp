@@ -929,7 +929,7 @@ void  vkvg_set_line_width(VkvgContext ctx, float width) { if (!vkvg_status(ctx))
 void  vkvg_set_miter_limit(VkvgContext ctx, float limit) { if (!vkvg_status(ctx)) ctx->miterLimit = limit; }
 void  vkvg_set_line_cap(VkvgContext ctx, vkvg_line_cap_t cap) { if (!vkvg_status(ctx)) ctx->cap = cap; }
 void  vkvg_set_line_join(VkvgContext ctx, vkvg_line_join_t join) { if (!vkvg_status(ctx)) ctx->join = join; }
-void  vkvg_set_operator(VkvgContext ctx, vkvg_operator_t op) { if (!vkvg_status(ctx)) ctx->op = op; }  // only OVER is rendered
+void  vkvg_set_operator(VkvgContext ctx, vkvg_operator_t op) { if (!vkvg_status(ctx)) ctx->op = op; }  // :1065-1079; takes effect for later draws
 void  vkvg_set_fill_rule(VkvgContext ctx, vkvg_fill_rule_t fr) { if (!vkvg_status(ctx)) ctx->fillRule = fr; }
 float vkvg_get_line_width(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->lineWidth; }
 float vkvg_get_miter_limit(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->miterLimit; }
@@ -1064,7 +1064,9 @@ void vkvg_get_matrix(VkvgContext ctx, vkvg_matrix_t *const matrix) { if (!vkvg_s
 static vkb_draw base_draw(VkvgContext ctx, uint32_t kind, uint32_t rule) {
     vkb_draw d;
     d.kind = kind;
-    d.rule_pattern = rule | (ctx->patType << 8);
+    // _bind_draw_pipeline, internal.c:606-621: CLEAR and DIFFERENCE have pipelines of their own, everything else draws with OVER
+    const uint32_t bop = ctx->op == VKVG_OPERATOR_CLEAR ? VKB_OP_CLEAR : (ctx->op == VKVG_OPERATOR_DIFFERENCE ? VKB_OP_SUB : VKB_OP_OVER);
+    d.rule_pattern = rule | (ctx->patType << 8) | (bop << 16);
     d.first_subpath = ctx->path_first_sp;
     d.n_subpaths    = (uint32_t)ctx->batch.subpaths.size() - ctx->path_first_sp;
     d.color = ctx->curColor; d.opacity = ctx->opacity; d.gradient = 0;
