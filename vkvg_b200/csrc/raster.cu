@@ -226,7 +226,13 @@ __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const 
                 mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
             }
             if (mnx <= mxx) {
-                atomicMin(&bbox[4 * d0], mnx); atomicMin(&bbox[4 * d0 + 1], mny); atomicMax(&bbox[4 * d0 + 2], mxx); atomicMax(&bbox[4 * d0 + 3], mxy);
+                // millions of edges of one stroke all aim at the same four words: look first (a stale read only costs a redundant
+                // atomic, never a missed one: the box only ever grows), so that after the first few blocks almost none is issued
+                volatile int32_t *vb = bbox + 4 * d0;
+                if (mnx < vb[0]) atomicMin(&bbox[4 * d0], mnx);
+                if (mny < vb[1]) atomicMin(&bbox[4 * d0 + 1], mny);
+                if (mxx > vb[2]) atomicMax(&bbox[4 * d0 + 2], mxx);
+                if (mxy > vb[3]) atomicMax(&bbox[4 * d0 + 3], mxy);
             }
         }
     } else if (ok) {
