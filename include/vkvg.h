@@ -263,6 +263,20 @@ vkvg_public vkvg_pattern_type_t vkvg_pattern_get_type(VkvgPattern pat);
 vkvg_public void          vkvg_pattern_set_matrix(VkvgPattern pat, const vkvg_matrix_t *matrix);
 vkvg_public void          vkvg_pattern_get_matrix(VkvgPattern pat, vkvg_matrix_t *matrix);
 
+/* ---- recording: reference include/vkvg.h:1961-1970 (there only in builds with VKVG_RECORDING) ----
+ * Between vkvg_start_recording and vkvg_stop_recording the context stores drawing calls instead of executing them;
+ * vkvg_replay issues them on any context.  Command codes reported by vkvg_recording_get_command are the reference's
+ * (src/recording/vkvg_record_internal.h:28-95). */
+typedef struct _vkvg_recording_t *VkvgRecording;
+vkvg_public void          vkvg_start_recording(VkvgContext ctx);
+vkvg_public VkvgRecording vkvg_stop_recording(VkvgContext ctx);
+vkvg_public void          vkvg_replay(VkvgContext ctx, VkvgRecording rec);
+vkvg_public void          vkvg_replay_command(VkvgContext ctx, VkvgRecording rec, uint32_t cmdIndex);
+vkvg_public void          vkvg_recording_get_command(VkvgRecording rec, uint32_t cmdIndex, uint32_t *cmd, void **dataOffset);
+vkvg_public uint32_t      vkvg_recording_get_count(VkvgRecording rec);
+vkvg_public void         *vkvg_recording_get_data(VkvgRecording rec);
+vkvg_public void          vkvg_recording_destroy(VkvgRecording rec);
+
 #ifdef __cplusplus
 }
 #endif

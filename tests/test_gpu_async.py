@@ -147,3 +147,58 @@ def test_batch_of_canvases_equals_separate_surfaces(oracle_lib):
     with pytest.raises(v.VkvgError):
         ctx.set_canvas(8)
     dev.close()
+
+
+def test_recording_replays_to_the_same_pixels(oracle_lib):
+    """vkvg_start_recording / stop_recording / replay (reference include/vkvg.h:1961-1970): calls are stored, not executed, and a
+    replay on another context draws what the direct calls draw"""
+    import ctypes as C
+    from tests.golden import make_golden2 as mg2
+    L = v.lib()
+    dev = v.Device(4)
+    a, b = v.Surface(dev, 128, 128), v.Surface(dev, 128, 128)
+    ca, cb = v.Context(a), v.Context(b)
+    ca.start_recording()
+    for scene in (lambda g: mg.pixel_scene(g, "mixed", 1), lambda g: mg2.clip_scene(g, "save_restore", 0), lambda g: mg2.clip_scene(g, "op_mixed", 1)):
+        scene(ca)
+    ca.set_dash([4.0, 2.0, 1.0, 2.0], 1.5)
+    ca.set_line_width(3.0)
+    ca.move_to(10.0, 120.0)
+    ca.rel_line_to(100.0, -8.0)
+    ca.elliptic_arc_to(60.0, 90.0, True, False, 30.0, 14.0, 0.4)
+    ca.stroke()
+    rec = ca.stop_recording()
+    assert rec
+    ca.flush()
+    assert not a.pixels().any()                       # nothing was drawn while recording
+    n = L.vkvg_recording_get_count(rec)
+    assert n > 50
+    cmd, off = C.c_uint32(), C.c_void_p()
+    codes = []
+    for i in range(n):
+        L.vkvg_recording_get_command(rec, i, C.byref(cmd), C.byref(off))
+        codes.append(cmd.value)
+    # the reference's command codes (src/recording/vkvg_record_internal.h): fill, stroke, clip, save, restore, set_operator, set_dash ...
+    assert {0x0202, 0x0203, 0x0204, 0x0001, 0x0002, 0x1105, 0x1107, 0x0104, 0x0505, 0x010C, 0x0802} <= set(codes)
+    L.vkvg_recording_get_command(rec, n - 1, C.byref(cmd), C.byref(off))
+    assert cmd.value == 0x0203                        # VKVG_CMD_STROKE
+    L.vkvg_recording_get_command(rec, n, C.byref(cmd), C.byref(off))
+    assert cmd.value == 0 and not off.value
+    ca.replay_recording(rec)
+    ca.flush()
+    # the same calls issued directly
+    for scene in (lambda g: mg.pixel_scene(g, "mixed", 1), lambda g: mg2.clip_scene(g, "save_restore", 0), lambda g: mg2.clip_scene(g, "op_mixed", 1)):
+        scene(cb)
+    cb.set_dash([4.0, 2.0, 1.0, 2.0], 1.5)
+    cb.set_line_width(3.0)
+    cb.move_to(10.0, 120.0)
+    cb.rel_line_to(100.0, -8.0)
+    cb.elliptic_arc_to(60.0, 90.0, True, False, 30.0, 14.0, 0.4)
+    cb.stroke()
+    cb.flush()
+    pa, pb = a.pixels(), b.pixels()
+    assert np.array_equal(pa, pb) and pa.any()
+    L.vkvg_recording_destroy(rec)
+    ca.start_recording()
+    assert ca.stop_recording() is None               # an empty recording is dropped
+    dev.close()

@@ -98,6 +98,9 @@ _SIGS = {
     "vkvg_pattern_set_filter": (None, [_p, _i]), "vkvg_pattern_get_filter": (_i, [_p]),
     "vkvg_pattern_create_for_surface": (_p, [_p]), "vkvg_set_source_surface": (None, [_p, _p, _f, _f]),
     "vkvg_surface_create_from_image": (_p, [_p, C.c_char_p]), "vkvg_surface_create_from_bitmap": (_p, [_p, _p, _u, _u]),
+    "vkvg_start_recording": (None, [_p]), "vkvg_stop_recording": (_p, [_p]), "vkvg_replay": (None, [_p, _p]),
+    "vkvg_replay_command": (None, [_p, _p, _u]), "vkvg_recording_get_count": (_u, [_p]), "vkvg_recording_get_data": (_p, [_p]),
+    "vkvg_recording_get_command": (None, [_p, _u, C.POINTER(_u), C.POINTER(_p)]), "vkvg_recording_destroy": (None, [_p]),
     # vkvg-svg.h
     "vkvg_svg_load": (_p, [C.c_char_p]), "vkvg_svg_load_fragment": (_p, [C.c_char_p]), "vkvg_svg_destroy": (None, [_p]),
     "vkvg_svg_get_dimensions": (None, [_p, C.POINTER(_u), C.POINTER(_u)]), "vkvg_svg_render": (None, [_p, _p, C.c_char_p]),
@@ -371,6 +374,16 @@ class Context:
             L.vkvg_pattern_set_matrix(pat, m.ctypes.data)
         L.vkvg_set_source(self.h, pat)
         L.vkvg_pattern_destroy(pat)
+
+    def start_recording(self):
+        lib().vkvg_start_recording(self.h)
+
+    def stop_recording(self):
+        """returns an opaque VkvgRecording handle (or None when nothing was recorded); free it with lib().vkvg_recording_destroy"""
+        return lib().vkvg_stop_recording(self.h)
+
+    def replay_recording(self, rec):
+        lib().vkvg_replay(self.h, rec)
 
     def source_push(self):
         out = np.zeros(10, np.float32)

@@ -78,6 +78,31 @@ struct saved_state {  // vkvg_context_save_t, src/vkvg_context_internal.h:101-12
 };
 enum { CLIP_STATE_NONE = 0, CLIP_STATE_CLEAR = 1, CLIP_STATE_CLIP = 2, CLIP_STATE_CLIP_SAVED = 6 };
 
+// ---- recording (reference src/recording/: the optional VKVG_RECORDING build) ----
+// While a context records, drawing calls are stored instead of executed (RECORD macro, src/recording/vkvg_record_internal.h:117-123);
+// vkvg_replay issues them on any context.  Command codes are the reference's (vkvg_record_internal.h:28-95) so that
+// vkvg_recording_get_command reports the same values; arguments are stored as consecutive 4-byte floats / uint32s (dashes: count,
+// offset, values; matrices: six floats; set_source / set_source_surface: an index into the recording's object table).
+enum : uint16_t {
+    RC_SAVE = 0x0001, RC_RESTORE = 0x0002,
+    RC_NEW_PATH = 0x0101, RC_NEW_SUB_PATH = 0x0102, RC_CLOSE_PATH = 0x0103, RC_MOVE_TO = 0x0104, RC_LINE_TO = 0x0105, RC_RECTANGLE = 0x0106,
+    RC_ARC = 0x0107, RC_ARC_NEG = 0x0108, RC_CURVE_TO = 0x010A, RC_QUADRATIC_TO = 0x010B, RC_ELLIPTICAL_ARC_TO = 0x010C,
+    RC_REL_MOVE_TO = 0x0504, RC_REL_LINE_TO = 0x0505, RC_REL_CURVE_TO = 0x050A, RC_REL_QUADRATIC_TO = 0x050B, RC_REL_ELLIPTICAL_ARC_TO = 0x050C,
+    RC_SET_LINE_WIDTH = 0x1101, RC_SET_MITER_LIMIT = 0x1102, RC_SET_LINE_JOIN = 0x1103, RC_SET_LINE_CAP = 0x1104, RC_SET_OPERATOR = 0x1105,
+    RC_SET_FILL_RULE = 0x1106, RC_SET_DASH = 0x1107,
+    RC_TRANSLATE = 0x2001, RC_ROTATE = 0x2002, RC_SCALE = 0x2003, RC_TRANSFORM = 0x2004, RC_IDENTITY_MATRIX = 0x2005, RC_SET_MATRIX = 0x2006,
+    RC_PAINT = 0x0201, RC_FILL = 0x0202, RC_STROKE = 0x0203, RC_CLIP = 0x0204, RC_RESET_CLIP = 0x0205, RC_CLEAR = 0x0206,
+    RC_FILL_PRESERVE = 0x0602, RC_STROKE_PRESERVE = 0x0603, RC_CLIP_PRESERVE = 0x0604,
+    RC_SET_SOURCE_RGB = 0x0801, RC_SET_SOURCE_RGBA = 0x0802, RC_SET_SOURCE_COLOR = 0x0803, RC_SET_SOURCE = 0x0804, RC_SET_SOURCE_SURFACE = 0x0805,
+};
+struct rec_entry { uint16_t cmd; size_t off; };
+struct _vkvg_recording_t {
+    std::vector<rec_entry>   cmds;
+    std::vector<char>        buf;
+    std::vector<VkvgPattern> pats;   // referenced until the recording is destroyed
+    std::vector<VkvgSurface> surfs;
+};
+
 struct _vkvg_context_t {
     vkvg_status_t status;
     uint32_t      references;
@@ -116,7 +141,17 @@ struct _vkvg_context_t {
     vkvg_matrix_t      matInv;
     float              src[4];  // x, y (vkvg_set_source_surface offset), width, height of the source
     std::vector<VkvgSurface> held, held_prev;  // sources referenced by recorded / in-flight draws
+    VkvgRecording      recording;  // non-null while vkvg_start_recording is in effect
 };
+// stores one command when the context records; the caller then returns without executing
+static bool rec(VkvgContext ctx, uint16_t cmd, std::initializer_list<float> f = {}, std::initializer_list<uint32_t> u = {}) {
+    VkvgRecording r = ctx->recording;
+    if (!r) return false;
+    r->cmds.push_back(rec_entry{cmd, r->buf.size()});
+    for (float v : f) { const char *p = (const char *)&v; r->buf.insert(r->buf.end(), p, p + 4); }
+    for (uint32_t v : u) { const char *p = (const char *)&v; r->buf.insert(r->buf.end(), p, p + 4); }
+    return true;
+}
 
 // ====================================================================================================
 // matrices — cairo-derived 2x3 affine, reference src/vkvg_matrix.c
@@ -484,6 +519,7 @@ static void init_ctx(VkvgContext ctx) {  // _init_ctx :24-61
     ctx->curClipState = CLIP_STATE_NONE;
     ctx->curSavBit = 0;
     ctx->canvas = 0;
+    ctx->recording = NULL;
     vkvg_matrix_init_identity(&ctx->matInv);
     ctx->src[0] = ctx->src[1] = ctx->src[2] = ctx->src[3] = 0;
 }
@@ -588,9 +624,10 @@ static void line_to_(VkvgContext ctx, float x, float y) {  // _line_to, internal
     add_point(ctx, x, y, false);
     ctx->simpleConvex = false;
 }
-void vkvg_new_sub_path(VkvgContext ctx) { if (!vkvg_status(ctx)) finish_path(ctx); }
+void vkvg_new_sub_path(VkvgContext ctx) { if (!vkvg_status(ctx) && rec(ctx, RC_NEW_SUB_PATH)) return; if (!vkvg_status(ctx)) finish_path(ctx); }
 void vkvg_new_path(VkvgContext ctx) {
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_NEW_PATH)) return;
     // drop the elements of an unfinished sub-path; finished sub-paths may be referenced by recorded draws
     if (ctx->sp_points) {
         ctx->batch.elem_data.resize(ctx->batch.elem_hdr[ctx->sp_first_elem] >> VKB_EL_PAYLOAD_SHIFT);
@@ -600,6 +637,7 @@ void vkvg_new_path(VkvgContext ctx) {
 }
 void vkvg_close_path(VkvgContext ctx) {  // :350-373
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_CLOSE_PATH)) return;
     if (ctx->sp_points < 3) return;
     uint32_t flags = VKB_SP_CLOSED;
     if (EQUF(ctx->cur_x, ctx->first_x) && EQUF(ctx->cur_y, ctx->first_y)) {
@@ -610,19 +648,22 @@ void vkvg_close_path(VkvgContext ctx) {  // :350-373
 }
 void vkvg_move_to(VkvgContext ctx, float x, float y) {  // :515-522
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_MOVE_TO, {x, y})) return;
     finish_path(ctx);
     add_point(ctx, x, y, false);
 }
 void vkvg_rel_move_to(VkvgContext ctx, float x, float y) {  // :504-514
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_REL_MOVE_TO, {x, y})) return;
     if (path_empty(ctx)) add_point(ctx, 0, 0, false);
     float cx = ctx->cur_x, cy = ctx->cur_y;
     finish_path(ctx);
     add_point(ctx, cx + x, cy + y, false);
 }
-void vkvg_line_to(VkvgContext ctx, float x, float y) { if (!vkvg_status(ctx)) line_to_(ctx, x, y); }
+void vkvg_line_to(VkvgContext ctx, float x, float y) { if (!vkvg_status(ctx) && !rec(ctx, RC_LINE_TO, {x, y})) line_to_(ctx, x, y); }
 void vkvg_rel_line_to(VkvgContext ctx, float dx, float dy) {  // :374-385
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_REL_LINE_TO, {dx, dy})) return;
     if (path_empty(ctx)) add_point(ctx, 0, 0, false);
     line_to_(ctx, ctx->cur_x + dx, ctx->cur_y + dy);
 }
@@ -678,8 +719,8 @@ static void arc_impl(VkvgContext ctx, float xc, float yc, float radius, float a1
     }
     add_point(ctx, cosf(a2) * radius + xc, sinf(a2) * radius + yc, true);
 }
-void vkvg_arc(VkvgContext ctx, float xc, float yc, float radius, float a1, float a2) { if (!vkvg_status(ctx)) arc_impl(ctx, xc, yc, radius, a1, a2, false); }
-void vkvg_arc_negative(VkvgContext ctx, float xc, float yc, float radius, float a1, float a2) { if (!vkvg_status(ctx)) arc_impl(ctx, xc, yc, radius, a1, a2, true); }
+void vkvg_arc(VkvgContext ctx, float xc, float yc, float radius, float a1, float a2) { if (!vkvg_status(ctx) && !rec(ctx, RC_ARC, {xc, yc, radius, a1, a2})) arc_impl(ctx, xc, yc, radius, a1, a2, false); }
+void vkvg_arc_negative(VkvgContext ctx, float xc, float yc, float radius, float a1, float a2) { if (!vkvg_status(ctx) && !rec(ctx, RC_ARC_NEG, {xc, yc, radius, a1, a2})) arc_impl(ctx, xc, yc, radius, a1, a2, true); }
 
 static void curve_to_(VkvgContext ctx, float x1, float y1, float x2, float y2, float x3, float y3) {  // _curve_to :541-566
     if (EQUF(x1, x2) && EQUF(x2, x3) && EQUF(y1, y2) && EQUF(y2, y3)) {
@@ -696,9 +737,10 @@ static void curve_to_(VkvgContext ctx, float x1, float y1, float x2, float y2, f
     ctx->sp_points += 3;  // >= 2 recursion points (level 0 always splits) + the end point
     ctx->cur_x = x3; ctx->cur_y = y3;
 }
-void vkvg_curve_to(VkvgContext ctx, float x1, float y1, float x2, float y2, float x3, float y3) { if (!vkvg_status(ctx)) curve_to_(ctx, x1, y1, x2, y2, x3, y3); }
+void vkvg_curve_to(VkvgContext ctx, float x1, float y1, float x2, float y2, float x3, float y3) { if (!vkvg_status(ctx) && !rec(ctx, RC_CURVE_TO, {x1, y1, x2, y2, x3, y3})) curve_to_(ctx, x1, y1, x2, y2, x3, y3); }
 void vkvg_rel_curve_to(VkvgContext ctx, float x1, float y1, float x2, float y2, float x3, float y3) {  // :600-611
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_REL_CURVE_TO, {x1, y1, x2, y2, x3, y3})) return;
     if (path_empty(ctx)) { ctx->status = VKVG_STATUS_NO_CURRENT_POINT; return; }
     float cx = ctx->cur_x, cy = ctx->cur_y;
     curve_to_(ctx, cx + x1, cy + y1, cx + x2, cy + y2, cx + x3, cy + y3);
@@ -710,14 +752,16 @@ static void quadratic_to_(VkvgContext ctx, float x1, float y1, float x2, float y
     else { x0 = ctx->cur_x; y0 = ctx->cur_y; }
     curve_to_(ctx, x0 + (x1 - x0) * qf, y0 + (y1 - y0) * qf, x2 + (x1 - x2) * qf, y2 + (y1 - y2) * qf, x2, y2);
 }
-void vkvg_quadratic_to(VkvgContext ctx, float x1, float y1, float x2, float y2) { if (!vkvg_status(ctx)) quadratic_to_(ctx, x1, y1, x2, y2); }
+void vkvg_quadratic_to(VkvgContext ctx, float x1, float y1, float x2, float y2) { if (!vkvg_status(ctx) && !rec(ctx, RC_QUADRATIC_TO, {x1, y1, x2, y2})) quadratic_to_(ctx, x1, y1, x2, y2); }
 void vkvg_rel_quadratic_to(VkvgContext ctx, float x1, float y1, float x2, float y2) {
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_REL_QUADRATIC_TO, {x1, y1, x2, y2})) return;
     float cx = ctx->cur_x, cy = ctx->cur_y;
     quadratic_to_(ctx, cx + x1, cy + y1, cx + x2, cy + y2);
 }
 vkvg_status_t vkvg_rectangle(VkvgContext ctx, float x, float y, float w, float h) {  // :620-639
     if (vkvg_status(ctx)) return ctx->status;
+    if (rec(ctx, RC_RECTANGLE, {x, y, w, h})) return VKVG_STATUS_SUCCESS;
     finish_path(ctx);
     if (w <= 0 || h <= 0) return VKVG_STATUS_INVALID_RECT;
     add_point(ctx, x, y, false);
@@ -746,6 +790,15 @@ vkvg_status_t vkvg_rounded_rectangle(VkvgContext ctx, float x, float y, float w,
 }
 void vkvg_ellipse(VkvgContext ctx, float radiusX, float radiusY, float x, float y, float rotationAngle) {  // :1605-1639
     if (vkvg_status(ctx)) return;
+    if (ctx->recording) {  // stored as the path calls it stands for
+        float w23 = radiusX * 4 / 3, dx1 = sinf(rotationAngle) * radiusY, dy1 = cosf(rotationAngle) * radiusY;
+        float dx2 = cosf(rotationAngle) * w23, dy2 = sinf(rotationAngle) * w23, tcx = x - dx1, tcy = y + dy1, bcx = x + dx1, bcy = y - dy1;
+        vkvg_move_to(ctx, bcx, bcy);
+        vkvg_curve_to(ctx, bcx + dx2, bcy + dy2, tcx + dx2, tcy + dy2, tcx, tcy);
+        vkvg_curve_to(ctx, tcx - dx2, tcy - dy2, bcx - dx2, bcy - dy2, bcx, bcy);
+        vkvg_close_path(ctx);
+        return;
+    }
     float w23 = radiusX * 4 / 3;
     float dx1 = sinf(rotationAngle) * radiusY, dy1 = cosf(rotationAngle) * radiusY;
     float dx2 = cosf(rotationAngle) * w23, dy2 = sinf(rotationAngle) * w23;
@@ -826,12 +879,14 @@ static void elliptic_arc(VkvgContext ctx, float x1, float y1, float x2, float y2
 }
 void vkvg_elliptic_arc_to(VkvgContext ctx, float x2, float y2, bool largeArc, bool sweepFlag, float rx, float ry, float phi) {  // :1579-1590
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_ELLIPTICAL_ARC_TO, {x2, y2, rx, ry, phi}, {largeArc ? 1u : 0u, sweepFlag ? 1u : 0u})) return;
     float x1 = 0, y1 = 0;
     vkvg_get_current_point(ctx, &x1, &y1);
     elliptic_arc(ctx, x1, y1, x2, y2, largeArc, sweepFlag, rx, ry, phi);
 }
 void vkvg_rel_elliptic_arc_to(VkvgContext ctx, float x2, float y2, bool largeArc, bool sweepFlag, float rx, float ry, float phi) {  // :1591-1603
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_REL_ELLIPTICAL_ARC_TO, {x2, y2, rx, ry, phi}, {largeArc ? 1u : 0u, sweepFlag ? 1u : 0u})) return;
     float x1 = 0, y1 = 0;
     vkvg_get_current_point(ctx, &x1, &y1);
     elliptic_arc(ctx, x1, y1, x2 + x1, y2 + y1, largeArc, sweepFlag, rx, ry, phi);
@@ -862,9 +917,9 @@ static void set_solid(VkvgContext ctx, uint32_t c) {  // _update_cur_pattern(ctx
     if (ctx->pattern) vkvg_pattern_destroy(ctx->pattern);
     ctx->pattern = NULL; ctx->patType = VKB_PAT_SOLID; ctx->grad_slot = -1;
 }
-void vkvg_set_source_color(VkvgContext ctx, uint32_t c) { if (!vkvg_status(ctx)) set_solid(ctx, c); }
-void vkvg_set_source_rgb(VkvgContext ctx, float r, float g, float b) { if (!vkvg_status(ctx)) set_solid(ctx, rgbaf(r, g, b, 1)); }
-void vkvg_set_source_rgba(VkvgContext ctx, float r, float g, float b, float a) { if (!vkvg_status(ctx)) set_solid(ctx, rgbaf(r, g, b, a)); }
+void vkvg_set_source_color(VkvgContext ctx, uint32_t c) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_SOURCE_COLOR, {}, {c})) set_solid(ctx, c); }
+void vkvg_set_source_rgb(VkvgContext ctx, float r, float g, float b) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_SOURCE_RGB, {r, g, b})) set_solid(ctx, rgbaf(r, g, b, 1)); }
+void vkvg_set_source_rgba(VkvgContext ctx, float r, float g, float b, float a) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_SOURCE_RGBA, {r, g, b, a})) set_solid(ctx, rgbaf(r, g, b, a)); }
 static void update_cur_pattern(VkvgContext ctx, VkvgPattern pat) {  // surface branch internal.c:705-773, gradient branch :774-826
     VkvgPattern last = ctx->pattern;
     ctx->pattern     = pat;
@@ -911,11 +966,21 @@ static void update_cur_pattern(VkvgContext ctx, VkvgPattern pat) {  // surface b
 void vkvg_set_source(VkvgContext ctx, VkvgPattern pat) {  // :1034-1040
     if (vkvg_status(ctx) || vkvg_pattern_status(pat)) return;
     if (pat->type != VKVG_PATTERN_TYPE_LINEAR && pat->type != VKVG_PATTERN_TYPE_RADIAL && pat->type != VKVG_PATTERN_TYPE_SURFACE) return;
+    if (ctx->recording) {  // the recording keeps the pattern alive (record :79-85)
+        ctx->recording->pats.push_back(vkvg_pattern_reference(pat));
+        rec(ctx, RC_SET_SOURCE, {}, {(uint32_t)ctx->recording->pats.size() - 1});
+        return;
+    }
     update_cur_pattern(ctx, pat);
     vkvg_pattern_reference(pat);
 }
 void vkvg_set_source_surface(VkvgContext ctx, VkvgSurface surf, float x, float y) {  // :1025-1033
     if (vkvg_status(ctx) || vkvg_surface_status(surf)) return;
+    if (ctx->recording) {
+        ctx->recording->surfs.push_back(vkvg_surface_reference(surf));
+        rec(ctx, RC_SET_SOURCE_SURFACE, {x, y}, {(uint32_t)ctx->recording->surfs.size() - 1});
+        return;
+    }
     ctx->src[0] = x; ctx->src[1] = y;
     update_cur_pattern(ctx, vkvg_pattern_create_for_surface(surf));  // the context owns the pattern's only reference
 }
@@ -925,12 +990,12 @@ VkvgPattern vkvg_get_source(VkvgContext ctx) {
     return ctx->pattern;
 }
 VkvgSurface vkvg_get_target(VkvgContext ctx) { return vkvg_status(ctx) ? NULL : ctx->pSurf; }
-void  vkvg_set_line_width(VkvgContext ctx, float width) { if (!vkvg_status(ctx)) ctx->lineWidth = width; }
-void  vkvg_set_miter_limit(VkvgContext ctx, float limit) { if (!vkvg_status(ctx)) ctx->miterLimit = limit; }
-void  vkvg_set_line_cap(VkvgContext ctx, vkvg_line_cap_t cap) { if (!vkvg_status(ctx)) ctx->cap = cap; }
-void  vkvg_set_line_join(VkvgContext ctx, vkvg_line_join_t join) { if (!vkvg_status(ctx)) ctx->join = join; }
-void  vkvg_set_operator(VkvgContext ctx, vkvg_operator_t op) { if (!vkvg_status(ctx)) ctx->op = op; }  // :1065-1079; takes effect for later draws
-void  vkvg_set_fill_rule(VkvgContext ctx, vkvg_fill_rule_t fr) { if (!vkvg_status(ctx)) ctx->fillRule = fr; }
+void  vkvg_set_line_width(VkvgContext ctx, float width) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_LINE_WIDTH, {width})) ctx->lineWidth = width; }
+void  vkvg_set_miter_limit(VkvgContext ctx, float limit) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_MITER_LIMIT, {limit})) ctx->miterLimit = limit; }  // (the reference records this one under the line-width code: :1050)
+void  vkvg_set_line_cap(VkvgContext ctx, vkvg_line_cap_t cap) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_LINE_CAP, {}, {(uint32_t)cap})) ctx->cap = cap; }
+void  vkvg_set_line_join(VkvgContext ctx, vkvg_line_join_t join) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_LINE_JOIN, {}, {(uint32_t)join})) ctx->join = join; }
+void  vkvg_set_operator(VkvgContext ctx, vkvg_operator_t op) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_OPERATOR, {}, {(uint32_t)op})) ctx->op = op; }  // :1065-1079; takes effect for later draws
+void  vkvg_set_fill_rule(VkvgContext ctx, vkvg_fill_rule_t fr) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_FILL_RULE, {}, {(uint32_t)fr})) ctx->fillRule = fr; }
 float vkvg_get_line_width(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->lineWidth; }
 float vkvg_get_miter_limit(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->miterLimit; }
 vkvg_line_cap_t  vkvg_get_line_cap(VkvgContext ctx) { return vkvg_status(ctx) ? (vkvg_line_cap_t)0 : ctx->cap; }
@@ -939,6 +1004,14 @@ vkvg_operator_t  vkvg_get_operator(VkvgContext ctx) { return vkvg_status(ctx) ? 
 vkvg_fill_rule_t vkvg_get_fill_rule(VkvgContext ctx) { return vkvg_status(ctx) ? VKVG_FILL_RULE_NON_ZERO : ctx->fillRule; }
 void vkvg_set_dash(VkvgContext ctx, const float *dashes, uint32_t num_dashes, float offset) {  // :1103-1115
     if (vkvg_status(ctx)) return;
+    if (ctx->recording) {
+        rec(ctx, RC_SET_DASH, {}, {dashes ? num_dashes : 0u});
+        VkvgRecording r = ctx->recording;
+        const char *po = (const char *)&offset;
+        r->buf.insert(r->buf.end(), po, po + 4);
+        if (dashes) r->buf.insert(r->buf.end(), (const char *)dashes, (const char *)(dashes + num_dashes));
+        return;
+    }
     ctx->dashOffset = offset;
     ctx->dashes.assign(dashes, dashes + (dashes ? num_dashes : 0));
 }
@@ -977,20 +1050,23 @@ static void clip_preserve_(VkvgContext ctx) {  // _clip_preserve :754-795
     ctx->batch.draws.push_back(d);
     ctx->curClipState = CLIP_STATE_CLIP;
 }
-void vkvg_clip_preserve(VkvgContext ctx) { if (!vkvg_status(ctx)) clip_preserve_(ctx); }
+void vkvg_clip_preserve(VkvgContext ctx) { if (!vkvg_status(ctx) && !rec(ctx, RC_CLIP_PRESERVE)) clip_preserve_(ctx); }
 void vkvg_clip(VkvgContext ctx) {
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_CLIP)) return;
     clip_preserve_(ctx);
     clear_path(ctx);
 }
 void vkvg_reset_clip(VkvgContext ctx) {  // :719-733; _reset_clip clears the whole stencil attachment, save bits included (:706-717)
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_RESET_CLIP)) return;
     if (ctx->curClipState == CLIP_STATE_CLEAR) return;
     ctx->curClipState = previous_clip_state(ctx) == CLIP_STATE_CLEAR ? CLIP_STATE_NONE : CLIP_STATE_CLEAR;
     stencil_op(ctx, VKB_RULE_ST_CLEAR, 0);
 }
 void vkvg_save(VkvgContext ctx) {  // :1251-1375
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_SAVE)) return;
     saved_state s;
     if (ctx->curClipState == CLIP_STATE_CLIP) {
         s.clippingState = CLIP_STATE_CLIP_SAVED;
@@ -1014,6 +1090,7 @@ void vkvg_save(VkvgContext ctx) {  // :1251-1375
 }
 void vkvg_restore(VkvgContext ctx) {  // :1376-1512
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_RESTORE)) return;
     if (ctx->saved.empty()) { ctx->status = VKVG_STATUS_INVALID_RESTORE; return; }
     saved_state s = ctx->saved.back();
     ctx->saved.pop_back();
@@ -1046,18 +1123,19 @@ static void set_mat_inv(VkvgContext ctx) {  // _set_mat_inv_and_vkCmdPush, inter
     ctx->matInv = ctx->mat;
     vkvg_matrix_invert(&ctx->matInv);
 }
-void vkvg_translate(VkvgContext ctx, float dx, float dy) { if (!vkvg_status(ctx)) { vkvg_matrix_translate(&ctx->mat, dx, dy); set_mat_inv(ctx); } }
-void vkvg_scale(VkvgContext ctx, float sx, float sy) { if (!vkvg_status(ctx)) { vkvg_matrix_scale(&ctx->mat, sx, sy); set_mat_inv(ctx); } }
-void vkvg_rotate(VkvgContext ctx, float radians) { if (!vkvg_status(ctx)) { vkvg_matrix_rotate(&ctx->mat, radians); set_mat_inv(ctx); } }
+void vkvg_translate(VkvgContext ctx, float dx, float dy) { if (!vkvg_status(ctx) && !rec(ctx, RC_TRANSLATE, {dx, dy})) { vkvg_matrix_translate(&ctx->mat, dx, dy); set_mat_inv(ctx); } }
+void vkvg_scale(VkvgContext ctx, float sx, float sy) { if (!vkvg_status(ctx) && !rec(ctx, RC_SCALE, {sx, sy})) { vkvg_matrix_scale(&ctx->mat, sx, sy); set_mat_inv(ctx); } }
+void vkvg_rotate(VkvgContext ctx, float radians) { if (!vkvg_status(ctx) && !rec(ctx, RC_ROTATE, {radians})) { vkvg_matrix_rotate(&ctx->mat, radians); set_mat_inv(ctx); } }
 void vkvg_transform(VkvgContext ctx, const vkvg_matrix_t *matrix) {
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_TRANSFORM, {matrix->xx, matrix->yx, matrix->xy, matrix->yy, matrix->x0, matrix->y0})) return;
     vkvg_matrix_t res;
     vkvg_matrix_multiply(&res, &ctx->mat, matrix);
     ctx->mat = res;
     set_mat_inv(ctx);
 }
-void vkvg_identity_matrix(VkvgContext ctx) { if (!vkvg_status(ctx)) { vkvg_matrix_init_identity(&ctx->mat); set_mat_inv(ctx); } }
-void vkvg_set_matrix(VkvgContext ctx, const vkvg_matrix_t *matrix) { if (!vkvg_status(ctx)) { ctx->mat = *matrix; set_mat_inv(ctx); } }
+void vkvg_identity_matrix(VkvgContext ctx) { if (!vkvg_status(ctx) && !rec(ctx, RC_IDENTITY_MATRIX)) { vkvg_matrix_init_identity(&ctx->mat); set_mat_inv(ctx); } }
+void vkvg_set_matrix(VkvgContext ctx, const vkvg_matrix_t *matrix) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_MATRIX, {matrix->xx, matrix->yx, matrix->xy, matrix->yy, matrix->x0, matrix->y0})) { ctx->mat = *matrix; set_mat_inv(ctx); } }
 void vkvg_get_matrix(VkvgContext ctx, vkvg_matrix_t *const matrix) { if (!vkvg_status(ctx) && matrix) *matrix = ctx->mat; }
 
 // ---- draws ----
@@ -1150,20 +1228,23 @@ static void stroke_preserve_(VkvgContext ctx) {  // _stroke_preserve :822-948
     d.xform_stroke |= ((uint32_t)sv.size() - 1) << 16;
     ctx->batch.draws.push_back(d);
 }
-void vkvg_fill_preserve(VkvgContext ctx) { if (!vkvg_status(ctx)) fill_preserve_(ctx); }
+void vkvg_fill_preserve(VkvgContext ctx) { if (!vkvg_status(ctx) && !rec(ctx, RC_FILL_PRESERVE)) fill_preserve_(ctx); }
 void vkvg_fill(VkvgContext ctx) {
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_FILL)) return;
     fill_preserve_(ctx);
     clear_path(ctx);
 }
-void vkvg_stroke_preserve(VkvgContext ctx) { if (!vkvg_status(ctx)) stroke_preserve_(ctx); }
+void vkvg_stroke_preserve(VkvgContext ctx) { if (!vkvg_status(ctx) && !rec(ctx, RC_STROKE_PRESERVE)) stroke_preserve_(ctx); }
 void vkvg_stroke(VkvgContext ctx) {
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_STROKE)) return;
     stroke_preserve_(ctx);
     clear_path(ctx);
 }
 void vkvg_paint(VkvgContext ctx) {  // :990-1003
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_PAINT)) return;
     finish_path(ctx);
     if (ctx->batch.subpaths.size() != ctx->path_first_sp) { vkvg_fill(ctx); return; }
     vkb_draw d = base_draw(ctx, VKB_DRAW_PAINT, VKB_RULE_NON_ZERO);
@@ -1172,6 +1253,7 @@ void vkvg_paint(VkvgContext ctx) {  // :990-1003
 }
 void vkvg_clear(VkvgContext ctx) {  // :734-753: everything drawn so far is wiped, so pending draws can be dropped
     if (vkvg_status(ctx)) return;
+    if (rec(ctx, RC_CLEAR)) return;
     ctx->curClipState = previous_clip_state(ctx) == CLIP_STATE_CLEAR ? CLIP_STATE_NONE : CLIP_STATE_CLEAR;  // :740-743
     ctx->batch.clear_draws();
     ctx->grad_slot = -1;
@@ -1237,6 +1319,7 @@ void vkvg_flush(VkvgContext ctx) {  // :180-184
 void vkvg_destroy(VkvgContext ctx) {  // :246-304
     if (vkvg_status(ctx)) return;
     if (--ctx->references > 0) return;
+    if (ctx->recording) { vkvg_recording_destroy(ctx->recording); ctx->recording = NULL; }
     vkvg_flush(ctx);
     if (!ctx->held_prev.empty() || !ctx->held.empty()) {
         vkvg_b200_device_synchronize(ctx->dev);
@@ -1247,6 +1330,89 @@ void vkvg_destroy(VkvgContext ctx) {  // :246-304
     for (saved_state &s : ctx->saved) if (s.pattern) vkvg_pattern_destroy(s.pattern);
     vkvg_surface_destroy(ctx->pSurf);
     delete ctx;
+}
+// ---- recording API: reference include/vkvg.h:1961-1970, src/recording/vkvg_record.c:28-76 ----
+void vkvg_start_recording(VkvgContext ctx) {
+    if (vkvg_status(ctx)) return;
+    if (ctx->recording) vkvg_recording_destroy(ctx->recording);
+    ctx->recording = new _vkvg_recording_t();
+}
+VkvgRecording vkvg_stop_recording(VkvgContext ctx) {  // NULL when nothing was recorded
+    if (vkvg_status(ctx)) return NULL;
+    VkvgRecording r = ctx->recording;
+    ctx->recording  = NULL;
+    if (r && r->cmds.empty()) { vkvg_recording_destroy(r); return NULL; }
+    return r;
+}
+uint32_t vkvg_recording_get_count(VkvgRecording rec) { return rec ? (uint32_t)rec->cmds.size() : 0; }
+void    *vkvg_recording_get_data(VkvgRecording rec) { return rec ? (void *)rec->buf.data() : NULL; }
+void     vkvg_recording_get_command(VkvgRecording rec, uint32_t cmdIndex, uint32_t *cmd, void **dataOffset) {
+    if (!rec) return;
+    if (cmdIndex < rec->cmds.size()) { *cmd = rec->cmds[cmdIndex].cmd; *dataOffset = (void *)rec->cmds[cmdIndex].off; }
+    else { *cmd = 0; *dataOffset = NULL; }
+}
+void vkvg_recording_destroy(VkvgRecording rec) {
+    if (!rec) return;
+    for (VkvgPattern p : rec->pats) vkvg_pattern_destroy(p);
+    for (VkvgSurface s : rec->surfs) vkvg_surface_destroy(s);
+    delete rec;
+}
+void vkvg_replay_command(VkvgContext ctx, VkvgRecording rec, uint32_t i) {  // _replay_command, src/recording/vkvg_record_internal.c:253-420
+    if (vkvg_status(ctx) || !rec || i >= rec->cmds.size()) return;
+    const float    *f = (const float *)(rec->buf.data() + rec->cmds[i].off);
+    const uint32_t *u = (const uint32_t *)f;
+    switch (rec->cmds[i].cmd) {
+    case RC_SAVE: vkvg_save(ctx); break;
+    case RC_RESTORE: vkvg_restore(ctx); break;
+    case RC_NEW_PATH: vkvg_new_path(ctx); break;
+    case RC_NEW_SUB_PATH: vkvg_new_sub_path(ctx); break;
+    case RC_CLOSE_PATH: vkvg_close_path(ctx); break;
+    case RC_MOVE_TO: vkvg_move_to(ctx, f[0], f[1]); break;
+    case RC_LINE_TO: vkvg_line_to(ctx, f[0], f[1]); break;
+    case RC_REL_MOVE_TO: vkvg_rel_move_to(ctx, f[0], f[1]); break;
+    case RC_REL_LINE_TO: vkvg_rel_line_to(ctx, f[0], f[1]); break;
+    case RC_RECTANGLE: vkvg_rectangle(ctx, f[0], f[1], f[2], f[3]); break;
+    case RC_ARC: vkvg_arc(ctx, f[0], f[1], f[2], f[3], f[4]); break;
+    case RC_ARC_NEG: vkvg_arc_negative(ctx, f[0], f[1], f[2], f[3], f[4]); break;
+    case RC_CURVE_TO: vkvg_curve_to(ctx, f[0], f[1], f[2], f[3], f[4], f[5]); break;
+    case RC_REL_CURVE_TO: vkvg_rel_curve_to(ctx, f[0], f[1], f[2], f[3], f[4], f[5]); break;
+    case RC_QUADRATIC_TO: vkvg_quadratic_to(ctx, f[0], f[1], f[2], f[3]); break;
+    case RC_REL_QUADRATIC_TO: vkvg_rel_quadratic_to(ctx, f[0], f[1], f[2], f[3]); break;
+    case RC_ELLIPTICAL_ARC_TO: vkvg_elliptic_arc_to(ctx, f[0], f[1], u[5] != 0, u[6] != 0, f[2], f[3], f[4]); break;
+    case RC_REL_ELLIPTICAL_ARC_TO: vkvg_rel_elliptic_arc_to(ctx, f[0], f[1], u[5] != 0, u[6] != 0, f[2], f[3], f[4]); break;
+    case RC_SET_LINE_WIDTH: vkvg_set_line_width(ctx, f[0]); break;
+    case RC_SET_MITER_LIMIT: vkvg_set_miter_limit(ctx, f[0]); break;
+    case RC_SET_LINE_JOIN: vkvg_set_line_join(ctx, (vkvg_line_join_t)u[0]); break;
+    case RC_SET_LINE_CAP: vkvg_set_line_cap(ctx, (vkvg_line_cap_t)u[0]); break;
+    case RC_SET_OPERATOR: vkvg_set_operator(ctx, (vkvg_operator_t)u[0]); break;
+    case RC_SET_FILL_RULE: vkvg_set_fill_rule(ctx, (vkvg_fill_rule_t)u[0]); break;
+    case RC_SET_DASH: vkvg_set_dash(ctx, u[0] ? f + 2 : NULL, u[0], f[1]); break;
+    case RC_TRANSLATE: vkvg_translate(ctx, f[0], f[1]); break;
+    case RC_ROTATE: vkvg_rotate(ctx, f[0]); break;
+    case RC_SCALE: vkvg_scale(ctx, f[0], f[1]); break;
+    case RC_TRANSFORM: { vkvg_matrix_t m = {f[0], f[1], f[2], f[3], f[4], f[5]}; vkvg_transform(ctx, &m); break; }
+    case RC_SET_MATRIX: { vkvg_matrix_t m = {f[0], f[1], f[2], f[3], f[4], f[5]}; vkvg_set_matrix(ctx, &m); break; }
+    case RC_IDENTITY_MATRIX: vkvg_identity_matrix(ctx); break;
+    case RC_PAINT: vkvg_paint(ctx); break;
+    case RC_FILL: vkvg_fill(ctx); break;
+    case RC_STROKE: vkvg_stroke(ctx); break;
+    case RC_CLIP: vkvg_clip(ctx); break;
+    case RC_RESET_CLIP: vkvg_reset_clip(ctx); break;
+    case RC_CLEAR: vkvg_clear(ctx); break;
+    case RC_FILL_PRESERVE: vkvg_fill_preserve(ctx); break;
+    case RC_STROKE_PRESERVE: vkvg_stroke_preserve(ctx); break;
+    case RC_CLIP_PRESERVE: vkvg_clip_preserve(ctx); break;
+    case RC_SET_SOURCE_RGB: vkvg_set_source_rgb(ctx, f[0], f[1], f[2]); break;
+    case RC_SET_SOURCE_RGBA: vkvg_set_source_rgba(ctx, f[0], f[1], f[2], f[3]); break;
+    case RC_SET_SOURCE_COLOR: vkvg_set_source_color(ctx, u[0]); break;
+    case RC_SET_SOURCE: if (u[0] < rec->pats.size()) vkvg_set_source(ctx, rec->pats[u[0]]); break;
+    case RC_SET_SOURCE_SURFACE: if (u[2] < rec->surfs.size()) vkvg_set_source_surface(ctx, rec->surfs[u[2]], f[0], f[1]); break;
+    default: break;
+    }
+}
+void vkvg_replay(VkvgContext ctx, VkvgRecording rec) {
+    if (!rec) return;
+    for (uint32_t i = 0; i < rec->cmds.size(); i++) vkvg_replay_command(ctx, rec, i);
 }
 const char *vkvg_status_to_string(vkvg_status_t status) {  // :1647-1692
     switch (status) {
