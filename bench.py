@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — the driver's benchmark contract for the vkvg path-rendering hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4] [--rule nz|eo] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5a|c5b|blit] [--rule nz|eo] [--coverage msaa|analytic]
+                    [--no-graph] [--impl reference]
 
 One "step" = one pass of the hot path (flatten -> stroke/fill edges -> tile binning -> winding + paint + OVER) over one
 synthetic scene.  Default workload = BASELINE.json configs[1] ("c2": 100k random self-intersecting polygons, 4096x4096,
@@ -9,7 +10,9 @@ synthetic scene.  Default workload = BASELINE.json configs[1] ("c2": 100k random
 collective on the data path: SURVEY.md §8e "independent canvases").
 
   value  = whole-job Mpix/s with the recorded scene already resident in HBM (device-timed, CUDA events on the library's
-           stream, max over ranks, L2 flushed between steps outside the timed events)
+           stream, max over ranks, L2 flushed between steps outside the timed events); each step is one replay of the CUDA graph the
+           library captures for a repeating frame (--no-graph: plain launches); a separate pass with plain launches and events
+           between the pipeline stages supplies stage_ms
   e2e    = same metric through the public C ABI with HOST buffers: command arrays in pinned host memory -> vkvg_b200_replay
            -> vkvg_flush -> read the surface back to pinned host memory, all inside the timed region (wall clock, max over ranks)
   --impl reference: the reference's own CPU implementation of the path (oracle/_ref = its unmodified tessellation sources,

@@ -1,5 +1,8 @@
 // Orchestration of one flush: upload -> flatten -> stroke / fill edges -> binning -> fine pass.
-// Everything runs on one CUDA stream per device; device buffers are grow-only and reused between flushes.
+// Everything runs on one CUDA stream per device; device buffers are grow-only and reused between flushes.  A flush is queued
+// without any host round trip (counts that only the device knows stay there: dev_util.cuh vkb_counts; overflowing a capacity
+// makes the rest of the flush a no-op and the host replays it with room), and flushes that repeat the structure of the previous
+// one are replayed as a CUDA graph (FlushKey).
 #include "pipeline.h"
 #include "renderer.h"
 #include <string.h>
@@ -24,7 +27,6 @@ struct vkb_device_impl {
     // pinned staging
     uint8_t *stage     = nullptr;
     size_t   stage_cap = 0;
-    uint64_t *readback = nullptr;  // pinned, 16 slots
     // batch (device)
     DevBuf   elem_hdr, elem_data, subpaths, draws, xforms, strokes, grads, dashes, paints, fcnt, scnt, pcnt, srank, surfpats;
     cudaEvent_t ev_h2d = nullptr;
@@ -95,7 +97,6 @@ vkb_device_impl *vkb_device_open(int ordinal) {
     VKB_CUDA_OK(cudaEventCreate(&d->ev_fine1));
     VKB_CUDA_OK(cudaEventCreateWithFlags(&d->ev_h2d, cudaEventDisableTiming));
     for (cudaEvent_t &e : d->ev_stage) VKB_CUDA_OK(cudaEventCreate(&e));
-    VKB_CUDA_OK(cudaHostAlloc((void **)&d->readback, 16 * sizeof(uint64_t), cudaHostAllocDefault));
     VKB_CUDA_OK(cudaHostAlloc((void **)&d->counts_host, sizeof(vkb_counts), cudaHostAllocDefault));
     if (d->counts_host) memset(d->counts_host, 0, sizeof(vkb_counts));
     if (g_cuda_failed) { delete d; return nullptr; }
@@ -116,7 +117,6 @@ void vkb_device_close(vkb_device_impl *d) {
                       &d->tile_end, &d->tile_edges, &d->winding, &d->tmp_image, &d->scan.sums, &d->sort.hist, &d->sort.k2, &d->sort.v2, &d->sort.scan.sums};
     for (DevBuf *b : bufs) b->release();
     if (d->stage) cudaFreeHost(d->stage);
-    cudaFreeHost(d->readback);
     for (cudaEvent_t &e : d->ev_stage) cudaEventDestroy(e);
     if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
     d->l2_flush.release();
@@ -454,10 +454,6 @@ __global__ void commit_pt_k(vkb_counts *C, const uint64_t *totals) {
     if (C->overflow) return;
     vkc_commit(C, VKC_PT, (uint32_t)(totals[4] & 0xffffffffull));
     vkc_commit(C, VKC_ROWS, (uint32_t)(totals[4] >> 32));
-}
-__global__ void commit_one_k(vkb_counts *C, int idx, const uint32_t *raw) {
-    if (C->overflow) return;
-    vkc_commit(C, idx, *raw);
 }
 __global__ void set_edge_count_k(vkb_counts *C, uint32_t n) {  // raw edge lists (vkb_winding_raw)
     for (int i = 0; i < VKC_N; i++) { C->n[i] = 0; C->need[i] = 0; }
