@@ -202,3 +202,51 @@ def test_recording_replays_to_the_same_pixels(oracle_lib):
     ca.start_recording()
     assert ca.stop_recording() is None               # an empty recording is dropped
     dev.close()
+
+
+def test_contexts_on_different_threads(oracle_lib):
+    """the reference's tests/multithreading/multithreaded.c idiom: one device, every thread its own surface and context; then the
+    thread results are composited onto one surface as surface paints"""
+    import threading
+    names = ["mixed", "stroke_alpha", "grad_radial", "eo", "stroke_dash", "grad_linear"]
+    dev = v.Device(4)
+    surfs = [v.Surface(dev, 128, 128) for _ in names]
+    errors = []
+
+    def work(i):
+        try:
+            c = v.Context(surfs[i])
+            for rep in range(3):             # several flushes per thread, interleaved with the other threads' on the one device stream
+                if rep:
+                    c.clear()
+                mg.pixel_scene(c, names[i], 1)
+                c.flush()
+            c.close()
+        except Exception as e:               # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(names))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    refs = []
+    for i, name in enumerate(names):
+        o = oracle_lib.Oracle(128, 128, 4)
+        mg.pixel_scene(o, name, 1)
+        refs.append(o.pixels())
+        assert np.array_equal(surfs[i].pixels(), refs[i]), name
+        o.close()
+    # composite: 3 x 2 grid of the thread surfaces
+    dst = v.Surface(dev, 384, 256)
+    dc = v.Context(dst)
+    od = oracle_lib.Oracle(384, 256, 4)
+    for g, srcs in ((dc, surfs), (od, refs)):
+        for i, src in enumerate(srcs):
+            g.set_source_surface(src, 128.0 * (i % 3), 128.0 * (i // 3))
+            g.rectangle(128.0 * (i % 3), 128.0 * (i // 3), 128.0, 128.0)
+            g.fill()
+    dc.flush()
+    assert np.array_equal(dst.pixels(), od.pixels())
+    dev.close()

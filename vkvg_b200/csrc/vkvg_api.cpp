@@ -8,6 +8,7 @@
 #include "renderer.h"
 #include <float.h>
 #include <math.h>
+#include <atomic>
 #include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
@@ -30,7 +31,7 @@ static vkvg_status_t s_file_not_found  = VKVG_STATUS_FILE_NOT_FOUND;
 
 struct _vkvg_device_t {
     vkvg_status_t    status;
-    uint32_t         references;
+    std::atomic<uint32_t> references;  // handles may be shared between threads (the reference guards them with the device mutex when threadAware)
     uint32_t         samples;
     bool             analytic;  // vkvg_b200_device_set_coverage_mode: exact-area coverage, one colour per pixel
     uint32_t         raster_samples() const { return analytic ? 0u : samples; }  // what the pipeline is asked for
@@ -43,7 +44,7 @@ struct _vkvg_device_t {
 };
 struct _vkvg_surface_t {
     vkvg_status_t     status;
-    uint32_t          references;
+    std::atomic<uint32_t> references;
     VkvgDevice        dev;
     uint32_t          width, height;
     vkb_surface_impl *impl;
@@ -51,7 +52,7 @@ struct _vkvg_surface_t {
 };
 struct _vkvg_pattern_t {
     vkvg_status_t       status;
-    uint32_t            references;
+    std::atomic<uint32_t> references;
     vkvg_pattern_type_t type;
     vkvg_extend_t       extend;
     vkvg_filter_t       filter;
@@ -105,7 +106,7 @@ struct _vkvg_recording_t {
 
 struct _vkvg_context_t {
     vkvg_status_t status;
-    uint32_t      references;
+    std::atomic<uint32_t> references;
     VkvgDevice    dev;
     VkvgSurface   pSurf;
 
@@ -269,7 +270,7 @@ VkvgDevice vkvg_device_reference(VkvgDevice dev) {
     if (!vkvg_device_status(dev)) dev->references++;
     return dev;
 }
-uint32_t vkvg_device_get_reference_count(VkvgDevice dev) { return vkvg_device_status(dev) ? 0 : dev->references; }
+uint32_t vkvg_device_get_reference_count(VkvgDevice dev) { return vkvg_device_status(dev) ? 0u : dev->references.load(); }
 void vkvg_device_set_dpy(VkvgDevice dev, int hdpy, int vdpy) {
     if (vkvg_device_status(dev)) return;
     dev->hdpi = hdpy; dev->vdpi = vdpy;
@@ -333,7 +334,7 @@ VkvgSurface   vkvg_surface_reference(VkvgSurface surf) {
     if (!vkvg_surface_status(surf)) surf->references++;
     return surf;
 }
-uint32_t vkvg_surface_get_reference_count(VkvgSurface surf) { return vkvg_surface_status(surf) ? 0 : surf->references; }
+uint32_t vkvg_surface_get_reference_count(VkvgSurface surf) { return vkvg_surface_status(surf) ? 0u : surf->references.load(); }
 void     vkvg_surface_destroy(VkvgSurface surf) {
     if (vkvg_surface_status(surf)) return;
     if (--surf->references > 0) return;
@@ -403,7 +404,9 @@ const void *vkvg_b200_surface_device_pointer(VkvgSurface surf) { return vkvg_sur
 vkvg_status_t vkvg_pattern_status(VkvgPattern pat) { return !pat ? VKVG_STATUS_NULL_POINTER : pat->status; }
 static VkvgPattern new_pattern(vkvg_pattern_type_t type) {
     VkvgPattern pat = new _vkvg_pattern_t();
-    memset(pat, 0, sizeof *pat);
+    pat->status = VKVG_STATUS_SUCCESS; pat->filter = VKVG_FILTER_FAST; pat->hasMatrix = false; pat->surf = NULL;
+    memset(&pat->grad, 0, sizeof pat->grad);
+    vkvg_matrix_init_identity(&pat->matrix);
     pat->type       = type;
     pat->extend     = VKVG_EXTEND_NONE;
     pat->references = 1;
@@ -450,7 +453,7 @@ VkvgPattern vkvg_pattern_reference(VkvgPattern pat) {
     if (!vkvg_pattern_status(pat)) pat->references++;
     return pat;
 }
-uint32_t vkvg_pattern_get_reference_count(VkvgPattern pat) { return vkvg_pattern_status(pat) ? 0 : pat->references; }
+uint32_t vkvg_pattern_get_reference_count(VkvgPattern pat) { return vkvg_pattern_status(pat) ? 0u : pat->references.load(); }
 void     vkvg_pattern_destroy(VkvgPattern pat) {
     if (vkvg_pattern_status(pat)) return;
     if (--pat->references > 0) return;
@@ -550,7 +553,7 @@ VkvgContext   vkvg_reference(VkvgContext ctx) {
     if (!vkvg_status(ctx)) ctx->references++;
     return ctx;
 }
-uint32_t vkvg_get_reference_count(VkvgContext ctx) { return vkvg_status(ctx) ? 0 : ctx->references; }
+uint32_t vkvg_get_reference_count(VkvgContext ctx) { return vkvg_status(ctx) ? 0u : ctx->references.load(); }
 
 // ---- path bookkeeping ----
 static inline bool path_empty(VkvgContext ctx) { return ctx->sp_points == 0; }  // _current_path_is_empty, internal.c:132
