@@ -10,6 +10,7 @@ WANT = {
     "gpu__time_duration.sum": "dur",
     "dram__bytes_read.sum": "rd",
     "dram__bytes_write.sum": "wr",
+    "dram__bytes.sum.per_second": "bps",
     "dram__cycles_active.avg.pct_of_peak_sustained_elapsed": "dram%",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2%",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm%",
@@ -47,7 +48,12 @@ def main():
             if m in col:
                 g[k] = (r[col[m]], units[col[m]])
         us = to_us(*g["dur"])
-        rd, wr = to_bytes(*g["rd"]), to_bytes(*g["wr"])
+        if "rd" in g and g["rd"][0] not in ("", "n/a"):
+            rd, wr = to_bytes(*g["rd"]), to_bytes(*g["wr"])
+        else:   # reports captured without the full set carry the rate only: bytes = rate x duration
+            v, unit = g.get("bps", ("0", "byte/s"))
+            rate = float(v.replace(",", "")) * {"byte/s": 1, "kbyte/s": 1e3, "mbyte/s": 1e6, "gbyte/s": 1e9, "tbyte/s": 1e12}.get(unit.lower(), 1)
+            rd, wr = rate * us * 1e-6, 0.0
         f = lambda k: float(g[k][0].replace(",", "")) if k in g and g[k][0] not in ("", "n/a") else float("nan")  # noqa: E731
         print("%-44s %9.1f %9.2f %9.2f %9.1f %6.1f %6.1f %6.1f %6.1f %5d" % (name[:44], us, rd / 1e6, wr / 1e6, (rd + wr) / us / 1e3, f("dram%"), f("l2%"),
                                                                          f("sm%"), f("occ%"), int(f("regs"))))
