@@ -43,7 +43,7 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges;
+    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped;
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
     ScanScratch scan;
@@ -107,7 +107,7 @@ void vkb_device_close(vkb_device_impl *d) {
     cudaSetDevice(d->ordinal);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -726,7 +726,8 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         gather_first_items_k<<<vkb_div_up(d->n_sdraws, 256), 256, 0, st>>>(d->sdraw_first_job.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
                                                                           d->sdraw_first_item.as<uint32_t>());
         VKB_LAUNCHED();
-        vkb_launch_tri_edges(d->verts.as<float2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
+        d->snapped.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
+        vkb_launch_tri_edges(d->verts.as<float2>(), cv[VKC_VERTS], d->snapped.as<int2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
                              d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, st);
     }
     if (d->n_extra) {

@@ -51,9 +51,10 @@ void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_x
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
                            vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
 // edges / edge_draw: start of the edge arrays (the kernel skips the C->n[VKC_FILL] fill edges itself)
-void vkb_launch_tri_edges(const float2 *verts, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms,
-                          const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
-                          SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
+// snapped: cap_verts int2 of scratch (every stroke vertex goes through the vertex stage once, then the triangles read integers)
+void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
+                          const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
+                          const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
 
 struct BinBuffers {  // all device pointers
     int32_t  *draw_bbox;    // n_draws x 4 (minx, miny, maxx, maxy), fixed point

@@ -110,22 +110,37 @@ __device__ __forceinline__ void tri_idx(const uint32_t *inds, uint32_t n_tris, l
     if (t < 0 || t >= (long long)n_tris) { i[0] = i[1] = i[2] = 0xffffffffu; return; }
     i[0] = inds[3 * t]; i[1] = inds[3 * t + 1]; i[2] = inds[3 * t + 2];
 }
-__device__ __forceinline__ int tri_sign(const float2 *verts, uint32_t n_verts, const uint32_t (&i)[3], const float *m, int32_t yoff, SurfaceDesc sd,
-                                        int32_t (&x)[3], int32_t (&y)[3]) {
+// every stroke vertex through the vertex stage once (a vertex is shared by up to six triangles, and tri_edges_k also looks at
+// the two neighbouring triangles of each one: snapping inside it cost nine vertex transforms per triangle)
+__global__ void __launch_bounds__(256)
+snap_verts_k(const float2 *verts, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id,
+             const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd, int2 *snapped) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (C->overflow || v >= C->n[VKC_VERTS]) return;
+    uint32_t lo = 0, hi = n_sdraws;  // stroke draw owning vertex v: last q whose first item's vertex offset <= v
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)(item_offsets[sdraw_first_item[mid]] & 0xffffffffull) <= v) lo = mid; else hi = mid;
+    }
+    const vkb_xform &xf = xforms[draws[sdraw_id[lo]].xform_stroke & 0xFFFF];
+    const float2     p  = verts[v];
+    int32_t          x, y;
+    vs_snap(xf.mat, (float)sd.width, (float)sd.full_height, p.x, p.y, x, y);
+    snapped[v] = make_int2(x, y + (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256);
+}
+__device__ __forceinline__ int tri_sign(const int2 *snapped, uint32_t n_verts, const uint32_t (&i)[3], int32_t (&x)[3], int32_t (&y)[3]) {
     if (i[0] >= n_verts || i[1] >= n_verts || i[2] >= n_verts) return 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float2 p = verts[i[k]];
-        vs_snap(m, (float)sd.width, (float)sd.full_height, p.x, p.y, x[k], y[k]);
-        y[k] += yoff;
+        const int2 p = snapped[i[k]];
+        x[k] = p.x; y[k] = p.y;
     }
     long long area = (long long)(x[1] - x[0]) * (y[2] - y[0]) - (long long)(x[2] - x[0]) * (y[1] - y[0]);
     return area > 0 ? -1 : (area < 0 ? 1 : 0);  // cross > 0 winds -1 under our convention: such a triangle is reversed
 }
 __global__ void __launch_bounds__(256)
-tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms,
-            const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd,
-            vkb_edge *edges, uint32_t *edge_draw) {
+tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item,
+            uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_tris = C->n[VKC_TRIS], n_verts = C->n[VKC_VERTS];
@@ -138,9 +153,6 @@ tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, cons
         if ((uint32_t)(item_offsets[sdraw_first_item[mid]] >> 32) <= 3 * t) lo = mid; else hi = mid;
     }
     const uint32_t   d  = sdraw_id[lo];
-    const vkb_xform &xf = xforms[draws[d].xform_stroke & 0xFFFF];
-    const float     *m  = xf.mat;
-    const int32_t    yoff = (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256;
     uint32_t       i0[3], ip1[3], ip2[3], im1[3], im2[3];
     tri_idx(inds, n_tris, (long long)t, i0);
     tri_idx(inds, n_tris, (long long)t + 1, ip1);
@@ -148,7 +160,7 @@ tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, cons
     tri_idx(inds, n_tris, (long long)t - 1, im1);
     tri_idx(inds, n_tris, (long long)t - 2, im2);
     int32_t x[3], y[3], nx[3], ny[3];
-    const int sg = tri_sign(verts, n_verts, i0, m, yoff, sd, x, y);
+    const int sg = tri_sign(snapped, n_verts, i0, x, y);
     int       sg_next = 2, sg_prev = 2;  // 2: not evaluated yet (vertices of a neighbour share this draw's matrix: shared indices)
     vkb_edge  e[3];
 #pragma unroll
@@ -161,13 +173,13 @@ tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, cons
         bool           drop = false;
         if (tri_has(ip1, u, v)) {
             if (!tri_has(im1, u, v) && !tri_has(ip2, u, v)) {
-                if (sg_next == 2) sg_next = tri_sign(verts, n_verts, ip1, m, yoff, sd, nx, ny);
+                if (sg_next == 2) sg_next = tri_sign(snapped, n_verts, ip1, nx, ny);
                 // direction of u->v inside the neighbour after ITS normalisation; opposite to ours (which is u->v) cancels
                 drop = sg_next != 0 && tri_dir(ip1, u, v) * sg_next < 0;
             }
         } else if (tri_has(im1, u, v)) {
             if (!tri_has(im2, u, v)) {
-                if (sg_prev == 2) sg_prev = tri_sign(verts, n_verts, im1, m, yoff, sd, nx, ny);
+                if (sg_prev == 2) sg_prev = tri_sign(snapped, n_verts, im1, nx, ny);
                 drop = sg_prev != 0 && tri_dir(im1, u, v) * sg_prev < 0;
             }
         }
@@ -176,11 +188,13 @@ tri_edges_k(const float2 *verts, const uint32_t *inds, const vkb_counts *C, cons
     edges[3 * t] = e[0]; edges[3 * t + 1] = e[1]; edges[3 * t + 2] = e[2];
     edge_draw[3 * t] = d; edge_draw[3 * t + 1] = d; edge_draw[3 * t + 2] = d;
 }
-void vkb_launch_tri_edges(const float2 *verts, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms,
-                          const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets,
-                          SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
+void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
+                          const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
+                          const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
     if (!cap_tris || !n_sdraws) return;
-    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(verts, inds, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, edges, edge_draw);
+    snap_verts_k<<<vkb_div_up(cap_verts, 256), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
+    VKB_LAUNCHED();
+    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw);
     VKB_LAUNCHED();
 }
 
