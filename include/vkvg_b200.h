@@ -165,6 +165,12 @@ vkvg_public vkvg_status_t vkvg_b200_set_canvas(VkvgContext ctx, uint32_t index);
 vkvg_public void     vkvg_b200_device_set_graphs(VkvgDevice dev, int on);
 vkvg_public void     vkvg_b200_device_set_stage_timing(VkvgDevice dev, int on);
 vkvg_public uint64_t vkvg_b200_device_graph_replays(VkvgDevice dev);
+/* Which fine-pass kernel renders batches that carry no clip state (process-wide; both give identical pixels):
+ *   0 (default)  fine_warp_k: one warp per 16x16 tile, covered pixels compacted into a queue
+ *   1            fine_k: one block of 8 warps per tile (the kernel that also serves clip / save / restore batches)
+ * Environment: VKVG_B200_FINE=block selects 1 at start-up. */
+vkvg_public void     vkvg_b200_set_fine_kernel(int mode);
+vkvg_public int      vkvg_b200_get_fine_kernel(void);
 
 /* ---- SVG parser introspection (parity tests against nanoSVG dumps, tests/test_svg.py) ----
  * Flat dump of a document parsed by vkvg_svg_load (include/vkvg-svg.h), byte-compatible with what oracle/nsvg_dump.c

@@ -598,3 +598,55 @@ def test_surface_as_layer_and_png_roundtrip(dev4, oracle_lib, tmp_path):
     assert L.vkvg_surface_status(L.vkvg_surface_create_from_image(dev4.h, b"/no/such/file.png")) != 0
     lc.close()
     dc.close()
+
+
+# ---- the two fine-pass kernels (one warp per tile / one block per tile) are interchangeable ----
+@pytest.fixture
+def fine_kernel_knob():
+    L = v.lib()
+    yield L.vkvg_b200_set_fine_kernel
+    L.vkvg_b200_set_fine_kernel(0)
+
+
+@pytest.mark.parametrize("samples", [1, 2, 4])
+def test_warp_and_block_fine_kernels_agree(fine_kernel_knob, oracle_lib, samples):
+    """every pixel scene, drawn over one another and in several flushes (so the per-sample plane written by one kernel is read by
+    the next flush of the same kernel), plus a many-edge tile (more than one chunk of 32 edges) and an overlapping translucent
+    stroke (COUNT rule, blended |winding| times): both kernels and the oracle give the same pixels."""
+    imgs = []
+    for mode in (0, 1):
+        fine_kernel_knob(mode)
+        assert v.lib().vkvg_b200_get_fine_kernel() == mode
+        dev = v.Device(samples)
+        s = v.Surface(dev, 150, 131)
+        c = v.Context(s)
+        o = oracle_lib.Oracle(150, 131, samples) if mode == 0 else None
+        for g in (c, o) if o is not None else (c,):
+            for k, name in enumerate(mg.PIXEL_SCENES):
+                mg.pixel_scene(g, name, k % 3, size=128)
+                if g is c and k % 2:
+                    c.flush()
+            # a dense fan: ~200 edges through the same tiles
+            g.set_fill_rule(k % 2)
+            g.set_source_rgba(0.2, 0.7, 0.3, 0.6)
+            r = scenes.SplitMix64(5)
+            g.move_to(70.0, 60.0)
+            for _ in range(200):
+                g.line_to(r.uniform(40, 110), r.uniform(30, 100))
+            g.close_path()
+            g.fill()
+            # translucent zig-zag stroke overlapping itself
+            g.set_source_rgba(0.9, 0.1, 0.4, 0.35)
+            g.set_line_width(9.0)
+            g.set_line_join(1)
+            g.move_to(10.0, 10.0)
+            for i in range(60):
+                g.line_to(10.0 + (i % 2) * 120.0 + r.uniform(-3, 3), 12.0 + 1.9 * i)
+            g.stroke()
+        c.flush()
+        imgs.append(s.pixels())
+        if o is not None:
+            assert np.array_equal(imgs[0], o.pixels())
+        c.close()
+        s.close()
+    assert np.array_equal(imgs[0], imgs[1])

@@ -121,6 +121,7 @@ _SIGS = {
     "vkvg_b200_time_resident": (_i, [_p, _p, _u, _i, _i, C.POINTER(Stats)]),
     "vkvg_b200_device_set_graphs": (None, [_p, _i]), "vkvg_b200_device_set_stage_timing": (None, [_p, _i]),
     "vkvg_b200_device_graph_replays": (C.c_uint64, [_p]),
+    "vkvg_b200_set_fine_kernel": (None, [_i]), "vkvg_b200_get_fine_kernel": (_i, []),
     "vkvg_b200_device_set_coverage_mode": (_i, [_p, _i]), "vkvg_b200_device_get_coverage_mode": (_i, [_p]),
     "vkvg_b200_get_source_push": (None, [_p, _p]),
     "vkvg_b200_surface_create_batch": (_p, [_p, _u, _u, _u]), "vkvg_b200_set_canvas": (_i, [_p, _u]),

@@ -24,6 +24,7 @@
 // tile, applies Porter-Duff OVER with the reference's UNORM8 rounding per sample, resolves (box filter) and
 // writes each pixel once.
 #include "pipeline.h"
+#include <cstdlib>
 
 // ---- vertex stage: shaders/vkvg_main.vert:74-79 + viewport + 8-bit sub-pixel snap (round half up) ----
 __device__ __forceinline__ void vs_snap(const float *m, float W, float H, float x, float y, int32_t &fx, int32_t &fy) {
@@ -1309,8 +1310,331 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
     if (CLIP) a.stencil[(size_t)tile * 256 + threadIdx.x] = stw[0];
     if (inside) a.image[pix] = col;
 }
+// ----------------------------------------------------------------------------------------------------
+// fine pass, one WARP per tile (the variant launched for batches without clip state; fine_k above keeps the stencil and
+// winding-capture variants).
+//
+// With a mean of 3-5 edges and ~170 covered samples per path-tile (C2, C4, tiger) a block of 8 warps per tile spends its time
+// on barriers and on every warp walking every task.  Here a tile belongs to one warp, which needs no barrier at all:
+//   * the tile's 256*S sample colours live in shared memory ([sample row][column]) for the whole list of path-tiles;
+//   * winding: lanes are sample rows (row_edge above, unchanged: same exact predicates), one chunk of <= FINE_CH edges at a
+//     time, edges fetched one per lane and handed round with shuffles; a path-tile that fits one chunk never leaves the
+//     registers, longer ones (and COUNT-rule draws with a translucent source, which blend |winding| times) accumulate
+//     per-sample int32 windings in shared memory;
+//   * the covered PIXELS of the path-tile are compacted into a queue (each lane pushes its share of the set bits), and the warp
+//     blends them 32 at a time: the paint is evaluated once per pixel, the covered samples of the pixel are blended with the
+//     reference's per-sample arithmetic (blend_over).  Lanes are pixels that need work, not pixels that might.
+// Same results as fine_k bit for bit (tests/test_gpu_parity.py runs both on the same scenes).
+// ----------------------------------------------------------------------------------------------------
+#define FW_TILES 4      // tiles (= warps) per block; they only share the u8 -> float table
+#define FW_WSTRIDE 17   // words per sample row of the winding plane (odd: lanes = rows hit distinct banks)
+template <int S> struct FwShared {
+    uint32_t col[16 * S * 16];        // sample colours, [sample row = ly * S + s][lx]
+    int32_t  W[16 * S * FW_WSTRIDE];  // per-sample windings of the current path-tile (multi-chunk / COUNT rule only)
+    uint16_t rowmask[16 * S];         // per sample row: bit lx = covered by the current path-tile
+    uint8_t  queue[256];              // pixels (ly * 16 + lx) with at least one covered sample
+};
+
+// sample positions as packed nibbles (sample s = nibble s): no select chain, cheap enough to recompute anywhere
+template <int S> struct SamplePack;
+template <> struct SamplePack<1> { static constexpr unsigned long long X = 0x8ull, Y = 0x8ull; };
+template <> struct SamplePack<2> { static constexpr unsigned long long X = 0x4Cull, Y = 0x4Cull; };
+template <> struct SamplePack<4> { static constexpr unsigned long long X = 0xA2E6ull, Y = 0xEA62ull; };
+
+#define FW_CH 15      // edges per chunk: per-column deltas (and every partial sum along a row) stay within +-15
+#define FW_DBIAS 32u  // bias of the packed deltas: bytes in [17, 47], so the byte-wise prefix sums of a word (x * 0x01010101) never carry
+// 4-bit mask of the ZERO bytes of v (bit i = byte i is zero)
+__device__ __forceinline__ uint32_t zero_bytes4(uint32_t v) {
+    const uint32_t t = ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu);  // 0x80 in every zero byte
+    return ((t >> 7) * 0x10204080u) >> 28;
+}
+// coverage bits of one sample row from its packed biased per-column deltas: bit c = ((off + sum_{k<=c} delta_k) & par) != 0,
+// par = 1 (even-odd) or -1 (non-zero).  |sum of deltas| <= FW_CH.
+__device__ __forceinline__ uint32_t row_cover_bits(const uint32_t (&d)[4], int32_t off, int par) {
+    uint32_t bits = 0;
+    if (par == 1) {
+        uint32_t odd = (uint32_t)off & 1u;  // bias 32 per column is even: parity of the biased prefix = parity of the true prefix
+#pragma unroll
+        for (int w4 = 0; w4 < 4; w4++) {
+            const uint32_t pre = d[w4] * 0x01010101u;
+            const uint32_t lo  = (pre ^ (odd * 0x01010101u)) & 0x01010101u;
+            bits |= ((lo * 0x10204080u) >> 28) << (4 * w4);
+            odd ^= (pre >> 24) & 1u;
+        }
+        return bits;
+    }
+    if (off > FW_CH || off < -FW_CH) return 0xFFFFu;  // no run of crossings can bring the winding back to zero
+#pragma unroll
+    for (int w4 = 0; w4 < 4; w4++) {
+        const uint32_t pre = d[w4] * 0x01010101u;  // byte i = sum_{k<=i} (delta_k + 32)
+        // winding of column i is zero <=> byte i == 32 * (i + 1) - off ; |off| <= 2 * FW_CH here, so every target byte stays in
+        // [2, 158]: the packed subtraction neither borrows nor wraps
+        const uint32_t tgt = 0x80604020u - (uint32_t)off * 0x01010101u;
+        bits |= (zero_bytes4(pre ^ tgt) ^ 0xFu) << (4 * w4);
+        off += (int32_t)(pre >> 24) - 128;
+    }
+    return bits;
+}
+
+template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k(FineArgs a, uint32_t n_tiles) {
+    constexpr int ROWS = 16 * S;
+    constexpr int P    = ROWS >= 64 ? 2 : 1;  // sample rows per lane
+    constexpr uint32_t FULL = 0xffffffffu;
+    __shared__ float       lut[256];
+    __shared__ FwShared<S> sh_all[FW_TILES];
+    for (uint32_t i = threadIdx.x; i < 256; i += 32 * FW_TILES) lut[i] = (float)i / 255.0f;
+    __syncthreads();  // the only block-wide barrier
+    if (a.counts->overflow) return;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * FW_TILES + warp;
+    if (tile >= n_tiles) return;
+    const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
+    if (first == end) return;
+    FwShared<S>   &sh = sh_all[warp];
+    const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
+    const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
+    const uint32_t band_y0 = a.sd.band_tiles ? (ty / a.sd.band_tiles) * a.sd.band_tiles * VKB_TILE : 0u;
+
+    // ---- destination colours -> shared memory (pixel i * 32 + lane of the tile-major planes is pixel "thread" of fine_k) ----
+    {
+        const bool tms = !a.dst_is_clear && a.tile_ms[tile];
+#pragma unroll 1
+        for (uint32_t i = 0; i < 8; i++) {
+            const uint32_t lx = (lane & 7) + 8 * (i & 1), ly = (lane >> 3) + 4 * (i >> 1);
+            const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
+            const bool     ms = tms && ((a.ms_mask[tile * 8 + i] >> lane) & 1u);
+            if (ms) {
+#pragma unroll
+                for (int s = 0; s < S; s++) sh.col[(ly * S + s) * 16 + lx] = a.ms_image[((size_t)tile * 256 + i * 32 + lane) * S + s];
+            } else {
+                const uint32_t c = (!a.dst_is_clear && px < a.sd.width && py < a.sd.height) ? a.image[(size_t)py * a.sd.width + px] : 0u;
+#pragma unroll
+                for (int s = 0; s < S; s++) sh.col[(ly * S + s) * 16 + lx] = c;
+            }
+        }
+    }
+    // ---- this lane's sample rows ----
+    int32_t ry[P], rxo[P];
+    int     row[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        row[j] = j * 32 + (int)lane;
+        const int r = min(row[j], ROWS - 1);
+        ry[j]  = (r / S) * 256 + 16 * (int32_t)((SamplePack<S>::Y >> (4 * (r % S))) & 15);
+        rxo[j] = 16 * (int32_t)((SamplePack<S>::X >> (4 * (r % S))) & 15);
+    }
+    const uint32_t grp = lane / S, sub = lane % S;  // pixel row group / which of its pixels this lane queues
+    const uint32_t share = (S == 4 ? 0x11111111u : (S == 2 ? 0x55555555u : 0xffffffffu)) << sub;
+    __syncwarp();
+
+    for (uint32_t pb = first; pb < end; pb += 32) {
+        // headers of the next 32 path-tiles, one per lane
+        int4 hh0 = make_int4(0, 0, 0, 0), hh1 = hh0;
+        if (pb + lane < end) { hh0 = __ldg(a.hdr + 2 * (size_t)(pb + lane)); hh1 = __ldg(a.hdr + 2 * (size_t)(pb + lane) + 1); }
+        const int np = (int)min(32u, end - pb);
+        int4      cur = make_int4(0, 0, 0, 0);  // edge (chunk start + lane) of the chunk about to be processed
+        {
+            const uint32_t eo = (uint32_t)__shfl_sync(FULL, hh0.z, 0);
+            const int      ne = __shfl_sync(FULL, hh0.w, 0);
+            if ((int)lane < min(ne, FW_CH)) cur = __ldg((const int4 *)(a.tile_edges + eo + lane));
+        }
+        for (int q = 0; q < np; q++) {
+            const int32_t   bd   = __shfl_sync(FULL, hh0.y, q);
+            const uint32_t  eoff = (uint32_t)__shfl_sync(FULL, hh0.z, q);
+            const int       n_e  = __shfl_sync(FULL, hh0.w, q);
+            const vkb_paint pt   = vkb_paint{(uint32_t)__shfl_sync(FULL, hh1.x, q), (uint32_t)__shfl_sync(FULL, hh1.y, q),
+                                             __int_as_float(__shfl_sync(FULL, hh1.z, q)), (uint32_t)__shfl_sync(FULL, hh1.w, q)};
+            uint32_t        eoff_n = 0;
+            int             ne_n   = 0;
+            if (q + 1 < np) { eoff_n = (uint32_t)__shfl_sync(FULL, hh0.z, q + 1); ne_n = __shfl_sync(FULL, hh0.w, q + 1); }
+            const uint32_t rule = pt.rule_pattern & 0xFF, pattern = (pt.rule_pattern >> 8) & 0xFF, op = (pt.rule_pattern >> 16) & 0xFF;
+            // solid sources: one colour for the whole path-tile
+            float src[4], ia = 0.0f;
+            if (pattern == VKB_PAT_SOLID) {
+                eval_paint(pattern, nullptr, nullptr, 0.0f, 0.0f, pt.color, pt.opacity, 0.0f, 0.0f, src, lut);
+                ia = 1.0f - src[3];
+                if (op == VKB_OP_SUB) ia = -ia;
+                else if (op == VKB_OP_CLEAR) { src[0] = src[1] = src[2] = src[3] = 0.0f; ia = 0.0f; }
+            }
+            // COUNT rule (stroke triangles blended one by one): the number of blends matters unless the result does not depend on the destination
+            const bool counted = rule == VKB_RULE_COUNT && !(pattern == VKB_PAT_SOLID && ia == 0.0f);
+            const bool use_w   = counted || n_e > FW_CH;
+            const int  par     = rule == VKB_RULE_EVEN_ODD ? 1 : -1;  // covered <=> (winding & par) != 0
+            uint32_t   m       = 0;                                   // bit j * 16 + c: sample row row[j], column c is covered
+            const bool skip    = rule >= VKB_RULE_CLIP_EO;            // stencil entries never reach this kernel (they bring a stencil plane with them)
+
+            // ---- winding: chunks of <= FW_CH edges ----
+            for (int e0 = 0;; e0 += FW_CH) {
+                const int nn = max(0, min(FW_CH, n_e - e0));
+                int4      nx = make_int4(0, 0, 0, 0);  // prefetch: the next chunk of this path-tile, else the first chunk of the next one
+                if (e0 + FW_CH < n_e) {
+                    if ((int)lane < min(FW_CH, n_e - e0 - FW_CH)) nx = __ldg((const int4 *)(a.tile_edges + eoff + e0 + FW_CH + lane));
+                } else if ((int)lane < min(ne_n, FW_CH)) nx = __ldg((const int4 *)(a.tile_edges + eoff_n + lane));
+                int32_t  base[P];
+                uint32_t d[P][4];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    base[j] = 0;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) d[j][w4] = FW_DBIAS * 0x01010101u;
+                }
+                // every lane classifies its own edge once; the loop below reads one bit per edge
+                const uint32_t nearmask = __ballot_sync(FULL, (uint32_t)(cur.x - X0 + 16384) < 36864u && (uint32_t)(cur.y - Y0 + 16384) < 36864u &&
+                                                                  (uint32_t)(cur.z - X0 + 16384) < 36864u && (uint32_t)(cur.w - Y0 + 16384) < 36864u);
+                for (int k = 0; k < nn; k++) {
+                    const int32_t ax = __shfl_sync(FULL, cur.x, k) - X0, ay = __shfl_sync(FULL, cur.y, k) - Y0;
+                    const int32_t bx = __shfl_sync(FULL, cur.z, k) - X0, by = __shfl_sync(FULL, cur.w, k) - Y0;
+                    const bool    crossL = (ax <= 0) != (bx <= 0);
+                    const bool    near = (nearmask >> k) & 1u;
+                    if (near) row_edge<P, int32_t>(ax, ay, bx, by, crossL, ry, rxo, d, base);
+                    else row_edge<P, long long>(ax, ay, bx, by, crossL, ry, rxo, d, base);
+                }
+                cur = nx;
+                if (!use_w) {  // (one chunk) the coverage bits come straight from the registers
+#pragma unroll
+                    for (int j = 0; j < P; j++)
+                        if (row[j] < ROWS) m |= row_cover_bits(d[j], base[j] + bd, par) << (16 * j);
+                    break;
+                }
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    if (row[j] < ROWS) {
+                        int      run = base[j] + (e0 == 0 ? bd : 0);
+                        int32_t *wr  = sh.W + row[j] * FW_WSTRIDE;
+#pragma unroll
+                        for (int c = 0; c < 16; c++) {
+                            run += (int)((d[j][c >> 2] >> (8 * (c & 3))) & 0xFF) - (int)FW_DBIAS;
+                            if (e0 == 0) wr[c] = run; else wr[c] += run;
+                        }
+                    }
+                }
+                if (e0 + FW_CH >= n_e) break;
+            }
+            if (skip) continue;
+            if (use_w) {  // each lane reads back the rows it accumulated itself
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    if (row[j] < ROWS) {
+                        const int32_t *wr   = sh.W + row[j] * FW_WSTRIDE;
+                        uint32_t       bits = 0;
+#pragma unroll
+                        for (int c = 0; c < 16; c++) bits |= ((wr[c] & par) != 0 ? 1u : 0u) << c;
+                        m |= bits << (16 * j);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < P; j++)
+                if (row[j] < ROWS) sh.rowmask[row[j]] = (uint16_t)(m >> (16 * j));
+            // ---- queue of the pixels with a covered sample: OR over the S sample rows of a pixel row, then every lane of the
+            //      group pushes its share of the set bits ----
+            uint32_t many = m;
+            if (S >= 2) many |= __shfl_xor_sync(FULL, many, 1);
+            if (S >= 4) many |= __shfl_xor_sync(FULL, many, 2);
+            uint32_t       mine  = many & share;
+            const uint32_t cnt   = (uint32_t)__popc(mine);
+            const uint32_t incl  = warp_incl_scan(cnt);
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (total == 0) continue;  // (warp uniform; nothing was written that a later path-tile does not overwrite)
+            uint32_t off = incl - cnt;
+            while (mine) {
+                const uint32_t b = (uint32_t)__ffs((int)mine) - 1u;
+                mine &= mine - 1u;
+                sh.queue[off++] = (uint8_t)((grp + 8 * (b >> 4)) * 16 + (b & 15));
+            }
+            __syncwarp();
+            // ---- blend, 32 pixels at a time ----
+            for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+                const bool     act = i0 + lane < total;
+                const uint32_t pq  = act ? sh.queue[i0 + lane] : 0u;
+                const uint32_t lx = pq & 15, ly = pq >> 4;
+                int32_t        n[S];
+                if (counted) {
+#pragma unroll
+                    for (int s = 0; s < S; s++) n[s] = act ? abs(sh.W[(ly * S + s) * FW_WSTRIDE + lx]) : 0;
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; s++) n[s] = act ? (int32_t)((sh.rowmask[ly * S + s] >> lx) & 1u) : 0;
+                }
+                if (pattern != VKB_PAT_SOLID) {
+                    const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
+                    eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color,
+                               pt.opacity, (float)px + 0.5f, (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut, a.surfpats, pt.gradient);
+                    ia = 1.0f - src[3];
+                    if (op == VKB_OP_SUB) ia = -ia;
+                    else if (op == VKB_OP_CLEAR) { src[0] = src[1] = src[2] = src[3] = 0.0f; ia = 0.0f; }
+                }
+                if (counted && ia == 0.0f) {  // the result does not depend on the destination: repeating the blend changes nothing
+#pragma unroll
+                    for (int s = 0; s < S; s++) n[s] = n[s] ? 1 : 0;
+                }
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    if (n[s] != 0) {  // (a sample no lane covers costs one branch)
+                        uint32_t *cp = sh.col + (ly * S + s) * 16 + lx;
+                        uint32_t  c  = blend_over(*cp, src, ia, lut);
+                        if (counted)
+                            for (int32_t r = 1; r < n[s]; r++) c = blend_over(c, src, ia, lut);
+                        *cp = c;
+                    }
+                }
+            }
+            __syncwarp();  // the queue, the row masks and the winding plane are reused by the next path-tile
+        }
+    }
+
+    // ---- resolve; pixels whose samples differ also go to the per-sample plane (same layout and flags as fine_k) ----
+    __syncwarp();
+    uint32_t my_mask = 0, any_mask = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t lx = (lane & 7) + 8 * (i & 1), ly = (lane >> 3) + 4 * (i >> 1);
+        const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
+        uint32_t       c[S];
+        bool           differ = false;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            c[s]   = sh.col[(ly * S + s) * 16 + lx];
+            differ = differ || c[s] != c[0];
+        }
+        const uint32_t dmask = __ballot_sync(FULL, differ);
+        if (lane == i) my_mask = dmask;
+        any_mask |= dmask;
+        if (differ) {
+#pragma unroll
+            for (int s = 0; s < S; s++) a.ms_image[((size_t)tile * 256 + i * 32 + lane) * S + s] = c[s];
+        }
+        if (px < a.sd.width && py < a.sd.height) {
+            uint32_t out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t sum = 0;
+#pragma unroll
+                for (int s = 0; s < S; s++) sum += (c[s] >> (8 * k)) & 0xFF;
+                out |= ((sum + S / 2) / S) << (8 * k);
+            }
+            a.image[(size_t)py * a.sd.width + px] = out;
+        }
+    }
+    if (any_mask && lane < 8) a.ms_mask[tile * 8 + lane] = my_mask;
+    if (lane == 0) a.tile_ms[tile] = any_mask ? 1 : 0;
+}
+
+// VKVG_B200_FINE=block (or vkvg_b200_set_fine_kernel(1)) forces fine_k for every batch: A/B timing and the kernel-equivalence test
+static int g_fine_force_block = [] {
+    const char *e = getenv("VKVG_B200_FINE");
+    return (e && e[0] == 'b') ? 1 : 0;
+}();
+void vkb_fine_force_block(int on) { g_fine_force_block = on ? 1 : 0; }
+int  vkb_fine_block_forced() { return g_fine_force_block; }
+template <int S> static void launch_fine_warp(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
+    fine_warp_k<S><<<vkb_div_up(tiles, FW_TILES), 32 * FW_TILES, 0, s>>>(a, tiles);
+}
 template <int S> static void launch_fine_s(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
     const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
+    if constexpr (S <= 4) {
+        if (!cap && !clip && !g_fine_force_block) { launch_fine_warp<S>(a, tiles, s); return; }
+    }
     if (cap) { if (clip) fine_k<S, true, true><<<tiles, 256, 0, s>>>(a); else fine_k<S, true, false><<<tiles, 256, 0, s>>>(a); }
     else { if (clip) fine_k<S, false, true><<<tiles, 256, 0, s>>>(a); else fine_k<S, false, false><<<tiles, 256, 0, s>>>(a); }
 }
