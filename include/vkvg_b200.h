@@ -166,9 +166,10 @@ vkvg_public void     vkvg_b200_device_set_graphs(VkvgDevice dev, int on);
 vkvg_public void     vkvg_b200_device_set_stage_timing(VkvgDevice dev, int on);
 vkvg_public uint64_t vkvg_b200_device_graph_replays(VkvgDevice dev);
 /* Which fine-pass kernel renders batches that carry no clip state (process-wide; both give identical pixels):
- *   0 (default)  fine_warp_k: one warp per 16x16 tile, covered pixels compacted into a queue
+ *   0 (default)  by surface size: fine_warp_k from 16384 tiles (2048 x 2048 pixels) up, fine_k below
  *   1            fine_k: one block of 8 warps per tile (the kernel that also serves clip / save / restore batches)
- * Environment: VKVG_B200_FINE=block selects 1 at start-up. */
+ *   2            fine_warp_k: one warp per 16x16 tile, covered pixels compacted into a queue
+ * Environment: VKVG_B200_FINE=block|warp selects 1 / 2 at start-up. */
 vkvg_public void     vkvg_b200_set_fine_kernel(int mode);
 vkvg_public int      vkvg_b200_get_fine_kernel(void);
 

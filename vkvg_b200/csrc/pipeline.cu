@@ -749,7 +749,7 @@ struct FlushKey {
     const void *surf;
     uint32_t w, h, samples, full_h, origin_y;
     uint32_t known_clear, stencil_live, stencil_samples, tile_ms_allocated;
-    uint32_t fine_mode, pad0;  // vkb_fine_force_block: which fine kernel a captured graph holds
+    uint32_t fine_mode, pad0;  // vkb_fine_set_mode: which fine kernel a captured graph holds
     unsigned long long alloc_generation;
 };
 static_assert(sizeof(FlushKey) <= 256, "FlushKey");
@@ -774,7 +774,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     k.known_clear = surf->known_clear; k.stencil_live = surf->stencil_live; k.stencil_samples = surf->stencil_samples;
     k.tile_ms_allocated = surf->tile_ms.p != nullptr;
     k.alloc_generation = g_vkb_alloc_generation;
-    k.fine_mode = (uint32_t)vkb_fine_block_forced();
+    k.fine_mode = (uint32_t)vkb_fine_get_mode();
     memcpy(kbuf, &k, sizeof k);
     if (d->graph_exec && !memcmp(kbuf, d->graph_key, sizeof kbuf)) {
         // replay; the host-side effects of enqueue_flush on the surface flags are re-applied by hand

@@ -112,9 +112,9 @@ struct FineArgs {
 };
 void vkb_launch_grad_prep(const vkb_gradient *grads, uint32_t n, float W, float H, float *out, cudaStream_t s);
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s);
-// 1: every batch goes through the block-per-tile kernel fine_k (A/B timing, kernel-equivalence test); 0: batches without clip
-// state or winding capture use the warp-per-tile kernel fine_warp_k.  Process-wide; VKVG_B200_FINE=block sets it at start-up
-void vkb_fine_force_block(int on);
-int  vkb_fine_block_forced();
+// fine kernel for batches without clip state or winding capture: 0 = chosen by tile count, 1 = block-per-tile fine_k, 2 = warp-per-tile
+// fine_warp_k.  Process-wide; VKVG_B200_FINE=block|warp sets it at start-up
+void vkb_fine_set_mode(int mode);
+int  vkb_fine_get_mode();
 
 void vkb_launch_unpremultiply(const uint32_t *image, uint64_t n_pixels, uint32_t *out, cudaStream_t s);

@@ -1328,7 +1328,7 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
 // ----------------------------------------------------------------------------------------------------
 #define FW_TILES 4      // tiles (= warps) per block; they only share the u8 -> float table
 #define FW_WSTRIDE 17   // words per sample row of the winding plane (odd: lanes = rows hit distinct banks)
-template <int S> struct FwShared {
+template <int S> struct alignas(16) FwShared {
     uint32_t col[16 * S * 16];        // sample colours, [sample row = ly * S + s][lx]
     int32_t  W[16 * S * FW_WSTRIDE];  // per-sample windings of the current path-tile (multi-chunk / COUNT rule only)
     uint16_t rowmask[16 * S];         // per sample row: bit lx = covered by the current path-tile
@@ -1548,13 +1548,18 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                 const bool     act = i0 + lane < total;
                 const uint32_t pq  = act ? sh.queue[i0 + lane] : 0u;
                 const uint32_t lx = pq & 15, ly = pq >> 4;
-                int32_t        n[S];
+                int32_t        n[S], nmax = 0;
                 if (counted) {
 #pragma unroll
                     for (int s = 0; s < S; s++) n[s] = act ? abs(sh.W[(ly * S + s) * FW_WSTRIDE + lx]) : 0;
-                } else {
+                } else {  // the S row masks of a pixel row are adjacent: one load
+                    unsigned long long rm;
+                    if (S == 4) rm = *(const unsigned long long *)(sh.rowmask + ly * 4);
+                    else if (S == 2) rm = *(const uint32_t *)(sh.rowmask + ly * 2);
+                    else rm = sh.rowmask[ly];
+                    rm = act ? rm >> lx : 0ull;
 #pragma unroll
-                    for (int s = 0; s < S; s++) n[s] = act ? (int32_t)((sh.rowmask[ly * S + s] >> lx) & 1u) : 0;
+                    for (int s = 0; s < S; s++) n[s] = (int32_t)((uint32_t)(rm >> (16 * s)) & 1u);
                 }
                 if (pattern != VKB_PAT_SOLID) {
                     const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
@@ -1564,18 +1569,41 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                     if (op == VKB_OP_SUB) ia = -ia;
                     else if (op == VKB_OP_CLEAR) { src[0] = src[1] = src[2] = src[3] = 0.0f; ia = 0.0f; }
                 }
-                if (counted && ia == 0.0f) {  // the result does not depend on the destination: repeating the blend changes nothing
-#pragma unroll
-                    for (int s = 0; s < S; s++) n[s] = n[s] ? 1 : 0;
-                }
+                const bool opaque = ia == 0.0f;  // the result does not depend on the destination: repeating the blend changes nothing
+                uint32_t  *cp = sh.col + (ly * S) * 16 + lx;
+                uint32_t   c[S];
+                bool       uni = true, two = true;
 #pragma unroll
                 for (int s = 0; s < S; s++) {
-                    if (n[s] != 0) {  // (a sample no lane covers costs one branch)
-                        uint32_t *cp = sh.col + (ly * S + s) * 16 + lx;
-                        uint32_t  c  = blend_over(*cp, src, ia, lut);
-                        if (counted)
-                            for (int32_t r = 1; r < n[s]; r++) c = blend_over(c, src, ia, lut);
-                        *cp = c;
+                    if (counted && opaque) n[s] = n[s] ? 1 : 0;
+                    nmax = max(nmax, n[s]);
+                    c[s] = cp[16 * s];
+                    uni  = uni && c[s] == c[0];
+                }
+                if (counted) {
+#pragma unroll
+                    for (int s = 0; s < S; s++) two = two && (n[s] == 0 || n[s] == nmax);
+                }
+                // one result per pixel when its samples hold one colour (or the source is opaque) and are blended equally often:
+                // warp-uniform choice, a divergent one would execute both variants
+                if (__all_sync(FULL, !act || ((uni || opaque) && two))) {
+                    uint32_t r = blend_over(c[0], src, ia, lut);
+                    if (counted)
+                        for (int32_t k = 1; k < nmax; k++) r = blend_over(r, src, ia, lut);
+                    if (act) {
+#pragma unroll
+                        for (int s = 0; s < S; s++)
+                            if (n[s]) cp[16 * s] = r;
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        if (n[s] != 0) {  // (a sample no lane covers costs one branch)
+                            uint32_t r = blend_over(c[s], src, ia, lut);
+                            if (counted)
+                                for (int32_t k = 1; k < n[s]; k++) r = blend_over(r, src, ia, lut);
+                            cp[16 * s] = r;
+                        }
                     }
                 }
             }
@@ -1620,20 +1648,24 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
     if (lane == 0) a.tile_ms[tile] = any_mask ? 1 : 0;
 }
 
-// VKVG_B200_FINE=block (or vkvg_b200_set_fine_kernel(1)) forces fine_k for every batch: A/B timing and the kernel-equivalence test
-static int g_fine_force_block = [] {
+// Which kernel serves a batch without clip state: the warp-per-tile kernel needs many more tiles than the GPU has warp slots
+// (148 SMs x 24 warps) to keep every scheduler busy, and a tile with a long list is walked by one warp from start to end; on
+// small surfaces (tiger at 1024^2: 4096 tiles) the block-per-tile kernel finishes sooner.  vkvg_b200_set_fine_kernel /
+// VKVG_B200_FINE=block|warp override the choice (A/B timing, kernel-equivalence test).
+#define FW_MIN_TILES 16384u
+static int g_fine_mode = [] {
     const char *e = getenv("VKVG_B200_FINE");
-    return (e && e[0] == 'b') ? 1 : 0;
+    return (e && e[0] == 'b') ? 1 : ((e && e[0] == 'w') ? 2 : 0);
 }();
-void vkb_fine_force_block(int on) { g_fine_force_block = on ? 1 : 0; }
-int  vkb_fine_block_forced() { return g_fine_force_block; }
+void vkb_fine_set_mode(int mode) { g_fine_mode = (mode == 1 || mode == 2) ? mode : 0; }
+int  vkb_fine_get_mode() { return g_fine_mode; }
 template <int S> static void launch_fine_warp(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
     fine_warp_k<S><<<vkb_div_up(tiles, FW_TILES), 32 * FW_TILES, 0, s>>>(a, tiles);
 }
 template <int S> static void launch_fine_s(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
     const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
     if constexpr (S <= 4) {
-        if (!cap && !clip && !g_fine_force_block) { launch_fine_warp<S>(a, tiles, s); return; }
+        if (!cap && !clip && (g_fine_mode == 2 || (g_fine_mode == 0 && tiles >= FW_MIN_TILES))) { launch_fine_warp<S>(a, tiles, s); return; }
     }
     if (cap) { if (clip) fine_k<S, true, true><<<tiles, 256, 0, s>>>(a); else fine_k<S, true, false><<<tiles, 256, 0, s>>>(a); }
     else { if (clip) fine_k<S, false, true><<<tiles, 256, 0, s>>>(a); else fine_k<S, false, false><<<tiles, 256, 0, s>>>(a); }

@@ -94,8 +94,8 @@ int              vkb_device_failed(vkb_device_impl *d);
 void             vkb_device_sync(vkb_device_impl *d);
 void             vkb_device_set_stage_timing(vkb_device_impl *d, bool on);
 void             vkb_device_set_graphs(vkb_device_impl *d, bool on);
-void             vkb_fine_force_block(int on);  // raster.cu: which fine kernel serves batches without clip state (process-wide)
-int              vkb_fine_block_forced();
+void             vkb_fine_set_mode(int mode);  // raster.cu: which fine kernel serves batches without clip state (process-wide)
+int              vkb_fine_get_mode();
 unsigned long long vkb_device_graph_replays(vkb_device_impl *d);
 
 vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, uint32_t full_h, uint32_t origin_y);

@@ -1468,8 +1468,8 @@ void vkvg_b200_device_set_graphs(VkvgDevice dev, int on) {
     std::lock_guard<std::mutex> lk(dev->mtx);
     vkb_device_set_graphs(dev->impl, on != 0);
 }
-void vkvg_b200_set_fine_kernel(int mode) { vkb_fine_force_block(mode == 1); }
-int  vkvg_b200_get_fine_kernel(void) { return vkb_fine_block_forced(); }
+void vkvg_b200_set_fine_kernel(int mode) { vkb_fine_set_mode(mode); }
+int  vkvg_b200_get_fine_kernel(void) { return vkb_fine_get_mode(); }
 uint64_t vkvg_b200_device_graph_replays(VkvgDevice dev) { return vkvg_device_status(dev) ? 0 : vkb_device_graph_replays(dev->impl); }
 void vkvg_b200_get_source_push(VkvgContext ctx, float out[10]) {  // what the reference keeps in pushConsts.source / .matInv
     if (vkvg_status(ctx) || !out) return;
