@@ -497,11 +497,21 @@ def run_ours(args):
         fine_src = "events around the kernel in %d plain-launch steps run before the timed region" % args.steps
     achieved = alg_bytes / (fine_ms * 1e-3) / 1e9
     stage = {k: val / (args.steps * reps) for k, val in st_stages["ms_stage"].items()}   # per flush
+    # which fine kernel ran: batches without clip state go to the warp-per-tile kernel from 16384 tiles up (raster.cu: FW_MIN_TILES)
+    n_tiles = ((size + 15) // 16) * ((surf.height + 15) // 16)
+    mode = L.vkvg_b200_get_fine_kernel()
+    if args.coverage != "msaa":
+        fine_name = "fine_analytic_k"
+    elif mode == 2 or (mode == 0 and n_tiles >= 16384):
+        fine_name = "fine_warp_k<4>"
+    else:
+        fine_name = "fine_k<4>"
     traffic = None   # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture of this workload
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if w in tj and args.coverage == "msaa" and world == 1:
-            traffic = int(tj[w]["dram_bytes_per_launch"])
+        for key in (w, w + "_block"):
+            if key in tj and tj[key]["kernel"] == fine_name and world == 1:
+                traffic = int(tj[key]["dram_bytes_per_launch"])
     except Exception:
         pass
     name, unit = UNITS[w]
@@ -518,7 +528,7 @@ def run_ours(args):
                 "host_record_ms": parts[0] / args.steps * 1e3, "upload_render_ms": parts[1] / args.steps * 1e3,
                 "readback_ms": parts[2] / args.steps * 1e3, "h2d_bytes_wire": int(st["h2d_bytes"])},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "fine_k<4>" if args.coverage == "msaa" else "fine_analytic_k", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": fine_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "kernel_ms": fine_ms, "kernel_ms_source": fine_src, "peak_source": peak_src,
                      "whole_step_frac": alg_bytes * reps / (ms_step * 1e-3) / 1e9 / peak},
         "stage_ms": stage, "stage_ms_note": "per flush, plain launches with events between stages: %.3f ms per flush" % (st_stages["ms_total"] / (args.steps * reps)),

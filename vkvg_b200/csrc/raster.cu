@@ -350,6 +350,7 @@ template <class F> __device__ __forceinline__ void for_each_tile_of_edge(const v
     if (tw <= 0) return;
     const int32_t ymin = min(e.y0, e.y1), ymax = max(e.y0, e.y1);
     int32_t r0 = max(floor_div(ymin, VKB_TILE_FX), ty0), r1 = min(floor_div(ymax, VKB_TILE_FX), ty0 + th - 1);
+    if (r0 + row_off > r1) return;  // outside the draw's rows (on a stripe surface: most edges of the scene) before any double arithmetic
     const double dxdy = (e.y1 != e.y0) ? ((double)e.x1 - (double)e.x0) / ((double)e.y1 - (double)e.y0) : 0.0;
     const int    sgn  = e.y1 > e.y0 ? 1 : -1;
     for (int32_t r = r0 + row_off; r <= r1; r += row_step) {
@@ -1422,6 +1423,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
         const int r = min(row[j], ROWS - 1);
         ry[j]  = (r / S) * 256 + 16 * (int32_t)((SamplePack<S>::Y >> (4 * (r % S))) & 15);
         rxo[j] = 16 * (int32_t)((SamplePack<S>::X >> (4 * (r % S))) & 15);
+        asm volatile("" : "+r"(ry[j]), "+r"(rxo[j]));  // keep them: the compiler otherwise re-derives both for every path-tile
     }
     const uint32_t grp = lane / S, sub = lane % S;  // pixel row group / which of its pixels this lane queues
     const uint32_t share = (S == 4 ? 0x11111111u : (S == 2 ? 0x55555555u : 0xffffffffu)) << sub;
