@@ -418,13 +418,12 @@ __global__ void gather_first_items_k(const uint32_t *first_job, const uint32_t *
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = job_base[first_job[i]];
 }
-// the four edges of a rectangle one tile larger than the surface for every whole-surface draw; they follow the fill and
-// stroke edges, whose number only the device knows
+// the four edges of a rectangle one tile larger than the surface for every whole-surface draw; they follow the fill edges
 __global__ void extra_rect_edges_k(vkb_edge *edges, uint32_t *edge_draw, const uint32_t *extra_edge_draw, uint32_t n_rects, int32_t W, int32_t H,
                                    const vkb_counts *C) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rects || C->overflow) return;
-    const uint32_t base = C->n[VKC_FILL] + 3u * C->n[VKC_TRIS];
+    const uint32_t base = C->n[VKC_FILL];  // (before the stroke edges, whose stored number is only known after tri_edges_k)
     vkb_edge      *e    = edges + base;
     const int32_t  x0 = -VKB_TILE_FX, y0 = -VKB_TILE_FX, x1 = W * 256 + VKB_TILE_FX, y1 = H * 256 + VKB_TILE_FX;
     e[4 * i]     = vkb_edge{x0, y0, x1, y0};
@@ -728,7 +727,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         VKB_LAUNCHED();
         d->snapped.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
         vkb_launch_tri_edges(d->verts.as<float2>(), cv[VKC_VERTS], d->snapped.as<int2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
-                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, st);
+                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, d->n_extra, (uint32_t *)(totals + 9), C, st);
     }
     if (d->n_extra) {
         extra_rect_edges_k<<<vkb_div_up(d->n_extra / 4, 64), 64, 0, st>>>(edges, edraw, d->extra_edge_draw.as<uint32_t>(), d->n_extra / 4, (int32_t)sd.width,

@@ -50,11 +50,13 @@ struct SurfaceDesc {
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
                            vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
-// edges / edge_draw: start of the edge arrays (the kernel skips the C->n[VKC_FILL] fill edges itself)
+// edges / edge_draw: start of the edge arrays (the kernel skips the C->n[VKC_FILL] fill edges and the n_extra rectangle edges itself);
+// live: zeroed device counter of the stroke edges stored (cancelled ones are dropped); Cw->n[VKC_EDGES] is set to the stored total
 // snapped: cap_verts int2 of scratch (every stroke vertex goes through the vertex stage once, then the triangles read integers)
 void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
                           const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
-                          const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
+                          const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
+                          vkb_counts *Cw, cudaStream_t s);
 
 struct BinBuffers {  // all device pointers
     int32_t  *draw_bbox;    // n_draws x 4 (minx, miny, maxx, maxy), fixed point

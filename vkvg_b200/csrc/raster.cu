@@ -139,14 +139,19 @@ __device__ __forceinline__ int tri_sign(const int2 *snapped, uint32_t n_verts, c
     long long area = (long long)(x[1] - x[0]) * (y[2] - y[0]) - (long long)(x[2] - x[0]) * (y[1] - y[0]);
     return area > 0 ? -1 : (area < 0 ? 1 : 0);  // cross > 0 winds -1 under our convention: such a triangle is reversed
 }
+// Only the edges that survive are stored: every warp reserves room for its live edges with one atomic on *live (the order of
+// the edges of a draw is immaterial: windings and backdrops are sums), so the binning kernels never see the ~60 % of slots that
+// cancelled.  Layout of the edge array: fill edges, whole-surface rectangles (n_extra), then the live stroke edges.
 __global__ void __launch_bounds__(256)
 tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item,
-            uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw) {
+            uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_tris = C->n[VKC_TRIS], n_verts = C->n[VKC_VERTS];
-    if (t >= n_tris) return;
-    edges += C->n[VKC_FILL]; edge_draw += C->n[VKC_FILL];  // stroke edges follow the fill edges
+    if ((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) >= n_tris) return;  // whole warps leave; a partial warp stays for the shuffles below
+    const bool in_range = t < n_tris;
+    if (!in_range) t = n_tris - 1;
+    edges += C->n[VKC_FILL] + n_extra; edge_draw += C->n[VKC_FILL] + n_extra;
     // stroke draw owning index 3t: last q whose first item's index offset <= 3t
     uint32_t lo = 0, hi = n_sdraws;
     while (hi - lo > 1) {
@@ -186,16 +191,37 @@ tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, cons
         }
         if (!drop) e[k] = vkb_edge{x[ka], y[ka], x[kb], y[kb]};
     }
-    edges[3 * t] = e[0]; edges[3 * t + 1] = e[1]; edges[3 * t + 2] = e[2];
-    edge_draw[3 * t] = d; edge_draw[3 * t + 1] = d; edge_draw[3 * t + 2] = d;
+    bool     keep[3];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        keep[k] = in_range && !(e[k].x0 == e[k].x1 && e[k].y0 == e[k].y1);
+        cnt += keep[k] ? 1u : 0u;
+    }
+    const uint32_t incl = warp_incl_scan(cnt);
+    uint32_t       base = 0;
+    if ((threadIdx.x & 31) == 31 && incl) base = atomicAdd(live, incl);
+    uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (keep[k]) { edges[pos] = e[k]; edge_draw[pos] = d; pos++; }
+}
+// the stroke edges that survived are only counted by tri_edges_k: C->n[VKC_EDGES] (so far the upper bound fill + 3 x triangles +
+// rectangles, which sized the buffers) becomes the number actually stored
+__global__ void commit_live_edges_k(vkb_counts *C, const uint32_t *live, uint32_t n_extra) {
+    if (C->overflow) return;
+    C->n[VKC_EDGES] = C->n[VKC_FILL] + n_extra + *live;
 }
 void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
                           const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
-                          const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
+                          const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
+                          vkb_counts *Cw, cudaStream_t s) {
     if (!cap_tris || !n_sdraws) return;
     snap_verts_k<<<vkb_div_up(cap_verts, 256), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
     VKB_LAUNCHED();
-    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw);
+    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live);
+    VKB_LAUNCHED();
+    commit_live_edges_k<<<1, 1, 0, s>>>(Cw, live, n_extra);
     VKB_LAUNCHED();
 }
 
@@ -206,6 +232,19 @@ __global__ void draw_bbox_init_k(int32_t *bbox, uint32_t n_draws) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_draws) return;
     bbox[4 * i] = INT32_MAX; bbox[4 * i + 1] = INT32_MAX; bbox[4 * i + 2] = INT32_MIN; bbox[4 * i + 3] = INT32_MIN;
+}
+// Three tiers, because millions of edges may aim at the four words of one draw (a long stroke) while elsewhere every few edges
+// belong to another draw (small fills): a block whose edges all belong to one draw reduces in shared memory and issues at most four
+// atomics; else a warp whose edges all belong to one draw reduces with redux.sync; else every edge goes to the atomics directly.
+// The reducing tiers look at the box first: a stale read only costs a redundant atomic, never a missed one (the box only grows),
+// so after the first few blocks of a long stroke almost none is issued.
+__device__ __forceinline__ void bbox_grow(int32_t *bbox, uint32_t d, int32_t mnx, int32_t mny, int32_t mxx, int32_t mxy) {
+    if (mnx > mxx) return;
+    volatile int32_t *vb = bbox + 4 * (size_t)d;
+    if (mnx < vb[0]) atomicMin(&bbox[4 * (size_t)d], mnx);
+    if (mny < vb[1]) atomicMin(&bbox[4 * (size_t)d + 1], mny);
+    if (mxx > vb[2]) atomicMax(&bbox[4 * (size_t)d + 2], mxx);
+    if (mxy > vb[3]) atomicMax(&bbox[4 * (size_t)d + 3], mxy);
 }
 __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, int32_t *bbox) {
     if (C->overflow) return;
@@ -218,20 +257,18 @@ __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const 
     ok          = ok && !edge_degenerate(e);
     int32_t mnx = ok ? min(e.x0, e.x1) : INT32_MAX, mny = ok ? min(e.y0, e.y1) : INT32_MAX;
     int32_t mxx = ok ? max(e.x0, e.x1) : INT32_MIN, mxy = ok ? max(e.y0, e.y1) : INT32_MIN;
-    // one long stroke puts millions of edges on one draw: reduce inside the block when it is uniform
     __shared__ uint32_t d0;
     __shared__ int32_t  red[4][8];
-    if (threadIdx.x == 0) d0 = edge_draw[min((uint64_t)blockIdx.x * blockDim.x, n_edges - 1)];
+    if (threadIdx.x == 0) d0 = d;
     __syncthreads();
-    bool uniform = __syncthreads_and(d == d0 || i >= n_edges);
-    if (uniform) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-            mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-        }
+    const bool block_uniform = __syncthreads_and(d == d0 || i >= n_edges);
+    const uint32_t dw = __shfl_sync(0xffffffffu, d, 0);
+    const bool warp_uniform = block_uniform || __all_sync(0xffffffffu, d == dw || i >= n_edges);
+    if (warp_uniform) {
+        mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+        mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    }
+    if (block_uniform) {
         if ((threadIdx.x & 31) == 0) {
             red[0][threadIdx.x >> 5] = mnx; red[1][threadIdx.x >> 5] = mny; red[2][threadIdx.x >> 5] = mxx; red[3][threadIdx.x >> 5] = mxy;
         }
@@ -240,18 +277,12 @@ __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const 
             for (int w = 1; w < 8; w++) {
                 mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
             }
-            if (mnx <= mxx) {
-                // millions of edges of one stroke all aim at the same four words: look first (a stale read only costs a redundant
-                // atomic, never a missed one: the box only ever grows), so that after the first few blocks almost none is issued
-                volatile int32_t *vb = bbox + 4 * d0;
-                if (mnx < vb[0]) atomicMin(&bbox[4 * d0], mnx);
-                if (mny < vb[1]) atomicMin(&bbox[4 * d0 + 1], mny);
-                if (mxx > vb[2]) atomicMax(&bbox[4 * d0 + 2], mxx);
-                if (mxy > vb[3]) atomicMax(&bbox[4 * d0 + 3], mxy);
-            }
+            bbox_grow(bbox, d0, mnx, mny, mxx, mxy);
         }
+    } else if (warp_uniform) {
+        if ((threadIdx.x & 31) == 0) bbox_grow(bbox, dw, mnx, mny, mxx, mxy);
     } else if (ok) {
-        atomicMin(&bbox[4 * d], mnx); atomicMin(&bbox[4 * d + 1], mny); atomicMax(&bbox[4 * d + 2], mxx); atomicMax(&bbox[4 * d + 3], mxy);
+        atomicMin(&bbox[4 * (size_t)d], mnx); atomicMin(&bbox[4 * (size_t)d + 1], mny); atomicMax(&bbox[4 * (size_t)d + 2], mxx); atomicMax(&bbox[4 * (size_t)d + 3], mxy);
     }
 }
 void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
