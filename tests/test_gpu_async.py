@@ -250,3 +250,33 @@ def test_contexts_on_different_threads(oracle_lib):
     dc.flush()
     assert np.array_equal(dst.pixels(), od.pixels())
     dev.close()
+
+
+def test_recording_right_after_a_flush_does_not_disturb_it():
+    """vkvg_flush returns while the GPU still works; the recorder's arrays (copied to the device straight from pinned memory) are
+    overwritten by the next frame's calls at once.  A large upload (24 MB) followed immediately by a different frame must give the
+    same pixels as the same two frames with a device synchronisation in between."""
+    n = 1_000_000
+    rng = np.random.default_rng(11)
+    a = (rng.random((n, 2)) * 500 + 6).astype(np.float32)
+    b = (rng.random((n, 2)) * 500 + 6).astype(np.float32)
+    imgs = []
+    for wait in (True, False):
+        dev = v.Device(4)
+        surf = v.Surface(dev, 512, 512)
+        ctx = v.Context(surf)
+        for k, pts in enumerate((a, b, a[::-1].copy())):
+            cs = v.CommandStream()
+            cs.set_source_rgba(0.2 + 0.3 * k, 0.9 - 0.3 * k, 0.5, 0.5)
+            cs.set_line_width(1.0)
+            cs.polyline(pts)
+            cs.stroke()
+            assert ctx.replay(*cs.arrays()) == 0
+            ctx.flush()
+            if wait:
+                dev.synchronize()
+        imgs.append(surf.pixels())
+        ctx.close()
+        surf.close()
+        dev.close()
+    assert np.array_equal(imgs[0], imgs[1])

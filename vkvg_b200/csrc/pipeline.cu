@@ -904,7 +904,11 @@ int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sam
 
 int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const vkb_batch &b, vkb_capture *cap, vkb_stats *stats) {
     if (vkb_upload(d, b)) return 1;
-    return run_flush(d, s, samples, cap, stats, true);
+    const int r = run_flush(d, s, samples, cap, stats, true);
+    // the element arrays were copied straight out of the recorder's pinned vectors, which the caller goes on writing into as soon
+    // as the flush returns: wait for that copy (not for the kernels queued behind it)
+    VKB_CUDA_OK(cudaEventSynchronize(d->ev_h2d));
+    return r | g_cuda_failed;
 }
 
 int vkb_device_ordinal(vkb_device_impl *d) { return d->ordinal; }

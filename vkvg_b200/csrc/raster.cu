@@ -235,8 +235,8 @@ __global__ void draw_bbox_init_k(int32_t *bbox, uint32_t n_draws) {
 }
 // Three tiers, because millions of edges may aim at the four words of one draw (a long stroke) while elsewhere every few edges
 // belong to another draw (small fills): a block whose edges all belong to one draw reduces in shared memory and issues at most four
-// atomics; else a warp whose edges all belong to one draw reduces with redux.sync; else every edge goes to the atomics directly.
-// The reducing tiers look at the box first: a stale read only costs a redundant atomic, never a missed one (the box only grows),
+// atomics; else a warp whose edges all belong to one draw reduces with redux.sync; else every edge goes to the atomics on its own.
+// All tiers look at the box first: a stale read only costs a redundant atomic, never a missed one (the box only grows),
 // so after the first few blocks of a long stroke almost none is issued.
 __device__ __forceinline__ void bbox_grow(int32_t *bbox, uint32_t d, int32_t mnx, int32_t mny, int32_t mxx, int32_t mxy) {
     if (mnx > mxx) return;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const 
     } else if (warp_uniform) {
         if ((threadIdx.x & 31) == 0) bbox_grow(bbox, dw, mnx, mny, mxx, mxy);
     } else if (ok) {
-        atomicMin(&bbox[4 * (size_t)d], mnx); atomicMin(&bbox[4 * (size_t)d + 1], mny); atomicMax(&bbox[4 * (size_t)d + 2], mxx); atomicMax(&bbox[4 * (size_t)d + 3], mxy);
+        bbox_grow(bbox, d, mnx, mny, mxx, mxy);  // (looks first here too: where two long strokes meet, warps mix their edges)
     }
 }
 void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
