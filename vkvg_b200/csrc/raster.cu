@@ -62,6 +62,12 @@ void vkb_launch_job_counts(const uint32_t *job_sp, uint32_t n_jobs, const uint32
     VKB_LAUNCHED();
 }
 
+// An edge wholly above, below or to the right of the surface changes no sample of it: the winding of a sample only counts edges that
+// span its height and cross at or left of it.  (Wholly to the LEFT does count: it is part of every backdrop of its rows.)  On a stripe
+// surface (multi-GPU tile rows) this removes most of the scene before binning looks at it.
+__device__ __forceinline__ bool edge_off_surface(const vkb_edge &e, const SurfaceDesc &sd) {
+    return max(e.y0, e.y1) < 0 || min(e.y0, e.y1) > (int32_t)sd.height * 256 || min(e.x0, e.x1) > (int32_t)sd.width * 256;
+}
 // ---- fill: one edge per point of every sub-path with > 2 points (the fan of _poly_fill covers exactly the
 //      implicitly closed polygon, internal.c:1617-1642) ----
 __global__ void __launch_bounds__(256)
@@ -79,6 +85,7 @@ fill_edges_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, 
     vs_snap(m, (float)sd.width, (float)sd.full_height, b.x, b.y, e.x1, e.y1);
     const int32_t yoff = (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256;
     e.y0 += yoff; e.y1 += yoff;
+    if (edge_off_surface(e, sd)) e = vkb_edge{0, 0, 0, 0};  // (a degenerate edge: every later stage skips it)
     edges[item]     = e;
     edge_draw[item] = d;
 }
@@ -144,7 +151,8 @@ __device__ __forceinline__ int tri_sign(const int2 *snapped, uint32_t n_verts, c
 // cancelled.  Layout of the edge array: fill edges, whole-surface rectangles (n_extra), then the live stroke edges.
 __global__ void __launch_bounds__(256)
 tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item,
-            uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live) {
+            uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
+            SurfaceDesc sd) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_tris = C->n[VKC_TRIS], n_verts = C->n[VKC_VERTS];
@@ -195,7 +203,7 @@ tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, cons
     uint32_t cnt = 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        keep[k] = in_range && !(e[k].x0 == e[k].x1 && e[k].y0 == e[k].y1);
+        keep[k] = in_range && !(e[k].x0 == e[k].x1 && e[k].y0 == e[k].y1) && !edge_off_surface(e[k], sd);
         cnt += keep[k] ? 1u : 0u;
     }
     const uint32_t incl = warp_incl_scan(cnt);
@@ -219,7 +227,7 @@ void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped
     if (!cap_tris || !n_sdraws) return;
     snap_verts_k<<<vkb_div_up(cap_verts, 256), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
     VKB_LAUNCHED();
-    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live);
+    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd);
     VKB_LAUNCHED();
     commit_live_edges_k<<<1, 1, 0, s>>>(Cw, live, n_extra);
     VKB_LAUNCHED();
