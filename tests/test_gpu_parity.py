@@ -650,3 +650,48 @@ def test_warp_and_block_fine_kernels_agree(fine_kernel_knob, oracle_lib, samples
         c.close()
         s.close()
     assert np.array_equal(imgs[0], imgs[1])
+
+
+def test_warp_kernel_on_batch_and_stripe_surfaces(fine_kernel_knob, oracle_lib):
+    """the warp-per-tile kernel evaluates gradients in canvas coordinates on a batch surface and in whole-surface coordinates on a
+    stripe (neither test surface is large enough for it to be chosen on its own: it is forced, then compared with the block kernel's
+    pixels and with the oracle)"""
+    names = ["grad_radial", "mixed", "grad_linear", "stroke_alpha"]
+    for mode in (2, 1):
+        fine_kernel_knob(mode)
+        dev = v.Device(4)
+        surf = v.Surface(dev, 128, 128, batch=len(names))
+        ctx = v.Context(surf)
+        for i, name in enumerate(names):
+            ctx.set_canvas(i)
+            ctx.identity_matrix()
+            ctx.translate(0.5 * i, -0.25 * i)
+            mg.pixel_scene(ctx, name, 2)
+        ctx.flush()
+        got = surf.pixels()
+        for i, name in enumerate(names):
+            o = oracle_lib.Oracle(128, 128, 4)
+            o.translate(0.5 * i, -0.25 * i)
+            mg.pixel_scene(o, name, 2)
+            assert np.array_equal(got[128 * i:128 * (i + 1)], o.pixels()), (mode, name)
+            o.close()
+        ctx.close()
+        surf.close()
+        # stripes of a 128 x 192 surface: rows 64..127 and 128..191 rendered on their own
+        o = oracle_lib.Oracle(128, 192, 4)
+        o.translate(0.0, 40.0)   # the 128 x 128 scenes land on rows 40..167: every stripe holds part of them
+        for name in ("grad_linear", "grad_radial", "eo"):
+            mg.pixel_scene(o, name, 1)
+        whole = o.pixels()
+        o.close()
+        for y0, h in ((64, 64), (128, 64), (0, 192)):
+            s = v.Surface(dev, 128, h, full_height=192, origin_y=y0)
+            c = v.Context(s)
+            c.translate(0.0, 40.0)
+            for name in ("grad_linear", "grad_radial", "eo"):
+                mg.pixel_scene(c, name, 1)
+            c.flush()
+            assert np.array_equal(s.pixels(), whole[y0:y0 + h]), (mode, y0)
+            c.close()
+            s.close()
+        dev.close()
