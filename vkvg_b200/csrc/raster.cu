@@ -512,29 +512,36 @@ void vkb_launch_owners(const int32_t *draw_rect, const uint32_t *draw_ptbase, co
     VKB_LAUNCHED();
 }
 
-// ---- backdrop: inclusive prefix sum along every path-tile row; one warp per row, grid-stride over rows ----
+// ---- backdrop: inclusive prefix sum along every path-tile row; eight lanes per row (most draws are a few tiles wide: a whole
+//      warp per row left 29 lanes idle on C2), grid-stride over rows ----
 __global__ void __launch_bounds__(256) backdrop_prefix_k(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase,
                                                         const uint32_t *row_owner, const vkb_counts *C, int32_t *pt_backdrop) {
     if (C->overflow) return;
     const uint32_t n_rows = C->n[VKC_ROWS];
-    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+    const uint32_t sub = threadIdx.x & 7, groups = (gridDim.x * blockDim.x) >> 3;
+    const uint32_t gmask = 0xFFu << (threadIdx.x & 24);  // the eight lanes of this group
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < n_rows; row += groups) {
         const uint32_t d = row_owner[row];
         uint32_t tw   = (uint32_t)draw_rect[4 * d + 2];
         int32_t *p    = pt_backdrop + draw_ptbase[d] + (row - draw_rowbase[d]) * tw;
         int32_t  carry = 0;
-        for (uint32_t c = 0; c < tw; c += 32) {
-            int32_t v = c + lane < tw ? p[c + lane] : 0;
-            int32_t s = warp_incl_scan(v) + carry;
-            if (c + lane < tw) p[c + lane] = s;
-            carry = __shfl_sync(0xffffffffu, s, 31);
+        for (uint32_t c = 0; c < tw; c += 8) {
+            int32_t v = c + sub < tw ? p[c + sub] : 0;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const int32_t u = __shfl_up_sync(gmask, v, o, 8);
+                if (sub >= (uint32_t)o) v += u;
+            }
+            v += carry;
+            if (c + sub < tw) p[c + sub] = v;
+            carry = __shfl_sync(gmask, v, 7, 8);
         }
     }
 }
 void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, const uint32_t *row_owner,
                                 uint32_t cap_rows, const vkb_counts *C, int32_t *pt_backdrop, cudaStream_t s) {
     if (!cap_rows) return;
-    const uint32_t blocks = cap_rows / 8 + 1 < 148 * 16 ? cap_rows / 8 + 1 : 148 * 16;  // one warp per row, grid-stride
+    const uint32_t blocks = cap_rows / 32 + 1 < 148 * 16 ? cap_rows / 32 + 1 : 148 * 16;  // eight lanes per row, grid-stride
     backdrop_prefix_k<<<blocks, 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, row_owner, C, pt_backdrop);
     VKB_LAUNCHED();
 }
