@@ -679,10 +679,10 @@ void vkb_launch_grad_prep(const vkb_gradient *grads, uint32_t n, float W, float 
     grad_prep_k<<<vkb_div_up(n, 128), 128, 0, s>>>(grads, n, W, H, out);
     VKB_LAUNCHED();
 }
-__device__ __noinline__ void eval_gradient(uint32_t pattern, const vkb_gradient *g, const float *gp, float W, float H, float fx, float fy, float c[4]) {
+// px, py: the pixel centre divided by the surface size (gl_FragCoord.xy / size in the shader): fx / W, fy / H
+__device__ __noinline__ void eval_gradient(uint32_t pattern, const vkb_gradient *g, const float *gp, float px, float py, float c[4]) {
     if (pattern == VKB_PAT_LINEAR) {
         const float p0x = gp[0], l = gp[1], ux = gp[2], uy = gp[3];
-        float px = fx / W, py = fy / H;
         float dist;
         if (uy == 0.0f) {
             if (ux < 0.0f) dist = -(px - p0x) / l;
@@ -697,7 +697,6 @@ __device__ __noinline__ void eval_gradient(uint32_t pattern, const vkb_gradient 
         for (uint32_t i = 1; i + 1 < g->count; ++i) mix4(c, g->colors[i + 1], smoothstepf(g->stops[i], g->stops[i + 1], dist));
     } else {
         const float c0x = gp[8], c0y = gp[9], r0 = gp[10], dfx = gp[11], dfy = gp[12], cc = gp[13];
-        float px = fx / W, py = fy / H;
         float gradLength = 1.0f;
         float rx = px - c0x, ry = py - c0y;
         float rl = sqrtf(rx * rx + ry * ry);
@@ -767,10 +766,25 @@ __device__ __noinline__ void eval_surface(const vkb_surfpat *spp, float fx, floa
 __device__ __forceinline__ void eval_paint(uint32_t pattern, const vkb_gradient *g, const float *gp, float W, float H, uint32_t solid, float opacity, float fx,
                                            float fy, float out[4], const float *lut, const vkb_surfpat *surfpats = nullptr, uint32_t slot = 0) {
     float c[4];
-    if (pattern == VKB_PAT_LINEAR || pattern == VKB_PAT_RADIAL) eval_gradient(pattern, g, gp, W, H, fx, fy, c);  // out of line: keeps the solid-colour loop small
+    if (pattern == VKB_PAT_LINEAR || pattern == VKB_PAT_RADIAL) eval_gradient(pattern, g, gp, fx / W, fy / H, c);  // out of line: keeps the solid-colour loop small
     else if (pattern == VKB_PAT_SURFACE) eval_surface(surfpats + slot, fx, fy, c, lut);
     else {
         c[0] = lut[solid & 0xFF];  // lut[i] == (float)i / 255.0f exactly
+        c[1] = lut[(solid >> 8) & 0xFF];
+        c[2] = lut[(solid >> 16) & 0xFF];
+        c[3] = lut[solid >> 24];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = c[k] * opacity;
+}
+// the same with fx / W and fy / H supplied (the warp-per-tile kernel divides once per tile column / row, not per pixel and path)
+__device__ __forceinline__ void eval_paint_q(uint32_t pattern, const vkb_gradient *g, const float *gp, uint32_t solid, float opacity, float fx, float fy, float qx,
+                                             float qy, float out[4], const float *lut, const vkb_surfpat *surfpats, uint32_t slot) {
+    float c[4];
+    if (pattern == VKB_PAT_LINEAR || pattern == VKB_PAT_RADIAL) eval_gradient(pattern, g, gp, qx, qy, c);
+    else if (pattern == VKB_PAT_SURFACE) eval_surface(surfpats + slot, fx, fy, c, lut);
+    else {
+        c[0] = lut[solid & 0xFF];
         c[1] = lut[(solid >> 8) & 0xFF];
         c[2] = lut[(solid >> 16) & 0xFF];
         c[3] = lut[solid >> 24];
@@ -1380,6 +1394,7 @@ template <int S> struct alignas(16) FwShared {
     int32_t  W[16 * S * FW_WSTRIDE];  // per-sample windings of the current path-tile (multi-chunk / COUNT rule only)
     uint16_t rowmask[16 * S];         // per sample row: bit lx = covered by the current path-tile
     uint8_t  queue[256];              // pixels (ly * 16 + lx) with at least one covered sample
+    float    qxy[32];                 // pixel centre / surface size: 16 columns, then 16 rows (what the gradient evaluation starts from)
 };
 
 // sample positions as packed nibbles (sample s = nibble s): no select chain, cheap enough to recompute anywhere
@@ -1471,6 +1486,8 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
         rxo[j] = 16 * (int32_t)((SamplePack<S>::X >> (4 * (r % S))) & 15);
         asm volatile("" : "+r"(ry[j]), "+r"(rxo[j]));  // keep them: the compiler otherwise re-derives both for every path-tile
     }
+    sh.qxy[lane] = lane < 16 ? ((float)(tx * VKB_TILE + lane) + 0.5f) / (float)a.sd.width
+                             : ((float)(ty * VKB_TILE + (lane - 16) + a.sd.origin_y - band_y0) + 0.5f) / (float)a.sd.full_height;
     const uint32_t grp = lane / S, sub = lane % S;  // pixel row group / which of its pixels this lane queues
     const uint32_t share = (S == 4 ? 0x11111111u : (S == 2 ? 0x55555555u : 0xffffffffu)) << sub;
     __syncwarp();
@@ -1611,8 +1628,8 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                 }
                 if (pattern != VKB_PAT_SOLID) {
                     const uint32_t px = tx * VKB_TILE + lx, py = ty * VKB_TILE + ly;
-                    eval_paint(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, (float)a.sd.width, (float)a.sd.full_height, pt.color,
-                               pt.opacity, (float)px + 0.5f, (float)(py + a.sd.origin_y - band_y0) + 0.5f, src, lut, a.surfpats, pt.gradient);
+                    eval_paint_q(pattern, a.grads + pt.gradient, a.gprep + (size_t)pt.gradient * VKB_GPREP_FLOATS, pt.color, pt.opacity, (float)px + 0.5f,
+                                 (float)(py + a.sd.origin_y - band_y0) + 0.5f, sh.qxy[lx], sh.qxy[16 + ly], src, lut, a.surfpats, pt.gradient);
                     ia = 1.0f - src[3];
                     if (op == VKB_OP_SUB) ia = -ia;
                     else if (op == VKB_OP_CLEAR) { src[0] = src[1] = src[2] = src[3] = 0.0f; ia = 0.0f; }
