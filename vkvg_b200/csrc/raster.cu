@@ -1660,6 +1660,13 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                         for (int s = 0; s < S; s++)
                             if (n[s]) cp[16 * s] = r;
                     }
+                } else if (!counted && pattern != VKB_PAT_SOLID) {  // rolled: one copy of the blend in the instruction cache, which the gradient code fills
+                    uint32_t nb = 0;
+#pragma unroll
+                    for (int s = 0; s < S; s++) nb |= (uint32_t)n[s] << s;
+#pragma unroll 1
+                    for (int s = 0; s < S; s++)
+                        if ((nb >> s) & 1u) cp[16 * s] = blend_over(cp[16 * s], src, ia, lut);  // (a sample no lane covers costs one branch)
                 } else {
 #pragma unroll
                     for (int s = 0; s < S; s++) {
