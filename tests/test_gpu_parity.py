@@ -635,6 +635,16 @@ def test_warp_and_block_fine_kernels_agree(fine_kernel_knob, oracle_lib, samples
                 g.line_to(r.uniform(40, 110), r.uniform(30, 100))
             g.close_path()
             g.fill()
+            # more than 32 draws over the same tiles (the warp kernel fetches path-tile headers 32 at a time)
+            for i in range(75):
+                g.set_fill_rule(i % 2)
+                g.set_source_rgba(r.u(), r.u(), r.u(), 0.15 + 0.8 * r.u())
+                x, y = r.uniform(16, 40), r.uniform(70, 100)
+                g.move_to(x, y)
+                g.line_to(x + r.uniform(4, 30), y + r.uniform(-6, 6))
+                g.line_to(x + r.uniform(0, 20), y + r.uniform(5, 25))
+                g.close_path()
+                g.fill()
             # translucent zig-zag stroke overlapping itself
             g.set_source_rgba(0.9, 0.1, 0.4, 0.35)
             g.set_line_width(9.0)
