@@ -1403,7 +1403,9 @@ template <> struct SamplePack<1> { static constexpr unsigned long long X = 0x8ul
 template <> struct SamplePack<2> { static constexpr unsigned long long X = 0x4Cull, Y = 0x4Cull; };
 template <> struct SamplePack<4> { static constexpr unsigned long long X = 0xA2E6ull, Y = 0xEA62ull; };
 
-#define FW_CH 15      // edges per chunk: per-column deltas (and every partial sum along a row) stay within +-15
+#define FW_CH 15      // edges per chunk of a path-tile that fits one: per-column deltas (and every partial sum along a row) stay within +-15
+#define FW_CH_LONG 31 // edges per chunk of a longer list (windings accumulate in shared memory: the biased bytes only have to stay within [1, 63])
+#define FW_CHUNK(n) ((n) > FW_CH ? FW_CH_LONG : FW_CH)
 #define FW_DBIAS 32u  // bias of the packed deltas: bytes in [17, 47], so the byte-wise prefix sums of a word (x * 0x01010101) never carry
 // 4-bit mask of the ZERO bytes of v (bit i = byte i is zero)
 __device__ __forceinline__ uint32_t zero_bytes4(uint32_t v) {
@@ -1501,7 +1503,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
         {
             const uint32_t eo = (uint32_t)__shfl_sync(FULL, hh0.z, 0);
             const int      ne = __shfl_sync(FULL, hh0.w, 0);
-            if ((int)lane < min(ne, FW_CH)) cur = __ldg((const int4 *)(a.tile_edges + eo + lane));
+            if ((int)lane < min(ne, FW_CHUNK(ne))) cur = __ldg((const int4 *)(a.tile_edges + eo + lane));
         }
         for (int q = 0; q < np; q++) {
             const int32_t   bd   = __shfl_sync(FULL, hh0.y, q);
@@ -1528,13 +1530,14 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
             uint32_t   m       = 0;                                   // bit j * 16 + c: sample row row[j], column c is covered
             const bool skip    = rule >= VKB_RULE_CLIP_EO;            // stencil entries never reach this kernel (they bring a stencil plane with them)
 
-            // ---- winding: chunks of <= FW_CH edges ----
-            for (int e0 = 0;; e0 += FW_CH) {
-                const int nn = max(0, min(FW_CH, n_e - e0));
+            // ---- winding: one chunk of <= FW_CH edges, or chunks of FW_CH_LONG ----
+            const int CH = FW_CHUNK(n_e);
+            for (int e0 = 0;; e0 += CH) {
+                const int nn = max(0, min(CH, n_e - e0));
                 int4      nx = make_int4(0, 0, 0, 0);  // prefetch: the next chunk of this path-tile, else the first chunk of the next one
-                if (e0 + FW_CH < n_e) {
-                    if ((int)lane < min(FW_CH, n_e - e0 - FW_CH)) nx = __ldg((const int4 *)(a.tile_edges + eoff + e0 + FW_CH + lane));
-                } else if ((int)lane < min(ne_n, FW_CH)) nx = __ldg((const int4 *)(a.tile_edges + eoff_n + lane));
+                if (e0 + CH < n_e) {
+                    if ((int)lane < min(CH, n_e - e0 - CH)) nx = __ldg((const int4 *)(a.tile_edges + eoff + e0 + CH + lane));
+                } else if ((int)lane < min(ne_n, FW_CHUNK(ne_n))) nx = __ldg((const int4 *)(a.tile_edges + eoff_n + lane));
                 int32_t  base[P];
                 uint32_t d[P][4];
 #pragma unroll
@@ -1573,7 +1576,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                         }
                     }
                 }
-                if (e0 + FW_CH >= n_e) break;
+                if (e0 + CH >= n_e) break;
             }
             if (skip) continue;
             if (use_w) {  // each lane reads back the rows it accumulated itself
