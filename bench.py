@@ -271,6 +271,8 @@ def _ref_worker(args):
 
 
 SAMPLE = {"blit": 1, "c5b": None, "c1": None, "c2": 1500, "c3": 40000, "c4": 200, "c5a": 1000}  # units of work per host thread per step (paths / segments)
+# the single-thread cpu_baseline leg of the default run works on a larger slice: about 10-30 s of CPU work
+CPU_SAMPLE = dict(SAMPLE, c2=40000)
 FULL = {"blit": 8, "c5b": 239 * C5B_CANVASES, "c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000, "c5a": 476000}
 
 
@@ -547,7 +549,7 @@ def cpu_baseline(workload, rule):
     import oracle
     if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
         oracle.build(ref=False)
-    n = SAMPLE[workload]
+    n = CPU_SAMPLE[workload]
     dt, info, kind = _ref_worker(("c1" if workload == "c5b" else workload, 1, rule, n, 0))
     frac = (1.0 / C5B_CANVASES) if workload == "c5b" else (1.0 if n is None else n / FULL[workload])
     name, unit = UNITS[workload]
