@@ -272,7 +272,7 @@ def _ref_worker(args):
 
 SAMPLE = {"blit": 1, "c5b": None, "c1": None, "c2": 1500, "c3": 40000, "c4": 200, "c5a": 1000}  # units of work per host thread per step (paths / segments)
 # the single-thread cpu_baseline leg of the default run works on a larger slice: about 10-30 s of CPU work
-CPU_SAMPLE = dict(SAMPLE, c2=40000)
+CPU_SAMPLE = dict(SAMPLE, c2=None)   # the whole C2 scene: ~10 s on the GPU box's host, ~25 s on a slow core
 FULL = {"blit": 8, "c5b": 239 * C5B_CANVASES, "c1": 239, "c2": 100000, "c3": 1000000, "c4": 50000, "c5a": 476000}
 
 
