@@ -46,7 +46,10 @@ vkvg_public void vkvg_b200_stroke_geometry(VkvgContext ctx, float *xy, uint32_t 
                                            uint32_t cap_indices, uint32_t *n_indices);
 
 /* Device-space edges (24.8 fixed point x0,y0,x1,y1) that filling or stroking the current path would hand to
- * the rasteriser.  kind: 0 = fill, 1 = stroke.  Returns the edge count. */
+ * the rasteriser.  kind: 0 = fill, 1 = stroke.  Returns the edge count.  Fill edges come one per path point, in path order, with
+ * an edge that lies wholly above, below or right of the surface stored as 0,0,0,0 (it cannot change any sample); stroke edges
+ * are only the ones that survive (an edge shared by two consecutive triangles in opposite directions cancels, off-surface
+ * edges are dropped), in no particular order. */
 vkvg_public uint64_t vkvg_b200_path_edges(VkvgContext ctx, int kind, int32_t *edges_xyxy, uint64_t cap_edges);
 
 /* Flush the context; additionally copy the per-sample integer winding computed by the tile rasteriser for the
