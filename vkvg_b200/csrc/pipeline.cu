@@ -582,6 +582,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->gprep.ensure((size_t)(d->n_grads + 1) * 16 * 4, st);
     vkb_launch_grad_prep(fa.grads, draws ? d->n_grads : 0, (float)sd.width, (float)sd.full_height, d->gprep.as<float>(), st);
     fa.gprep = d->gprep.as<float>();
+    fa.tile_counter = (uint32_t *)(totals + 10);  // (zeroed with the other totals when the flush starts)
     fa.surfpats = d->surfpats.as<vkb_surfpat>();
     fa.image = surf->image.as<uint32_t>();
     if (samples) {  // (analytic mode, samples == 0, keeps one colour per pixel: no per-sample plane)

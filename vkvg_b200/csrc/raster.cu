@@ -1450,11 +1450,16 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
     __syncthreads();  // the only block-wide barrier
     if (a.counts->overflow) return;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile = blockIdx.x * FW_TILES + warp;
-    if (tile >= n_tiles) return;
-    const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
-    if (first == end) return;
     FwShared<S>   &sh = sh_all[warp];
+    // Tiles differ a lot in the length of their lists: every warp takes the next tile from a counter when it has finished one, so
+    // that no warp slot of the SM sits idle while the slowest tile of a block is still being walked (the grid is one wave).
+    for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile >= n_tiles) break;
+    const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
+    if (first == end) continue;  // no draw of this batch touches the tile: the stored pixels stay as they are
     const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
     const int32_t  X0 = (int32_t)tx * VKB_TILE_FX, Y0 = (int32_t)ty * VKB_TILE_FX;
     const uint32_t band_y0 = a.sd.band_tiles ? (ty / a.sd.band_tiles) * a.sd.band_tiles * VKB_TILE : 0u;
@@ -1721,6 +1726,8 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
     }
     if (any_mask && lane < 8) a.ms_mask[tile * 8 + lane] = my_mask;
     if (lane == 0) a.tile_ms[tile] = any_mask ? 1 : 0;
+    __syncwarp();  // the next tile's colours overwrite this one's
+    }
 }
 
 // Which kernel serves a batch without clip state: the warp-per-tile kernel needs many more tiles than the GPU has warp slots
@@ -1735,7 +1742,8 @@ static int g_fine_mode = [] {
 void vkb_fine_set_mode(int mode) { g_fine_mode = (mode == 1 || mode == 2) ? mode : 0; }
 int  vkb_fine_get_mode() { return g_fine_mode; }
 template <int S> static void launch_fine_warp(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
-    fine_warp_k<S><<<vkb_div_up(tiles, FW_TILES), 32 * FW_TILES, 0, s>>>(a, tiles);
+    const uint32_t blocks = vkb_div_up(tiles, FW_TILES);
+    fine_warp_k<S><<<blocks < 148u * 6u ? blocks : 148u * 6u, 32 * FW_TILES, 0, s>>>(a, tiles);  // one wave: 6 blocks of 4 warps per SM
 }
 template <int S> static void launch_fine_s(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
     const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
