@@ -1375,10 +1375,11 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
 // fine pass, one WARP per tile (the variant launched for batches without clip state; fine_k above keeps the stencil and
 // winding-capture variants).
 //
-// With a mean of 3-5 edges and ~170 covered samples per path-tile (C2, C4, tiger) a block of 8 warps per tile spends its time
-// on barriers and on every warp walking every task.  Here a tile belongs to one warp, which needs no barrier at all:
+// With a mean of 3-5 edges and ~80 covered pixels per path-tile (C2, C4, tiger) a block of 8 warps per tile spends its time
+// on barriers and on every warp walking every task.  Here a tile belongs to one warp, which needs no barrier at all (and warps are
+// persistent: each takes its next tile from a counter, so no warp slot waits for the slowest tile of a block):
 //   * the tile's 256*S sample colours live in shared memory ([sample row][column]) for the whole list of path-tiles;
-//   * winding: lanes are sample rows (row_edge above, unchanged: same exact predicates), one chunk of <= FINE_CH edges at a
+//   * winding: lanes are sample rows (row_edge above, unchanged: same exact predicates), one chunk of <= FW_CH (else FW_CH_LONG) edges at a
 //     time, edges fetched one per lane and handed round with shuffles; a path-tile that fits one chunk never leaves the
 //     registers, longer ones (and COUNT-rule draws with a translucent source, which blend |winding| times) accumulate
 //     per-sample int32 windings in shared memory;
@@ -1387,7 +1388,7 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
 //     reference's per-sample arithmetic (blend_over).  Lanes are pixels that need work, not pixels that might.
 // Same results as fine_k bit for bit (tests/test_gpu_parity.py runs both on the same scenes).
 // ----------------------------------------------------------------------------------------------------
-#define FW_TILES 4      // tiles (= warps) per block; they only share the u8 -> float table
+#define FW_TILES 4      // warps per block, each working on a tile of its own; they only share the u8 -> float table
 #define FW_WSTRIDE 17   // words per sample row of the winding plane (odd: lanes = rows hit distinct banks)
 template <int S> struct alignas(16) FwShared {
     uint32_t col[16 * S * 16];        // sample colours, [sample row = ly * S + s][lx]
