@@ -645,6 +645,18 @@ def test_warp_and_block_fine_kernels_agree(fine_kernel_knob, oracle_lib, samples
                 g.line_to(x + r.uniform(0, 20), y + r.uniform(5, 25))
                 g.close_path()
                 g.fill()
+            # backdrops beyond what the four / eight bit-sliced winding planes of the warp kernel hold (|winding| 20 and 300)
+            for depth, (x0, y0) in ((20, (20.0, 20.0)), (300, (84.0, 70.0))):
+                g.set_fill_rule(1)
+                g.set_source_rgba(0.3, 0.2, 0.9, 0.5)
+                for i in range(depth):
+                    d = 0.09 * i
+                    g.move_to(x0 - d, y0 - d)
+                    g.line_to(x0 + 40.0 + d, y0 - d)
+                    g.line_to(x0 + 40.0 + d, y0 + 33.0 + d)
+                    g.line_to(x0 - d, y0 + 33.0 + d)
+                    g.close_path()
+                g.fill()
             # translucent zig-zag stroke overlapping itself
             g.set_source_rgba(0.9, 0.1, 0.4, 0.35)
             g.set_line_width(9.0)

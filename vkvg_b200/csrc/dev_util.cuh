@@ -17,7 +17,7 @@
         }                                                                                                    \
     } while (0)
 
-void vkb_note_cuda_error(cudaError_t e);  // pipeline.cu: makes the owning device sticky-failed
+void vkb_note_cuda_error(cudaError_t e);  // pipeline.cu: makes the device whose entry point is running on this thread sticky-failed
 extern unsigned long long g_vkb_launches; // number of kernels launched by this library (bench: gpu_launches)
 #define VKB_LAUNCHED() (++g_vkb_launches)
 
@@ -35,7 +35,12 @@ struct DevBuf {
         size_t ncap = cap ? cap : 4096;
         while (ncap < bytes) ncap *= 2;
         void *np = nullptr;
-        VKB_CUDA_OK(cudaMalloc(&np, ncap));
+        if (cudaMalloc(&np, ncap) != cudaSuccess) {  // out of memory: keep what there is (the device turns sticky-failed and launches nothing more)
+            cudaGetLastError();
+            fprintf(stderr, "vkvg_b200: cudaMalloc of %zu bytes failed\n", ncap);
+            vkb_note_cuda_error(cudaErrorMemoryAllocation);
+            return;
+        }
         if (p) {
             if (keep) VKB_CUDA_OK(cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, s));
             VKB_CUDA_OK(cudaStreamSynchronize(s));

@@ -11,8 +11,16 @@
 
 unsigned long long g_vkb_launches = 0;
 unsigned long long g_vkb_alloc_generation = 0;
-static int         g_cuda_failed  = 0;
-void               vkb_note_cuda_error(cudaError_t) { g_cuda_failed = 1; }
+// A CUDA error is charged to the device whose entry point is running on this thread (an out-of-memory on one device, or one
+// oversized surface, must not put every other device of the process into VKVG_STATUS_DEVICE_ERROR); errors outside any entry
+// point land in a process-wide flag that only vkb_device_open looks at.
+struct vkb_device_impl;
+static thread_local vkb_device_impl *t_dev = nullptr;
+static int                           g_failed_nodev = 0;
+static int  dev_failed(const vkb_device_impl *d);
+static void dev_set_failed(vkb_device_impl *d);
+void        vkb_note_cuda_error(cudaError_t) { if (t_dev) dev_set_failed(t_dev); else g_failed_nodev = 1; }
+#define g_cuda_failed (t_dev ? dev_failed(t_dev) : g_failed_nodev)
 
 struct SurfFlags { bool known_clear, stencil_live; uint32_t stencil_samples; };  // surface state a flush attempt changes
 struct vkb_device_impl;
@@ -20,6 +28,7 @@ static int finish_pending(vkb_device_impl *d);
 
 struct vkb_device_impl {
     int          ordinal = 0;
+    int          failed  = 0;  // sticky: a CUDA call made on behalf of this device failed
     cudaStream_t stream  = nullptr;
     cudaEvent_t  ev_begin = nullptr, ev_end = nullptr, ev_fine0 = nullptr, ev_fine1 = nullptr;
     cudaEvent_t  ev_stage[VKB_N_STAGES + 1] = {};  // boundaries between pipeline stages (profiling)
@@ -43,7 +52,7 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped;
+    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped, wscratch;
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
     ScanScratch scan;
@@ -68,6 +77,9 @@ struct vkb_device_impl {
     SurfFlags         graph_after = {};       // surface flags a flush of the cached graph leaves behind
     bool              graph_fine_events = false;  // the cached graph records ev_fine0 / ev_fine1 as external event nodes
 };
+static int  dev_failed(const vkb_device_impl *d) { return d->failed; }
+static void dev_set_failed(vkb_device_impl *d) { d->failed = 1; }
+static inline void dev_enter(vkb_device_impl *d) { t_dev = d; cudaSetDevice(d->ordinal); }
 #define VKB_EVENT_RECORD(d, ev) do { if (!(d)->capturing) VKB_CUDA_OK(cudaEventRecord((ev), (d)->stream)); } while (0)
 struct vkb_surface_impl {
     vkb_device_impl *dev;
@@ -90,6 +102,7 @@ vkb_device_impl *vkb_device_open(int ordinal) {
     if (cudaSetDevice(ordinal) != cudaSuccess) return nullptr;
     vkb_device_impl *d = new vkb_device_impl();
     d->ordinal         = ordinal;
+    t_dev              = d;
     VKB_CUDA_OK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     VKB_CUDA_OK(cudaEventCreate(&d->ev_begin));
     VKB_CUDA_OK(cudaEventCreate(&d->ev_end));
@@ -99,15 +112,15 @@ vkb_device_impl *vkb_device_open(int ordinal) {
     for (cudaEvent_t &e : d->ev_stage) VKB_CUDA_OK(cudaEventCreate(&e));
     VKB_CUDA_OK(cudaHostAlloc((void **)&d->counts_host, sizeof(vkb_counts), cudaHostAllocDefault));
     if (d->counts_host) memset(d->counts_host, 0, sizeof(vkb_counts));
-    if (g_cuda_failed) { delete d; return nullptr; }
+    if (d->failed) { t_dev = nullptr; delete d; return nullptr; }
     return d;
 }
 void vkb_device_close(vkb_device_impl *d) {
     if (!d) return;
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -123,17 +136,18 @@ void vkb_device_close(vkb_device_impl *d) {
     cudaEventDestroy(d->ev_h2d);
     cudaEventDestroy(d->ev_begin); cudaEventDestroy(d->ev_end); cudaEventDestroy(d->ev_fine0); cudaEventDestroy(d->ev_fine1);
     cudaStreamDestroy(d->stream);
+    if (t_dev == d) t_dev = nullptr;
     delete d;
 }
-int  vkb_device_failed(vkb_device_impl *) { return g_cuda_failed; }
+int  vkb_device_failed(vkb_device_impl *d) { return d->failed; }
 void vkb_device_sync(vkb_device_impl *d) {
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     finish_pending(d);
     VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
 }
 
 vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, uint32_t full_h, uint32_t origin_y) {
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     vkb_surface_impl *s = new vkb_surface_impl();
     s->dev = d; s->w = w; s->h = h;
     s->full_h = full_h ? full_h : h; s->origin_y = origin_y;
@@ -144,7 +158,7 @@ vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, ui
 }
 void vkb_surface_free(vkb_surface_impl *s) {
     if (!s) return;
-    cudaSetDevice(s->dev->ordinal);
+    dev_enter(s->dev);
     finish_pending(s->dev);
     cudaStreamSynchronize(s->dev->stream);
     s->image.release();
@@ -156,7 +170,7 @@ void vkb_surface_free(vkb_surface_impl *s) {
     delete s;
 }
 void vkb_surface_clear(vkb_surface_impl *s) {
-    cudaSetDevice(s->dev->ordinal);
+    dev_enter(s->dev);
     finish_pending(s->dev);
     if (!s->known_clear) VKB_CUDA_OK(cudaMemsetAsync(s->image.p, 0, (size_t)s->w * s->h * 4, s->dev->stream));
     s->known_clear = true;
@@ -174,7 +188,7 @@ static size_t stencil_bytes(const vkb_surface_impl *s, uint32_t samples) {
 // the reference parks the whole stencil image in a spare one every six nested clip saves and copies it back on the matching
 // restore (src/vkvg_context.c:1268-1318, :1425-1470); same here with the stencil plane.  Both run after a flush.
 int vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples) {
-    cudaSetDevice(s->dev->ordinal);
+    dev_enter(s->dev);
     finish_pending(s->dev);
     const size_t bytes = stencil_bytes(s, samples);
     s->stencil_spills.emplace_back();
@@ -185,7 +199,7 @@ int vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples) {
     return g_cuda_failed;
 }
 int vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples) {
-    cudaSetDevice(s->dev->ordinal);
+    dev_enter(s->dev);
     finish_pending(s->dev);
     if (s->stencil_spills.empty()) return 1;
     const size_t bytes = stencil_bytes(s, samples);
@@ -200,7 +214,7 @@ int vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples) {
 const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s) { return s->image.as<uint32_t>(); }
 // replace the contents of the surface by width*height premultiplied RGBA8 pixels from the host (vkvg_surface_create_from_bitmap)
 int vkb_surface_upload(vkb_surface_impl *s, const uint8_t *rgba) {
-    cudaSetDevice(s->dev->ordinal);
+    dev_enter(s->dev);
     finish_pending(s->dev);
     VKB_CUDA_OK(cudaMemcpyAsync(s->image.p, rgba, (size_t)s->w * s->h * 4, cudaMemcpyHostToDevice, s->dev->stream));
     VKB_CUDA_OK(cudaStreamSynchronize(s->dev->stream));
@@ -210,7 +224,7 @@ int vkb_surface_upload(vkb_surface_impl *s, const uint8_t *rgba) {
 }
 // device-to-device copy of the premultiplied pixels (e.g. into a tensor handed to an NCCL gather); synchronous
 int vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst) {
-    cudaSetDevice(s->dev->ordinal);
+    dev_enter(s->dev);
     finish_pending(s->dev);
     VKB_CUDA_OK(cudaMemcpyAsync(dst, s->image.p, (size_t)s->w * s->h * 4, cudaMemcpyDeviceToDevice, s->dev->stream));
     VKB_CUDA_OK(cudaStreamSynchronize(s->dev->stream));
@@ -218,7 +232,7 @@ int vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst) {
 }
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) {
     vkb_device_impl *d = s->dev;
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     if (finish_pending(d)) return 1;
     size_t          bytes = (size_t)s->w * s->h * 4;
     const uint32_t *src   = s->image.as<uint32_t>();
@@ -293,7 +307,7 @@ __global__ void list_draws_k(const vkb_draw *draws, const uint32_t *sbase, const
 
 int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     const auto t_begin = std::chrono::steady_clock::now();
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     cudaStream_t st = d->stream;
     finish_pending(d);
     // the previous flush may still be reading the staging area
@@ -507,6 +521,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->draw_counts.ensure((size_t)(nd + 1) * 8, st);
     d->draw_ptbase.ensure((size_t)(nd + 1) * 4, st);
     d->draw_rowbase.ensure((size_t)(nd + 1) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     vkb_launch_draw_bbox(edges, edraw, cv[VKC_EDGES], C, nd, d->draw_bbox.as<int32_t>(), st);
     unsigned long long *dc = d->draw_counts.as<unsigned long long>();
     const bool clip_draws = draws && d->has_clip_draws, stencil_ops = draws && d->has_stencil_ops;
@@ -524,11 +539,13 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->pt_slot.ensure((size_t)(cap_pt + 1) * 4, st);
     d->pt_owner.ensure((size_t)(cap_pt + 1) * 4, st);
     d->row_owner.ensure((size_t)(cv[VKC_ROWS] + 1) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     vkb_launch_owners(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd, C, d->pt_owner.as<uint32_t>(),
                       d->row_owner.as<uint32_t>(), st);
     VKB_CUDA_OK(cudaMemsetAsync(d->pt_count.p, 0, (size_t)cap_pt * 4, st));
     VKB_CUDA_OK(cudaMemsetAsync(d->pt_backdrop.p, 0, (size_t)cap_pt * 4, st));
     d->long_edges.ensure(((size_t)cv[VKC_EDGES] + 1) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     uint32_t *long_n = (uint32_t *)(totals + 8);  // (zeroed with the other totals when the flush starts)
     vkb_launch_bin_count(edges, edraw, cv[VKC_EDGES], C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_count.as<uint32_t>(),
                          d->pt_backdrop.as<int32_t>(), d->long_edges.as<uint32_t>(), long_n, st);
@@ -538,6 +555,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
                         d->pt_flags.as<uint32_t>(), st);
     // pt_slot doubles as the exclusive scan of the flags until the sorted slots overwrite it
     d->sorted_cnt.ensure((size_t)(cap_pt + 1) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     uint32_t *flag_scan = d->sorted_cnt.as<uint32_t>();
     vkb_exclusive_scan<uint32_t, uint32_t>(d->pt_flags.as<uint32_t>(), flag_scan, 0, (uint32_t *)(totals + 5), d->scan, st, C, VKC_PT, cap_pt, VKC_NE);
 
@@ -548,6 +566,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->hdr.ensure((size_t)(cap_ne + 1) * 32, st);
     d->tile_first.ensure((size_t)n_tiles * 4 + 16, st);
     d->tile_end.ensure((size_t)n_tiles * 4 + 16, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     vkb_launch_pt_compact(d->pt_flags.as<uint32_t>(), flag_scan, cap_pt, C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_owner.as<uint32_t>(), sd,
                           d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), d->pt_draw.as<uint32_t>(), st);
     int bits = 1;
@@ -557,6 +576,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     uint32_t *eoff = d->cursor.as<uint32_t>();  // scan output; cursor proper is a separate zeroed array below
     DevBuf   &cur2 = d->cursor2;
     cur2.ensure((size_t)(cap_ne + 1) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     {
         // sorted_cnt currently holds flag_scan which headers_k still needs: put the sorted counts in pt_flags instead
         uint32_t *scnt = d->pt_flags.as<uint32_t>();
@@ -564,6 +584,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
         vkb_exclusive_scan<uint32_t, uint32_t>(scnt, eoff, 0, (uint32_t *)(totals + 6), d->scan, st, C, VKC_NE, cap_ne, VKC_TE);
     }
     d->tile_edges.ensure((size_t)(cv[VKC_TE] + 1) * 16, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     VKB_CUDA_OK(cudaMemsetAsync(d->tile_first.p, 0, (size_t)n_tiles * 4, st));
     VKB_CUDA_OK(cudaMemsetAsync(d->tile_end.p, 0, (size_t)n_tiles * 4, st));
     vkb_launch_headers(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), cap_ne, C, d->pt_draw.as<uint32_t>(), flag_scan, d->pt_backdrop.as<int32_t>(),
@@ -580,9 +601,13 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     fa.hdr = d->hdr.as<int4>(); fa.tile_edges = d->tile_edges.as<vkb_edge>();
     fa.paints = d->paints.as<vkb_paint>(); fa.grads = d->grads.as<vkb_gradient>();
     d->gprep.ensure((size_t)(d->n_grads + 1) * 16 * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     vkb_launch_grad_prep(fa.grads, draws ? d->n_grads : 0, (float)sd.width, (float)sd.full_height, d->gprep.as<float>(), st);
     fa.gprep = d->gprep.as<float>();
     fa.tile_counter = (uint32_t *)(totals + 10);  // (zeroed with the other totals when the flush starts)
+    d->wscratch.ensure(vkb_fine_wscratch_words(samples) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
+    fa.wscratch = d->wscratch.as<int32_t>();
     fa.surfpats = d->surfpats.as<vkb_surfpat>();
     fa.image = surf->image.as<uint32_t>();
     if (samples) {  // (analytic mode, samples == 0, keeps one colour per pixel: no per-sample plane)
@@ -590,6 +615,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
         surf->ms_image.ensure((size_t)n_tiles * 256 * samples * 4, st);
         surf->tile_ms.ensure((size_t)n_tiles + 16, st);
         surf->ms_mask.ensure((size_t)n_tiles * 32 + 16, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         if (fresh || surf->known_clear) VKB_CUDA_OK(cudaMemsetAsync(surf->tile_ms.p, 0, n_tiles, st));
     }
     fa.ms_image = surf->ms_image.as<uint32_t>(); fa.tile_ms = surf->tile_ms.as<uint8_t>(); fa.ms_mask = surf->ms_mask.as<uint32_t>();
@@ -599,6 +625,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     if (stencil_ops || surf->stencil_live) {
         if (surf->stencil_samples != samples) { surf->stencil_live = false; surf->stencil_samples = samples; }  // coverage mode changed: layout differs
         surf->stencil.ensure(stencil_bytes(surf, samples), st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         fa.stencil    = surf->stencil.as<uint32_t>();
         fa.stencil_in = surf->stencil_live ? 1 : 0;
         if (stencil_ops && d->stencil_after) surf->stencil_live = d->stencil_after == 1;
@@ -607,6 +634,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     if (cap && cap->winding) {
         size_t wb = (size_t)sd.width * sd.height * (samples ? samples : 1) * 4;  // analytic mode: one float area per pixel
         wbuf.ensure(wb, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         VKB_CUDA_OK(cudaMemsetAsync(wbuf.p, 0, wb, st));
         fa.winding_out = wbuf.as<int32_t>(); fa.winding_draw = cap->winding_draw;
     }
@@ -644,6 +672,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     vkb_counts *C = d->counts.as<vkb_counts>();
     VKB_EVENT_RECORD(d, d->ev_stage[0]);
     d->totals.ensure(16 * 8, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     uint64_t *totals = d->totals.as<uint64_t>();
     VKB_CUDA_OK(cudaMemsetAsync(totals, 0, 16 * 8, st));
 
@@ -655,10 +684,12 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     d->ptflags.ensure((size_t)cv[VKC_POINTS] + 16, st);
     d->fjob_base.ensure((size_t)(d->n_fjobs + 1) * 4, st);
     d->sjob_base.ensure((size_t)(d->n_sjobs + 1) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     // curve-heavy batches keep the first 16 points of every element from the counting pass (16 * 8 B per element)
     float2 *fcache = nullptr;
     if (d->n_curves && (uint64_t)d->n_curves * 8 >= d->n_elems) {
         d->flat_cache.ensure((size_t)d->n_elems * 16 * 8, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         fcache = d->flat_cache.as<float2>();
     }
     if (d->n_elems) {
@@ -692,12 +723,14 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         if (d->any_dash) {
             d->seglen.ensure((size_t)(cap_items + 1) * 4, st);
             d->cum.ensure((size_t)(cap_items + 1) * 8, st);
+            if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
             vkb_launch_stroke_seglen(sa, d->seglen.as<float>(), st);
             vkb_exclusive_scan<float, double>(d->seglen.as<float>(), d->cum.as<double>(), 1, nullptr, d->scan, st, C, VKC_SITEMS, (uint64_t)cap_items + 1);
             sa.cum = d->cum.as<double>();
         }
         d->item_counts.ensure((size_t)(cap_items + 1) * 8, st);
         d->job_inverse.ensure((size_t)(d->n_sjobs + 1) * 4, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         VKB_CUDA_OK(cudaMemsetAsync(d->job_inverse.p, 0, (size_t)d->n_sjobs * 4, st));
         unsigned long long *ic = d->item_counts.as<unsigned long long>();
         vkb_launch_stroke_count(sa, ic, st);
@@ -706,6 +739,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         VKB_LAUNCHED();
         d->verts.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
         d->inds.ensure((size_t)(cv[VKC_INDS] + 3) * 4, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         vkb_launch_stroke_emit(sa, ic, d->verts.as<float2>(), d->inds.as<uint32_t>(), d->job_inverse.as<uint32_t>(), st);
     } else {
         commit_stroke_k<<<1, 1, 0, st>>>(C, totals, 0u, d->n_extra);
@@ -716,6 +750,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     VKB_EVENT_RECORD(d, d->ev_stage[2]);
     d->edges.ensure(((size_t)cv[VKC_EDGES] + 1) * 16, st);
     d->edge_draw.ensure(((size_t)cv[VKC_EDGES] + 1) * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     vkb_edge *edges = d->edges.as<vkb_edge>();
     uint32_t *edraw = d->edge_draw.as<uint32_t>();
     vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
@@ -723,10 +758,12 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     if (cap_items && d->n_sdraws) {
         // first work item of every stroke draw (to map a triangle back to its draw)
         d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         gather_first_items_k<<<vkb_div_up(d->n_sdraws, 256), 256, 0, st>>>(d->sdraw_first_job.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
                                                                           d->sdraw_first_item.as<uint32_t>());
         VKB_LAUNCHED();
         d->snapped.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         vkb_launch_tri_edges(d->verts.as<float2>(), cv[VKC_VERTS], d->snapped.as<int2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
                              d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, d->n_extra, (uint32_t *)(totals + 9), C, st);
     }
@@ -898,7 +935,7 @@ static int finish_pending(vkb_device_impl *d) {
 }
 
 int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats) {
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     finish_pending(d);
     return run_flush(d, surf, samples, cap, stats, false);
 }
@@ -916,7 +953,7 @@ int vkb_device_ordinal(vkb_device_impl *d) { return d->ordinal; }
 
 // raw directed edges as a single non-zero draw; returns the per-sample winding the fine pass computed
 int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h, uint64_t n, uint32_t w, uint32_t h, int32_t *out) {
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     cudaStream_t st = d->stream;
     finish_pending(d);
     VKB_CUDA_OK(cudaStreamSynchronize(st));
@@ -968,7 +1005,7 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
 // bench support: `steps` resident replays, each timed on its own with CUDA events on the pipeline stream; between
 // steps (outside the timed events) a 256 MiB scratch buffer is overwritten so that no step starts with its inputs in L2.
 int vkb_time_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, uint32_t steps, bool clear_first, bool flush_l2, vkb_stats *sum) {
-    cudaSetDevice(d->ordinal);
+    dev_enter(d);
     finish_pending(d);
     vkb_stats acc;
     memset(&acc, 0, sizeof acc);

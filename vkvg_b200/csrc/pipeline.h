@@ -107,6 +107,7 @@ struct FineArgs {
     uint8_t            *tile_ms;     // per tile: 1 when the samples of some pixel differ (the resolved image alone would lose them)
     uint32_t           *ms_mask;     // per tile: 8 words (one per warp = two pixel rows), bit = that pixel's samples are in ms_image
     uint32_t           *tile_counter; // zeroed before the launch: the warp-per-tile kernel hands out tiles from it
+    int32_t            *wscratch;    // vkb_fine_wscratch_words() int32: one per-sample winding plane per resident warp of fine_warp_k (COUNT rule / huge lists only)
     int                 dst_is_clear;  // destination known to be transparent black: do not read it
     uint32_t           *stencil;     // per-sample stencil bytes (clip bit + save bits), tile-major [tile][256][ceil(S/4)] words; null: no clip in play
     int                 stencil_in;  // the plane holds state from earlier flushes (else it is taken as all zero)
@@ -115,6 +116,7 @@ struct FineArgs {
 };
 void vkb_launch_grad_prep(const vkb_gradient *grads, uint32_t n, float W, float H, float *out, cudaStream_t s);
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s);
+size_t vkb_fine_wscratch_words(uint32_t samples);
 // fine kernel for batches without clip state or winding capture: 0 = chosen by tile count, 1 = block-per-tile fine_k, 2 = warp-per-tile
 // fine_warp_k.  Process-wide; VKVG_B200_FINE=block|warp sets it at start-up
 void vkb_fine_set_mode(int mode);

@@ -919,6 +919,104 @@ __device__ __forceinline__ void row_edge(int32_t ax, int32_t ay, int32_t bx, int
     }
 }
 
+// The same edge against the same rows, but as MASKS for the bit-sliced winding counters of fine_warp_k (bit 16 * j + c = sample row j of
+// this lane, column c):
+//   hm   columns at or right of the crossing of each row the edge spans, when that crossing lies right of L (a crossing at or left of L is
+//        already counted by the backdrop and the V term: its two H contributions cancel) - winding += sign(dy) there;
+//   vm   rows whose V term differs from the one of C - winding += (vneg ? -1 : +1) in all their columns.
+// Same exact predicates as row_edge above (which stays for the COUNT-rule / very long lists).
+template <int P, class T>
+__device__ __forceinline__ void row_edge_masks(int32_t ax, int32_t ay, int32_t bx, int32_t by, bool crossL, const int32_t (&ry)[P], const int32_t (&rxo)[P],
+                                               uint32_t &hm, uint32_t &vm, bool &vneg) {
+    const int32_t dx = bx - ax, dy = by - ay;
+    const T       K  = (T)dy * ax - (T)dx * ay;
+    hm = 0; vm = 0; vneg = false;
+    if (dy != 0) {
+        const int32_t h = dy > 0 ? (dy >> 1) : ((dy + 1) >> 1);
+        const T       D = (T)256 * (dy > 0 ? dy : -dy);
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            const int32_t y = ry[j];
+            if ((ay <= y) != (by <= y)) {
+                const T m = (T)dx * y + K;
+                if (!(dy > 0 ? (m <= (T)h) : (m >= (T)h))) {
+                    T qq = m - (T)dy * rxo[j];
+                    if (dy < 0) qq = -qq;
+                    uint32_t cm = 0xFFFFu;  // crossing between L and the first sample: every column
+                    if (qq > 0) {
+                        int c = 0;
+                        T   Dc = 0;
+                        if (D * 8 < qq) { c = 8; Dc = D * 8; }
+                        if (Dc + D * 4 < qq) { c += 4; Dc += D * 4; }
+                        if (Dc + D * 2 < qq) { c += 2; Dc += D * 2; }
+                        if (Dc + D < qq) { c += 1; }
+                        cm = (0xFFFEu << c) & 0xFFFFu;  // c = last column still left of the crossing
+                    }
+                    hm |= cm << (16 * j);
+                }
+            }
+        }
+    }
+    if (crossL) {
+        const bool    tie = dy == 0 || ((dx > 0) != (dy > 0));
+        const int32_t rc  = dy - dx;
+        if (dx > 0) {
+            const bool belowC = twice_gt<T>(K, rc) || (!twice_lt<T>(K, rc) && tie);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const T    m    = (T)dx * ry[j] + K;
+                const bool cond = twice_gt<T>(m, dy) || (!twice_lt<T>(m, dy) && tie);
+                if (cond != belowC) vm |= 0xFFFFu << (16 * j);
+            }
+            vneg = !belowC;
+        } else {
+            const bool belowC = twice_lt<T>(K, rc) || (!twice_gt<T>(K, rc) && tie);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const T    m    = (T)dx * ry[j] + K;
+                const bool cond = twice_lt<T>(m, dy) || (!twice_gt<T>(m, dy) && tie);
+                if (cond != belowC) vm |= 0xFFFFu << (16 * j);
+            }
+            vneg = belowC;
+        }
+    }
+}
+// edges far from the tile (64-bit products): rare, kept out of line so that the hot loop stays small
+template <int P>
+__device__ __noinline__ void row_edge_masks_far(int32_t ax, int32_t ay, int32_t bx, int32_t by, bool crossL, const int32_t (&ry)[P], const int32_t (&rxo)[P],
+                                                uint32_t &hm, uint32_t &vm, bool &vneg) {
+    row_edge_masks<P, long long>(ax, ay, bx, by, crossL, ry, rxo, hm, vm, vneg);
+}
+// Bit-sliced winding counters: plane p holds bit p of the (two's complement) winding of the 16 columns of this lane's sample rows.  Adding
+// +-1 to the columns of `mask` is a ripple carry over the planes: two LOP3 per plane for all 16 * P samples at once, against one byte-wise
+// add per sample row for the packed deltas (and the coverage of the path-tile is an OR of the planes instead of a prefix sum per row).
+// mode 0: parity only (even-odd); 1: four planes (|winding| <= 15); 2: eight planes (|winding| <= 255).  neg and mode are warp-uniform.
+__device__ __forceinline__ void plane_add(uint32_t (&pl)[8], uint32_t mask, bool neg, int mode) {
+    if (mode == 0) { pl[0] ^= mask; return; }
+    const uint32_t s = neg ? 0xffffffffu : 0u;
+    uint32_t       c = mask;
+#pragma unroll
+    for (int p = 0; p < 4; p++) { const uint32_t t = (pl[p] ^ s) & c; pl[p] ^= c; c = t; }
+    if (mode == 2) {
+#pragma unroll
+        for (int p = 4; p < 8; p++) { const uint32_t t = (pl[p] ^ s) & c; pl[p] ^= c; c = t; }
+    }
+}
+
+// Premultiplied OVER on packed bytes for a source whose channels are exact multiples of 1/255 (a solid colour at opacity 1) with every
+// colour channel <= alpha: r = S + round(D * (255 - A) / 255) per channel, two channels per 32-bit multiply, the division by 255 as
+// (v + (v >> 8)) >> 8 with v = D * IA + 128.  Identical to blend_over for all 2^24 (S, A, D) with S <= A: the fp32 chain there errs by
+// < 1e-4 while D * IA / 255 + 1/2 is never closer than 1/510 to an integer (tests/test_blend_int.py enumerates every case).
+__device__ __forceinline__ uint32_t blend_int(uint32_t dst, uint32_t s_lo, uint32_t s_hi, uint32_t IA) {
+    uint32_t x = __byte_perm(dst, 0, 0x4240) * IA + 0x00800080u;  // R, B
+    uint32_t y = __byte_perm(dst, 0, 0x4341) * IA + 0x00800080u;  // G, A
+    x += __byte_perm(x, 0, 0x4341);
+    y += __byte_perm(y, 0, 0x4341);
+    x = __byte_perm(x, 0, 0x4341) + s_lo;
+    y = __byte_perm(y, 0, 0x4341) + s_hi;
+    return __byte_perm(x, y, 0x6240);
+}
+
 // Warp 0 turns the next path-tiles of the tile (headers prefetched in nh0 / nh1, one per lane) into at most FINE_SLOTS
 // tasks, advances the cursor (s_p = path-tile, s_k = edges of it already consumed) and publishes the task count.
 __device__ __forceinline__ void fine_build_group(uint32_t lane, uint32_t end, uint32_t &s_p, uint32_t &s_k, uint32_t &s_nslots, FineTask *tasks,
@@ -1389,10 +1487,11 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
 // Same results as fine_k bit for bit (tests/test_gpu_parity.py runs both on the same scenes).
 // ----------------------------------------------------------------------------------------------------
 #define FW_TILES 4      // warps per block, each working on a tile of its own; they only share the u8 -> float table
+#define FW_BLOCKS_PER_SM 8
 #define FW_WSTRIDE 17   // words per sample row of the winding plane (odd: lanes = rows hit distinct banks)
+#define FW_WPLANE(S) (16 * (S) * FW_WSTRIDE)  // int32 words of one warp's winding plane (global scratch, see FineArgs::wscratch)
 template <int S> struct alignas(16) FwShared {
     uint32_t col[16 * S * 16];        // sample colours, [sample row = ly * S + s][lx]
-    int32_t  W[16 * S * FW_WSTRIDE];  // per-sample windings of the current path-tile (multi-chunk / COUNT rule only)
     uint16_t rowmask[16 * S];         // per sample row: bit lx = covered by the current path-tile
     uint8_t  queue[256];              // pixels (ly * 16 + lx) with at least one covered sample
     float    qxy[32];                 // pixel centre / surface size: 16 columns, then 16 rows (what the gradient evaluation starts from)
@@ -1404,44 +1503,8 @@ template <> struct SamplePack<1> { static constexpr unsigned long long X = 0x8ul
 template <> struct SamplePack<2> { static constexpr unsigned long long X = 0x4Cull, Y = 0x4Cull; };
 template <> struct SamplePack<4> { static constexpr unsigned long long X = 0xA2E6ull, Y = 0xEA62ull; };
 
-#define FW_CH 15      // edges per chunk of a path-tile that fits one: per-column deltas (and every partial sum along a row) stay within +-15
-#define FW_CH_LONG 31 // edges per chunk of a longer list (windings accumulate in shared memory: the biased bytes only have to stay within [1, 63])
-#define FW_CHUNK(n) ((n) > FW_CH ? FW_CH_LONG : FW_CH)
-#define FW_DBIAS 32u  // bias of the packed deltas: bytes in [17, 47], so the byte-wise prefix sums of a word (x * 0x01010101) never carry
-// 4-bit mask of the ZERO bytes of v (bit i = byte i is zero)
-__device__ __forceinline__ uint32_t zero_bytes4(uint32_t v) {
-    const uint32_t t = ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu);  // 0x80 in every zero byte
-    return ((t >> 7) * 0x10204080u) >> 28;
-}
-// coverage bits of one sample row from its packed biased per-column deltas: bit c = ((off + sum_{k<=c} delta_k) & par) != 0,
-// par = 1 (even-odd) or -1 (non-zero).  |sum of deltas| <= FW_CH.
-__device__ __forceinline__ uint32_t row_cover_bits(const uint32_t (&d)[4], int32_t off, int par) {
-    uint32_t bits = 0;
-    if (par == 1) {
-        uint32_t odd = (uint32_t)off & 1u;  // bias 32 per column is even: parity of the biased prefix = parity of the true prefix
-#pragma unroll
-        for (int w4 = 0; w4 < 4; w4++) {
-            const uint32_t pre = d[w4] * 0x01010101u;
-            const uint32_t lo  = (pre ^ (odd * 0x01010101u)) & 0x01010101u;
-            bits |= ((lo * 0x10204080u) >> 28) << (4 * w4);
-            odd ^= (pre >> 24) & 1u;
-        }
-        return bits;
-    }
-    if (off > FW_CH || off < -FW_CH) return 0xFFFFu;  // no run of crossings can bring the winding back to zero
-#pragma unroll
-    for (int w4 = 0; w4 < 4; w4++) {
-        const uint32_t pre = d[w4] * 0x01010101u;  // byte i = sum_{k<=i} (delta_k + 32)
-        // winding of column i is zero <=> byte i == 32 * (i + 1) - off ; |off| <= 2 * FW_CH here, so every target byte stays in
-        // [2, 158]: the packed subtraction neither borrows nor wraps
-        const uint32_t tgt = 0x80604020u - (uint32_t)off * 0x01010101u;
-        bits |= (zero_bytes4(pre ^ tgt) ^ 0xFu) << (4 * w4);
-        off += (int32_t)(pre >> 24) - 128;
-    }
-    return bits;
-}
 
-template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k(FineArgs a, uint32_t n_tiles) {
+template <int S> __global__ void __launch_bounds__(32 * FW_TILES, FW_BLOCKS_PER_SM) fine_warp_k(FineArgs a, uint32_t n_tiles) {
     constexpr int ROWS = 16 * S;
     constexpr int P    = ROWS >= 64 ? 2 : 1;  // sample rows per lane
     constexpr uint32_t FULL = 0xffffffffu;
@@ -1452,6 +1515,10 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
     if (a.counts->overflow) return;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FwShared<S>   &sh = sh_all[warp];
+    // per-sample int32 windings of the current path-tile, only for COUNT-rule draws with a translucent source (which blend |winding| times)
+    // and for lists so long that |winding| may exceed 255: global scratch of this warp (it stays in L1 / L2), not shared memory that every
+    // resident warp would have to pay for
+    int32_t *const Wg = a.wscratch + (size_t)(blockIdx.x * FW_TILES + warp) * FW_WPLANE(S);
     // Tiles differ a lot in the length of their lists: every warp takes the next tile from a counter when it has finished one, so
     // that no warp slot of the SM sits idle while the slowest tile of a block is still being walked (the grid is one wave).
     for (;;) {
@@ -1494,6 +1561,8 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
         rxo[j] = 16 * (int32_t)((SamplePack<S>::X >> (4 * (r % S))) & 15);
         asm volatile("" : "+r"(ry[j]), "+r"(rxo[j]));  // keep them: the compiler otherwise re-derives both for every path-tile
     }
+    // rows of this lane that exist (S = 1: lanes 16-31 have none), as a mask over the bits of the coverage word
+    const uint32_t rowsel = (row[0] < ROWS ? 0xFFFFu : 0u) | ((P > 1 && row[P - 1] < ROWS) ? 0xFFFF0000u : 0u);
     sh.qxy[lane] = lane < 16 ? ((float)(tx * VKB_TILE + lane) + 0.5f) / (float)a.sd.width
                              : ((float)(ty * VKB_TILE + (lane - 16) + a.sd.origin_y - band_y0) + 0.5f) / (float)a.sd.full_height;
     const uint32_t grp = lane / S, sub = lane % S;  // pixel row group / which of its pixels this lane queues
@@ -1509,7 +1578,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
         {
             const uint32_t eo = (uint32_t)__shfl_sync(FULL, hh0.z, 0);
             const int      ne = __shfl_sync(FULL, hh0.w, 0);
-            if ((int)lane < min(ne, FW_CHUNK(ne))) cur = __ldg((const int4 *)(a.tile_edges + eo + lane));
+            if ((int)lane < ne) cur = __ldg((const int4 *)(a.tile_edges + eo + lane));
         }
         for (int q = 0; q < np; q++) {
             const int32_t   bd   = __shfl_sync(FULL, hh0.y, q);
@@ -1522,81 +1591,102 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
             if (q + 1 < np) { eoff_n = (uint32_t)__shfl_sync(FULL, hh0.z, q + 1); ne_n = __shfl_sync(FULL, hh0.w, q + 1); }
             const uint32_t rule = pt.rule_pattern & 0xFF, pattern = (pt.rule_pattern >> 8) & 0xFF, op = (pt.rule_pattern >> 16) & 0xFF;
             // solid sources: one colour for the whole path-tile
-            float src[4], ia = 0.0f;
+            float    src[4], ia = 0.0f;
+            bool     use_int = false;
+            uint32_t s_lo = 0, s_hi = 0, IA = 0;
             if (pattern == VKB_PAT_SOLID) {
                 eval_paint(pattern, nullptr, nullptr, 0.0f, 0.0f, pt.color, pt.opacity, 0.0f, 0.0f, src, lut);
                 ia = 1.0f - src[3];
                 if (op == VKB_OP_SUB) ia = -ia;
                 else if (op == VKB_OP_CLEAR) { src[0] = src[1] = src[2] = src[3] = 0.0f; ia = 0.0f; }
+                // exact multiples of 1/255 with no channel above alpha: the blend is done on packed integers (blend_int)
+                const uint32_t A = pt.color >> 24;
+                if (op == VKB_OP_CLEAR) use_int = true;  // (S = 0, IA = 0)
+                else if (op == VKB_OP_OVER && pt.opacity == 1.0f && (pt.color & 0xFF) <= A && ((pt.color >> 8) & 0xFF) <= A && ((pt.color >> 16) & 0xFF) <= A) {
+                    use_int = true;
+                    s_lo = __byte_perm(pt.color, 0, 0x4240); s_hi = __byte_perm(pt.color, 0, 0x4341); IA = 255u - A;
+                }
             }
             // COUNT rule (stroke triangles blended one by one): the number of blends matters unless the result does not depend on the destination
             const bool counted = rule == VKB_RULE_COUNT && !(pattern == VKB_PAT_SOLID && ia == 0.0f);
-            const bool use_w   = counted || n_e > FW_CH;
-            const int  par     = rule == VKB_RULE_EVEN_ODD ? 1 : -1;  // covered <=> (winding & par) != 0
-            uint32_t   m       = 0;                                   // bit j * 16 + c: sample row row[j], column c is covered
-            const bool skip    = rule >= VKB_RULE_CLIP_EO;            // stencil entries never reach this kernel (they bring a stencil plane with them)
+            // |winding| of a sample <= |backdrop| + one per edge of the list (an edge crosses the path from C to the sample at most once net)
+            const uint32_t wmax  = (bd < 0 ? 0u - (uint32_t)bd : (uint32_t)bd) + (uint32_t)n_e;
+            const bool     use_w = counted || (rule != VKB_RULE_EVEN_ODD && wmax > 255u);  // (parity needs one plane whatever the magnitude)
+            const int      par   = rule == VKB_RULE_EVEN_ODD ? 1 : -1;  // covered <=> (winding & par) != 0
+            uint32_t       m     = 0;                                   // bit j * 16 + c: sample row row[j], column c is covered
+            const bool     skip  = rule >= VKB_RULE_CLIP_EO;            // stencil entries never reach this kernel (they bring a stencil plane with them)
 
-            // ---- winding: one chunk of <= FW_CH edges, or chunks of FW_CH_LONG ----
-            const int CH = FW_CHUNK(n_e);
-            for (int e0 = 0;; e0 += CH) {
-                const int nn = max(0, min(CH, n_e - e0));
-                int4      nx = make_int4(0, 0, 0, 0);  // prefetch: the next chunk of this path-tile, else the first chunk of the next one
-                if (e0 + CH < n_e) {
-                    if ((int)lane < min(CH, n_e - e0 - CH)) nx = __ldg((const int4 *)(a.tile_edges + eoff + e0 + CH + lane));
-                } else if ((int)lane < min(ne_n, FW_CHUNK(ne_n))) nx = __ldg((const int4 *)(a.tile_edges + eoff_n + lane));
-                int32_t  base[P];
-                uint32_t d[P][4];
+            {
+                // ---- winding in bit-sliced counters, 32 edges per load ----
+                // use_w (COUNT rule with a translucent source, or |winding| possibly above 255): the counters are folded into this warp's
+                // int32 plane every 96 edges (partial sums stay within the signed 8 bits), which then holds the exact windings
+                const int mode = par == 1 ? 0 : ((use_w || wmax > 15u) ? 2 : 1);
+                uint32_t  pl[8];
 #pragma unroll
-                for (int j = 0; j < P; j++) {
-                    base[j] = 0;
+                for (int p = 0; p < 8; p++) pl[p] = (!use_w && ((bd >> p) & 1)) ? FULL : 0u;
+                bool first_fold = true;
+                for (int e0 = 0;; e0 += 32) {
+                    const int nn = max(0, min(32, n_e - e0));
+                    int4      nx = make_int4(0, 0, 0, 0);  // prefetch: the next 32 edges of this path-tile, else the first ones of the next
+                    if (e0 + 32 < n_e) {
+                        if ((int)lane < n_e - e0 - 32) nx = __ldg((const int4 *)(a.tile_edges + eoff + e0 + 32 + lane));
+                    } else if ((int)lane < ne_n) nx = __ldg((const int4 *)(a.tile_edges + eoff_n + lane));
+                    // every lane classifies its own edge once; the loop below reads one bit per edge
+                    const uint32_t nearmask = __ballot_sync(FULL, (uint32_t)(cur.x - X0 + 16384) < 36864u && (uint32_t)(cur.y - Y0 + 16384) < 36864u &&
+                                                                      (uint32_t)(cur.z - X0 + 16384) < 36864u && (uint32_t)(cur.w - Y0 + 16384) < 36864u);
+                    for (int k = 0; k < nn; k++) {
+                        const int32_t ax = __shfl_sync(FULL, cur.x, k) - X0, ay = __shfl_sync(FULL, cur.y, k) - Y0;
+                        const int32_t bx = __shfl_sync(FULL, cur.z, k) - X0, by = __shfl_sync(FULL, cur.w, k) - Y0;
+                        const bool    crossL = (ax <= 0) != (bx <= 0);
+                        uint32_t      hm, vm;
+                        bool          vneg;
+                        if ((nearmask >> k) & 1u) row_edge_masks<P, int32_t>(ax, ay, bx, by, crossL, ry, rxo, hm, vm, vneg);
+                        else row_edge_masks_far<P>(ax, ay, bx, by, crossL, ry, rxo, hm, vm, vneg);
+                        plane_add(pl, hm, by < ay, mode);
+                        if (crossL) plane_add(pl, vm, vneg, mode);
+                    }
+                    cur = nx;
+                    const bool last = e0 + 32 >= n_e;
+                    if (use_w && (last || (e0 >> 5) % 3 == 2)) {
 #pragma unroll
-                    for (int w4 = 0; w4 < 4; w4++) d[j][w4] = FW_DBIAS * 0x01010101u;
+                        for (int j = 0; j < P; j++) {
+                            if (row[j] < ROWS) {
+                                int32_t *wr = Wg + row[j] * FW_WSTRIDE;
+#pragma unroll 4
+                                for (int c = 0; c < 16; c++) {
+                                    uint32_t v = 0;
+#pragma unroll
+                                    for (int p = 0; p < 8; p++) v |= ((pl[p] >> (16 * j + c)) & 1u) << p;
+                                    const int32_t sv = (int32_t)(int8_t)v;
+                                    if (first_fold) wr[c] = bd + sv; else wr[c] += sv;
+                                }
+                            }
+                        }
+                        first_fold = false;
+#pragma unroll
+                        for (int p = 0; p < 8; p++) pl[p] = 0u;
+                    }
+                    if (last) break;
                 }
-                // every lane classifies its own edge once; the loop below reads one bit per edge
-                const uint32_t nearmask = __ballot_sync(FULL, (uint32_t)(cur.x - X0 + 16384) < 36864u && (uint32_t)(cur.y - Y0 + 16384) < 36864u &&
-                                                                  (uint32_t)(cur.z - X0 + 16384) < 36864u && (uint32_t)(cur.w - Y0 + 16384) < 36864u);
-                for (int k = 0; k < nn; k++) {
-                    const int32_t ax = __shfl_sync(FULL, cur.x, k) - X0, ay = __shfl_sync(FULL, cur.y, k) - Y0;
-                    const int32_t bx = __shfl_sync(FULL, cur.z, k) - X0, by = __shfl_sync(FULL, cur.w, k) - Y0;
-                    const bool    crossL = (ax <= 0) != (bx <= 0);
-                    const bool    near = (nearmask >> k) & 1u;
-                    if (near) row_edge<P, int32_t>(ax, ay, bx, by, crossL, ry, rxo, d, base);
-                    else row_edge<P, long long>(ax, ay, bx, by, crossL, ry, rxo, d, base);
-                }
-                cur = nx;
-                if (!use_w) {  // (one chunk) the coverage bits come straight from the registers
+                if (!use_w) {
+                    m = pl[0];
+                    if (mode >= 1) m |= pl[1] | pl[2] | pl[3];
+                    if (mode == 2) m |= pl[4] | pl[5] | pl[6] | pl[7];
+                    m &= rowsel;
+                } else {  // each lane reads back the rows it accumulated itself
 #pragma unroll
-                    for (int j = 0; j < P; j++)
-                        if (row[j] < ROWS) m |= row_cover_bits(d[j], base[j] + bd, par) << (16 * j);
-                    break;
-                }
+                    for (int j = 0; j < P; j++) {
+                        if (row[j] < ROWS) {
+                            const int32_t *wr   = Wg + row[j] * FW_WSTRIDE;
+                            uint32_t       bits = 0;
 #pragma unroll
-                for (int j = 0; j < P; j++) {
-                    if (row[j] < ROWS) {
-                        int      run = base[j] + (e0 == 0 ? bd : 0);
-                        int32_t *wr  = sh.W + row[j] * FW_WSTRIDE;
-#pragma unroll
-                        for (int c = 0; c < 16; c++) {
-                            run += (int)((d[j][c >> 2] >> (8 * (c & 3))) & 0xFF) - (int)FW_DBIAS;
-                            if (e0 == 0) wr[c] = run; else wr[c] += run;
+                            for (int c = 0; c < 16; c++) bits |= ((wr[c] & par) != 0 ? 1u : 0u) << c;
+                            m |= bits << (16 * j);
                         }
                     }
                 }
-                if (e0 + CH >= n_e) break;
             }
             if (skip) continue;
-            if (use_w) {  // each lane reads back the rows it accumulated itself
-#pragma unroll
-                for (int j = 0; j < P; j++) {
-                    if (row[j] < ROWS) {
-                        const int32_t *wr   = sh.W + row[j] * FW_WSTRIDE;
-                        uint32_t       bits = 0;
-#pragma unroll
-                        for (int c = 0; c < 16; c++) bits |= ((wr[c] & par) != 0 ? 1u : 0u) << c;
-                        m |= bits << (16 * j);
-                    }
-                }
-            }
 #pragma unroll
             for (int j = 0; j < P; j++)
                 if (row[j] < ROWS) sh.rowmask[row[j]] = (uint16_t)(m >> (16 * j));
@@ -1616,7 +1706,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                 mine &= mine - 1u;
                 sh.queue[off++] = (uint8_t)((grp + 8 * (b >> 4)) * 16 + (b & 15));
             }
-            __syncwarp();
+            __syncwarp();  // (also orders the winding plane in global memory between the lanes of the warp)
             // ---- blend, 32 pixels at a time ----
             for (uint32_t i0 = 0; i0 < total; i0 += 32) {
                 const bool     act = i0 + lane < total;
@@ -1625,7 +1715,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                 int32_t        n[S], nmax = 0;
                 if (counted) {
 #pragma unroll
-                    for (int s = 0; s < S; s++) n[s] = act ? abs(sh.W[(ly * S + s) * FW_WSTRIDE + lx]) : 0;
+                    for (int s = 0; s < S; s++) n[s] = act ? abs(Wg[(ly * S + s) * FW_WSTRIDE + lx]) : 0;
                 } else {  // the S row masks of a pixel row are adjacent: one load
                     unsigned long long rm;
                     if (S == 4) rm = *(const unsigned long long *)(sh.rowmask + ly * 4);
@@ -1660,7 +1750,29 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                 }
                 // one result per pixel when its samples hold one colour (or the source is opaque) and are blended equally often:
                 // warp-uniform choice, a divergent one would execute both variants
-                if (__all_sync(FULL, !act || ((uni || opaque) && two))) {
+                const bool one = __all_sync(FULL, !act || ((uni || opaque) && two));
+                if (use_int) {  // (warp uniform) packed-integer blend: ten instructions per sample
+                    if (one) {
+                        uint32_t r = blend_int(c[0], s_lo, s_hi, IA);
+                        if (counted)
+                            for (int32_t k = 1; k < nmax; k++) r = blend_int(r, s_lo, s_hi, IA);
+                        if (act) {
+#pragma unroll
+                            for (int s = 0; s < S; s++)
+                                if (n[s]) cp[16 * s] = r;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            if (n[s] != 0) {
+                                uint32_t r = blend_int(c[s], s_lo, s_hi, IA);
+                                if (counted)
+                                    for (int32_t k = 1; k < n[s]; k++) r = blend_int(r, s_lo, s_hi, IA);
+                                cp[16 * s] = r;
+                            }
+                        }
+                    }
+                } else if (one) {
                     uint32_t r = blend_over(c[0], src, ia, lut);
                     if (counted)
                         for (int32_t k = 1; k < nmax; k++) r = blend_over(r, src, ia, lut);
@@ -1669,20 +1781,18 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, 6) fine_warp_k
                         for (int s = 0; s < S; s++)
                             if (n[s]) cp[16 * s] = r;
                     }
-                } else if (!counted && pattern != VKB_PAT_SOLID) {  // rolled: one copy of the blend in the instruction cache, which the gradient code fills
+                } else {  // rolled: one copy of the fp32 blend in the instruction cache, which the gradient code fills
                     uint32_t nb = 0;
 #pragma unroll
-                    for (int s = 0; s < S; s++) nb |= (uint32_t)n[s] << s;
+                    for (int s = 0; s < S; s++) nb |= (n[s] ? 1u : 0u) << s;
 #pragma unroll 1
-                    for (int s = 0; s < S; s++)
-                        if ((nb >> s) & 1u) cp[16 * s] = blend_over(cp[16 * s], src, ia, lut);  // (a sample no lane covers costs one branch)
-                } else {
-#pragma unroll
                     for (int s = 0; s < S; s++) {
-                        if (n[s] != 0) {  // (a sample no lane covers costs one branch)
-                            uint32_t r = blend_over(c[s], src, ia, lut);
-                            if (counted)
-                                for (int32_t k = 1; k < n[s]; k++) r = blend_over(r, src, ia, lut);
+                        if ((nb >> s) & 1u) {  // (a sample no lane covers costs one branch)
+                            uint32_t r = blend_over(cp[16 * s], src, ia, lut);
+                            if (counted) {
+                                const int32_t reps = abs(Wg[(ly * S + s) * FW_WSTRIDE + lx]);
+                                for (int32_t k = 1; k < (opaque ? 1 : reps); k++) r = blend_over(r, src, ia, lut);
+                            }
                             cp[16 * s] = r;
                         }
                     }
@@ -1742,9 +1852,11 @@ static int g_fine_mode = [] {
 }();
 void vkb_fine_set_mode(int mode) { g_fine_mode = (mode == 1 || mode == 2) ? mode : 0; }
 int  vkb_fine_get_mode() { return g_fine_mode; }
+// words of winding-plane scratch the warp-per-tile kernel needs (FineArgs::wscratch): one plane per warp of the (one-wave) grid
+size_t vkb_fine_wscratch_words(uint32_t samples) { return (size_t)148 * FW_BLOCKS_PER_SM * FW_TILES * FW_WPLANE(samples > 4 ? 4 : (samples ? samples : 1)); }
 template <int S> static void launch_fine_warp(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
-    const uint32_t blocks = vkb_div_up(tiles, FW_TILES);
-    fine_warp_k<S><<<blocks < 148u * 6u ? blocks : 148u * 6u, 32 * FW_TILES, 0, s>>>(a, tiles);  // one wave: 6 blocks of 4 warps per SM
+    const uint32_t blocks = vkb_div_up(tiles, FW_TILES), wave = 148u * FW_BLOCKS_PER_SM;
+    fine_warp_k<S><<<blocks < wave ? blocks : wave, 32 * FW_TILES, 0, s>>>(a, tiles);  // one wave: FW_BLOCKS_PER_SM blocks of FW_TILES warps per SM
 }
 template <int S> static void launch_fine_s(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
     const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
