@@ -657,6 +657,15 @@ def test_warp_and_block_fine_kernels_agree(fine_kernel_knob, oracle_lib, samples
                     g.line_to(x0 - d, y0 + 33.0 + d)
                     g.close_path()
                 g.fill()
+            # more edges through one tile than the int16 deltas of the warp kernel's work-item path hold (folded into its int32 plane)
+            if samples == 4:
+                g.set_fill_rule(1)
+                g.set_source_rgba(0.8, 0.5, 0.1, 0.4)
+                g.move_to(120.0, 100.0)
+                for i in range(17000):
+                    g.line_to(114.0 + r.uniform(0, 12), 94.0 + r.uniform(0, 12))
+                g.close_path()
+                g.fill()
             # translucent zig-zag stroke overlapping itself
             g.set_source_rgba(0.9, 0.1, 0.4, 0.35)
             g.set_line_width(9.0)

@@ -1486,22 +1486,234 @@ template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_a
 //     reference's per-sample arithmetic (blend_over).  Lanes are pixels that need work, not pixels that might.
 // Same results as fine_k bit for bit (tests/test_gpu_parity.py runs both on the same scenes).
 // ----------------------------------------------------------------------------------------------------
-#define FW_TILES 4      // warps per block, each working on a tile of its own; they only share the u8 -> float table
-#define FW_BLOCKS_PER_SM 8
-#define FW_WSTRIDE 17   // words per sample row of the winding plane (odd: lanes = rows hit distinct banks)
-#define FW_WPLANE(S) (16 * (S) * FW_WSTRIDE)  // int32 words of one warp's winding plane (global scratch, see FineArgs::wscratch)
-template <int S> struct alignas(16) FwShared {
-    uint32_t col[16 * S * 16];        // sample colours, [sample row = ly * S + s][lx]
-    uint16_t rowmask[16 * S];         // per sample row: bit lx = covered by the current path-tile
-    uint8_t  queue[256];              // pixels (ly * 16 + lx) with at least one covered sample
-    float    qxy[32];                 // pixel centre / surface size: 16 columns, then 16 rows (what the gradient evaluation starts from)
-};
-
+// ----------------------------------------------------------------------------------------------------
+// fine_warp_k, winding: (edge, sample row) WORK ITEMS.
+// With one lane per sample row every lane walks every edge of the list, although a short edge (a flattened curve, a piece of a
+// round join: the bulk of C3 / C4 / tiger) spans a handful of the tile's 16 * S sample rows: the C3 capture of the previous version
+// showed 5 of 32 lanes active in the crossing code.  Here the 32 edges of a chunk are first looked at by one lane EACH (row range,
+// per-edge constants), the (edge, row) pairs are numbered by a prefix sum, and the warp then works through them 32 at a time: every
+// lane finds its pair (binary search over the prefix sums with shuffles), computes the exact first covered column with the same
+// integer predicates as row_edge, and adds +-1 there to the row's packed per-column deltas in shared memory (one ATOMS per crossing).
+// The V term (a constant per row) is evaluated by the row lanes only for the edges that cross L.  At the end of the list each row
+// lane turns the deltas of its rows into coverage bits: a parity word (even-odd) or biased int16 walked column by column (non-zero, COUNT
+// rule; lists of more than 16000 edges fold them into this warp's int32 plane every 16000 edges).  Lists of at most FW_CH edges do not
+// come here: for them one lane per row with bit-sliced counters (plane_add) is cheaper than the fixed cost of numbering the pairs.
+// Sample rows are numbered in order of y for this: y(r) = FW_YSTEP * r + FW_YOFF (the standard sample positions are evenly spaced
+// in y), which turns "rows the edge spans" into two shifts.
+// ----------------------------------------------------------------------------------------------------
 // sample positions as packed nibbles (sample s = nibble s): no select chain, cheap enough to recompute anywhere
 template <int S> struct SamplePack;
 template <> struct SamplePack<1> { static constexpr unsigned long long X = 0x8ull, Y = 0x8ull; };
 template <> struct SamplePack<2> { static constexpr unsigned long long X = 0x4Cull, Y = 0x4Cull; };
 template <> struct SamplePack<4> { static constexpr unsigned long long X = 0xA2E6ull, Y = 0xEA62ull; };
+
+#define FW_WSTRIDE 17   // words per sample row of the winding plane (odd: lanes = rows hit distinct banks)
+#define FW_DL_STRIDE 8  // words per sample row of the delta plane: 16 x int16 (no padding: 8 blocks of 4 warps then fit the shared memory of an SM)
+#define FW_CH 15        // lists of up to FW_CH edges take the one-lane-per-row path with bit-sliced counters, longer ones the work items
+#define FW_HBIAS 0x4000u  // bias of the packed int16: room for 16383 crossings of either sign in one column of one row
+#define FW_SEG_CHUNKS 500  // lists of more than 16000 edges are folded into the int32 plane every 500 chunks of 32
+template <int S> struct FwRows;  // sample rows in order of y: y(r) = STEP * r + OFF (tile-relative 24.8), sample index of row r
+template <> struct FwRows<1> { static constexpr int LOG = 8, OFF = 128; static __device__ __forceinline__ int smp(int) { return 0; } };
+template <> struct FwRows<2> { static constexpr int LOG = 7, OFF = 64;  static __device__ __forceinline__ int smp(int r) { return 1 - (r & 1); } };
+template <> struct FwRows<4> { static constexpr int LOG = 6, OFF = 32;  static __device__ __forceinline__ int smp(int r) { return r & 3; } };
+
+// One chunk of <= 32 edges (this lane's edge: tile-relative a -> b, `valid` when the lane has one).  T = int32_t when every edge of the
+// chunk lies within [-16384, 20479] of the tile origin (products < 7.6e8, sums < 1.6e9, as in row_edge), else long long.
+// mode 0: parity words, 2: packed biased int16.  base[j] accumulates the V term of this lane's sample rows.
+template <int S, int P, class T>
+__device__ __forceinline__ void fw_chunk(uint32_t lane, bool valid, int32_t ax, int32_t ay, int32_t bx, int32_t by, const int32_t (&ry)[P], int mode,
+                                         uint32_t *dl, int32_t (&base)[P]) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int      ROWS = 16 * S;
+    const int32_t dx = bx - ax, dy = by - ay;
+    const T       K  = (T)dy * ax - (T)dx * ay;  // m(y) = dx*y + K ;  2*E(L,y) = 2*m - dy ;  E(sample) = m - dy*sx
+    // ---- V term: crossings of the vertical segment from C down to (L, y).  Only edges that cross L and lie on the far side of C ----
+    {
+        bool vact = false;
+        if (valid && ((ax <= 0) != (bx <= 0))) {
+            const bool    tie = dy == 0 || ((dx > 0) != (dy > 0));
+            const int32_t rc  = dy - dx;  // 2*E(C) = 2*K - rc
+            const bool belowC = dx > 0 ? (twice_gt<T>(K, rc) || (!twice_lt<T>(K, rc) && tie)) : (twice_lt<T>(K, rc) || (!twice_gt<T>(K, rc) && tie));
+            vact = !belowC;  // (the predicate is monotone in y: once true at C it is true for every row, and the term vanishes)
+        }
+        uint32_t vmask = __ballot_sync(FULL, vact);
+        while (vmask) {
+            const int k = __ffs((int)vmask) - 1;
+            vmask &= vmask - 1u;
+            const int32_t edx = __shfl_sync(FULL, dx, k), edy = __shfl_sync(FULL, dy, k);
+            const T       eK  = __shfl_sync(FULL, K, k);
+            const bool    tie = edy == 0 || ((edx > 0) != (edy > 0));
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const T m = (T)edx * ry[j] + eK;
+                if (edx > 0) base[j] -= (int)(twice_gt<T>(m, edy) || (!twice_lt<T>(m, edy) && tie));
+                else base[j] += (int)(twice_lt<T>(m, edy) || (!twice_gt<T>(m, edy) && tie));
+            }
+        }
+    }
+    // ---- H term: one work item per (edge, spanned sample row) ----
+    int ra = 0, n_i = 0;
+    if (valid && dy != 0) {  // rows with min(ay, by) <= y(r) < max(ay, by)  (the "spans" test of row_edge)
+        const int32_t lo = min(ay, by), hi = max(ay, by);
+        const int32_t STEPM1 = (1 << FwRows<S>::LOG) - 1;
+        ra = min(max((lo - FwRows<S>::OFF + STEPM1) >> FwRows<S>::LOG, 0), ROWS);
+        const int rb = min(max((hi - FwRows<S>::OFF + STEPM1) >> FwRows<S>::LOG, 0), ROWS);
+        n_i = rb - ra;
+    }
+    const int incl = warp_incl_scan(n_i), total = __shfl_sync(FULL, incl, 31), start = incl - n_i;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + (int)lane;
+        int       i = 0;  // the edge whose items include t: the last one with start <= t
+#pragma unroll
+        for (int b = 16; b >= 1; b >>= 1) {
+            const int s = __shfl_sync(FULL, start, i + b);
+            if (s <= t) i += b;
+        }
+        const int     r   = __shfl_sync(FULL, ra, i) + (t - __shfl_sync(FULL, start, i));
+        const int32_t edx = __shfl_sync(FULL, dx, i), edy = __shfl_sync(FULL, dy, i);
+        const T       eK  = __shfl_sync(FULL, K, i);
+        if (t < total) {
+            const int     smp = FwRows<S>::smp(r);
+            const int32_t y   = (r << FwRows<S>::LOG) + FwRows<S>::OFF;
+            const int32_t rxo = 16 * (int32_t)((SamplePack<S>::X >> (4 * smp)) & 15);
+            const T       m   = (T)edx * y + eK;
+            const int32_t h   = edy > 0 ? (edy >> 1) : ((edy + 1) >> 1);
+            // a crossing at or left of L is already counted by the backdrop and the V term (its two H contributions cancel)
+            if (!(edy > 0 ? (m <= (T)h) : (m >= (T)h))) {
+                T qq = m - (T)edy * rxo;  // first column c with 256*|dy|*c >= qq is the first one at or right of the crossing
+                if (edy < 0) qq = -qq;
+                int c0 = 0;
+                if (qq > 0) {
+                    const T D = (T)256 * (edy > 0 ? edy : -edy);
+                    int     c = 0;
+                    T       Dc = 0;
+                    if (D * 8 < qq) { c = 8; Dc = D * 8; }
+                    if (Dc + D * 4 < qq) { c += 4; Dc += D * 4; }
+                    if (Dc + D * 2 < qq) { c += 2; Dc += D * 2; }
+                    if (Dc + D < qq) { c += 1; }
+                    c0 = c + 1;  // c = last column still left of the crossing
+                }
+                if (c0 < 16) {
+                    uint32_t *row = dl + ((r & ~(S - 1)) | smp) * FW_DL_STRIDE;  // (storage order of the rows: pixel row * S + sample)
+                    const uint32_t one = edy > 0 ? 1u : 0xffffffffu;
+                    if (mode == 0) atomicXor(row, (0xFFFFu << c0) & 0xFFFFu);
+                    else atomicAdd(row + (c0 >> 1), one << (16 * (c0 & 1)));
+                }
+            }
+        }
+    }
+}
+template <int S, int P>
+__device__ __noinline__ void fw_chunk_far(uint32_t lane, bool valid, int32_t ax, int32_t ay, int32_t bx, int32_t by, int32_t ry0, int32_t ry1, int mode,
+                                          uint32_t *dl, int32_t *base0, int32_t *base1) {
+    int32_t ry[P], base[P];
+    ry[0] = ry0; base[0] = *base0;
+    if (P > 1) { ry[P - 1] = ry1; base[P - 1] = *base1; }
+    fw_chunk<S, P, long long>(lane, valid, ax, ay, bx, by, ry, mode, dl, base);
+    *base0 = base[0];
+    if (P > 1) *base1 = base[P - 1];
+}
+
+// A path-tile with more than FW_CH edges: (edge, sample row) work items into the packed deltas of the rows, then the coverage bits of this
+// lane's rows (bit 16 * j + c).  Out of line: the hot loop of fine_warp_k (short lists) keeps its size in the instruction cache.
+// *cur holds edge `lane` of the list on entry and the first edges of the NEXT path-tile (eoff_n, ne_n) on return.
+template <int S, int P>
+__device__ __noinline__ uint32_t fw_long_list(uint32_t lane, const vkb_edge *tile_edges, uint32_t eoff, int n_e, uint32_t eoff_n, int ne_n, int4 *curp,
+                                              int32_t X0, int32_t Y0, int32_t ry0, int32_t ry1, int32_t bd, int par, bool counted, uint32_t *dl, int32_t *Wg) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int      ROWS = 16 * S;
+    int32_t ry[P];
+    int     row[P];
+    ry[0] = ry0; row[0] = (int)lane;
+    if (P > 1) { ry[P - 1] = ry1; row[P - 1] = 32 + (int)lane; }
+    int4       cur   = *curp;
+    const int  mode  = par == 1 ? 0 : 2;  // 0: parity words, 2: packed biased int16
+    const bool use_w = counted;           // the blend needs |winding| per sample: kept in this warp's int32 plane
+    const bool multi = mode == 2 && n_e > 32 * FW_SEG_CHUNKS;  // the int16 deltas are folded into the int32 plane every FW_SEG_CHUNKS chunks
+    const uint32_t bias = mode == 0 ? 0u : FW_HBIAS * 0x00010001u;
+    const int      nw   = mode == 0 ? 1 : 8;
+#pragma unroll
+    for (int j = 0; j < P; j++)
+        if (row[j] < ROWS)
+            for (int w = 0; w < nw; w++) dl[row[j] * FW_DL_STRIDE + w] = bias;
+    __syncwarp();
+    int32_t base[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) base[j] = 0;
+    bool first_fold = true;
+    for (int e0 = 0;; e0 += 32) {
+        const int nn = max(0, min(32, n_e - e0));
+        int4      nx = make_int4(0, 0, 0, 0);  // prefetch: the next 32 edges of this path-tile, else the first ones of the next
+        if (e0 + 32 < n_e) {
+            if ((int)lane < n_e - e0 - 32) nx = __ldg((const int4 *)(tile_edges + eoff + e0 + 32 + lane));
+        } else if ((int)lane < ne_n) nx = __ldg((const int4 *)(tile_edges + eoff_n + lane));
+        const bool    valid = (int)lane < nn;
+        const int32_t ax = cur.x - X0, ay = cur.y - Y0, bx = cur.z - X0, by = cur.w - Y0;
+        const bool    near = (uint32_t)(ax + 16384) < 36864u && (uint32_t)(ay + 16384) < 36864u && (uint32_t)(bx + 16384) < 36864u &&
+                          (uint32_t)(by + 16384) < 36864u;
+        if (__all_sync(FULL, near || !valid)) fw_chunk<S, P, int32_t>(lane, valid, ax, ay, bx, by, ry, mode, dl, base);
+        else fw_chunk_far<S, P>(lane, valid, ax, ay, bx, by, ry[0], ry[P - 1], mode, dl, &base[0], &base[P - 1]);
+        cur = nx;
+        const bool last = e0 + 32 >= n_e;
+        if (multi && (last || (e0 >> 5) % FW_SEG_CHUNKS == FW_SEG_CHUNKS - 1)) {  // fold the deltas so far into the int32 plane
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                if (row[j] < ROWS) {
+                    uint32_t *dr  = dl + row[j] * FW_DL_STRIDE;
+                    int32_t  *wr  = Wg + row[j] * FW_WSTRIDE;
+                    for (int c = 0; c < 16; c++) {  // (per-column deltas; the prefix sums along the row are taken once, at the end)
+                        const int32_t dlt = (int32_t)((dr[c >> 1] >> (16 * (c & 1))) & 0xFFFFu) - (int32_t)FW_HBIAS;
+                        if (first_fold) wr[c] = dlt; else wr[c] += dlt;
+                    }
+                    for (int w = 0; w < 8; w++) dr[w] = bias;
+                }
+            }
+            first_fold = false;
+            __syncwarp();
+        }
+        if (last) break;
+    }
+    __syncwarp();
+    *curp = cur;
+    // ---- coverage bits of this lane's rows ----
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        if (row[j] < ROWS) {
+            const uint32_t *dr  = dl + row[j] * FW_DL_STRIDE;
+            const int32_t   off = bd + base[j];
+            uint32_t        bits;
+            if (mode == 0) bits = (dr[0] ^ ((off & 1) ? 0xFFFFu : 0u)) & 0xFFFFu;
+            else {
+                int32_t *wr  = Wg + row[j] * FW_WSTRIDE;
+                int32_t  run = off;
+                bits = 0;
+                for (int c = 0; c < 16; c++) {
+                    int32_t w;
+                    if (multi) run += wr[c];
+                    else run += (int32_t)((dr[c >> 1] >> (16 * (c & 1))) & 0xFFFFu) - (int32_t)FW_HBIAS;
+                    w = run;
+                    if (use_w) wr[c] = w;
+                    bits |= (w != 0 ? 1u : 0u) << c;
+                }
+            }
+            m |= bits << (16 * j);
+        }
+    }
+    return m;
+}
+
+#define FW_TILES 4      // warps per block, each working on a tile of its own; they only share the u8 -> float table
+#define FW_BLOCKS_PER_SM 8
+#define FW_WPLANE(S) (16 * (S) * FW_WSTRIDE)  // int32 words of one warp's winding plane (global scratch, see FineArgs::wscratch)
+template <int S> struct alignas(16) FwShared {
+    uint32_t col[16 * S * 16];        // sample colours, [sample row = ly * S + s][lx]
+    uint32_t dl[16 * S * FW_DL_STRIDE];  // per sample row: packed per-column winding deltas of the current path-tile (see fw_chunk)
+    uint16_t rowmask[16 * S];         // per sample row: bit lx = covered by the current path-tile
+    uint8_t  queue[256];              // pixels (ly * 16 + lx) with at least one covered sample
+    float    qxy[32];                 // pixel centre / surface size: 16 columns, then 16 rows (what the gradient evaluation starts from)
+};
 
 
 template <int S> __global__ void __launch_bounds__(32 * FW_TILES, FW_BLOCKS_PER_SM) fine_warp_k(FineArgs a, uint32_t n_tiles) {
@@ -1561,8 +1773,6 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, FW_BLOCKS_PER_
         rxo[j] = 16 * (int32_t)((SamplePack<S>::X >> (4 * (r % S))) & 15);
         asm volatile("" : "+r"(ry[j]), "+r"(rxo[j]));  // keep them: the compiler otherwise re-derives both for every path-tile
     }
-    // rows of this lane that exist (S = 1: lanes 16-31 have none), as a mask over the bits of the coverage word
-    const uint32_t rowsel = (row[0] < ROWS ? 0xFFFFu : 0u) | ((P > 1 && row[P - 1] < ROWS) ? 0xFFFF0000u : 0u);
     sh.qxy[lane] = lane < 16 ? ((float)(tx * VKB_TILE + lane) + 0.5f) / (float)a.sd.width
                              : ((float)(ty * VKB_TILE + (lane - 16) + a.sd.origin_y - band_y0) + 0.5f) / (float)a.sd.full_height;
     const uint32_t grp = lane / S, sub = lane % S;  // pixel row group / which of its pixels this lane queues
@@ -1609,15 +1819,14 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, FW_BLOCKS_PER_
             }
             // COUNT rule (stroke triangles blended one by one): the number of blends matters unless the result does not depend on the destination
             const bool counted = rule == VKB_RULE_COUNT && !(pattern == VKB_PAT_SOLID && ia == 0.0f);
-            // |winding| of a sample <= |backdrop| + one per edge of the list (an edge crosses the path from C to the sample at most once net)
-            const uint32_t wmax  = (bd < 0 ? 0u - (uint32_t)bd : (uint32_t)bd) + (uint32_t)n_e;
-            const bool     use_w = counted || (rule != VKB_RULE_EVEN_ODD && wmax > 255u);  // (parity needs one plane whatever the magnitude)
             const int      par   = rule == VKB_RULE_EVEN_ODD ? 1 : -1;  // covered <=> (winding & par) != 0
             uint32_t       m     = 0;                                   // bit j * 16 + c: sample row row[j], column c is covered
             const bool     skip  = rule >= VKB_RULE_CLIP_EO;            // stencil entries never reach this kernel (they bring a stencil plane with them)
 
-            {
-                // ---- winding in bit-sliced counters, 32 edges per load ----
+            if (n_e <= FW_CH) {
+                // ---- short lists: winding in bit-sliced counters, one lane per sample row (plane_add) ----
+                const uint32_t wmax = (bd < 0 ? 0u - (uint32_t)bd : (uint32_t)bd) + (uint32_t)n_e;  // |winding| <= |backdrop| + one per edge
+                const bool     use_w = counted || (rule != VKB_RULE_EVEN_ODD && wmax > 255u);
                 // use_w (COUNT rule with a translucent source, or |winding| possibly above 255): the counters are folded into this warp's
                 // int32 plane every 96 edges (partial sums stay within the signed 8 bits), which then holds the exact windings
                 const int mode = par == 1 ? 0 : ((use_w || wmax > 15u) ? 2 : 1);
@@ -1672,7 +1881,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, FW_BLOCKS_PER_
                     m = pl[0];
                     if (mode >= 1) m |= pl[1] | pl[2] | pl[3];
                     if (mode == 2) m |= pl[4] | pl[5] | pl[6] | pl[7];
-                    m &= rowsel;
+                    m &= (row[0] < ROWS ? 0xFFFFu : 0u) | ((P > 1 && row[P - 1] < ROWS) ? 0xFFFF0000u : 0u);
                 } else {  // each lane reads back the rows it accumulated itself
 #pragma unroll
                     for (int j = 0; j < P; j++) {
@@ -1685,6 +1894,8 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, FW_BLOCKS_PER_
                         }
                     }
                 }
+            } else {  // long lists: (edge, sample row) work items, out of line (fw_long_list)
+                m = fw_long_list<S, P>(lane, a.tile_edges, eoff, n_e, eoff_n, ne_n, &cur, X0, Y0, ry[0], ry[P - 1], bd, par, counted, sh.dl, Wg);
             }
             if (skip) continue;
 #pragma unroll
@@ -1855,8 +2066,17 @@ int  vkb_fine_get_mode() { return g_fine_mode; }
 // words of winding-plane scratch the warp-per-tile kernel needs (FineArgs::wscratch): one plane per warp of the (one-wave) grid
 size_t vkb_fine_wscratch_words(uint32_t samples) { return (size_t)148 * FW_BLOCKS_PER_SM * FW_TILES * FW_WPLANE(samples > 4 ? 4 : (samples ? samples : 1)); }
 template <int S> static void launch_fine_warp(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
-    const uint32_t blocks = vkb_div_up(tiles, FW_TILES), wave = 148u * FW_BLOCKS_PER_SM;
-    fine_warp_k<S><<<blocks < wave ? blocks : wave, 32 * FW_TILES, 0, s>>>(a, tiles);  // one wave: FW_BLOCKS_PER_SM blocks of FW_TILES warps per SM
+    // one wave of persistent warps: as many blocks as are resident at once (registers allow FW_BLOCKS_PER_SM, shared memory may allow fewer)
+    static int per_sm = 0;
+    if (!per_sm) {
+        int n = 0;
+        if (const char *e = getenv("VKVG_B200_FW_CARVEOUT")) cudaFuncSetAttribute(fine_warp_k<S>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));  // (experiments)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fine_warp_k<S>, 32 * FW_TILES, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
+        per_sm = n < FW_BLOCKS_PER_SM ? n : FW_BLOCKS_PER_SM;
+        if (const char *e = getenv("VKVG_B200_FW_BLOCKS")) per_sm = atoi(e) > 0 && atoi(e) < per_sm ? atoi(e) : per_sm;
+    }
+    const uint32_t blocks = vkb_div_up(tiles, FW_TILES), wave = 148u * (uint32_t)per_sm;
+    fine_warp_k<S><<<blocks < wave ? blocks : wave, 32 * FW_TILES, 0, s>>>(a, tiles);
 }
 template <int S> static void launch_fine_s(const FineArgs &a, uint32_t tiles, cudaStream_t s) {
     const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
