@@ -4,8 +4,11 @@
  * include/vkvg.h that SURVEY.md §8(b) lists: same names, argument meaning, enum values, struct layouts,
  * refcount and sticky-status conventions.  Each group cites the reference declaration it replaces.
  *
- * Not provided (out of scope): text/fonts, surface patterns and image loading, recording,
- * clipping, operators other than OVER.  A program that only uses the calls below links unchanged.
+ * Provided: everything SURVEY.md 8(a)/(b) names plus the 8(f) widening - clipping and save / restore, surfaces as paint
+ * (vkvg_set_source_surface, vkvg_pattern_create_for_surface, vkvg_surface_create_from_image / _from_bitmap, PNG only), the recording
+ * API, the CLEAR and DIFFERENCE operators, vkvg_set_source_color_name, vkvg_device_get_stats.
+ * Not provided (out of scope, SURVEY.md 2 / DESIGN.md 7): text and fonts, JPEG decoding, the Vulkan interop entry points
+ * (vkvg_surface_get_vk_image ...).  A program that only uses the calls below links unchanged.
  */
 #ifndef VKVG_H
 #define VKVG_H
@@ -131,6 +134,13 @@ vkvg_public uint32_t      vkvg_device_get_reference_count(VkvgDevice dev);
 vkvg_public void          vkvg_device_set_dpy(VkvgDevice dev, int hdpy, int vdpy);
 vkvg_public void          vkvg_device_get_dpy(VkvgDevice dev, int *hdpy, int *vdpy);
 vkvg_public void          vkvg_device_set_context_cache_size(VkvgDevice dev, uint32_t maxCount);
+/* reference include/vkvg.h:331-349 (its VKVG_DBG_STATS build): high-water marks of the path / vertex arrays */
+#define VKVG_HAS_DBG_STATS
+typedef struct {
+    uint32_t sizePoints, sizePathes, sizeVertices, sizeIndices, sizeVBO, sizeIBO;
+} vkvg_debug_stats_t;
+vkvg_public vkvg_debug_stats_t vkvg_device_get_stats(VkvgDevice dev);
+vkvg_public void               vkvg_device_reset_stats(VkvgDevice dev);
 
 /* ---- surface: reference include/vkvg.h:725-845 ---- */
 vkvg_public VkvgSurface   vkvg_surface_create(VkvgDevice dev, uint32_t width, uint32_t height);
@@ -206,6 +216,7 @@ vkvg_public void vkvg_clip_preserve(VkvgContext ctx);
 vkvg_public void  vkvg_set_opacity(VkvgContext ctx, float opacity);
 vkvg_public float vkvg_get_opacity(VkvgContext ctx);
 vkvg_public void  vkvg_set_source_color(VkvgContext ctx, uint32_t c);
+vkvg_public void  vkvg_set_source_color_name(VkvgContext ctx, const char *color); /* reference include/vkvg.h:1958 (declared there, never defined) */
 vkvg_public void  vkvg_set_source_rgba(VkvgContext ctx, float r, float g, float b, float a);
 vkvg_public void  vkvg_set_source_rgb(VkvgContext ctx, float r, float g, float b);
 vkvg_public void  vkvg_set_source(VkvgContext ctx, VkvgPattern pat);

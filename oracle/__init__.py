@@ -58,6 +58,14 @@ class _Base:
             return lambda *a: fn(ctx, *a)
         raise AttributeError(name)
 
+    def polyline(self, xy):
+        """move_to(xy[0]) then line_to for the rest (the two entry points are bound once: a million-point line is a million calls)"""
+        xy = np.asarray(xy, np.float32).reshape(-1, 2).tolist()
+        mv, ln = self.move_to, self.line_to
+        mv(*xy[0])
+        for q in xy[1:]:
+            ln(q[0], q[1])
+
     def set_dash(self, dashes, offset=0.0):
         arr = (C.c_float * len(dashes))(*dashes)
         fn = getattr(self._lib, self._prefix + "set_dash")
@@ -75,6 +83,8 @@ class Oracle(_Base):
             L = _load(os.path.join(_HERE, "liboracle.so"))
             L.ovk_create.restype = _p
             L.ovk_create.argtypes = [_u, _u, _u]
+            L.ovk_create_window.restype = _p
+            L.ovk_create_window.argtypes = [_u] * 7
             L.ovk_pixels.restype = _p
             L.ovk_sample_pixels.restype = _p
             L.ovk_last_coverage.restype = _p
@@ -101,14 +111,25 @@ class Oracle(_Base):
             cls._libh = L
         return cls._libh
 
-    def __init__(self, width, height, samples=4, analytic=False):
+    def __init__(self, width, height, samples=4, analytic=False, window=None):
+        """window=(x0, y0, w, h): only that part of the logical width x height surface is stored and rasterised (it holds
+        exactly the pixels the same region of the whole surface would); pixels() etc. then return window-sized arrays."""
         self._lib = self.lib()
         if analytic:
             samples = 1   # analytic-coverage mode keeps one colour per pixel
-        self.width, self.height, self.samples = width, height, samples
-        self._ctx = self._lib.ovk_create(width, height, samples)
+        self.full_width, self.full_height = width, height
+        if window is not None:
+            assert not analytic, "the analytic-coverage restatement needs the whole surface"
+            x0, y0, w, h = (int(t) for t in window)
+            self.window = (x0, y0, w, h)
+            self._ctx = self._lib.ovk_create_window(width, height, samples, x0, y0, w, h)
+            width, height = w, h
+        else:
+            self.window = (0, 0, width, height)
+            self._ctx = self._lib.ovk_create(width, height, samples)
+        self.width, self.height, self.samples = width, height, samples   # of the stored pixels
         if not self._ctx:
-            raise ValueError("unsupported sample count %r" % samples)
+            raise ValueError("unsupported sample count %r or window %r" % (samples, window))
         if analytic:
             self._lib.ovk_set_coverage_mode(self._ctx, 1)
 

@@ -37,6 +37,8 @@ enum { OVK_RULE_EVEN_ODD = 0, OVK_RULE_NON_ZERO = 1, OVK_RULE_COUNT = 2 };
 
 /* ---- context: surface + state ---- */
 ovk_ctx *ovk_create(uint32_t width, uint32_t height, uint32_t samples);
+/* logical W x H surface of which only the window [x0, x0+w) x [y0, y0+h) is stored / rasterised (MSAA mode only) */
+ovk_ctx *ovk_create_window(uint32_t W, uint32_t H, uint32_t S, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h);
 void     ovk_destroy(ovk_ctx *c);
 void     ovk_clear(ovk_ctx *c);
 int      ovk_status(ovk_ctx *c);

@@ -87,3 +87,34 @@ def test_oracle_invalid_dash_status(oracle_lib):
     o.line_to(30, 30)
     o.stroke()
     assert o.status() == 13  # VKVG_STATUS_INVALID_DASH (include/vkvg.h:125-150)
+
+
+def test_windowed_oracle_equals_the_crop_of_the_whole_surface():
+    """Oracle(..., window=...) (test infrastructure for the 8192^2 / 16384^2 configs) stores and rasterises only a window of the logical
+    surface; it must hold exactly the pixels of that region of the whole-surface render - fills of both rules, gradients, strokes,
+    clip / save / restore, and the reference's recorded draw list."""
+    import oracle
+    from oracle import Oracle
+    from tests.golden import make_golden2 as mg2
+    for name in mg.PIXEL_SCENES:
+        full = Oracle(128, 128, 4)
+        mg.pixel_scene(full, name, 1)
+        a = full.pixels()
+        for (x0, y0, w, h) in ((16, 32, 64, 48), (0, 0, 128, 16), (100, 90, 28, 38)):
+            o = Oracle(128, 128, 4, window=(x0, y0, w, h))
+            mg.pixel_scene(o, name, 1)
+            assert np.array_equal(o.pixels(), a[y0:y0 + h, x0:x0 + w]), (name, x0, y0)
+    full, o = Oracle(128, 128, 4), Oracle(128, 128, 4, window=(30, 20, 70, 90))
+    for g in (full, o):
+        mg2.clip_scene(g, "save_restore", 0)
+    assert np.array_equal(o.pixels(), full.pixels()[20:110, 30:100])
+    if oracle.ref_available():
+        imgs = []
+        for win in (None, (40, 8, 60, 100)):
+            r = oracle.Ref(128, 128, 4)
+            mg.pixel_scene(r, "mixed", 1)
+            t = Oracle(128, 128, 4, window=win)
+            r.render_with(t)
+            imgs.append(t.pixels())
+            r.close()
+        assert np.array_equal(imgs[1], imgs[0][8:108, 40:100])

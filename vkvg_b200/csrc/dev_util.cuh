@@ -70,7 +70,7 @@ struct DevBuf {
 // ----------------------------------------------------------------------------------------------------
 enum {
     VKC_POINTS = 0,  // flattened points
-    VKC_FILL,        // fill / clip polygon edges
+    VKC_FILL,        // fill / clip work items: the points of the filled sub-paths (one polygon edge each)
     VKC_SITEMS,      // stroke work items (points of stroked sub-paths)
     VKC_VERTS,       // stroke vertices
     VKC_INDS,        // stroke indices
@@ -80,6 +80,7 @@ enum {
     VKC_ROWS,        // path-tile rows
     VKC_NE,          // non-empty path-tiles
     VKC_TE,          // edges copied into tile lists
+    VKC_FEDGES,      // fill / clip polygon edges: the items, plus the pieces NON_ZERO draws are split into at their self-intersections
     VKC_N
 };
 struct vkb_counts {

@@ -52,7 +52,8 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped, wscratch;
+    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped, wscratch, nz_mode, nz_cnt;
+    bool   nz_any = false;  // the batch holds NON_ZERO fills / clips: they go through nz_classify / nz_split (raster.cu)
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
     ScanScratch scan;
@@ -120,7 +121,7 @@ void vkb_device_close(vkb_device_impl *d) {
     dev_enter(d);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release(); d->nz_mode.release(); d->nz_cnt.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -320,7 +321,9 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     d->stencil_after = 0;
     d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
     d->any_dash = false;
+    d->nz_any   = false;
     for (const vkb_draw &dr : b.draws) {
+        if (dr.n_subpaths && ((dr.kind == VKB_DRAW_FILL && (dr.rule_pattern & 0xFF) == VKB_RULE_NON_ZERO) || (dr.kind == VKB_DRAW_CLIP && (dr.rule_pattern & 0xFF) == VKB_RULE_CLIP_NZ))) d->nz_any = true;
         if (dr.kind == VKB_DRAW_CLIP) { d->has_clip_draws = d->has_stencil_ops = true; d->stencil_after = 1; }
         else if (dr.kind == VKB_DRAW_STENCIL) {
             d->has_stencil_ops = true;
@@ -437,7 +440,7 @@ __global__ void extra_rect_edges_k(vkb_edge *edges, uint32_t *edge_draw, const u
                                    const vkb_counts *C) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rects || C->overflow) return;
-    const uint32_t base = C->n[VKC_FILL];  // (before the stroke edges, whose stored number is only known after tri_edges_k)
+    const uint32_t base = C->n[VKC_FEDGES];  // (before the stroke edges, whose stored number is only known after tri_edges_k)
     vkb_edge      *e    = edges + base;
     const int32_t  x0 = -VKB_TILE_FX, y0 = -VKB_TILE_FX, x1 = W * 256 + VKB_TILE_FX, y1 = H * 256 + VKB_TILE_FX;
     e[4 * i]     = vkb_edge{x0, y0, x1, y0};
@@ -448,10 +451,11 @@ __global__ void extra_rect_edges_k(vkb_edge *edges, uint32_t *edge_draw, const u
 }
 
 // ---- commit kernels: one thread turns the raw totals of a producing scan into checked counts (dev_util.cuh: vkb_counts) ----
-__global__ void commit_flatten_k(vkb_counts *C, const uint64_t *totals, uint32_t has_fill, uint32_t has_stroke) {
+__global__ void commit_flatten_k(vkb_counts *C, const uint64_t *totals, uint32_t has_fill, uint32_t has_stroke, uint32_t split) {
     if (C->overflow) return;
     vkc_commit(C, VKC_POINTS, (uint32_t)totals[0]);
     vkc_commit(C, VKC_FILL, has_fill ? (uint32_t)totals[1] : 0u);
+    if (!split) vkc_commit(C, VKC_FEDGES, has_fill ? (uint32_t)totals[1] : 0u);  // (else the scan of the split counts commits it)
     vkc_commit(C, VKC_SITEMS, has_stroke ? (uint32_t)totals[2] : 0u);
 }
 __global__ void commit_stroke_k(vkb_counts *C, const uint64_t *totals, uint32_t has_stroke, uint32_t n_extra) {
@@ -461,7 +465,7 @@ __global__ void commit_stroke_k(vkb_counts *C, const uint64_t *totals, uint32_t 
     vkc_commit(C, VKC_VERTS, nv);
     vkc_commit(C, VKC_INDS, ni);
     vkc_commit(C, VKC_TRIS, ni / 3);
-    vkc_commit(C, VKC_EDGES, C->n[VKC_FILL] + 3u * (ni / 3) + n_extra);
+    vkc_commit(C, VKC_EDGES, C->n[VKC_FEDGES] + 3u * (ni / 3) + n_extra);
 }
 __global__ void commit_pt_k(vkb_counts *C, const uint64_t *totals) {
     if (C->overflow) return;
@@ -487,7 +491,8 @@ static void plan_caps(vkb_device_impl *d, const SurfaceDesc &sd) {
         up(VKC_INDS, (uint64_t)c[VKC_SITEMS] * 18 + 192);
     }
     up(VKC_TRIS, (uint64_t)c[VKC_INDS] / 3);
-    up(VKC_EDGES, (uint64_t)c[VKC_FILL] + 3ull * c[VKC_TRIS] + d->n_extra);
+    up(VKC_FEDGES, (uint64_t)c[VKC_FILL] + (d->nz_any ? (uint64_t)c[VKC_FILL] / 2 + 64 : 0));  // split NON_ZERO draws: a guess, grown on overflow
+    up(VKC_EDGES, (uint64_t)c[VKC_FEDGES] + 3ull * c[VKC_TRIS] + d->n_extra);
     const uint64_t n_tiles = (uint64_t)sd.tiles_x * sd.tiles_y;
     up(VKC_PT, (uint64_t)d->n_draws * 8 + ((uint64_t)d->n_extra / 4 + (d->has_clip_draws ? 2 : 0)) * n_tiles + 1024);
     up(VKC_ROWS, c[VKC_PT]);
@@ -707,11 +712,23 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         vkb_launch_job_counts(d->sjob_sp.as<uint32_t>(), d->n_sjobs, d->sp_count.as<uint32_t>(), 2, d->sjob_base.as<uint32_t>(), st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->sjob_base.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, (uint32_t *)(totals + 2), d->scan, st);
     }
-    commit_flatten_k<<<1, 1, 0, st>>>(C, totals, d->n_fjobs ? 1u : 0u, d->n_sjobs ? 1u : 0u);
+    const bool nz_split = d->nz_any && d->n_fjobs;
+    commit_flatten_k<<<1, 1, 0, st>>>(C, totals, d->n_fjobs ? 1u : 0u, d->n_sjobs ? 1u : 0u, nz_split ? 1u : 0u);
     VKB_LAUNCHED();
     if (d->n_elems)
         vkb_launch_flatten_emit(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), d->pts.as<float2>(),
                                 d->ptflags.as<uint8_t>(), C, fcache, st);
+    if (nz_split) {  // NON_ZERO fills / clips as libtess makes them: classify the draws, count the pieces of every edge, scan
+        d->nz_mode.ensure((size_t)d->n_draws + 16, st);
+        d->nz_cnt.ensure(((size_t)cv[VKC_FILL] + 1) * 4, st);
+        if (d->failed) return;
+        vkb_launch_nz_classify(d->draws.as<vkb_draw>(), d->n_draws, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->pts.as<float2>(), C,
+                               d->paints.as<vkb_paint>(), d->nz_mode.as<uint8_t>(), st);
+        vkb_launch_nz_split_count(d->pts.as<float2>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(), d->n_fjobs,
+                                  d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->fcnt.as<uint32_t>(), d->n_draws, d->nz_mode.as<uint8_t>(), cv[VKC_FILL], C,
+                                  d->nz_cnt.as<uint32_t>(), st);
+        vkb_exclusive_scan<uint32_t, uint32_t>(d->nz_cnt.as<uint32_t>(), d->nz_cnt.as<uint32_t>(), 0, (uint32_t *)(totals + 11), d->scan, st, C, VKC_FILL, cv[VKC_FILL], VKC_FEDGES);
+    }
     VKB_EVENT_RECORD(d, d->ev_stage[1]);
 
     // ---- 3. strokes: (dash phase scan) -> count -> scan -> emit ----
@@ -753,8 +770,13 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     vkb_edge *edges = d->edges.as<vkb_edge>();
     uint32_t *edraw = d->edge_draw.as<uint32_t>();
-    vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
-                          d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->n_fjobs ? cv[VKC_FILL] : 0, C, sd, edges, edraw, st);
+    if (nz_split)
+        vkb_launch_nz_split_emit(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(),
+                                 d->fjob_base.as<uint32_t>(), d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->fcnt.as<uint32_t>(), d->n_draws,
+                                 d->nz_mode.as<uint8_t>(), d->nz_cnt.as<uint32_t>(), cv[VKC_FILL], C, sd, edges, edraw, st);
+    else
+        vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
+                              d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->n_fjobs ? cv[VKC_FILL] : 0, C, sd, edges, edraw, st);
     if (cap_items && d->n_sdraws) {
         // first work item of every stroke draw (to map a triangle back to its draw)
         d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
@@ -805,7 +827,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     memset(&k, 0, sizeof k);
     k.n_curves = d->n_curves; k.n_grads = d->n_grads;
     k.n_elems = d->n_elems; k.n_sp = d->n_sp; k.n_draws = d->n_draws; k.n_fjobs = d->n_fjobs; k.n_sjobs = d->n_sjobs; k.n_sdraws = d->n_sdraws; k.n_extra = d->n_extra;
-    k.flags = (d->any_dash ? 1u : 0u) | (d->has_clip_draws ? 2u : 0u) | (d->has_stencil_ops ? 4u : 0u) | ((uint32_t)d->stencil_after << 3);
+    k.flags = (d->any_dash ? 1u : 0u) | (d->has_clip_draws ? 2u : 0u) | (d->has_stencil_ops ? 4u : 0u) | ((uint32_t)d->stencil_after << 3) | (d->nz_any ? 32u : 0u);
     memcpy(k.capv, d->capv, sizeof k.capv);
     k.surf = surf; k.w = sd.width; k.h = sd.height; k.samples = sd.samples; k.full_h = sd.full_height; k.origin_y = sd.origin_y;
     k.known_clear = surf->known_clear; k.stencil_live = surf->stencil_live; k.stencil_samples = surf->stencil_samples;
@@ -857,7 +879,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
 
 static void fill_stats(vkb_device_impl *d, const vkb_counts &h, vkb_stats &S, bool with_stages) {
     S.n_elems = d->n_elems; S.h2d_bytes = d->h2d_bytes; S.ms_host_upload = d->ms_host_upload;
-    S.n_points = h.n[VKC_POINTS]; S.n_fill_edges = h.n[VKC_FILL]; S.n_stroke_items = h.n[VKC_SITEMS];
+    S.n_points = h.n[VKC_POINTS]; S.n_fill_edges = h.n[VKC_FEDGES]; S.n_stroke_items = h.n[VKC_SITEMS];
     S.n_verts = h.n[VKC_VERTS]; S.n_inds = h.n[VKC_INDS]; S.n_edges = h.n[VKC_EDGES];
     S.n_path_tiles = h.n[VKC_PT]; S.n_nonempty = h.n[VKC_NE]; S.n_tile_edges = h.n[VKC_TE];
     cudaEventElapsedTime(&S.ms_total, d->ev_begin, d->ev_end);

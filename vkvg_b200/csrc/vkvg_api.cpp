@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include <vector>
 
 #define M_PIF 3.14159265358979323846f
@@ -41,6 +42,7 @@ struct _vkvg_device_t {
     std::mutex       mtx;  // one stream + shared scratch buffers per device: flushes are serialised
     bool             profiling;
     vkb_stats        last;
+    vkvg_debug_stats_t dbg;  // high-water marks (vkvg_device_get_stats)
 };
 struct _vkvg_surface_t {
     vkvg_status_t     status;
@@ -257,6 +259,7 @@ VkvgDevice vkvg_device_create(vkvg_device_create_info_t *info) {
     dev->impl        = impl;
     dev->profiling   = getenv("VKVG_B200_PROFILE") != nullptr;
     memset(&dev->last, 0, sizeof dev->last);
+    memset(&dev->dbg, 0, sizeof dev->dbg);
     return dev;
 }
 vkvg_status_t vkvg_device_status(VkvgDevice dev) { return !dev ? VKVG_STATUS_NULL_POINTER : dev->status; }
@@ -278,6 +281,17 @@ void vkvg_device_set_dpy(VkvgDevice dev, int hdpy, int vdpy) {
 void vkvg_device_get_dpy(VkvgDevice dev, int *hdpy, int *vdpy) {
     if (vkvg_device_status(dev)) return;
     *hdpy = dev->hdpi; *vdpy = dev->vdpi;
+}
+// VKVG_DBG_STATS build of the reference (include/vkvg.h:331-349, src/vkvg_device.c:512-519): high-water marks of the path / vertex arrays.
+// Here: of the device-side arrays the flushes of this device produced (points, sub-paths, stroke vertices / indices; the VBO / IBO
+// entries report the same, the "buffers" being those arrays).
+vkvg_debug_stats_t vkvg_device_get_stats(VkvgDevice dev) {
+    vkvg_debug_stats_t z = {0, 0, 0, 0, 0, 0};
+    return vkvg_device_status(dev) ? z : dev->dbg;
+}
+void vkvg_device_reset_stats(VkvgDevice dev) {
+    if (vkvg_device_status(dev)) return;
+    memset(&dev->dbg, 0, sizeof dev->dbg);
 }
 void vkvg_device_set_context_cache_size(VkvgDevice, uint32_t) {}  // contexts hold no device objects here: nothing to cache
 
@@ -921,6 +935,32 @@ static void set_solid(VkvgContext ctx, uint32_t c) {  // _update_cur_pattern(ctx
     ctx->pattern = NULL; ctx->patType = VKB_PAT_SOLID; ctx->grad_slot = -1;
 }
 void vkvg_set_source_color(VkvgContext ctx, uint32_t c) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_SOURCE_COLOR, {}, {c})) set_solid(ctx, c); }
+// include/vkvg.h:1958 of the reference declares this without defining it anywhere in src/: "#rgb", "#rrggbb", "#rrggbbaa" and the
+// sixteen CSS basic colour names are understood here; anything else leaves the source unchanged
+void vkvg_set_source_color_name(VkvgContext ctx, const char *color) {
+    if (vkvg_status(ctx) || !color) return;
+    static const struct { const char *name; uint32_t rgb; } names[] = {
+        {"black", 0x000000}, {"silver", 0xc0c0c0}, {"gray", 0x808080}, {"grey", 0x808080}, {"white", 0xffffff}, {"maroon", 0x800000}, {"red", 0xff0000},
+        {"purple", 0x800080}, {"fuchsia", 0xff00ff}, {"magenta", 0xff00ff}, {"green", 0x008000}, {"lime", 0x00ff00}, {"olive", 0x808000}, {"yellow", 0xffff00},
+        {"navy", 0x000080}, {"blue", 0x0000ff}, {"teal", 0x008080}, {"aqua", 0x00ffff}, {"cyan", 0x00ffff}, {"orange", 0xffa500}};
+    uint32_t rgb = 0, alpha = 255;
+    if (color[0] == '#') {
+        const size_t n = strlen(color + 1);
+        char        *end = nullptr;
+        const unsigned long v = strtoul(color + 1, &end, 16);
+        if (!end || *end) return;
+        if (n == 3) rgb = (uint32_t)(((v >> 8) & 0xF) * 0x110000 + ((v >> 4) & 0xF) * 0x1100 + (v & 0xF) * 0x11);
+        else if (n == 6) rgb = (uint32_t)v;
+        else if (n == 8) { rgb = (uint32_t)(v >> 8); alpha = (uint32_t)(v & 0xFF); }
+        else return;
+    } else {
+        bool found = false;
+        for (const auto &e : names)
+            if (!strcasecmp(e.name, color)) { rgb = e.rgb; found = true; break; }
+        if (!found) return;
+    }
+    vkvg_set_source_rgba(ctx, ((rgb >> 16) & 0xFF) / 255.0f, ((rgb >> 8) & 0xFF) / 255.0f, (rgb & 0xFF) / 255.0f, alpha / 255.0f);
+}
 void vkvg_set_source_rgb(VkvgContext ctx, float r, float g, float b) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_SOURCE_RGB, {r, g, b})) set_solid(ctx, rgbaf(r, g, b, 1)); }
 void vkvg_set_source_rgba(VkvgContext ctx, float r, float g, float b, float a) { if (!vkvg_status(ctx) && !rec(ctx, RC_SET_SOURCE_RGBA, {r, g, b, a})) set_solid(ctx, rgbaf(r, g, b, a)); }
 static void update_cur_pattern(VkvgContext ctx, VkvgPattern pat) {  // surface branch internal.c:705-773, gradient branch :774-826
@@ -1208,7 +1248,12 @@ static void stroke_preserve_(VkvgContext ctx) {  // _stroke_preserve :822-948
     if (!ctx->dashes.empty()) {
         float tot = 0;
         for (float v : ctx->dashes) tot += v;
-        if (tot == 0 || ctx->dashes.size() > VKB_MAX_DASHES) { ctx->status = VKVG_STATUS_INVALID_DASH; return; }
+        if (tot == 0) { ctx->status = VKVG_STATUS_INVALID_DASH; return; }  // the reference's only dash error (src/vkvg_context.c:853-860)
+        if (ctx->dashes.size() > VKB_MAX_DASHES) {  // limit of the stroke kernels: this stroke is skipped, the context stays usable
+            static bool warned = false;
+            if (!warned) { fprintf(stderr, "vkvg_b200: dash patterns of more than %d entries are not supported; stroke skipped\n", VKB_MAX_DASHES); warned = true; }
+            return;
+        }
         // reuse the previous stroke's dash table entry when the pattern is unchanged
         std::vector<float> &dt = ctx->batch.dashes;
         bool same = false;
@@ -1306,6 +1351,13 @@ static void flush_impl(VkvgContext ctx, vkb_capture *cap, bool keep_resident) {
                 dev->status = VKVG_STATUS_DEVICE_ERROR;
             }
             if (want_stats) dev->last = st;
+            {
+                vkvg_debug_stats_t &g = dev->dbg;
+                auto up = [](uint32_t &m, uint64_t v) { if (v > m) m = (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v); };
+                up(g.sizePoints, ctx->batch.elem_hdr.size());   // recorded path elements (a lower bound of the flattened points when curves are in)
+                up(g.sizePathes, ctx->batch.subpaths.size());
+                if (want_stats) { up(g.sizePoints, st.n_points); up(g.sizeVertices, st.n_verts); up(g.sizeIndices, st.n_inds); up(g.sizeVBO, st.n_verts); up(g.sizeIBO, st.n_inds); }
+            }
         }
     }
     (void)keep_resident;
@@ -1640,7 +1692,7 @@ vkvg_status_t vkvg_b200_time_resident(VkvgDevice dev, VkvgSurface surf, uint32_t
 vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *a, uint64_t n_args) {
     if (vkvg_status(ctx)) return vkvg_status(ctx);
     uint64_t k = 0;
-#define NEED(n) if (k + (n) > n_args) return VKVG_STATUS_INVALID_INDEX
+#define NEED(n) if ((uint64_t)(n) > n_args - k) return VKVG_STATUS_INVALID_INDEX  /* (k <= n_args always) */
     for (uint64_t i = 0; i < n_ops; i++) {
         switch (ops[i]) {
         case VKVG_B200_OP_MOVE_TO: NEED(2); vkvg_move_to(ctx, a[k], a[k + 1]); k += 2; break;
@@ -1658,15 +1710,16 @@ vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_o
         case VKVG_B200_OP_PAINT: vkvg_paint(ctx); break;
         case VKVG_B200_OP_SET_SOURCE_RGBA: NEED(4); vkvg_set_source_rgba(ctx, a[k], a[k + 1], a[k + 2], a[k + 3]); k += 4; break;
         case VKVG_B200_OP_SET_LINE_WIDTH: NEED(1); vkvg_set_line_width(ctx, a[k]); k += 1; break;
-        case VKVG_B200_OP_SET_LINE_CAP: NEED(1); vkvg_set_line_cap(ctx, (vkvg_line_cap_t)(int)a[k]); k += 1; break;
-        case VKVG_B200_OP_SET_LINE_JOIN: NEED(1); vkvg_set_line_join(ctx, (vkvg_line_join_t)(int)a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_LINE_CAP: NEED(1); if (!(a[k] >= 0.0f && a[k] <= 2.0f)) return VKVG_STATUS_INVALID_INDEX; vkvg_set_line_cap(ctx, (vkvg_line_cap_t)(int)a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_LINE_JOIN: NEED(1); if (!(a[k] >= 0.0f && a[k] <= 2.0f)) return VKVG_STATUS_INVALID_INDEX; vkvg_set_line_join(ctx, (vkvg_line_join_t)(int)a[k]); k += 1; break;
         case VKVG_B200_OP_SET_MITER_LIMIT: NEED(1); vkvg_set_miter_limit(ctx, a[k]); k += 1; break;
-        case VKVG_B200_OP_SET_FILL_RULE: NEED(1); vkvg_set_fill_rule(ctx, (vkvg_fill_rule_t)(int)a[k]); k += 1; break;
+        case VKVG_B200_OP_SET_FILL_RULE: NEED(1); if (!(a[k] >= 0.0f && a[k] <= 1.0f)) return VKVG_STATUS_INVALID_INDEX; vkvg_set_fill_rule(ctx, (vkvg_fill_rule_t)(int)a[k]); k += 1; break;
         case VKVG_B200_OP_SET_DASH: {
             NEED(2);
-            uint32_t n = (uint32_t)a[k];
+            if (!(a[k] >= 0.0f && a[k] <= 16777216.0f)) return VKVG_STATUS_INVALID_INDEX;  // NaN, negative or absurd count: the conversion below would be undefined
+            uint64_t n = (uint64_t)a[k];
             NEED(2 + n);
-            vkvg_set_dash(ctx, a + k + 2, n, a[k + 1]);
+            vkvg_set_dash(ctx, a + k + 2, (uint32_t)n, a[k + 1]);
             k += 2 + n;
             break;
         }
@@ -1674,12 +1727,14 @@ vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_o
         case VKVG_B200_OP_SET_SOURCE_RADIAL: {
             int np = ops[i] == VKVG_B200_OP_SET_SOURCE_LINEAR ? 4 : 6;
             NEED(np + 1);
-            uint32_t ns = (uint32_t)a[k + np];
-            NEED(np + 1 + 5 * ns);
+            if (!(a[k + np] >= 0.0f && a[k + np] <= 16.0f)) return VKVG_STATUS_INVALID_INDEX;  // a gradient holds at most 16 stops (and 5 * ns must not wrap)
+            uint64_t ns = (uint64_t)a[k + np];
+            NEED((uint64_t)np + 1 + 5 * ns);
             VkvgPattern pat = np == 4 ? vkvg_pattern_create_linear(a[k], a[k + 1], a[k + 2], a[k + 3])
                                       : vkvg_pattern_create_radial(a[k], a[k + 1], a[k + 2], a[k + 3], a[k + 4], a[k + 5]);
             const float *s = a + k + np + 1;
-            for (uint32_t j = 0; j < ns; j++) vkvg_pattern_add_color_stop(pat, s[5 * j], s[5 * j + 1], s[5 * j + 2], s[5 * j + 3], s[5 * j + 4]);
+            for (uint64_t j = 0; j < ns; j++)
+                if (vkvg_pattern_add_color_stop(pat, s[5 * j], s[5 * j + 1], s[5 * j + 2], s[5 * j + 3], s[5 * j + 4])) break;
             vkvg_set_source(ctx, pat);
             vkvg_pattern_destroy(pat);
             k += np + 1 + 5 * ns;
@@ -1704,7 +1759,11 @@ vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_o
             break;
         }
         case VKVG_B200_OP_FLUSH: vkvg_flush(ctx); break;
-        case VKVG_B200_OP_SET_CANVAS: NEED(1); if (vkvg_b200_set_canvas(ctx, (uint32_t)a[k])) return VKVG_STATUS_INVALID_INDEX; k += 1; break;
+        case VKVG_B200_OP_SET_CANVAS:
+            NEED(1);
+            if (!(a[k] >= 0.0f && a[k] <= 16777216.0f) || vkvg_b200_set_canvas(ctx, (uint32_t)a[k])) return VKVG_STATUS_INVALID_INDEX;
+            k += 1;
+            break;
         case VKVG_B200_OP_CLIP: vkvg_clip(ctx); break;
         case VKVG_B200_OP_CLIP_PRESERVE: vkvg_clip_preserve(ctx); break;
         case VKVG_B200_OP_RESET_CLIP: vkvg_reset_clip(ctx); break;
