@@ -1384,9 +1384,10 @@ static bool nz_cross(v2 a, v2 b, v2 c, v2 d, double *t, double *u, v2 *p) {
     const double den = rx * sy - ry * sx;
     if (den == 0.0) return false;
     const double qx = (double)c.x - (double)a.x, qy = (double)c.y - (double)a.y;
-    *t = (qx * sy - qy * sx) / den;
-    *u = (qx * ry - qy * rx) / den;
-    if (!(*t > 0.0 && *t < 1.0 && *u > 0.0 && *u < 1.0)) return false;
+    const double tn = qx * sy - qy * sx, un = qx * ry - qy * rx;   /* t = tn / den, u = un / den: proper when both lie strictly inside (0, 1) */
+    if (den > 0.0 ? !(tn > 0.0 && tn < den && un > 0.0 && un < den) : !(tn < 0.0 && tn > den && un < 0.0 && un > den)) return false;
+    *t = tn / den;
+    *u = un / den;
     p->x = (float)((double)a.x + *t * rx);
     p->y = (float)((double)a.y + *t * ry);
     return true;

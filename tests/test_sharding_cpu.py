@@ -52,6 +52,12 @@ def _worker(rank, world, port):
     ref = Oracle(W, H, 4)
     _scene(ref)
     assert np.array_equal(full, ref.pixels()), "rank %d: gathered stripes differ from the unsharded render" % rank
+    # gather to one root: every stripe straight into its rows of the root's buffer, nothing on the other ranks
+    root_img = sharding.gather_to_root(local, H, root=0)
+    if rank == 0:
+        assert np.array_equal(root_img.numpy(), ref.pixels())
+    else:
+        assert root_img is None
     # independent canvases: every canvas is rendered by exactly one rank
     mine = torch.zeros(37, dtype=torch.int64)
     mine[sharding.canvases_for_rank(37, rank, world)] = 1
@@ -82,3 +88,25 @@ def test_canvas_round_robin():
 @pytest.mark.timeout(180)
 def test_striped_render_and_gather_world2(oracle_lib):
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _worker_more_ranks_than_rows(rank, world, port):
+    """a 20-row surface has two tile rows: the third rank owns no rows, must still take part in both gathers and not hang"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Hs = 20
+    rows = sharding.stripe_rows(Hs, world)
+    assert any(h == 0 for _, h in rows)
+    y0, h = rows[rank]
+    full_ref = (np.arange(Hs * 8 * 4, dtype=np.uint32) % 251).astype(np.uint8).reshape(Hs, 8, 4)
+    local = torch.from_numpy(full_ref[y0:y0 + h].copy()) if h else torch.zeros((0, 8, 4), dtype=torch.uint8)
+    assert np.array_equal(sharding.gather_stripes(local, Hs).numpy(), full_ref)
+    img = sharding.gather_to_root(local, Hs, root=0)
+    assert (rank == 0 and np.array_equal(img.numpy(), full_ref)) or (rank != 0 and img is None)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_gathers_with_more_ranks_than_tile_rows():
+    mp.spawn(_worker_more_ranks_than_rows, args=(3, _free_port()), nprocs=3, join=True)

@@ -261,6 +261,20 @@ class Surface:
     def clear(self):
         lib().vkvg_surface_clear(self.h)
 
+    def as_tensor(self):
+        """the premultiplied RGBA8 image in device memory as a (H, W, 4) uint8 torch tensor WITHOUT a copy (what an NCCL gather of
+        the stripes sends from).  The library renders on a stream of its own: call Device.synchronize() before reading it."""
+        import torch
+
+        class _View:
+            pass
+        view = _View()
+        view.__cuda_array_interface__ = {"shape": (self.height, self.width, 4), "typestr": "|u1", "data": (int(lib().vkvg_b200_surface_device_pointer(self.h)), False),
+                                         "version": 3, "strides": None}
+        t = torch.as_tensor(view, device="cuda:%d" % lib().vkvg_b200_device_ordinal(self.dev.h))
+        t._vkvg_surface = self   # (keeps the surface alive as long as the view)
+        return t
+
     def pixels(self):
         """premultiplied RGBA8 exactly as stored, (H, W, 4)."""
         out = np.zeros((self.height, self.width, 4), np.uint8)

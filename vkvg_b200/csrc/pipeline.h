@@ -51,15 +51,13 @@ void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_x
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
                            vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
 // NON_ZERO fills / clips as the reference's libtess makes them (raster.cu): nz_mode per draw (0 none, 1 fan fast path -> COUNT rule, 2 edges
-// split at their crossings, 3 too large to split), then count -> scan -> emit of the pieces.  draw_first_job: exclusive scan of fill jobs per draw
+// split at their crossings, 3 too large to split), then the pieces in one pass.  draw_first_job: exclusive scan of fill jobs per draw
 void vkb_launch_nz_classify(const vkb_draw *draws, uint32_t n_draws, const uint32_t *sp_first, const uint32_t *sp_count, const float2 *pts, const vkb_counts *C,
                             vkb_paint *paints, uint8_t *nz_mode, cudaStream_t s);
-void vkb_launch_nz_split_count(const float2 *pts, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first,
-                               const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode, uint32_t cap_items,
-                               const vkb_counts *C, uint32_t *out_count, cudaStream_t s);
-void vkb_launch_nz_split_emit(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
-                              uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode,
-                              const uint32_t *offs, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
+// one pass over the fill items: pieces written where the warp reserved room (*n_out: zeroed device counter), then VKC_FEDGES committed from it
+void vkb_launch_nz_split(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
+                         uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode,
+                         uint32_t cap_items, vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap_edges, cudaStream_t s);
 // edges / edge_draw: start of the edge arrays (the kernel skips the C->n[VKC_FEDGES] fill edges and the n_extra rectangle edges itself);
 // live: zeroed device counter of the stroke edges stored (cancelled ones are dropped); Cw->n[VKC_EDGES] is set to the stored total
 // snapped: cap_verts int2 of scratch (every stroke vertex goes through the vertex stage once, then the triangles read integers)

@@ -31,16 +31,23 @@ def canvases_for_rank(n_canvases, rank, world):
 
 
 def gather_stripes(local, height, group=None):
-    """all-gather stripes of shape (h_r, W, 4) uint8 (torch tensors on the backend's device) into the (height, W, 4) image.
-    Stripes may differ in height (ragged last block): every rank pads to the tallest, gathers, and crops."""
+    """all-gather stripes of shape (h_r, W, 4) uint8 (torch tensors on the backend's device) into the (height, W, 4) image on every
+    rank.  Equal heights (the usual case: 16384 rows over 2 / 4 / 8 ranks): one all_gather_into_tensor straight into the final buffer,
+    no staging.  Ragged heights or ranks without rows: every rank pads to the tallest stripe, gathers, and crops."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rows = stripe_rows(height, world)
-    hmax = max(h for _, h in rows)
     w = local.shape[1]
+    hs = [h for _, h in rows]
+    if min(hs) == max(hs) and sum(hs) == height:
+        full = torch.empty((height, w, 4), dtype=torch.uint8, device=local.device)
+        dist.all_gather_into_tensor(full.view(-1), local[:hs[0]].contiguous().view(-1), group=group)
+        return full
+    hmax = max(hs)
     pad = torch.zeros((hmax, w, 4), dtype=torch.uint8, device=local.device)
-    pad[:local.shape[0]] = local
+    n = min(local.shape[0], rows[dist.get_rank(group)][1])
+    pad[:n] = local[:n]
     out = torch.empty((world, hmax, w, 4), dtype=torch.uint8, device=local.device)
     dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
     full = torch.empty((height, w, 4), dtype=torch.uint8, device=local.device)
@@ -49,13 +56,52 @@ def gather_stripes(local, height, group=None):
     return full
 
 
+def gather_to_root(local, height, out=None, root=0, group=None):
+    """Stripes (h_r, W, 4) uint8 -> the (height, W, 4) image on `root` (None elsewhere).  Every stripe travels once, straight into its
+    rows of the final buffer: the root posts one receive per sender into a view of `out`, senders send from `local` (which may be the
+    surface's own memory, Surface.as_tensor(): no staging copy on either side).  Ragged heights and ranks without rows (more ranks
+    than tile rows) are fine: such a rank sends nothing."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rows = stripe_rows(height, world)
+    w = local.shape[1]
+    ops = []
+    if rank == root:
+        if out is None:
+            out = torch.empty((height, w, 4), dtype=torch.uint8, device=local.device)
+        for r, (y0, h) in enumerate(rows):
+            if h == 0:
+                continue
+            if r == root:
+                out[y0:y0 + h].copy_(local[:h])
+            else:
+                ops.append(dist.P2POp(dist.irecv, out[y0:y0 + h], r, group))
+    elif rows[rank][1] > 0:
+        ops.append(dist.P2POp(dist.isend, local[:rows[rank][1]], root, group))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+    return out if rank == root else None
+
+
+def stripe_surface(dev, width, height, rank, world):
+    """the stripe surface of `rank` (one tile row at the bottom of the logical surface for a rank without rows, so that every rank can
+    issue the same calls); returns (Surface, y0, h) with h the rows that count."""
+    import vkvg_b200 as v
+    y0, h = stripe_rows(height, world)[rank]
+    if h == 0:
+        last = ((height - 1) // TILE) * TILE
+        return v.Surface(dev, width, height - last, full_height=height, origin_y=last), height, 0
+    return v.Surface(dev, width, h, full_height=height, origin_y=y0), y0, h
+
+
 def render_striped(dev, width, height, emit, rank, world):
     """GPU path: render this rank's stripe of a width x height surface; returns (Surface, y0, h).  `emit(ctx)` issues the
     drawing calls of the WHOLE scene (every rank replays all of it; geometry outside the stripe is culled by the tile
     binning)."""
     import vkvg_b200 as v
-    y0, h = stripe_rows(height, world)[rank]
-    surf = v.Surface(dev, width, max(h, 1), full_height=height, origin_y=y0)
+    surf, y0, h = stripe_surface(dev, width, height, rank, world)
     ctx = v.Context(surf)
     emit(ctx)
     ctx.flush()
@@ -64,9 +110,14 @@ def render_striped(dev, width, height, emit, rank, world):
 
 
 def gather_surface(surf, y0, h, height, group=None):
-    """GPU path: NCCL all-gather of the stripes rendered by render_striped -> (height, W, 4) uint8 CUDA tensor."""
-    import torch
-    local = torch.empty((max(h, 1), surf.width, 4), dtype=torch.uint8, device="cuda")
-    surf.copy_to_device(local.data_ptr())
-    torch.cuda.synchronize()
-    return gather_stripes(local[:h], height, group)
+    """GPU path: NCCL all-gather of the stripes rendered by render_striped -> (height, W, 4) uint8 CUDA tensor on every rank."""
+    surf.dev.synchronize()
+    return gather_stripes(surf.as_tensor()[:h], height, group)
+
+
+def gather_surface_to_root(surf, height, out=None, root=0, group=None):
+    """GPU path: the stripes rendered on stripe surfaces gathered into one image on `root`, sent straight from the surfaces' memory."""
+    import torch.distributed as dist
+    surf.dev.synchronize()   # the library renders on its own stream
+    h = stripe_rows(height, dist.get_world_size(group))[dist.get_rank(group)][1]
+    return gather_to_root(surf.as_tensor()[:max(h, 0)], height, out=out, root=root, group=group)
