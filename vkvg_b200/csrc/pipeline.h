@@ -13,7 +13,9 @@ void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint
                                uint32_t *sp_first, uint32_t *sp_count, cudaStream_t s);
 
 // ---- job tables: one job = one sub-path of one draw; items = its points ----
-void vkb_launch_job_counts(const uint32_t *job_sp, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, uint32_t *job_n, cudaStream_t s);
+// sp_bbox: user-space box of every sub-path (vkb_launch_sp_bounds), or null for no culling; job_n = 0 for jobs that cannot touch the surface
+struct SurfaceDesc;
+void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, bool any_long, int4 *sp_bbox, cudaStream_t s);
 
 // ---- stroke.cu ----
 struct StrokeArgs {
@@ -47,6 +49,8 @@ struct SurfaceDesc {
     // canvas coordinates (so each canvas holds exactly the pixels it would hold alone) and shifted by whole tiles.  0: no bands
     uint32_t band_tiles;
 };
+void vkb_launch_job_counts(const uint32_t *job_sp, const uint32_t *job_draw, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
+                           const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n, cudaStream_t s);
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
                            vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);

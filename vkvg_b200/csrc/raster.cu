@@ -50,15 +50,122 @@ __device__ __forceinline__ uint32_t find_job(const uint32_t *job_base, uint32_t 
     return lo;
 }
 
-__global__ void job_counts_k(const uint32_t *job_sp, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, uint32_t *job_n) {
+// ---- bounding box of every sub-path in user space, from its ELEMENTS (a cubic lies inside the hull of its control points, an arc inside
+//      the square about its circle): one warp per sub-path, lanes stride the elements.  What job_counts_k culls with. ----
+// (boxes are kept as order-preserving ints so that the long sub-paths can be reduced with atomicMin / atomicMax)
+__device__ __forceinline__ int32_t f2ord(float f) { const int32_t k = __float_as_int(f); return k >= 0 ? k : k ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float   ord2f(int32_t k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+#define VKB_SP_LONG 1024  // sub-paths of more elements are reduced by sp_bounds_long_k (one thread per element) instead of by one warp
+__device__ __forceinline__ void elem_box(uint32_t h, const float *elem_data, float &x0, float &y0, float &x1, float &y1) {
+    const float   *e = elem_data + (h >> VKB_EL_PAYLOAD_SHIFT);
+    const uint32_t t = h & VKB_EL_TYPE_MASK;
+    if (t == VKB_EL_ARC) {
+        const float r = fabsf(e[2]);
+        x0 = fminf(x0, e[0] - r); x1 = fmaxf(x1, e[0] + r); y0 = fminf(y0, e[1] - r); y1 = fmaxf(y1, e[1] + r);
+    } else {
+        const int np = t == VKB_EL_CUBIC ? 4 : 1;
+        for (int k = 0; k < np; k++) { x0 = fminf(x0, e[2 * k]); x1 = fmaxf(x1, e[2 * k]); y0 = fminf(y0, e[2 * k + 1]); y1 = fmaxf(y1, e[2 * k + 1]); }
+    }
+}
+__device__ __forceinline__ void warp_box(float &x0, float &y0, float &x1, float &y1) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+}
+__global__ void __launch_bounds__(256)
+sp_bounds_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, int4 *sp_bbox) {
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= n_sp) return;
+    const vkb_subpath sp = sps[s];
+    float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
+    if (sp.n_elems <= VKB_SP_LONG) {
+        for (uint32_t i = lane; i < sp.n_elems; i += 32) elem_box(elem_hdr[sp.first_elem + i], elem_data, x0, y0, x1, y1);
+        warp_box(x0, y0, x1, y1);
+    }
+    if (lane == 0) sp_bbox[s] = make_int4(f2ord(x0), f2ord(y0), f2ord(x1), f2ord(y1));  // (empty for the long ones: sp_bounds_long_k grows it)
+}
+// the long sub-paths (a 1M-point polyline is ONE sub-path: a single warp would walk it for a millisecond): one thread per element of the
+// batch, the sub-path found by binary search over the (ascending) first elements; warps wholly inside one long sub-path reduce first
+__global__ void __launch_bounds__(256)
+sp_bounds_long_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, int4 *sp_bbox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i & ~31u) >= n_elems) return;
+    const uint32_t e = i < n_elems ? i : n_elems - 1;
+    uint32_t lo = 0, hi = n_sp;  // last sub-path whose first element is <= e
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sps[mid].first_elem <= e) lo = mid; else hi = mid;
+    }
+    const vkb_subpath sp = sps[lo];
+    const bool mine = i < n_elems && sp.n_elems > VKB_SP_LONG && e >= sp.first_elem && e < sp.first_elem + sp.n_elems;
+    if (!__any_sync(0xffffffffu, mine)) return;
+    float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
+    if (mine) elem_box(elem_hdr[e], elem_data, x0, y0, x1, y1);
+    const uint32_t lo0 = __shfl_sync(0xffffffffu, lo, 0);
+    const bool uniform = __all_sync(0xffffffffu, !mine || lo == lo0);
+    if (uniform) warp_box(x0, y0, x1, y1);
+    const uint32_t mm = __ballot_sync(0xffffffffu, mine);
+    if (mine && (!uniform || (threadIdx.x & 31) == (uint32_t)(__ffs((int)mm) - 1))) {
+        // (a stale read only costs a redundant atomic, never a missed one: the box only grows - as in draw_bbox_k)
+        volatile int32_t *vb = (volatile int32_t *)(sp_bbox + lo);
+        int32_t          *b  = (int32_t *)(sp_bbox + lo);
+        if (f2ord(x0) < vb[0]) atomicMin(b, f2ord(x0));
+        if (f2ord(y0) < vb[1]) atomicMin(b + 1, f2ord(y0));
+        if (f2ord(x1) > vb[2]) atomicMax(b + 2, f2ord(x1));
+        if (f2ord(y1) > vb[3]) atomicMax(b + 3, f2ord(y1));
+    }
+}
+void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, bool any_long, int4 *sp_bbox, cudaStream_t s) {
+    if (!n_sp) return;
+    sp_bounds_k<<<vkb_div_up((uint64_t)n_sp * 32, 256), 256, 0, s>>>(sps, n_sp, elem_hdr, elem_data, sp_bbox);
+    VKB_LAUNCHED();
+    if (any_long && n_elems) {
+        sp_bounds_long_k<<<vkb_div_up(n_elems, 256), 256, 0, s>>>(sps, n_sp, elem_hdr, elem_data, n_elems, sp_bbox);
+        VKB_LAUNCHED();
+    }
+}
+// Work items of a job = the points of its sub-path, or none when the sub-path is too short - or when it cannot touch the surface: a
+// sub-path is a closed curve of its own for fills and clips (and a stroke stays within its half width / miter length of the path), so
+// one whose box lies wholly above, below, left or right of the surface leaves every sample's winding as it is.  On a stripe surface
+// (multi-GPU tile rows) that removes most of the scene before anything is tessellated, snapped or binned.
+__global__ void job_counts_k(const uint32_t *job_sp, const uint32_t *job_draw, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
+                             const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
-    uint32_t n = sp_count[job_sp[j]];
-    job_n[j]   = n >= min_points ? n : 0;
+    const uint32_t s = job_sp[j];
+    uint32_t       n = sp_count[s];
+    if (n < min_points) n = 0;
+    if (n && sp_bbox) {
+        const vkb_draw  &dr = draws[job_draw[j]];
+        const vkb_xform &xf = xforms[dr.xform_stroke & 0xFFFF];
+        const float     *m  = xf.mat;
+        const int4       bi = sp_bbox[s];
+        const float4     b  = make_float4(ord2f(bi.x), ord2f(bi.y), ord2f(bi.z), ord2f(bi.w));
+        float            ext = 2.0f;  // (vertex-stage rounding, 1/256 snap, sample offsets: far below one pixel; two for good measure)
+        if (dr.kind == VKB_DRAW_STROKE) {
+            const vkb_stroke &st = strokes[dr.xform_stroke >> 16];
+            ext += fmaxf(st.lhMax, 2.0f * st.hw) * sqrtf(m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+        }
+        float xlo = 3.0e38f, ylo = 3.0e38f, xhi = -3.0e38f, yhi = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float x = (c & 1) ? b.z : b.x, y = (c & 2) ? b.w : b.y;
+            const float px = m[0] * x + m[2] * y + m[4], py = m[1] * x + m[3] * y + m[5];
+            xlo = fminf(xlo, px); xhi = fmaxf(xhi, px); ylo = fminf(ylo, py); yhi = fmaxf(yhi, py);
+        }
+        const float yoff = (float)(xf.band * sd.band_tiles * VKB_TILE) - (float)sd.origin_y;  // canvas of a batch surface / stripe of a taller one
+        ylo += yoff; yhi += yoff;
+        // (comparisons written so that NaN / inf boxes are kept)
+        if (yhi + ext < 0.0f || ylo - ext > (float)sd.height || xhi + ext < 0.0f || xlo - ext > (float)sd.width) n = 0;
+    }
+    job_n[j] = n;
 }
-void vkb_launch_job_counts(const uint32_t *job_sp, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, uint32_t *job_n, cudaStream_t s) {
+void vkb_launch_job_counts(const uint32_t *job_sp, const uint32_t *job_draw, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
+                           const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n, cudaStream_t s) {
     if (!n_jobs) return;
-    job_counts_k<<<vkb_div_up(n_jobs, 256), 256, 0, s>>>(job_sp, n_jobs, sp_count, min_points, job_n);
+    job_counts_k<<<vkb_div_up(n_jobs, 256), 256, 0, s>>>(job_sp, job_draw, n_jobs, sp_count, min_points, sp_bbox, draws, xforms, strokes, sd, job_n);
     VKB_LAUNCHED();
 }
 
@@ -176,15 +283,17 @@ struct NzHit { double key; uint32_t other; float2 p; };
 __device__ __forceinline__ bool nz_hit_less(const NzHit &x, const NzHit &y) { return x.key < y.key || (x.key == y.key && x.other < y.other); }
 // visits the crossings of fill item `item` (edge f.a -> f.b of draw f.d) with every other edge of the draw: visit(other, pair, item_is_first)
 template <class F>
-__device__ __forceinline__ void nz_for_each_crossing(uint32_t item, const FillItem &f, const float2 *pts, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs,
+__device__ __forceinline__ void nz_for_each_crossing(uint32_t item_unused, const FillItem &f, const float2 *pts, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs,
                                                      const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, F &&visit) {
     const uint32_t j0 = draw_first_job[f.d], j1 = f.d + 1 < n_draws ? draw_first_job[f.d + 1] : n_jobs;
+    const uint32_t item = f.first + f.k;
+    (void)item_unused; (void)job_base;
     const float    lox = fminf(f.a.x, f.b.x), hix = fmaxf(f.a.x, f.b.x), loy = fminf(f.a.y, f.b.y), hiy = fmaxf(f.a.y, f.b.y);
     for (uint32_t jj = j0; jj < j1; jj++) {
         const uint32_t s2 = job_sp[jj], n2 = sp_count[s2];
         if (n2 < 3) continue;
-        const float2  *q = pts + sp_first[s2];
-        const uint32_t base = job_base[jj];
+        const uint32_t base = sp_first[s2];   // edges are identified by the index of their first point: the same on every stripe / canvas
+        const float2  *q = pts + base;        // (the work items of a culled sub-path are gone, its edges still split the others)
         float2         c = __ldg(q);
         for (uint32_t k2 = 0; k2 < n2; k2++) {
             const float2   dd = __ldg(q + (k2 + 1 == n2 ? 0 : k2 + 1));

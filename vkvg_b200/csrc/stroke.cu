@@ -371,6 +371,7 @@ __global__ void stroke_patch_closed_k(const vkb_draw *draws, const vkb_stroke *s
     const unsigned long long total   = (unsigned long long)C->n[VKC_VERTS] | ((unsigned long long)C->n[VKC_INDS] << 32);
     uint32_t s = job_sp[j];
     if (!(sps[s].flags & VKB_SP_CLOSED) || strokes[draws[job_draw[j]].xform_stroke >> 16].dash_count != 0 || sp_count[s] < 2) return;
+    if ((j + 1 < n_jobs ? job_base[j + 1] : n_items) == job_base[j]) return;  // a job without work items (culled: it cannot touch the surface)
     unsigned long long a = offsets[job_base[j]];
     uint32_t           e = job_base[j] + sp_count[s];
     unsigned long long b = e < n_items ? offsets[e] : total;
