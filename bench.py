@@ -530,6 +530,7 @@ def measure(env, w, rule, steps, strong_world=None):
     st = dev.time_resident(surf, steps * reps, True, True)
     launches = L.vkvg_b200_launch_count() - l0
     graph_replays = dev.graph_replays() - g0
+    env.barrier()   # (the ranks leave the render loop at different times: the first gather must not be charged for the wait)
     gather_ms[0] = 0.0
     for _ in range(steps if striped else 0):
         gather()

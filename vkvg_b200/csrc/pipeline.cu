@@ -53,7 +53,8 @@ struct vkb_device_impl {
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
     DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped, wscratch, nz_mode, sp_bbox;
-    bool   any_long_sp = false;  // some sub-path has more than 1024 elements (its box is reduced by a kernel of its own)
+    uint32_t n_long_sp = 0, n_long_blocks = 0;  // sub-paths of more than 1024 elements: their boxes are reduced block by block (long_sp: {sub-path, first block})
+    DevBuf   long_sp;
     bool   nz_any = false;  // the batch holds NON_ZERO fills / clips: they go through nz_classify / nz_split (raster.cu)
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
@@ -123,7 +124,7 @@ void vkb_device_close(vkb_device_impl *d) {
     dev_enter(d);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release(); d->nz_mode.release(); d->sp_bbox.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release(); d->long_sp.release(); d->nz_mode.release(); d->sp_bbox.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -324,9 +325,15 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
     d->any_dash = false;
     d->nz_any   = false;
-    d->any_long_sp = false;
-    for (const vkb_subpath &sp : b.subpaths)
-        if (sp.n_elems > 1024) { d->any_long_sp = true; break; }
+    std::vector<uint32_t> long_list;   // {sub-path index, first block of 256 elements} per long sub-path
+    d->n_long_blocks = 0;
+    for (size_t i = 0; i < b.subpaths.size(); i++)
+        if (b.subpaths[i].n_elems > 1024) {
+            long_list.push_back((uint32_t)i);
+            long_list.push_back(d->n_long_blocks);
+            d->n_long_blocks += (b.subpaths[i].n_elems + 255) / 256;
+        }
+    d->n_long_sp = (uint32_t)(long_list.size() / 2);
     for (const vkb_draw &dr : b.draws) {
         if (dr.n_subpaths && ((dr.kind == VKB_DRAW_FILL && (dr.rule_pattern & 0xFF) == VKB_RULE_NON_ZERO) || (dr.kind == VKB_DRAW_CLIP && (dr.rule_pattern & 0xFF) == VKB_RULE_CLIP_NZ))) d->nz_any = true;
         if (dr.kind == VKB_DRAW_CLIP) { d->has_clip_draws = d->has_stencil_ops = true; d->stencil_after = 1; }
@@ -355,6 +362,7 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
         {&d->grads, b.grads.data(), b.grads.size() * sizeof(vkb_gradient), false},
         {&d->dashes, b.dashes.data(), b.dashes.size() * 4, false},
         {&d->surfpats, b.surfpats.data(), b.surfpats.size() * sizeof(vkb_surfpat), false},
+        {&d->long_sp, long_list.data(), long_list.size() * 4, false},
     };
     size_t total = 0;
     for (Src &s : srcs) if (!s.pinned) total += (s.bytes + 255) & ~(size_t)255;
@@ -442,7 +450,7 @@ __global__ void gather_first_items_k(const uint32_t *first_job, const uint32_t *
 }
 // the four edges of a rectangle one tile larger than the surface for every whole-surface draw; they follow the fill edges
 __global__ void extra_rect_edges_k(vkb_edge *edges, uint32_t *edge_draw, const uint32_t *extra_edge_draw, uint32_t n_rects, int32_t W, int32_t H,
-                                   const vkb_counts *C) {
+                                   const vkb_counts *C, int32_t *bbox) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rects || C->overflow) return;
     const uint32_t base = C->n[VKC_FEDGES];  // (before the stroke edges, whose stored number is only known after tri_edges_k)
@@ -453,6 +461,8 @@ __global__ void extra_rect_edges_k(vkb_edge *edges, uint32_t *edge_draw, const u
     e[4 * i + 2] = vkb_edge{x1, y1, x0, y1};
     e[4 * i + 3] = vkb_edge{x0, y1, x0, y0};
     for (int k = 0; k < 4; k++) edge_draw[base + 4 * i + k] = extra_edge_draw[4 * i + k];
+    int32_t *b = bbox + 4 * (size_t)extra_edge_draw[4 * i];   // (one rectangle per whole-surface draw: nobody else writes its box)
+    b[0] = x0; b[1] = y0; b[2] = x1; b[3] = y1;
 }
 
 // ---- commit kernels: one thread turns the raw totals of a producing scan into checked counts (dev_util.cuh: vkb_counts) ----
@@ -532,7 +542,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->draw_ptbase.ensure((size_t)(nd + 1) * 4, st);
     d->draw_rowbase.ensure((size_t)(nd + 1) * 4, st);
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-    vkb_launch_draw_bbox(edges, edraw, cv[VKC_EDGES], C, nd, d->draw_bbox.as<int32_t>(), st);
+    if (!draws) vkb_launch_draw_bbox(edges, edraw, cv[VKC_EDGES], C, nd, d->draw_bbox.as<int32_t>(), st);  // (else grown by the kernels that emitted the edges)
     unsigned long long *dc = d->draw_counts.as<unsigned long long>();
     const bool clip_draws = draws && d->has_clip_draws, stencil_ops = draws && d->has_stencil_ops;
     vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), (clip_draws || sd.band_tiles) ? draws : nullptr, d->xforms.as<vkb_xform>(), nd, sd,
@@ -686,6 +696,9 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     uint64_t *totals = d->totals.as<uint64_t>();
     VKB_CUDA_OK(cudaMemsetAsync(totals, 0, 16 * 8, st));
 
+    d->draw_bbox.ensure((size_t)(d->n_draws + 1) * 16, st);
+    if (d->failed) return;
+    vkb_launch_draw_bbox_init(d->n_draws, d->draw_bbox.as<int32_t>(), st);
     // ---- 1. flatten: count -> scan -> emit ----
     d->elem_cnt.ensure((size_t)(d->n_elems + 1) * 4, st);
     d->sp_first.ensure((size_t)(d->n_sp + 1) * 4, st);
@@ -713,7 +726,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     if (d->failed) return;
     // (geometry captures - vkvg_b200_stroke_geometry, path_edges - report the whole tessellation, on or off the surface)
     const int4 *sp_bbox = (cap && cap->geometry_only) ? nullptr : d->sp_bbox.as<int4>();
-    if (sp_bbox) vkb_launch_sp_bounds(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->any_long_sp, d->sp_bbox.as<int4>(), st);
+    if (sp_bbox) vkb_launch_sp_bounds(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->long_sp.as<uint32_t>(), d->n_long_sp, d->n_long_blocks, d->sp_bbox.as<int4>(), st);
     if (d->n_fjobs) {
         vkb_launch_job_counts(d->fjob_sp.as<uint32_t>(), d->fjob_draw.as<uint32_t>(), d->n_fjobs, d->sp_count.as<uint32_t>(), 3, sp_bbox, d->draws.as<vkb_draw>(),
                               d->xforms.as<vkb_xform>(), d->strokes.as<vkb_stroke>(), sd, d->fjob_base.as<uint32_t>(), st);
@@ -739,7 +752,8 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
                                d->paints.as<vkb_paint>(), d->nz_mode.as<uint8_t>(), st);
         vkb_launch_nz_split(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(),
                             d->fjob_base.as<uint32_t>(), d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->fcnt.as<uint32_t>(), d->n_draws,
-                            d->nz_mode.as<uint8_t>(), cv[VKC_FILL], C, sd, d->edges.as<vkb_edge>(), d->edge_draw.as<uint32_t>(), (uint32_t *)(totals + 11), cv[VKC_FEDGES], st);
+                            d->nz_mode.as<uint8_t>(), cv[VKC_FILL], C, sd, d->edges.as<vkb_edge>(), d->edge_draw.as<uint32_t>(), (uint32_t *)(totals + 11), cv[VKC_FEDGES],
+                            d->draw_bbox.as<int32_t>(), st);
     }
     VKB_EVENT_RECORD(d, d->ev_stage[1]);
 
@@ -784,7 +798,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     uint32_t *edraw = d->edge_draw.as<uint32_t>();
     if (!nz_split)  // (else the fill edges are in place since the end of the flatten stage)
         vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
-                              d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->n_fjobs ? cv[VKC_FILL] : 0, C, sd, edges, edraw, st);
+                              d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->n_fjobs ? cv[VKC_FILL] : 0, C, sd, edges, edraw, d->draw_bbox.as<int32_t>(), st);
     if (cap_items && d->n_sdraws) {
         // first work item of every stroke draw (to map a triangle back to its draw)
         d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
@@ -795,11 +809,11 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         d->snapped.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
         if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         vkb_launch_tri_edges(d->verts.as<float2>(), cv[VKC_VERTS], d->snapped.as<int2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
-                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, d->n_extra, (uint32_t *)(totals + 9), C, st);
+                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, d->n_extra, (uint32_t *)(totals + 9), C, d->draw_bbox.as<int32_t>(), st);
     }
     if (d->n_extra) {
         extra_rect_edges_k<<<vkb_div_up(d->n_extra / 4, 64), 64, 0, st>>>(edges, edraw, d->extra_edge_draw.as<uint32_t>(), d->n_extra / 4, (int32_t)sd.width,
-                                                                         (int32_t)sd.height, C);
+                                                                         (int32_t)sd.height, C, d->draw_bbox.as<int32_t>());
         VKB_LAUNCHED();
     }
     if ((cap && cap->geometry_only) || d->n_draws == 0) return;
@@ -843,6 +857,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     k.tile_ms_allocated = surf->tile_ms.p != nullptr;
     k.alloc_generation = g_vkb_alloc_generation;
     k.fine_mode = (uint32_t)vkb_fine_get_mode();
+    k.pad0 = d->n_long_blocks ^ (d->n_long_sp << 20);
     memcpy(kbuf, &k, sizeof k);
     if (d->graph_exec && !memcmp(kbuf, d->graph_key, sizeof kbuf)) {
         // replay; the host-side effects of enqueue_flush on the surface flags are re-applied by hand

@@ -15,7 +15,8 @@ void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint
 // ---- job tables: one job = one sub-path of one draw; items = its points ----
 // sp_bbox: user-space box of every sub-path (vkb_launch_sp_bounds), or null for no culling; job_n = 0 for jobs that cannot touch the surface
 struct SurfaceDesc;
-void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, bool any_long, int4 *sp_bbox, cudaStream_t s);
+void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, const uint32_t *long_sp, uint32_t n_long, uint32_t n_long_blocks,
+                          int4 *sp_bbox, cudaStream_t s);
 
 // ---- stroke.cu ----
 struct StrokeArgs {
@@ -53,7 +54,7 @@ void vkb_launch_job_counts(const uint32_t *job_sp, const uint32_t *job_draw, uin
                            const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n, cudaStream_t s);
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
-                           vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s);
+                           vkb_edge *edges, uint32_t *edge_draw, int32_t *draw_bbox, cudaStream_t s);
 // NON_ZERO fills / clips as the reference's libtess makes them (raster.cu): nz_mode per draw (0 none, 1 fan fast path -> COUNT rule, 2 edges
 // split at their crossings, 3 too large to split), then the pieces in one pass.  draw_first_job: exclusive scan of fill jobs per draw
 void vkb_launch_nz_classify(const vkb_draw *draws, uint32_t n_draws, const uint32_t *sp_first, const uint32_t *sp_count, const float2 *pts, const vkb_counts *C,
@@ -61,14 +62,14 @@ void vkb_launch_nz_classify(const vkb_draw *draws, uint32_t n_draws, const uint3
 // one pass over the fill items: pieces written where the warp reserved room (*n_out: zeroed device counter), then VKC_FEDGES committed from it
 void vkb_launch_nz_split(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                          uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode,
-                         uint32_t cap_items, vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap_edges, cudaStream_t s);
+                         uint32_t cap_items, vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap_edges, int32_t *draw_bbox, cudaStream_t s);
 // edges / edge_draw: start of the edge arrays (the kernel skips the C->n[VKC_FEDGES] fill edges and the n_extra rectangle edges itself);
 // live: zeroed device counter of the stroke edges stored (cancelled ones are dropped); Cw->n[VKC_EDGES] is set to the stored total
 // snapped: cap_verts int2 of scratch (every stroke vertex goes through the vertex stage once, then the triangles read integers)
 void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
                           const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
                           const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
-                          vkb_counts *Cw, cudaStream_t s);
+                          vkb_counts *Cw, int32_t *draw_bbox, cudaStream_t s);
 
 struct BinBuffers {  // all device pointers
     int32_t  *draw_bbox;    // n_draws x 4 (minx, miny, maxx, maxy), fixed point
@@ -77,6 +78,8 @@ struct BinBuffers {  // all device pointers
     uint32_t *draw_rowbase; // n_draws (+1): first path-tile row of the draw
 };
 // every launcher below sizes its grid for a capacity (cap_*) and reads the count from C (dev_util.cuh: vkb_counts)
+// every kernel that emits edges of a draw grows draw_bbox[draw] itself (after vkb_launch_draw_bbox_init); vkb_launch_draw_bbox is for raw edge lists
+void vkb_launch_draw_bbox_init(uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s);
 void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
                           cudaStream_t s);
 // draws may be null (raw edge lists); a VKB_DRAW_CLIP draw takes the whole surface as its rectangle

@@ -86,43 +86,37 @@ sp_bounds_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, con
     }
     if (lane == 0) sp_bbox[s] = make_int4(f2ord(x0), f2ord(y0), f2ord(x1), f2ord(y1));  // (empty for the long ones: sp_bounds_long_k grows it)
 }
-// the long sub-paths (a 1M-point polyline is ONE sub-path: a single warp would walk it for a millisecond): one thread per element of the
-// batch, the sub-path found by binary search over the (ascending) first elements; warps wholly inside one long sub-path reduce first
+// the long sub-paths (a 1M-point polyline is ONE sub-path: a single warp would walk it for a millisecond): one block per 256 of their
+// elements; long_sp lists {sub-path, its first block} in ascending order (built by the host, which knows the sub-path table)
 __global__ void __launch_bounds__(256)
-sp_bounds_long_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, int4 *sp_bbox) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((i & ~31u) >= n_elems) return;
-    const uint32_t e = i < n_elems ? i : n_elems - 1;
-    uint32_t lo = 0, hi = n_sp;  // last sub-path whose first element is <= e
+sp_bounds_long_k(const vkb_subpath *sps, const uint32_t *long_sp, uint32_t n_long, const uint32_t *elem_hdr, const float *elem_data, int4 *sp_bbox) {
+    uint32_t lo = 0, hi = n_long;  // last long sub-path whose first block is <= this one
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (sps[mid].first_elem <= e) lo = mid; else hi = mid;
+        if (long_sp[2 * mid + 1] <= blockIdx.x) lo = mid; else hi = mid;
     }
-    const vkb_subpath sp = sps[lo];
-    const bool mine = i < n_elems && sp.n_elems > VKB_SP_LONG && e >= sp.first_elem && e < sp.first_elem + sp.n_elems;
-    if (!__any_sync(0xffffffffu, mine)) return;
+    const uint32_t    s  = long_sp[2 * lo];
+    const vkb_subpath sp = sps[s];
+    const uint32_t    i  = (blockIdx.x - long_sp[2 * lo + 1]) * 256 + threadIdx.x;
     float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
-    if (mine) elem_box(elem_hdr[e], elem_data, x0, y0, x1, y1);
-    const uint32_t lo0 = __shfl_sync(0xffffffffu, lo, 0);
-    const bool uniform = __all_sync(0xffffffffu, !mine || lo == lo0);
-    if (uniform) warp_box(x0, y0, x1, y1);
-    const uint32_t mm = __ballot_sync(0xffffffffu, mine);
-    if (mine && (!uniform || (threadIdx.x & 31) == (uint32_t)(__ffs((int)mm) - 1))) {
-        // (a stale read only costs a redundant atomic, never a missed one: the box only grows - as in draw_bbox_k)
-        volatile int32_t *vb = (volatile int32_t *)(sp_bbox + lo);
-        int32_t          *b  = (int32_t *)(sp_bbox + lo);
-        if (f2ord(x0) < vb[0]) atomicMin(b, f2ord(x0));
-        if (f2ord(y0) < vb[1]) atomicMin(b + 1, f2ord(y0));
-        if (f2ord(x1) > vb[2]) atomicMax(b + 2, f2ord(x1));
-        if (f2ord(y1) > vb[3]) atomicMax(b + 3, f2ord(y1));
+    if (i < sp.n_elems) elem_box(elem_hdr[sp.first_elem + i], elem_data, x0, y0, x1, y1);
+    warp_box(x0, y0, x1, y1);
+    __shared__ float red[4][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = x0; red[1][threadIdx.x >> 5] = y0; red[2][threadIdx.x >> 5] = x1; red[3][threadIdx.x >> 5] = y1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { x0 = fminf(x0, red[0][w]); y0 = fminf(y0, red[1][w]); x1 = fmaxf(x1, red[2][w]); y1 = fmaxf(y1, red[3][w]); }
+        int32_t *b = (int32_t *)(sp_bbox + s);
+        atomicMin(b, f2ord(x0)); atomicMin(b + 1, f2ord(y0)); atomicMax(b + 2, f2ord(x1)); atomicMax(b + 3, f2ord(y1));
     }
 }
-void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, bool any_long, int4 *sp_bbox, cudaStream_t s) {
+void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, const uint32_t *long_sp, uint32_t n_long, uint32_t n_long_blocks,
+                          int4 *sp_bbox, cudaStream_t s) {
     if (!n_sp) return;
     sp_bounds_k<<<vkb_div_up((uint64_t)n_sp * 32, 256), 256, 0, s>>>(sps, n_sp, elem_hdr, elem_data, sp_bbox);
     VKB_LAUNCHED();
-    if (any_long && n_elems) {
-        sp_bounds_long_k<<<vkb_div_up(n_elems, 256), 256, 0, s>>>(sps, n_sp, elem_hdr, elem_data, n_elems, sp_bbox);
+    if (n_long && n_long_blocks) {
+        sp_bounds_long_k<<<n_long_blocks, 256, 0, s>>>(sps, long_sp, n_long, elem_hdr, elem_data, sp_bbox);
         VKB_LAUNCHED();
     }
 }
@@ -175,6 +169,38 @@ void vkb_launch_job_counts(const uint32_t *job_sp, const uint32_t *job_draw, uin
 __device__ __forceinline__ bool edge_off_surface(const vkb_edge &e, const SurfaceDesc &sd) {
     return max(e.y0, e.y1) < 0 || min(e.y0, e.y1) > (int32_t)sd.height * 256 || min(e.x0, e.x1) > (int32_t)sd.width * 256;
 }
+// ---- per-draw bounding boxes of the stored edges, grown by the kernels that EMIT the edges (a pass of its own over 25 M edges cost
+//      0.87 ms on C5a).  A warp whose edges all belong to one draw reduces with redux.sync and issues at most four atomics; every tier looks
+//      at the box first: a stale read only costs a redundant atomic, never a missed one (the box only grows). ----
+__device__ __forceinline__ bool edge_degenerate(const vkb_edge &e) { return e.x0 == e.x1 && e.y0 == e.y1; }
+__device__ __forceinline__ void bbox_grow(int32_t *bbox, uint32_t d, int32_t mnx, int32_t mny, int32_t mxx, int32_t mxy) {
+    if (mnx > mxx) return;
+    volatile int32_t *vb = bbox + 4 * (size_t)d;
+    if (mnx < vb[0]) atomicMin(&bbox[4 * (size_t)d], mnx);
+    if (mny < vb[1]) atomicMin(&bbox[4 * (size_t)d + 1], mny);
+    if (mxx > vb[2]) atomicMax(&bbox[4 * (size_t)d + 2], mxx);
+    if (mxy > vb[3]) atomicMax(&bbox[4 * (size_t)d + 3], mxy);
+}
+struct BoxAcc {  // what one thread contributes: the box of the (non-degenerate) edges it stored for draw d
+    int32_t mnx = INT32_MAX, mny = INT32_MAX, mxx = INT32_MIN, mxy = INT32_MIN;
+    __device__ __forceinline__ void add(const vkb_edge &e) {
+        if (edge_degenerate(e)) return;
+        mnx = min(mnx, min(e.x0, e.x1)); mny = min(mny, min(e.y0, e.y1)); mxx = max(mxx, max(e.x0, e.x1)); mxy = max(mxy, max(e.y0, e.y1));
+    }
+};
+// every lane of the warp must call this (lanes without edges pass an empty box and any d)
+__device__ __forceinline__ void bbox_accumulate(int32_t *bbox, uint32_t d, BoxAcc b) {
+    const bool     has = b.mnx <= b.mxx;
+    const uint32_t hm  = __ballot_sync(0xffffffffu, has);
+    if (!hm) return;
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs((int)hm) - 1);
+    if (__all_sync(0xffffffffu, !has || d == d0)) {
+        b.mnx = __reduce_min_sync(0xffffffffu, b.mnx); b.mny = __reduce_min_sync(0xffffffffu, b.mny);
+        b.mxx = __reduce_max_sync(0xffffffffu, b.mxx); b.mxy = __reduce_max_sync(0xffffffffu, b.mxy);
+        if ((threadIdx.x & 31) == 0) bbox_grow(bbox, d0, b.mnx, b.mny, b.mxx, b.mxy);
+    } else if (has) bbox_grow(bbox, d, b.mnx, b.mny, b.mxx, b.mxy);
+}
+
 // ---- fill: one edge per point of every sub-path with > 2 points (the fan of _poly_fill covers exactly the
 //      implicitly closed polygon, internal.c:1617-1642) ----
 struct FillItem {
@@ -201,12 +227,21 @@ __device__ __forceinline__ vkb_edge fill_snap_edge(const vkb_xform &xf, const Su
 }
 __global__ void __launch_bounds__(256)
 fill_edges_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs,
-             const uint32_t *sp_first, const uint32_t *sp_count, const vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw) {
+             const uint32_t *sp_first, const uint32_t *sp_count, const vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, int32_t *bbox) {
     uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (C->overflow || item >= C->n[VKC_FILL]) return;
-    const FillItem f = fill_item(item, pts, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count);
-    edges[item]     = fill_snap_edge(xforms[draws[f.d].xform_stroke & 0xFFFF], sd, f.a, f.b);
-    edge_draw[item] = f.d;
+    if (C->overflow) return;
+    const uint32_t n_items = C->n[VKC_FILL];
+    if ((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) >= n_items) return;  // whole warps leave; a partial warp stays for bbox_accumulate
+    BoxAcc   box;
+    uint32_t d = 0;
+    if (item < n_items) {
+        const FillItem f = fill_item(item, pts, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count);
+        const vkb_edge e = fill_snap_edge(xforms[draws[f.d].xform_stroke & 0xFFFF], sd, f.a, f.b);
+        edges[item]     = e;
+        edge_draw[item] = d = f.d;
+        box.add(e);
+    }
+    bbox_accumulate(bbox, d, box);
 }
 
 // ---- NON_ZERO fills and clips the way the reference's libtess makes them (src/vkvg_context_internal.c:1720-1793, external/glutess) ----
@@ -325,7 +360,7 @@ __device__ __forceinline__ NzHit nz_hit(uint32_t other, const NzPair &pr, bool f
 __global__ void __launch_bounds__(128)
 nz_split_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode,
-           const vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap) {
+           const vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap, int32_t *bbox) {
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_items = C->n[VKC_FILL];
@@ -354,11 +389,14 @@ nz_split_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, co
     uint32_t       base = 0;
     if ((threadIdx.x & 31) == 31 && incl) base = atomicAdd(n_out, incl);
     uint32_t o = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-    if (!live) return;
+    BoxAcc   box;
+    if (!live) { bbox_accumulate(bbox, 0, box); return; }
     const vkb_xform &xf = xforms[draws[f.d].xform_stroke & 0xFFFF];
     float2           prev = f.a;
     auto put = [&](float2 to) {
-        if (o < cap) { edges[o] = fill_snap_edge(xf, sd, prev, to); edge_draw[o] = f.d; }
+        const vkb_edge e = fill_snap_edge(xf, sd, prev, to);
+        if (o < cap) { edges[o] = e; edge_draw[o] = f.d; }
+        box.add(e);
         o++;
         prev = to;
     };
@@ -379,6 +417,7 @@ nz_split_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, co
         }
     }
     put(f.b);
+    bbox_accumulate(bbox, f.d, box);
 }
 __global__ void commit_fedges_k(vkb_counts *C, const uint32_t *n_out) {
     if (C->overflow) return;
@@ -386,9 +425,9 @@ __global__ void commit_fedges_k(vkb_counts *C, const uint32_t *n_out) {
 }
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
-                           vkb_edge *edges, uint32_t *edge_draw, cudaStream_t s) {
+                           vkb_edge *edges, uint32_t *edge_draw, int32_t *draw_bbox, cudaStream_t s) {
     if (!cap_items || !n_jobs) return;
-    fill_edges_k<<<vkb_div_up(cap_items, 256), 256, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, C, sd, edges, edge_draw);
+    fill_edges_k<<<vkb_div_up(cap_items, 256), 256, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, C, sd, edges, edge_draw, draw_bbox);
     VKB_LAUNCHED();
 }
 void vkb_launch_nz_classify(const vkb_draw *draws, uint32_t n_draws, const uint32_t *sp_first, const uint32_t *sp_count, const float2 *pts, const vkb_counts *C,
@@ -399,10 +438,10 @@ void vkb_launch_nz_classify(const vkb_draw *draws, uint32_t n_draws, const uint3
 }
 void vkb_launch_nz_split(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                          uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode,
-                         uint32_t cap_items, vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap_edges, cudaStream_t s) {
+                         uint32_t cap_items, vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap_edges, int32_t *draw_bbox, cudaStream_t s) {
     if (!cap_items || !n_jobs) return;
     nz_split_k<<<vkb_div_up(cap_items, 128), 128, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, draw_first_job, n_draws, nz_mode, C, sd,
-                                                          edges, edge_draw, n_out, cap_edges);
+                                                          edges, edge_draw, n_out, cap_edges, draw_bbox);
     VKB_LAUNCHED();
     commit_fedges_k<<<1, 1, 0, s>>>(C, n_out);
     VKB_LAUNCHED();
@@ -463,7 +502,7 @@ __device__ __forceinline__ int tri_sign(const int2 *snapped, uint32_t n_verts, c
 __global__ void __launch_bounds__(256)
 tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item,
             uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
-            SurfaceDesc sd) {
+            SurfaceDesc sd, int32_t *bbox) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_tris = C->n[VKC_TRIS], n_verts = C->n[VKC_VERTS];
@@ -521,9 +560,11 @@ tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, cons
     uint32_t       base = 0;
     if ((threadIdx.x & 31) == 31 && incl) base = atomicAdd(live, incl);
     uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+    BoxAcc box;
 #pragma unroll
     for (int k = 0; k < 3; k++)
-        if (keep[k]) { edges[pos] = e[k]; edge_draw[pos] = d; pos++; }
+        if (keep[k]) { edges[pos] = e[k]; edge_draw[pos] = d; pos++; box.add(e[k]); }
+    bbox_accumulate(bbox, d, box);
 }
 // the stroke edges that survived are only counted by tri_edges_k: C->n[VKC_EDGES] (so far the upper bound fill + 3 x triangles +
 // rectangles, which sized the buffers) becomes the number actually stored
@@ -534,36 +575,22 @@ __global__ void commit_live_edges_k(vkb_counts *C, const uint32_t *live, uint32_
 void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
                           const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
                           const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
-                          vkb_counts *Cw, cudaStream_t s) {
+                          vkb_counts *Cw, int32_t *draw_bbox, cudaStream_t s) {
     if (!cap_tris || !n_sdraws) return;
     snap_verts_k<<<vkb_div_up(cap_verts, 256), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
     VKB_LAUNCHED();
-    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd);
+    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd, draw_bbox);
     VKB_LAUNCHED();
     commit_live_edges_k<<<1, 1, 0, s>>>(Cw, live, n_extra);
     VKB_LAUNCHED();
 }
 
-// ---- per-draw bounding boxes ----
-__device__ __forceinline__ bool edge_degenerate(const vkb_edge &e) { return e.x0 == e.x1 && e.y0 == e.y1; }
+// ---- per-draw bounding boxes of a RAW edge list (vkb_winding_raw; draws' own edges grow their boxes where they are emitted) ----
 
 __global__ void draw_bbox_init_k(int32_t *bbox, uint32_t n_draws) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_draws) return;
     bbox[4 * i] = INT32_MAX; bbox[4 * i + 1] = INT32_MAX; bbox[4 * i + 2] = INT32_MIN; bbox[4 * i + 3] = INT32_MIN;
-}
-// Three tiers, because millions of edges may aim at the four words of one draw (a long stroke) while elsewhere every few edges
-// belong to another draw (small fills): a block whose edges all belong to one draw reduces in shared memory and issues at most four
-// atomics; else a warp whose edges all belong to one draw reduces with redux.sync; else every edge goes to the atomics on its own.
-// All tiers look at the box first: a stale read only costs a redundant atomic, never a missed one (the box only grows),
-// so after the first few blocks of a long stroke almost none is issued.
-__device__ __forceinline__ void bbox_grow(int32_t *bbox, uint32_t d, int32_t mnx, int32_t mny, int32_t mxx, int32_t mxy) {
-    if (mnx > mxx) return;
-    volatile int32_t *vb = bbox + 4 * (size_t)d;
-    if (mnx < vb[0]) atomicMin(&bbox[4 * (size_t)d], mnx);
-    if (mny < vb[1]) atomicMin(&bbox[4 * (size_t)d + 1], mny);
-    if (mxx > vb[2]) atomicMax(&bbox[4 * (size_t)d + 2], mxx);
-    if (mxy > vb[3]) atomicMax(&bbox[4 * (size_t)d + 3], mxy);
 }
 __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, int32_t *bbox) {
     if (C->overflow) return;
@@ -604,10 +631,14 @@ __global__ void __launch_bounds__(256) draw_bbox_k(const vkb_edge *edges, const 
         bbox_grow(bbox, d, mnx, mny, mxx, mxy);  // (looks first here too: where two long strokes meet, warps mix their edges)
     }
 }
-void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
-                          cudaStream_t s) {
+void vkb_launch_draw_bbox_init(uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s) {
+    if (!n_draws) return;
     draw_bbox_init_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, n_draws);
     VKB_LAUNCHED();
+}
+void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
+                          cudaStream_t s) {
+    vkb_launch_draw_bbox_init(n_draws, draw_bbox, s);
     if (!cap_edges) return;
     draw_bbox_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_bbox);
     VKB_LAUNCHED();
