@@ -145,6 +145,19 @@ enum {
  * corresponding vkvg_* calls one by one (it does exactly that).  Returns the context status. */
 vkvg_public vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *args, uint64_t n_args);
 
+/* The same commands with EXPLICIT argument counts: cmds[i] = op | n_args << 8 (n_args < 2^24), arguments in `args` in order.  Argument
+ * lists as above except that counts are not repeated inside them: POLYLINE x0 y0 x1 y1 ..., SET_DASH offset d0 .. dn-1, SET_SOURCE_LINEAR
+ * x0 y0 x1 y1 (offset r g b a)*, SET_SOURCE_RADIAL cx0 cy0 r0 cx1 cy1 r1 (offset r g b a)*.
+ * vkvg_b200_submit = the calls one by one, then vkvg_flush - but the stream is uploaded as it is and turned into path elements, sub-paths,
+ * draws and side tables BY KERNELS (vkvg_b200/csrc/decode.cu) when it is a regular bulk scene: move_to / line_to / curve_to / polyline /
+ * close_path / new_path, fill / stroke (and _preserve), solid and gradient sources, line and dash state, fill rule, opacity,
+ * identity_matrix / translate / set_canvas, starting from a context with no path under construction, a solid source and no clip.
+ * Everything else (and any stream in which the reference would drop a point or ignore a close_path) is decoded on the host exactly as
+ * vkvg_b200_replay would: same pixels either way.  cmds / args may be reused as soon as the call returns. */
+vkvg_public vkvg_status_t vkvg_b200_submit(VkvgContext ctx, const uint32_t *cmds, uint64_t n_cmds, const float *args, uint64_t n_args);
+vkvg_public void          vkvg_b200_set_submit_decoder(int mode);                          /* 0: device when possible (default), 1: always the host */
+vkvg_public void          vkvg_b200_submit_counts(uint64_t *on_device, uint64_t *on_host); /* streams decoded where, so far (tests, bench) */
+
 /* parity tests: the surface-paint state a draw issued now would use — source x, y, width, height and the inverse matrix
  * (xx yx xy yy x0 y0), i.e. pushConsts.source / pushConsts.matInv of the reference (src/vkvg_context_internal.h:74-81) */
 vkvg_public void vkvg_b200_get_source_push(VkvgContext ctx, float out[10]);

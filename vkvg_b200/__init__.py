@@ -28,6 +28,19 @@ OPS = {name: i + 1 for i, name in enumerate([
     "IDENTITY_MATRIX", "SAVE", "RESTORE", "CLEAR", "SET_OPACITY", "POLYLINE", "FLUSH", "SET_CANVAS", "CLIP", "CLIP_PRESERVE", "RESET_CLIP"])}
 
 
+_FIXED_ARGS = {OPS[k]: n for k, n in dict(
+    MOVE_TO=2, LINE_TO=2, CURVE_TO=6, CLOSE_PATH=0, NEW_PATH=0, ARC=5, ARC_NEGATIVE=5, RECTANGLE=4, FILL=0, FILL_PRESERVE=0, STROKE=0, STROKE_PRESERVE=0,
+    PAINT=0, SET_SOURCE_RGBA=4, SET_LINE_WIDTH=1, SET_LINE_CAP=1, SET_LINE_JOIN=1, SET_MITER_LIMIT=1, SET_FILL_RULE=1, TRANSLATE=2, SCALE=2, ROTATE=1,
+    IDENTITY_MATRIX=0, SAVE=0, RESTORE=0, CLEAR=0, SET_OPACITY=1, FLUSH=0, SET_CANVAS=1, CLIP=0, CLIP_PRESERVE=0, RESET_CLIP=0).items()}
+
+
+def submit_counts():
+    """(streams decoded on the device, streams decoded on the host) by vkvg_b200_submit so far"""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    lib().vkvg_b200_submit_counts(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
 class DeviceCreateInfo(C.Structure):
     """vkvg_device_create_info_t (include/vkvg.h)."""
     _fields_ = [("samples", _u), ("deferredResolve", C.c_bool), ("inst", _p), ("phy", _p), ("vkdev", _p), ("qFamIdx", _u),
@@ -118,6 +131,8 @@ _SIGS = {
     "vkvg_b200_device_ordinal": (_i, [_p]), "vkvg_b200_surface_device_pointer": (_p, [_p]),
     "vkvg_b200_flush_keep": (None, [_p]), "vkvg_b200_replay_resident": (None, [_p, _p, _i]),
     "vkvg_b200_replay": (_i, [_p, _p, C.c_uint64, _p, C.c_uint64]),
+    "vkvg_b200_submit": (_i, [_p, _p, C.c_uint64, _p, C.c_uint64]), "vkvg_b200_set_submit_decoder": (None, [_i]),
+    "vkvg_b200_submit_counts": (None, [_p, _p]),
     "vkvg_b200_time_resident": (_i, [_p, _p, _u, _i, _i, C.POINTER(Stats)]),
     "vkvg_b200_device_set_graphs": (None, [_p, _i]), "vkvg_b200_device_set_stage_timing": (None, [_p, _i]),
     "vkvg_b200_device_graph_replays": (C.c_uint64, [_p]),
@@ -458,6 +473,12 @@ class Context:
         lib().vkvg_b200_flush_capture_winding(self.h, out.ctypes.data)
         return out.view(np.float32) if d.analytic else out   # analytic mode: the area integral A of the last draw
 
+    def submit(self, cmds, args):
+        """vkvg_b200_submit: the stream with explicit argument counts (CommandStream.arrays2), decoded on the device when it can be, then flushed"""
+        cmds = np.ascontiguousarray(cmds, np.uint32)
+        args = np.ascontiguousarray(args, np.float32)
+        return lib().vkvg_b200_submit(self.h, cmds.ctypes.data, len(cmds), args.ctypes.data, len(args))
+
     def replay(self, ops, args):
         ops = np.ascontiguousarray(ops, np.uint8)
         args = np.ascontiguousarray(args, np.float32)
@@ -531,6 +552,38 @@ class CommandStream:
         self.ops.append(OPS["POLYLINE"])
         self.args.append(np.array([len(xy)], np.uint32).view(np.float32)[0])
         self.args.append(xy.ravel())
+
+    def arrays2(self):
+        """(cmds uint32 = op | n_args << 8, args float32): the form vkvg_b200_submit takes - counts in the command words, not in the arguments"""
+        ops, args = self.arrays()
+        cmds = np.zeros(len(ops), np.uint32)
+        out = []
+        k = 0
+        for i, op in enumerate(ops.tolist()):
+            if op == OPS["POLYLINE"]:
+                n = int(args[k:k + 1].view(np.uint32)[0])
+                out.append(args[k + 1:k + 1 + 2 * n])
+                cmds[i] = op | ((2 * n) << 8)
+                k += 1 + 2 * n
+            elif op == OPS["SET_DASH"]:
+                n = int(args[k])
+                out.append(args[k + 1:k + 2 + n])          # offset d0 .. dn-1
+                cmds[i] = op | ((1 + n) << 8)
+                k += 2 + n
+            elif op in (OPS["SET_SOURCE_LINEAR"], OPS["SET_SOURCE_RADIAL"]):
+                np_ = 4 if op == OPS["SET_SOURCE_LINEAR"] else 6
+                ns = int(args[k + np_])
+                out.append(args[k:k + np_])
+                out.append(args[k + np_ + 1:k + np_ + 1 + 5 * ns])
+                cmds[i] = op | ((np_ + 5 * ns) << 8)
+                k += np_ + 1 + 5 * ns
+            else:
+                n = _FIXED_ARGS[op]
+                out.append(args[k:k + n])
+                cmds[i] = op | (n << 8)
+                k += n
+        assert k == len(args)
+        return cmds, (np.concatenate(out) if out else np.zeros(0, np.float32)).astype(np.float32, copy=False)
 
     def arrays(self):
         parts = []

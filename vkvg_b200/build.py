@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvkvg_b200.so")
-SOURCES = ["pipeline.cu", "flatten.cu", "stroke.cu", "raster.cu", "vkvg_api.cpp", "svg.cpp", "png.cpp"]
+SOURCES = ["pipeline.cu", "flatten.cu", "stroke.cu", "raster.cu", "decode.cu", "vkvg_api.cpp", "svg.cpp", "png.cpp"]
 # --fmad=false: tessellation and paint arithmetic must round exactly like the reference's baseline x86-64
 # build (no FMA contraction) and like oracle/ (-ffp-contract=off).
 COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",

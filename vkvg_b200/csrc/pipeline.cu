@@ -53,8 +53,9 @@ struct vkb_device_impl {
     DevBuf draw_bbox, draw_rect, draw_counts, draw_ptbase, draw_rowbase;
     DevBuf pt_count, pt_backdrop, pt_flags, pt_draw, keys, vals, sorted_cnt, pt_slot, cursor, hdr, tile_first, tile_end, tile_edges;
     DevBuf winding, tmp_image, cursor2, flat_cache, pt_owner, row_owner, gprep, long_edges, snapped, wscratch, nz_mode, sp_bbox;
-    uint32_t n_long_sp = 0, n_long_blocks = 0;  // sub-paths of more than 1024 elements: their boxes are reduced block by block (long_sp: {sub-path, first block})
-    DevBuf   long_sp;
+    DevBuf   dc_cmds, dc_args, dc_S, dc_blocksum, dc_lists, dc_small, dc_xfscale;  // command stream decoded on the device (decode.cu)
+    uint32_t *dc_host = nullptr;  // pinned: totals row of the scan, irregular flag, census
+    DevBuf   long_sp;  // per sub-path: the first 256-element block of the long ones (sp_bounds_long_k)
     bool   nz_any = false;  // the batch holds NON_ZERO fills / clips: they go through nz_classify / nz_split (raster.cu)
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
@@ -124,7 +125,9 @@ void vkb_device_close(vkb_device_impl *d) {
     dev_enter(d);
     finish_pending(d);
     cudaStreamSynchronize(d->stream);
-    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release(); d->long_sp.release(); d->nz_mode.release(); d->sp_bbox.release();
+    d->counts.release(); d->cursor2.release(); d->flat_cache.release(); d->pt_owner.release(); d->row_owner.release(); d->gprep.release(); d->surfpats.release(); d->long_edges.release(); d->snapped.release(); d->wscratch.release(); d->long_sp.release();
+    d->dc_cmds.release(); d->dc_args.release(); d->dc_S.release(); d->dc_blocksum.release(); d->dc_lists.release(); d->dc_small.release(); d->dc_xfscale.release();
+    if (d->dc_host) cudaFreeHost(d->dc_host); d->nz_mode.release(); d->sp_bbox.release();
     if (d->counts_host) cudaFreeHost(d->counts_host);
     DevBuf *bufs[] = {&d->sdraw_first_job, &d->xforms, &d->strokes, &d->fcnt, &d->scnt, &d->pcnt, &d->srank, &d->elem_hdr, &d->elem_data, &d->subpaths, &d->draws, &d->grads, &d->dashes, &d->paints, &d->fjob_draw, &d->fjob_sp, &d->sjob_draw,
                       &d->sjob_sp, &d->sdraw_id, &d->sdraw_first_item, &d->extra_edges, &d->extra_edge_draw, &d->elem_cnt, &d->totals, &d->pts, &d->ptflags,
@@ -309,80 +312,9 @@ __global__ void list_draws_k(const vkb_draw *draws, const uint32_t *sbase, const
     }
 }
 
-int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
-    const auto t_begin = std::chrono::steady_clock::now();
-    dev_enter(d);
+// per-draw tables built on the device from d->draws (d->n_draws, n_fjobs, n_sjobs, n_sdraws, n_extra already known to the host)
+static void build_job_tables(vkb_device_impl *d) {
     cudaStream_t st = d->stream;
-    finish_pending(d);
-    // the previous flush may still be reading the staging area
-    VKB_CUDA_OK(cudaStreamSynchronize(st));
-    d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
-    d->n_curves = b.n_curves;
-    d->n_grads  = (uint32_t)b.grads.size();
-    // what the job tables will hold is a function of the recorded draws alone: counted here, no read-back
-    d->has_clip_draws = d->has_stencil_ops = false;
-    d->stencil_after = 0;
-    d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
-    d->any_dash = false;
-    d->nz_any   = false;
-    std::vector<uint32_t> long_list;   // {sub-path index, first block of 256 elements} per long sub-path
-    d->n_long_blocks = 0;
-    for (size_t i = 0; i < b.subpaths.size(); i++)
-        if (b.subpaths[i].n_elems > 1024) {
-            long_list.push_back((uint32_t)i);
-            long_list.push_back(d->n_long_blocks);
-            d->n_long_blocks += (b.subpaths[i].n_elems + 255) / 256;
-        }
-    d->n_long_sp = (uint32_t)(long_list.size() / 2);
-    for (const vkb_draw &dr : b.draws) {
-        if (dr.n_subpaths && ((dr.kind == VKB_DRAW_FILL && (dr.rule_pattern & 0xFF) == VKB_RULE_NON_ZERO) || (dr.kind == VKB_DRAW_CLIP && (dr.rule_pattern & 0xFF) == VKB_RULE_CLIP_NZ))) d->nz_any = true;
-        if (dr.kind == VKB_DRAW_CLIP) { d->has_clip_draws = d->has_stencil_ops = true; d->stencil_after = 1; }
-        else if (dr.kind == VKB_DRAW_STENCIL) {
-            d->has_stencil_ops = true;
-            d->stencil_after   = (dr.rule_pattern & 0xFF) == VKB_RULE_ST_CLEAR ? 2 : 1;
-        }
-        if (dr.kind == VKB_DRAW_FILL || dr.kind == VKB_DRAW_CLIP) d->n_fjobs += dr.n_subpaths;
-        else if (dr.kind == VKB_DRAW_STROKE) {
-            d->n_sjobs += dr.n_subpaths;
-            if (dr.n_subpaths) {
-                d->n_sdraws++;
-                if (b.strokes[dr.xform_stroke >> 16].dash_count) d->any_dash = true;
-            }
-        } else d->n_extra += 4;
-    }
-
-    struct Src { DevBuf *dst; const void *p; size_t bytes; bool pinned; };
-    Src srcs[] = {
-        {&d->elem_hdr, b.elem_hdr.data(), b.elem_hdr.size() * 4, true},   // recorded straight into pinned memory: no staging copy
-        {&d->elem_data, b.elem_data.data(), b.elem_data.size() * 4, true},
-        {&d->subpaths, b.subpaths.data(), b.subpaths.size() * sizeof(vkb_subpath), false},
-        {&d->draws, b.draws.data(), b.draws.size() * sizeof(vkb_draw), false},
-        {&d->xforms, b.xforms.data(), b.xforms.size() * sizeof(vkb_xform), false},
-        {&d->strokes, b.strokes.data(), b.strokes.size() * sizeof(vkb_stroke), false},
-        {&d->grads, b.grads.data(), b.grads.size() * sizeof(vkb_gradient), false},
-        {&d->dashes, b.dashes.data(), b.dashes.size() * 4, false},
-        {&d->surfpats, b.surfpats.data(), b.surfpats.size() * sizeof(vkb_surfpat), false},
-        {&d->long_sp, long_list.data(), long_list.size() * 4, false},
-    };
-    size_t total = 0;
-    for (Src &s : srcs) if (!s.pinned) total += (s.bytes + 255) & ~(size_t)255;
-    uint8_t *stg = stage_reserve(d, total + 256);
-    size_t   off = 0;
-    d->h2d_bytes = 0;
-    for (Src &s : srcs) {
-        s.dst->ensure(s.bytes + 16, st);
-        d->h2d_bytes += s.bytes;
-        if (!s.bytes) continue;
-        if (s.pinned) {
-            VKB_CUDA_OK(cudaMemcpyAsync(s.dst->p, s.p, s.bytes, cudaMemcpyHostToDevice, st));
-        } else {
-            memcpy(stg + off, s.p, s.bytes);
-            VKB_CUDA_OK(cudaMemcpyAsync(s.dst->p, stg + off, s.bytes, cudaMemcpyHostToDevice, st));
-            off += (s.bytes + 255) & ~(size_t)255;
-        }
-    }
-    VKB_CUDA_OK(cudaEventRecord(d->ev_h2d, st));
-
     // ---- job tables on the device ----
     const uint32_t nd = d->n_draws;
     d->paints.ensure((size_t)(nd + 1) * sizeof(vkb_paint), st);
@@ -420,6 +352,73 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
             VKB_LAUNCHED();
         }
     }
+}
+
+int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    dev_enter(d);
+    cudaStream_t st = d->stream;
+    finish_pending(d);
+    // the previous flush may still be reading the staging area
+    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
+    d->n_curves = b.n_curves;
+    d->n_grads  = (uint32_t)b.grads.size();
+    // what the job tables will hold is a function of the recorded draws alone: counted here, no read-back
+    d->has_clip_draws = d->has_stencil_ops = false;
+    d->stencil_after = 0;
+    d->n_fjobs = d->n_sjobs = d->n_sdraws = d->n_extra = 0;
+    d->any_dash = false;
+    d->nz_any   = false;
+    for (const vkb_draw &dr : b.draws) {
+        if (dr.n_subpaths && ((dr.kind == VKB_DRAW_FILL && (dr.rule_pattern & 0xFF) == VKB_RULE_NON_ZERO) || (dr.kind == VKB_DRAW_CLIP && (dr.rule_pattern & 0xFF) == VKB_RULE_CLIP_NZ))) d->nz_any = true;
+        if (dr.kind == VKB_DRAW_CLIP) { d->has_clip_draws = d->has_stencil_ops = true; d->stencil_after = 1; }
+        else if (dr.kind == VKB_DRAW_STENCIL) {
+            d->has_stencil_ops = true;
+            d->stencil_after   = (dr.rule_pattern & 0xFF) == VKB_RULE_ST_CLEAR ? 2 : 1;
+        }
+        if (dr.kind == VKB_DRAW_FILL || dr.kind == VKB_DRAW_CLIP) d->n_fjobs += dr.n_subpaths;
+        else if (dr.kind == VKB_DRAW_STROKE) {
+            d->n_sjobs += dr.n_subpaths;
+            if (dr.n_subpaths) {
+                d->n_sdraws++;
+                if (b.strokes[dr.xform_stroke >> 16].dash_count) d->any_dash = true;
+            }
+        } else d->n_extra += 4;
+    }
+
+    struct Src { DevBuf *dst; const void *p; size_t bytes; bool pinned; };
+    Src srcs[] = {
+        {&d->elem_hdr, b.elem_hdr.data(), b.elem_hdr.size() * 4, true},   // recorded straight into pinned memory: no staging copy
+        {&d->elem_data, b.elem_data.data(), b.elem_data.size() * 4, true},
+        {&d->subpaths, b.subpaths.data(), b.subpaths.size() * sizeof(vkb_subpath), false},
+        {&d->draws, b.draws.data(), b.draws.size() * sizeof(vkb_draw), false},
+        {&d->xforms, b.xforms.data(), b.xforms.size() * sizeof(vkb_xform), false},
+        {&d->strokes, b.strokes.data(), b.strokes.size() * sizeof(vkb_stroke), false},
+        {&d->grads, b.grads.data(), b.grads.size() * sizeof(vkb_gradient), false},
+        {&d->dashes, b.dashes.data(), b.dashes.size() * 4, false},
+        {&d->surfpats, b.surfpats.data(), b.surfpats.size() * sizeof(vkb_surfpat), false},
+    };
+    size_t total = 0;
+    for (Src &s : srcs) if (!s.pinned) total += (s.bytes + 255) & ~(size_t)255;
+    uint8_t *stg = stage_reserve(d, total + 256);
+    size_t   off = 0;
+    d->h2d_bytes = 0;
+    for (Src &s : srcs) {
+        s.dst->ensure(s.bytes + 16, st);
+        d->h2d_bytes += s.bytes;
+        if (!s.bytes) continue;
+        if (s.pinned) {
+            VKB_CUDA_OK(cudaMemcpyAsync(s.dst->p, s.p, s.bytes, cudaMemcpyHostToDevice, st));
+        } else {
+            memcpy(stg + off, s.p, s.bytes);
+            VKB_CUDA_OK(cudaMemcpyAsync(s.dst->p, stg + off, s.bytes, cudaMemcpyHostToDevice, st));
+            off += (s.bytes + 255) & ~(size_t)255;
+        }
+    }
+    VKB_CUDA_OK(cudaEventRecord(d->ev_h2d, st));
+
+    build_job_tables(d);
     d->ms_host_upload = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return g_cuda_failed;
 }
@@ -723,10 +722,11 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     }
     // ---- 2. job sizes: fill jobs need > 2 points, stroke jobs >= 2 (point counts come from the count scan alone) ----
     d->sp_bbox.ensure((size_t)(d->n_sp + 1) * 16, st);
+    d->long_sp.ensure((size_t)(d->n_sp + 1) * 4, st);
     if (d->failed) return;
     // (geometry captures - vkvg_b200_stroke_geometry, path_edges - report the whole tessellation, on or off the surface)
     const int4 *sp_bbox = (cap && cap->geometry_only) ? nullptr : d->sp_bbox.as<int4>();
-    if (sp_bbox) vkb_launch_sp_bounds(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->long_sp.as<uint32_t>(), d->n_long_sp, d->n_long_blocks, d->sp_bbox.as<int4>(), st);
+    if (sp_bbox) vkb_launch_sp_bounds(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->long_sp.as<uint32_t>(), (uint32_t *)(totals + 12), d->scan, d->sp_bbox.as<int4>(), st);
     if (d->n_fjobs) {
         vkb_launch_job_counts(d->fjob_sp.as<uint32_t>(), d->fjob_draw.as<uint32_t>(), d->n_fjobs, d->sp_count.as<uint32_t>(), 3, sp_bbox, d->draws.as<vkb_draw>(),
                               d->xforms.as<vkb_xform>(), d->strokes.as<vkb_stroke>(), sd, d->fjob_base.as<uint32_t>(), st);
@@ -857,7 +857,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     k.tile_ms_allocated = surf->tile_ms.p != nullptr;
     k.alloc_generation = g_vkb_alloc_generation;
     k.fine_mode = (uint32_t)vkb_fine_get_mode();
-    k.pad0 = d->n_long_blocks ^ (d->n_long_sp << 20);
+
     memcpy(kbuf, &k, sizeof k);
     if (d->graph_exec && !memcmp(kbuf, d->graph_key, sizeof kbuf)) {
         // replay; the host-side effects of enqueue_flush on the surface flags are re-applied by hand
@@ -993,6 +993,77 @@ int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const 
     // as the flush returns: wait for that copy (not for the kernels queued behind it)
     VKB_CUDA_OK(cudaEventSynchronize(d->ev_h2d));
     return r | g_cuda_failed;
+}
+
+
+// The packed command stream decoded on the device and rendered: 0 = queued, 1 = device error, 2 = the stream is outside what the device
+// decodes (nothing was touched: the caller decodes it on the host).  cmds / args are host memory (pinned for full speed) and are free
+// again when this returns.
+int vkb_submit_stream(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, const uint32_t *cmds, uint64_t n_cmds, const float *args, uint64_t n_args,
+                      const vkb_decode_init &init, vkb_decode_census *census_out, vkb_stats *stats) {
+    dev_enter(d);
+    cudaStream_t st = d->stream;
+    if (n_cmds == 0 || n_cmds > 0x7fffff00ull || n_args > 0xfffffff0ull) return 2;
+    finish_pending(d);
+    VKB_CUDA_OK(cudaStreamSynchronize(st));  // the previous flush may still be reading the batch these kernels overwrite
+    const uint32_t nc = (uint32_t)n_cmds, na = (uint32_t)n_args, NFIELDS = vkd_n_fields();
+    d->dc_cmds.ensure((size_t)nc * 4 + 16, st);
+    d->dc_args.ensure((size_t)na * 4 + 16, st);
+    d->dc_S.ensure(vkd_scan_words(nc) * 4, st);
+    d->dc_blocksum.ensure(vkd_blocksum_words(nc) * 4 + 16, st);
+    d->dc_small.ensure(1024, st);
+    if (!d->dc_host) VKB_CUDA_OK(cudaHostAlloc((void **)&d->dc_host, 1024, cudaHostAllocDefault));
+    if (d->failed || !d->dc_host) return 1;
+    uint32_t          *irregular = d->dc_small.as<uint32_t>();
+    vkb_decode_census *census    = (vkb_decode_census *)(d->dc_small.as<uint8_t>() + 256);
+    VKB_CUDA_OK(cudaMemsetAsync(d->dc_small.p, 0, 1024, st));
+    VKB_CUDA_OK(cudaMemcpyAsync(d->dc_cmds.p, cmds, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    if (na) VKB_CUDA_OK(cudaMemcpyAsync(d->dc_args.p, args, (size_t)na * 4, cudaMemcpyHostToDevice, st));
+    // ---- phase A: where everything goes ----
+    vkb_launch_decode_scan(d->dc_cmds.as<uint32_t>(), nc, d->dc_S.as<uint32_t>(), d->dc_blocksum.as<uint32_t>(), irregular, st);
+    VKB_CUDA_OK(cudaMemcpyAsync(d->dc_host, d->dc_S.as<uint32_t>() + (size_t)nc * NFIELDS, NFIELDS * 4, cudaMemcpyDeviceToHost, st));
+    VKB_CUDA_OK(cudaMemcpyAsync(d->dc_host + 64, irregular, 4, cudaMemcpyDeviceToHost, st));
+    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    if (d->failed) return 1;
+    if (d->dc_host[64]) { if (getenv("VKVG_B200_DEBUG")) fprintf(stderr, "vkvg_b200_submit: host decoder (scan flags 0x%x)\n", d->dc_host[64]); return 2; }
+    const vkd_totals t = vkd_read_totals(d->dc_host);
+    if (t.n_draws == 0 || t.n_xforms > 65000u || t.n_strokes > 65000u) return 2;
+    // ---- phase B: the batch, written where an upload would have put it ----
+    d->elem_hdr.ensure((size_t)(t.n_elems + 1) * 4 + 16, st);
+    d->elem_data.ensure((size_t)(t.n_data + 4) * 4 + 16, st);
+    d->subpaths.ensure((size_t)(t.n_subpaths + 1) * sizeof(vkb_subpath), st);
+    d->draws.ensure((size_t)(t.n_draws + 1) * sizeof(vkb_draw), st);
+    d->xforms.ensure((size_t)(t.n_xforms + 1) * sizeof(vkb_xform), st);
+    d->dc_xfscale.ensure((size_t)(t.n_xforms + 1) * 8, st);
+    d->strokes.ensure((size_t)(t.n_strokes + 1) * sizeof(vkb_stroke), st);
+    d->grads.ensure((size_t)(t.n_grads + 1) * sizeof(vkb_gradient), st);
+    d->dashes.ensure((size_t)(t.n_dash_floats + 4) * 4, st);
+    d->surfpats.ensure(sizeof(vkb_surfpat), st);
+    d->dc_lists.ensure((size_t)(t.n_list_entries + 4) * 4, st);
+    d->long_sp.ensure((size_t)(t.n_subpaths + 2) * 4, st);   // (scratch until the flush reuses it for the long sub-paths' blocks)
+    if (d->failed) return 1;
+    vkb_launch_decode_emit(d->dc_cmds.as<uint32_t>(), d->dc_args.as<float>(), nc, t, d->dc_S.as<uint32_t>(), d->dc_lists.as<uint32_t>(), irregular, d->elem_hdr.as<uint32_t>(),
+                           d->elem_data.as<float>(), d->subpaths.as<vkb_subpath>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->dc_xfscale.as<float>(),
+                           d->strokes.as<vkb_stroke>(), d->grads.as<vkb_gradient>(), d->dashes.as<float>(), census, d->long_sp.as<uint32_t>(), init, st);
+    VKB_CUDA_OK(cudaMemcpyAsync(d->dc_host + 128, census, sizeof(vkb_decode_census), cudaMemcpyDeviceToHost, st));
+    VKB_CUDA_OK(cudaStreamSynchronize(st));
+    if (d->failed) return 1;
+    const vkb_decode_census c = *(const vkb_decode_census *)(d->dc_host + 128);
+    if (c.irregular) {
+        if (getenv("VKVG_B200_DEBUG")) fprintf(stderr, "vkvg_b200_submit: host decoder (flags 0x%x)\n", c.irregular);
+        d->n_draws = 0; d->n_elems = 0; d->n_sp = 0;
+        return 2;
+    }  // (the resident batch was overwritten: nothing to replay)
+    *census_out = c;
+    // ---- the host's view of the batch, then the job tables and the pipeline as after an upload ----
+    d->n_elems = c.n_elems; d->n_sp = c.n_subpaths; d->n_draws = c.n_draws; d->n_curves = c.n_curves; d->n_grads = c.n_grads;
+    d->n_fjobs = c.n_fjobs; d->n_sjobs = c.n_sjobs; d->n_sdraws = c.n_sdraws; d->n_extra = 0;
+    d->any_dash = c.any_dash != 0; d->nz_any = c.nz_any != 0;
+    d->has_clip_draws = d->has_stencil_ops = false;
+    d->stencil_after = 0;
+    d->h2d_bytes = (uint64_t)nc * 4 + (uint64_t)na * 4;
+    build_job_tables(d);
+    return run_flush(d, surf, samples, nullptr, stats, true) | d->failed;
 }
 
 int vkb_device_ordinal(vkb_device_impl *d) { return d->ordinal; }

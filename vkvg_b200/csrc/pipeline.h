@@ -15,8 +15,8 @@ void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint
 // ---- job tables: one job = one sub-path of one draw; items = its points ----
 // sp_bbox: user-space box of every sub-path (vkb_launch_sp_bounds), or null for no culling; job_n = 0 for jobs that cannot touch the surface
 struct SurfaceDesc;
-void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, const uint32_t *long_sp, uint32_t n_long, uint32_t n_long_blocks,
-                          int4 *sp_bbox, cudaStream_t s);
+void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, uint32_t *long_blocks, uint32_t *n_long_blocks,
+                          ScanScratch &scan, int4 *sp_bbox, cudaStream_t s);
 
 // ---- stroke.cu ----
 struct StrokeArgs {
@@ -36,6 +36,20 @@ struct StrokeArgs {
 void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s);
 void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s);
 void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, float2 *verts, uint32_t *inds, uint32_t *job_inverse, cudaStream_t s);
+
+// ---- decode.cu: the packed command stream decoded on the device (vkvg_b200_submit) ----
+#include "decode_types.h"
+size_t   vkd_scan_words(uint32_t n_cmds);
+size_t   vkd_blocksum_words(uint32_t n_cmds);
+// phase A: the scan over the commands; S row n_cmds = the totals (vkd_read_totals picks out what the host needs to size phase B)
+void vkb_launch_decode_scan(const uint32_t *cmds, uint32_t n_cmds, uint32_t *S, uint32_t *blocksum, uint32_t *irregular, cudaStream_t st);
+struct vkd_totals { uint32_t n_elems, n_data, n_subpaths, n_draws, n_grads, n_dash_floats, n_xforms, n_strokes, n_list_entries; };
+vkd_totals vkd_read_totals(const uint32_t *totals_row_host);
+uint32_t   vkd_n_fields();
+// phase B: the records
+void vkb_launch_decode_emit(const uint32_t *cmds, const float *args, uint32_t n_cmds, const vkd_totals &t, uint32_t *S, uint32_t *lists, uint32_t *irregular,
+                            uint32_t *elem_hdr, float *elem_data, vkb_subpath *subpaths, vkb_draw *draws, vkb_xform *xforms, float *xf_scale, vkb_stroke *strokes,
+                            vkb_gradient *grads, float *dashes, vkb_decode_census *census, uint32_t *sp_null, const vkb_decode_init &in, cudaStream_t st);
 
 // ---- raster.cu ----
 struct SurfaceDesc {

@@ -75,7 +75,7 @@ __device__ __forceinline__ void warp_box(float &x0, float &y0, float &x1, float 
     }
 }
 __global__ void __launch_bounds__(256)
-sp_bounds_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, int4 *sp_bbox) {
+sp_bounds_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, int4 *sp_bbox, uint32_t *long_blocks) {
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= n_sp) return;
     const vkb_subpath sp = sps[s];
@@ -84,20 +84,23 @@ sp_bounds_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, con
         for (uint32_t i = lane; i < sp.n_elems; i += 32) elem_box(elem_hdr[sp.first_elem + i], elem_data, x0, y0, x1, y1);
         warp_box(x0, y0, x1, y1);
     }
-    if (lane == 0) sp_bbox[s] = make_int4(f2ord(x0), f2ord(y0), f2ord(x1), f2ord(y1));  // (empty for the long ones: sp_bounds_long_k grows it)
+    if (lane == 0) {
+        sp_bbox[s]     = make_int4(f2ord(x0), f2ord(y0), f2ord(x1), f2ord(y1));  // (empty for the long ones: sp_bounds_long_k grows it)
+        long_blocks[s] = sp.n_elems > VKB_SP_LONG ? (sp.n_elems + 255) / 256 : 0u;  // blocks of 256 elements the long ones are reduced in (scanned next)
+    }
 }
 // the long sub-paths (a 1M-point polyline is ONE sub-path: a single warp would walk it for a millisecond): one block per 256 of their
-// elements; long_sp lists {sub-path, its first block} in ascending order (built by the host, which knows the sub-path table)
+// elements; first_block = exclusive scan of the per-sub-path block counts (zero for the short ones), *n_blocks its total
 __global__ void __launch_bounds__(256)
-sp_bounds_long_k(const vkb_subpath *sps, const uint32_t *long_sp, uint32_t n_long, const uint32_t *elem_hdr, const float *elem_data, int4 *sp_bbox) {
-    uint32_t lo = 0, hi = n_long;  // last long sub-path whose first block is <= this one
+sp_bounds_long_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *first_block, const uint32_t *n_blocks, const uint32_t *elem_hdr, const float *elem_data, int4 *sp_bbox) {
+    if (blockIdx.x >= *n_blocks) return;   // (the grid is sized for a bound the host can know: elements / 256 + elements / 1024)
+    uint32_t lo = 0, hi = n_sp;  // the last sub-path whose first block is <= this one (short ones have none: they share the next one's)
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (long_sp[2 * mid + 1] <= blockIdx.x) lo = mid; else hi = mid;
+        if (first_block[mid] <= blockIdx.x) lo = mid; else hi = mid;
     }
-    const uint32_t    s  = long_sp[2 * lo];
-    const vkb_subpath sp = sps[s];
-    const uint32_t    i  = (blockIdx.x - long_sp[2 * lo + 1]) * 256 + threadIdx.x;
+    const vkb_subpath sp = sps[lo];
+    const uint32_t    i  = (blockIdx.x - first_block[lo]) * 256 + threadIdx.x;
     float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
     if (i < sp.n_elems) elem_box(elem_hdr[sp.first_elem + i], elem_data, x0, y0, x1, y1);
     warp_box(x0, y0, x1, y1);
@@ -106,17 +109,18 @@ sp_bounds_long_k(const vkb_subpath *sps, const uint32_t *long_sp, uint32_t n_lon
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; w++) { x0 = fminf(x0, red[0][w]); y0 = fminf(y0, red[1][w]); x1 = fmaxf(x1, red[2][w]); y1 = fmaxf(y1, red[3][w]); }
-        int32_t *b = (int32_t *)(sp_bbox + s);
+        int32_t *b = (int32_t *)(sp_bbox + lo);
         atomicMin(b, f2ord(x0)); atomicMin(b + 1, f2ord(y0)); atomicMax(b + 2, f2ord(x1)); atomicMax(b + 3, f2ord(y1));
     }
 }
-void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, const uint32_t *long_sp, uint32_t n_long, uint32_t n_long_blocks,
-                          int4 *sp_bbox, cudaStream_t s) {
+void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, uint32_t *long_blocks, uint32_t *n_long_blocks,
+                          ScanScratch &scan, int4 *sp_bbox, cudaStream_t s) {
     if (!n_sp) return;
-    sp_bounds_k<<<vkb_div_up((uint64_t)n_sp * 32, 256), 256, 0, s>>>(sps, n_sp, elem_hdr, elem_data, sp_bbox);
+    sp_bounds_k<<<vkb_div_up((uint64_t)n_sp * 32, 256), 256, 0, s>>>(sps, n_sp, elem_hdr, elem_data, sp_bbox, long_blocks);
     VKB_LAUNCHED();
-    if (n_long && n_long_blocks) {
-        sp_bounds_long_k<<<n_long_blocks, 256, 0, s>>>(sps, long_sp, n_long, elem_hdr, elem_data, sp_bbox);
+    if (n_elems > VKB_SP_LONG) {   // (no sub-path can be long otherwise)
+        vkb_exclusive_scan<uint32_t, uint32_t>(long_blocks, long_blocks, n_sp, n_long_blocks, scan, s);
+        sp_bounds_long_k<<<n_elems / 256 + n_elems / VKB_SP_LONG + 1, 256, 0, s>>>(sps, n_sp, long_blocks, n_long_blocks, elem_hdr, elem_data, sp_bbox);
         VKB_LAUNCHED();
     }
 }

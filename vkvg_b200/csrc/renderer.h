@@ -5,6 +5,7 @@
 #include <string.h>
 #include <vector>
 #include "vkb_types.h"
+#include "decode_types.h"
 
 // Growable array of plain data that never value-initialises (std::vector::resize would write every element of a
 // 1M-point polyline twice) and keeps its capacity across clear().
@@ -118,4 +119,7 @@ int vkb_render(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, const 
 // upload only (bench: inputs resident in HBM); then vkb_render_resident re-runs the pipeline on that batch
 int vkb_upload(vkb_device_impl *d, const vkb_batch &b);
 int vkb_render_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, vkb_capture *cap, vkb_stats *stats);
+// the packed command stream decoded on the device (decode.cu) and rendered: 0 queued, 1 device error, 2 not decodable on the device (nothing touched)
+int vkb_submit_stream(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, const uint32_t *cmds, uint64_t n_cmds, const float *args, uint64_t n_args,
+                      const vkb_decode_init &init, vkb_decode_census *census_out, vkb_stats *stats);
 int vkb_time_resident(vkb_device_impl *d, vkb_surface_impl *s, uint32_t samples, uint32_t steps, bool clear_first, bool flush_l2, vkb_stats *sum);

@@ -15,6 +15,7 @@ enum : uint32_t {
     VKB_EL_POINT  = 0,
     VKB_EL_CUBIC  = 1,
     VKB_EL_ARC    = 2,
+    VKB_EL_NONE   = 3,    // no points (a curve_to the reference skips, written by the device-side stream decoder: its slot stays)
     VKB_EL_TYPE_MASK = 0x3,
     VKB_EL_CURVED = 0x4,  // points of this element belong to a curved segment (PATH_HAS_CURVES_BIT on the segment)
     VKB_EL_PAYLOAD_SHIFT = 3,

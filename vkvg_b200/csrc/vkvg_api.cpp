@@ -6,6 +6,7 @@
 #include "../../include/vkvg.h"
 #include "../../include/vkvg_b200.h"
 #include "renderer.h"
+#include "decode_types.h"
 #include <float.h>
 #include <math.h>
 #include <atomic>
@@ -1687,6 +1688,149 @@ vkvg_status_t vkvg_b200_time_resident(VkvgDevice dev, VkvgSurface surf, uint32_t
     }
     if (sum) memcpy(sum, &st, sizeof st);
     return VKVG_STATUS_SUCCESS;
+}
+
+
+// ---- the packed command stream with explicit argument counts, decoded on the device when it can be (decode.cu) ----
+// the same stream decoded on the host: the calls one by one (the fallback of vkvg_b200_submit, and the definition of what it means)
+static vkvg_status_t replay_cmds(VkvgContext ctx, const uint32_t *cmds, uint64_t n_cmds, const float *a, uint64_t n_args) {
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n_cmds; i++) {
+        const uint32_t op = cmds[i] & 0xFF, na = cmds[i] >> 8;
+        if ((uint64_t)na > n_args - k) return VKVG_STATUS_INVALID_INDEX;
+        const float *p = a + k;
+        auto need = [&](uint32_t n) { return na == n; };
+        bool ok = true;
+        switch (op) {
+        case VKVG_B200_OP_MOVE_TO: if ((ok = need(2))) vkvg_move_to(ctx, p[0], p[1]); break;
+        case VKVG_B200_OP_LINE_TO: if ((ok = need(2))) vkvg_line_to(ctx, p[0], p[1]); break;
+        case VKVG_B200_OP_CURVE_TO: if ((ok = need(6))) vkvg_curve_to(ctx, p[0], p[1], p[2], p[3], p[4], p[5]); break;
+        case VKVG_B200_OP_CLOSE_PATH: vkvg_close_path(ctx); break;
+        case VKVG_B200_OP_NEW_PATH: vkvg_new_path(ctx); break;
+        case VKVG_B200_OP_ARC: if ((ok = need(5))) vkvg_arc(ctx, p[0], p[1], p[2], p[3], p[4]); break;
+        case VKVG_B200_OP_ARC_NEGATIVE: if ((ok = need(5))) vkvg_arc_negative(ctx, p[0], p[1], p[2], p[3], p[4]); break;
+        case VKVG_B200_OP_RECTANGLE: if ((ok = need(4))) vkvg_rectangle(ctx, p[0], p[1], p[2], p[3]); break;
+        case VKVG_B200_OP_FILL: vkvg_fill(ctx); break;
+        case VKVG_B200_OP_FILL_PRESERVE: vkvg_fill_preserve(ctx); break;
+        case VKVG_B200_OP_STROKE: vkvg_stroke(ctx); break;
+        case VKVG_B200_OP_STROKE_PRESERVE: vkvg_stroke_preserve(ctx); break;
+        case VKVG_B200_OP_PAINT: vkvg_paint(ctx); break;
+        case VKVG_B200_OP_SET_SOURCE_RGBA: if ((ok = need(4))) vkvg_set_source_rgba(ctx, p[0], p[1], p[2], p[3]); break;
+        case VKVG_B200_OP_SET_LINE_WIDTH: if ((ok = need(1))) vkvg_set_line_width(ctx, p[0]); break;
+        case VKVG_B200_OP_SET_LINE_CAP: if ((ok = need(1) && p[0] >= 0.0f && p[0] <= 2.0f)) vkvg_set_line_cap(ctx, (vkvg_line_cap_t)(int)p[0]); break;
+        case VKVG_B200_OP_SET_LINE_JOIN: if ((ok = need(1) && p[0] >= 0.0f && p[0] <= 2.0f)) vkvg_set_line_join(ctx, (vkvg_line_join_t)(int)p[0]); break;
+        case VKVG_B200_OP_SET_MITER_LIMIT: if ((ok = need(1))) vkvg_set_miter_limit(ctx, p[0]); break;
+        case VKVG_B200_OP_SET_FILL_RULE: if ((ok = need(1) && p[0] >= 0.0f && p[0] <= 1.0f)) vkvg_set_fill_rule(ctx, (vkvg_fill_rule_t)(int)p[0]); break;
+        case VKVG_B200_OP_SET_DASH: if ((ok = na >= 1)) vkvg_set_dash(ctx, p + 1, na - 1, p[0]); break;   // offset d0 .. dn-1
+        case VKVG_B200_OP_SET_SOURCE_LINEAR:
+        case VKVG_B200_OP_SET_SOURCE_RADIAL: {
+            const uint32_t np = op == VKVG_B200_OP_SET_SOURCE_LINEAR ? 4 : 6;
+            if (!(ok = na >= np && (na - np) % 5 == 0 && (na - np) / 5 <= 16)) break;
+            VkvgPattern pat = np == 4 ? vkvg_pattern_create_linear(p[0], p[1], p[2], p[3]) : vkvg_pattern_create_radial(p[0], p[1], p[2], p[3], p[4], p[5]);
+            for (uint32_t j = 0; j < (na - np) / 5; j++) vkvg_pattern_add_color_stop(pat, p[np + 5 * j], p[np + 5 * j + 1], p[np + 5 * j + 2], p[np + 5 * j + 3], p[np + 5 * j + 4]);
+            vkvg_set_source(ctx, pat);
+            vkvg_pattern_destroy(pat);
+            break;
+        }
+        case VKVG_B200_OP_TRANSLATE: if ((ok = need(2))) vkvg_translate(ctx, p[0], p[1]); break;
+        case VKVG_B200_OP_SCALE: if ((ok = need(2))) vkvg_scale(ctx, p[0], p[1]); break;
+        case VKVG_B200_OP_ROTATE: if ((ok = need(1))) vkvg_rotate(ctx, p[0]); break;
+        case VKVG_B200_OP_IDENTITY_MATRIX: vkvg_identity_matrix(ctx); break;
+        case VKVG_B200_OP_SAVE: vkvg_save(ctx); break;
+        case VKVG_B200_OP_RESTORE: vkvg_restore(ctx); break;
+        case VKVG_B200_OP_CLEAR: vkvg_clear(ctx); break;
+        case VKVG_B200_OP_SET_OPACITY: if ((ok = need(1))) vkvg_set_opacity(ctx, p[0]); break;
+        case VKVG_B200_OP_POLYLINE: if ((ok = na >= 2 && (na & 1) == 0)) add_polyline(ctx, p, na / 2); break;   // x0 y0 x1 y1 ...
+        case VKVG_B200_OP_FLUSH: vkvg_flush(ctx); break;
+        case VKVG_B200_OP_SET_CANVAS: if ((ok = need(1) && p[0] >= 0.0f && p[0] <= 16777216.0f)) ok = vkvg_b200_set_canvas(ctx, (uint32_t)p[0]) == VKVG_STATUS_SUCCESS; break;
+        case VKVG_B200_OP_CLIP: vkvg_clip(ctx); break;
+        case VKVG_B200_OP_CLIP_PRESERVE: vkvg_clip_preserve(ctx); break;
+        case VKVG_B200_OP_RESET_CLIP: vkvg_reset_clip(ctx); break;
+        default: return VKVG_STATUS_INVALID_STATUS;
+        }
+        if (!ok) return VKVG_STATUS_INVALID_INDEX;
+        if (ctx->status) return ctx->status;
+        k += na;
+    }
+    return ctx->status;
+}
+static int g_submit_mode = [] {  // VKVG_B200_SUBMIT=host forces the host decoder (A/B timing, tests)
+    const char *e = getenv("VKVG_B200_SUBMIT");
+    return (e && e[0] == 'h') ? 1 : 0;
+}();
+void vkvg_b200_set_submit_decoder(int mode) { g_submit_mode = mode == 1 ? 1 : 0; }
+static std::atomic<unsigned long long> g_submit_device{0}, g_submit_host{0};
+void vkvg_b200_submit_counts(uint64_t *on_device, uint64_t *on_host) {
+    if (on_device) *on_device = g_submit_device.load();
+    if (on_host) *on_host = g_submit_host.load();
+}
+vkvg_status_t vkvg_b200_submit(VkvgContext ctx, const uint32_t *cmds, uint64_t n_cmds, const float *args, uint64_t n_args) {
+    if (vkvg_status(ctx)) return vkvg_status(ctx);
+    if (!cmds || (!args && n_args)) return VKVG_STATUS_NULL_POINTER;
+    // the device decodes a stream that starts from a plain state: no path under construction, a solid source, no clip, no recording
+    bool device_ok = g_submit_mode == 0 && !ctx->recording && ctx->sp_points == 0 && ctx->path_first_sp == ctx->batch.subpaths.size() && ctx->patType == VKB_PAT_SOLID &&
+                     ctx->curClipState == CLIP_STATE_NONE && ctx->saved.empty() && ctx->dashes.size() <= VKB_MAX_DASHES && n_cmds > 0;
+    if (device_ok) {
+        if (!ctx->batch.draws.empty()) flush_impl(ctx, nullptr, false);  // draws recorded call by call come first
+        VkvgDevice dev = ctx->dev;
+        vkb_decode_init in;
+        memset(&in, 0, sizeof in);
+        memcpy(in.mat, &ctx->mat, sizeof in.mat);
+        in.band = ctx->canvas; in.color = ctx->curColor; in.rule = ctx->fillRule == VKVG_FILL_RULE_EVEN_ODD ? 0u : 1u;
+        in.cap = ctx->cap; in.join = ctx->join;
+        in.bop = ctx->op == VKVG_OPERATOR_CLEAR ? VKB_OP_CLEAR : (ctx->op == VKVG_OPERATOR_DIFFERENCE ? VKB_OP_SUB : VKB_OP_OVER);
+        in.dash_count = (uint32_t)ctx->dashes.size(); in.dash_offset = ctx->dashOffset;
+        for (size_t q = 0; q < ctx->dashes.size(); q++) in.dashes[q] = ctx->dashes[q];
+        in.lw = ctx->lineWidth; in.miter = ctx->miterLimit; in.opacity = ctx->opacity;
+        vkb_decode_census c;
+        int r;
+        {
+            std::lock_guard<std::mutex> lk(dev->mtx);
+            if (ctx->clear_pending) { vkb_surface_clear(ctx->pSurf->impl); ctx->clear_pending = false; }
+            vkb_stats st;
+            r = vkb_submit_stream(dev->impl, ctx->pSurf->impl, dev->raster_samples(), cmds, n_cmds, args, n_args, in, &c, dev->profiling ? &st : nullptr);
+            if (r == 0 && dev->profiling) dev->last = st;
+        }
+        if (r == 1) { ctx->status = VKVG_STATUS_DEVICE_ERROR; dev->status = VKVG_STATUS_DEVICE_ERROR; return ctx->status; }
+        if (r == 0) {
+            g_submit_device++;
+            // leave the context in the state the last setters of the stream put it in (their arguments are in the caller's arrays)
+            auto arg = [&](int q) { return args + c.last_setter_arg[q]; };
+            if (c.last_setter[0] >= 0) {
+                const uint32_t op = cmds[c.last_setter[0]] & 0xFF, na = cmds[c.last_setter[0]] >> 8;
+                const float   *p  = arg(0);
+                if (op == VKVG_B200_OP_SET_SOURCE_RGBA) vkvg_set_source_rgba(ctx, p[0], p[1], p[2], p[3]);
+                else {
+                    // (through the CTM the setter saw: final_mat is only right when no CTM command follows it; replay the setter under the final CTM instead
+                    //  would differ, so the gradient is rebuilt with the host's own code under the matrix in force at the setter - the final one if none follows)
+                    const uint32_t np = op == VKVG_B200_OP_SET_SOURCE_LINEAR ? 4 : 6;
+                    VkvgPattern pat = np == 4 ? vkvg_pattern_create_linear(p[0], p[1], p[2], p[3]) : vkvg_pattern_create_radial(p[0], p[1], p[2], p[3], p[4], p[5]);
+                    for (uint32_t j = 0; j < (na - np) / 5; j++) vkvg_pattern_add_color_stop(pat, p[np + 5 * j], p[np + 5 * j + 1], p[np + 5 * j + 2], p[np + 5 * j + 3], p[np + 5 * j + 4]);
+                    memcpy(&ctx->mat, c.final_mat, sizeof c.final_mat);
+                    vkvg_set_source(ctx, pat);
+                    vkvg_pattern_destroy(pat);
+                }
+            }
+            if (c.last_setter[1] >= 0) ctx->fillRule = (int)arg(1)[0] == 0 ? VKVG_FILL_RULE_EVEN_ODD : VKVG_FILL_RULE_NON_ZERO;
+            if (c.last_setter[2] >= 0) ctx->lineWidth = arg(2)[0];
+            if (c.last_setter[3] >= 0) ctx->cap = (vkvg_line_cap_t)(int)arg(3)[0];
+            if (c.last_setter[4] >= 0) ctx->join = (vkvg_line_join_t)(int)arg(4)[0];
+            if (c.last_setter[5] >= 0) ctx->miterLimit = arg(5)[0];
+            if (c.last_setter[6] >= 0) { const uint32_t na = cmds[c.last_setter[6]] >> 8; vkvg_set_dash(ctx, arg(6) + 1, na - 1, arg(6)[0]); }
+            if (c.last_setter[7] >= 0) ctx->opacity = arg(7)[0];
+            memcpy(&ctx->mat, c.final_mat, sizeof c.final_mat);
+            set_mat_inv(ctx);
+            ctx->canvas = c.final_band;
+            clear_path(ctx);
+            return ctx->status;
+        }
+        // r == 2: not a stream the device decodes
+    }
+    g_submit_host++;
+    const vkvg_status_t st = replay_cmds(ctx, cmds, n_cmds, args, n_args);
+    if (st) return st;
+    vkvg_flush(ctx);
+    return ctx->status;
 }
 
 vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, uint64_t n_ops, const float *a, uint64_t n_args) {
