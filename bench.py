@@ -462,11 +462,12 @@ def measure(env, w, rule, steps, strong_world=None):
         direct = LayerSource(ctx, layer)
     else:
         emit(cs)
-    ops_np, args_np = cs.arrays()
-    # host buffers of the end-to-end path live in pinned memory
-    ops_t = torch.from_numpy(ops_np.copy()).pin_memory()
+    ops_np, args_np = cs.arrays2() if direct is None else (np.zeros(0, np.uint32), np.zeros(0, np.float32))
+    # host buffers of the end-to-end path live in pinned memory: the command stream (cmds = op | n_args << 8, args) and the image
+    ops_t = torch.from_numpy(ops_np.view(np.int32).copy()).pin_memory()
     args_t = torch.from_numpy(args_np.copy()).pin_memory()
     out_t = torch.empty((surf.height, size, 4), dtype=torch.uint8).pin_memory()
+    on_dev0 = v.submit_counts()
     gather_ms = [0.0]
     full_t = [None]
 
@@ -490,11 +491,15 @@ def measure(env, w, rule, steps, strong_world=None):
             ctx.identity_matrix()
             ctx.set_opacity(1.0)
             st = 0
+            t1 = time.perf_counter()
+            L.vkvg_flush(ctx.h)
         else:
-            st = L.vkvg_b200_replay(ctx.h, ops_t.data_ptr(), ops_t.numel(), args_t.data_ptr(), args_t.numel())
+            # one call: the stream is uploaded and decoded into the batch by kernels (decode.cu), the pipeline is queued behind it - a CUDA
+            # graph replay once the frame structure repeats - and the call returns; finished bands of the image are copied to out_t on a
+            # second stream while later bands render (vkvg_b200_surface_set_readback)
+            st = L.vkvg_b200_submit(ctx.h, ops_t.data_ptr(), ops_t.numel(), args_t.data_ptr(), args_t.numel())
+            t1 = time.perf_counter()
         assert st == 0, st
-        t1 = time.perf_counter()
-        L.vkvg_flush(ctx.h)   # queues the upload and the whole pipeline (a CUDA graph replay once the frame structure repeats) and returns
         t2 = time.perf_counter()
         gather()
         assert L.vkvg_b200_surface_read_premultiplied(surf.h, out_t.data_ptr()) == 0
@@ -507,10 +512,13 @@ def measure(env, w, rule, steps, strong_world=None):
         for _ in range(reps):
             e2e_one()
 
+    if not striped:
+        L.vkvg_b200_surface_set_readback(surf.h, out_t.data_ptr())
     for _ in range(3):
         e2e_one()
     frame = out_t.numpy().copy()
     checksum = int(frame.view(np.uint32).sum(dtype=np.uint64))
+    L.vkvg_b200_surface_set_readback(surf.h, None)   # (the device-timed runs below render only)
     dev.set_profiling(True)
     dev.set_stage_timing(True)
     dev.time_resident(surf, 2, True, True)   # warm the resident path (buffers sized, L2 scratch allocated)
@@ -539,6 +547,8 @@ def measure(env, w, rule, steps, strong_world=None):
     gather_step_ms = env.max_over_ranks(gather_ms[0] / steps)
     # ---- end to end through the C ABI with host buffers ----
     dev.set_profiling(False)   # flushes return as soon as the work is queued; the read-back waits for it
+    if not striped:
+        L.vkvg_b200_surface_set_readback(surf.h, out_t.data_ptr())
     for _ in range(2):
         e2e_step()
     env.barrier()
@@ -592,9 +602,10 @@ def measure(env, w, rule, steps, strong_world=None):
                    "l2": "256 MiB scratch overwritten between timed steps",
                    "launch": ("one CUDA graph replay per flush (%d of %d flushes)" % (graph_replays, steps * reps)) if use_graph else "plain kernel launches",
                    **info, "n_edges": int(n_edges), "n_tile_edges": int(st["n_tile_edges"]), "n_points": int(st["n_points"]), "n_path_tiles": int(st["n_nonempty"])},
-        "e2e": {"value": scale_units * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(ops_t.numel() + 4 * args_t.numel()) * reps,
+        "e2e": {"value": scale_units * units / e2e_s, "unit": unit, "h2d_bytes_per_step": int(4 * ops_t.numel() + 4 * args_t.numel()) * reps,
+                "decoded_on": "device" if v.submit_counts()[0] > on_dev0[0] and v.submit_counts()[1] == on_dev0[1] else ("host" if direct is None else "host (API calls)"),
                 "d2h_bytes_per_step": int(out_t.numel()) * reps, "ms_per_step": e2e_s * 1e3,
-                "host_record_ms": parts[0] / steps * 1e3, "upload_render_ms": parts[1] / steps * 1e3,
+                "host_record_ms": parts[0] / steps * 1e3, "upload_render_ms": parts[1] / steps * 1e3,   # submit call (upload + decode + queue) | explicit flush (call-by-call workloads only)
                 "readback_ms": parts[2] / steps * 1e3, "h2d_bytes_wire": int(st["h2d_bytes"])},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": fine_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -631,7 +642,7 @@ def slim(rec):
     out["sharding"] = rec["config"]["sharding"]
     out["n_edges"], out["n_path_tiles"] = rec["config"]["n_edges"], rec["config"]["n_path_tiles"]
     out["roofline"] = {k: rec["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "algorithmic_bytes", "kernel_ms", "whole_step_frac")}
-    out["e2e"] = {k: rec["e2e"][k] for k in ("value", "unit", "ms_per_step", "host_record_ms", "upload_render_ms", "readback_ms", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+    out["e2e"] = {k: rec["e2e"][k] for k in ("value", "unit", "ms_per_step", "host_record_ms", "upload_render_ms", "readback_ms", "h2d_bytes_per_step", "d2h_bytes_per_step", "decoded_on")}
     return out
 
 

@@ -65,6 +65,12 @@ vkvg_public vkvg_status_t vkvg_b200_winding(VkvgDevice dev, const int32_t *edges
 
 /* premultiplied RGBA8 pixels exactly as stored (vkvg_surface_write_to_memory un-premultiplies) */
 vkvg_public vkvg_status_t vkvg_b200_surface_read_premultiplied(VkvgSurface surf, unsigned char *rgba);
+/* Read-back overlapped with rendering: host_rgba (width * height * 4 bytes, pinned memory for the copies to be asynchronous) becomes the
+ * place every later flush onto surf ALSO delivers the premultiplied image to - the fine pass then runs in bands of tile rows and each
+ * finished band is copied on a second stream while the next ones render.  vkvg_b200_surface_read_premultiplied(surf, host_rgba) then only
+ * waits for the last band instead of copying the whole image after the whole frame.  NULL switches it off; the memory must stay valid
+ * until then. */
+vkvg_public vkvg_status_t vkvg_b200_surface_set_readback(VkvgSurface surf, unsigned char *host_rgba);
 
 /* ---- 2. measurement ------------------------------------------------------------------------------------ */
 typedef struct {

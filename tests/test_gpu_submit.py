@@ -115,3 +115,43 @@ def test_irregular_streams_fall_back_to_the_host(dev4, case):
     b, _ = _render(dev4, 256, cs, 1, post=post)
     assert where == (0, 1), (case, where)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("size", [512, 2048])
+def test_read_back_target_gets_the_same_image(dev4, size):
+    """vkvg_b200_surface_set_readback: the fine pass runs in bands of tile rows, each copied out while the next renders; the registered
+    host buffer then holds exactly what an ordinary read-back returns - over several frames (graph replays included) and a clear."""
+    import ctypes as C
+    emit, _, _ = bench.build_scene("c2", 3, "nz", n_limit=2500)
+    cs = v.CommandStream()
+    emit(cs)
+    cmds, args = cs.arrays2()
+    L = v.lib()
+    s = v.Surface(dev4, size, size)
+    c = v.Context(s)
+    assert c.submit(cmds, args) == 0
+    want = s.pixels()
+    target = np.zeros((size, size, 4), np.uint8)
+    assert L.vkvg_b200_surface_set_readback(s.h, target.ctypes.data) == 0
+    for frame in range(5):
+        target[:] = 7
+        c.clear()
+        assert c.submit(cmds, args) == 0
+        assert L.vkvg_b200_surface_read_premultiplied(s.h, target.ctypes.data) == 0
+        assert np.array_equal(target, want), frame
+    # drawing on top without a clear: the per-sample plane of the banded frames is what the next flush continues from
+    c.set_source_rgba(0.1, 0.8, 0.2, 0.5)
+    c.rectangle(10.0, 10.0, size - 60.0, size / 2.0)
+    c.fill()
+    c.flush()
+    assert L.vkvg_b200_surface_read_premultiplied(s.h, target.ctypes.data) == 0
+    assert L.vkvg_b200_surface_set_readback(s.h, None) == 0
+    s2 = v.Surface(dev4, size, size)
+    c2 = v.Context(s2)
+    assert c2.submit(cmds, args) == 0
+    c2.set_source_rgba(0.1, 0.8, 0.2, 0.5)
+    c2.rectangle(10.0, 10.0, size - 60.0, size / 2.0)
+    c2.fill()
+    c2.flush()
+    assert np.array_equal(target, s2.pixels())
+    assert np.array_equal(s.pixels(), s2.pixels())

@@ -125,7 +125,7 @@ _SIGS = {
     "vkvg_b200_path_edges": (C.c_uint64, [_p, _i, _p, C.c_uint64]),
     "vkvg_b200_flush_capture_winding": (None, [_p, _p]),
     "vkvg_b200_winding": (_i, [_p, _p, C.c_uint64, _u, _u, _p]),
-    "vkvg_b200_surface_read_premultiplied": (_i, [_p, _p]),
+    "vkvg_b200_surface_read_premultiplied": (_i, [_p, _p]), "vkvg_b200_surface_set_readback": (_i, [_p, _p]),
     "vkvg_b200_launch_count": (C.c_uint64, []), "vkvg_b200_set_profiling": (None, [_p, _i]),
     "vkvg_b200_last_stats": (None, [_p, C.POINTER(Stats)]), "vkvg_b200_device_synchronize": (None, [_p]),
     "vkvg_b200_device_ordinal": (_i, [_p]), "vkvg_b200_surface_device_pointer": (_p, [_p]),

@@ -22,7 +22,8 @@ static void dev_set_failed(vkb_device_impl *d);
 void        vkb_note_cuda_error(cudaError_t) { if (t_dev) dev_set_failed(t_dev); else g_failed_nodev = 1; }
 #define g_cuda_failed (t_dev ? dev_failed(t_dev) : g_failed_nodev)
 
-struct SurfFlags { bool known_clear, stencil_live; uint32_t stencil_samples; };  // surface state a flush attempt changes
+#define VKB_MAX_BANDS 8
+struct SurfFlags { bool known_clear, stencil_live; uint32_t stencil_samples; bool readback_valid; };  // surface state a flush attempt changes
 struct vkb_device_impl;
 static int finish_pending(vkb_device_impl *d);
 
@@ -32,6 +33,9 @@ struct vkb_device_impl {
     cudaStream_t stream  = nullptr;
     cudaEvent_t  ev_begin = nullptr, ev_end = nullptr, ev_fine0 = nullptr, ev_fine1 = nullptr;
     cudaEvent_t  ev_stage[VKB_N_STAGES + 1] = {};  // boundaries between pipeline stages (profiling)
+    cudaStream_t copy_stream = nullptr;             // read-back of finished bands of tile rows while later bands render (vkb_surface_set_readback)
+    cudaEvent_t  ev_band[VKB_MAX_BANDS] = {}, ev_copied = nullptr;
+    DevBuf       band_counters;
     DevBuf       l2_flush;
     // pinned staging
     uint8_t *stage     = nullptr;
@@ -98,6 +102,8 @@ struct vkb_surface_impl {
     uint32_t         stencil_samples = 0;         // sample count the plane was laid out for
     std::vector<DevBuf> stencil_spills;           // whole-plane copies, one per six nested clip saves
     bool             known_clear;
+    uint8_t         *readback = nullptr;   // host memory every flush copies the finished image to, band by band (vkb_surface_set_readback)
+    bool             readback_valid = false;  // *readback holds the image as the last flush left it
 };
 
 vkb_device_impl *vkb_device_open(int ordinal) {
@@ -114,6 +120,9 @@ vkb_device_impl *vkb_device_open(int ordinal) {
     VKB_CUDA_OK(cudaEventCreate(&d->ev_fine0));
     VKB_CUDA_OK(cudaEventCreate(&d->ev_fine1));
     VKB_CUDA_OK(cudaEventCreateWithFlags(&d->ev_h2d, cudaEventDisableTiming));
+    VKB_CUDA_OK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : d->ev_band) VKB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    VKB_CUDA_OK(cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming));
     for (cudaEvent_t &e : d->ev_stage) VKB_CUDA_OK(cudaEventCreate(&e));
     VKB_CUDA_OK(cudaHostAlloc((void **)&d->counts_host, sizeof(vkb_counts), cudaHostAllocDefault));
     if (d->counts_host) memset(d->counts_host, 0, sizeof(vkb_counts));
@@ -141,6 +150,10 @@ void vkb_device_close(vkb_device_impl *d) {
     if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
     d->l2_flush.release();
     cudaEventDestroy(d->ev_h2d);
+    for (cudaEvent_t &e : d->ev_band) cudaEventDestroy(e);
+    cudaEventDestroy(d->ev_copied);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    d->band_counters.release();
     cudaEventDestroy(d->ev_begin); cudaEventDestroy(d->ev_end); cudaEventDestroy(d->ev_fine0); cudaEventDestroy(d->ev_fine1);
     cudaStreamDestroy(d->stream);
     if (t_dev == d) t_dev = nullptr;
@@ -181,6 +194,7 @@ void vkb_surface_clear(vkb_surface_impl *s) {
     finish_pending(s->dev);
     if (!s->known_clear) VKB_CUDA_OK(cudaMemsetAsync(s->image.p, 0, (size_t)s->w * s->h * 4, s->dev->stream));
     s->known_clear = true;
+    s->readback_valid = false;
     s->stencil_live = false;  // vkvg_clear wipes the stencil attachment too (src/vkvg_context.c:745-752)
 }
 void vkb_surface_set_band_height(vkb_surface_impl *s, uint32_t band_h) { s->band_h = band_h; }
@@ -237,10 +251,24 @@ int vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst) {
     VKB_CUDA_OK(cudaStreamSynchronize(s->dev->stream));
     return g_cuda_failed;
 }
+// Host memory (pinned, width * height * 4 bytes) that every later flush onto s also delivers the premultiplied image to: the fine pass then
+// runs in bands of tile rows and each finished band is copied on a second stream while the next ones render, so that reading the surface
+// back costs the copy of the last band instead of the whole image after the whole frame.  vkb_surface_download(s, that pointer, false)
+// then only waits.  NULL: off.
+void vkb_surface_set_readback(vkb_surface_impl *s, uint8_t *host) {
+    dev_enter(s->dev);
+    finish_pending(s->dev);
+    s->readback = host;
+    s->readback_valid = false;
+}
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) {
     vkb_device_impl *d = s->dev;
     dev_enter(d);
     if (finish_pending(d)) return 1;
+    if (!unpremultiply && out && out == s->readback && s->readback_valid) {  // delivered by the flush itself
+        VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
+        return g_cuda_failed;
+    }
     size_t          bytes = (size_t)s->w * s->h * 4;
     const uint32_t *src   = s->image.as<uint32_t>();
     if (unpremultiply) {
@@ -254,8 +282,8 @@ int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) 
 }
 
 // ---- pending (asynchronous) flush bookkeeping ----
-static SurfFlags surf_flags(const vkb_surface_impl *s) { return SurfFlags{s->known_clear, s->stencil_live, s->stencil_samples}; }
-static void      surf_restore(vkb_surface_impl *s, SurfFlags f) { s->known_clear = f.known_clear; s->stencil_live = f.stencil_live; s->stencil_samples = f.stencil_samples; }
+static SurfFlags surf_flags(const vkb_surface_impl *s) { return SurfFlags{s->known_clear, s->stencil_live, s->stencil_samples, s->readback_valid}; }
+static void      surf_restore(vkb_surface_impl *s, SurfFlags f) { s->known_clear = f.known_clear; s->stencil_live = f.stencil_live; s->stencil_samples = f.stencil_samples; s->readback_valid = f.readback_valid; }
 static int  run_flush(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t samples, vkb_capture *cap, vkb_stats *stats, bool allow_async);
 
 // ---- upload ----
@@ -624,6 +652,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     vkb_launch_grad_prep(fa.grads, draws ? d->n_grads : 0, (float)sd.width, (float)sd.full_height, d->gprep.as<float>(), st);
     fa.gprep = d->gprep.as<float>();
     fa.tile_counter = (uint32_t *)(totals + 10);  // (zeroed with the other totals when the flush starts)
+    fa.tile_lo = 0; fa.tile_hi = n_tiles;
     d->wscratch.ensure(vkb_fine_wscratch_words(samples) * 4, st);
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     fa.wscratch = d->wscratch.as<int32_t>();
@@ -660,7 +689,29 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     VKB_EVENT_RECORD(d, d->ev_stage[4]);
     if (d->capturing) d->graph_fine_events = cudaEventRecordWithFlags(d->ev_fine0, st, cudaEventRecordExternal) == cudaSuccess;
     else VKB_EVENT_RECORD(d, d->ev_fine0);
-    vkb_launch_fine(fa, st);
+    // a surface with a read-back target: bands of tile rows, each copied to the host on the copy stream as soon as it is finished
+    const bool     banded  = surf->readback && !(cap && cap->winding) && sd.tiles_y >= 2 * VKB_MAX_BANDS;
+    const uint32_t n_bands = banded ? (sd.tiles_y >= 128 ? 4u : 2u) : 1u;
+    d->band_counters.ensure(VKB_MAX_BANDS * 4, st);
+    if (banded) VKB_CUDA_OK(cudaMemsetAsync(d->band_counters.p, 0, VKB_MAX_BANDS * 4, st));
+    for (uint32_t k = 0; k < n_bands; k++) {
+        const uint32_t r0 = (uint32_t)((uint64_t)sd.tiles_y * k / n_bands), r1 = (uint32_t)((uint64_t)sd.tiles_y * (k + 1) / n_bands);
+        fa.tile_lo = r0 * sd.tiles_x; fa.tile_hi = r1 * sd.tiles_x;
+        if (banded) fa.tile_counter = d->band_counters.as<uint32_t>() + k;
+        vkb_launch_fine(fa, st);
+        if (banded) {
+            const size_t y0 = (size_t)r0 * VKB_TILE, y1 = r1 * VKB_TILE < sd.height ? (size_t)r1 * VKB_TILE : sd.height;
+            VKB_CUDA_OK(cudaEventRecord(d->ev_band[k], st));
+            VKB_CUDA_OK(cudaStreamWaitEvent(d->copy_stream, d->ev_band[k], 0));
+            VKB_CUDA_OK(cudaMemcpyAsync(surf->readback + y0 * sd.width * 4, surf->image.as<uint8_t>() + y0 * sd.width * 4, (y1 - y0) * sd.width * 4, cudaMemcpyDeviceToHost,
+                                        d->copy_stream));
+        }
+    }
+    if (banded) {  // the stream that renders goes on only when the image is out (the next flush may clear it) - and the capture, if any, is joined
+        VKB_CUDA_OK(cudaEventRecord(d->ev_copied, d->copy_stream));
+        VKB_CUDA_OK(cudaStreamWaitEvent(st, d->ev_copied, 0));
+    }
+    surf->readback_valid = banded;
     if (d->capturing) d->graph_fine_events = d->graph_fine_events && cudaEventRecordWithFlags(d->ev_fine1, st, cudaEventRecordExternal) == cudaSuccess;
     else VKB_EVENT_RECORD(d, d->ev_fine1);
     VKB_EVENT_RECORD(d, d->ev_stage[5]);
@@ -831,6 +882,7 @@ struct FlushKey {
     uint32_t w, h, samples, full_h, origin_y;
     uint32_t known_clear, stencil_live, stencil_samples, tile_ms_allocated;
     uint32_t fine_mode, pad0;  // vkb_fine_set_mode: which fine kernel a captured graph holds
+    const void *readback;      // the host pointer the band copies of a captured graph write to
     unsigned long long alloc_generation;
 };
 static_assert(sizeof(FlushKey) <= 256, "FlushKey");
@@ -857,6 +909,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     k.tile_ms_allocated = surf->tile_ms.p != nullptr;
     k.alloc_generation = g_vkb_alloc_generation;
     k.fine_mode = (uint32_t)vkb_fine_get_mode();
+    k.readback = surf->readback;
 
     memcpy(kbuf, &k, sizeof k);
     if (d->graph_exec && !memcmp(kbuf, d->graph_key, sizeof kbuf)) {

@@ -135,7 +135,8 @@ struct FineArgs {
     uint32_t           *ms_image;    // per-sample colours, tile-major [tile][256][S]; valid for tiles whose tile_ms flag is set
     uint8_t            *tile_ms;     // per tile: 1 when the samples of some pixel differ (the resolved image alone would lose them)
     uint32_t           *ms_mask;     // per tile: 8 words (one per warp = two pixel rows), bit = that pixel's samples are in ms_image
-    uint32_t           *tile_counter; // zeroed before the launch: the warp-per-tile kernel hands out tiles from it
+    uint32_t            tile_lo, tile_hi;  // tiles this launch renders (all of them, or a band of tile rows: pipeline.cu, read-back overlap)
+    uint32_t           *tile_counter; // zeroed before the launch: the warp-per-tile kernel hands out tiles (relative to tile_lo) from it
     int32_t            *wscratch;    // vkb_fine_wscratch_words() int32: one per-sample winding plane per resident warp of fine_warp_k (COUNT rule / huge lists only)
     int                 dst_is_clear;  // destination known to be transparent black: do not read it
     uint32_t           *stencil;     // per-sample stencil bytes (clip bit + save bits), tile-major [tile][256][ceil(S/4)] words; null: no clip in play

@@ -1433,7 +1433,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
     constexpr int ROWS   = 16 * S;
     constexpr int P      = ROWS >= 64 ? 2 : 1;                 // sample rows per lane per pass
     constexpr int PASSES = (ROWS + 32 * P - 1) / (32 * P);
-    const uint32_t tile  = blockIdx.x;
+    const uint32_t tile  = a.tile_lo + blockIdx.x;  // (a band of tile rows when the surface has a read-back target, else all of them)
     if (a.counts->overflow) return;  // some intermediate did not fit this attempt's buffers: the host replays the batch (vkb_counts)
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) return;  // no draw of this batch touches the tile: the stored pixels stay as they are
@@ -1682,7 +1682,7 @@ template <int S, bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256)
 #define FA_STRIDE 17
 #define FA_ONE 1048576.0f
 template <bool CAPTURE, bool CLIP> __global__ void __launch_bounds__(256) fine_analytic_k(FineArgs a) {
-    const uint32_t tile  = blockIdx.x;
+    const uint32_t tile  = a.tile_lo + blockIdx.x;  // (a band of tile rows when the surface has a read-back target, else all of them)
     if (a.counts->overflow) return;
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) return;
@@ -2086,6 +2086,7 @@ template <int S> __global__ void __launch_bounds__(32 * FW_TILES, FW_BLOCKS_PER_
     if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
     tile = __shfl_sync(FULL, tile, 0);
     if (tile >= n_tiles) break;
+    tile += a.tile_lo;
     const uint32_t first = a.tile_first[tile], end = a.tile_end[tile];
     if (first == end) continue;  // no draw of this batch touches the tile: the stored pixels stay as they are
     const uint32_t tx = tile % a.sd.tiles_x, ty = tile / a.sd.tiles_x;
@@ -2439,7 +2440,7 @@ template <int S> static void launch_fine_s(const FineArgs &a, uint32_t tiles, cu
     else { if (clip) fine_k<S, false, true><<<tiles, 256, 0, s>>>(a); else fine_k<S, false, false><<<tiles, 256, 0, s>>>(a); }
 }
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s) {
-    uint32_t tiles = a.sd.tiles_x * a.sd.tiles_y;
+    uint32_t tiles = a.tile_hi - a.tile_lo;   // (the whole surface, or one band of tile rows: FineArgs::tile_lo / tile_hi)
     if (!tiles) return;
     const bool cap = a.winding_out != nullptr, clip = a.stencil != nullptr;
     switch (a.sd.samples) {

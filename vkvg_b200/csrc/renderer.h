@@ -111,6 +111,8 @@ int               vkb_surface_stencil_push(vkb_surface_impl *s, uint32_t samples
 int               vkb_surface_stencil_pop(vkb_surface_impl *s, uint32_t samples);
 // premultiplied RGBA8 rows, or un-premultiplied as vkvg_surface_write_to_memory does; synchronous
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply);
+// host memory every later flush also delivers the premultiplied image to, band by band while it renders (NULL: off)
+void vkb_surface_set_readback(vkb_surface_impl *s, uint8_t *host);
 const uint32_t *vkb_surface_device_pixels(vkb_surface_impl *s);
 int             vkb_surface_upload(vkb_surface_impl *s, const uint8_t *rgba);
 

@@ -376,6 +376,12 @@ vkvg_status_t vkvg_surface_write_to_memory(VkvgSurface surf, unsigned char *cons
     std::lock_guard<std::mutex> lk(surf->dev->mtx);
     return vkb_surface_download(surf->impl, bitmap, true) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
 }
+vkvg_status_t vkvg_b200_surface_set_readback(VkvgSurface surf, unsigned char *host_rgba) {
+    if (vkvg_surface_status(surf)) return VKVG_STATUS_INVALID_SURFACE;
+    std::lock_guard<std::mutex> lk(surf->dev->mtx);
+    vkb_surface_set_readback(surf->impl, host_rgba);
+    return VKVG_STATUS_SUCCESS;
+}
 vkvg_status_t vkvg_b200_surface_read_premultiplied(VkvgSurface surf, unsigned char *rgba) {
     if (vkvg_surface_status(surf)) return VKVG_STATUS_INVALID_STATUS;
     if (!rgba) return VKVG_STATUS_WRITE_ERROR;
