@@ -157,7 +157,7 @@ vkvg_public vkvg_status_t vkvg_b200_replay(VkvgContext ctx, const uint8_t *ops, 
  * vkvg_b200_submit = the calls one by one, then vkvg_flush - but the stream is uploaded as it is and turned into path elements, sub-paths,
  * draws and side tables BY KERNELS (vkvg_b200/csrc/decode.cu) when it is a regular bulk scene: move_to / line_to / curve_to / polyline /
  * close_path / new_path, fill / stroke (and _preserve), solid and gradient sources, line and dash state, fill rule, opacity,
- * identity_matrix / translate / set_canvas, starting from a context with no path under construction, a solid source and no clip.
+ * identity_matrix / translate / set_canvas, starting from a context with no path under construction, a solid or gradient source and no clip.
  * Everything else (and any stream in which the reference would drop a point or ignore a close_path) is decoded on the host exactly as
  * vkvg_b200_replay would: same pixels either way.  cmds / args may be reused as soon as the call returns. */
 vkvg_public vkvg_status_t vkvg_b200_submit(VkvgContext ctx, const uint32_t *cmds, uint64_t n_cmds, const float *args, uint64_t n_args);

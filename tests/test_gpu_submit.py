@@ -155,3 +155,30 @@ def test_read_back_target_gets_the_same_image(dev4, size):
     c2.flush()
     assert np.array_equal(target, s2.pixels())
     assert np.array_equal(s.pixels(), s2.pixels())
+
+
+def test_gradient_source_in_force_when_the_stream_starts(dev4):
+    """a stream may begin with draws that use the source the previous stream (or ordinary calls) left behind - a gradient included"""
+    first = v.CommandStream()
+    first.set_source_radial(120.0, 110.0, 10.0, 130.0, 100.0, 150.0, [(0, 1, 1, 0, 1), (0.6, 0, 1, 1, 0.7), (1, 0, 0, 1, 0.4)])
+    first.move_to(10.0, 10.0); first.line_to(200.0, 30.0); first.line_to(60.0, 180.0); first.close_path(); first.fill()
+    second = v.CommandStream()
+    second.move_to(60.0, 60.0); second.line_to(250.0, 90.0); second.line_to(120.0, 240.0); second.close_path(); second.fill()   # with the radial gradient
+    second.set_source_rgba(0.9, 0.2, 0.1, 0.5)
+    second.move_to(5.0, 200.0); second.line_to(100.0, 210.0); second.line_to(40.0, 250.0); second.close_path(); second.fill()
+    imgs = []
+    for mode in (0, 1):
+        v.lib().vkvg_b200_set_submit_decoder(mode)
+        try:
+            s = v.Surface(dev4, 256, 256)
+            c = v.Context(s)
+            d0 = v.submit_counts()
+            assert c.submit(*first.arrays2()) == 0 and c.submit(*second.arrays2()) == 0
+            d1 = v.submit_counts()
+            assert (d1[0] - d0[0], d1[1] - d0[1]) == ((2, 0) if mode == 0 else (0, 2))
+            imgs.append(s.pixels())
+            c.close()
+            s.close()
+        finally:
+            v.lib().vkvg_b200_set_submit_decoder(0)
+    assert imgs[0][..., 3].any() and np.array_equal(imgs[0], imgs[1])

@@ -155,12 +155,7 @@ struct DecodeBufs {
     vkb_decode_census *census;
     uint32_t       *sp_null;    // per sub-path: curve_to commands the reference skips (zeroed before vkd_elems_k)
 };
-struct DecodeInit {  // the context's state when the stream starts
-    float    mat[6];
-    uint32_t band, color, rule, cap, join, bop, dash_count;
-    float    lw, miter, opacity, dash_offset;
-    float    dashes[VKB_MAX_DASHES];
-};
+typedef vkb_decode_init DecodeInit;  // the context's state when the stream starts
 __device__ __forceinline__ const uint32_t *tot_row(const DecodeBufs &b) { return b.S + (size_t)b.n_cmds * NF; }
 __device__ __forceinline__ uint32_t list_base(const DecodeBufs &b, int f) {  // where list f starts inside b.lists
     uint32_t o = 0;
@@ -410,12 +405,12 @@ __global__ void __launch_bounds__(128) vkd_draws_k(DecodeBufs b, DecodeInit init
             rule = (uint32_t)(int)v;   // vkvg_fill_rule_t: 0 even-odd, 1 non-zero
         }
     }
-    uint32_t pat = VKB_PAT_SOLID, color = init.color, grad = 0;
+    uint32_t pat = init.pattern, color = init.color, grad = T[F_GRAD];  // (the gradient in force at entry sits behind the stream's own)
     {
         const int c = latest(b, i, F_SRC);
         if (c >= 0) {
             const uint32_t sop = b.cmds[c] & 0xFF, a = Sv(b, (uint32_t)c, F_ARGS);
-            if (sop == VKVG_B200_OP_SET_SOURCE_RGBA) color = rgbaf_dev(b.args[a], b.args[a + 1], b.args[a + 2], b.args[a + 3]);
+            if (sop == VKVG_B200_OP_SET_SOURCE_RGBA) { pat = VKB_PAT_SOLID; color = rgbaf_dev(b.args[a], b.args[a + 1], b.args[a + 2], b.args[a + 3]); }
             else {
                 pat  = sop == VKVG_B200_OP_SET_SOURCE_LINEAR ? VKB_PAT_LINEAR : VKB_PAT_RADIAL;
                 grad = Sv(b, (uint32_t)c, F_GRAD);
@@ -477,6 +472,7 @@ __global__ void vkd_census_k(DecodeBufs b, DecodeInit init) {
     if (T[F_SP] != last_pb_sp) atomicOr(b.irregular, 256u);
     if (T[F_XF] + 1 > 65000u || T[F_SDRAW] > 65000u) atomicOr(b.irregular, 512u);  // side tables are addressed with 16 bits
     for (uint32_t k = 0; k < VKB_MAX_DASHES; k++) b.dashes[k] = k < init.dash_count ? init.dashes[k] : 0.0f;
+    b.grads[T[F_GRAD]] = init.grad;
     __threadfence();
     c->irregular = *b.irregular;
 }
@@ -508,11 +504,7 @@ void vkb_launch_decode_emit(const uint32_t *cmds, const float *args, uint32_t n_
                             vkb_gradient *grads, float *dashes, vkb_decode_census *census, uint32_t *sp_null, const vkb_decode_init &in, cudaStream_t st) {
     DecodeBufs b = {cmds, args, n_cmds, S, lists, irregular, elem_hdr, elem_data, subpaths, draws, xforms, xf_scale, strokes, grads, dashes, census, sp_null};
     VKB_CUDA_OK(cudaMemsetAsync(sp_null, 0, ((size_t)t.n_subpaths + 1) * 4, st));
-    DecodeInit init;
-    memcpy(init.mat, in.mat, sizeof init.mat);
-    init.band = in.band; init.color = in.color; init.rule = in.rule; init.cap = in.cap; init.join = in.join; init.bop = in.bop; init.dash_count = in.dash_count;
-    init.lw = in.lw; init.miter = in.miter; init.opacity = in.opacity; init.dash_offset = in.dash_offset;
-    memcpy(init.dashes, in.dashes, sizeof init.dashes);
+    const DecodeInit &init = in;
     vkd_lists_k<<<vkb_div_up(n_cmds, 256), 256, 0, st>>>(b);
     VKB_LAUNCHED();
     vkd_xforms_k<<<1, 32, 0, st>>>(b, init);

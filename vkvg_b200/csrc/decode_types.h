@@ -8,6 +8,8 @@ struct vkb_decode_init {  // the context's state when the stream starts
     uint32_t band, color, rule, cap, join, bop, dash_count;
     float    lw, miter, opacity, dash_offset;
     float    dashes[VKB_MAX_DASHES];
+    uint32_t pattern;        // VKB_PAT_SOLID, or VKB_PAT_LINEAR / VKB_PAT_RADIAL with the gradient below (as _update_cur_pattern left it)
+    vkb_gradient grad;
 };
 struct vkb_decode_census {  // read back once per stream: what the host sizes the pipeline from, and the state the context is left in
     uint32_t n_elems, n_data, n_subpaths, n_draws, n_curves, n_grads, n_dash_floats, n_xforms, n_strokes;

@@ -1089,7 +1089,7 @@ int vkb_submit_stream(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sampl
     d->xforms.ensure((size_t)(t.n_xforms + 1) * sizeof(vkb_xform), st);
     d->dc_xfscale.ensure((size_t)(t.n_xforms + 1) * 8, st);
     d->strokes.ensure((size_t)(t.n_strokes + 1) * sizeof(vkb_stroke), st);
-    d->grads.ensure((size_t)(t.n_grads + 1) * sizeof(vkb_gradient), st);
+    d->grads.ensure((size_t)(t.n_grads + 2) * sizeof(vkb_gradient), st);
     d->dashes.ensure((size_t)(t.n_dash_floats + 4) * 4, st);
     d->surfpats.ensure(sizeof(vkb_surfpat), st);
     d->dc_lists.ensure((size_t)(t.n_list_entries + 4) * 4, st);
@@ -1109,7 +1109,7 @@ int vkb_submit_stream(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sampl
     }  // (the resident batch was overwritten: nothing to replay)
     *census_out = c;
     // ---- the host's view of the batch, then the job tables and the pipeline as after an upload ----
-    d->n_elems = c.n_elems; d->n_sp = c.n_subpaths; d->n_draws = c.n_draws; d->n_curves = c.n_curves; d->n_grads = c.n_grads;
+    d->n_elems = c.n_elems; d->n_sp = c.n_subpaths; d->n_draws = c.n_draws; d->n_curves = c.n_curves; d->n_grads = c.n_grads + 1;
     d->n_fjobs = c.n_fjobs; d->n_sjobs = c.n_sjobs; d->n_sdraws = c.n_sdraws; d->n_extra = 0;
     d->any_dash = c.any_dash != 0; d->nz_any = c.nz_any != 0;
     d->has_clip_draws = d->has_stencil_ops = false;

@@ -1773,8 +1773,8 @@ void vkvg_b200_submit_counts(uint64_t *on_device, uint64_t *on_host) {
 vkvg_status_t vkvg_b200_submit(VkvgContext ctx, const uint32_t *cmds, uint64_t n_cmds, const float *args, uint64_t n_args) {
     if (vkvg_status(ctx)) return vkvg_status(ctx);
     if (!cmds || (!args && n_args)) return VKVG_STATUS_NULL_POINTER;
-    // the device decodes a stream that starts from a plain state: no path under construction, a solid source, no clip, no recording
-    bool device_ok = g_submit_mode == 0 && !ctx->recording && ctx->sp_points == 0 && ctx->path_first_sp == ctx->batch.subpaths.size() && ctx->patType == VKB_PAT_SOLID &&
+    // the device decodes a stream that starts from a plain state: no path under construction, a solid or gradient source, no clip, no recording
+    bool device_ok = g_submit_mode == 0 && !ctx->recording && ctx->sp_points == 0 && ctx->path_first_sp == ctx->batch.subpaths.size() && ctx->patType != VKB_PAT_SURFACE &&
                      ctx->curClipState == CLIP_STATE_NONE && ctx->saved.empty() && ctx->dashes.size() <= VKB_MAX_DASHES && n_cmds > 0;
     if (device_ok) {
         if (!ctx->batch.draws.empty()) flush_impl(ctx, nullptr, false);  // draws recorded call by call come first
@@ -1788,6 +1788,8 @@ vkvg_status_t vkvg_b200_submit(VkvgContext ctx, const uint32_t *cmds, uint64_t n
         in.dash_count = (uint32_t)ctx->dashes.size(); in.dash_offset = ctx->dashOffset;
         for (size_t q = 0; q < ctx->dashes.size(); q++) in.dashes[q] = ctx->dashes[q];
         in.lw = ctx->lineWidth; in.miter = ctx->miterLimit; in.opacity = ctx->opacity;
+        in.pattern = ctx->patType;
+        if (ctx->patType != VKB_PAT_SOLID) in.grad = ctx->grad;
         vkb_decode_census c;
         int r;
         {
