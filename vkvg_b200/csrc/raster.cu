@@ -468,6 +468,7 @@ __device__ __forceinline__ bool tri_has(const uint32_t (&i)[3], uint32_t u, uint
 __device__ __forceinline__ int tri_dir(const uint32_t (&i)[3], uint32_t u, uint32_t v) {
     return ((i[0] == u && i[1] == v) || (i[1] == u && i[2] == v) || (i[2] == u && i[0] == v)) ? 1 : -1;
 }
+#define VKB_EDGE_GRID (148u * 8u * 8u)  // most blocks of a per-edge / per-vertex / per-triangle kernel: eight waves of eight 256-thread blocks per SM, grid-stride beyond
 __device__ __forceinline__ void tri_idx(const uint32_t *inds, uint32_t n_tris, long long t, uint32_t (&i)[3]) {
     if (t < 0 || t >= (long long)n_tris) { i[0] = i[1] = i[2] = 0xffffffffu; return; }
     i[0] = inds[3 * t]; i[1] = inds[3 * t + 1]; i[2] = inds[3 * t + 2];
@@ -477,18 +478,20 @@ __device__ __forceinline__ void tri_idx(const uint32_t *inds, uint32_t n_tris, l
 __global__ void __launch_bounds__(256)
 snap_verts_k(const float2 *verts, const vkb_counts *C, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id,
              const uint32_t *sdraw_first_item, uint32_t n_sdraws, const unsigned long long *item_offsets, SurfaceDesc sd, int2 *snapped) {
-    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (C->overflow || v >= C->n[VKC_VERTS]) return;
-    uint32_t lo = 0, hi = n_sdraws;  // stroke draw owning vertex v: last q whose first item's vertex offset <= v
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if ((uint32_t)(item_offsets[sdraw_first_item[mid]] & 0xffffffffull) <= v) lo = mid; else hi = mid;
+    if (C->overflow) return;
+    const uint32_t n_verts = C->n[VKC_VERTS];
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_verts; v += gridDim.x * blockDim.x) {  // (grid from the capacity, capped)
+        uint32_t lo = 0, hi = n_sdraws;  // stroke draw owning vertex v: last q whose first item's vertex offset <= v
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)(item_offsets[sdraw_first_item[mid]] & 0xffffffffull) <= v) lo = mid; else hi = mid;
+        }
+        const vkb_xform &xf = xforms[draws[sdraw_id[lo]].xform_stroke & 0xFFFF];
+        const float2     p  = verts[v];
+        int32_t          x, y;
+        vs_snap(xf.mat, (float)sd.width, (float)sd.full_height, p.x, p.y, x, y);
+        snapped[v] = make_int2(x, y + (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256);
     }
-    const vkb_xform &xf = xforms[draws[sdraw_id[lo]].xform_stroke & 0xFFFF];
-    const float2     p  = verts[v];
-    int32_t          x, y;
-    vs_snap(xf.mat, (float)sd.width, (float)sd.full_height, p.x, p.y, x, y);
-    snapped[v] = make_int2(x, y + (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256);
 }
 __device__ __forceinline__ int tri_sign(const int2 *snapped, uint32_t n_verts, const uint32_t (&i)[3], int32_t (&x)[3], int32_t (&y)[3]) {
     if (i[0] >= n_verts || i[1] >= n_verts || i[2] >= n_verts) return 0;
@@ -507,68 +510,79 @@ __global__ void __launch_bounds__(256)
 tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item,
             uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
             SurfaceDesc sd, int32_t *bbox) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_tris = C->n[VKC_TRIS], n_verts = C->n[VKC_VERTS];
-    if ((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) >= n_tris) return;  // whole warps leave; a partial warp stays for the shuffles below
-    const bool in_range = t < n_tris;
-    if (!in_range) t = n_tris - 1;
     edges += C->n[VKC_FEDGES] + n_extra; edge_draw += C->n[VKC_FEDGES] + n_extra;
-    // stroke draw owning index 3t: last q whose first item's index offset <= 3t
-    uint32_t lo = 0, hi = n_sdraws;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if ((uint32_t)(item_offsets[sdraw_first_item[mid]] >> 32) <= 3 * t) lo = mid; else hi = mid;
-    }
-    const uint32_t   d  = sdraw_id[lo];
-    uint32_t       i0[3], ip1[3], ip2[3], im1[3], im2[3];
-    tri_idx(inds, n_tris, (long long)t, i0);
-    tri_idx(inds, n_tris, (long long)t + 1, ip1);
-    tri_idx(inds, n_tris, (long long)t + 2, ip2);
-    tri_idx(inds, n_tris, (long long)t - 1, im1);
-    tri_idx(inds, n_tris, (long long)t - 2, im2);
-    int32_t x[3], y[3], nx[3], ny[3];
-    const int sg = tri_sign(snapped, n_verts, i0, x, y);
-    int       sg_next = 2, sg_prev = 2;  // 2: not evaluated yet (vertices of a neighbour share this draw's matrix: shared indices)
-    vkb_edge  e[3];
+    // whole warps stride the LIVE triangles (the grid comes from the capacity of the index buffer, capped); a partial warp stays for the shuffles
+    for (uint32_t wb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < n_tris; wb += gridDim.x * blockDim.x) {
+        uint32_t   t = wb + (threadIdx.x & 31u);
+        const bool in_range = t < n_tris;
+        if (!in_range) t = n_tris - 1;
+        uint32_t i0[3];
+        tri_idx(inds, n_tris, (long long)t, i0);
+        int32_t x[3], y[3], nx[3], ny[3];
+        int     sg = tri_sign(snapped, n_verts, i0, x, y);
+        // a triangle wholly above, below or right of the surface: each of its edges is (edge_off_surface), so none of them is stored whether
+        // or not a neighbour cancels it - skip the neighbours.  On a stripe of a taller surface that is most of the triangles.
+        if (sg != 0 && (max(max(y[0], y[1]), y[2]) < 0 || min(min(y[0], y[1]), y[2]) > (int32_t)sd.height * 256 ||
+                        min(min(x[0], x[1]), x[2]) > (int32_t)sd.width * 256))
+            sg = 0;
+        vkb_edge e[3];
+        uint32_t d = 0;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        e[k] = vkb_edge{0, 0, 0, 0};
-        if (sg == 0) continue;
-        // k-th edge in normalised orientation: kept order a->b, b->c, c->a; reversed a->c, c->b, b->a
-        const int ka = sg > 0 ? k : (3 - k) % 3, kb = sg > 0 ? (k + 1) % 3 : (5 - k) % 3;
-        const uint32_t u = i0[ka], v = i0[kb];
-        bool           drop = false;
-        if (tri_has(ip1, u, v)) {
-            if (!tri_has(im1, u, v) && !tri_has(ip2, u, v)) {
-                if (sg_next == 2) sg_next = tri_sign(snapped, n_verts, ip1, nx, ny);
-                // direction of u->v inside the neighbour after ITS normalisation; opposite to ours (which is u->v) cancels
-                drop = sg_next != 0 && tri_dir(ip1, u, v) * sg_next < 0;
+        for (int k = 0; k < 3; k++) e[k] = vkb_edge{0, 0, 0, 0};
+        if (sg != 0) {
+            // stroke draw owning index 3t: last q whose first item's index offset <= 3t
+            uint32_t lo = 0, hi = n_sdraws;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if ((uint32_t)(item_offsets[sdraw_first_item[mid]] >> 32) <= 3 * t) lo = mid; else hi = mid;
             }
-        } else if (tri_has(im1, u, v)) {
-            if (!tri_has(im2, u, v)) {
-                if (sg_prev == 2) sg_prev = tri_sign(snapped, n_verts, im1, nx, ny);
-                drop = sg_prev != 0 && tri_dir(im1, u, v) * sg_prev < 0;
+            d = sdraw_id[lo];
+            uint32_t ip1[3], ip2[3], im1[3], im2[3];
+            tri_idx(inds, n_tris, (long long)t + 1, ip1);
+            tri_idx(inds, n_tris, (long long)t + 2, ip2);
+            tri_idx(inds, n_tris, (long long)t - 1, im1);
+            tri_idx(inds, n_tris, (long long)t - 2, im2);
+            int sg_next = 2, sg_prev = 2;  // 2: not evaluated yet (vertices of a neighbour share this draw's matrix: shared indices)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                // k-th edge in normalised orientation: kept order a->b, b->c, c->a; reversed a->c, c->b, b->a
+                const int ka = sg > 0 ? k : (3 - k) % 3, kb = sg > 0 ? (k + 1) % 3 : (5 - k) % 3;
+                const uint32_t u = i0[ka], v = i0[kb];
+                bool           drop = false;
+                if (tri_has(ip1, u, v)) {
+                    if (!tri_has(im1, u, v) && !tri_has(ip2, u, v)) {
+                        if (sg_next == 2) sg_next = tri_sign(snapped, n_verts, ip1, nx, ny);
+                        // direction of u->v inside the neighbour after ITS normalisation; opposite to ours (which is u->v) cancels
+                        drop = sg_next != 0 && tri_dir(ip1, u, v) * sg_next < 0;
+                    }
+                } else if (tri_has(im1, u, v)) {
+                    if (!tri_has(im2, u, v)) {
+                        if (sg_prev == 2) sg_prev = tri_sign(snapped, n_verts, im1, nx, ny);
+                        drop = sg_prev != 0 && tri_dir(im1, u, v) * sg_prev < 0;
+                    }
+                }
+                if (!drop) e[k] = vkb_edge{x[ka], y[ka], x[kb], y[kb]};
             }
         }
-        if (!drop) e[k] = vkb_edge{x[ka], y[ka], x[kb], y[kb]};
-    }
-    bool     keep[3];
-    uint32_t cnt = 0;
+        bool     keep[3];
+        uint32_t cnt = 0;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        keep[k] = in_range && !(e[k].x0 == e[k].x1 && e[k].y0 == e[k].y1) && !edge_off_surface(e[k], sd);
-        cnt += keep[k] ? 1u : 0u;
-    }
-    const uint32_t incl = warp_incl_scan(cnt);
-    uint32_t       base = 0;
-    if ((threadIdx.x & 31) == 31 && incl) base = atomicAdd(live, incl);
-    uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-    BoxAcc box;
+        for (int k = 0; k < 3; k++) {
+            keep[k] = in_range && !(e[k].x0 == e[k].x1 && e[k].y0 == e[k].y1) && !edge_off_surface(e[k], sd);
+            cnt += keep[k] ? 1u : 0u;
+        }
+        const uint32_t incl = warp_incl_scan(cnt);
+        uint32_t       base = 0;
+        if ((threadIdx.x & 31) == 31 && incl) base = atomicAdd(live, incl);
+        uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        BoxAcc box;
 #pragma unroll
-    for (int k = 0; k < 3; k++)
-        if (keep[k]) { edges[pos] = e[k]; edge_draw[pos] = d; pos++; box.add(e[k]); }
-    bbox_accumulate(bbox, d, box);
+        for (int k = 0; k < 3; k++)
+            if (keep[k]) { edges[pos] = e[k]; edge_draw[pos] = d; pos++; box.add(e[k]); }
+        bbox_accumulate(bbox, d, box);
+    }
 }
 // the stroke edges that survived are only counted by tri_edges_k: C->n[VKC_EDGES] (so far the upper bound fill + 3 x triangles +
 // rectangles, which sized the buffers) becomes the number actually stored
@@ -581,9 +595,9 @@ void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped
                           const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
                           vkb_counts *Cw, int32_t *draw_bbox, cudaStream_t s) {
     if (!cap_tris || !n_sdraws) return;
-    snap_verts_k<<<vkb_div_up(cap_verts, 256), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
+    snap_verts_k<<<min(vkb_div_up(cap_verts, 256), VKB_EDGE_GRID), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
     VKB_LAUNCHED();
-    tri_edges_k<<<vkb_div_up(cap_tris, 256), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd, draw_bbox);
+    tri_edges_k<<<min(vkb_div_up(cap_tris, 256), VKB_EDGE_GRID), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd, draw_bbox);
     VKB_LAUNCHED();
     commit_live_edges_k<<<1, 1, 0, s>>>(Cw, live, n_extra);
     VKB_LAUNCHED();
@@ -762,13 +776,17 @@ __device__ __forceinline__ bool edge_is_shallow(const vkb_edge &e) { return llab
 __global__ void __launch_bounds__(256) bin_count_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
                                                   const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, uint32_t *long_list,
                                                   uint32_t *long_n) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (C->overflow || i >= C->n[VKC_EDGES]) return;
-    vkb_edge e = edges[i];
-    if (edge_degenerate(e)) return;
-    uint32_t d = edge_draw[i];
-    if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) { long_list[atomicAdd(long_n, 1u)] = (uint32_t)i; return; }
-    for_each_tile_of_edge(e, draw_rect + 4 * d, [&](uint32_t pt) { atomicAdd(&pt_count[pt], 1u); }, true, pt_backdrop, draw_ptbase[d]);
+    if (C->overflow) return;
+    // grid-stride over the LIVE edges: the grid is sized from the capacity of the buffer (3 x triangles for strokes, of which a stripe keeps
+    // an eighth), capped at a few waves
+    const uint32_t n = C->n[VKC_EDGES], stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        vkb_edge e = edges[i];
+        if (edge_degenerate(e)) continue;
+        uint32_t d = edge_draw[i];
+        if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) { long_list[atomicAdd(long_n, 1u)] = i; continue; }
+        for_each_tile_of_edge(e, draw_rect + 4 * d, [&](uint32_t pt) { atomicAdd(&pt_count[pt], 1u); }, true, pt_backdrop, draw_ptbase[d]);
+    }
 }
 // one warp per long edge (grid-stride over the list)
 __global__ void __launch_bounds__(256) bin_count_long_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
@@ -787,7 +805,7 @@ __global__ void __launch_bounds__(256) bin_count_long_k(const vkb_edge *edges, c
 void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
                           const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, uint32_t *long_list, uint32_t *long_n, cudaStream_t s) {
     if (!cap_edges) return;
-    bin_count_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop, long_list, long_n);
+    bin_count_k<<<min(vkb_div_up(cap_edges, 256), VKB_EDGE_GRID), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop, long_list, long_n);
     VKB_LAUNCHED();
     bin_count_long_k<<<148 * 2, 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop, long_list, long_n);
     VKB_LAUNCHED();
@@ -795,20 +813,22 @@ void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint
 __global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
                                                     const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor,
                                                     vkb_edge *tile_edges) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (C->overflow || i >= C->n[VKC_EDGES]) return;
-    vkb_edge e = edges[i];
-    if (edge_degenerate(e)) return;
-    uint32_t d = edge_draw[i];
-    if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) return;  // on the long list, see bin_scatter_long_k
-    for_each_tile_of_edge(
-        e, draw_rect + 4 * d,
-        [&](uint32_t pt) {
-            uint32_t p   = pt_slot[pt];
-            uint32_t pos = eoff[p] + atomicAdd(&cursor[p], 1u);
-            tile_edges[pos] = e;
-        },
-        false, nullptr, draw_ptbase[d]);
+    if (C->overflow) return;
+    const uint32_t n = C->n[VKC_EDGES], stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        vkb_edge e = edges[i];
+        if (edge_degenerate(e)) continue;
+        uint32_t d = edge_draw[i];
+        if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) continue;  // on the long list, see bin_scatter_long_k
+        for_each_tile_of_edge(
+            e, draw_rect + 4 * d,
+            [&](uint32_t pt) {
+                uint32_t p   = pt_slot[pt];
+                uint32_t pos = eoff[p] + atomicAdd(&cursor[p], 1u);
+                tile_edges[pos] = e;
+            },
+            false, nullptr, draw_ptbase[d]);
+    }
 }
 __global__ void __launch_bounds__(256) bin_scatter_long_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
                                                          const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor,
@@ -833,7 +853,7 @@ void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, ui
                             const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges,
                             const uint32_t *long_list, const uint32_t *long_n, cudaStream_t s) {
     if (!cap_edges) return;
-    bin_scatter_k<<<vkb_div_up(cap_edges, 256), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges);
+    bin_scatter_k<<<min(vkb_div_up(cap_edges, 256), VKB_EDGE_GRID), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges);
     VKB_LAUNCHED();
     bin_scatter_long_k<<<148 * 2, 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges, long_list, long_n);
     VKB_LAUNCHED();

@@ -254,10 +254,11 @@ stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws,
                const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count,
                const vkb_subpath *sps, const double *cum, const vkb_counts *C, unsigned long long *counts, const unsigned long long *offsets,
                float2 *verts, uint32_t *inds, uint32_t *job_inverse) {
-    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_items = C->n[VKC_SITEMS];
-    if (item >= n_items) return;
+    // grid-stride over the LIVE items: the grid is sized from the capacity of the item space (a guess for the first flush, what earlier
+    // flushes needed afterwards) and capped, see VKB_STROKE_GRID
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
     // locate the job (sub-path of a stroke draw) this point belongs to: last j with job_base[j] <= item
     uint32_t lo = 0, hi = n_jobs;
     while (hi - lo > 1) {
@@ -336,28 +337,29 @@ stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws,
         }
     }
     if (!EMIT) counts[item] = (unsigned long long)o.nv | ((unsigned long long)o.ni << 32);
+    }
 }
 
 // float segment lengths for the dash phase scan (one per stroke item; 0 where there is no segment)
 __global__ void stroke_seglen_k(const float2 *pts, const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first,
                                 const uint32_t *sp_count, const vkb_subpath *sps, const vkb_counts *C, float *seglen) {
-    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_items = C->n[VKC_SITEMS];
-    if (item > n_items) return;
-    if (item == n_items) { seglen[item] = 0.f; return; }
-    uint32_t lo = 0, hi = n_jobs;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (job_base[mid] <= item) lo = mid; else hi = mid;
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item <= n_items; item += gridDim.x * blockDim.x) {
+        if (item == n_items) { seglen[item] = 0.f; break; }
+        uint32_t lo = 0, hi = n_jobs;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (job_base[mid] <= item) lo = mid; else hi = mid;
+        }
+        uint32_t k = item - job_base[lo], s = job_sp[lo], first = sp_first[s], n = sp_count[s];
+        float    L = 0.f;
+        if (n >= 2) {
+            uint32_t iR = k + 1 < n ? k + 1 : ((sps[s].flags & VKB_SP_CLOSED) ? 0 : n);
+            if (iR < n) L = v2len(v2sub(ld(pts + first, iR), ld(pts + first, k)));
+        }
+        seglen[item] = L;
     }
-    uint32_t k = item - job_base[lo], s = job_sp[lo], first = sp_first[s], n = sp_count[s];
-    float    L = 0.f;
-    if (n >= 2) {
-        uint32_t iR = k + 1 < n ? k + 1 : ((sps[s].flags & VKB_SP_CLOSED) ? 0 : n);
-        if (iR < n) L = v2len(v2sub(ld(pts + first, iR), ld(pts + first, k)));
-    }
-    seglen[item] = L;
 }
 
 // closed, undashed sub-paths: redirect the forward references of the closing quad to the first two
@@ -382,18 +384,19 @@ __global__ void stroke_patch_closed_k(const vkb_draw *draws, const vkb_stroke *s
     else { t[1] = ii; t[4] = ii; t[5] = ii + 1; }
 }
 
-// a.n_items is the CAPACITY of the item space (grids are sized for it); the item count is a.C->n[VKC_SITEMS]
+// a.n_items is the CAPACITY of the item space (grids are sized for it, up to VKB_STROKE_GRID blocks that stride); the item count is a.C->n[VKC_SITEMS]
+#define VKB_STROKE_GRID (148u * 16u * 8u)
 void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s) {
-    stroke_seglen_k<<<vkb_div_up(a.n_items + 1, 256), 256, 0, s>>>(a.pts, a.job_sp, a.job_base, a.n_jobs, a.sp_first, a.sp_count, a.sps, a.C, seglen);
+    stroke_seglen_k<<<min(vkb_div_up(a.n_items + 1, 256), VKB_STROKE_GRID), 256, 0, s>>>(a.pts, a.job_sp, a.job_base, a.n_jobs, a.sp_first, a.sp_count, a.sps, a.C, seglen);
     VKB_LAUNCHED();
 }
 void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s) {
-    stroke_items_k<false><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
+    stroke_items_k<false><<<min(vkb_div_up(a.n_items, 128), VKB_STROKE_GRID), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
                                                                    a.sp_first, a.sp_count, a.sps, a.cum, a.C, counts, nullptr, nullptr, nullptr, nullptr);
     VKB_LAUNCHED();
 }
 void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, float2 *verts, uint32_t *inds, uint32_t *job_inverse, cudaStream_t s) {
-    stroke_items_k<true><<<vkb_div_up(a.n_items, 128), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
+    stroke_items_k<true><<<min(vkb_div_up(a.n_items, 128), VKB_STROKE_GRID), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
                                                                   a.sp_first, a.sp_count, a.sps, a.cum, a.C, nullptr, offsets, verts, inds, job_inverse);
     VKB_LAUNCHED();
     stroke_patch_closed_k<<<vkb_div_up(a.n_jobs, 128), 128, 0, s>>>(a.draws, a.strokes, a.job_draw, a.job_sp, a.job_base, a.n_jobs, a.sps, a.sp_count, offsets,
