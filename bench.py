@@ -11,7 +11,7 @@ The same line carries, unless --only is given:
   configs  the other single-GPU configurations of BASELINE.json measured the same way on rank 0's GPU: c1 (tiger frames/s, with
            vkvg_surface_write_to_png timed separately), c2_eo, c3 (Msegments/s), c4
   sharded  the two configurations that shard, STRONG scaling over the N ranks of this run: c5a (tile-row stripes of one
-           16384^2 surface, NCCL gather of the stripes) and c5b (1024 independent tiger canvases split across the ranks)
+           16384^2 surface, each stripe delivered into rank 0's picture over NVLink while it renders) and c5b (1024 independent tiger canvases split across the ranks)
   parity   the GPU's C2 frame against the cpu_baseline leg's frame (reference tessellation + oracle raster), every pixel
 
   value  = whole-job throughput with the recorded scene already resident in HBM (device-timed: CUDA events on the library's stream around
@@ -49,7 +49,7 @@ WORKLOAD_NAMES = {
     "c4": "C4 50k cubic-Bezier paths, linear/radial gradient fills, OVER, 8192x8192, 4 samples",
     "c5b": "C5b batch of 1024 independent 1024x1024 tiger canvases (per-canvas affine jitter), 16 canvases per flush in one batch surface, canvases split across ranks",
     "blit": "layer compositing: 8 translucent 2048x2048 surface sources (bilinear, rotated) painted over a 4096x4096 surface (SURVEY 8f rank 2)",
-    "c5a": "C5a 16384x16384 surface, 5M-segment mix (C2-style polygons + C3-style dashed polylines), sharded by tile-row stripes, NCCL gather",
+    "c5a": "C5a 16384x16384 surface, 5M-segment mix (C2-style polygons + C3-style dashed polylines), sharded by tile-row stripes, stripes delivered into rank 0's picture",
 }
 REF_LABEL = "restated CPU baseline - not lavapipe (reference tessellation object code + scalar restatement of the Vulkan rasteriser)"
 BIG = 1e30
@@ -470,6 +470,9 @@ def measure(env, w, rule, steps, strong_world=None):
     on_dev0 = v.submit_counts()
     gather_ms = [0.0]
     full_t = [None]
+    # stripes on more than one GPU: every rank's finished bands go straight into the root's picture over NVLink (CUDA IPC pointer as the
+    # read-back target of the stripe surface, copy engines, overlapped with the bands still rendering) - no collective behind the frame
+    peer = sharding.deliver_to_root(surf, y0, sh, size, size) if striped and env.dist is not None and world > 1 else None
 
     def gather():   # striped surfaces only: the finished stripes are gathered into one image on rank 0 (NCCL over NVLink)
         if not striped or env.dist is None:
@@ -501,7 +504,8 @@ def measure(env, w, rule, steps, strong_world=None):
             t1 = time.perf_counter()
         assert st == 0, st
         t2 = time.perf_counter()
-        gather()
+        if peer is None:
+            gather()
         assert L.vkvg_b200_surface_read_premultiplied(surf.h, out_t.data_ptr()) == 0
         t3 = time.perf_counter()
         parts[0] += t1 - t0
@@ -518,7 +522,15 @@ def measure(env, w, rule, steps, strong_world=None):
         e2e_one()
     frame = out_t.numpy().copy()
     checksum = int(frame.view(np.uint32).sum(dtype=np.uint64))
-    L.vkvg_b200_surface_set_readback(surf.h, None)   # (the device-timed runs below render only)
+    if peer is None:
+        L.vkvg_b200_surface_set_readback(surf.h, None)   # (the device-timed runs below render only)
+    else:   # (... and deliver: the root's picture must hold every rank's rows)
+        peer.barrier()
+        sums = torch.tensor([checksum if sh > 0 else 0, 0], dtype=torch.int64, device="cuda")
+        if rank == 0:
+            sums[1] = peer.full.as_tensor().view(torch.int32).to(torch.int64).bitwise_and(0xffffffff).sum()
+        env.dist.all_reduce(sums)
+        assert int(sums[0]) == int(sums[1]), "the root's picture is not the sum of the stripes: %d != %d" % (int(sums[0]), int(sums[1]))
     dev.set_profiling(True)
     dev.set_stage_timing(True)
     dev.time_resident(surf, 2, True, True)   # warm the resident path (buffers sized, L2 scratch allocated)
@@ -540,11 +552,35 @@ def measure(env, w, rule, steps, strong_world=None):
     graph_replays = dev.graph_replays() - g0
     env.barrier()   # (the ranks leave the render loop at different times: the first gather must not be charged for the wait)
     gather_ms[0] = 0.0
-    for _ in range(steps if striped else 0):
-        gather()
-    env.barrier()
-    ms_step = env.max_over_ranks((st["ms_total"] + gather_ms[0]) / steps)
-    gather_step_ms = env.max_over_ranks(gather_ms[0] / steps)
+    notify_ms = 0.0
+    if peer is not None:
+        # the frame time above already holds the delivery (the stream that renders joins the copy stream before the end event); what a
+        # consumer on the root still needs is the ranks' word that their rows are there: one barrier per frame, timed on its own
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            env.dist.barrier()
+        torch.cuda.synchronize()
+        notify_ms = (time.perf_counter() - t0) / 20 * 1e3
+        peer.surf.set_readback(None)      # the NCCL gather of the same stripes behind a render-only frame, for comparison
+        dev.time_resident(surf, 4, True, True)   # (another read-back target is another graph: captured here)
+        env.barrier()
+        render_only = dev.time_resident(surf, steps, True, True)
+        env.barrier()
+        for _ in range(steps):
+            gather()
+        peer.surf.set_readback(peer.target or None)
+        dev.time_resident(surf, 4, True, True)
+        env.barrier()
+        ms_step = env.max_over_ranks(st["ms_total"] / steps) + env.max_over_ranks(notify_ms)
+        gather_step_ms = env.max_over_ranks(gather_ms[0] / steps)
+        render_only_ms = env.max_over_ranks(render_only["ms_total"] / steps)
+    else:
+        for _ in range(steps if striped else 0):
+            gather()
+        env.barrier()
+        ms_step = env.max_over_ranks((st["ms_total"] + gather_ms[0]) / steps)
+        gather_step_ms = env.max_over_ranks(gather_ms[0] / steps)
     # ---- end to end through the C ABI with host buffers ----
     dev.set_profiling(False)   # flushes return as soon as the work is queued; the read-back waits for it
     if not striped:
@@ -597,7 +633,9 @@ def measure(env, w, rule, steps, strong_world=None):
         "metric": name, "value": scale_units * units / (ms_step * 1e-3), "unit": unit, "ms_per_step": ms_step, "scaling": "strong" if strong else "weak",
         "config": {"workload": WORKLOAD_NAMES[w] if args.coverage == "msaa" else WORKLOAD_NAMES[w].replace("4 samples", "analytic coverage"),
                    "rule": rule, "samples": 4 if args.coverage == "msaa" else 0, "coverage": args.coverage,
-                   "sharding": ("tile-row stripes of one surface over %d ranks, %.3f ms gather to rank 0 per step" % (world, gather_step_ms)) if striped else (
+                   "sharding": (("tile-row stripes of one surface over %d ranks, finished bands delivered into rank 0's picture over NVLink while later bands render "
+                                 "(+ %.3f ms barrier per frame); render-only frame %.3f ms, NCCL gather behind it %.3f ms" % (world, notify_ms, render_only_ms, gather_step_ms)) if peer is not None
+                                else "tile-row stripes of one surface over %d ranks, %.3f ms gather to rank 0 per step" % (world, gather_step_ms)) if striped else (
                        "%d canvases per rank in %d flushes of %d" % (C5B_CANVASES // world, reps, C5B_BATCH) if w == "c5b" else "one independent canvas per rank"),
                    "l2": "256 MiB scratch overwritten between timed steps",
                    "launch": ("one CUDA graph replay per flush (%d of %d flushes)" % (graph_replays, steps * reps)) if use_graph else "plain kernel launches",
@@ -615,6 +653,9 @@ def measure(env, w, rule, steps, strong_world=None):
     }
     if striped:
         rec["gather_ms"] = gather_step_ms
+        if peer is not None:
+            rec["delivery"] = {"how": "peer bands", "notify_ms": notify_ms, "render_only_ms": render_only_ms, "nccl_gather_ms": gather_step_ms}
+            peer.close()
     if w == "c1":   # vkvg_surface_write_to_png timed separately (un-premultiply on the device, read-back, deflate on the host)
         path = "/tmp/vkvg_b200_bench_tiger_%d.png" % rank
         ts = []
@@ -635,7 +676,7 @@ def measure(env, w, rule, steps, strong_world=None):
 
 def slim(rec):
     """what a sub-record of the headline line keeps"""
-    keep = ("metric", "value", "unit", "ms_per_step", "scaling", "stage_ms", "gather_ms", "write_to_png_ms", "gpu_launches")
+    keep = ("metric", "value", "unit", "ms_per_step", "scaling", "stage_ms", "gather_ms", "delivery", "write_to_png_ms", "gpu_launches")
     out = {k: rec[k] for k in keep if k in rec}
     out["workload"] = rec["config"]["workload"]
     out["rule"] = rec["config"]["rule"]
@@ -654,7 +695,7 @@ def run_ours(args):
     line = {"metric": rec["metric"], "value": rec["value"], "unit": rec["unit"], "n_gpus": env.world, "steps": steps, "warmup": warmup,
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": rec["scaling"], "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic"}
     line.update({k: rec[k] for k in ("config", "e2e", "gpu_launches", "clocks", "roofline", "stage_ms", "stage_ms_note") if k in rec})
-    for k in ("gather_ms", "write_to_png_ms"):
+    for k in ("gather_ms", "delivery", "write_to_png_ms"):
         if k in rec:
             line[k] = rec[k]
     sub_steps = max(3, min(steps, 10))

@@ -71,6 +71,16 @@ vkvg_public vkvg_status_t vkvg_b200_surface_read_premultiplied(VkvgSurface surf,
  * waits for the last band instead of copying the whole image after the whole frame.  NULL switches it off; the memory must stay valid
  * until then. */
 vkvg_public vkvg_status_t vkvg_b200_surface_set_readback(VkvgSurface surf, unsigned char *host_rgba);
+/* The same delivery to ANOTHER GPU of the node (tile-row stripes of one picture, one process per GPU; no counterpart in the reference, which
+ * renders a surface on one device): the root exports the image of its full-height surface as a 64-byte inter-process handle
+ * (cudaIpcMemHandle_t), every other rank opens it - the pointer is the root's premultiplied RGBA8 image, row-major - and names
+ * `ptr + y0 * width * 4` as the read-back target of its stripe surface: finished bands of the stripe then travel over NVLink on the copy
+ * engines while later bands render, and no gather follows the frame.  The target of vkvg_b200_surface_set_readback may therefore be host
+ * memory or device memory of any GPU this process can reach.  A rank must synchronise (vkvg_b200_surface_read_premultiplied onto the same
+ * pointer returns once its bands are delivered) before it tells the root, by whatever barrier the ranks share, that its rows are there. */
+vkvg_public vkvg_status_t vkvg_b200_surface_ipc_export(VkvgSurface surf, unsigned char *handle64);
+vkvg_public void         *vkvg_b200_ipc_open(VkvgDevice dev, const unsigned char *handle64);
+vkvg_public vkvg_status_t vkvg_b200_ipc_close(VkvgDevice dev, void *ptr);
 
 /* ---- 2. measurement ------------------------------------------------------------------------------------ */
 typedef struct {

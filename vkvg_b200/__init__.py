@@ -126,6 +126,7 @@ _SIGS = {
     "vkvg_b200_flush_capture_winding": (None, [_p, _p]),
     "vkvg_b200_winding": (_i, [_p, _p, C.c_uint64, _u, _u, _p]),
     "vkvg_b200_surface_read_premultiplied": (_i, [_p, _p]), "vkvg_b200_surface_set_readback": (_i, [_p, _p]),
+    "vkvg_b200_surface_ipc_export": (_i, [_p, _p]), "vkvg_b200_ipc_open": (_p, [_p, _p]), "vkvg_b200_ipc_close": (_i, [_p, _p]),
     "vkvg_b200_launch_count": (C.c_uint64, []), "vkvg_b200_set_profiling": (None, [_p, _i]),
     "vkvg_b200_last_stats": (None, [_p, C.POINTER(Stats)]), "vkvg_b200_device_synchronize": (None, [_p]),
     "vkvg_b200_device_ordinal": (_i, [_p]), "vkvg_b200_surface_device_pointer": (_p, [_p]),
@@ -220,6 +221,16 @@ class Device:
     def synchronize(self):
         lib().vkvg_b200_device_synchronize(self.h)
 
+    def ipc_open(self, handle):
+        """device address, valid in this process, of the surface image another process exported with Surface.ipc_export()"""
+        p = lib().vkvg_b200_ipc_open(self.h, C.c_char_p(handle))
+        if not p:
+            raise VkvgError("vkvg_b200_ipc_open failed (no peer access between the two GPUs, or not the same node)")
+        return int(p)
+
+    def ipc_close(self, address):
+        lib().vkvg_b200_ipc_close(self.h, C.c_void_p(address))
+
     def time_resident(self, surf, steps, clear_first=True, flush_l2=True):
         """re-run the pipeline `steps` times on the batch kept by the last flush; returns summed stats (ms) as a dict."""
         s = Stats()
@@ -275,6 +286,31 @@ class Surface:
 
     def clear(self):
         lib().vkvg_surface_clear(self.h)
+
+    def device_pointer(self):
+        """address of the premultiplied RGBA8 image in device memory (row-major, width * 4 bytes per row)"""
+        return int(lib().vkvg_b200_surface_device_pointer(self.h))
+
+    def set_readback(self, address):
+        """every later flush also delivers the image to `address`, band by band while later bands render: pinned host memory, or device
+        memory of this or another GPU (Device.ipc_open).  None / 0 switches it off."""
+        st = lib().vkvg_b200_surface_set_readback(self.h, C.c_void_p(address or None))
+        if st:
+            raise VkvgError("vkvg_b200_surface_set_readback: status %d" % st)
+
+    def wait_delivered(self, address):
+        """returns once the last flush's image is at the read-back target `address` (no copy when the flush delivered it itself)"""
+        st = lib().vkvg_b200_surface_read_premultiplied(self.h, C.c_void_p(address))
+        if st:
+            raise VkvgError("vkvg_b200_surface_read_premultiplied: status %d" % st)
+
+    def ipc_export(self):
+        """64-byte inter-process handle of the image (cudaIpcMemHandle_t) for Device.ipc_open in another process of this node"""
+        buf = C.create_string_buffer(64)
+        st = lib().vkvg_b200_surface_ipc_export(self.h, buf)
+        if st:
+            raise VkvgError("vkvg_b200_surface_ipc_export: status %d" % st)
+        return bytes(buf.raw)
 
     def as_tensor(self):
         """the premultiplied RGBA8 image in device memory as a (H, W, 4) uint8 torch tensor WITHOUT a copy (what an NCCL gather of

@@ -261,6 +261,32 @@ void vkb_surface_set_readback(vkb_surface_impl *s, uint8_t *host) {
     s->readback = host;
     s->readback_valid = false;
 }
+// The image of a surface as an inter-process handle (cudaIpcMemHandle_t, 64 bytes): another process - another GPU of the node - opens it and
+// names the returned pointer as the read-back target of its own stripe surface, whose bands then travel over NVLink while later bands render.
+int vkb_surface_ipc_export(vkb_surface_impl *s, void *handle64) {
+    dev_enter(s->dev);
+    if (finish_pending(s->dev)) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, s->image.p) != cudaSuccess) { cudaGetLastError(); return 1; }
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+void *vkb_ipc_open(vkb_device_impl *d, const void *handle64) {
+    dev_enter(d);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+int vkb_ipc_close(vkb_device_impl *d, void *p) {
+    dev_enter(d);
+    finish_pending(d);
+    cudaStreamSynchronize(d->copy_stream);
+    if (cudaIpcCloseMemHandle(p) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return 0;
+}
 int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) {
     vkb_device_impl *d = s->dev;
     dev_enter(d);
@@ -276,7 +302,7 @@ int vkb_surface_download(vkb_surface_impl *s, uint8_t *out, bool unpremultiply) 
         vkb_launch_unpremultiply(src, (uint64_t)s->w * s->h, d->tmp_image.as<uint32_t>(), d->stream);
         src = d->tmp_image.as<uint32_t>();
     }
-    VKB_CUDA_OK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, d->stream));
+    VKB_CUDA_OK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDefault, d->stream));  // (out: host memory, or device memory of any GPU in reach)
     VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
     return g_cuda_failed;
 }
@@ -690,8 +716,8 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     if (d->capturing) d->graph_fine_events = cudaEventRecordWithFlags(d->ev_fine0, st, cudaEventRecordExternal) == cudaSuccess;
     else VKB_EVENT_RECORD(d, d->ev_fine0);
     // a surface with a read-back target: bands of tile rows, each copied to the host on the copy stream as soon as it is finished
-    const bool     banded  = surf->readback && !(cap && cap->winding) && sd.tiles_y >= 2 * VKB_MAX_BANDS;
-    const uint32_t n_bands = banded ? (sd.tiles_y >= 128 ? 4u : 2u) : 1u;
+    const bool     banded  = surf->readback && !(cap && cap->winding);
+    const uint32_t n_bands = banded ? (sd.tiles_y >= 128 ? 4u : (sd.tiles_y >= 2 * VKB_MAX_BANDS ? 2u : 1u)) : 1u;  // (a small surface: one band, copied behind the frame)
     d->band_counters.ensure(VKB_MAX_BANDS * 4, st);
     if (banded) VKB_CUDA_OK(cudaMemsetAsync(d->band_counters.p, 0, VKB_MAX_BANDS * 4, st));
     for (uint32_t k = 0; k < n_bands; k++) {
@@ -703,7 +729,8 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
             const size_t y0 = (size_t)r0 * VKB_TILE, y1 = r1 * VKB_TILE < sd.height ? (size_t)r1 * VKB_TILE : sd.height;
             VKB_CUDA_OK(cudaEventRecord(d->ev_band[k], st));
             VKB_CUDA_OK(cudaStreamWaitEvent(d->copy_stream, d->ev_band[k], 0));
-            VKB_CUDA_OK(cudaMemcpyAsync(surf->readback + y0 * sd.width * 4, surf->image.as<uint8_t>() + y0 * sd.width * 4, (y1 - y0) * sd.width * 4, cudaMemcpyDeviceToHost,
+            // (cudaMemcpyDefault: the target is host memory for a read-back, this or a PEER device's memory for a stripe delivered to its root)
+            VKB_CUDA_OK(cudaMemcpyAsync(surf->readback + y0 * sd.width * 4, surf->image.as<uint8_t>() + y0 * sd.width * 4, (y1 - y0) * sd.width * 4, cudaMemcpyDefault,
                                         d->copy_stream));
         }
     }

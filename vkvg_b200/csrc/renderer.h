@@ -101,6 +101,9 @@ unsigned long long vkb_device_graph_replays(vkb_device_impl *d);
 
 vkb_surface_impl *vkb_surface_new(vkb_device_impl *d, uint32_t w, uint32_t h, uint32_t full_h, uint32_t origin_y);
 int               vkb_surface_copy_to_device(vkb_surface_impl *s, void *dst);
+int               vkb_surface_ipc_export(vkb_surface_impl *s, void *handle64);
+void             *vkb_ipc_open(vkb_device_impl *d, const void *handle64);
+int               vkb_ipc_close(vkb_device_impl *d, void *p);
 void              vkb_surface_free(vkb_surface_impl *s);
 void              vkb_surface_clear(vkb_surface_impl *s);
 // clip support: forget the stencil plane (a new context clears the stencil attachment with its first render pass,

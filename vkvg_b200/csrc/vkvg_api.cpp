@@ -382,6 +382,23 @@ vkvg_status_t vkvg_b200_surface_set_readback(VkvgSurface surf, unsigned char *ho
     vkb_surface_set_readback(surf->impl, host_rgba);
     return VKVG_STATUS_SUCCESS;
 }
+vkvg_status_t vkvg_b200_surface_ipc_export(VkvgSurface surf, unsigned char *handle64) {
+    if (vkvg_surface_status(surf)) return VKVG_STATUS_INVALID_SURFACE;
+    if (!handle64) return VKVG_STATUS_NULL_POINTER;
+    std::lock_guard<std::mutex> lk(surf->dev->mtx);
+    return vkb_surface_ipc_export(surf->impl, handle64) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
+}
+void *vkvg_b200_ipc_open(VkvgDevice dev, const unsigned char *handle64) {
+    if (vkvg_device_status(dev) || !handle64) return NULL;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    return vkb_ipc_open(dev->impl, handle64);
+}
+vkvg_status_t vkvg_b200_ipc_close(VkvgDevice dev, void *ptr) {
+    if (vkvg_device_status(dev)) return VKVG_STATUS_DEVICE_ERROR;
+    if (!ptr) return VKVG_STATUS_NULL_POINTER;
+    std::lock_guard<std::mutex> lk(dev->mtx);
+    return vkb_ipc_close(dev->impl, ptr) ? VKVG_STATUS_DEVICE_ERROR : VKVG_STATUS_SUCCESS;
+}
 vkvg_status_t vkvg_b200_surface_read_premultiplied(VkvgSurface surf, unsigned char *rgba) {
     if (vkvg_surface_status(surf)) return VKVG_STATUS_INVALID_STATUS;
     if (!rgba) return VKVG_STATUS_WRITE_ERROR;

@@ -5,6 +5,9 @@ needs an exchange:
     SAME drawing calls on a stripe surface (`vkvg_b200_surface_create_stripe`); the rows are gathered afterwards with one
     all-gather of contiguous RGBA8 rows (NCCL over NVLink on GPUs, gloo in the CPU tests) only when an assembled image is
     needed;
+    or - `deliver_to_root` - every rank names its rows of the ROOT's surface (opened through CUDA IPC) as the read-back target of
+    its stripe: finished bands of tile rows cross NVLink on the copy engines while later bands still render, and nothing follows
+    the frame but a barrier;
   * independent canvases: canvas i belongs to rank i mod world; no collective at all.
 
 The functions here are pure host logic plus `torch.distributed` plumbing; rendering itself is done by whoever calls them
@@ -121,3 +124,50 @@ def gather_surface_to_root(surf, height, out=None, root=0, group=None):
     surf.dev.synchronize()   # the library renders on its own stream
     h = stripe_rows(height, dist.get_world_size(group))[dist.get_rank(group)][1]
     return gather_to_root(surf.as_tensor()[:max(h, 0)], height, out=out, root=root, group=group)
+
+
+class StripeDelivery:
+    """What deliver_to_root returns.  `full` is the root's whole-picture Surface (None elsewhere); `target` the address this rank's stripe
+    is delivered to (0 for a rank without rows).  wait() returns when THIS rank's rows of the last flush have arrived; the ranks then
+    meet at whatever barrier they share (dist.barrier) before the root reads `full`."""
+
+    def __init__(self, surf, full, target, base, group):
+        self.surf, self.full, self.target, self._base, self.group = surf, full, target, base, group
+
+    def wait(self):
+        if self.target:
+            self.surf.wait_delivered(self.target)
+        else:
+            self.surf.dev.synchronize()
+
+    def barrier(self):
+        import torch.distributed as dist
+        self.wait()
+        dist.barrier(self.group)
+
+    def close(self):
+        self.surf.set_readback(None)
+        if self._base:
+            self.surf.dev.ipc_close(self._base)
+            self._base = 0
+
+
+def deliver_to_root(surf, y0, h, width, height, root=0, group=None):
+    """GPU path, no collective on the data path: the root creates the width x height surface and exports its image (cudaIpcMemHandle_t),
+    every other rank opens it and sets rows [y0, y0 + h) of it as the read-back target of its stripe surface `surf` (the root does the same
+    with a plain device pointer).  From then on every flush of `surf` lands in the root's picture band by band, overlapped with the
+    rendering of the later bands (vkvg_b200_surface_set_readback).  Returns a StripeDelivery."""
+    import vkvg_b200 as v
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    full = v.Surface(surf.dev, width, height) if rank == root else None
+    box = [full.ipc_export() if rank == root else None]
+    dist.broadcast_object_list(box, src=root, group=group)
+    base = 0
+    if rank == root:
+        addr = full.device_pointer()
+    else:
+        base = addr = surf.dev.ipc_open(box[0])
+    target = addr + y0 * width * 4 if h > 0 else 0
+    surf.set_readback(target or None)
+    return StripeDelivery(surf, full, target, base, group)
