@@ -566,7 +566,9 @@ def measure(env, w, rule, steps, strong_world=None):
         dev.time_resident(surf, 4, True, True)   # (another read-back target is another graph: captured here)
         env.barrier()
         render_only = dev.time_resident(surf, steps, True, True)
+        gather()   # (the first one sets up NCCL's point-to-point channels)
         env.barrier()
+        gather_ms[0] = 0.0
         for _ in range(steps):
             gather()
         peer.surf.set_readback(peer.target or None)
