@@ -26,6 +26,8 @@
 #include "pipeline.h"
 #include <cstdlib>
 
+#define VKB_EDGE_GRID (148u * 8u * 8u)  // most blocks of a per-edge / per-vertex / per-triangle kernel: eight waves of eight 256-thread blocks per SM, grid-stride beyond
+
 // ---- vertex stage: shaders/vkvg_main.vert:74-79 + viewport + 8-bit sub-pixel snap (round half up) ----
 __device__ __forceinline__ void vs_snap(const float *m, float W, float H, float x, float y, int32_t &fx, int32_t &fy) {
     float px = m[0] * x + m[2] * y + m[4];
@@ -365,10 +367,12 @@ __global__ void __launch_bounds__(128)
 nz_split_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode,
            const vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap, int32_t *bbox) {
-    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (C->overflow) return;
     const uint32_t n_items = C->n[VKC_FILL];
-    if ((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) >= n_items) return;  // whole warps leave; a partial warp stays for the shuffles below
+    // whole warps stride the LIVE items (the grid comes from the capacity of the item space, capped: on a stripe most of the scene's sub-paths
+    // were culled and have no items); a partial warp stays for the shuffles below
+    for (uint32_t wb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < n_items; wb += gridDim.x * blockDim.x) {
+    const uint32_t item = wb + (threadIdx.x & 31u);
     const bool live = item < n_items;
     FillItem   f;
     NzHit      loc[VKB_NZ_LOCAL];
@@ -394,7 +398,7 @@ nz_split_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, co
     if ((threadIdx.x & 31) == 31 && incl) base = atomicAdd(n_out, incl);
     uint32_t o = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
     BoxAcc   box;
-    if (!live) { bbox_accumulate(bbox, 0, box); return; }
+    if (!live) { bbox_accumulate(bbox, 0, box); continue; }
     const vkb_xform &xf = xforms[draws[f.d].xform_stroke & 0xFFFF];
     float2           prev = f.a;
     auto put = [&](float2 to) {
@@ -422,6 +426,7 @@ nz_split_k(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, co
     }
     put(f.b);
     bbox_accumulate(bbox, f.d, box);
+    }
 }
 __global__ void commit_fedges_k(vkb_counts *C, const uint32_t *n_out) {
     if (C->overflow) return;
@@ -444,7 +449,7 @@ void vkb_launch_nz_split(const float2 *pts, const vkb_draw *draws, const vkb_xfo
                          uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, const uint32_t *draw_first_job, uint32_t n_draws, const uint8_t *nz_mode,
                          uint32_t cap_items, vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap_edges, int32_t *draw_bbox, cudaStream_t s) {
     if (!cap_items || !n_jobs) return;
-    nz_split_k<<<vkb_div_up(cap_items, 128), 128, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, draw_first_job, n_draws, nz_mode, C, sd,
+    nz_split_k<<<min(vkb_div_up(cap_items, 128), VKB_EDGE_GRID * 2u), 128, 0, s>>>(pts, draws, xforms, job_draw, job_sp, job_base, n_jobs, sp_first, sp_count, draw_first_job, n_draws, nz_mode, C, sd,
                                                           edges, edge_draw, n_out, cap_edges, draw_bbox);
     VKB_LAUNCHED();
     commit_fedges_k<<<1, 1, 0, s>>>(C, n_out);
@@ -468,7 +473,6 @@ __device__ __forceinline__ bool tri_has(const uint32_t (&i)[3], uint32_t u, uint
 __device__ __forceinline__ int tri_dir(const uint32_t (&i)[3], uint32_t u, uint32_t v) {
     return ((i[0] == u && i[1] == v) || (i[1] == u && i[2] == v) || (i[2] == u && i[0] == v)) ? 1 : -1;
 }
-#define VKB_EDGE_GRID (148u * 8u * 8u)  // most blocks of a per-edge / per-vertex / per-triangle kernel: eight waves of eight 256-thread blocks per SM, grid-stride beyond
 __device__ __forceinline__ void tri_idx(const uint32_t *inds, uint32_t n_tris, long long t, uint32_t (&i)[3]) {
     if (t < 0 || t >= (long long)n_tris) { i[0] = i[1] = i[2] = 0xffffffffu; return; }
     i[0] = inds[3 * t]; i[1] = inds[3 * t + 1]; i[2] = inds[3 * t + 2];
