@@ -13,7 +13,8 @@
 #define TWO_OVER_PIF 0.63661977236758134308f  // the reference's M_2_PIF (2/pi), used where 2*pi was meant
 #define VKB_BEZ_STACK 40                      // reference limit is 100 levels; finite input never gets near 40
 
-// The counting pass keeps the first VKB_FLAT_CACHE points of every curved element (most cubics flatten to fewer), so the
+// The counting pass keeps the first cache_n points (VKB_FLAT_CACHE, or VKB_FLAT_CACHE_SMALL_SCENE for batches of few elements, where the
+// longest curve of the frame is what the emitting pass waits for) of every curved element (most cubics flatten to fewer), so the
 // emitting pass copies them instead of walking the subdivision tree a second time.
 #define VKB_FLAT_CACHE 16
 struct PointSink {
@@ -22,14 +23,14 @@ struct PointSink {
     uint32_t n;
     uint8_t  flag;
     bool     emit;
-    float2  *cache;    // counting pass: this element's VKB_FLAT_CACHE slots, or null
-    uint32_t n_cached;
+    float2  *cache;    // counting pass: this element's cache_cap slots, or null
+    uint32_t n_cached, cache_cap;
     __device__ __forceinline__ void add(float x, float y) {
         if (isnan(x) || isnan(y)) return;  // _add_point drops NaN, internal.c:224
         if (emit) {
             pts[n]   = make_float2(x, y);
             flags[n] = flag;
-        } else if (cache && n_cached < VKB_FLAT_CACHE) cache[n_cached++] = make_float2(x, y);
+        } else if (cache && n_cached < cache_cap) cache[n_cached++] = make_float2(x, y);
         n++;
     }
 };
@@ -127,7 +128,7 @@ __device__ __forceinline__ void flatten_arc(PointSink &s, const float *e) {
 
 template <bool EMIT>
 __global__ void __launch_bounds__(128) flatten_k(const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, uint32_t *counts,
-                                                const uint32_t *offsets, float2 *pts, uint8_t *flags, const vkb_counts *C, float2 *cache) {
+                                                const uint32_t *offsets, float2 *pts, uint8_t *flags, const vkb_counts *C, float2 *cache, uint32_t cache_n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_elems) return;
     if (EMIT && C->overflow) return;  // the points do not fit the buffers of this attempt (dev_util.cuh: vkb_counts)
@@ -139,13 +140,13 @@ __global__ void __launch_bounds__(128) flatten_k(const uint32_t *elem_hdr, const
     s.pts   = pts;
     s.flags = flags;
     s.flag  = (hdr & VKB_EL_CURVED) ? 1 : 0;
-    s.cache = (!EMIT && cache && (hdr & VKB_EL_TYPE_MASK) != VKB_EL_POINT) ? cache + (size_t)i * VKB_FLAT_CACHE : nullptr;
-    s.n_cached = 0;
+    s.cache = (!EMIT && cache && (hdr & VKB_EL_TYPE_MASK) != VKB_EL_POINT) ? cache + (size_t)i * cache_n : nullptr;
+    s.n_cached = 0; s.cache_cap = cache_n;
     uint32_t start = s.n;
     if (EMIT && cache && (hdr & VKB_EL_TYPE_MASK) != VKB_EL_POINT) {
         const uint32_t cnt = (i + 1 < n_elems ? offsets[i + 1] : C->n[VKC_POINTS]) - start;
-        if (cnt <= VKB_FLAT_CACHE) {  // the counting pass already produced every point of this element
-            const float2 *c = cache + (size_t)i * VKB_FLAT_CACHE;
+        if (cnt <= cache_n) {  // the counting pass already produced every point of this element
+            const float2 *c = cache + (size_t)i * cache_n;
             for (uint32_t k = 0; k < cnt; k++) { pts[start + k] = c[k]; flags[start + k] = s.flag; }
             return;
         }
@@ -174,15 +175,15 @@ __global__ void subpath_ranges_k(const vkb_subpath *sps, uint32_t n_sp, const ui
     sp_count[i] = n;
 }
 
-void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, float2 *cache, cudaStream_t s) {
+void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, float2 *cache, uint32_t cache_n, cudaStream_t s) {
     if (!n) return;
-    flatten_k<false><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, nullptr, nullptr, nullptr, nullptr, cache);
+    flatten_k<false><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, nullptr, nullptr, nullptr, nullptr, cache, cache_n);
     VKB_LAUNCHED();
 }
 void vkb_launch_flatten_emit(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, const uint32_t *offsets, float2 *pts, uint8_t *flags,
-                             const vkb_counts *C, float2 *cache, cudaStream_t s) {
+                             const vkb_counts *C, float2 *cache, uint32_t cache_n, cudaStream_t s) {
     if (!n) return;
-    flatten_k<true><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, nullptr, offsets, pts, flags, C, cache);
+    flatten_k<true><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, nullptr, offsets, pts, flags, C, cache, cache_n);
     VKB_LAUNCHED();
 }
 void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_off, uint32_t n_elems, const uint32_t *total,

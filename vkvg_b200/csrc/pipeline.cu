@@ -785,15 +785,17 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     d->fjob_base.ensure((size_t)(d->n_fjobs + 1) * 4, st);
     d->sjob_base.ensure((size_t)(d->n_sjobs + 1) * 4, st);
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-    // curve-heavy batches keep the first 16 points of every element from the counting pass (16 * 8 B per element)
-    float2 *fcache = nullptr;
+    // curve-heavy batches keep the first 16 points of every element from the counting pass (16 * 8 B per element); batches of few elements
+    // (a tiger: 2500) the first 64 - there the emitting pass lasts as long as its longest curve, and with 64 slots it only copies
+    float2        *fcache = nullptr;
+    const uint32_t fcache_n = d->n_elems <= 65536 ? 64u : 16u;
     if (d->n_curves && (uint64_t)d->n_curves * 8 >= d->n_elems) {
-        d->flat_cache.ensure((size_t)d->n_elems * 16 * 8, st);
+        d->flat_cache.ensure((size_t)d->n_elems * fcache_n * 8, st);
         if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
         fcache = d->flat_cache.as<float2>();
     }
     if (d->n_elems) {
-        vkb_launch_flatten_count(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), fcache, st);
+        vkb_launch_flatten_count(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), fcache, fcache_n, st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->elem_cnt.as<uint32_t>(), d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals, d->scan, st);
         vkb_launch_subpath_ranges(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_cnt.as<uint32_t>(), d->n_elems, (uint32_t *)totals,
                                   d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), st);
@@ -820,7 +822,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     VKB_LAUNCHED();
     if (d->n_elems)
         vkb_launch_flatten_emit(d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->elem_cnt.as<uint32_t>(), d->pts.as<float2>(),
-                                d->ptflags.as<uint8_t>(), C, fcache, st);
+                                d->ptflags.as<uint8_t>(), C, fcache, fcache_n, st);
     if (nz_split) {  // NON_ZERO fills / clips as libtess makes them: classify the draws, then every fill edge in its pieces
         d->nz_mode.ensure((size_t)d->n_draws + 16, st);
         d->edges.ensure(((size_t)cv[VKC_EDGES] + 1) * 16, st);

@@ -5,10 +5,10 @@
 #include "vkb_types.h"
 
 // ---- flatten.cu ----
-// cache: n * VKB_FLAT_CACHE points kept by the counting pass for the emitting pass (null: every curve is walked twice)
-void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, float2 *cache, cudaStream_t s);
+// cache: n * cache_n points kept by the counting pass for the emitting pass (null: every curve is walked twice)
+void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, float2 *cache, uint32_t cache_n, cudaStream_t s);
 void vkb_launch_flatten_emit(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, const uint32_t *offsets, float2 *pts, uint8_t *flags,
-                             const vkb_counts *C, float2 *cache, cudaStream_t s);
+                             const vkb_counts *C, float2 *cache, uint32_t cache_n, cudaStream_t s);
 void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_off, uint32_t n_elems, const uint32_t *total,
                                uint32_t *sp_first, uint32_t *sp_count, cudaStream_t s);
 
