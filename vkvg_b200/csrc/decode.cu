@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(256) vkd_subpaths_k(DecodeBufs b) {
     }
     if ((b.cmds[j] & 0xFF) == VKVG_B200_OP_NEW_PATH) bad = true;  // vkvg_new_path drops the elements of an unfinished sub-path
     b.subpaths[s] = vkb_subpath{first, n, flags, 0};
+    if (n > VKB_SP_LONG) atomicMax(&b.census->max_sp_elems, n);
     if (bad) atomicOr(b.irregular, 16u);
 }
 

@@ -19,5 +19,6 @@ struct vkb_decode_census {  // read back once per stream: what the host sizes th
     uint32_t last_setter_arg[9];  // where its arguments start in `args`
     float    final_mat[6];
     uint32_t final_band;
-    uint32_t pad[2];
+    uint32_t max_sp_elems;     // elements of the longest sub-path when some hold more than 1024 (else 0): the flush then reduces their boxes block by block
+    uint32_t pad;
 };

@@ -136,8 +136,14 @@ template <class T, int BLOCK> __device__ __forceinline__ T block_excl_scan(T v, 
 #define VKB_SCAN_CHUNK (VKB_SCAN_BLOCK * VKB_SCAN_ITEMS)
 
 // n = n_add (+ C->n[idx] when C is given: a count that lives on the device, see vkb_counts)
-template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) scan_reduce_k(const TI *in, T *sums, uint64_t n, const vkb_counts *C, int idx) {
-    if (C) { if (C->overflow) return; n += C->n[idx]; }
+// The block that finishes LAST (a ticket from *ticket, which it hands back as zero: the next scan - or the next replay of a captured graph -
+// starts from a clean counter) goes on to scan the chunk sums, in chunk order, so the middle launch of the classic three is gone.
+// Cw: the counts an overflow of which turns the scan into a no-op, and where the total is committed (commit_idx >= 0).
+template <class TI, class T>
+__global__ void __launch_bounds__(VKB_SCAN_BLOCK) scan_reduce_k(const TI *in, T *sums, uint64_t n, const vkb_counts *C, int idx, uint32_t *ticket, T *total_out, vkb_counts *Cw,
+                                                                 int commit_idx) {
+    if (Cw && Cw->overflow) return;   // (uniform over the grid: nothing sets the flag while this kernel runs but its own last block, at the very end)
+    if (C) n += C->n[idx];
     uint64_t base = (uint64_t)blockIdx.x * VKB_SCAN_CHUNK;
     T        acc  = 0;
 #pragma unroll
@@ -147,24 +153,33 @@ template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) s
     }
     T total;
     block_excl_scan<T, VKB_SCAN_BLOCK>(acc, total);
-    if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-template <class T> __global__ void __launch_bounds__(1024) scan_sums_k(T *sums, uint32_t m, T *total_out, vkb_counts *C, int commit_idx) {
-    if (C && C->overflow) return;
-    __shared__ T carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ bool is_last;
+    __shared__ T    carry;
+    if (threadIdx.x == 0) {
+        sums[blockIdx.x] = total;
+        __threadfence();   // the sum is visible before the ticket is
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        carry   = 0;
+    }
     __syncthreads();
-    for (uint32_t base = 0; base < m; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        T        v = i < m ? sums[i] : T(0), tot;
-        T        e = block_excl_scan<T, 1024>(v, tot);
-        if (i < m) sums[i] = carry + e;
+    if (!is_last) return;
+    __threadfence();
+    const uint32_t  m = gridDim.x;
+    volatile T     *vs = sums;   // (written by other blocks: not through this SM's L1)
+    for (uint32_t b0 = 0; b0 < m; b0 += VKB_SCAN_BLOCK) {
+        uint32_t i = b0 + threadIdx.x;
+        T        v = i < m ? vs[i] : T(0), tot;
+        T        e = block_excl_scan<T, VKB_SCAN_BLOCK>(v, tot);
+        if (i < m) vs[i] = carry + e;
         __syncthreads();
         if (threadIdx.x == 0) carry += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
-    if (threadIdx.x == 0 && commit_idx >= 0) vkc_commit(C, commit_idx, (uint32_t)carry);  // the total is itself a device-side count
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+        if (total_out) *total_out = carry;
+        if (commit_idx >= 0) vkc_commit(Cw, commit_idx, (uint32_t)carry);  // the total is itself a device-side count
+    }
 }
 // short inputs: one block does the whole scan in one launch.  Up to ONE pass of the block (8192 items): the 32 k path-tile and 16 k histogram
 // scans of a tiger frame are faster as three launches of many blocks than as four sequential passes of one (measured, threshold 64 k / 16 k /
@@ -199,8 +214,27 @@ template <class TI, class T> __global__ void __launch_bounds__(1024) scan_small_
         if (commit_idx >= 0) vkc_commit(C, commit_idx, (uint32_t)carry_s);
     }
 }
+// two independent short scans (each at most VKB_SCAN_SMALL items, lengths known to the host) in one launch: block 0 the first, block 1 the second
+template <class T> __global__ void __launch_bounds__(1024) scan_small2_k(T *a, uint32_t na, T *total_a, T *b, uint32_t nb, T *total_b) {
+    T             *p = blockIdx.x ? b : a, *total_out = blockIdx.x ? total_b : total_a;
+    const uint32_t n = blockIdx.x ? nb : na, b0 = threadIdx.x * 8;
+    T              v[8], acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = b0 + k < n ? p[b0 + k] : T(0);
+        acc += v[k];
+    }
+    T tot;
+    T e = block_excl_scan<T, 1024>(acc, tot);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (b0 + k < n) p[b0 + k] = e;
+        e += v[k];
+    }
+    if (threadIdx.x == 0) *total_out = tot;
+}
 template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) scan_apply_k(const TI *in, T *out, const T *sums, uint64_t n, const vkb_counts *C, int idx) {
-    if (C) { if (C->overflow) return; n += C->n[idx]; }
+    if (C) { if (C->overflow) return; n += C->n[idx]; }   // (an overflow the scan's own commit raised included: the offsets would be of no use)
     // each thread owns VKB_SCAN_ITEMS consecutive items so the order of summation is the input order
     uint64_t base = (uint64_t)blockIdx.x * VKB_SCAN_CHUNK + (uint64_t)threadIdx.x * VKB_SCAN_ITEMS;
     T        v[VKB_SCAN_ITEMS], acc = 0;
@@ -224,7 +258,16 @@ template <class TI, class T> __global__ void __launch_bounds__(VKB_SCAN_BLOCK) s
 // from scan_apply_k, which is deterministic run to run.
 struct ScanScratch {
     DevBuf sums;
+    DevBuf ticket;  // one zeroed word: which block of scan_reduce_k finishes last
 };
+// the zeroed words the "last block" kernels take their tickets from (word 0: scan_reduce_k, word 1: sort_hist_k); each hands its word back as zero
+static inline uint32_t *vkb_scan_ticket(ScanScratch &sc, cudaStream_t s) {
+    if (!sc.ticket.p) {
+        sc.ticket.ensure(256, s);
+        if (sc.ticket.p) VKB_CUDA_OK(cudaMemsetAsync(sc.ticket.p, 0, 256, s));
+    }
+    return sc.ticket.as<uint32_t>();
+}
 // host-known length n; with C the length is n + C->n[idx] and `cap` bounds it (grid and scratch are sized for cap)
 // commit_idx >= 0: the total is committed as count commit_idx of C (checked against its capacity)
 template <class TI, class T>
@@ -243,9 +286,9 @@ static inline void vkb_exclusive_scan(const TI *in, T *out, uint64_t n, T *total
     const vkb_counts *Cn = (C && idx >= 0) ? C : nullptr;
     uint32_t chunks = vkb_div_up(bound, VKB_SCAN_CHUNK);
     sc.sums.ensure((size_t)chunks * sizeof(T), s);
-    scan_reduce_k<TI, T><<<chunks, VKB_SCAN_BLOCK, 0, s>>>(in, sc.sums.as<T>(), n, Cn, idx);
-    VKB_LAUNCHED();
-    scan_sums_k<T><<<1, 1024, 0, s>>>(sc.sums.as<T>(), chunks, total_dev, C, commit_idx);
+    uint32_t *ticket = vkb_scan_ticket(sc, s);
+    if (!sc.sums.p || !ticket) return;  // out of memory: the device is sticky-failed already
+    scan_reduce_k<TI, T><<<chunks, VKB_SCAN_BLOCK, 0, s>>>(in, sc.sums.as<T>(), n, Cn, idx, ticket, total_dev, C, commit_idx);
     VKB_LAUNCHED();
     scan_apply_k<TI, T><<<chunks, VKB_SCAN_BLOCK, 0, s>>>(in, out, sc.sums.as<T>(), n, Cn, idx);
     VKB_LAUNCHED();
@@ -269,9 +312,11 @@ template <int ROUNDS> __device__ __forceinline__ void sort_warp_hist(const uint3
         __syncwarp();
     }
 }
+// ticket != null (short inputs: at most 32 blocks): the block that finishes last also turns the histogram into its exclusive scan - thread d
+// walks the row of digit d - so that the pass is two launches, not three
 template <int ROUNDS>
 static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_hist_k(const uint32_t *keys, uint64_t n, int shift, uint32_t *hist, uint32_t nblocks,
-                                                                     const vkb_counts *C, int idx) {
+                                                                     const vkb_counts *C, int idx, uint32_t *ticket) {
     constexpr int VKB_SORT_ROUNDS = ROUNDS, VKB_SORT_CHUNK = VKB_SORT_BLOCK * ROUNDS;
     if (C) { if (C->overflow) return; n = C->n[idx]; }
     __shared__ uint32_t wc[VKB_SORT_BLOCK / 32][256];
@@ -283,6 +328,24 @@ static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_hist_k(const uint3
     uint32_t sum = 0;
     for (int w = 0; w < VKB_SORT_BLOCK / 32; w++) sum += wc[w][threadIdx.x];
     hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = sum;  // digit-major so one scan yields global offsets
+    if (!ticket) return;
+    __shared__ bool is_last;
+    __threadfence();   // this thread's count is visible before the block's ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    volatile uint32_t *row = hist + (uint64_t)threadIdx.x * nblocks;   // (written by other blocks: not through this SM's L1)
+    uint32_t           rsum = 0, tot;
+    for (uint32_t b = 0; b < nblocks; b++) rsum += row[b];
+    uint32_t base = block_excl_scan<uint32_t, VKB_SORT_BLOCK>(rsum, tot);
+    for (uint32_t b = 0; b < nblocks; b++) {
+        const uint32_t c = row[b];
+        row[b] = base;
+        base += c;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
 }
 template <int ROUNDS>
 static __global__ void __launch_bounds__(VKB_SORT_BLOCK) sort_scatter_k(const uint32_t *keys, const uint32_t *vals, uint32_t *okeys, uint32_t *ovals,
@@ -339,11 +402,13 @@ static inline void vkb_radix_sort(uint32_t *keys, uint32_t *vals, uint64_t n, in
     uint32_t *ka = keys, *va = vals, *kb = sc.k2.as<uint32_t>(), *vb = sc.v2.as<uint32_t>();
     int       passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
+    uint32_t *ticket = (small && nblocks <= 32) ? vkb_scan_ticket(sc.scan, s) : nullptr;   // (then the histogram kernel scans its own output)
+    if (ticket) ticket += 1;
     for (int p = 0; p < passes; p++) {
-        if (small) sort_hist_k<2><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
-        else sort_hist_k<16><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
+        if (small) sort_hist_k<2><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx, ticket);
+        else sort_hist_k<16><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx, nullptr);
         VKB_LAUNCHED();
-        vkb_exclusive_scan<uint32_t, uint32_t>(sc.hist.as<uint32_t>(), sc.hist.as<uint32_t>(), (uint64_t)256 * nblocks, nullptr, sc.scan, s);
+        if (!ticket) vkb_exclusive_scan<uint32_t, uint32_t>(sc.hist.as<uint32_t>(), sc.hist.as<uint32_t>(), (uint64_t)256 * nblocks, nullptr, sc.scan, s);
         if (small) sort_scatter_k<2><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, va, kb, vb, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
         else sort_scatter_k<16><<<nblocks, VKB_SORT_BLOCK, 0, s>>>(ka, va, kb, vb, n, p * 8, sc.hist.as<uint32_t>(), nblocks, C, idx);
         VKB_LAUNCHED();

@@ -63,6 +63,7 @@ struct vkb_device_impl {
     bool   nz_any = false;  // the batch holds NON_ZERO fills / clips: they go through nz_classify / nz_split (raster.cu)
     uint32_t n_grads = 0;
     uint32_t n_curves = 0;  // cubic / arc elements in the resident batch
+    uint32_t max_sp_elems = 0;  // elements of the longest sub-path of the resident batch
     ScanScratch scan;
     SortScratch sort;
     // counts that live on the device (dev_util.cuh: vkb_counts) and the flush that may still be in flight
@@ -143,7 +144,7 @@ void vkb_device_close(vkb_device_impl *d) {
                       &d->sp_first, &d->sp_count, &d->fjob_base, &d->sjob_base, &d->seglen, &d->cum, &d->item_counts, &d->verts, &d->inds, &d->job_inverse,
                       &d->edges, &d->edge_draw, &d->draw_bbox, &d->draw_rect, &d->draw_counts, &d->draw_ptbase, &d->draw_rowbase, &d->pt_count,
                       &d->pt_backdrop, &d->pt_flags, &d->pt_draw, &d->keys, &d->vals, &d->sorted_cnt, &d->pt_slot, &d->cursor, &d->hdr, &d->tile_first,
-                      &d->tile_end, &d->tile_edges, &d->winding, &d->tmp_image, &d->scan.sums, &d->sort.hist, &d->sort.k2, &d->sort.v2, &d->sort.scan.sums};
+                      &d->tile_end, &d->tile_edges, &d->winding, &d->tmp_image, &d->scan.sums, &d->scan.ticket, &d->sort.hist, &d->sort.k2, &d->sort.v2, &d->sort.scan.sums, &d->sort.scan.ticket};
     for (DevBuf *b : bufs) b->release();
     if (d->stage) cudaFreeHost(d->stage);
     for (cudaEvent_t &e : d->ev_stage) cudaEventDestroy(e);
@@ -417,6 +418,8 @@ int vkb_upload(vkb_device_impl *d, const vkb_batch &b) {
     VKB_CUDA_OK(cudaStreamSynchronize(st));
     d->n_elems = (uint32_t)b.elem_hdr.size(); d->n_sp = (uint32_t)b.subpaths.size(); d->n_draws = (uint32_t)b.draws.size();
     d->n_curves = b.n_curves;
+    d->max_sp_elems = 0;
+    for (const vkb_subpath &sp : b.subpaths) if (sp.n_elems > d->max_sp_elems) d->max_sp_elems = sp.n_elems;
     d->n_grads  = (uint32_t)b.grads.size();
     // what the job tables will hold is a function of the recorded draws alone: counted here, no read-back
     d->has_clip_draws = d->has_stencil_ops = false;
@@ -497,10 +500,6 @@ template <class T> static void download(vkb_device_impl *d, std::vector<T> *out,
     VKB_CUDA_OK(cudaStreamSynchronize(d->stream));
 }
 
-__global__ void gather_first_items_k(const uint32_t *first_job, const uint32_t *job_base, uint32_t n, uint32_t *out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = job_base[first_job[i]];
-}
 // the four edges of a rectangle one tile larger than the surface for every whole-surface draw; they follow the fill edges
 __global__ void extra_rect_edges_k(vkb_edge *edges, uint32_t *edge_draw, const uint32_t *extra_edge_draw, uint32_t n_rects, int32_t W, int32_t H,
                                    const vkb_counts *C, int32_t *bbox) {
@@ -526,19 +525,19 @@ __global__ void commit_flatten_k(vkb_counts *C, const uint64_t *totals, uint32_t
     if (!split) vkc_commit(C, VKC_FEDGES, has_fill ? (uint32_t)totals[1] : 0u);  // (else the scan of the split counts commits it)
     vkc_commit(C, VKC_SITEMS, has_stroke ? (uint32_t)totals[2] : 0u);
 }
-__global__ void commit_stroke_k(vkb_counts *C, const uint64_t *totals, uint32_t has_stroke, uint32_t n_extra) {
+// (its other threads gather the first work item of every stroke draw - what maps a triangle back to its draw in tri_edges_k)
+__global__ void commit_stroke_k(vkb_counts *C, const uint64_t *totals, uint32_t has_stroke, uint32_t n_extra, const uint32_t *first_job, const uint32_t *job_base,
+                                uint32_t n_sdraws, uint32_t *first_item) {
     if (C->overflow) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_sdraws) first_item[i] = job_base[first_job[i]];
+    if (i) return;
     const unsigned long long tot = has_stroke ? totals[3] : 0ull;
     const uint32_t nv = (uint32_t)(tot & 0xffffffffull), ni = (uint32_t)(tot >> 32);
     vkc_commit(C, VKC_VERTS, nv);
     vkc_commit(C, VKC_INDS, ni);
     vkc_commit(C, VKC_TRIS, ni / 3);
     vkc_commit(C, VKC_EDGES, C->n[VKC_FEDGES] + 3u * (ni / 3) + n_extra);
-}
-__global__ void commit_pt_k(vkb_counts *C, const uint64_t *totals) {
-    if (C->overflow) return;
-    vkc_commit(C, VKC_PT, (uint32_t)(totals[4] & 0xffffffffull));
-    vkc_commit(C, VKC_ROWS, (uint32_t)(totals[4] >> 32));
 }
 __global__ void set_edge_count_k(vkb_counts *C, uint32_t n) {  // raw edge lists (vkb_winding_raw)
     for (int i = 0; i < VKC_N; i++) { C->n[i] = 0; C->need[i] = 0; }
@@ -578,7 +577,7 @@ static void grow_caps_from_need(vkb_device_impl *d, const vkb_counts &h) {
 
 // binning + fine pass over d->edges / d->edge_draw (count C->n[VKC_EDGES], nd draws, paints / grads already on the device)
 static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDesc sd, uint32_t nd, vkb_capture *cap, const vkb_draw *draws,
-                                 DevBuf &wbuf) {  // draws: device pointer, or null for a raw edge list (no clip draws then)
+                                 DevBuf &wbuf, const uint32_t *live_edges = nullptr) {  // draws: device pointer, or null for a raw edge list (no clip draws then)
     cudaStream_t st     = d->stream;
     uint64_t    *totals = d->totals.as<uint64_t>();
     vkb_counts  *C      = d->counts.as<vkb_counts>();
@@ -597,13 +596,14 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     if (!draws) vkb_launch_draw_bbox(edges, edraw, cv[VKC_EDGES], C, nd, d->draw_bbox.as<int32_t>(), st);  // (else grown by the kernels that emitted the edges)
     unsigned long long *dc = d->draw_counts.as<unsigned long long>();
+    d->gprep.ensure((size_t)(d->n_grads + 1) * 16 * 4, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
+    const GradPrep gp = {d->grads.as<vkb_gradient>(), draws ? d->n_grads : 0u, (float)sd.width, (float)sd.full_height, d->gprep.as<float>()};
     const bool clip_draws = draws && d->has_clip_draws, stencil_ops = draws && d->has_stencil_ops;
     vkb_launch_draw_rects(d->draw_bbox.as<int32_t>(), (clip_draws || sd.band_tiles) ? draws : nullptr, d->xforms.as<vkb_xform>(), nd, sd,
-                          d->draw_rect.as<int32_t>(), dc, st);
+                          d->draw_rect.as<int32_t>(), dc, C, live_edges, d->n_extra, gp, st);   // (+ the live stroke edges committed as the edge count, the gradients prepared)
     vkb_exclusive_scan<unsigned long long, unsigned long long>(dc, dc, nd, (unsigned long long *)(totals + 4), d->scan, st);
-    vkb_launch_split_bases(dc, nd, d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), st);
-    commit_pt_k<<<1, 1, 0, st>>>(C, totals);
-    VKB_LAUNCHED();
+    vkb_launch_split_bases(dc, nd, d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), C, (const unsigned long long *)(totals + 4), st);   // (+ VKC_PT / VKC_ROWS committed)
 
     const uint32_t cap_pt = cv[VKC_PT], cap_ne = cv[VKC_NE];
     d->pt_count.ensure((size_t)(cap_pt + 1) * 4, st);
@@ -614,9 +614,7 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     d->row_owner.ensure((size_t)(cv[VKC_ROWS] + 1) * 4, st);
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     vkb_launch_owners(d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->draw_rowbase.as<uint32_t>(), nd, C, d->pt_owner.as<uint32_t>(),
-                      d->row_owner.as<uint32_t>(), st);
-    VKB_CUDA_OK(cudaMemsetAsync(d->pt_count.p, 0, (size_t)cap_pt * 4, st));
-    VKB_CUDA_OK(cudaMemsetAsync(d->pt_backdrop.p, 0, (size_t)cap_pt * 4, st));
+                      d->row_owner.as<uint32_t>(), d->pt_count.as<uint32_t>(), d->pt_backdrop.as<int32_t>(), st);   // (+ pt_count / pt_backdrop zeroed)
     d->long_edges.ensure(((size_t)cv[VKC_EDGES] + 1) * 4, st);
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     uint32_t *long_n = (uint32_t *)(totals + 8);  // (zeroed with the other totals when the flush starts)
@@ -650,19 +648,27 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     DevBuf   &cur2 = d->cursor2;
     cur2.ensure((size_t)(cap_ne + 1) * 4, st);
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
+    uint32_t *tile_ms_words = nullptr;   // the per-tile multisample flags, when this frame must start from none set
+    if (samples) {  // (analytic mode, samples == 0, keeps one colour per pixel: no per-sample plane)
+        const bool fresh = surf->tile_ms.p == nullptr;
+        surf->ms_image.ensure((size_t)n_tiles * 256 * samples * 4, st);
+        surf->tile_ms.ensure((size_t)n_tiles + 16, st);
+        surf->ms_mask.ensure((size_t)n_tiles * 32 + 16, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
+        if (fresh || surf->known_clear) tile_ms_words = surf->tile_ms.as<uint32_t>();
+    }
     {
         // sorted_cnt currently holds flag_scan which headers_k still needs: put the sorted counts in pt_flags instead
         uint32_t *scnt = d->pt_flags.as<uint32_t>();
-        vkb_launch_sorted_counts(d->vals.as<uint32_t>(), cap_ne, C, d->pt_count.as<uint32_t>(), scnt, d->pt_slot.as<uint32_t>(), st);
+        // (the same launch zeroes the scatter cursors, the tile list bounds and those flags)
+        vkb_launch_sorted_counts(d->vals.as<uint32_t>(), cap_ne, C, d->pt_count.as<uint32_t>(), scnt, d->pt_slot.as<uint32_t>(), cur2.as<uint32_t>(), d->tile_first.as<uint32_t>(),
+                                 d->tile_end.as<uint32_t>(), n_tiles, tile_ms_words, st);
         vkb_exclusive_scan<uint32_t, uint32_t>(scnt, eoff, 0, (uint32_t *)(totals + 6), d->scan, st, C, VKC_NE, cap_ne, VKC_TE);
     }
     d->tile_edges.ensure((size_t)(cv[VKC_TE] + 1) * 16, st);
     if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-    VKB_CUDA_OK(cudaMemsetAsync(d->tile_first.p, 0, (size_t)n_tiles * 4, st));
-    VKB_CUDA_OK(cudaMemsetAsync(d->tile_end.p, 0, (size_t)n_tiles * 4, st));
     vkb_launch_headers(d->keys.as<uint32_t>(), d->vals.as<uint32_t>(), cap_ne, C, d->pt_draw.as<uint32_t>(), flag_scan, d->pt_backdrop.as<int32_t>(),
                        d->pt_count.as<uint32_t>(), eoff, d->paints.as<vkb_paint>(), d->hdr.as<int4>(), d->tile_first.as<uint32_t>(), d->tile_end.as<uint32_t>(), st);
-    VKB_CUDA_OK(cudaMemsetAsync(cur2.p, 0, (size_t)cap_ne * 4, st));
     vkb_launch_bin_scatter(edges, edraw, cv[VKC_EDGES], C, d->draw_rect.as<int32_t>(), d->draw_ptbase.as<uint32_t>(), d->pt_slot.as<uint32_t>(), eoff,
                            cur2.as<uint32_t>(), d->tile_edges.as<vkb_edge>(), d->long_edges.as<uint32_t>(), long_n, st);
 
@@ -673,9 +679,6 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     fa.tile_first = d->tile_first.as<uint32_t>(); fa.tile_end = d->tile_end.as<uint32_t>();
     fa.hdr = d->hdr.as<int4>(); fa.tile_edges = d->tile_edges.as<vkb_edge>();
     fa.paints = d->paints.as<vkb_paint>(); fa.grads = d->grads.as<vkb_gradient>();
-    d->gprep.ensure((size_t)(d->n_grads + 1) * 16 * 4, st);
-    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-    vkb_launch_grad_prep(fa.grads, draws ? d->n_grads : 0, (float)sd.width, (float)sd.full_height, d->gprep.as<float>(), st);
     fa.gprep = d->gprep.as<float>();
     fa.tile_counter = (uint32_t *)(totals + 10);  // (zeroed with the other totals when the flush starts)
     fa.tile_lo = 0; fa.tile_hi = n_tiles;
@@ -684,14 +687,6 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
     fa.wscratch = d->wscratch.as<int32_t>();
     fa.surfpats = d->surfpats.as<vkb_surfpat>();
     fa.image = surf->image.as<uint32_t>();
-    if (samples) {  // (analytic mode, samples == 0, keeps one colour per pixel: no per-sample plane)
-        bool fresh = surf->tile_ms.p == nullptr;
-        surf->ms_image.ensure((size_t)n_tiles * 256 * samples * 4, st);
-        surf->tile_ms.ensure((size_t)n_tiles + 16, st);
-        surf->ms_mask.ensure((size_t)n_tiles * 32 + 16, st);
-        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-        if (fresh || surf->known_clear) VKB_CUDA_OK(cudaMemsetAsync(surf->tile_ms.p, 0, n_tiles, st));
-    }
     fa.ms_image = surf->ms_image.as<uint32_t>(); fa.tile_ms = surf->tile_ms.as<uint8_t>(); fa.ms_mask = surf->ms_mask.as<uint32_t>();
     fa.dst_is_clear = surf->known_clear ? 1 : 0;
     // clip / save bits: the stencil-aware kernel variant only runs when this batch writes them or earlier ones left some behind
@@ -746,17 +741,22 @@ static void enqueue_bin_and_fine(vkb_device_impl *d, vkb_surface_impl *surf, Sur
 }
 
 // the capacities of this attempt travel as kernel arguments (no staging copy to wait on); every count starts at zero
+// The same launch zeroes the 16 raw totals of the flush and empties the per-draw boxes (bbox: n_draws x 4, or null) - one graph node
+// instead of a kernel, a memset and another kernel at the head of every frame.
 struct CapArgs { uint32_t v[16]; };
-__global__ void counts_reset_k(vkb_counts *C, CapArgs caps) {
-    const uint32_t i = threadIdx.x;
-    if (i < 16) { C->n[i] = 0; C->need[i] = 0; C->cap[i] = caps.v[i]; }
+__global__ void counts_reset_k(vkb_counts *C, CapArgs caps, uint64_t *totals, int32_t *bbox, uint32_t n_draws) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 16) { C->n[i] = 0; C->need[i] = 0; C->cap[i] = caps.v[i]; totals[i] = 0; }
     if (i == 0) C->overflow = 0;
+    if (bbox && i < n_draws) { bbox[4 * i] = INT32_MAX; bbox[4 * i + 1] = INT32_MAX; bbox[4 * i + 2] = INT32_MIN; bbox[4 * i + 3] = INT32_MIN; }
 }
-static void enqueue_counts_reset(vkb_device_impl *d) {
+static void enqueue_counts_reset(vkb_device_impl *d, int32_t *bbox, uint32_t n_draws) {
     d->counts.ensure(sizeof(vkb_counts), d->stream);
+    d->totals.ensure(16 * 8, d->stream);
+    if (d->failed) return;
     CapArgs a;
     memcpy(a.v, d->capv, sizeof a.v);
-    counts_reset_k<<<1, 32, 0, d->stream>>>(d->counts.as<vkb_counts>(), a);
+    counts_reset_k<<<bbox && n_draws > 256 ? vkb_div_up(n_draws, 256) : 1, 256, 0, d->stream>>>(d->counts.as<vkb_counts>(), a, d->totals.as<uint64_t>(), bbox, n_draws);
     VKB_LAUNCHED();
 }
 
@@ -765,17 +765,13 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     cudaStream_t st = d->stream;
     plan_caps(d, sd);
     const uint32_t *cv = d->capv;
-    enqueue_counts_reset(d);
+    d->draw_bbox.ensure((size_t)(d->n_draws + 1) * 16, st);
+    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
+    enqueue_counts_reset(d, d->draw_bbox.as<int32_t>(), d->n_draws);   // (+ the totals zeroed, the draw boxes emptied)
+    if (d->failed) return;
     vkb_counts *C = d->counts.as<vkb_counts>();
     VKB_EVENT_RECORD(d, d->ev_stage[0]);
-    d->totals.ensure(16 * 8, st);
-    if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
     uint64_t *totals = d->totals.as<uint64_t>();
-    VKB_CUDA_OK(cudaMemsetAsync(totals, 0, 16 * 8, st));
-
-    d->draw_bbox.ensure((size_t)(d->n_draws + 1) * 16, st);
-    if (d->failed) return;
-    vkb_launch_draw_bbox_init(d->n_draws, d->draw_bbox.as<int32_t>(), st);
     // ---- 1. flatten: count -> scan -> emit ----
     d->elem_cnt.ensure((size_t)(d->n_elems + 1) * 4, st);
     d->sp_first.ensure((size_t)(d->n_sp + 1) * 4, st);
@@ -806,7 +802,14 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     if (d->failed) return;
     // (geometry captures - vkvg_b200_stroke_geometry, path_edges - report the whole tessellation, on or off the surface)
     const int4 *sp_bbox = (cap && cap->geometry_only) ? nullptr : d->sp_bbox.as<int4>();
-    if (sp_bbox) vkb_launch_sp_bounds(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->long_sp.as<uint32_t>(), (uint32_t *)(totals + 12), d->scan, d->sp_bbox.as<int4>(), st);
+    if (sp_bbox) vkb_launch_sp_bounds(d->subpaths.as<vkb_subpath>(), d->n_sp, d->elem_hdr.as<uint32_t>(), d->elem_data.as<float>(), d->n_elems, d->long_sp.as<uint32_t>(), (uint32_t *)(totals + 12), d->scan, d->sp_bbox.as<int4>(), d->max_sp_elems > VKB_SP_LONG, st);
+    if (d->n_fjobs && d->n_sjobs && d->n_fjobs <= VKB_SCAN_SMALL && d->n_sjobs <= VKB_SCAN_SMALL) {   // a small batch that fills and strokes: two launches instead of four
+        vkb_launch_job_counts2(d->fjob_sp.as<uint32_t>(), d->fjob_draw.as<uint32_t>(), d->n_fjobs, d->fjob_base.as<uint32_t>(), d->sjob_sp.as<uint32_t>(), d->sjob_draw.as<uint32_t>(),
+                               d->n_sjobs, d->sjob_base.as<uint32_t>(), d->sp_count.as<uint32_t>(), sp_bbox, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(),
+                               d->strokes.as<vkb_stroke>(), sd, st);
+        scan_small2_k<uint32_t><<<2, 1024, 0, st>>>(d->fjob_base.as<uint32_t>(), d->n_fjobs, (uint32_t *)(totals + 1), d->sjob_base.as<uint32_t>(), d->n_sjobs, (uint32_t *)(totals + 2));
+        VKB_LAUNCHED();
+    } else {
     if (d->n_fjobs) {
         vkb_launch_job_counts(d->fjob_sp.as<uint32_t>(), d->fjob_draw.as<uint32_t>(), d->n_fjobs, d->sp_count.as<uint32_t>(), 3, sp_bbox, d->draws.as<vkb_draw>(),
                               d->xforms.as<vkb_xform>(), d->strokes.as<vkb_stroke>(), sd, d->fjob_base.as<uint32_t>(), st);
@@ -816,6 +819,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         vkb_launch_job_counts(d->sjob_sp.as<uint32_t>(), d->sjob_draw.as<uint32_t>(), d->n_sjobs, d->sp_count.as<uint32_t>(), 2, sp_bbox, d->draws.as<vkb_draw>(),
                               d->xforms.as<vkb_xform>(), d->strokes.as<vkb_stroke>(), sd, d->sjob_base.as<uint32_t>(), st);
         vkb_exclusive_scan<uint32_t, uint32_t>(d->sjob_base.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, (uint32_t *)(totals + 2), d->scan, st);
+    }
     }
     const bool nz_split = d->nz_any && d->n_fjobs;
     commit_flatten_k<<<1, 1, 0, st>>>(C, totals, d->n_fjobs ? 1u : 0u, d->n_sjobs ? 1u : 0u, nz_split ? 1u : 0u);
@@ -839,6 +843,7 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
 
     // ---- 3. strokes: (dash phase scan) -> count -> scan -> emit ----
     const uint32_t cap_items = d->n_sjobs ? cv[VKC_SITEMS] : 0;
+    const bool     legacy_emit = vkb_stroke_emit_mode() == 1;
     if (cap_items) {
         StrokeArgs sa = {d->pts.as<float2>(), d->ptflags.as<uint8_t>(), d->draws.as<vkb_draw>(), d->strokes.as<vkb_stroke>(), d->dashes.as<float>(), d->sjob_draw.as<uint32_t>(),
                          d->sjob_sp.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(),
@@ -854,18 +859,26 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
         d->item_counts.ensure((size_t)(cap_items + 1) * 8, st);
         d->job_inverse.ensure((size_t)(d->n_sjobs + 1) * 4, st);
         if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-        VKB_CUDA_OK(cudaMemsetAsync(d->job_inverse.p, 0, (size_t)d->n_sjobs * 4, st));
+        // (job_inverse needs no clearing: stroke_patch_closed_k reads it for closed undashed jobs of at least two points, and the last item of
+        // exactly those writes it)
         unsigned long long *ic = d->item_counts.as<unsigned long long>();
         vkb_launch_stroke_count(sa, ic, st);
         vkb_exclusive_scan<unsigned long long, unsigned long long>(ic, ic, 0, (unsigned long long *)(totals + 3), d->scan, st, C, VKC_SITEMS, cap_items);
-        commit_stroke_k<<<1, 1, 0, st>>>(C, totals, 1u, d->n_extra);
-        VKB_LAUNCHED();
-        d->verts.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
-        d->inds.ensure((size_t)(cv[VKC_INDS] + 3) * 4, st);
+        d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
         if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-        vkb_launch_stroke_emit(sa, ic, d->verts.as<float2>(), d->inds.as<uint32_t>(), d->job_inverse.as<uint32_t>(), st);
+        commit_stroke_k<<<vkb_div_up(d->n_sdraws ? d->n_sdraws : 1, 256), 256, 0, st>>>(C, totals, 1u, d->n_extra, d->sdraw_first_job.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
+                                                                                      d->sdraw_first_item.as<uint32_t>());
+        VKB_LAUNCHED();
+        const bool want_verts = cap && cap->verts;   // float vertices: geometry captures only (the rasteriser reads the snapped ones)
+        if (legacy_emit || want_verts) d->verts.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
+        d->inds.ensure((size_t)(cv[VKC_INDS] + 4) * 4, st);
+        d->snapped.ensure((size_t)(cv[VKC_VERTS] + 2) * 8, st);
+        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
+        if (legacy_emit) vkb_launch_stroke_emit(sa, ic, d->verts.as<float2>(), d->inds.as<uint32_t>(), d->job_inverse.as<uint32_t>(), st);
+        else vkb_launch_stroke_emit_snapped(sa, ic, d->xforms.as<vkb_xform>(), sd, want_verts ? d->verts.as<float2>() : nullptr, d->snapped.as<int2>(), d->inds.as<uint32_t>(),
+                                            d->job_inverse.as<uint32_t>(), st);
     } else {
-        commit_stroke_k<<<1, 1, 0, st>>>(C, totals, 0u, d->n_extra);
+        commit_stroke_k<<<1, 32, 0, st>>>(C, totals, 0u, d->n_extra, nullptr, nullptr, 0u, nullptr);
         VKB_LAUNCHED();
     }
 
@@ -879,25 +892,20 @@ static void enqueue_flush(vkb_device_impl *d, vkb_surface_impl *surf, SurfaceDes
     if (!nz_split)  // (else the fill edges are in place since the end of the flatten stage)
         vkb_launch_fill_edges(d->pts.as<float2>(), d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->fjob_draw.as<uint32_t>(), d->fjob_sp.as<uint32_t>(), d->fjob_base.as<uint32_t>(),
                               d->n_fjobs, d->sp_first.as<uint32_t>(), d->sp_count.as<uint32_t>(), d->n_fjobs ? cv[VKC_FILL] : 0, C, sd, edges, edraw, d->draw_bbox.as<int32_t>(), st);
-    if (cap_items && d->n_sdraws) {
-        // first work item of every stroke draw (to map a triangle back to its draw)
-        d->sdraw_first_item.ensure((size_t)d->n_sdraws * 4 + 16, st);
-        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-        gather_first_items_k<<<vkb_div_up(d->n_sdraws, 256), 256, 0, st>>>(d->sdraw_first_job.as<uint32_t>(), d->sjob_base.as<uint32_t>(), d->n_sdraws,
-                                                                          d->sdraw_first_item.as<uint32_t>());
-        VKB_LAUNCHED();
-        d->snapped.ensure((size_t)(cv[VKC_VERTS] + 1) * 8, st);
-        if (d->failed) return;  // an allocation failed: nothing that would use the buffer is launched
-        vkb_launch_tri_edges(d->verts.as<float2>(), cv[VKC_VERTS], d->snapped.as<int2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
-                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, d->n_extra, (uint32_t *)(totals + 9), C, d->draw_bbox.as<int32_t>(), st);
+    const bool      stops_here = (cap && cap->geometry_only) || d->n_draws == 0;
+    const uint32_t *live_edges = nullptr;   // the stored stroke edges, when the binning stage is to commit their number
+    if (cap_items && d->n_sdraws) {   // (sdraw_first_item: written by commit_stroke_k)
+        vkb_launch_tri_edges(legacy_emit ? d->verts.as<float2>() : nullptr, cv[VKC_VERTS], d->snapped.as<int2>(), d->inds.as<uint32_t>(), cv[VKC_TRIS], C, d->draws.as<vkb_draw>(), d->xforms.as<vkb_xform>(), d->sdraw_id.as<uint32_t>(),
+                             d->sdraw_first_item.as<uint32_t>(), d->n_sdraws, d->item_counts.as<unsigned long long>(), sd, edges, edraw, d->n_extra, (uint32_t *)(totals + 9), C, d->draw_bbox.as<int32_t>(), stops_here, st);
+        if (!stops_here) live_edges = (const uint32_t *)(totals + 9);
     }
     if (d->n_extra) {
         extra_rect_edges_k<<<vkb_div_up(d->n_extra / 4, 64), 64, 0, st>>>(edges, edraw, d->extra_edge_draw.as<uint32_t>(), d->n_extra / 4, (int32_t)sd.width,
                                                                          (int32_t)sd.height, C, d->draw_bbox.as<int32_t>());
         VKB_LAUNCHED();
     }
-    if ((cap && cap->geometry_only) || d->n_draws == 0) return;
-    enqueue_bin_and_fine(d, surf, sd, d->n_draws, cap, d->draws.as<vkb_draw>(), wbuf);
+    if (stops_here) return;
+    enqueue_bin_and_fine(d, surf, sd, d->n_draws, cap, d->draws.as<vkb_draw>(), wbuf, live_edges);
 }
 
 // Everything that shapes the launches of a flush besides the data in the buffers.  Two flushes with equal keys issue the
@@ -931,7 +939,7 @@ static void enqueue_flush_maybe_graph(vkb_device_impl *d, vkb_surface_impl *surf
     memset(&k, 0, sizeof k);
     k.n_curves = d->n_curves; k.n_grads = d->n_grads;
     k.n_elems = d->n_elems; k.n_sp = d->n_sp; k.n_draws = d->n_draws; k.n_fjobs = d->n_fjobs; k.n_sjobs = d->n_sjobs; k.n_sdraws = d->n_sdraws; k.n_extra = d->n_extra;
-    k.flags = (d->any_dash ? 1u : 0u) | (d->has_clip_draws ? 2u : 0u) | (d->has_stencil_ops ? 4u : 0u) | ((uint32_t)d->stencil_after << 3) | (d->nz_any ? 32u : 0u);
+    k.flags = (d->any_dash ? 1u : 0u) | (d->has_clip_draws ? 2u : 0u) | (d->has_stencil_ops ? 4u : 0u) | ((uint32_t)d->stencil_after << 3) | (d->nz_any ? 32u : 0u) | (d->max_sp_elems > VKB_SP_LONG ? 64u : 0u);
     memcpy(k.capv, d->capv, sizeof k.capv);
     k.surf = surf; k.w = sd.width; k.h = sd.height; k.samples = sd.samples; k.full_h = sd.full_height; k.origin_y = sd.origin_y;
     k.known_clear = surf->known_clear; k.stencil_live = surf->stencil_live; k.stencil_samples = surf->stencil_samples;
@@ -1141,6 +1149,7 @@ int vkb_submit_stream(vkb_device_impl *d, vkb_surface_impl *surf, uint32_t sampl
     d->n_elems = c.n_elems; d->n_sp = c.n_subpaths; d->n_draws = c.n_draws; d->n_curves = c.n_curves; d->n_grads = c.n_grads + 1;
     d->n_fjobs = c.n_fjobs; d->n_sjobs = c.n_sjobs; d->n_sdraws = c.n_sdraws; d->n_extra = 0;
     d->any_dash = c.any_dash != 0; d->nz_any = c.nz_any != 0;
+    d->max_sp_elems = c.max_sp_elems;
     d->has_clip_draws = d->has_stencil_ops = false;
     d->stencil_after = 0;
     d->h2d_bytes = (uint64_t)nc * 4 + (uint64_t)na * 4;
@@ -1182,10 +1191,9 @@ int vkb_winding_raw(vkb_device_impl *d, uint32_t samples, const int32_t *edges_h
         if (c[VKC_ROWS] < c[VKC_PT]) c[VKC_ROWS] = c[VKC_PT];
         if (c[VKC_NE] < c[VKC_PT]) c[VKC_NE] = c[VKC_PT];
         if (c[VKC_TE] < 2 * n + 1024) c[VKC_TE] = (uint32_t)(2 * n + 1024);
-        enqueue_counts_reset(d);
+        enqueue_counts_reset(d, nullptr, 0);
         set_edge_count_k<<<1, 1, 0, st>>>(d->counts.as<vkb_counts>(), (uint32_t)n);
         VKB_LAUNCHED();
-        VKB_CUDA_OK(cudaMemsetAsync(d->totals.p, 0, 16 * 8, st));
         DevBuf wbuf;
         enqueue_bin_and_fine(d, surf, sd, 1, &cap, nullptr, wbuf);
         VKB_CUDA_OK(cudaMemcpyAsync(d->counts_host, d->counts.p, sizeof(vkb_counts), cudaMemcpyDeviceToHost, st));

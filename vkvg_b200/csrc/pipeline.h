@@ -14,9 +14,11 @@ void vkb_launch_subpath_ranges(const vkb_subpath *sps, uint32_t n_sp, const uint
 
 // ---- job tables: one job = one sub-path of one draw; items = its points ----
 // sp_bbox: user-space box of every sub-path (vkb_launch_sp_bounds), or null for no culling; job_n = 0 for jobs that cannot touch the surface
+#define VKB_SP_LONG 1024  // sub-paths of more elements are reduced by sp_bounds_long_k (one thread per element) instead of by one warp
 struct SurfaceDesc;
+// any_long: some sub-path holds more than VKB_SP_LONG elements (the host knows from the recorder or the decoder's census)
 void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, uint32_t *long_blocks, uint32_t *n_long_blocks,
-                          ScanScratch &scan, int4 *sp_bbox, cudaStream_t s);
+                          ScanScratch &scan, int4 *sp_bbox, bool any_long, cudaStream_t s);
 
 // ---- stroke.cu ----
 struct StrokeArgs {
@@ -64,8 +66,33 @@ struct SurfaceDesc {
     // canvas coordinates (so each canvas holds exactly the pixels it would hold alone) and shifted by whole tiles.  0: no bands
     uint32_t band_tiles;
 };
+// the emitter of stroke.cu that runs the vertex stage itself: snapped = every vertex on the 1/256 grid (what vkb_launch_tri_edges reads), verts =
+// the float vertices for geometry captures or null.  vkb_stroke_emit_mode(): 0 this emitter with block-staged 16-byte stores, 1 the first
+// emitter (vkb_launch_stroke_emit + snap_verts_k), 2 this emitter writing straight to global memory (VKVG_B200_STROKE=legacy|direct, for A/B runs)
+int  vkb_stroke_emit_mode();
+void vkb_launch_stroke_emit_snapped(const StrokeArgs &a, const unsigned long long *offsets, const vkb_xform *xforms, const SurfaceDesc &sd, float2 *verts, int2 *snapped,
+                                    uint32_t *inds, uint32_t *job_inverse, cudaStream_t s);
+
+// ---- vertex stage: shaders/vkvg_main.vert:74-79 + viewport + 8-bit sub-pixel snap (round half up) ----
+__device__ __forceinline__ void vs_snap(const float *m, float W, float H, float x, float y, int32_t &fx, int32_t &fy) {
+    float px = m[0] * x + m[2] * y + m[4];
+    float py = m[1] * x + m[3] * y + m[5];
+    float nx = px * 2.0f / W - 1.0f;
+    float ny = py * 2.0f / H - 1.0f;
+    float wx = nx * (W * 0.5f) + (W * 0.5f);
+    float wy = ny * (H * 0.5f) + (H * 0.5f);
+    // clamp far outside the guard band so the int32 conversion is defined; such coordinates are off-surface
+    wx = fminf(fmaxf(wx, -1.0e6f), 1.0e6f);
+    wy = fminf(fmaxf(wy, -1.0e6f), 1.0e6f);
+    fx = (int32_t)floorf(wx * 256.0f + 0.5f);
+    fy = (int32_t)floorf(wy * 256.0f + 0.5f);
+}
+
 void vkb_launch_job_counts(const uint32_t *job_sp, const uint32_t *job_draw, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
                            const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n, cudaStream_t s);
+void vkb_launch_job_counts2(const uint32_t *fjob_sp, const uint32_t *fjob_draw, uint32_t nf, uint32_t *fjob_n, const uint32_t *sjob_sp, const uint32_t *sjob_draw, uint32_t ns,
+                            uint32_t *sjob_n, const uint32_t *sp_count, const int4 *sp_bbox, const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes,
+                            SurfaceDesc sd, cudaStream_t s);
 void vkb_launch_fill_edges(const float2 *pts, const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *job_draw, const uint32_t *job_sp, const uint32_t *job_base,
                            uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count, uint32_t cap_items, const vkb_counts *C, SurfaceDesc sd,
                            vkb_edge *edges, uint32_t *edge_draw, int32_t *draw_bbox, cudaStream_t s);
@@ -79,11 +106,13 @@ void vkb_launch_nz_split(const float2 *pts, const vkb_draw *draws, const vkb_xfo
                          uint32_t cap_items, vkb_counts *C, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t *n_out, uint32_t cap_edges, int32_t *draw_bbox, cudaStream_t s);
 // edges / edge_draw: start of the edge arrays (the kernel skips the C->n[VKC_FEDGES] fill edges and the n_extra rectangle edges itself);
 // live: zeroed device counter of the stroke edges stored (cancelled ones are dropped); Cw->n[VKC_EDGES] is set to the stored total
-// snapped: cap_verts int2 of scratch (every stroke vertex goes through the vertex stage once, then the triangles read integers)
+// (commit_live; otherwise the caller passes live on to vkb_launch_draw_rects, which sets it)
+// snapped: cap_verts int2 (every stroke vertex goes through the vertex stage once, then the triangles read integers): filled here from verts
+// by snap_verts_k, or already by the emitter (verts == null)
 void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
                           const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
                           const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
-                          vkb_counts *Cw, int32_t *draw_bbox, cudaStream_t s);
+                          vkb_counts *Cw, int32_t *draw_bbox, bool commit_live, cudaStream_t s);
 
 struct BinBuffers {  // all device pointers
     int32_t  *draw_bbox;    // n_draws x 4 (minx, miny, maxx, maxy), fixed point
@@ -96,15 +125,19 @@ struct BinBuffers {  // all device pointers
 void vkb_launch_draw_bbox_init(uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s);
 void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
                           cudaStream_t s);
+// gradients whose position-independent terms (FineArgs::gprep, 16 floats each) the same launch evaluates; n == 0: none
+struct GradPrep { const vkb_gradient *grads; uint32_t n; float W, H; float *out; };
 // draws may be null (raw edge lists); a VKB_DRAW_CLIP draw takes the whole surface as its rectangle
 void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, const vkb_xform *xforms, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
-                           unsigned long long *tile_row_counts, cudaStream_t s);
-void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s);
+                           unsigned long long *tile_row_counts, vkb_counts *Cw, const uint32_t *live, uint32_t n_extra, const GradPrep &gp, cudaStream_t s);
+// (live: the counter vkb_launch_tri_edges filled when it was told not to commit it, or null)
+// + VKC_PT / VKC_ROWS committed from *total (path-tiles | rows << 32, the scan's total)
+void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, vkb_counts *C, const unsigned long long *total, cudaStream_t s);
 void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
                           const uint32_t *draw_ptbase, uint32_t *pt_count, int32_t *pt_backdrop, uint32_t *long_list, uint32_t *long_n, cudaStream_t s);
-// pt_owner[path-tile] / row_owner[path-tile row] = draw index
+// pt_owner[path-tile] / row_owner[path-tile row] = draw index; pt_count / pt_backdrop of every path-tile zeroed
 void vkb_launch_owners(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws, const vkb_counts *C,
-                       uint32_t *pt_owner, uint32_t *row_owner, cudaStream_t s);
+                       uint32_t *pt_owner, uint32_t *row_owner, uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s);
 void vkb_launch_backdrop_prefix(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, const uint32_t *row_owner,
                                 uint32_t cap_rows, const vkb_counts *C, int32_t *pt_backdrop, cudaStream_t s);
 // keep_clip: the batch holds VKB_DRAW_CLIP draws, whose path-tiles are all kept (an empty one means "clipped out")
@@ -112,8 +145,9 @@ void vkb_launch_pt_flags(const uint32_t *pt_count, const int32_t *pt_backdrop, u
                          const uint32_t *pt_owner, bool keep_clip, uint32_t *flags, cudaStream_t s);
 void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uint32_t cap_pt, const vkb_counts *C, const int32_t *draw_rect,
                            const uint32_t *draw_ptbase, const uint32_t *pt_owner, SurfaceDesc sd, uint32_t *keys, uint32_t *vals, uint32_t *pt_draw, cudaStream_t s);
+// also zeroes cursor[0, n_ne), tile_first / tile_end[0, n_tiles) and, if given, the per-tile multisample flags (as words)
 void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot,
-                              cudaStream_t s);
+                              uint32_t *cursor, uint32_t *tile_first, uint32_t *tile_end, uint32_t n_tiles, uint32_t *tile_ms_words, cudaStream_t s);
 void vkb_launch_headers(const uint32_t *keys, const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_draw_by_flagpos,
                         const uint32_t *flag_scan, const int32_t *pt_backdrop, const uint32_t *pt_count, const uint32_t *eoff, const vkb_paint *paints, int4 *hdr,
                         uint32_t *tile_first, uint32_t *tile_end, cudaStream_t s);
@@ -144,7 +178,6 @@ struct FineArgs {
     int32_t            *winding_out; // optional: per-sample winding of the LAST draw touching each sample (parity tests), or null
     uint32_t            winding_draw; // draw index captured into winding_out
 };
-void vkb_launch_grad_prep(const vkb_gradient *grads, uint32_t n, float W, float H, float *out, cudaStream_t s);
 void vkb_launch_fine(const FineArgs &a, cudaStream_t s);
 size_t vkb_fine_wscratch_words(uint32_t samples);
 // fine kernel for batches without clip state or winding capture: 0 = chosen by tile count, 1 = block-per-tile fine_k, 2 = warp-per-tile

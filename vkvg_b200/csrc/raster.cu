@@ -28,20 +28,7 @@
 
 #define VKB_EDGE_GRID (148u * 8u * 8u)  // most blocks of a per-edge / per-vertex / per-triangle kernel: eight waves of eight 256-thread blocks per SM, grid-stride beyond
 
-// ---- vertex stage: shaders/vkvg_main.vert:74-79 + viewport + 8-bit sub-pixel snap (round half up) ----
-__device__ __forceinline__ void vs_snap(const float *m, float W, float H, float x, float y, int32_t &fx, int32_t &fy) {
-    float px = m[0] * x + m[2] * y + m[4];
-    float py = m[1] * x + m[3] * y + m[5];
-    float nx = px * 2.0f / W - 1.0f;
-    float ny = py * 2.0f / H - 1.0f;
-    float wx = nx * (W * 0.5f) + (W * 0.5f);
-    float wy = ny * (H * 0.5f) + (H * 0.5f);
-    // clamp far outside the guard band so the int32 conversion is defined; such coordinates are off-surface
-    wx = fminf(fmaxf(wx, -1.0e6f), 1.0e6f);
-    wy = fminf(fmaxf(wy, -1.0e6f), 1.0e6f);
-    fx = (int32_t)floorf(wx * 256.0f + 0.5f);
-    fy = (int32_t)floorf(wy * 256.0f + 0.5f);
-}
+// (vertex stage: vs_snap in pipeline.h - the stroke emitter runs it too)
 
 __device__ __forceinline__ uint32_t find_job(const uint32_t *job_base, uint32_t n_jobs, uint32_t item) {
     uint32_t lo = 0, hi = n_jobs;
@@ -57,7 +44,6 @@ __device__ __forceinline__ uint32_t find_job(const uint32_t *job_base, uint32_t 
 // (boxes are kept as order-preserving ints so that the long sub-paths can be reduced with atomicMin / atomicMax)
 __device__ __forceinline__ int32_t f2ord(float f) { const int32_t k = __float_as_int(f); return k >= 0 ? k : k ^ 0x7FFFFFFF; }
 __device__ __forceinline__ float   ord2f(int32_t k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
-#define VKB_SP_LONG 1024  // sub-paths of more elements are reduced by sp_bounds_long_k (one thread per element) instead of by one warp
 __device__ __forceinline__ void elem_box(uint32_t h, const float *elem_data, float &x0, float &y0, float &x1, float &y1) {
     const float   *e = elem_data + (h >> VKB_EL_PAYLOAD_SHIFT);
     const uint32_t t = h & VKB_EL_TYPE_MASK;
@@ -116,11 +102,11 @@ sp_bounds_long_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *first_bl
     }
 }
 void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, uint32_t *long_blocks, uint32_t *n_long_blocks,
-                          ScanScratch &scan, int4 *sp_bbox, cudaStream_t s) {
+                          ScanScratch &scan, int4 *sp_bbox, bool any_long, cudaStream_t s) {
     if (!n_sp) return;
     sp_bounds_k<<<vkb_div_up((uint64_t)n_sp * 32, 256), 256, 0, s>>>(sps, n_sp, elem_hdr, elem_data, sp_bbox, long_blocks);
     VKB_LAUNCHED();
-    if (n_elems > VKB_SP_LONG) {   // (no sub-path can be long otherwise)
+    if (any_long && n_elems > VKB_SP_LONG) {
         vkb_exclusive_scan<uint32_t, uint32_t>(long_blocks, long_blocks, n_sp, n_long_blocks, scan, s);
         sp_bounds_long_k<<<n_elems / 256 + n_elems / VKB_SP_LONG + 1, 256, 0, s>>>(sps, n_sp, long_blocks, n_long_blocks, elem_hdr, elem_data, sp_bbox);
         VKB_LAUNCHED();
@@ -130,10 +116,8 @@ void vkb_launch_sp_bounds(const vkb_subpath *sps, uint32_t n_sp, const uint32_t 
 // sub-path is a closed curve of its own for fills and clips (and a stroke stays within its half width / miter length of the path), so
 // one whose box lies wholly above, below, left or right of the surface leaves every sample's winding as it is.  On a stripe surface
 // (multi-GPU tile rows) that removes most of the scene before anything is tessellated, snapped or binned.
-__global__ void job_counts_k(const uint32_t *job_sp, const uint32_t *job_draw, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
-                             const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
+__device__ __forceinline__ void job_count_one(uint32_t j, const uint32_t *job_sp, const uint32_t *job_draw, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
+                                              const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, const SurfaceDesc &sd, uint32_t *job_n) {
     const uint32_t s = job_sp[j];
     uint32_t       n = sp_count[s];
     if (n < min_points) n = 0;
@@ -161,6 +145,25 @@ __global__ void job_counts_k(const uint32_t *job_sp, const uint32_t *job_draw, u
         if (yhi + ext < 0.0f || ylo - ext > (float)sd.height || xhi + ext < 0.0f || xlo - ext > (float)sd.width) n = 0;
     }
     job_n[j] = n;
+}
+__global__ void job_counts_k(const uint32_t *job_sp, const uint32_t *job_draw, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
+                             const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_jobs) job_count_one(j, job_sp, job_draw, sp_count, min_points, sp_bbox, draws, xforms, strokes, sd, job_n);
+}
+// both job tables of a batch that fills AND strokes (a tiger): threads [0, nf) size the fill jobs (> 2 points), the next ns the stroke jobs (>= 2)
+__global__ void job_counts2_k(const uint32_t *fjob_sp, const uint32_t *fjob_draw, uint32_t nf, uint32_t *fjob_n, const uint32_t *sjob_sp, const uint32_t *sjob_draw, uint32_t ns,
+                              uint32_t *sjob_n, const uint32_t *sp_count, const int4 *sp_bbox, const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes,
+                              SurfaceDesc sd) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nf) job_count_one(j, fjob_sp, fjob_draw, sp_count, 3, sp_bbox, draws, xforms, strokes, sd, fjob_n);
+    else if (j - nf < ns) job_count_one(j - nf, sjob_sp, sjob_draw, sp_count, 2, sp_bbox, draws, xforms, strokes, sd, sjob_n);
+}
+void vkb_launch_job_counts2(const uint32_t *fjob_sp, const uint32_t *fjob_draw, uint32_t nf, uint32_t *fjob_n, const uint32_t *sjob_sp, const uint32_t *sjob_draw, uint32_t ns,
+                            uint32_t *sjob_n, const uint32_t *sp_count, const int4 *sp_bbox, const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes,
+                            SurfaceDesc sd, cudaStream_t s) {
+    job_counts2_k<<<vkb_div_up((uint64_t)nf + ns, 256), 256, 0, s>>>(fjob_sp, fjob_draw, nf, fjob_n, sjob_sp, sjob_draw, ns, sjob_n, sp_count, sp_bbox, draws, xforms, strokes, sd);
+    VKB_LAUNCHED();
 }
 void vkb_launch_job_counts(const uint32_t *job_sp, const uint32_t *job_draw, uint32_t n_jobs, const uint32_t *sp_count, uint32_t min_points, const int4 *sp_bbox,
                            const vkb_draw *draws, const vkb_xform *xforms, const vkb_stroke *strokes, SurfaceDesc sd, uint32_t *job_n, cudaStream_t s) {
@@ -588,6 +591,89 @@ tri_edges_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, cons
         bbox_accumulate(bbox, d, box);
     }
 }
+// The same kernel with the neighbours taken from the neighbouring LANES: lane L holds triangle t, so the index triples of t +- 1, t +- 2 and
+// the orientation of t +- 1 are already in the registers of lanes L +- 1, L +- 2 - five shuffles instead of twelve index loads, six vertex
+// gathers and two 64-bit cross products per triangle.  Only the two lanes at either end of the warp (and the last triangles of the list)
+// load what lies outside it.  Identical output, edge for edge (the order in which warps reserve room aside).
+__global__ void __launch_bounds__(256)
+tri_edges_warp_k(const int2 *snapped, const uint32_t *inds, const vkb_counts *C, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item,
+                 uint32_t n_sdraws, const unsigned long long *item_offsets, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
+                 SurfaceDesc sd, int32_t *bbox) {
+    if (C->overflow) return;
+    const uint32_t n_tris = C->n[VKC_TRIS], n_verts = C->n[VKC_VERTS], lane = threadIdx.x & 31u;
+    edges += C->n[VKC_FEDGES] + n_extra; edge_draw += C->n[VKC_FEDGES] + n_extra;
+    for (uint32_t wb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < n_tris; wb += gridDim.x * blockDim.x) {
+        uint32_t   t = wb + lane;
+        const bool in_range = t < n_tris;
+        if (!in_range) t = n_tris - 1;
+        uint32_t i0[3];
+        tri_idx(inds, n_tris, (long long)t, i0);
+        int32_t   x[3], y[3], nx[3], ny[3];
+        const int sg_own = tri_sign(snapped, n_verts, i0, x, y);   // (what the neighbours ask for: before the off-surface test below)
+        int       sg = sg_own;
+        if (sg != 0 && (max(max(y[0], y[1]), y[2]) < 0 || min(min(y[0], y[1]), y[2]) > (int32_t)sd.height * 256 ||
+                        min(min(x[0], x[1]), x[2]) > (int32_t)sd.width * 256))
+            sg = 0;
+        uint32_t ip1[3], ip2[3], im1[3], im2[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            ip1[k] = __shfl_down_sync(0xffffffffu, i0[k], 1); ip2[k] = __shfl_down_sync(0xffffffffu, i0[k], 2);
+            im1[k] = __shfl_up_sync(0xffffffffu, i0[k], 1);   im2[k] = __shfl_up_sync(0xffffffffu, i0[k], 2);
+        }
+        int sg_next = __shfl_down_sync(0xffffffffu, sg_own, 1), sg_prev = __shfl_up_sync(0xffffffffu, sg_own, 1);
+        // what the lanes next door do not hold: beyond either end of the warp, or beyond the last triangle (those lanes hold a copy of it)
+        if (lane > 30u || t + 1 >= n_tris) { tri_idx(inds, n_tris, (long long)t + 1, ip1); sg_next = 2; }
+        if (lane > 29u || t + 2 >= n_tris) tri_idx(inds, n_tris, (long long)t + 2, ip2);
+        if (lane < 1u) { tri_idx(inds, n_tris, (long long)t - 1, im1); sg_prev = 2; }
+        if (lane < 2u) tri_idx(inds, n_tris, (long long)t - 2, im2);
+        vkb_edge e[3];
+        uint32_t d = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) e[k] = vkb_edge{0, 0, 0, 0};
+        if (sg != 0) {
+            uint32_t lo = 0, hi = n_sdraws;  // stroke draw owning index 3t: last q whose first item's index offset <= 3t
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if ((uint32_t)(item_offsets[sdraw_first_item[mid]] >> 32) <= 3 * t) lo = mid; else hi = mid;
+            }
+            d = sdraw_id[lo];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int ka = sg > 0 ? k : (3 - k) % 3, kb = sg > 0 ? (k + 1) % 3 : (5 - k) % 3;
+                const uint32_t u = i0[ka], v = i0[kb];
+                bool           drop = false;
+                if (tri_has(ip1, u, v)) {
+                    if (!tri_has(im1, u, v) && !tri_has(ip2, u, v)) {
+                        if (sg_next == 2) sg_next = tri_sign(snapped, n_verts, ip1, nx, ny);
+                        drop = sg_next != 0 && tri_dir(ip1, u, v) * sg_next < 0;
+                    }
+                } else if (tri_has(im1, u, v)) {
+                    if (!tri_has(im2, u, v)) {
+                        if (sg_prev == 2) sg_prev = tri_sign(snapped, n_verts, im1, nx, ny);
+                        drop = sg_prev != 0 && tri_dir(im1, u, v) * sg_prev < 0;
+                    }
+                }
+                if (!drop) e[k] = vkb_edge{x[ka], y[ka], x[kb], y[kb]};
+            }
+        }
+        bool     keep[3];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            keep[k] = in_range && !(e[k].x0 == e[k].x1 && e[k].y0 == e[k].y1) && !edge_off_surface(e[k], sd);
+            cnt += keep[k] ? 1u : 0u;
+        }
+        const uint32_t incl = warp_incl_scan(cnt);
+        uint32_t       base = 0;
+        if (lane == 31 && incl) base = atomicAdd(live, incl);
+        uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        BoxAcc box;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (keep[k]) { edges[pos] = e[k]; edge_draw[pos] = d; pos++; box.add(e[k]); }
+        bbox_accumulate(bbox, d, box);
+    }
+}
 // the stroke edges that survived are only counted by tri_edges_k: C->n[VKC_EDGES] (so far the upper bound fill + 3 x triangles +
 // rectangles, which sized the buffers) becomes the number actually stored
 __global__ void commit_live_edges_k(vkb_counts *C, const uint32_t *live, uint32_t n_extra) {
@@ -597,14 +683,19 @@ __global__ void commit_live_edges_k(vkb_counts *C, const uint32_t *live, uint32_
 void vkb_launch_tri_edges(const float2 *verts, uint32_t cap_verts, int2 *snapped, const uint32_t *inds, uint32_t cap_tris, const vkb_counts *C,
                           const vkb_draw *draws, const vkb_xform *xforms, const uint32_t *sdraw_id, const uint32_t *sdraw_first_item, uint32_t n_sdraws,
                           const unsigned long long *item_offsets, SurfaceDesc sd, vkb_edge *edges, uint32_t *edge_draw, uint32_t n_extra, uint32_t *live,
-                          vkb_counts *Cw, int32_t *draw_bbox, cudaStream_t s) {
+                          vkb_counts *Cw, int32_t *draw_bbox, bool commit_live, cudaStream_t s) {
     if (!cap_tris || !n_sdraws) return;
-    snap_verts_k<<<min(vkb_div_up(cap_verts, 256), VKB_EDGE_GRID), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
+    if (verts) {   // (null: the stroke emitter has run the vertex stage itself)
+        snap_verts_k<<<min(vkb_div_up(cap_verts, 256), VKB_EDGE_GRID), 256, 0, s>>>(verts, C, draws, xforms, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, sd, snapped);
+        VKB_LAUNCHED();
+    }
+    if (vkb_stroke_emit_mode() == 1) tri_edges_k<<<min(vkb_div_up(cap_tris, 256), VKB_EDGE_GRID), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd, draw_bbox);
+    else tri_edges_warp_k<<<min(vkb_div_up(cap_tris, 256), VKB_EDGE_GRID), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd, draw_bbox);
     VKB_LAUNCHED();
-    tri_edges_k<<<min(vkb_div_up(cap_tris, 256), VKB_EDGE_GRID), 256, 0, s>>>(snapped, inds, C, sdraw_id, sdraw_first_item, n_sdraws, item_offsets, edges, edge_draw, n_extra, live, sd, draw_bbox);
-    VKB_LAUNCHED();
-    commit_live_edges_k<<<1, 1, 0, s>>>(Cw, live, n_extra);
-    VKB_LAUNCHED();
+    if (commit_live) {   // (else vkb_launch_draw_rects does it: a frame that goes on to binning saves the launch)
+        commit_live_edges_k<<<1, 1, 0, s>>>(Cw, live, n_extra);
+        VKB_LAUNCHED();
+    }
 }
 
 // ---- per-draw bounding boxes of a RAW edge list (vkb_winding_raw; draws' own edges grow their boxes where they are emitted) ----
@@ -671,9 +762,15 @@ __device__ __forceinline__ int32_t floor_div(int32_t a, int32_t b) {  // b > 0
     return (a % b < 0) ? q - 1 : q;
 }
 // tile rectangle of each draw (clipped to the surface) and its path-tile / row counts packed as lo | hi<<32
+#define VKB_GPREP_FLOATS 16
+__device__ void grad_prep_one(const vkb_gradient *g, float W, float H, float *o);   // (with the paint evaluation, below)
+// (live != null: thread 0 first turns the number of stroke edges tri_edges_k stored into the edge count the binning kernels behind it read)
 __global__ void draw_rects_k(const int32_t *bbox, const vkb_draw *draws, const vkb_xform *xforms, uint32_t n_draws, SurfaceDesc sd, int32_t *rect,
-                             unsigned long long *counts) {
+                             unsigned long long *counts, vkb_counts *Cw, const uint32_t *live, uint32_t n_extra, GradPrep gp) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && live && !Cw->overflow) Cw->n[VKC_EDGES] = Cw->n[VKC_FEDGES] + n_extra + *live;
+    // the position-independent terms of every gradient of the batch, for the fine pass (what used to be a launch of its own)
+    for (uint32_t g = i; g < gp.n; g += gridDim.x * blockDim.x) grad_prep_one(gp.grads + g, gp.W, gp.H, gp.out + (size_t)g * VKB_GPREP_FLOATS);
     if (i >= n_draws) return;
     int32_t mnx = bbox[4 * i], mny = bbox[4 * i + 1], mxx = bbox[4 * i + 2], mxy = bbox[4 * i + 3];
     int32_t tx0 = 0, ty0 = 0, tw = 0, th = 0;
@@ -699,19 +796,24 @@ __global__ void draw_rects_k(const int32_t *bbox, const vkb_draw *draws, const v
     counts[i] = (unsigned long long)((uint32_t)(tw * th)) | ((unsigned long long)(uint32_t)th << 32);
 }
 void vkb_launch_draw_rects(const int32_t *draw_bbox, const vkb_draw *draws, const vkb_xform *xforms, uint32_t n_draws, SurfaceDesc sd, int32_t *draw_rect,
-                           unsigned long long *tile_row_counts, cudaStream_t s) {
-    draw_rects_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, draws, xforms, n_draws, sd, draw_rect, tile_row_counts);
+                           unsigned long long *tile_row_counts, vkb_counts *Cw, const uint32_t *live, uint32_t n_extra, const GradPrep &gp, cudaStream_t s) {
+    draw_rects_k<<<vkb_div_up(n_draws, 256), 256, 0, s>>>(draw_bbox, draws, xforms, n_draws, sd, draw_rect, tile_row_counts, Cw, live, n_extra, gp);
     VKB_LAUNCHED();
 }
-__global__ void split_bases_k(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi) {
+// (thread 0 also commits the totals of the scan - path-tiles and path-tile rows - as checked counts: one launch less per frame)
+__global__ void split_bases_k(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, vkb_counts *C, const unsigned long long *total) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && C && !C->overflow) {
+        vkc_commit(C, VKC_PT, (uint32_t)(*total & 0xffffffffull));
+        vkc_commit(C, VKC_ROWS, (uint32_t)(*total >> 32));
+    }
     if (i >= n) return;
     lo[i] = (uint32_t)(packed[i] & 0xffffffffull);
     hi[i] = (uint32_t)(packed[i] >> 32);
 }
-void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, cudaStream_t s) {
+void vkb_launch_split_bases(const unsigned long long *packed, uint32_t n, uint32_t *lo, uint32_t *hi, vkb_counts *C, const unsigned long long *total, cudaStream_t s) {
     if (!n) return;
-    split_bases_k<<<vkb_div_up(n, 256), 256, 0, s>>>(packed, n, lo, hi);
+    split_bases_k<<<vkb_div_up(n, 256), 256, 0, s>>>(packed, n, lo, hi, C, total);
     VKB_LAUNCHED();
 }
 
@@ -814,16 +916,35 @@ void vkb_launch_bin_count(const vkb_edge *edges, const uint32_t *edge_draw, uint
     bin_count_long_k<<<148 * 2, 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_count, pt_backdrop, long_list, long_n);
     VKB_LAUNCHED();
 }
+// the first main_blocks blocks stride the live edges, one thread per edge; the blocks behind them walk the long list bin_count_k made, one warp
+// per edge (one launch for both: the list is complete before this kernel starts)
 __global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
                                                     const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor,
-                                                    vkb_edge *tile_edges) {
+                                                    vkb_edge *tile_edges, const uint32_t *long_list, const uint32_t *long_n, uint32_t main_blocks) {
     if (C->overflow) return;
-    const uint32_t n = C->n[VKC_EDGES], stride = gridDim.x * blockDim.x;
+    if (blockIdx.x >= main_blocks) {
+        const uint32_t n = *long_n, lane = threadIdx.x & 31, warps = ((gridDim.x - main_blocks) * blockDim.x) >> 5;
+        for (uint32_t k = ((blockIdx.x - main_blocks) * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+            const uint32_t i = long_list[k], d = edge_draw[i];
+            const vkb_edge e = edges[i];
+            const bool     sh = edge_is_shallow(e);
+            for_each_tile_of_edge(
+                e, draw_rect + 4 * d,
+                [&](uint32_t pt) {
+                    uint32_t p   = pt_slot[pt];
+                    uint32_t pos = eoff[p] + atomicAdd(&cursor[p], 1u);
+                    tile_edges[pos] = e;
+                },
+                false, nullptr, draw_ptbase[d], sh ? 0 : (int32_t)lane, sh ? 1 : 32, sh ? (int32_t)lane : 0, sh ? 32 : 1);
+        }
+        return;
+    }
+    const uint32_t n = C->n[VKC_EDGES], stride = main_blocks * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         vkb_edge e = edges[i];
         if (edge_degenerate(e)) continue;
         uint32_t d = edge_draw[i];
-        if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) continue;  // on the long list, see bin_scatter_long_k
+        if (edge_tile_span(e, draw_rect + 4 * d) > VKB_LONG_EDGE) continue;  // on the long list
         for_each_tile_of_edge(
             e, draw_rect + 4 * d,
             [&](uint32_t pt) {
@@ -834,51 +955,33 @@ __global__ void __launch_bounds__(256) bin_scatter_k(const vkb_edge *edges, cons
             false, nullptr, draw_ptbase[d]);
     }
 }
-__global__ void __launch_bounds__(256) bin_scatter_long_k(const vkb_edge *edges, const uint32_t *edge_draw, const vkb_counts *C, const int32_t *draw_rect,
-                                                         const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor,
-                                                         vkb_edge *tile_edges, const uint32_t *long_list, const uint32_t *long_n) {
-    if (C->overflow) return;
-    const uint32_t n = *long_n, lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
-        const uint32_t i = long_list[k], d = edge_draw[i];
-        const vkb_edge e = edges[i];
-        const bool     sh = edge_is_shallow(e);
-        for_each_tile_of_edge(
-            e, draw_rect + 4 * d,
-            [&](uint32_t pt) {
-                uint32_t p   = pt_slot[pt];
-                uint32_t pos = eoff[p] + atomicAdd(&cursor[p], 1u);
-                tile_edges[pos] = e;
-            },
-            false, nullptr, draw_ptbase[d], sh ? 0 : (int32_t)lane, sh ? 1 : 32, sh ? (int32_t)lane : 0, sh ? 32 : 1);
-    }
-}
 void vkb_launch_bin_scatter(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, const int32_t *draw_rect,
                             const uint32_t *draw_ptbase, const uint32_t *pt_slot, const uint32_t *eoff, uint32_t *cursor, vkb_edge *tile_edges,
                             const uint32_t *long_list, const uint32_t *long_n, cudaStream_t s) {
     if (!cap_edges) return;
-    bin_scatter_k<<<min(vkb_div_up(cap_edges, 256), VKB_EDGE_GRID), 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges);
-    VKB_LAUNCHED();
-    bin_scatter_long_k<<<148 * 2, 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges, long_list, long_n);
+    const uint32_t main_blocks = min(vkb_div_up(cap_edges, 256), VKB_EDGE_GRID);
+    bin_scatter_k<<<main_blocks + 148 * 2, 256, 0, s>>>(edges, edge_draw, C, draw_rect, draw_ptbase, pt_slot, eoff, cursor, tile_edges, long_list, long_n, main_blocks);
     VKB_LAUNCHED();
 }
 
 // ---- which draw owns a path-tile / a path-tile row: written once per draw (one warp each) so that the per-path-tile and
 //      per-row kernels below read one word instead of binary-searching the draw table ----
 __global__ void __launch_bounds__(256) owners_k(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws,
-                                               const vkb_counts *C, uint32_t *pt_owner, uint32_t *row_owner) {
+                                               const vkb_counts *C, uint32_t *pt_owner, uint32_t *row_owner, uint32_t *pt_count, int32_t *pt_backdrop) {
     if (C->overflow) return;
     const uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (d >= n_draws) return;
     const uint32_t tw = (uint32_t)draw_rect[4 * d + 2], th = (uint32_t)draw_rect[4 * d + 3];
-    uint32_t *po = pt_owner + draw_ptbase[d], *ro = row_owner + draw_rowbase[d];
-    for (uint32_t k = lane; k < tw * th; k += 32) po[k] = d;
+    const uint32_t base = draw_ptbase[d];
+    uint32_t *po = pt_owner + base, *ro = row_owner + draw_rowbase[d];
+    // (the path-tiles of the draws tile [0, C->n[VKC_PT]) exactly: what bin_count_k adds to starts from zero without a memset of the capacity)
+    for (uint32_t k = lane; k < tw * th; k += 32) { po[k] = d; pt_count[base + k] = 0u; pt_backdrop[base + k] = 0; }
     for (uint32_t k = lane; k < th; k += 32) ro[k] = d;
 }
 void vkb_launch_owners(const int32_t *draw_rect, const uint32_t *draw_ptbase, const uint32_t *draw_rowbase, uint32_t n_draws, const vkb_counts *C,
-                       uint32_t *pt_owner, uint32_t *row_owner, cudaStream_t s) {
+                       uint32_t *pt_owner, uint32_t *row_owner, uint32_t *pt_count, int32_t *pt_backdrop, cudaStream_t s) {
     if (!n_draws) return;
-    owners_k<<<vkb_div_up((uint64_t)n_draws * 32, 256), 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, n_draws, C, pt_owner, row_owner);
+    owners_k<<<vkb_div_up((uint64_t)n_draws * 32, 256), 256, 0, s>>>(draw_rect, draw_ptbase, draw_rowbase, n_draws, C, pt_owner, row_owner, pt_count, pt_backdrop);
     VKB_LAUNCHED();
 }
 
@@ -949,17 +1052,27 @@ void vkb_launch_pt_compact(const uint32_t *flags, const uint32_t *flag_scan, uin
     pt_compact_k<<<vkb_div_up(cap_pt, 256), 256, 0, s>>>(flags, flag_scan, C, draw_rect, draw_ptbase, pt_owner, sd, keys, vals, pt_draw);
     VKB_LAUNCHED();
 }
-__global__ void sorted_counts_k(const uint32_t *vals, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot) {
+// Also zeroes what the kernels behind it start from - the scatter cursor of every non-empty path-tile, the list bounds of every tile
+// (headers_k only writes the tiles that have a list) and, when the frame starts from a cleared surface, the per-tile multisample flags
+// (tile_ms_words: the flags as 32-bit words, or null) - in place of four memsets of whole capacities.
+__global__ void sorted_counts_k(const uint32_t *vals, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot, uint32_t *cursor,
+                                uint32_t *tile_first, uint32_t *tile_end, uint32_t n_tiles, uint32_t *tile_ms_words) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t t = p; t < n_tiles; t += gridDim.x * blockDim.x) {   // (whatever became of the counts: a freshly allocated flag plane is zeroed by the attempt that allocated it)
+        tile_first[t] = 0u; tile_end[t] = 0u;
+        if (tile_ms_words && t < (n_tiles + 3) / 4) tile_ms_words[t] = 0u;
+    }
     if (C->overflow || p >= C->n[VKC_NE]) return;
     uint32_t pt   = vals[p];
     sorted_cnt[p] = pt_count[pt];
     pt_slot[pt]   = p;
+    cursor[p]     = 0u;
 }
 void vkb_launch_sorted_counts(const uint32_t *vals, uint32_t cap_ne, const vkb_counts *C, const uint32_t *pt_count, uint32_t *sorted_cnt, uint32_t *pt_slot,
-                              cudaStream_t s) {
+                              uint32_t *cursor, uint32_t *tile_first, uint32_t *tile_end, uint32_t n_tiles, uint32_t *tile_ms_words, cudaStream_t s) {
     if (!cap_ne) return;
-    sorted_counts_k<<<vkb_div_up(cap_ne, 256), 256, 0, s>>>(vals, C, pt_count, sorted_cnt, pt_slot);
+    // (a few path-tiles on a large surface: enough blocks for the zeroing loop as well)
+    sorted_counts_k<<<max(vkb_div_up(cap_ne, 256), min(vkb_div_up(n_tiles, 256), 148u * 8u)), 256, 0, s>>>(vals, C, pt_count, sorted_cnt, pt_slot, cursor, tile_first, tile_end, n_tiles, tile_ms_words);
     VKB_LAUNCHED();
 }
 // pt_draw_by_flagpos: draw of the path-tile at compaction position flag_scan[pt] (pt_compact_k output)
@@ -1018,14 +1131,9 @@ __device__ __forceinline__ void mix4(float *c, const float *b, float t) {
 }
 // shaders/vkvg_main.frag:68-157 (SOLID / LINEAR / RADIAL) at the pixel centre; identical arithmetic to
 // oracle/vkvg_oracle.c: eval_paint.  Everything the shader derives from the gradient record alone (normalised control
-// points, axis direction, line slope ...) is evaluated once per gradient by grad_prep_k with the same float operations in
+// points, axis direction, line slope ...) is evaluated once per gradient by grad_prep_one (run by draw_rects_k) with the same float operations in
 // the same order, so a pixel only pays for what depends on its position.
-#define VKB_GPREP_FLOATS 16
-__global__ void grad_prep_k(const vkb_gradient *grads, uint32_t n, float W, float H, float *out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const vkb_gradient *g = grads + i;
-    float *o = out + (size_t)i * VKB_GPREP_FLOATS;
+__device__ void grad_prep_one(const vkb_gradient *g, float W, float H, float *o) {
     {   // linear (frag :84-107)
         float p0x = g->cp[0][0] / W, p0y = g->cp[0][1] / H;
         float p1x = g->cp[0][2] / W, p1y = g->cp[0][3] / H;
@@ -1043,11 +1151,6 @@ __global__ void grad_prep_k(const vkb_gradient *grads, uint32_t n, float W, floa
         float dfx = c0x - c1x, dfy = c0y - c1y;
         o[8] = c0x; o[9] = c0y; o[10] = r0; o[11] = dfx; o[12] = dfy; o[13] = (dfx * dfx + dfy * dfy) - r1 * r1;
     }
-}
-void vkb_launch_grad_prep(const vkb_gradient *grads, uint32_t n, float W, float H, float *out, cudaStream_t s) {
-    if (!n) return;
-    grad_prep_k<<<vkb_div_up(n, 128), 128, 0, s>>>(grads, n, W, H, out);
-    VKB_LAUNCHED();
 }
 // px, py: the pixel centre divided by the surface size (gl_FragCoord.xy / size in the shader): fx / W, fy / H
 __device__ __noinline__ void eval_gradient(uint32_t pattern, const vkb_gradient *g, const float *gp, float px, float py, float c[4]) {

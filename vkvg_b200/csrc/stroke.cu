@@ -11,6 +11,7 @@
 // double-precision prefix scan of the float segment lengths instead of a carried float.
 #include "pipeline.h"
 #include <float.h>
+#include <string.h>
 
 #define PIF 3.14159265358979323846f
 #define PIF_2 1.57079632679489661923f
@@ -29,21 +30,39 @@ __device__ __forceinline__ float v2len(v2 a) { return sqrtf(a.x * a.x + a.y * a.
 __device__ __forceinline__ v2    v2norm(v2 a) { float m = sqrtf(a.x * a.x + a.y * a.y); return mk(a.x / m, a.y / m); }
 __device__ __forceinline__ v2    ld(const float2 *p, uint32_t i) { float2 f = p[i]; return mk(f.x, f.y); }
 
-template <bool EMIT> struct Out {
+// MODE 0: count only.  MODE 1: float vertices + indices straight to global memory (the first emitter, kept as VKVG_B200_STROKE=legacy).
+// MODE 2: every vertex also goes through the vertex stage here (vs_snap: what the rasteriser reads are the snapped integers) and vertices and
+// indices are written wherever sn / idx point - global memory, or the block's staging area in shared memory, which holds the contiguous
+// output range of the block's 128 items from the 16-byte aligned global positions voff / ioff on (stroke_emit_k).
+template <int MODE> struct Out {
     float2  *v;
     uint32_t *idx;
     uint32_t vbase, ibase;  // absolute offsets of this item
     uint32_t nv, ni;
+    int2    *sn;
+    uint32_t voff, ioff;
+    float    m[6], W, H;
+    int32_t  yoff;
     __device__ __forceinline__ uint32_t cur() const { return vbase + nv; }  // == reference's (vertCount - curVertOffset)
     __device__ __forceinline__ void     vert(v2 p) {
-        if (EMIT) v[vbase + nv] = make_float2(p.x, p.y);
+        if (MODE == 1) v[vbase + nv] = make_float2(p.x, p.y);
+        if (MODE == 2) {
+            if (v) v[vbase + nv] = make_float2(p.x, p.y);  // (geometry captures)
+            int32_t x, y;
+            vs_snap(m, W, H, p.x, p.y, x, y);
+            sn[vbase + nv - voff] = make_int2(x, y + yoff);
+        }
         nv++;
     }
     __device__ __forceinline__ void tri(uint32_t a, uint32_t b, uint32_t c) {
-        if (EMIT) {
+        if (MODE == 1) {
             idx[ibase + ni]     = a;
             idx[ibase + ni + 1] = b;
             idx[ibase + ni + 2] = c;
+        }
+        if (MODE == 2) {
+            uint32_t *t = idx + (ibase + ni - ioff);
+            t[0] = a; t[1] = b; t[2] = c;
         }
         ni += 3;
     }
@@ -59,7 +78,7 @@ struct StrokeParams {
 };
 
 // one join, internal.c:924-1163.  Returns the reference's `inverse` flag.
-template <bool EMIT> __device__ bool build_join(Out<EMIT> &o, const StrokeParams &sp, v2 pL, v2 p0, v2 pR, bool isCurve) {
+template <int MODE> __device__ bool build_join(Out<MODE> &o, const StrokeParams &sp, v2 pL, v2 p0, v2 pR, bool isCurve) {
     v2    v0 = v2sub(p0, pL), v1 = v2sub(pR, p0);
     float length_v0 = v2len(v0), length_v1 = v2len(v1);
     if (length_v0 < FLT_EPSILON || length_v1 < FLT_EPSILON) return false;
@@ -178,7 +197,7 @@ template <bool EMIT> __device__ bool build_join(Out<EMIT> &o, const StrokeParams
 }
 
 // caps, internal.c:1165-1239
-template <bool EMIT> __device__ void draw_cap(Out<EMIT> &o, const StrokeParams &sp, v2 p0, v2 n, bool isStart) {
+template <int MODE> __device__ void draw_cap(Out<MODE> &o, const StrokeParams &sp, v2 p0, v2 n, bool isStart) {
     uint32_t firstIdx = o.cur();
     if (isStart) {
         v2 vhw = v2mul(n, sp.hw);
@@ -248,95 +267,181 @@ struct StrokeJob {
     uint32_t item_base;                           // first work item (== point) of this job in the global item space
 };
 
-template <bool EMIT>
+// what every stroke kernel needs to find an item's job, sub-path and stroke state
+struct ItemArgs {
+    const float2      *pts;
+    const uint8_t     *ptflags;
+    const vkb_draw    *draws;
+    const vkb_stroke  *strokes;
+    const float       *dash_table;
+    const uint32_t    *job_draw, *job_sp, *job_base;
+    uint32_t           n_jobs;
+    const uint32_t    *sp_first, *sp_count;
+    const vkb_subpath *sps;
+    const double      *cum;
+};
+static ItemArgs item_args(const StrokeArgs &a) {
+    return ItemArgs{a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs, a.sp_first, a.sp_count, a.sps, a.cum};
+}
+__device__ __forceinline__ uint32_t item_job(const ItemArgs &a, uint32_t item) {  // last j with job_base[j] <= item
+    uint32_t lo = 0, hi = a.n_jobs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a.job_base[mid] <= item) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// one work item = one point of a stroked sub-path (job j): its join or cap, or - dashed - its segment with the dash caps that fall on it.
+// The same code counts (MODE 0) and emits, so the offsets the scan made of the counts are exactly where the emitting pass writes.
+template <int MODE>
+__device__ __forceinline__ void stroke_item(const ItemArgs &a, uint32_t item, uint32_t j, Out<MODE> &o, uint32_t *job_inverse) {
+    const uint32_t k = item - a.job_base[j];
+    const uint32_t s = a.job_sp[j];
+    const uint32_t first = a.sp_first[s], n = a.sp_count[s];
+    const bool     closed = a.sps[s].flags & VKB_SP_CLOSED;
+    const vkb_stroke &d = a.strokes[a.draws[a.job_draw[j]].xform_stroke >> 16];
+    StrokeParams   sp = {d.hw, d.lhMax, d.arcStep, d.join, d.cap};
+    const uint8_t *ptflags = a.ptflags;
+    const float2  *P = a.pts + first;
+    if (n < 2) return;
+    if (d.dash_count == 0) {
+        if (closed) {
+            // join at every point; the one at the last point closes the loop (vkvg_context.c:917-932)
+            uint32_t iL = k == 0 ? n - 1 : k - 1, iR = k == n - 1 ? 0 : k + 1;
+            bool     inv = build_join(o, sp, ld(P, iL), ld(P, k), ld(P, iR), k == n - 1 ? false : (ptflags[first + k] != 0));
+            if (MODE && k == n - 1) job_inverse[j] = inv;
+        } else if (k == 0) {
+            draw_cap(o, sp, ld(P, 0), v2norm(v2sub(ld(P, 1), ld(P, 0))), true);  // vkvg_context.c:871-873
+        } else if (k == n - 1) {
+            draw_cap(o, sp, ld(P, k), v2norm(v2sub(ld(P, k), ld(P, k - 1))), false);  // :934-935
+        } else {
+            build_join(o, sp, ld(P, k - 1), ld(P, k), ld(P, k + 1), ptflags[first + k] != 0);
+        }
+    } else {
+        // dashed: item k owns segment k -> k+1 (the closing segment for k == n-1 of a closed path) and,
+        // if it is the last segment, the tail cap (vkvg_context.c:898-916)
+        DashPat dp;
+        dp.n      = (int)d.dash_count;
+        dp.pre[0] = 0.0;
+        for (int i = 0; i < dp.n; i++) {
+            dp.d[i]       = a.dash_table[d.dash_first + i];
+            dp.pre[i + 1] = dp.pre[i] + (double)dp.d[i];
+        }
+        float totf = 0.f;
+        for (int i = 0; i < dp.n; i++) totf += dp.d[i];  // float accumulation as the reference, :858-859
+        dp.off0 = (double)fmodf(d.dash_offset, totf);
+        const double   c0       = a.cum[a.job_base[j]];
+        const bool     has_seg  = (k + 1 < n) || closed;
+        const uint32_t last_seg = closed ? n - 1 : n - 2;
+        if (has_seg) {
+            const double ck = a.cum[item] - c0, ck1 = a.cum[item + 1] - c0;
+            long long    m0 = k == 0 ? 0 : dash_count_before(dp, ck);
+            long long    m1 = dash_count_before(dp, ck1);
+            uint32_t     iL = k == 0 ? n - 1 : k - 1, iR = k == n - 1 ? 0 : k + 1;  // str.iL = lastPathPointIdx, :867
+            v2           p = ld(P, k), pR = ld(P, iR);
+            if (m0 & 1)  // inside a dash at the segment start: !dashOn, internal.c:1245
+                build_join(o, sp, ld(P, iL), p, pR, k == n - 1 ? false : (ptflags[first + k] != 0));
+            v2 dvec = v2sub(pR, p);
+            v2 nrm  = v2norm(dvec);
+            for (long long m = m0; m < m1; m++) {
+                float off = (float)(dash_boundary_pos(dp, m) - ck);
+                draw_cap(o, sp, v2add(p, v2mul(nrm, off)), nrm, (m & 1) == 0);
+            }
+            if (k == last_seg && (m1 & 1)) {
+                int   cur  = (int)(m1 % dp.n);
+                int   prev = cur - 1 < 0 ? dp.n - 1 : cur - 1;  // the reference reads dashes[-1] here for odd counts (UB)
+                float curOff = (float)(dash_boundary_pos(dp, m1) - ck1);
+                float mlen   = fminf(dp.d[prev] - curOff, dp.d[cur]);
+                draw_cap(o, sp, v2sub(pR, v2mul(nrm, mlen)), nrm, false);
+            }
+        }
+    }
+}
+
+// counting pass (MODE 0) and the first emitter (MODE 1: one thread writes its item's vertices and indices straight to global memory)
+template <int MODE>
 __global__ void __launch_bounds__(128)
-stroke_items_k(const float2 *pts, const uint8_t *ptflags, const vkb_draw *draws, const vkb_stroke *strokes, const float *dash_table, const uint32_t *job_draw,
-               const uint32_t *job_sp, const uint32_t *job_base, uint32_t n_jobs, const uint32_t *sp_first, const uint32_t *sp_count,
-               const vkb_subpath *sps, const double *cum, const vkb_counts *C, unsigned long long *counts, const unsigned long long *offsets,
-               float2 *verts, uint32_t *inds, uint32_t *job_inverse) {
+stroke_items_k(ItemArgs a, const vkb_counts *C, unsigned long long *counts, const unsigned long long *offsets, float2 *verts, uint32_t *inds, uint32_t *job_inverse) {
     if (C->overflow) return;
     const uint32_t n_items = C->n[VKC_SITEMS];
     // grid-stride over the LIVE items: the grid is sized from the capacity of the item space (a guess for the first flush, what earlier
     // flushes needed afterwards) and capped, see VKB_STROKE_GRID
     for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
-    // locate the job (sub-path of a stroke draw) this point belongs to: last j with job_base[j] <= item
-    uint32_t lo = 0, hi = n_jobs;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (job_base[mid] <= item) lo = mid; else hi = mid;
+        Out<MODE> o;
+        o.v = verts; o.idx = inds; o.nv = 0; o.ni = 0;
+        if (MODE) {
+            unsigned long long off = offsets[item];
+            o.vbase = (uint32_t)(off & 0xffffffffull);
+            o.ibase = (uint32_t)(off >> 32);
+        } else
+            o.vbase = o.ibase = 0;
+        stroke_item<MODE>(a, item, item_job(a, item), o, job_inverse);
+        if (!MODE) counts[item] = (unsigned long long)o.nv | ((unsigned long long)o.ni << 32);
     }
-    const uint32_t j = lo, k = item - job_base[j];
-    const uint32_t s = job_sp[j];
-    const uint32_t first = sp_first[s], n = sp_count[s];
-    const bool     closed = sps[s].flags & VKB_SP_CLOSED;
-    const vkb_stroke &d = strokes[draws[job_draw[j]].xform_stroke >> 16];
-    StrokeParams   sp = {d.hw, d.lhMax, d.arcStep, d.join, d.cap};
+}
 
-    Out<EMIT> o;
-    o.v = verts; o.idx = inds; o.nv = 0; o.ni = 0;
-    if (EMIT) {
-        unsigned long long off = offsets[item];
-        o.vbase = (uint32_t)(off & 0xffffffffull);
-        o.ibase = (uint32_t)(off >> 32);
-    } else
-        o.vbase = o.ibase = 0;
-
-    const float2 *P = pts + first;
-    if (n >= 2) {
-        if (d.dash_count == 0) {
-            if (closed) {
-                // join at every point; the one at the last point closes the loop (vkvg_context.c:917-932)
-                uint32_t iL = k == 0 ? n - 1 : k - 1, iR = k == n - 1 ? 0 : k + 1;
-                bool     inv = build_join(o, sp, ld(P, iL), ld(P, k), ld(P, iR), k == n - 1 ? false : (ptflags[first + k] != 0));
-                if (EMIT && k == n - 1) job_inverse[j] = inv;
-            } else if (k == 0) {
-                draw_cap(o, sp, ld(P, 0), v2norm(v2sub(ld(P, 1), ld(P, 0))), true);  // vkvg_context.c:871-873
-            } else if (k == n - 1) {
-                draw_cap(o, sp, ld(P, k), v2norm(v2sub(ld(P, k), ld(P, k - 1))), false);  // :934-935
-            } else {
-                build_join(o, sp, ld(P, k - 1), ld(P, k), ld(P, k + 1), ptflags[first + k] != 0);
-            }
-        } else {
-            // dashed: item k owns segment k -> k+1 (the closing segment for k == n-1 of a closed path) and,
-            // if it is the last segment, the tail cap (vkvg_context.c:898-916)
-            DashPat dp;
-            dp.n      = (int)d.dash_count;
-            dp.pre[0] = 0.0;
-            for (int i = 0; i < dp.n; i++) {
-                dp.d[i]       = dash_table[d.dash_first + i];
-                dp.pre[i + 1] = dp.pre[i] + (double)dp.d[i];
-            }
-            float totf = 0.f;
-            for (int i = 0; i < dp.n; i++) totf += dp.d[i];  // float accumulation as the reference, :858-859
-            dp.off0 = (double)fmodf(d.dash_offset, totf);
-            const double   c0       = cum[job_base[j]];
-            const bool     has_seg  = (k + 1 < n) || closed;
-            const uint32_t last_seg = closed ? n - 1 : n - 2;
-            if (has_seg) {
-                const double ck = cum[item] - c0, ck1 = cum[item + 1] - c0;
-                long long    m0 = k == 0 ? 0 : dash_count_before(dp, ck);
-                long long    m1 = dash_count_before(dp, ck1);
-                uint32_t     iL = k == 0 ? n - 1 : k - 1, iR = k == n - 1 ? 0 : k + 1;  // str.iL = lastPathPointIdx, :867
-                v2           p = ld(P, k), pR = ld(P, iR);
-                if (m0 & 1)  // inside a dash at the segment start: !dashOn, internal.c:1245
-                    build_join(o, sp, ld(P, iL), p, pR, k == n - 1 ? false : (ptflags[first + k] != 0));
-                v2 dvec = v2sub(pR, p);
-                v2 nrm  = v2norm(dvec);
-                for (long long m = m0; m < m1; m++) {
-                    float off = (float)(dash_boundary_pos(dp, m) - ck);
-                    draw_cap(o, sp, v2add(p, v2mul(nrm, off)), nrm, (m & 1) == 0);
-                }
-                if (k == last_seg && (m1 & 1)) {
-                    int   cur  = (int)(m1 % dp.n);
-                    int   prev = cur - 1 < 0 ? dp.n - 1 : cur - 1;  // the reference reads dashes[-1] here for odd counts (UB)
-                    float curOff = (float)(dash_boundary_pos(dp, m1) - ck1);
-                    float mlen   = fminf(dp.d[prev] - curOff, dp.d[cur]);
-                    draw_cap(o, sp, v2sub(pR, v2mul(nrm, mlen)), nrm, false);
-                }
-            }
+// The emitter.  A block takes 128 consecutive items; the scan made their outputs one contiguous range of the vertex array and one of the
+// index array, so the block builds both ranges in shared memory - every vertex already through the vertex stage (the float vertices are
+// only stored for geometry captures) - and then copies them out with 16-byte stores, a warp writing 512 contiguous bytes at a time,
+// instead of 128 threads each walking its own few vertices.  Slot 0 of a staging array corresponds to the 16-byte aligned global
+// element at or below the range's first one, so shared and global addresses are aligned alike.  A block whose ranges do not fit (round
+// joins of a wide stroke: a hundred vertices per item) writes straight to global memory, as does every block when direct != 0.
+#define SE_BLOCK 128
+#define SE_VERTS 1536  // snapped vertices (int2) a block can stage: 12 KB
+#define SE_INDS  4608  // indices: 18 KB
+__global__ void __launch_bounds__(SE_BLOCK)
+stroke_emit_k(ItemArgs a, const vkb_counts *C, const unsigned long long *offsets, const vkb_xform *xforms, SurfaceDesc sd, int direct, float2 *verts, int2 *snapped,
+              uint32_t *inds, uint32_t *job_inverse) {
+    if (C->overflow) return;
+    __shared__ __align__(16) int2     s_v[SE_VERTS];
+    __shared__ __align__(16) uint32_t s_i[SE_INDS];
+    const uint32_t n_items = C->n[VKC_SITEMS], tot_v = C->n[VKC_VERTS], tot_i = C->n[VKC_INDS];
+    for (uint32_t i0 = blockIdx.x * SE_BLOCK; i0 < n_items; i0 += gridDim.x * SE_BLOCK) {   // (block-uniform: the barriers below are safe)
+        const uint32_t           i1 = min(i0 + SE_BLOCK, n_items);
+        const unsigned long long o0 = offsets[i0], o1 = i1 < n_items ? offsets[i1] : ((unsigned long long)tot_v | ((unsigned long long)tot_i << 32));
+        const uint32_t v0 = (uint32_t)(o0 & 0xffffffffull), v1 = (uint32_t)(o1 & 0xffffffffull), x0 = (uint32_t)(o0 >> 32), x1 = (uint32_t)(o1 >> 32);
+        const uint32_t voff = v0 & ~1u, ioff = x0 & ~3u;
+        // (joins of two vertices and a quad - a tiger's miter joins - gain nothing from the detour and pay its two barriers)
+        const bool     staged = !direct && v1 - v0 > 3u * SE_BLOCK && v1 - voff <= SE_VERTS && x1 - ioff <= SE_INDS;
+        const uint32_t item = i0 + threadIdx.x;
+        if (item < i1) {
+            const uint32_t   j  = item_job(a, item);
+            const vkb_xform &xf = xforms[a.draws[a.job_draw[j]].xform_stroke & 0xFFFF];
+            Out<2> o;
+            o.v = verts; o.nv = 0; o.ni = 0;
+            const unsigned long long off = offsets[item];
+            o.vbase = (uint32_t)(off & 0xffffffffull);
+            o.ibase = (uint32_t)(off >> 32);
+            o.sn = staged ? s_v : snapped; o.voff = staged ? voff : 0u;
+            o.idx = staged ? s_i : inds;   o.ioff = staged ? ioff : 0u;
+#pragma unroll
+            for (int q = 0; q < 6; q++) o.m[q] = xf.mat[q];
+            o.W = (float)sd.width; o.H = (float)sd.full_height;
+            o.yoff = (int32_t)(xf.band * sd.band_tiles) * VKB_TILE_FX - (int32_t)sd.origin_y * 256;
+            stroke_item<2>(a, item, j, o, job_inverse);
         }
-    }
-    if (!EMIT) counts[item] = (unsigned long long)o.nv | ((unsigned long long)o.ni << 32);
+        if (staged) {
+            __syncthreads();
+            for (uint32_t q = threadIdx.x; 2 * q < v1 - voff; q += SE_BLOCK) {   // vertices, two to a 16-byte store
+                const uint32_t g = voff + 2 * q;
+                if (g >= v0 && g + 2 <= v1) *reinterpret_cast<int4 *>(snapped + g) = *reinterpret_cast<const int4 *>(s_v + 2 * q);
+                else {
+                    if (g >= v0 && g < v1) snapped[g] = s_v[2 * q];
+                    if (g + 1 >= v0 && g + 1 < v1) snapped[g + 1] = s_v[2 * q + 1];
+                }
+            }
+            for (uint32_t q = threadIdx.x; 4 * q < x1 - ioff; q += SE_BLOCK) {   // indices, four to a 16-byte store
+                const uint32_t g = ioff + 4 * q;
+                if (g >= x0 && g + 4 <= x1) *reinterpret_cast<uint4 *>(inds + g) = *reinterpret_cast<const uint4 *>(s_i + 4 * q);
+                else {
+#pragma unroll
+                    for (uint32_t e = 0; e < 4; e++)
+                        if (g + e >= x0 && g + e < x1) inds[g + e] = s_i[4 * q + e];
+                }
+            }
+            __syncthreads();   // (the next chunk of a grid-stride block reuses the staging area)
+        }
     }
 }
 
@@ -391,15 +496,32 @@ void vkb_launch_stroke_seglen(const StrokeArgs &a, float *seglen, cudaStream_t s
     VKB_LAUNCHED();
 }
 void vkb_launch_stroke_count(const StrokeArgs &a, unsigned long long *counts, cudaStream_t s) {
-    stroke_items_k<false><<<min(vkb_div_up(a.n_items, 128), VKB_STROKE_GRID), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
-                                                                   a.sp_first, a.sp_count, a.sps, a.cum, a.C, counts, nullptr, nullptr, nullptr, nullptr);
+    stroke_items_k<0><<<min(vkb_div_up(a.n_items, 128), VKB_STROKE_GRID), 128, 0, s>>>(item_args(a), a.C, counts, nullptr, nullptr, nullptr, nullptr);
     VKB_LAUNCHED();
 }
-void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, float2 *verts, uint32_t *inds, uint32_t *job_inverse, cudaStream_t s) {
-    stroke_items_k<true><<<min(vkb_div_up(a.n_items, 128), VKB_STROKE_GRID), 128, 0, s>>>(a.pts, a.ptflags, a.draws, a.strokes, a.dash_table, a.job_draw, a.job_sp, a.job_base, a.n_jobs,
-                                                                  a.sp_first, a.sp_count, a.sps, a.cum, a.C, nullptr, offsets, verts, inds, job_inverse);
-    VKB_LAUNCHED();
+static void launch_patch_closed(const StrokeArgs &a, const unsigned long long *offsets, uint32_t *inds, uint32_t *job_inverse, cudaStream_t s) {
     stroke_patch_closed_k<<<vkb_div_up(a.n_jobs, 128), 128, 0, s>>>(a.draws, a.strokes, a.job_draw, a.job_sp, a.job_base, a.n_jobs, a.sps, a.sp_count, offsets,
                                                                    a.C, job_inverse, inds);
     VKB_LAUNCHED();
+}
+// VKVG_B200_STROKE=legacy: the first emitter (float vertices, snapped by snap_verts_k afterwards); =direct: the fused vertex stage without the staging area
+int vkb_stroke_emit_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("VKVG_B200_STROKE");
+        mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "direct")) ? 2 : 0;
+    }
+    return mode;
+}
+void vkb_launch_stroke_emit(const StrokeArgs &a, const unsigned long long *offsets, float2 *verts, uint32_t *inds, uint32_t *job_inverse, cudaStream_t s) {
+    stroke_items_k<1><<<min(vkb_div_up(a.n_items, 128), VKB_STROKE_GRID), 128, 0, s>>>(item_args(a), a.C, nullptr, offsets, verts, inds, job_inverse);
+    VKB_LAUNCHED();
+    launch_patch_closed(a, offsets, inds, job_inverse, s);
+}
+void vkb_launch_stroke_emit_snapped(const StrokeArgs &a, const unsigned long long *offsets, const vkb_xform *xforms, const SurfaceDesc &sd, float2 *verts, int2 *snapped,
+                                    uint32_t *inds, uint32_t *job_inverse, cudaStream_t s) {
+    stroke_emit_k<<<min(vkb_div_up(a.n_items, SE_BLOCK), VKB_STROKE_GRID), SE_BLOCK, 0, s>>>(item_args(a), a.C, offsets, xforms, sd, vkb_stroke_emit_mode() == 2 ? 1 : 0, verts,
+                                                                                          snapped, inds, job_inverse);
+    VKB_LAUNCHED();
+    launch_patch_closed(a, offsets, inds, job_inverse, s);
 }
