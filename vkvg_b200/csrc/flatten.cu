@@ -81,13 +81,12 @@ __device__ __forceinline__ bool bez_leaf_test(PointSink &s, float tol, const Bez
     return false;
 }
 
-__device__ void flatten_cubic(PointSink &s, const float *e) {
+// The reference's depth-first walk, startable at any node of the subdivision tree: `pending` = right siblings that wait above the node
+// (one per left turn on the way down from the root), so that the depth limit cuts where it would in a walk from the root.
+__device__ void bez_dfs(PointSink &s, BezNode cur, unsigned level, int pending, const float tol) {
     BezNode  stack[VKB_BEZ_STACK];
     uint8_t  lvl[VKB_BEZ_STACK];
     int      sp  = 0;
-    BezNode  cur = {e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]};
-    const float tol = e[8];
-    unsigned level = 0;
     for (;;) {
         // de Casteljau midpoints, internal.c:1321-1332
         float x12 = (cur.x1 + cur.x2) / 2, y12 = (cur.y1 + cur.y2) / 2;
@@ -97,7 +96,7 @@ __device__ void flatten_cubic(PointSink &s, const float *e) {
         float x234 = (x23 + x34) / 2, y234 = (y23 + y34) / 2;
         float x1234 = (x123 + x234) / 2, y1234 = (y123 + y234) / 2;
         bool  leaf = level > 0 && bez_leaf_test(s, tol, cur, x1234, y1234);  // level 0 always subdivides
-        if (!leaf && sp < VKB_BEZ_STACK) {
+        if (!leaf && pending + sp < VKB_BEZ_STACK) {
             // right child waits on the stack, continue with the left one (internal.c:1459-1460)
             stack[sp] = BezNode{x1234, y1234, x234, y234, x34, y34, cur.x4, cur.y4};
             lvl[sp]   = (uint8_t)(level + 1);
@@ -112,7 +111,43 @@ __device__ void flatten_cubic(PointSink &s, const float *e) {
         cur   = stack[sp];
         level = lvl[sp];
     }
+}
+__device__ void flatten_cubic(PointSink &s, const float *e) {
+    bez_dfs(s, BezNode{e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]}, 0, 0, e[8]);
     s.add(e[6], e[7]);  // end point appended unconditionally, vkvg_context.c:564
+}
+
+// One lane's share of a cubic when a WARP flattens it: the subtree below the depth-5 node whose path from the root is the lane number (bit 4
+// decides first, 0 = left child), so the lanes in order are the tree in order and the curve's points are the lanes' points concatenated.
+// A node on the way down that passes the leaf test belongs to the leftmost lane below it; the other lanes below it find nothing.  Every
+// lane recomputes its up to five ancestors with the operations the serial walk performs on them: same floats, same leaf set.
+__device__ void bez_lane_walk(PointSink &s, const float *e, uint32_t lane) {
+    BezNode     cur = {e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]};
+    const float tol = e[8];
+    int         pending = 0;
+    for (int d = 0; d < 5; d++) {
+        float x12 = (cur.x1 + cur.x2) / 2, y12 = (cur.y1 + cur.y2) / 2;
+        float x23 = (cur.x2 + cur.x3) / 2, y23 = (cur.y2 + cur.y3) / 2;
+        float x34 = (cur.x3 + cur.x4) / 2, y34 = (cur.y3 + cur.y4) / 2;
+        float x123 = (x12 + x23) / 2, y123 = (y12 + y23) / 2;
+        float x234 = (x23 + x34) / 2, y234 = (y23 + y34) / 2;
+        float x1234 = (x123 + x234) / 2, y1234 = (y123 + y234) / 2;
+        if (d > 0) {  // (level 0 always subdivides)
+            float2    tmp[2];
+            PointSink t;
+            t.pts = nullptr; t.flags = nullptr; t.n = 0; t.flag = 0; t.emit = false; t.cache = tmp; t.n_cached = 0; t.cache_cap = 2;
+            if (bez_leaf_test(t, tol, cur, x1234, y1234)) {
+                if ((lane & ((1u << (5 - d)) - 1u)) == 0u) {
+                    if (t.n_cached > 0) s.add(tmp[0].x, tmp[0].y);
+                    if (t.n_cached > 1) s.add(tmp[1].x, tmp[1].y);
+                }
+                return;
+            }
+        }
+        if ((lane >> (4 - d)) & 1u) cur = BezNode{x1234, y1234, x234, y234, x34, y34, cur.x4, cur.y4};
+        else { cur = BezNode{cur.x1, cur.y1, x12, y12, x123, y123, x1234, y1234}; pending++; }
+    }
+    bez_dfs(s, cur, 5, pending, tol);
 }
 
 __device__ __forceinline__ void flatten_arc(PointSink &s, const float *e) {
@@ -159,6 +194,41 @@ __global__ void __launch_bounds__(128) flatten_k(const uint32_t *elem_hdr, const
     if (!EMIT) counts[i] = s.n - start;
 }
 
+// Counting pass for batches of few elements (a tiger frame: 2500 cubics), where the pass lasts as long as the serial walk of the frame's
+// longest curve (33 us of a 255 us frame): one WARP per element.  The lanes count their shares (bez_lane_walk), a prefix sum orders them,
+// and - when the curve fits the cache - a second walk writes every lane's points where the emitting pass expects them.  Points and arcs are
+// lane 0's, as in flatten_k.
+__global__ void __launch_bounds__(128) flatten_count_warp_k(const uint32_t *elem_hdr, const float *elem_data, uint32_t n_elems, uint32_t *counts, float2 *cache, uint32_t cache_n) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (i >= n_elems) return;  // (whole warps)
+    const uint32_t hdr = elem_hdr[i], type = hdr & VKB_EL_TYPE_MASK;
+    const float   *e   = elem_data + (hdr >> VKB_EL_PAYLOAD_SHIFT);
+    PointSink s;
+    s.pts = nullptr; s.flags = nullptr; s.n = 0; s.flag = 0; s.emit = false; s.cache = nullptr; s.n_cached = 0; s.cache_cap = 0;
+    if (type == VKB_EL_CUBIC) {
+        bez_lane_walk(s, e, lane);
+        const uint32_t n = s.n, incl = warp_incl_scan(n), total = __shfl_sync(0xffffffffu, incl, 31), off = incl - n;
+        const uint32_t end_ok = (isnan(e[6]) || isnan(e[7])) ? 0u : 1u;  // (PointSink::add drops NaN)
+        if (total + end_ok <= cache_n) {  // (a longer curve is walked again by the emitting pass: nothing of it is read from the cache)
+            float2 *c = cache + (size_t)i * cache_n;
+            if (n) {
+                PointSink w;
+                w.pts = nullptr; w.flags = nullptr; w.n = 0; w.flag = 0; w.emit = false; w.cache = c + off; w.n_cached = 0; w.cache_cap = n;
+                bez_lane_walk(w, e, lane);
+            }
+            if (lane == 31 && end_ok) c[total] = make_float2(e[6], e[7]);
+        }
+        if (lane == 0) counts[i] = total + end_ok;
+        return;
+    }
+    if (lane) return;
+    s.cache = type != VKB_EL_POINT ? cache + (size_t)i * cache_n : nullptr;
+    s.cache_cap = cache_n;
+    if (type == VKB_EL_POINT) s.add(e[0], e[1]);
+    else if (type == VKB_EL_ARC) flatten_arc(s, e);
+    counts[i] = s.n;
+}
+
 // sub-path point ranges from the element offsets: first point = offset of the first element,
 // count = offset(end) - offset(first) minus one if close_path dropped the duplicated last point
 __global__ void subpath_ranges_k(const vkb_subpath *sps, uint32_t n_sp, const uint32_t *elem_off, uint32_t n_elems, const uint32_t *total,
@@ -177,7 +247,8 @@ __global__ void subpath_ranges_k(const vkb_subpath *sps, uint32_t n_sp, const ui
 
 void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, float2 *cache, uint32_t cache_n, cudaStream_t s) {
     if (!n) return;
-    flatten_k<false><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, nullptr, nullptr, nullptr, nullptr, cache, cache_n);
+    if (cache && cache_n >= 64) flatten_count_warp_k<<<vkb_div_up((uint64_t)n * 32, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, cache, cache_n);  // (few elements: a warp each)
+    else flatten_k<false><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, nullptr, nullptr, nullptr, nullptr, cache, cache_n);
     VKB_LAUNCHED();
 }
 void vkb_launch_flatten_emit(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, const uint32_t *offsets, float2 *pts, uint8_t *flags,
