@@ -77,8 +77,11 @@ void vkb_launch_stroke_emit_snapped(const StrokeArgs &a, const unsigned long lon
 __device__ __forceinline__ void vs_snap(const float *m, float W, float H, float x, float y, int32_t &fx, int32_t &fy) {
     float px = m[0] * x + m[2] * y + m[4];
     float py = m[1] * x + m[3] * y + m[5];
-    float nx = px * 2.0f / W - 1.0f;
-    float ny = py * 2.0f / H - 1.0f;
+    // x / 2^k and x * 2^-k are the same correctly rounded value, and every surface of the benchmark configurations is a power of two wide and
+    // high: the two IEEE divisions were half of the vertex stage's instructions (ncu, profiles/r2y_stroke_c3_lines.txt)
+    const uint32_t wb = __float_as_uint(W), hb = __float_as_uint(H);
+    float nx = (wb & 0x007FFFFFu) == 0u ? px * 2.0f * __uint_as_float(0x7F000000u - wb) - 1.0f : px * 2.0f / W - 1.0f;
+    float ny = (hb & 0x007FFFFFu) == 0u ? py * 2.0f * __uint_as_float(0x7F000000u - hb) - 1.0f : py * 2.0f / H - 1.0f;
     float wx = nx * (W * 0.5f) + (W * 0.5f);
     float wy = ny * (H * 0.5f) + (H * 0.5f);
     // clamp far outside the guard band so the int32 conversion is defined; such coordinates are off-surface
