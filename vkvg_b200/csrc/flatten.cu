@@ -8,6 +8,7 @@
 //
 // Compiled with --fmad=false: every float expression is evaluated as the reference's gcc build does.
 #include "pipeline.h"
+#include <stdlib.h>
 
 #define PIF 3.14159265358979323846f
 #define TWO_OVER_PIF 0.63661977236758134308f  // the reference's M_2_PIF (2/pi), used where 2*pi was meant
@@ -247,7 +248,8 @@ __global__ void subpath_ranges_k(const vkb_subpath *sps, uint32_t n_sp, const ui
 
 void vkb_launch_flatten_count(const uint32_t *elem_hdr, const float *elem_data, uint32_t n, uint32_t *counts, float2 *cache, uint32_t cache_n, cudaStream_t s) {
     if (!n) return;
-    if (cache && cache_n >= 64) flatten_count_warp_k<<<vkb_div_up((uint64_t)n * 32, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, cache, cache_n);  // (few elements: a warp each)
+    static const bool per_thread = [] { const char *e = getenv("VKVG_B200_FLATTEN"); return e && e[0] == 't'; }();   // =thread: A/B against the kernel below
+    if (cache && cache_n >= 64 && !per_thread) flatten_count_warp_k<<<vkb_div_up((uint64_t)n * 32, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, cache, cache_n);  // (few elements: a warp each)
     else flatten_k<false><<<vkb_div_up(n, 128), 128, 0, s>>>(elem_hdr, elem_data, n, counts, nullptr, nullptr, nullptr, nullptr, cache, cache_n);
     VKB_LAUNCHED();
 }

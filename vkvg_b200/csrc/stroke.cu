@@ -9,6 +9,8 @@
 // numbering is contiguous, the reference's forward references ("closing quad of a join uses the next
 // join's first two vertices") are simply base + own_count (+1).  The dash phase comes from a
 // double-precision prefix scan of the float segment lengths instead of a carried float.
+// The emit pass (stroke_emit_k) also runs the vertex stage - what the rasteriser reads are the snapped integer vertices - and writes a
+// block's contiguous output ranges through shared memory with 16-byte stores; the float vertices exist only for geometry captures.
 #include "pipeline.h"
 #include <float.h>
 #include <string.h>
