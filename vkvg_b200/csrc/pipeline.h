@@ -124,7 +124,8 @@ struct BinBuffers {  // all device pointers
     uint32_t *draw_rowbase; // n_draws (+1): first path-tile row of the draw
 };
 // every launcher below sizes its grid for a capacity (cap_*) and reads the count from C (dev_util.cuh: vkb_counts)
-// every kernel that emits edges of a draw grows draw_bbox[draw] itself (after vkb_launch_draw_bbox_init); vkb_launch_draw_bbox is for raw edge lists
+// every kernel that emits edges of a draw grows draw_bbox[draw] itself (the boxes are emptied by the flush's counts_reset_k); vkb_launch_draw_bbox_init /
+// vkb_launch_draw_bbox are for raw edge lists
 void vkb_launch_draw_bbox_init(uint32_t n_draws, int32_t *draw_bbox, cudaStream_t s);
 void vkb_launch_draw_bbox(const vkb_edge *edges, const uint32_t *edge_draw, uint64_t cap_edges, const vkb_counts *C, uint32_t n_draws, int32_t *draw_bbox,
                           cudaStream_t s);
@@ -167,7 +168,7 @@ struct FineArgs {
     const vkb_paint    *paints;      // per draw
     const vkb_gradient *grads;
     const vkb_surfpat  *surfpats;    // surface paints of the batch
-    const float        *gprep;       // per gradient: VKB_GPREP_FLOATS position-independent terms of the paint evaluation (grad_prep_k)
+    const float        *gprep;       // per gradient: VKB_GPREP_FLOATS position-independent terms of the paint evaluation (grad_prep_one, run by draw_rects_k)
     uint32_t           *image;       // width*height premultiplied RGBA8 (resolved)
     uint32_t           *ms_image;    // per-sample colours, tile-major [tile][256][S]; valid for tiles whose tile_ms flag is set
     uint8_t            *tile_ms;     // per tile: 1 when the samples of some pixel differ (the resolved image alone would lose them)
